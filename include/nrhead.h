@@ -1,0 +1,151 @@
+/* nrhead.h — C ABI of the B200-native NeighborRetr retrieval head (libnrhead.so, sm_100a).
+ *
+ * The reference (zzezze/NeighborRetr) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary it exposes for this path is the Python module surface of NeighborRetr/models
+ * (SURVEY.md §8(b)).  Each entry point below replaces the ATen op chain of one reference
+ * function and cites it (paths relative to the reference repo).  The Python mirror of the
+ * reference interface lives in neighborretr_b200/{modeling,until_module,metrics,evaluator}.py and
+ * calls these through ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to a contiguous row-major buffer owned by the caller;
+ *    the library never allocates, frees or retains device memory;
+ *  - functions only ENQUEUE work on `stream` (a cudaStream_t passed as void*), never synchronise;
+ *  - return 0 on success, a negative code otherwise; nr_last_error() gives the message;
+ *  - masks are int64 {0,1} exactly as the reference passes them (modeling.py:486);
+ *  - "f32" = IEEE binary32, "bf16" = bfloat16, index outputs are int32 / uint8 as stated.
+ */
+#ifndef NRHEAD_H_
+#define NRHEAD_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NR_ABI_VERSION 1
+
+/* loss selection flags for nr_row_losses_* */
+#define NR_LOSS_CENTRALITY 1
+#define NR_LOSS_NEIGHBOR 2
+#define NR_LOSS_KL 4
+#define NR_LOSS_UNIFORM 8
+#define NR_NSAVE 16        /* per-row scalars kept between nr_row_losses_fwd and _bwd */
+#define NR_MAX_K 128       /* largest num_neighbors */
+#define NR_MAX_ROW_B 16384 /* largest B (columns) of a row-loss block */
+#define NR_MAX_TOKENS 128  /* largest Nt / Nv of the max-sim kernels */
+
+/* arithmetic of the token-pair contraction */
+#define NR_PREC_FP32 0 /* CUDA-core fp32 FMA: the exact mode used for fp32-tolerance parity   */
+#define NR_PREC_BF16 1 /* tcgen05 kind::f16, bf16 operands, fp32 accumulation in TMEM          */
+
+int nr_version(void);
+const char* nr_last_error(void);
+/* 1 if `nr_*` tensor-core entry points can run on the current device (compute capability 10.x) */
+int nr_device_supported(void);
+
+/* ---- token preparation: F.normalize(x, dim=-1) (modeling.py:495-496, :415-418) -------------
+ * x [rows, d] f32 -> xn_f32 [rows, d] (nullable), xn_bf16 [rows, d] (nullable),
+ * inv_norm [rows] = 1/max(||x||, 1e-12), colsum_partials [nr_prep_partials(rows), d] (nullable):
+ * per-CTA partial column sums of the normalised rows (for the centrality mean, modeling.py:419-424). */
+int64_t nr_prep_partials(int64_t rows);
+int nr_prep_tokens(const float* x, int64_t rows, int64_t d, float* xn_f32, void* xn_bf16, float* inv_norm,
+                   float* colsum_partials, void* stream);
+/* backward of the normalisation: dx = (dxn + add_vec - xn <xn, dxn + add_vec>) * inv_norm.
+ * add_vec [d] (nullable) is a gradient broadcast to every row (centrality mean path).
+ * accumulate != 0: dx += ... */
+int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* dxn, const float* add_vec,
+                       int64_t rows, int64_t d, float* dx, int accumulate, void* stream);
+
+/* ---- masked max-sim late interaction: one direction of local_level (modeling.py:499-509) ----
+ *   H[rx, ry] = sum_x wx[rx,x] * max_y ( <xn[rx,x,:], yn[ry,y,:]> * mx[rx,x] * my[ry,y] )
+ * local_level's S = 1/2 (H(text,video,text_weight) + H(video,text,video_weight)^T).
+ * xn [Rx,Nx,d], yn [Ry,Ny,d] are L2-normalised tokens (f32 for NR_PREC_FP32, bf16 for NR_PREC_BF16),
+ * wx [Rx,Nx] f32, mx [Rx,Nx] / my [Ry,Ny] int64 (nullable = all ones).
+ * out[rx*out_sr + ry*out_sc] = alpha*H (+ previous value if accumulate);  out2 likewise (nullable),
+ * so S and S^T can be produced by the same launch.
+ * pmax [Rx,Ry,Nx] f32 and ystar [Rx,Ry,Nx] u8 (both nullable) keep max / arg-max for backward. */
+int nr_maxsim_fwd(int precision, const void* xn, const void* yn, const float* wx, const int64_t* mx,
+                  const int64_t* my, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float alpha,
+                  float* out, int64_t out_sr, int64_t out_sc, float* out2, int64_t out2_sr, int64_t out2_sc,
+                  int accumulate, float* pmax, uint8_t* ystar, void* stream);
+/* backward of nr_maxsim_fwd w.r.t. the X tokens ("gather"):
+ *   dxn[rx,x,:] += mx*wx[rx,x] * sum_ry dH[rx,ry] * my[ry,y*] * yn[ry,y*,:]
+ * dH is read as dH[rx*dh_sr + ry*dh_sc] * dh_scale. */
+int nr_maxsim_bwd_x(int precision, const void* yn, const float* wx, const int64_t* mx, const int64_t* my,
+                    const uint8_t* ystar, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale,
+                    int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dxn, void* stream);
+/* ... w.r.t. the Y tokens ("scatter"):
+ *   dyn[ry,y,:] += my[ry,y] * sum_rx dH[rx,ry] * sum_{x: y*(rx,ry,x)=y} mx*wx[rx,x] * xn[rx,x,:] */
+int nr_maxsim_bwd_y(int precision, const void* xn, const float* wx, const int64_t* mx, const int64_t* my,
+                    const uint8_t* ystar, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale,
+                    int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dyn, void* stream);
+/* ... w.r.t. the token weights: dwx[rx,x] += sum_ry dH[rx,ry] * pmax[rx,ry,x] */
+int nr_maxsim_bwd_w(const float* pmax, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale, int64_t Rx,
+                    int64_t Nx, int64_t Ry, float* dwx, void* stream);
+
+/* ---- centrality weights (modeling.py:403-430) ---------------------------------------------
+ * mean_vec [d] = (sum over colsum partials) / rows_total;  g [B,d] raw global features.
+ * w[a] = exp(cs * <normalize(g_a), mean_vec>).  gn [B,d] and ginv [B] are saved for backward. */
+int nr_centrality_fwd(const float* colsum_partials, int64_t n_partials, int64_t rows_total, const float* g,
+                      int64_t B, int64_t d, float cs, float* mean_vec, float* gn, float* ginv, float* w,
+                      void* stream);
+/* dw [B] -> dg [B,d] (+= if accumulate) and dmean [d] (the vector to broadcast to every token row,
+ * already divided by rows_total). */
+int nr_centrality_bwd(const float* mean_vec, const float* gn, const float* ginv, const float* w, const float* dw,
+                      int64_t B, int64_t d, float cs, int64_t rows_total, float* dg, int accumulate,
+                      float* dmean, void* stream);
+
+/* ---- row-block losses (until_module.py:56-211, :263-291, :303-328, :339-359) ----------------
+ * X [rows,B] rows row0..row0+rows of the local similarity (t2v) or of its transpose (v2t);
+ * G likewise for the global similarity; cbank [B] bank centrality by column (until_module.py:181);
+ * w [rows]; sk_u [rows], sk_v [B] Sinkhorn duals; logit_scale: device scalar (NULL = 1).
+ * row_out [4,rows]: per-row terms {centrality, neighbour, kl, uniform} (not yet divided by B);
+ * nbr_idx [rows,k] int32: the top-k neighbour columns, descending similarity, ties -> lower column. */
+int nr_row_losses_fwd(const float* X, int64_t ldx, const float* G, int64_t ldg, const float* cbank,
+                      const float* w, const float* sk_u, const float* sk_v, int64_t rows, int64_t B,
+                      int64_t row0, const float* logit_scale, int k, float tau_nbr, float tau_uni, float beta,
+                      int flags, float* row_out, int32_t* nbr_idx, float* saved, void* stream);
+/* gscale [4] device: upstream multipliers of the four per-row terms.  Writes dX [rows,B], dG [rows,B]
+ * (nullable); accumulates dc [B] (atomic), writes dw [rows], accumulates dls [1] (atomic). */
+int nr_row_losses_bwd(const float* X, int64_t ldx, const float* G, int64_t ldg, const float* cbank,
+                      const float* w, const float* sk_u, const float* sk_v, int64_t rows, int64_t B,
+                      int64_t row0, const float* logit_scale, int k, float tau_nbr, float tau_uni, float beta,
+                      int flags, const int32_t* nbr_idx, const float* saved, const float* gscale, float* dX,
+                      int64_t lddx, float* dG, int64_t lddg, float* dc, float* dw, float* dls, void* stream);
+int nr_row_mean(const float* X, int64_t ld, int64_t rows, int64_t cols, float* out, void* stream);
+int nr_vec_sums(const float* in, int64_t nvec, int64_t len, const float* scale, float* out, void* stream);
+int nr_transpose_add(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo,
+                     int64_t rows, int64_t cols, float alpha, float beta, void* stream);
+
+/* ---- log-space Sinkhorn (until_module.py:222-251), both directions in one cooperative launch --
+ * G [B,B], GT [B,B] (= G^T, caller-provided).  Chain 1 runs on G, chain 2 on G^T; outputs the
+ * duals u1,v1,u2,v2 [B].  workspace: nr_sinkhorn_workspace_bytes(B) bytes, zero-initialised by
+ * the library on `stream`. */
+size_t nr_sinkhorn_workspace_bytes(int64_t B);
+int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
+                float* v2, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- memory-bank FIFO (modeling.py:222-249): bank = cat(new, old)[:capacity] -----------------
+ * out [cap, row_bytes] <- new [n_new, row_bytes] followed by old [n_old, row_bytes], truncated. */
+int nr_fifo_update(const void* new_rows, int64_t n_new, const void* old_rows, int64_t n_old, void* out,
+                   int64_t capacity, int64_t row_bytes, void* stream);
+
+/* ---- evaluation ranking (utils/metrics.py:38-79) ---------------------------------------------
+ * S [Q, N] (row stride lds), diag_col0: column of row q's positive is diag_col0 + q, its score is
+ * read from diag[q] if diag != NULL (sharded galleries) else from S.
+ * gt[q] += #{j : S[q,j] > s_qq},  eq[q] += #{j : S[q,j] == s_qq}   (int32, accumulate). */
+int nr_rank_count(const float* S, int64_t lds, int64_t Q, int64_t N, const float* diag, int64_t diag_col0,
+                  int32_t* gt, int32_t* eq, void* stream);
+/* per-row top-k (value desc, ties -> lower column): vals [Q,k] f32, idx [Q,k] int32 (+col_offset) */
+int nr_topk_rows(const float* S, int64_t lds, int64_t Q, int64_t N, int k, int32_t col_offset, float* vals,
+                 int32_t* idx, void* stream);
+/* merge W per-shard top-k lists [W,Q,k] into the global top-k [Q,k] (ties -> lower global column) */
+int nr_topk_merge(const float* vals, const int32_t* idx, int64_t W, int64_t Q, int k, float* out_vals,
+                  int32_t* out_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRHEAD_H_ */

@@ -1,0 +1,48 @@
+"""B200-native retrieval head for NeighborRetr.
+
+Public surface mirrors the reference's module names:
+    neighborretr_b200.modeling.NeighborRetr / HeadMixin
+    neighborretr_b200.until_module.{CentralityWeightingLoss, NeighborAdjustingLoss,
+                                    UniformRegularizationLoss, KLDivergenceLoss, AllGather, AllGather2}
+    neighborretr_b200.metrics.RetrievalMetrics.compute_metrics
+    neighborretr_b200.evaluator._run_on_single_gpu
+    neighborretr_b200.install(...)  -> rebind the above onto an imported reference checkout
+"""
+__all__ = ["install"]
+
+
+def install(reference_pkg=None):
+    """Rebind the CUDA head onto the already-importable reference package ``NeighborRetr`` so that the
+    reference's main.py / training loop run unchanged.  Returns the list of patched names."""
+    import importlib
+
+    from . import evaluator as ev
+    from . import metrics as mt
+    from . import modeling as md
+    from . import until_module as um
+
+    ref_modeling = importlib.import_module("NeighborRetr.models.modeling")
+    ref_until = importlib.import_module("NeighborRetr.models.until_module")
+    ref_metrics = importlib.import_module("NeighborRetr.utils.metrics")
+    ref_eval = importlib.import_module("NeighborRetr.training.evaluator")
+    patched = []
+    cls = ref_modeling.NeighborRetr
+    for name in ("local_level", "global_level", "get_similarity_logits", "compute_centrality_weights",
+                 "compute_centrality_loss", "compute_neighbor_loss", "compute_uniform_loss", "_compute_losses",
+                 "update_memory_bank", "_head_precision", "_head_bwd_precision"):
+        setattr(cls, name, getattr(md.HeadMixin, name))
+        patched.append(f"NeighborRetr.models.modeling.NeighborRetr.{name}")
+    for name in ("CentralityWeightingLoss", "NeighborAdjustingLoss", "UniformRegularizationLoss",
+                 "KLDivergenceLoss", "AllGather", "AllGather2"):
+        for mod in (ref_until, ref_modeling):
+            setattr(mod, name, getattr(um, name))
+        patched.append(f"NeighborRetr.models.until_module.{name}")
+    ref_modeling.allgather = um.AllGather.apply
+    ref_modeling.allgather2 = um.AllGather2.apply
+    ref_eval.AllGather = um.AllGather
+    ref_eval.allgather = um.AllGather.apply
+    ref_metrics.RetrievalMetrics.compute_metrics = staticmethod(mt.RetrievalMetrics.compute_metrics)
+    ref_eval._run_on_single_gpu = ev._run_on_single_gpu
+    patched += ["NeighborRetr.utils.metrics.RetrievalMetrics.compute_metrics",
+                "NeighborRetr.training.evaluator._run_on_single_gpu"]
+    return patched

@@ -1,0 +1,85 @@
+"""ctypes binding of libnrhead.so — the C ABI declared in include/nrhead.h.
+
+There is no CPU or PyTorch-eager fallback: if the shared library is missing (and cannot be built with
+nvcc) importing any op raises, and every op refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_I = ctypes.c_int
+_F = ctypes.c_float
+_SZ = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/nrhead.h one to one
+SIGNATURES = {
+    "nr_version": (_I, []),
+    "nr_last_error": (ctypes.c_char_p, []),
+    "nr_device_supported": (_I, []),
+    "nr_prep_partials": (_I64, [_I64]),
+    "nr_prep_tokens": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P]),
+    "nr_prep_tokens_bwd": (_I, [_P, _P, _P, _P, _I64, _I64, _P, _I, _P]),
+    "nr_maxsim_fwd": (_I, [_I, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _P, _I64, _I64, _P, _I64,
+                           _I64, _I, _P, _P, _P]),
+    "nr_maxsim_bwd_x": (_I, [_I, _P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "nr_maxsim_bwd_y": (_I, [_I, _P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "nr_maxsim_bwd_w": (_I, [_P, _P, _I64, _I64, _F, _I64, _I64, _I64, _P, _P]),
+    "nr_centrality_fwd": (_I, [_P, _I64, _I64, _P, _I64, _I64, _F, _P, _P, _P, _P, _P]),
+    "nr_centrality_bwd": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _P, _I, _P, _P]),
+    "nr_row_losses_fwd": (_I, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P, _I, _F, _F, _F, _I, _P,
+                               _P, _P, _P]),
+    "nr_row_losses_bwd": (_I, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P, _I, _F, _F, _F, _I, _P,
+                               _P, _P, _P, _I64, _P, _I64, _P, _P, _P, _P]),
+    "nr_row_mean": (_I, [_P, _I64, _I64, _I64, _P, _P]),
+    "nr_vec_sums": (_I, [_P, _I64, _I64, _P, _P, _P]),
+    "nr_transpose_add": (_I, [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _F, _F, _P]),
+    "nr_sinkhorn_workspace_bytes": (_SZ, [_I64]),
+    "nr_sinkhorn": (_I, [_P, _P, _I64, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "nr_fifo_update": (_I, [_P, _I64, _P, _I64, _P, _I64, _I64, _P]),
+    "nr_rank_count": (_I, [_P, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
+    "nr_topk_rows": (_I, [_P, _I64, _I64, _I64, _I, ctypes.c_int32, _P, _P, _P]),
+    "nr_topk_merge": (_I, [_P, _P, _I64, _I64, _I, _P, _P, _P]),
+}
+
+NR_LOSS_CENTRALITY, NR_LOSS_NEIGHBOR, NR_LOSS_KL, NR_LOSS_UNIFORM = 1, 2, 4, 8
+NR_NSAVE = 16
+NR_PREC_FP32, NR_PREC_BF16 = 0, 1
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed) libnrhead.so; raises if the CUDA extension is unavailable."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise RuntimeError(f"{path} is missing: run `python -m neighborretr_b200.build`")
+            _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = load().nr_last_error().decode(errors="replace")
+        raise RuntimeError(f"{name} failed (rc={rc}): {msg}")

@@ -1,0 +1,243 @@
+// Token preparation (L2 normalisation + bf16 operand copy + column sums) and the centrality
+// weights built on it.  All kernels here are HBM-bound streaming passes: one warp per token row,
+// 128-bit coalesced loads, warp-shuffle reductions, no atomics (per-CTA partials instead).
+//
+// Reference: F.normalize in local_level (NeighborRetr/models/modeling.py:495-496) and
+// compute_centrality_weights (modeling.py:403-430).  The mean over all B*N tokens of
+// <g_a, t_j> is computed as <g_a, mean_j t_j>: a column mean plus a GEMV instead of the
+// reference's [B,D]x[D,B*N] GEMM.
+// Algorithmic bytes: prep = rows*d*4 read + rows*d*(4+2) written.
+#include "common.cuh"
+#include "nrhead_internal.h"
+
+namespace nr {
+
+constexpr int PREP_WARPS = 8;
+constexpr int PREP_MAXQ = 8;          // d <= 128*PREP_MAXQ
+constexpr int PREP_MAX_BLOCKS = 296;  // 2 CTAs per SM
+
+__global__ void __launch_bounds__(PREP_WARPS * 32)
+prep_tokens_kernel(const float* __restrict__ x, int rows, int d, float* __restrict__ xn_f32,
+                   __nv_bfloat16* __restrict__ xn_bf16, float* __restrict__ inv_norm,
+                   float* __restrict__ partials) {
+  __shared__ float colsm[PREP_WARPS][128 * PREP_MAXQ];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 acc[PREP_MAXQ];
+#pragma unroll
+  for (int q = 0; q < PREP_MAXQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x * PREP_WARPS + warp; row < rows; row += gridDim.x * PREP_WARPS) {
+    const float* xr = x + (int64_t)row * d;
+    float4 v[PREP_MAXQ];
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < PREP_MAXQ; ++q) {
+      int c = q * 128 + lane * 4;
+      if (c < d) {
+        v[q] = *reinterpret_cast<const float4*>(xr + c);
+        ss += v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w;
+      }
+    }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);    // F.normalize eps
+    if (lane == 0 && inv_norm) inv_norm[row] = 1.0f / denom;
+#pragma unroll
+    for (int q = 0; q < PREP_MAXQ; ++q) {
+      int c = q * 128 + lane * 4;
+      if (c < d) {
+        float4 n = make_float4(v[q].x / denom, v[q].y / denom, v[q].z / denom, v[q].w / denom);
+        if (xn_f32) *reinterpret_cast<float4*>(xn_f32 + (int64_t)row * d + c) = n;
+        if (xn_bf16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(n.x, n.y), hi = __floats2bfloat162_rn(n.z, n.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(xn_bf16 + (int64_t)row * d + c) = pk;
+        }
+        acc[q].x += n.x; acc[q].y += n.y; acc[q].z += n.z; acc[q].w += n.w;
+      }
+    }
+  }
+  if (partials) {
+#pragma unroll
+    for (int q = 0; q < PREP_MAXQ; ++q) {
+      int c = q * 128 + lane * 4;
+      if (c < d) *reinterpret_cast<float4*>(&colsm[warp][c]) = acc[q];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < PREP_WARPS; ++w) s += colsm[w][c];
+      partials[(int64_t)blockIdx.x * d + c] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PREP_WARPS * 32)
+prep_tokens_bwd_kernel(const float* __restrict__ xn, const float* __restrict__ inv_norm,
+                       const float* __restrict__ dxn, const float* __restrict__ add_vec, int rows, int d,
+                       float* __restrict__ dx, int accumulate) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * PREP_WARPS + warp;
+  if (row >= rows) return;
+  const float* nr_ = xn + (int64_t)row * d;
+  float4 n[PREP_MAXQ], t[PREP_MAXQ];
+  float dot = 0.f;
+#pragma unroll
+  for (int q = 0; q < PREP_MAXQ; ++q) {
+    int c = q * 128 + lane * 4;
+    if (c < d) {
+      n[q] = *reinterpret_cast<const float4*>(nr_ + c);
+      t[q] = dxn ? *reinterpret_cast<const float4*>(dxn + (int64_t)row * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add_vec) {
+        float4 a = *reinterpret_cast<const float4*>(add_vec + c);
+        t[q].x += a.x; t[q].y += a.y; t[q].z += a.z; t[q].w += a.w;
+      }
+      dot += n[q].x * t[q].x + n[q].y * t[q].y + n[q].z * t[q].z + n[q].w * t[q].w;
+    }
+  }
+  dot = warp_sum(dot);
+  const float inv = inv_norm[row];
+  if (inv >= 1e12f) dot = 0.f;     // ||x|| below eps: the clamp has no gradient
+#pragma unroll
+  for (int q = 0; q < PREP_MAXQ; ++q) {
+    int c = q * 128 + lane * 4;
+    if (c < d) {
+      float4 o = make_float4((t[q].x - n[q].x * dot) * inv, (t[q].y - n[q].y * dot) * inv,
+                             (t[q].z - n[q].z * dot) * inv, (t[q].w - n[q].w * dot) * inv);
+      float4* p = reinterpret_cast<float4*>(dx + (int64_t)row * d + c);
+      if (accumulate) { float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+      *p = o;
+    }
+  }
+}
+
+__global__ void mean_vec_kernel(const float* __restrict__ partials, int n_partials, int d, float inv_rows,
+                                float* __restrict__ mean_vec) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float s = 0.f;
+  for (int p = 0; p < n_partials; ++p) s += partials[(int64_t)p * d + c];
+  mean_vec[c] = s * inv_rows;
+}
+
+// one warp per global-feature row: gn = normalize(g), w = exp(cs * <gn, mean>)
+__global__ void __launch_bounds__(PREP_WARPS * 32)
+centrality_rows_kernel(const float* __restrict__ g, const float* __restrict__ mean_vec, int B, int d, float cs,
+                       float* __restrict__ gn, float* __restrict__ ginv, float* __restrict__ w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * PREP_WARPS + warp;
+  if (row >= B) return;
+  const float* gr = g + (int64_t)row * d;
+  float ss = 0.f, dot = 0.f;
+  for (int c = lane; c < d; c += 32) { float v = gr[c]; ss += v * v; dot += v * mean_vec[c]; }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  for (int c = lane; c < d; c += 32) gn[(int64_t)row * d + c] = gr[c] / denom;
+  if (lane == 0) {
+    ginv[row] = 1.f / denom;
+    w[row] = expf(cs * (dot / denom));       // exp(centrality * scale), modeling.py:427-428
+  }
+}
+
+__global__ void __launch_bounds__(PREP_WARPS * 32)
+centrality_rows_bwd_kernel(const float* __restrict__ mean_vec, const float* __restrict__ gn,
+                           const float* __restrict__ ginv, const float* __restrict__ w,
+                           const float* __restrict__ dw, int B, int d, float cs, float* __restrict__ dg,
+                           int accumulate) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * PREP_WARPS + warp;
+  if (row >= B) return;
+  const float dcv = cs * w[row] * dw[row];
+  const float* nrow = gn + (int64_t)row * d;
+  float dot = 0.f;
+  for (int c = lane; c < d; c += 32) dot += nrow[c] * mean_vec[c];
+  dot = warp_sum(dot) * dcv;               // <gn, dgn>, dgn = dc * mean
+  const float inv = ginv[row];
+  if (inv >= 1e12f) dot = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    float o = (dcv * mean_vec[c] - nrow[c] * dot) * inv;
+    float* p = dg + (int64_t)row * d + c;
+    *p = accumulate ? (*p + o) : o;
+  }
+}
+
+// dmean[c] = (1/rows_total) * sum_a cs*w[a]*dw[a]*gn[a,c]
+__global__ void centrality_dmean_kernel(const float* __restrict__ gn, const float* __restrict__ w,
+                                        const float* __restrict__ dw, int B, int d, float cs, float inv_rows,
+                                        float* __restrict__ dmean) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float s = 0.f;
+  for (int a = 0; a < B; ++a) s += cs * w[a] * dw[a] * gn[(int64_t)a * d + c];
+  dmean[c] = s * inv_rows;
+}
+
+}  // namespace nr
+
+using namespace nr;
+
+extern "C" int64_t nr_prep_partials(int64_t rows) {
+  int64_t nb = (rows + PREP_WARPS - 1) / PREP_WARPS;
+  return nb < PREP_MAX_BLOCKS ? (nb < 1 ? 1 : nb) : PREP_MAX_BLOCKS;
+}
+
+extern "C" int nr_prep_tokens(const float* x, int64_t rows, int64_t d, float* xn_f32, void* xn_bf16,
+                              float* inv_norm, float* colsum_partials, void* stream) {
+  NR_CHECK_ARG(x && rows > 0, "nr_prep_tokens: bad arguments");
+  NR_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 128 * PREP_MAXQ, "nr_prep_tokens: d=%lld must be a multiple of 4, <= %d",
+               (long long)d, 128 * PREP_MAXQ);
+  int grid = (int)nr_prep_partials(rows);
+  prep_tokens_kernel<<<grid, PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      x, (int)rows, (int)d, xn_f32, (__nv_bfloat16*)xn_bf16, inv_norm, colsum_partials);
+  NR_CHECK_LAUNCH("nr_prep_tokens");
+  return 0;
+}
+
+extern "C" int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* dxn,
+                                  const float* add_vec, int64_t rows, int64_t d, float* dx, int accumulate,
+                                  void* stream) {
+  NR_CHECK_ARG(xn_f32 && inv_norm && dx && rows > 0 && (dxn || add_vec), "nr_prep_tokens_bwd: bad arguments");
+  NR_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 128 * PREP_MAXQ, "nr_prep_tokens_bwd: unsupported d=%lld", (long long)d);
+  int grid = (int)((rows + PREP_WARPS - 1) / PREP_WARPS);
+  prep_tokens_bwd_kernel<<<grid, PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(xn_f32, inv_norm, dxn, add_vec,
+                                                                            (int)rows, (int)d, dx, accumulate);
+  NR_CHECK_LAUNCH("nr_prep_tokens_bwd");
+  return 0;
+}
+
+extern "C" int nr_centrality_fwd(const float* colsum_partials, int64_t n_partials, int64_t rows_total,
+                                 const float* g, int64_t B, int64_t d, float cs, float* mean_vec, float* gn,
+                                 float* ginv, float* w, void* stream) {
+  NR_CHECK_ARG(colsum_partials && g && mean_vec && gn && ginv && w && n_partials > 0 && rows_total > 0 && B > 0 &&
+                   d > 0,
+               "nr_centrality_fwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  mean_vec_kernel<<<(unsigned)((d + 255) / 256), 256, 0, s>>>(colsum_partials, (int)n_partials, (int)d,
+                                                             1.0f / (float)rows_total, mean_vec);
+  NR_CHECK_LAUNCH("nr_centrality_fwd(mean)");
+  centrality_rows_kernel<<<(unsigned)((B + PREP_WARPS - 1) / PREP_WARPS), PREP_WARPS * 32, 0, s>>>(
+      g, mean_vec, (int)B, (int)d, cs, gn, ginv, w);
+  NR_CHECK_LAUNCH("nr_centrality_fwd(rows)");
+  return 0;
+}
+
+extern "C" int nr_centrality_bwd(const float* mean_vec, const float* gn, const float* ginv, const float* w,
+                                 const float* dw, int64_t B, int64_t d, float cs, int64_t rows_total, float* dg,
+                                 int accumulate, float* dmean, void* stream) {
+  NR_CHECK_ARG(mean_vec && gn && ginv && w && dw && B > 0 && d > 0 && rows_total > 0,
+               "nr_centrality_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dg) {
+    centrality_rows_bwd_kernel<<<(unsigned)((B + PREP_WARPS - 1) / PREP_WARPS), PREP_WARPS * 32, 0, s>>>(
+        mean_vec, gn, ginv, w, dw, (int)B, (int)d, cs, dg, accumulate);
+    NR_CHECK_LAUNCH("nr_centrality_bwd(rows)");
+  }
+  if (dmean) {
+    centrality_dmean_kernel<<<(unsigned)((d + 127) / 128), 128, 0, s>>>(gn, w, dw, (int)B, (int)d, cs,
+                                                                       1.0f / (float)rows_total, dmean);
+    NR_CHECK_LAUNCH("nr_centrality_bwd(dmean)");
+  }
+  return 0;
+}

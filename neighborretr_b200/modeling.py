@@ -1,0 +1,269 @@
+"""The retrieval head of NeighborRetr behind the reference's own module surface
+(reference NeighborRetr/models/modeling.py:137-153, :175-184, :222-249, :251-539, :625-632).
+
+``HeadMixin`` holds the head methods with the reference's names, positional order and return types:
+``local_level``, ``global_level``, ``compute_centrality_weights``, ``compute_centrality_loss``,
+``compute_neighbor_loss``, ``compute_uniform_loss``, ``_compute_losses``, ``update_memory_bank``,
+``get_similarity_logits``.  ``NeighborRetr`` is a weights-free standalone module built on it (encoders and
+token clustering are out of scope — SURVEY.md §2 rows 13/14 — and are injected by the caller);
+``neighborretr_b200.install()`` rebinds the same methods onto the reference's class so that the
+reference's ``main.py`` runs unchanged on the CUDA path.
+
+The token-weight MLPs stay ``nn.Sequential(Linear, ReLU, Linear)`` with the reference's parameter names
+(state_dict compatibility) and run through cuBLAS; everything below them is libnrhead.so.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import NR_LOSS_CENTRALITY, NR_LOSS_KL, NR_LOSS_NEIGHBOR, NR_LOSS_UNIFORM
+from .until_module import (AllGather, AllGather2, CentralityWeightingLoss, KLDivergenceLoss,  # noqa: F401
+                           NeighborAdjustingLoss, UniformRegularizationLoss)
+
+allgather = AllGather.apply
+allgather2 = AllGather2.apply
+
+DEFAULT_PRECISION = os.environ.get("NR_HEAD_PRECISION", "fp32")
+
+
+def _token_weights(mlp, feat, mask):
+    """softmax over tokens of the MLP logits, masked tokens filled with -9e15 (reference :485-492)."""
+    logit = mlp(feat).squeeze(2)
+    if mask is not None:
+        logit = logit.masked_fill((1 - mask).to(torch.bool), float(-9e15))
+    return torch.softmax(logit, dim=-1)
+
+
+class HeadMixin:
+    """Head methods; ``self`` provides the weight MLPs, ``config``, ``clip.logit_scale`` and mb_* state."""
+
+    # --- precision of the token-pair contraction: "bf16" (tcgen05) or "fp32" (CUDA cores) -----------
+    def _head_precision(self):
+        cfg = getattr(self, "config", None)
+        return getattr(self, "head_precision", None) or getattr(cfg, "head_precision", None) or DEFAULT_PRECISION
+
+    def _head_bwd_precision(self):
+        cfg = getattr(self, "config", None)
+        return (getattr(self, "head_bwd_precision", None) or getattr(cfg, "head_bwd_precision", None)
+                or self._head_precision())
+
+    # --- a1: local_level (reference :483-514) -------------------------------------------------------
+    def local_level(self, text_feat, video_feat, text_mask, video_mask):
+        tw = _token_weights(self.text_weight_fc, text_feat, text_mask)
+        vw = _token_weights(self.video_weight_fc, video_feat, video_mask)
+        s, st = ops.maxsim(text_feat, video_feat, tw, vw, text_mask, video_mask, self._head_precision(),
+                           self._head_bwd_precision())
+        return s, st
+
+    # --- a2: get_similarity_logits (reference :625-632) ---------------------------------------------
+    def get_similarity_logits(self, text_feat, video_feat, text_mask, video_mask, shaped=False):
+        if shaped is False:
+            text_mask = text_mask.view(-1, text_mask.shape[-1])
+            video_mask = video_mask.view(-1, video_mask.shape[-1])
+        return self.local_level(text_feat, video_feat, text_mask, video_mask)
+
+    # --- a4: global_level (reference :516-539) -------------------------------------------------------
+    def global_level(self, text_feat, video_feat):
+        if text_feat.shape[1] == 1 and video_feat.shape[1] == 1:
+            # one global token per sample: softmax over a single token is 1, so G is the plain
+            # [B,D]x[D,B] dot product — a library GEMM in fp32
+            t, v = text_feat[:, 0, :], video_feat[:, 0, :]
+            return t @ v.t(), v @ t.t()
+        tw = torch.softmax(self.text_weight_fc1(text_feat).squeeze(2), dim=-1)
+        vw = torch.softmax(self.video_weight_fc1(video_feat).squeeze(2), dim=-1)
+        return ops.maxsim(text_feat, video_feat, tw, vw, None, None, "fp32", normalize=False)
+
+    # --- a5: compute_centrality_weights (reference :403-430) ----------------------------------------
+    def compute_centrality_weights(self, text_feat, video_feat, global_text_feat, global_video_feat,
+                                   centrality_scale):
+        return (ops.centrality_weights(text_feat, global_text_feat, centrality_scale),
+                ops.centrality_weights(video_feat, global_video_feat, centrality_scale))
+
+    # --- a6 driver (reference :362-380) ---------------------------------------------------------------
+    def compute_centrality_loss(self, text_feat, video_feat, global_text_feat, global_video_feat,
+                                local_t2v_logits, local_v2t_logits, centrality_scale, logit_scale):
+        wt, wv = self.compute_centrality_weights(text_feat, video_feat, global_text_feat, global_video_feat,
+                                                 centrality_scale)
+        b = local_t2v_logits.shape[0]
+        ls = logit_scale if torch.is_tensor(logit_scale) else torch.tensor(float(logit_scale),
+                                                                           device=local_t2v_logits.device)
+        s1, _ = ops.row_losses(local_t2v_logits, w=wt, logit_scale=ls, flags=NR_LOSS_CENTRALITY)
+        s2, _ = ops.row_losses(local_v2t_logits, w=wv, logit_scale=ls, flags=NR_LOSS_CENTRALITY)
+        return (s1[0] + s2[0]) / (2 * b)
+
+    # --- a7 driver (reference :382-401) ---------------------------------------------------------------
+    def compute_neighbor_loss(self, text_feat, video_feat, text_mask, video_mask, mb_feat_t, mb_feat_v,
+                              mb_mask_t, mb_mask_v, local_t2v_logits, local_v2t_logits, num_neighbors, temperature):
+        if mb_feat_v.dim() != 3 or mb_feat_v.shape[0] == 0:
+            raise RuntimeError("memory bank is empty: prefill it (MemoryBankManager.load_memory_bank) or call "
+                               "update_memory_bank before the first training step")
+        b = local_t2v_logits.shape[0]
+        if b < num_neighbors + 2:
+            raise IndexError(f"neighbor loss needs batch >= num_neighbors + 2 (got {b}, k={num_neighbors})")
+        memory_bank_t2v_logits, _ = self.local_level(text_feat, mb_feat_v, text_mask, mb_mask_v)
+        _, memory_bank_v2t_logits = self.local_level(mb_feat_t, video_feat, mb_mask_t, video_mask)
+        c_v2t = ops.row_mean(memory_bank_v2t_logits)
+        c_t2v = ops.row_mean(memory_bank_t2v_logits)
+        s1, n1 = ops.row_losses(local_t2v_logits, cbank=c_v2t, k=num_neighbors, tau_nbr=temperature,
+                                flags=NR_LOSS_NEIGHBOR)
+        s2, n2 = ops.row_losses(local_v2t_logits, cbank=c_t2v, k=num_neighbors, tau_nbr=temperature,
+                                flags=NR_LOSS_NEIGHBOR)
+        self.last_neighbors = (n1, n2)
+        return (s1[1] + s2[1]) / (2 * b)
+
+    # --- a8 driver (reference :432-444) ---------------------------------------------------------------
+    def compute_uniform_loss(self, text_feat, video_feat, text_mask, video_mask, temperature, beta,
+                             global_feats=None):
+        if global_feats is None:
+            global_text_feat, global_video_feat = self.merge_global_features(text_feat, video_feat, text_mask,
+                                                                             video_mask)
+        else:
+            global_text_feat, global_video_feat = global_feats
+        g, gt = self.global_level(global_text_feat, global_video_feat)
+        b = g.shape[0]
+        u1, v1, u2, v2 = ops.sinkhorn_duals(g, gt, 50)
+        # NB the reference passes `temperature` as the uniform loss's logit_scale (modeling.py:440-441)
+        s1, _ = ops.row_losses(g, G=g, sk_u=u1, sk_v=v1, tau_uni=temperature, beta=beta, flags=NR_LOSS_UNIFORM)
+        s2, _ = ops.row_losses(gt, G=gt, sk_u=u2, sk_v=v2, tau_uni=temperature, beta=beta, flags=NR_LOSS_UNIFORM)
+        uniform_loss = (s1[3] + s2[3]) / (2 * b)
+        return uniform_loss, global_text_feat, global_video_feat, g, gt
+
+    # --- a14: _compute_losses (reference :314-360) ----------------------------------------------------
+    def _compute_losses(self, text_feat, video_feat, text_mask, video_mask, mb_feat_t, mb_feat_v, mb_mask_t,
+                        mb_mask_v, centrality_scale, beta, num_neighbors, temperature, logit_scale,
+                        global_feats=None):
+        local_t2v_logits, local_v2t_logits = self.local_level(text_feat, video_feat, text_mask, video_mask)
+        uniform_loss, global_text_feat, global_video_feat, g, gt = self.compute_uniform_loss(
+            text_feat, video_feat, text_mask, video_mask, temperature, beta, global_feats=global_feats)
+        b = g.shape[0]
+        k1, _ = ops.row_losses(local_t2v_logits, G=g, flags=NR_LOSS_KL)
+        k2, _ = ops.row_losses(local_v2t_logits, G=gt, flags=NR_LOSS_KL)
+        kl_loss = (k1[2] + k2[2]) / (2 * b * b)
+        centrality_loss = self.compute_centrality_loss(text_feat, video_feat, global_text_feat, global_video_feat,
+                                                       local_t2v_logits, local_v2t_logits, centrality_scale,
+                                                       logit_scale)
+        neighbor_loss = self.compute_neighbor_loss(text_feat, video_feat, text_mask, video_mask, mb_feat_t,
+                                                   mb_feat_v, mb_mask_t, mb_mask_v, local_t2v_logits,
+                                                   local_v2t_logits, num_neighbors, temperature)
+        total_loss = (centrality_loss + uniform_loss * self.config.uniform_weight
+                      + neighbor_loss * self.config.neighbor_weight + kl_loss * self.config.kl_weight)
+        return total_loss, centrality_loss, uniform_loss, neighbor_loss, kl_loss
+
+    # --- a13: update_memory_bank (reference :222-249) -------------------------------------------------
+    def update_memory_bank(self, idx, text_feat, video_feat, text_mask, video_mask):
+        if self.mb_feat_v.size(0) == 0:
+            self.mb_ind = idx.clone()
+            self.mb_feat_v = video_feat.clone()
+            self.mb_feat_t = text_feat.clone()
+            self.mb_mask_t = text_mask.clone()
+            self.mb_mask_v = video_mask.clone()
+            self.mb_batch = idx.size(0)
+            return
+        cap = self.mb_feat_v.size(0)
+        self.mb_ind = ops.fifo_update(idx, self.mb_ind, cap)
+        self.mb_feat_v = ops.fifo_update(video_feat.detach(), self.mb_feat_v, cap)
+        self.mb_feat_t = ops.fifo_update(text_feat.detach(), self.mb_feat_t, cap)
+        self.mb_mask_t = ops.fifo_update(text_mask.to(self.mb_mask_t.dtype), self.mb_mask_t, cap)
+        self.mb_mask_v = ops.fifo_update(video_mask.to(self.mb_mask_v.dtype), self.mb_mask_v, cap)
+
+    # --- everything of reference forward() below the encoders (:269-312) -----------------------------
+    def head_forward(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats=None):
+        cfg = self.config
+        if getattr(cfg, "world_size", 1) > 1:
+            idx = allgather(idx, cfg)
+            text_feat = allgather(text_feat, cfg)
+            video_feat = allgather(video_feat, cfg)
+            text_mask = allgather(text_mask, cfg)
+            video_mask = allgather(video_mask, cfg)
+            if global_feats is not None:
+                global_feats = (allgather(global_feats[0], cfg), allgather(global_feats[1], cfg))
+        logit_scale = self.clip.logit_scale.exp()
+        losses = self._compute_losses(text_feat, video_feat, text_mask, video_mask, self.mb_feat_t, self.mb_feat_v,
+                                      self.mb_mask_t, self.mb_mask_v, cfg.centrality_scale, cfg.beta,
+                                      cfg.num_neighbors, cfg.temperature, logit_scale, global_feats=global_feats)
+        with torch.no_grad():
+            self.update_memory_bank(idx, text_feat, video_feat, text_mask, video_mask)
+        return losses
+
+
+class _LogitScale(nn.Module):
+    def __init__(self, init=float(torch.log(torch.tensor(1.0 / 0.07)))):
+        super().__init__()
+        self.logit_scale = nn.Parameter(torch.tensor(init))
+
+
+class NeighborRetr(HeadMixin, nn.Module):
+    """Standalone retrieval head with the reference's parameter names.
+
+    ``encoder(text_ids, text_mask, video, video_mask) -> (text_feat [B,Nt,D], video_feat [B,Nv,D])`` and
+    ``global_merger(text_feat, video_feat, text_mask, video_mask) -> (gT [B,1,D], gV [B,1,D])`` stand in for
+    the CLIP towers and the token-clustering blocks, both out of scope here.
+    """
+
+    def __init__(self, config, encoder=None, global_merger=None, width=512):
+        super().__init__()
+        self.config = config
+        self.transformer_width = width
+        self.encoder = encoder
+        self.global_merger = global_merger
+        self._init_weighting_networks()
+        self._init_loss_functions()
+        self._init_memory_bank()
+        self.clip = _LogitScale()
+        self.apply(self._init_weights)
+
+    # reference :137-153 (all eight networks are kept so state_dicts load; four are unused, as there)
+    def _init_weighting_networks(self):
+        for name in ("text_weight_fc", "video_weight_fc", "text_weight_fc0", "video_weight_fc0",
+                     "text_weight_fc1", "video_weight_fc1", "text_weight_intra", "video_weight_intra"):
+            setattr(self, name, self._create_weighting_network())
+
+    def _create_weighting_network(self):
+        w = self.transformer_width
+        return nn.Sequential(nn.Linear(w, 2 * w), nn.ReLU(inplace=True), nn.Linear(2 * w, 1))
+
+    def _init_loss_functions(self):
+        self.centrality_weighting_loss = CentralityWeightingLoss()
+        self.neighbor_adjusting_loss = NeighborAdjustingLoss()
+        self.uniform_regularization_loss = UniformRegularizationLoss()
+        self.kl_loss = KLDivergenceLoss()
+
+    # reference :175-184: plain assignable attributes (MemoryBankManager writes them from outside)
+    def _init_memory_bank(self):
+        self.mb_ind = torch.tensor([], dtype=torch.long)
+        self.mb_feat_t = torch.empty((0, 0, 0), dtype=torch.float)
+        self.mb_feat_v = torch.empty((0, 0, 0), dtype=torch.float)
+        self.mb_mask_t = torch.empty((0, 0), dtype=torch.float)
+        self.mb_mask_v = torch.empty((0, 0), dtype=torch.float)
+        self.mb_batch = 0
+
+    # reference :648-659
+    def _init_weights(self, module):
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=0.02)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()
+
+    def merge_global_features(self, text_feat, video_feat, text_mask, video_mask):
+        if self.global_merger is None:
+            raise NotImplementedError("token clustering (reference cluster.py CTM/TCBlock) is out of scope: pass "
+                                      "global_merger=... or global_feats=(gT, gV)")
+        return self.global_merger(text_feat, video_feat, text_mask, video_mask)
+
+    def get_text_video_feat(self, text_ids, text_mask, video, video_mask, shaped=False):
+        if self.encoder is None:
+            raise NotImplementedError("CLIP encoders are out of scope: construct NeighborRetr(config, encoder=...)")
+        return self.encoder(text_ids, text_mask, video, video_mask)
+
+    # reference :251-312
+    def forward(self, text_ids, text_mask, video, video_mask=None, idx=None, global_step=0, logger=None):
+        text_mask = text_mask.view(-1, text_mask.shape[-1])
+        video_mask = video_mask.view(-1, video_mask.shape[-1])
+        text_feat, video_feat = self.get_text_video_feat(text_ids, text_mask, video, video_mask, shaped=True)
+        if not self.training:
+            return None
+        return self.head_forward(text_feat, video_feat, text_mask, video_mask, idx)

@@ -1,0 +1,369 @@
+"""torch.autograd.Functions of the retrieval head on top of the C ABI (include/nrhead.h).
+
+PyTorch is plumbing here: device buffers, the current CUDA stream, autograd graph edges.  All arithmetic
+of the path runs in libnrhead.so kernels.  Every op refuses CPU tensors — there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (NR_LOSS_CENTRALITY, NR_LOSS_KL, NR_LOSS_NEIGHBOR, NR_LOSS_UNIFORM, NR_NSAVE, NR_PREC_BF16,
+                   NR_PREC_FP32, check)
+
+PRECISIONS = {"fp32": NR_PREC_FP32, "bf16": NR_PREC_BF16}
+# kernel launches issued through the C ABI since the last reset (bench.py reports it as gpu_launches)
+LAUNCHES = {"count": 0}
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("neighborretr_b200: CUDA tensors required (no CPU fallback exists)")
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _mask(t):
+    if t is None:
+        return None
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+def _call(name, *args, launches=1):
+    rc = getattr(_lib.load(), name)(*args)
+    check(rc, name)
+    LAUNCHES["count"] += launches
+
+
+# ------------------------------------------------------------------------------------------------
+# token preparation
+# ------------------------------------------------------------------------------------------------
+class Prepared:
+    """L2-normalised tokens of one modality: fp32 copy (backward / fp32 mode), optional bf16 operand
+    copy (tensor-core mode), inverse norms and per-CTA column-sum partials."""
+
+    __slots__ = ("xn", "xn_bf16", "inv_norm", "partials", "rows", "n", "d", "r")
+
+    def __init__(self, x, bf16=False, colsum=False, normalize=True):
+        _req_cuda(x)
+        x = _f32c(x)
+        self.r, self.n, self.d = x.shape
+        self.rows = self.r * self.n
+        dev = x.device
+        if not normalize:        # global_level: raw dot products (reference modeling.py:525), fp32 only
+            self.xn, self.xn_bf16, self.inv_norm, self.partials = x, None, None, None
+            return
+        self.xn = torch.empty_like(x)
+        self.xn_bf16 = torch.empty(x.shape, dtype=torch.bfloat16, device=dev) if bf16 else None
+        self.inv_norm = torch.empty(self.rows, dtype=torch.float32, device=dev)
+        npart = _lib.load().nr_prep_partials(self.rows)
+        self.partials = torch.empty(npart, self.d, dtype=torch.float32, device=dev) if colsum else None
+        _call("nr_prep_tokens", _p(x), self.rows, self.d, _p(self.xn), _p(self.xn_bf16), _p(self.inv_norm),
+              _p(self.partials), _stream())
+
+    def operand(self, prec):
+        return self.xn_bf16 if prec == NR_PREC_BF16 else self.xn
+
+    def backward(self, dxn, add_vec=None):
+        if self.inv_norm is None:
+            return dxn
+        dx = torch.empty_like(self.xn)
+        _call("nr_prep_tokens_bwd", _p(self.xn), _p(self.inv_norm), _p(dxn), _p(add_vec), self.rows, self.d, _p(dx),
+              0, _stream())
+        return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# max-sim (one direction) raw helpers
+# ------------------------------------------------------------------------------------------------
+def _maxsim_dir_fwd(prec, X: Prepared, Y: Prepared, wx, mx, my, alpha, out, sr, sc, out2, sr2, sc2, accumulate,
+                    keep):
+    dev = X.xn.device
+    pmax = torch.empty(X.r, Y.r, X.n, dtype=torch.float32, device=dev) if keep else None
+    ystar = torch.empty(X.r, Y.r, X.n, dtype=torch.uint8, device=dev) if keep else None
+    _call("nr_maxsim_fwd", prec, _p(X.operand(prec)), _p(Y.operand(prec)), _p(wx), _p(mx), _p(my), X.r, X.n, Y.r,
+          Y.n, X.d, alpha, _p(out), sr, sc, _p(out2), sr2, sc2, accumulate, _p(pmax), _p(ystar), _stream())
+    return pmax, ystar
+
+
+class MaxSimFunction(torch.autograd.Function):
+    """local_level's token-pair part (reference modeling.py:495-512) given the token weights:
+    returns (S, S^T) as two contiguous tensors.  bwd_prec selects the arithmetic of the backward
+    contraction independently of the forward one."""
+
+    @staticmethod
+    def forward(ctx, text_feat, video_feat, tw, vw, text_mask, video_mask, prec, bwd_prec, normalize=True):
+        _req_cuda(text_feat, video_feat, tw, vw, text_mask, video_mask)
+        tw, vw = _f32c(tw), _f32c(vw)
+        tm, vm = _mask(text_mask), _mask(video_mask)
+        if not normalize:
+            prec = bwd_prec = NR_PREC_FP32
+        need_bf16 = prec == NR_PREC_BF16 or bwd_prec == NR_PREC_BF16
+        T = Prepared(text_feat, bf16=need_bf16, normalize=normalize)
+        V = Prepared(video_feat, bf16=need_bf16, normalize=normalize)
+        A, B = T.r, V.r
+        dev = T.xn.device
+        S = torch.empty(A, B, dtype=torch.float32, device=dev)
+        ST = torch.empty(B, A, dtype=torch.float32, device=dev)
+        keep = any(ctx.needs_input_grad[:4])
+        p1, y1 = _maxsim_dir_fwd(prec, T, V, tw, tm, vm, 0.5, S, B, 1, ST, 1, A, 0, keep)
+        p2, y2 = _maxsim_dir_fwd(prec, V, T, vw, vm, tm, 0.5, S, 1, B, ST, A, 1, 1, keep)
+        ctx.T, ctx.V, ctx.prec = T, V, bwd_prec
+        ctx.save_for_backward(tw, vw, tm, vm, p1, y1, p2, y2)
+        return S, ST
+
+    @staticmethod
+    def backward(ctx, dS, dST):
+        tw, vw, tm, vm, p1, y1, p2, y2 = ctx.saved_tensors
+        T, V, prec = ctx.T, ctx.V, ctx.prec
+        A, B = T.r, V.r
+        dev = T.xn.device
+        st = _stream()
+        # total gradient of S: dS + dST^T
+        if dS is None and dST is None:
+            return (None,) * 9
+        if dST is None:
+            g = _f32c(dS)
+        else:
+            g = torch.empty(A, B, dtype=torch.float32, device=dev)
+            a = _f32c(dS) if dS is not None else None
+            _call("nr_transpose_add", _p(a), B, _p(_f32c(dST)), A, _p(g), B, A, B, 1.0, 1.0, st)
+        need_t, need_v, need_tw, need_vw = ctx.needs_input_grad[:4]
+        dtn = torch.zeros_like(T.xn) if need_t else None
+        dvn = torch.zeros_like(V.xn) if need_v else None
+        dtw = torch.zeros_like(tw) if need_tw else None
+        dvw = torch.zeros_like(vw) if need_vw else None
+        # direction 1: X = text, Y = video, dH[rx=a, ry=b] = 0.5 g[a,b]
+        if need_t:
+            _call("nr_maxsim_bwd_x", prec, _p(V.operand(prec)), _p(tw), _p(tm), _p(vm), _p(y1), _p(g), B, 1, 0.5,
+                  A, T.n, B, V.n, T.d, _p(dtn), st)
+            _call("nr_maxsim_bwd_y", prec, _p(V.operand(prec)), _p(vw), _p(vm), _p(tm), _p(y2), _p(g), 1, B, 0.5,
+                  B, V.n, A, T.n, T.d, _p(dtn), st)
+        if need_v:
+            _call("nr_maxsim_bwd_y", prec, _p(T.operand(prec)), _p(tw), _p(tm), _p(vm), _p(y1), _p(g), B, 1, 0.5,
+                  A, T.n, B, V.n, T.d, _p(dvn), st)
+            _call("nr_maxsim_bwd_x", prec, _p(T.operand(prec)), _p(vw), _p(vm), _p(tm), _p(y2), _p(g), 1, B, 0.5,
+                  B, V.n, A, T.n, T.d, _p(dvn), st)
+        if need_tw:
+            _call("nr_maxsim_bwd_w", _p(p1), _p(g), B, 1, 0.5, A, T.n, B, _p(dtw), st)
+        if need_vw:
+            _call("nr_maxsim_bwd_w", _p(p2), _p(g), 1, B, 0.5, B, V.n, A, _p(dvw), st)
+        dtext = T.backward(dtn) if need_t else None
+        dvideo = V.backward(dvn) if need_v else None
+        ctx.T = ctx.V = None
+        return dtext, dvideo, dtw, dvw, None, None, None, None, None
+
+
+def maxsim(text_feat, video_feat, tw, vw, text_mask, video_mask, precision="fp32", bwd_precision=None,
+           normalize=True):
+    prec = PRECISIONS[precision]
+    bprec = PRECISIONS[bwd_precision or precision]
+    return MaxSimFunction.apply(text_feat, video_feat, tw, vw, text_mask, video_mask, prec, bprec, normalize)
+
+
+# ------------------------------------------------------------------------------------------------
+# centrality weights (reference modeling.py:403-430)
+# ------------------------------------------------------------------------------------------------
+class CentralityWeightsFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, gfeat, cs):
+        _req_cuda(feat, gfeat)
+        P = Prepared(feat, colsum=True)
+        g = _f32c(gfeat).reshape(-1, gfeat.shape[-1])
+        if g.shape[0] != feat.shape[0]:
+            # the reference broadcasts [B,G>1] weights into a shape error
+            raise RuntimeError("centrality weights need exactly one global token per sample "
+                               f"(got {tuple(gfeat.shape)})")
+        B, d = g.shape
+        dev = g.device
+        mean_vec = torch.empty(d, dtype=torch.float32, device=dev)
+        gn = torch.empty(B, d, dtype=torch.float32, device=dev)
+        ginv = torch.empty(B, dtype=torch.float32, device=dev)
+        w = torch.empty(B, dtype=torch.float32, device=dev)
+        _call("nr_centrality_fwd", _p(P.partials), P.partials.shape[0], P.rows, _p(g), B, d, float(cs), _p(mean_vec),
+              _p(gn), _p(ginv), _p(w), _stream(), launches=2)
+        ctx.P, ctx.cs, ctx.gshape = P, float(cs), gfeat.shape
+        ctx.save_for_backward(mean_vec, gn, ginv, w)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        mean_vec, gn, ginv, w = ctx.saved_tensors
+        P = ctx.P
+        B, d = gn.shape
+        dw = _f32c(dw)
+        need_f, need_g = ctx.needs_input_grad[:2]
+        dg = torch.empty(B, d, dtype=torch.float32, device=gn.device) if need_g else None
+        dmean = torch.empty(d, dtype=torch.float32, device=gn.device) if need_f else None
+        _call("nr_centrality_bwd", _p(mean_vec), _p(gn), _p(ginv), _p(w), _p(dw), B, d, ctx.cs, P.rows, _p(dg), 0,
+              _p(dmean), _stream(), launches=2)
+        dfeat = P.backward(None, add_vec=dmean) if need_f else None
+        ctx.P = None
+        return dfeat, (dg.reshape(ctx.gshape) if need_g else None), None
+
+
+def centrality_weights(feat, gfeat, cs):
+    return CentralityWeightsFunction.apply(feat, gfeat, cs)
+
+
+# ------------------------------------------------------------------------------------------------
+# Sinkhorn duals (no grad; reference until_module.py:222-251)
+# ------------------------------------------------------------------------------------------------
+def sinkhorn_duals(G, GT, iters=50):
+    """Both directions in one cooperative launch: returns (u1, v1, u2, v2); chain 1 on G, chain 2 on G^T."""
+    _req_cuda(G, GT)
+    G, GT = _f32c(G.detach()), _f32c(GT.detach())
+    B = G.shape[0]
+    if G.shape != (B, B) or GT.shape != (B, B):
+        raise RuntimeError("sinkhorn_duals: square [B,B] matrices required")
+    duals = torch.empty(4, B, dtype=torch.float32, device=G.device)
+    lib = _lib.load()
+    nbytes = lib.nr_sinkhorn_workspace_bytes(B)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=G.device)
+    _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]), _p(duals[3]),
+          _p(ws), nbytes, _stream(), launches=2)
+    return duals[0], duals[1], duals[2], duals[3]
+
+
+# ------------------------------------------------------------------------------------------------
+# row-block losses
+# ------------------------------------------------------------------------------------------------
+class RowLossesFunction(torch.autograd.Function):
+    """Per-row loss terms of ONE direction over a row block.  Returns the 4 row sums
+    {centrality, neighbour, kl, uniform} (un-normalised: divide by B or B^2 outside)."""
+
+    @staticmethod
+    def forward(ctx, X, G, cbank, w, logit_scale, sk_u, sk_v, row0, k, tau_nbr, tau_uni, beta, flags):
+        _req_cuda(X, G, cbank, w, logit_scale, sk_u, sk_v)
+        X = _f32c(X)
+        rows, B = X.shape
+        dev = X.device
+        G = _f32c(G) if G is not None else None
+        cbank = _f32c(cbank) if cbank is not None else None
+        w = _f32c(w) if w is not None else None
+        ls = _f32c(logit_scale).reshape(1) if logit_scale is not None else None
+        row_out = torch.zeros(4, rows, dtype=torch.float32, device=dev)
+        nbr = torch.empty(rows, max(int(k), 1), dtype=torch.int32, device=dev)
+        saved = torch.zeros(rows, NR_NSAVE, dtype=torch.float32, device=dev)
+        st = _stream()
+        _call("nr_row_losses_fwd", _p(X), B, _p(G), B, _p(cbank), _p(w), _p(sk_u), _p(sk_v), rows, B, int(row0),
+              _p(ls), int(k), float(tau_nbr), float(tau_uni), float(beta), int(flags), _p(row_out), _p(nbr),
+              _p(saved), st)
+        sums = torch.empty(4, dtype=torch.float32, device=dev)
+        _call("nr_vec_sums", _p(row_out), 4, rows, None, _p(sums), st)
+        ctx.cfg = (int(row0), int(k), float(tau_nbr), float(tau_uni), float(beta), int(flags))
+        ctx.save_for_backward(X, G, cbank, w, ls, sk_u, sk_v, nbr, saved)
+        ctx.mark_non_differentiable(nbr)
+        return sums, nbr
+
+    @staticmethod
+    def backward(ctx, dsums, _dnbr):
+        X, G, cbank, w, ls, sk_u, sk_v, nbr, saved = ctx.saved_tensors
+        row0, k, tau_nbr, tau_uni, beta, flags = ctx.cfg
+        rows, B = X.shape
+        dev = X.device
+        gscale = _f32c(dsums)
+        dX = torch.empty_like(X)
+        dG = torch.empty_like(G) if (G is not None and ctx.needs_input_grad[1]) else None
+        dc = torch.zeros(B, dtype=torch.float32, device=dev) if (cbank is not None and ctx.needs_input_grad[2]) else None
+        dw = torch.zeros(rows, dtype=torch.float32, device=dev) if (w is not None and ctx.needs_input_grad[3]) else None
+        dls = torch.zeros(1, dtype=torch.float32, device=dev) if (ls is not None and ctx.needs_input_grad[4]) else None
+        _call("nr_row_losses_bwd", _p(X), B, _p(G), B, _p(cbank), _p(w), _p(sk_u), _p(sk_v), rows, B, row0, _p(ls), k,
+              tau_nbr, tau_uni, beta, flags, _p(nbr), _p(saved), _p(gscale), _p(dX), B, _p(dG), B, _p(dc), _p(dw),
+              _p(dls), _stream())
+        if dls is not None:
+            dls = dls.reshape(())
+        return dX, dG, dc, dw, dls, None, None, None, None, None, None, None, None
+
+
+def row_losses(X, G=None, cbank=None, w=None, logit_scale=None, sk_u=None, sk_v=None, row0=0, k=1, tau_nbr=1.0,
+               tau_uni=1.0, beta=0.0, flags=0):
+    if logit_scale is not None and logit_scale.dim() != 0 and logit_scale.numel() != 1:
+        raise RuntimeError("logit_scale must be a scalar tensor")
+    return RowLossesFunction.apply(X, G, cbank, w, logit_scale, sk_u, sk_v, row0, k, tau_nbr, tau_uni, beta, flags)
+
+
+class RowMeanFunction(torch.autograd.Function):
+    """memory_bank_matrix.sum(-1) / size(-1)  (reference until_module.py:181)."""
+
+    @staticmethod
+    def forward(ctx, X):
+        _req_cuda(X)
+        X = _f32c(X)
+        out = torch.empty(X.shape[0], dtype=torch.float32, device=X.device)
+        _call("nr_row_mean", _p(X), X.shape[1], X.shape[0], X.shape[1], _p(out), _stream())
+        ctx.shape = X.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        return (dout / ctx.shape[1]).unsqueeze(1).expand(ctx.shape)
+
+
+def row_mean(X):
+    return RowMeanFunction.apply(X)
+
+
+# ------------------------------------------------------------------------------------------------
+# memory bank FIFO and evaluation ranking (no autograd)
+# ------------------------------------------------------------------------------------------------
+def fifo_update(new, old, capacity):
+    """cat(new, old)[:capacity] along dim 0 in one copy kernel (reference modeling.py:235-249)."""
+    _req_cuda(new, old)
+    new, old = new.contiguous(), old.contiguous()
+    if new.dtype != old.dtype or new.shape[1:] != old.shape[1:]:
+        raise RuntimeError("fifo_update: new/old rows differ in dtype or shape")
+    out = torch.empty((capacity,) + tuple(new.shape[1:]), dtype=new.dtype, device=new.device)
+    row_bytes = new[0].numel() * new.element_size() if new.shape[0] else old[0].numel() * old.element_size()
+    _call("nr_fifo_update", _p(new), new.shape[0], _p(old), old.shape[0], _p(out), capacity, row_bytes, _stream())
+    return out
+
+
+def rank_counts(S, diag=None, diag_col0=0, gt=None, eq=None):
+    """(#greater, #equal) per query row against its positive's score (reference metrics.py:58-66)."""
+    _req_cuda(S)
+    S = _f32c(S)
+    Q, N = S.shape
+    if gt is None:
+        gt = torch.zeros(Q, dtype=torch.int32, device=S.device)
+        eq = torch.zeros(Q, dtype=torch.int32, device=S.device)
+    _call("nr_rank_count", _p(S), N, Q, N, _p(diag), int(diag_col0), _p(gt), _p(eq), _stream())
+    return gt, eq
+
+
+def topk_rows(S, k, col_offset=0):
+    _req_cuda(S)
+    S = _f32c(S)
+    Q, N = S.shape
+    vals = torch.empty(Q, k, dtype=torch.float32, device=S.device)
+    idx = torch.empty(Q, k, dtype=torch.int32, device=S.device)
+    _call("nr_topk_rows", _p(S), N, Q, N, int(k), int(col_offset), _p(vals), _p(idx), _stream())
+    return vals, idx
+
+
+def topk_merge(vals, idx):
+    """[W,Q,k] per-shard lists -> global [Q,k]."""
+    _req_cuda(vals, idx)
+    vals, idx = _f32c(vals), idx.to(torch.int32).contiguous()
+    W, Q, k = vals.shape
+    ov = torch.empty(Q, k, dtype=torch.float32, device=vals.device)
+    oi = torch.empty(Q, k, dtype=torch.int32, device=vals.device)
+    _call("nr_topk_merge", _p(vals), _p(idx), W, Q, k, _p(ov), _p(oi), _stream())
+    return ov, oi

@@ -1,0 +1,192 @@
+"""GPU parity tests proper: the CUDA head (through the C ABI) against the oracle on identical seeded inputs and
+against the committed golden fixtures generated from the reference.  Tolerances are written where used:
+  fp32 mode  : S abs 2e-6; losses rel 1e-4 (north_star), measured ~1e-6; gradients rel-L2 1e-4
+  top-k sets and R@K ranks: bit-exact when derived from the same fp32 similarity matrix."""
+import numpy as np
+import pytest
+import torch
+
+from neighborretr_b200 import synth
+from oracle import head as O
+from oracle import metrics as OM
+from oracle.gen_golden import CASES, make_case
+
+from helpers import LOG100, cuda_losses, load_golden, make_head, oracle_losses, rel_l2, set_bank
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(t):
+    return t.cuda()
+
+
+@pytest.mark.parametrize("name", ["small", "small_k8", "cfg1"])
+def test_local_level_fp32(name):
+    c = CASES[name]
+    gold = load_golden(name)
+    h, bank, params, cfg = make_case(c)
+    m = make_head(c["d"], cfg, params, "fp32")
+    hd = h.to("cuda")
+    with torch.no_grad():
+        s, st = m.local_level(hd.text_feat, hd.video_feat, hd.text_mask, hd.video_mask)
+        mb, _ = m.local_level(hd.text_feat, _dev(bank.mb_feat_v), hd.text_mask, _dev(bank.mb_mask_v))
+        _, mb2 = m.local_level(_dev(bank.mb_feat_t), hd.video_feat, _dev(bank.mb_mask_t), hd.video_mask)
+    np.testing.assert_allclose(s.cpu().numpy(), gold["S"], rtol=1e-5, atol=2e-6)
+    assert torch.equal(st, s.t())
+    np.testing.assert_allclose(mb.cpu().numpy(), gold["mb_t2v"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(mb2.cpu().numpy(), gold["mb_v2t"], rtol=1e-5, atol=2e-6)
+
+
+def test_local_level_act_shaped():
+    gold = load_golden("act_piece")
+    c = dict(b=24, nt=64, nv=64, d=512, m=8, k=20)
+    h, bank, params, cfg = make_case(c)
+    m = make_head(c["d"], cfg, params, "fp32")
+    hd = h.to("cuda")
+    with torch.no_grad():
+        s, _ = m.local_level(hd.text_feat, hd.video_feat, hd.text_mask, hd.video_mask)
+    np.testing.assert_allclose(s.cpu().numpy(), gold["S"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["small", "small_k8"])
+def test_loss_modules_standalone(name):
+    """Each loss module on the SAME fp32 matrices as the oracle: values, gradients, bit-exact top-k set."""
+    from neighborretr_b200 import until_module as U
+    c = CASES[name]
+    gold = load_golden(name)
+    cfg = synth.default_config(num_neighbors=c["k"])
+    S = torch.from_numpy(gold["S"]); G = torch.from_numpy(gold["G"])
+    mb = torch.from_numpy(gold["mb_v2t"]); w = torch.from_numpy(gold["w_t"])
+
+    def both(fn_o, fn_c, *tensors):
+        cpu = [t.clone().requires_grad_(True) for t in tensors]
+        gpu = [t.clone().cuda().requires_grad_(True) for t in tensors]
+        lo = fn_o(*cpu); lo.backward()
+        lc = fn_c(*gpu); lc.backward()
+        assert abs(lc.item() - lo.item()) <= 1e-5 * abs(lo.item()) + 1e-7, (lc.item(), lo.item())
+        for a, b in zip(gpu, cpu):
+            assert rel_l2(a.grad, b.grad) < 1e-4
+        return lc
+
+    both(lambda x, ww: O.centrality_weighting_loss(x * 100.0, ww),
+         lambda x, ww: U.CentralityWeightingLoss()(x * 100.0, ww), S, w)
+    nal = U.NeighborAdjustingLoss()
+    both(lambda x, y: O.neighbor_adjusting_loss(x, y, c["k"], cfg.temperature),
+         lambda x, y: nal(x, y, c["k"], cfg.temperature), S, mb)
+    top = O.neighbor_topk(S, c["k"])
+    assert torch.equal(nal.last_neighbors.cpu().long(), top)          # order and set, bit-exact
+    both(lambda g: O.uniform_regularization_loss(g, cfg.temperature, cfg.beta),
+         lambda g: U.UniformRegularizationLoss()(g, cfg.temperature, cfg.beta), G)
+    both(lambda g, x: O.kl_divergence_loss(g, x), lambda g, x: U.KLDivergenceLoss()(g, x), G, S)
+    t_gpu = U.UniformRegularizationLoss().sinkhorn_algorithm(G.cuda(), cfg.beta, 50)
+    np.testing.assert_allclose(t_gpu.cpu().numpy(), gold["sinkhorn_T"], rtol=1e-4, atol=1e-7)
+
+
+def test_topk_ties_lower_index_wins():
+    from neighborretr_b200 import until_module as U
+    g = torch.Generator().manual_seed(3)
+    S = torch.randint(0, 7, (64, 64), generator=g).float()           # many exact ties
+    mb = torch.randn(64, 16, generator=g)
+    nal = U.NeighborAdjustingLoss()
+    nal(S.cuda(), mb.cuda(), 20, 3.0)
+    assert torch.equal(nal.last_neighbors.cpu().long(), O.neighbor_topk(S, 20))
+
+
+def test_neighbor_loss_needs_k_plus_2():
+    from neighborretr_b200 import until_module as U
+    S = torch.randn(16, 16).cuda()
+    with pytest.raises(IndexError):
+        U.NeighborAdjustingLoss()(S, torch.randn(16, 8).cuda(), 20, 3.0)
+
+
+def test_centrality_weights():
+    c = CASES["small"]
+    gold = load_golden("small")
+    h, bank, params, cfg = make_case(c)
+    m = make_head(c["d"], cfg, params, "fp32")
+    hd = h.to("cuda")
+    ins = [hd.text_feat, hd.video_feat, hd.global_text, hd.global_video]
+    ins = [t.clone().requires_grad_(True) for t in ins]
+    wt, wv = m.compute_centrality_weights(*ins, cfg.centrality_scale)
+    np.testing.assert_allclose(wt.detach().cpu().numpy(), gold["w_t"], rtol=1e-5)
+    np.testing.assert_allclose(wv.detach().cpu().numpy(), gold["w_v"], rtol=1e-5)
+    (wt.sum() * 2 + (wv * wv).sum()).backward()
+    cpu = [t.detach().cpu().clone().requires_grad_(True) for t in ins]
+    owt, owv = O.centrality_weights(*cpu, cfg.centrality_scale)
+    (owt.sum() * 2 + (owv * owv).sum()).backward()
+    for a, b in zip(ins, cpu):
+        assert rel_l2(a.grad, b.grad) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["small", "small_k8", "cfg1"])
+def test_compute_losses_fp32(name):
+    """Full head fwd+bwd in fp32 mode vs golden (reference) losses and oracle gradients."""
+    c = CASES[name]
+    gold = load_golden(name)
+    h, bank, params, cfg = make_case(c)
+    m = make_head(c["d"], cfg, params, "fp32")
+    set_bank(m, bank)
+    losses, grads = cuda_losses(m, h, cfg)
+    np.testing.assert_allclose(losses.numpy(), gold["losses"], rtol=1e-4)        # north_star: 1e-4 in fp32
+    _, ograds = oracle_losses(h, bank, params, cfg)
+    for k in ograds:
+        tol = 1e-4 if k != "logit_scale" else 1e-4
+        assert rel_l2(grads[k], ograds[k]) < tol, (k, rel_l2(grads[k], ograds[k]))
+    np.testing.assert_allclose(grads["logit_scale"].item(), gold["g_logit_scale"], rtol=1e-4)
+    # top-k neighbour sets used inside the head equal the reference's mask (same fp32 matrix up to 1e-6: the
+    # synthetic rows have no near-ties at that level)
+    n1 = m.last_neighbors[0].cpu().long()
+    mask = torch.zeros(c["b"], c["b"], dtype=torch.uint8).scatter_(1, n1, 1)
+    assert np.array_equal(mask.numpy(), gold["nbr_mask"])
+
+
+def test_eval_similarity_and_metrics():
+    from neighborretr_b200.evaluator import _run_on_single_gpu
+    from neighborretr_b200.metrics import RetrievalMetrics
+    gold = load_golden("eval")
+    c = dict(b=100, nt=8, nv=6, d=64, m=8, k=20)
+    h, bank, params, cfg = make_case(c)
+    m = make_head(c["d"], cfg, params, "fp32").eval()
+    hd = h.to("cuda")
+    sim, sim_t = _run_on_single_gpu(m, hd.text_mask, hd.video_mask[:70], hd.text_feat, hd.video_feat[:70])
+    assert isinstance(sim, np.ndarray) and sim.dtype == np.float32 and sim.shape == (100, 70)
+    assert sim_t.shape == (70, 100)
+    np.testing.assert_allclose(sim, gold["sim_100x70"], rtol=1e-5, atol=2e-6)
+    for k in ("rand", "ties", "sim"):
+        r = RetrievalMetrics.compute_metrics(gold[f"{k}_mat"])
+        assert r["cols"] == gold[f"{k}_cols"].tolist()                           # bit-exact ranks
+        got = np.asarray([r["R1"], r["R5"], r["R10"], r["R50"], r["MR"], r["MedianR"], r["MeanR"]])
+        np.testing.assert_array_equal(got, gold[f"{k}_scalars"])
+
+
+def test_memory_bank_fifo():
+    gold = load_golden("bank")
+    c = dict(b=6, nt=4, nv=3, d=8)
+    cfg = synth.default_config()
+    m = make_head(c["d"], cfg, synth.make_mlp_params(d=c["d"]), "fp32")
+    for step in range(4):
+        h = synth.make_batch(c["b"], c["nt"], c["nv"], d=c["d"], seed=50 + step, rank=step).to("cuda")
+        if step == 1:
+            set_bank(m, synth.make_bank(14, c["nt"], c["nv"], d=c["d"]))
+        m.update_memory_bank(h.idx, h.text_feat, h.video_feat, h.text_mask, h.video_mask)
+        assert np.array_equal(m.mb_ind.cpu().numpy(), gold[f"ind_{step}"])
+        assert np.array_equal(m.mb_feat_v.cpu().numpy(), gold[f"feat_v_{step}"])
+        assert np.array_equal(m.mb_mask_t.cpu().numpy(), gold[f"mask_t_{step}"])
+
+
+def test_topk_merge_matches_global_topk():
+    from neighborretr_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    S = torch.randint(0, 50, (37, 400), generator=g).float().cuda()             # ties across shards
+    W, k = 4, 10
+    parts = [ops.topk_rows(S[:, i * 100:(i + 1) * 100].contiguous(), k, col_offset=i * 100) for i in range(W)]
+    v, i = ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    ref_i = torch.sort(S.cpu(), dim=1, descending=True, stable=True)[1][:, :k]
+    assert torch.equal(i.cpu().long(), ref_i)
+    assert torch.equal(v.cpu(), torch.gather(S.cpu(), 1, ref_i))
+
+
+def test_no_cpu_fallback():
+    from neighborretr_b200 import until_module as U
+    with pytest.raises(RuntimeError):
+        U.KLDivergenceLoss()(torch.randn(8, 8), torch.randn(8, 8))
