@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the retrieval head: head fwd+bwd steps/s (BASELINE.json metric) on synthetic
+MSR-VTT-shaped embeddings, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape msrvtt|activitynet]
+
+A step = gather (N>1) + local/global similarity + the four losses + backward to the features, the token-weight
+MLPs and logit_scale + memory-bank FIFO update, on one batch of b=128 samples per GPU.  `value` times steps with
+inputs resident in HBM; `e2e` times the same step through the public module API from pinned HOST buffers with
+the H2D copies and the D2H read of the losses inside the timed region.  L2 is flushed between timed steps.
+`--impl reference` times the oracle port of the reference head (oracle/head.py) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from neighborretr_b200 import synth  # noqa: E402
+
+B_PER_GPU = 128
+D = 512
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    source="MEASURED_PEAKS.json")
+    except Exception:
+        return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback(B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def flops_maxsim(rx, ry, nt, nv, d=D):
+    return 2.0 * rx * ry * nt * nv * d
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(shape, steps, warmup, b=B_PER_GPU):
+    from oracle import head as O
+    nt, nv, mrows = synth.SHAPES[shape]
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    h = synth.make_batch(b, nt, nv, d=D, seed=1234)
+    bank = synth.make_bank(mrows, nt, nv, d=D)
+    params = synth.make_mlp_params(d=D)
+    cfg = synth.default_config()
+    lsp = torch.tensor(float(torch.log(torch.tensor(100.0))), requires_grad=True)
+
+    def step():
+        text = h.text_feat.clone().requires_grad_(True)
+        video = h.video_feat.clone().requires_grad_(True)
+        gt = h.global_text.clone().requires_grad_(True)
+        gv = h.global_video.clone().requires_grad_(True)
+        p = {k: {n: v.clone().requires_grad_(True) for n, v in sd.items()} for k, sd in params.items()}
+        losses = O.compute_losses(text, video, h.text_mask, h.video_mask, bank.mb_feat_t, bank.mb_feat_v,
+                                  bank.mb_mask_t, bank.mb_mask_v, gt, gv, p, lsp.exp(), cfg)
+        losses[0].backward()
+        return float(losses[0])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nt, nv, mrows = synth.SHAPES[args.shape]
+    steps = max(1, min(args.steps, 8))
+    warm = max(1, min(args.warmup, 2))
+    sps, ms, threads = cpu_reference_steps(args.shape, steps, warm)
+    line = {
+        "impl": "reference", "metric": "head_fwd_bwd_steps_per_s", "value": sps, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.shape, 1, "fp32"),
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} fwd+bwd steps of oracle/head.py compute_losses (torch CPU, fp32), "
+                                   f"b={B_PER_GPU}, single-process batch (no gather)"},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(shape, world, precision):
+    nt, nv, mrows = synth.SHAPES[shape]
+    return {"workload": f"{shape}_head_b{B_PER_GPU}_per_gpu", "per_gpu_batch": B_PER_GPU,
+            "global_batch": B_PER_GPU * world, "words": nt, "frames": nv, "dim": D, "memory_rows": mrows,
+            "num_neighbors": 20, "sinkhorn_iters": 50, "precision": precision,
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"dp{world}"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from neighborretr_b200 import ops
+    from neighborretr_b200.modeling import NeighborRetr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nt, nv, mrows = synth.SHAPES[args.shape]
+    cfg = synth.default_config(world_size=world, local_rank=local, rank=rank)
+    model = NeighborRetr(cfg, width=D)
+    for name, sd in synth.make_mlp_params(d=D).items():
+        getattr(model, name).load_state_dict(sd)
+    model.clip.logit_scale.data.fill_(float(torch.log(torch.tensor(100.0))))
+    model.head_precision = args.precision
+    model = model.to(dev).train()
+    bank = synth.make_bank(mrows, nt, nv, d=D)
+    host = synth.make_batch(B_PER_GPU, nt, nv, d=D, seed=1234, rank=rank)
+    pinned = {f: getattr(host, f).pin_memory() for f in host.__dataclass_fields__}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_host = torch.empty(5, dtype=torch.float32).pin_memory()
+
+    def reset_bank():
+        model.mb_ind = bank.mb_ind.to(dev); model.mb_feat_t = bank.mb_feat_t.to(dev)
+        model.mb_feat_v = bank.mb_feat_v.to(dev); model.mb_mask_t = bank.mb_mask_t.to(dev)
+        model.mb_mask_v = bank.mb_mask_v.to(dev); model.mb_batch = mrows
+
+    reset_bank()
+
+    def step(src, from_host):
+        if from_host:
+            t = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
+        else:
+            t = src
+        text = t["text_feat"].detach().requires_grad_(True)
+        video = t["video_feat"].detach().requires_grad_(True)
+        gt = t["global_text"].detach().requires_grad_(True)
+        gv = t["global_video"].detach().requires_grad_(True)
+        model.zero_grad(set_to_none=True)
+        losses = model.head_forward(text, video, t["text_mask"], t["video_mask"], t["idx"], global_feats=(gt, gv))
+        losses[0].backward()
+        if from_host:
+            loss_host.copy_(torch.stack([x.detach() for x in losses]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return losses
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(src, from_host, steps, profile=None):
+        evs = []
+        sync_all()
+        for _ in range(steps):
+            flush_buf.fill_(1)                         # L2 flush, outside the timed window
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            step(src, from_host)
+            e.record()
+            evs.append((s, e))
+        sync_all()
+        tot = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.LAUNCHES["count"] = 0
+    ops.KERNEL_TIMER.enable("nr_maxsim_fwd")
+    ms_total = timed(resident, False, args.steps)
+    launches = ops.LAUNCHES["count"]
+    kt = ops.KERNEL_TIMER.collect()
+    ops.KERNEL_TIMER.disable()
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step(pinned, True)
+    ms_e2e = timed(pinned, True, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    B = B_PER_GPU * world
+    pk = peaks()
+    # dominant kernel = nr_maxsim_fwd (6 launches / step): algorithmic flops 2*Rx*Ry*Nt*Nv*D per launch,
+    # every S / bank entry needs both orientations, each launch is one orientation => half of the pair's flops
+    flops_step = 0.5 * 2 * (flops_maxsim(B, B, nt, nv) + 2 * flops_maxsim(B, mrows, nt, nv))
+    n_l = max(kt["launches"], 1)
+    achieved = flops_step * args.steps / (kt["ms"] * 1e-3) / 1e12 if kt["ms"] > 0 else 0.0
+    peak = pk["bf16_sustained"]
+    line = {
+        "metric": "head_fwd_bwd_steps_per_s", "value": args.steps / (ms_total * 1e-3), "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(args.shape, world, args.precision),
+        "samples_per_s": args.steps * B / (ms_total * 1e-3),
+        "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "nr_maxsim_fwd", "bound": "tensor", "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "launches_timed": n_l, "avg_launch_ms": kt["ms"] / n_l,
+                     "share_of_step": kt["ms"] / ms_total if ms_total else None,
+                     "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside the step)"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sps, ms, threads = cpu_reference_steps(args.shape, 4, 1)
+        line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
+                                "sample": "4 fwd+bwd steps (after 1 warm-up) of oracle/head.py compute_losses on the "
+                                          f"same {args.shape} b={B_PER_GPU} batch, torch CPU fp32"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="msrvtt", choices=list(synth.SHAPES))
+    ap.add_argument("--precision", default=os.environ.get("NR_HEAD_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

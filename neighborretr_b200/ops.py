@@ -46,8 +46,37 @@ def _mask(t):
     return t.contiguous()
 
 
+class _KernelTimer:
+    """CUDA-event timing of one C-ABI entry point on the launching stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.name, self.events = None, []
+
+    def enable(self, name):
+        self.name, self.events = name, []
+
+    def disable(self):
+        self.name, self.events = None, []
+
+    def collect(self):
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in self.events)
+        return {"ms": ms, "launches": len(self.events)}
+
+
+KERNEL_TIMER = _KernelTimer()
+
+
 def _call(name, *args, launches=1):
-    rc = getattr(_lib.load(), name)(*args)
+    fn = getattr(_lib.load(), name)
+    if KERNEL_TIMER.name == name:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        KERNEL_TIMER.events.append((e0, e1))
+    else:
+        rc = fn(*args)
     check(rc, name)
     LAUNCHES["count"] += launches
 

@@ -130,8 +130,10 @@ def test_compute_losses_fp32(name):
     np.testing.assert_allclose(losses.numpy(), gold["losses"], rtol=1e-4)        # north_star: 1e-4 in fp32
     _, ograds = oracle_losses(h, bank, params, cfg)
     for k in ograds:
-        tol = 1e-4 if k != "logit_scale" else 1e-4
-        assert rel_l2(grads[k], ograds[k]) < tol, (k, rel_l2(grads[k], ograds[k]))
+        if k.endswith("2.bias"):      # softmax is shift-invariant: this gradient is identically 0 (+- rounding)
+            assert grads[k].abs().max() < 1e-6 and ograds[k].abs().max() < 1e-6
+            continue
+        assert rel_l2(grads[k], ograds[k]) < 1e-4, (k, rel_l2(grads[k], ograds[k]))
     np.testing.assert_allclose(grads["logit_scale"].item(), gold["g_logit_scale"], rtol=1e-4)
     # top-k neighbour sets used inside the head equal the reference's mask (same fp32 matrix up to 1e-6: the
     # synthetic rows have no near-ties at that level)
