@@ -54,8 +54,8 @@ def build(force=False, verbose=False):
         fail |= p.returncode != 0
     if fail:
         raise RuntimeError("nvcc failed; see output above")
-    cmd = [nvcc, "-shared", "-o", LIB + ".tmp", *objs, "-lcudart", "-lcuda",
-           "-L/usr/local/cuda/lib64/stubs", "-L/usr/local/cuda/lib64"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB + ".tmp", *objs, "-lcudart",
+           "-L/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
     os.replace(LIB + ".tmp", LIB)
     return LIB

@@ -1,12 +1,313 @@
-// placeholder until the tcgen05 kernels land (next commit)
+// Masked max-sim late interaction on the 5th-gen tensor cores (NR_PREC_BF16).
+//
+//   H[rx, ry] = sum_x wx[rx,x] * max_y ( <xn[rx,x,:], yn[ry,y,:]> * mx[rx,x] * my[ry,y] )
+//
+// (one direction of NeighborRetr.local_level, reference NeighborRetr/models/modeling.py:499-509; the
+// reference materialises the 4-D [A,B,Nt,Nv] fp32 tensor and makes >= 7 passes over it.)
+//
+// Persistent warp-specialised kernel, one CTA per SM:
+//   warp 0      TMA producer: {64 x rows} bf16 boxes of X and Y tokens, 128B swizzle, 4-stage mbarrier ring
+//   warp 1      tcgen05.mma issuer (one elected lane), M=128 x N<=256 x K=16, fp32 accumulators in TMEM,
+//               two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2..5  epilogue: tcgen05.ld one accumulator row per thread (row = one X token), masked running
+//               max / arg-max over the Ny columns of each Y sample in registers, token-weighted partial to
+//               shared memory, segmented sum over the Nx rows of each X sample -> H.  Only H, pmax and the
+//               arg-max bytes leave the SM: the token-pair tensor never exists in HBM.
+// A tile is SX whole X samples (SX*Nx <= 128 rows; rows up to 128 are don't-care) by SY whole Y samples
+// (SY*Ny <= 256 columns), so every max / sum segment is tile-local.
+// Roofline: tensor pipe.  Algorithmic flops per launch 2*Rx*Nx*Ry*Ny*D; executed: 128/(SX*Nx) more.
 #include "common.cuh"
 #include "nrhead_internal.h"
-int nr_maxsim_fwd_tc(const void*, const void*, const float*, const int64_t*, const int64_t*, int64_t, int64_t,
-                     int64_t, int64_t, int64_t, float, float*, int64_t, int64_t, float*, int64_t, int64_t, int,
-                     float*, uint8_t*, cudaStream_t) {
-  nr::set_error("nr_maxsim_fwd: NR_PREC_BF16 not built");
-  return -2;
+#include "tc_common.cuh"
+
+namespace nr {
+using namespace tc;
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * 128;    // 16 KB
+constexpr int TC_ACC_COLS = 256;           // TMEM columns per accumulator stage
+
+struct TcFwdArgs {
+  const float* wx; const int64_t* mx; const int64_t* my;
+  int Rx, Nx, Ry, Ny;
+  float alpha;
+  float* out; int64_t out_sr, out_sc; float* out2; int64_t out2_sr, out2_sc; int accumulate;
+  float* pmax; uint8_t* ystar;
+  int SX, SY, MU, UN;                      // samples per tile, used rows, UMMA N (multiple of 16)
+  int n_mt, n_nt, num_kb, stages, b_bytes; // tiles, k-blocks, pipeline depth, bytes of one B stage
+  int hp_ld;                               // leading dimension (floats) of the weighted-partial buffer
+};
+
+template <int NY>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+maxsim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+                     const TcFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] [hp 2 x 128 x hp_ld floats] [cmask 2 x 256] [barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = TC_A_BYTES + a.b_bytes;
+  float* hp = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes);
+  uint64_t* cmask = reinterpret_cast<uint64_t*>(hp + 2 * TC_BM * a.hp_ld);   // [2][64] bit y = my[ry, y]
+  uint64_t* bars = cmask + 2 * 64;
+  uint64_t* full = bars;                          // [stages]  TMA -> MMA
+  uint64_t* empty = bars + TC_MAX_STAGES;         // [stages]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * TC_MAX_STAGES;     // [2]       MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                   // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = a.n_mt * a.n_nt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmy);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(a.MU + a.SY * NY) * 128u;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int mt = tile / a.n_nt, nt = tile % a.n_nt;
+        const int row_x = mt * a.SX * a.Nx, row_y = nt * a.SY * NY;
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(full + stage, tx_bytes);
+          tma_load_2d(sa, &tmx, full + stage, kb * TC_BK, row_x);
+          tma_load_2d(sa + TC_A_BYTES, &tmy, full + stage, kb * TC_BK, row_y);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, a.UN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty + acc, acc_phase ^ 1);          // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_ACC_COLS);
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)           // advance 32 B (16 bf16) inside the swizzle row
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit(empty + stage);                    // smem slot free when these MMAs retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull + acc);                        // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                         // accumulator row = X token of the tile
+    const int et = threadIdx.x - 64;                     // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile / a.n_nt, nt = tile % a.n_nt;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int ry0 = nt * a.SY;
+      const int sy_n = min(a.SY, a.Ry - ry0);
+      uint64_t* cm = cmask + acc * 64;
+      float* hpb = hp + (size_t)acc * TC_BM * a.hp_ld;
+      // column masks of this tile, one bit per Y token
+      if (et < sy_n) {
+        uint64_t bits = 0;
+        if (a.my) {
+          const int64_t* mrow = a.my + (int64_t)(ry0 + et) * NY;
+#pragma unroll
+          for (int y = 0; y < NY; ++y) bits |= (uint64_t)(mrow[y] != 0) << y;
+        } else {
+          bits = ~0ull;
+        }
+        cm[et] = bits;
+      }
+      const int sx = r / a.Nx, x = r - sx * a.Nx;
+      const int rx = mt * a.SX + sx;
+      const bool row_ok = (r < a.MU) && (rx < a.Rx);
+      const bool mxv = row_ok && (a.mx ? (a.mx[(int64_t)rx * a.Nx + x] != 0) : true);
+      const float wxv = row_ok ? a.wx[(int64_t)rx * a.Nx + x] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS);
+      for (int sy = 0; sy < sy_n; ++sy) {
+        uint32_t v[NY];
+        tmem_ld_cols<NY>(taddr + (uint32_t)(sy * NY), v);
+        tmem_ld_wait();
+        reg_fence<NY>(v);
+        float best = NR_NEG_INF;
+        int bi = 0;
+        const uint64_t mb = cm[sy];
+#pragma unroll
+        for (int y = 0; y < NY; ++y) {
+          float f = ((mb >> y) & 1ull) ? __uint_as_float(v[y]) : 0.f;      // masked pairs are exactly 0
+          if (f > best) { best = f; bi = y; }
+        }
+        if (!mxv) { best = 0.f; bi = 0; }
+        hpb[r * a.hp_ld + sy] = wxv * best;
+        if (row_ok) {
+          const int64_t o = ((int64_t)rx * a.Ry + (ry0 + sy)) * a.Nx + x;
+          if (a.pmax) a.pmax[o] = best;
+          if (a.ystar) a.ystar[o] = (uint8_t)bi;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty + acc);                         // TMEM stage may be overwritten
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // segmented sum over the Nx rows of each X sample
+      for (int e = et; e < a.SX * sy_n; e += 128) {
+        const int s = e / sy_n, sy = e - s * sy_n;
+        const int rxx = mt * a.SX + s;
+        if (rxx < a.Rx) {
+          float h = 0.f;
+          for (int xx = 0; xx < a.Nx; ++xx) h += hpb[(s * a.Nx + xx) * a.hp_ld + sy];
+          h *= a.alpha;
+          const int ry = ry0 + sy;
+          float* p = a.out + (int64_t)rxx * a.out_sr + (int64_t)ry * a.out_sc;
+          *p = a.accumulate ? (*p + h) : h;
+          if (a.out2) {
+            float* p2 = a.out2 + (int64_t)rxx * a.out2_sr + (int64_t)ry * a.out2_sc;
+            *p2 = a.accumulate ? (*p2 + h) : h;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
 }
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, d] -> boxes of {64 elements, box_rows} with the 128B swizzle
+int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t d, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  NR_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NR_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld d=%lld box_rows=%d", (int)r,
+               (long long)rows, (long long)d, box_rows);
+  return 0;
+}
+
+template <int NY>
+static int launch_fwd(const CUtensorMap& tmx, const CUtensorMap& tmy, const TcFwdArgs& a, size_t smem, int grid,
+                      cudaStream_t stream) {
+  NR_CUDA(cudaFuncSetAttribute(maxsim_fwd_tc_kernel<NY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  maxsim_fwd_tc_kernel<NY><<<grid, TC_THREADS, smem, stream>>>(tmx, tmy, a);
+  NR_CHECK_LAUNCH("nr_maxsim_fwd(bf16)");
+  return 0;
+}
+
+}  // namespace nr
+
+using namespace nr;
+
+int nr_maxsim_fwd_tc(const void* xn, const void* yn, const float* wx, const int64_t* mx, const int64_t* my,
+                     int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float alpha, float* out,
+                     int64_t out_sr, int64_t out_sc, float* out2, int64_t out2_sr, int64_t out2_sc, int accumulate,
+                     float* pmax, uint8_t* ystar, cudaStream_t stream) {
+  NR_CHECK_ARG(d % TC_BK == 0, "nr_maxsim_fwd(bf16): d=%lld must be a multiple of %d", (long long)d, TC_BK);
+  NR_CHECK_ARG(Ny % 4 == 0, "nr_maxsim_fwd(bf16): Ny=%lld must be a multiple of 4", (long long)Ny);
+  NR_CHECK_ARG(((uintptr_t)xn & 15) == 0 && ((uintptr_t)yn & 15) == 0, "nr_maxsim_fwd(bf16): operands must be 16B aligned");
+  TcFwdArgs a{};
+  a.wx = wx; a.mx = mx; a.my = my;
+  a.Rx = (int)Rx; a.Nx = (int)Nx; a.Ry = (int)Ry; a.Ny = (int)Ny;
+  a.alpha = alpha;
+  a.out = out; a.out_sr = out_sr; a.out_sc = out_sc; a.out2 = out2; a.out2_sr = out2_sr; a.out2_sc = out2_sc;
+  a.accumulate = accumulate; a.pmax = pmax; a.ystar = ystar;
+  a.SX = TC_BM / (int)Nx;
+  if (a.SX > Rx) a.SX = (int)Rx;
+  a.MU = a.SX * (int)Nx;
+  a.SY = 256 / (int)Ny;
+  if (a.SY > Ry) a.SY = (int)Ry;
+  a.UN = (a.SY * (int)Ny + 15) / 16 * 16;
+  a.n_mt = (int)((Rx + a.SX - 1) / a.SX);
+  a.n_nt = (int)((Ry + a.SY - 1) / a.SY);
+  a.num_kb = (int)(d / TC_BK);
+  a.b_bytes = (a.UN * 128 + 1023) / 1024 * 1024;
+  a.hp_ld = a.SY | 1;
+  const size_t tail = (size_t)2 * TC_BM * a.hp_ld * sizeof(float) + 2 * 64 * 8 + 256;
+  const size_t budget = 227 * 1024 - 1024;   // alignment slack
+  int stages = (int)((budget - tail) / (size_t)(TC_A_BYTES + a.b_bytes));
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  NR_CHECK_ARG(stages >= 2, "nr_maxsim_fwd(bf16): tile does not fit shared memory");
+  a.stages = stages;
+  const size_t smem = (size_t)stages * (TC_A_BYTES + a.b_bytes) + tail + 1024;
+  CUtensorMap tmx, tmy;
+  if (int e = make_tmap_bf16(&tmx, xn, Rx * Nx, d, a.MU)) return e;
+  if (int e = make_tmap_bf16(&tmy, yn, Ry * Ny, d, a.SY * (int)Ny)) return e;
+  int dev = 0, sms = 0;
+  NR_CUDA(cudaGetDevice(&dev));
+  NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int grid = a.n_mt * a.n_nt < sms ? a.n_mt * a.n_nt : sms;
+  switch (Ny) {
+    case 4: return launch_fwd<4>(tmx, tmy, a, smem, grid, stream);
+    case 8: return launch_fwd<8>(tmx, tmy, a, smem, grid, stream);
+    case 12: return launch_fwd<12>(tmx, tmy, a, smem, grid, stream);
+    case 16: return launch_fwd<16>(tmx, tmy, a, smem, grid, stream);
+    case 24: return launch_fwd<24>(tmx, tmy, a, smem, grid, stream);
+    case 32: return launch_fwd<32>(tmx, tmy, a, smem, grid, stream);
+    case 48: return launch_fwd<48>(tmx, tmy, a, smem, grid, stream);
+    case 64: return launch_fwd<64>(tmx, tmy, a, smem, grid, stream);
+    default:
+      nr::set_error("nr_maxsim_fwd(bf16): Ny=%lld has no tensor-core instantiation (4,8,12,16,24,32,48,64)",
+                    (long long)Ny);
+      return -3;
+  }
+}
+
 int nr_maxsim_bwd_tc(int, const void*, const float*, const int64_t*, const int64_t*, const uint8_t*, const float*,
                      int64_t, int64_t, float, int64_t, int64_t, int64_t, int64_t, int64_t, float*, cudaStream_t) {
   nr::set_error("nr_maxsim_bwd: NR_PREC_BF16 not built");
