@@ -173,6 +173,7 @@ def run_ours(args):
         getattr(model, name).load_state_dict(sd)
     model.clip.logit_scale.data.fill_(float(torch.log(torch.tensor(100.0))))
     model.head_precision = args.precision
+    model.head_bwd_precision = args.bwd_precision or args.precision
     model = model.to(dev).train()
     bank = synth.make_bank(mrows, nt, nv, d=D)
     host = synth.make_batch(B_PER_GPU, nt, nv, d=D, seed=1234, rank=rank)
@@ -291,7 +292,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="msrvtt", choices=list(synth.SHAPES))
-    ap.add_argument("--precision", default=os.environ.get("NR_HEAD_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("NR_HEAD_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--bwd-precision", default=os.environ.get("NR_HEAD_BWD_PRECISION"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -70,15 +70,21 @@ int nr_maxsim_fwd(int precision, const void* xn, const void* yn, const float* wx
                   const int64_t* my, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float alpha,
                   float* out, int64_t out_sr, int64_t out_sc, float* out2, int64_t out2_sr, int64_t out2_sc,
                   int accumulate, float* pmax, uint8_t* ystar, void* stream);
+/* bf16 operand copy [rows, d] -> transposed [d, ld] (ld >= rows, multiple of 8): the K-major source
+ * operand of the tensor-core backward contractions. */
+int nr_transpose_tokens_bf16(const void* xn_bf16, int64_t rows, int64_t d, void* out, int64_t ld, void* stream);
 /* backward of nr_maxsim_fwd w.r.t. the X tokens ("gather"):
  *   dxn[rx,x,:] += mx*wx[rx,x] * sum_ry dH[rx,ry] * my[ry,y*] * yn[ry,y*,:]
- * dH is read as dH[rx*dh_sr + ry*dh_sc] * dh_scale. */
-int nr_maxsim_bwd_x(int precision, const void* yn, const float* wx, const int64_t* mx, const int64_t* my,
+ * dH is read as dH[rx*dh_sr + ry*dh_sc] * dh_scale.
+ * NR_PREC_FP32: yn = f32 tokens [Ry,Ny,d], src_ld ignored.
+ * NR_PREC_BF16: yn = TRANSPOSED bf16 tokens [d, src_ld] (nr_transpose_tokens_bf16); dxn must be zero- or
+ * partially-filled fp32: partial products are combined with float atomics (red.global.add). */
+int nr_maxsim_bwd_x(int precision, const void* yn, int64_t src_ld, const float* wx, const int64_t* mx, const int64_t* my,
                     const uint8_t* ystar, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale,
                     int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dxn, void* stream);
 /* ... w.r.t. the Y tokens ("scatter"):
  *   dyn[ry,y,:] += my[ry,y] * sum_rx dH[rx,ry] * sum_{x: y*(rx,ry,x)=y} mx*wx[rx,x] * xn[rx,x,:] */
-int nr_maxsim_bwd_y(int precision, const void* xn, const float* wx, const int64_t* mx, const int64_t* my,
+int nr_maxsim_bwd_y(int precision, const void* xn, int64_t src_ld, const float* wx, const int64_t* mx, const int64_t* my,
                     const uint8_t* ystar, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale,
                     int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dyn, void* stream);
 /* ... w.r.t. the token weights: dwx[rx,x] += sum_ry dH[rx,ry] * pmax[rx,ry,x] */

@@ -27,8 +27,9 @@ SIGNATURES = {
     "nr_prep_tokens_bwd": (_I, [_P, _P, _P, _P, _I64, _I64, _P, _I, _P]),
     "nr_maxsim_fwd": (_I, [_I, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _P, _I64, _I64, _P, _I64,
                            _I64, _I, _P, _P, _P]),
-    "nr_maxsim_bwd_x": (_I, [_I, _P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
-    "nr_maxsim_bwd_y": (_I, [_I, _P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "nr_transpose_tokens_bf16": (_I, [_P, _I64, _I64, _P, _I64, _P]),
+    "nr_maxsim_bwd_x": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "nr_maxsim_bwd_y": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
     "nr_maxsim_bwd_w": (_I, [_P, _P, _I64, _I64, _F, _I64, _I64, _I64, _P, _P]),
     "nr_centrality_fwd": (_I, [_P, _I64, _I64, _P, _I64, _I64, _F, _P, _P, _P, _P, _P]),
     "nr_centrality_bwd": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _P, _I, _P, _P]),

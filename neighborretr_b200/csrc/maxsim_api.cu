@@ -13,7 +13,7 @@ int nr_maxsim_bwd_y_simt(const float*, const float*, const int64_t*, const int64
 int nr_maxsim_fwd_tc(const void*, const void*, const float*, const int64_t*, const int64_t*, int64_t, int64_t,
                      int64_t, int64_t, int64_t, float, float*, int64_t, int64_t, float*, int64_t, int64_t, int,
                      float*, uint8_t*, cudaStream_t);
-int nr_maxsim_bwd_tc(int side, const void*, const float*, const int64_t*, const int64_t*, const uint8_t*,
+int nr_maxsim_bwd_tc(int side, const void*, int64_t, const float*, const int64_t*, const int64_t*, const uint8_t*,
                      const float*, int64_t, int64_t, float, int64_t, int64_t, int64_t, int64_t, int64_t, float*,
                      cudaStream_t);
 
@@ -43,7 +43,7 @@ extern "C" int nr_maxsim_fwd(int precision, const void* xn, const void* yn, cons
   return -1;
 }
 
-extern "C" int nr_maxsim_bwd_x(int precision, const void* yn, const float* wx, const int64_t* mx, const int64_t* my,
+extern "C" int nr_maxsim_bwd_x(int precision, const void* yn, int64_t src_ld, const float* wx, const int64_t* mx, const int64_t* my,
                                const uint8_t* ystar, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale,
                                int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dxn, void* stream) {
   if (int e = check_dims("nr_maxsim_bwd_x", Rx, Nx, Ry, Ny, d)) return e;
@@ -52,13 +52,13 @@ extern "C" int nr_maxsim_bwd_x(int precision, const void* yn, const float* wx, c
     return nr_maxsim_bwd_x_simt((const float*)yn, wx, mx, my, ystar, dH, dh_sr, dh_sc, dh_scale, Rx, Nx, Ry, Ny, d,
                                 dxn, (cudaStream_t)stream);
   if (precision == NR_PREC_BF16)
-    return nr_maxsim_bwd_tc(0, yn, wx, mx, my, ystar, dH, dh_sr, dh_sc, dh_scale, Rx, Nx, Ry, Ny, d, dxn,
+    return nr_maxsim_bwd_tc(0, yn, src_ld, wx, mx, my, ystar, dH, dh_sr, dh_sc, dh_scale, Rx, Nx, Ry, Ny, d, dxn,
                             (cudaStream_t)stream);
   nr::set_error("nr_maxsim_bwd_x: unknown precision %d", precision);
   return -1;
 }
 
-extern "C" int nr_maxsim_bwd_y(int precision, const void* xn, const float* wx, const int64_t* mx, const int64_t* my,
+extern "C" int nr_maxsim_bwd_y(int precision, const void* xn, int64_t src_ld, const float* wx, const int64_t* mx, const int64_t* my,
                                const uint8_t* ystar, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale,
                                int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dyn, void* stream) {
   if (int e = check_dims("nr_maxsim_bwd_y", Rx, Nx, Ry, Ny, d)) return e;
@@ -67,7 +67,7 @@ extern "C" int nr_maxsim_bwd_y(int precision, const void* xn, const float* wx, c
     return nr_maxsim_bwd_y_simt((const float*)xn, wx, mx, my, ystar, dH, dh_sr, dh_sc, dh_scale, Rx, Nx, Ry, Ny, d,
                                 dyn, (cudaStream_t)stream);
   if (precision == NR_PREC_BF16)
-    return nr_maxsim_bwd_tc(1, xn, wx, mx, my, ystar, dH, dh_sr, dh_sc, dh_scale, Rx, Nx, Ry, Ny, d, dyn,
+    return nr_maxsim_bwd_tc(1, xn, src_ld, wx, mx, my, ystar, dH, dh_sr, dh_sc, dh_scale, Rx, Nx, Ry, Ny, d, dyn,
                             (cudaStream_t)stream);
   nr::set_error("nr_maxsim_bwd_y: unknown precision %d", precision);
   return -1;

@@ -308,8 +308,302 @@ int nr_maxsim_fwd_tc(const void* xn, const void* yn, const float* wx, const int6
   }
 }
 
-int nr_maxsim_bwd_tc(int, const void*, const float*, const int64_t*, const int64_t*, const uint8_t*, const float*,
-                     int64_t, int64_t, float, int64_t, int64_t, int64_t, int64_t, int64_t, float*, cudaStream_t) {
-  nr::set_error("nr_maxsim_bwd: NR_PREC_BF16 not built");
-  return -2;
+namespace nr {
+// =================================================================================================
+// backward: dOut[out tokens, d] += C[out tokens, src tokens] * Src[src tokens, d]
+//
+// C is the (at most one non-zero per (token, partner sample)) routing matrix of the max: it is never
+// stored — the generator warps build each [128 x 64] bf16 tile of it in shared memory (128B-swizzled,
+// K-major, exactly the image a TMA load would have produced) from the saved arg-max bytes, dH, the token
+// weights and the masks, and the tensor core multiplies it with TMA-staged tiles of the TRANSPOSED source
+// tokens (srcT [d, tokens], K-major for this product).  fp32 accumulators for all d <= 512 columns of a
+// 128-token output tile fill the whole TMEM (2 x 256 columns); split-K over the source tokens spreads
+// the few output tiles over all SMs and partials are combined with red.global.add.v4.f32.
+//   side 0 ("gather"):  out = X tokens, src = Y tokens,  C[(rx,x),(ry,y)] = g(rx,ry) wx mx my [y == y*(rx,ry,x)]
+//   side 1 ("scatter"): out = Y tokens, src = X tokens,  C[(ry,y),(rx,x)] = same entry, transposed role
+// =================================================================================================
+struct TcBwdArgs {
+  const float* wx; const int64_t* mx; const int64_t* my; const uint8_t* ystar;
+  const float* dH; int64_t dh_sr, dh_sc; float dh_scale;
+  int Rx, Nx, Ry, Ny, D;
+  float* dst;
+  int out_tokens, src_tokens, n_mt, num_kb, KS, kb_per_split, n_half, half_cols, stages;
+};
+
+constexpr int TCB_B_HALF_BYTES = 256 * 128;   // one d-half of a source k-block: 256 rows x 128 B
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int SIDE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+maxsim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const TcBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = TC_A_BYTES + a.n_half * TCB_B_HALF_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
+  uint64_t* b_full = bars;            // [stages] TMA -> MMA
+  uint64_t* a_full = bars + 4;        // [stages] generators -> MMA
+  uint64_t* empty = bars + 8;         // [stages] MMA -> TMA + generators
+  uint64_t* acc_full = bars + 12;     // MMA -> epilogue
+  uint64_t* acc_empty = bars + 13;    // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = a.n_mt * a.KS;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tms);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(b_full + s, 1); mbar_init(a_full + s, 128); mbar_init(empty + s, 1); }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)a.n_half * (uint32_t)a.half_cols * 128u;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int ks = item % a.KS;
+        const int kb0 = ks * a.kb_per_split, kb1 = min(a.num_kb, kb0 + a.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sb = smem + (size_t)stage * stage_bytes + TC_A_BYTES;
+          mbar_expect_tx(b_full + stage, tx_bytes);
+          for (int h = 0; h < a.n_half; ++h)
+            tma_load_2d(sb + h * TCB_B_HALF_BYTES, &tms, b_full + stage, kb * TC_BK, h * 256);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, a.half_cols);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int ks = item % a.KS;
+        const int kb0 = ks * a.kb_per_split, kb1 = min(a.num_kb, kb0 + a.kb_per_split);
+        mbar_wait(acc_empty, (uint32_t)(it & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(a_full + stage, phase);
+          mbar_wait(b_full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          for (int h = 0; h < a.n_half; ++h) {
+            const uint64_t bdesc = umma_desc_kmajor_sw128(sa + TC_A_BYTES + h * TCB_B_HALF_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k)
+              umma_bf16(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty + stage);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ===================== generators + epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                       // row of the output tile / TMEM lane
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    const int No = SIDE == 0 ? a.Nx : a.Ny;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int mt = item / a.KS, ks = item % a.KS;
+      const int kb0 = ks * a.kb_per_split, kb1 = min(a.num_kb, kb0 + a.kb_per_split);
+      const int g = mt * TC_BM + m;                    // global output token
+      const bool valid = g < a.out_tokens;
+      const int ro = valid ? g / No : 0, o = valid ? g - ro * No : 0;   // (sample, token) of the output row
+      float coefx = 0.f;                               // side 0: wx*mx*scale of this X token
+      bool myv = false;                                // side 1: mask of this Y token
+      if (SIDE == 0) {
+        if (valid && (a.mx ? a.mx[g] != 0 : true)) coefx = a.wx[g] * a.dh_scale;
+      } else {
+        myv = valid && (a.my ? a.my[g] != 0 : true);
+      }
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty + stage, phase ^ 1);
+        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        // cooperative zero fill of this warp's 32 rows (512 contiguous bytes per store instruction)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(sa + (q * 32 + i * 4) * 128 + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+        const int t0 = kb * TC_BK;
+        uint8_t* srow = sa + m * 128;
+        if (SIDE == 0) {
+          if (coefx != 0.f) {
+            const int ry_lo = t0 / a.Ny, ry_hi = min(a.Ry - 1, (t0 + TC_BK - 1) / a.Ny);
+            for (int ry = ry_lo; ry <= ry_hi; ++ry) {
+              const int y = a.ystar[((int64_t)ro * a.Ry + ry) * a.Nx + o];
+              const int t = ry * a.Ny + y - t0;
+              if (t >= 0 && t < TC_BK && (a.my ? a.my[(int64_t)ry * a.Ny + y] != 0 : true)) {
+                const float v = a.dH[(int64_t)ro * a.dh_sr + (int64_t)ry * a.dh_sc] * coefx;
+                *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
+                    __float2bfloat16_rn(v);
+              }
+            }
+          }
+        } else {
+          if (myv) {
+            int rx = t0 / a.Nx, x = t0 - rx * a.Nx;
+            const int jmax = min(TC_BK, a.src_tokens - t0);
+            for (int j = 0; j < jmax; ++j) {
+              const int ys = a.ystar[((int64_t)rx * a.Ry + ro) * a.Nx + x];
+              if (ys == o) {
+                const int64_t tx = (int64_t)rx * a.Nx + x;
+                if (a.mx ? a.mx[tx] != 0 : true) {
+                  const float v = a.dH[(int64_t)rx * a.dh_sr + (int64_t)ro * a.dh_sc] * a.dh_scale * a.wx[tx];
+                  *reinterpret_cast<__nv_bfloat16*>(srow + (((j >> 3) ^ (m & 7)) << 4) + (j & 7) * 2) =
+                      __float2bfloat16_rn(v);
+                }
+              }
+              if (++x == a.Nx) { x = 0; ++rx; }
+            }
+          }
+        }
+        fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(a_full + stage);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      // ---- epilogue: TMEM -> red.global.add ----
+      mbar_wait(acc_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      if (kb1 > kb0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* drow = a.dst + (int64_t)g * a.D;
+        for (int c = 0; c < a.D; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)((c >> 8) * 256 + (c & 255)), v);
+          tmem_ld_wait();
+          reg_fence<16>(v);
+          if (valid) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              red_add_v4(drow + c + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                         __uint_as_float(v[e + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// 2-D bf16 [d, ld] (transposed tokens) -> boxes {64 tokens, box_rows d-rows}, 128B swizzle
+static int make_tmap_srcT(CUtensorMap* m, const void* base, int64_t d, int64_t tokens, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  NR_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)tokens, (cuuint64_t)d};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NR_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(srcT) failed (%d) d=%lld tokens=%lld ld=%lld", (int)r,
+               (long long)d, (long long)tokens, (long long)ld);
+  return 0;
+}
+
+// tiled transpose of the bf16 operand copy: in [rows, d] -> out [d, ld]
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int rows, int d,
+                                      __nv_bfloat16* __restrict__ out, int64_t ld) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    int r = r0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+      int c = c0 + j;
+      tile[i][j] = (r < rows && c < d) ? in[(int64_t)r * d + c] : __float2bfloat16_rn(0.f);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
+    int c = c0 + i;
+    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
+      int r = r0 + j;
+      if (c < d && r < rows) out[(int64_t)c * ld + r] = tile[j][i];
+    }
+  }
+}
+
+}  // namespace nr
+
+using namespace nr;
+
+extern "C" int nr_transpose_tokens_bf16(const void* xn_bf16, int64_t rows, int64_t d, void* out, int64_t ld,
+                                        void* stream) {
+  NR_CHECK_ARG(xn_bf16 && out && rows > 0 && d > 0, "nr_transpose_tokens_bf16: bad arguments");
+  NR_CHECK_ARG(ld >= rows && ld % 8 == 0, "nr_transpose_tokens_bf16: ld=%lld must be >= rows and a multiple of 8",
+               (long long)ld);
+  dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((d + 63) / 64)), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xn_bf16, (int)rows, (int)d,
+                                                                 (__nv_bfloat16*)out, ld);
+  NR_CHECK_LAUNCH("nr_transpose_tokens_bf16");
+  return 0;
+}
+
+// side 0: srcT = transposed Y tokens [d, src_ld]; side 1: srcT = transposed X tokens
+int nr_maxsim_bwd_tc(int side, const void* srcT, int64_t src_ld, const float* wx, const int64_t* mx,
+                     const int64_t* my, const uint8_t* ystar, const float* dH, int64_t dh_sr, int64_t dh_sc,
+                     float dh_scale, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dst,
+                     cudaStream_t stream) {
+  NR_CHECK_ARG(d % 16 == 0 && d <= 512 && (d <= 256 || d == 512),
+               "nr_maxsim_bwd(bf16): d=%lld unsupported (multiple of 16 up to 256, or 512)", (long long)d);
+  NR_CHECK_ARG(src_ld % 8 == 0 && ((uintptr_t)srcT & 15) == 0, "nr_maxsim_bwd(bf16): srcT must be 16B aligned, ld %% 8 == 0");
+  TcBwdArgs a{};
+  a.wx = wx; a.mx = mx; a.my = my; a.ystar = ystar; a.dH = dH; a.dh_sr = dh_sr; a.dh_sc = dh_sc; a.dh_scale = dh_scale;
+  a.Rx = (int)Rx; a.Nx = (int)Nx; a.Ry = (int)Ry; a.Ny = (int)Ny; a.D = (int)d; a.dst = dst;
+  a.out_tokens = side == 0 ? (int)(Rx * Nx) : (int)(Ry * Ny);
+  a.src_tokens = side == 0 ? (int)(Ry * Ny) : (int)(Rx * Nx);
+  a.n_mt = (a.out_tokens + TC_BM - 1) / TC_BM;
+  a.num_kb = (a.src_tokens + TC_BK - 1) / TC_BK;
+  a.n_half = d > 256 ? 2 : 1;
+  a.half_cols = d > 256 ? 256 : (int)d;
+  int dev = 0, sms = 0;
+  NR_CUDA(cudaGetDevice(&dev));
+  NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int ks = (sms + a.n_mt / 2) / a.n_mt;           // split-K so that n_mt*KS ~ one wave
+  if (ks < 1) ks = 1;
+  if (ks > a.num_kb) ks = a.num_kb;
+  a.kb_per_split = (a.num_kb + ks - 1) / ks;
+  a.KS = (a.num_kb + a.kb_per_split - 1) / a.kb_per_split;
+  a.stages = 2;
+  const size_t stage_bytes = (size_t)TC_A_BYTES + (size_t)a.n_half * TCB_B_HALF_BYTES;
+  const size_t smem = a.stages * stage_bytes + 256 + 1024;
+  CUtensorMap tms;
+  if (int e = make_tmap_srcT(&tms, srcT, d, a.src_tokens, src_ld, a.half_cols)) return e;
+  const int items = a.n_mt * a.KS;
+  const int grid = items < sms ? items : sms;
+  if (side == 0) {
+    NR_CUDA(cudaFuncSetAttribute(maxsim_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    maxsim_bwd_tc_kernel<0><<<grid, TC_THREADS, smem, stream>>>(tms, a);
+  } else {
+    NR_CUDA(cudaFuncSetAttribute(maxsim_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    maxsim_bwd_tc_kernel<1><<<grid, TC_THREADS, smem, stream>>>(tms, a);
+  }
+  NR_CHECK_LAUNCH("nr_maxsim_bwd(bf16)");
+  return 0;
 }

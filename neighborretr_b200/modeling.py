@@ -27,7 +27,7 @@ from .until_module import (AllGather, AllGather2, CentralityWeightingLoss, KLDiv
 allgather = AllGather.apply
 allgather2 = AllGather2.apply
 
-DEFAULT_PRECISION = os.environ.get("NR_HEAD_PRECISION", "fp32")
+DEFAULT_PRECISION = os.environ.get("NR_HEAD_PRECISION", "bf16")
 
 
 def _token_weights(mlp, feat, mask):

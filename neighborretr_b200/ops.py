@@ -88,13 +88,14 @@ class Prepared:
     """L2-normalised tokens of one modality: fp32 copy (backward / fp32 mode), optional bf16 operand
     copy (tensor-core mode), inverse norms and per-CTA column-sum partials."""
 
-    __slots__ = ("xn", "xn_bf16", "inv_norm", "partials", "rows", "n", "d", "r")
+    __slots__ = ("xn", "xn_bf16", "xnT_bf16", "inv_norm", "partials", "rows", "n", "d", "r")
 
     def __init__(self, x, bf16=False, colsum=False, normalize=True):
         _req_cuda(x)
         x = _f32c(x)
         self.r, self.n, self.d = x.shape
         self.rows = self.r * self.n
+        self.xnT_bf16 = None
         dev = x.device
         if not normalize:        # global_level: raw dot products (reference modeling.py:525), fp32 only
             self.xn, self.xn_bf16, self.inv_norm, self.partials = x, None, None, None
@@ -109,6 +110,17 @@ class Prepared:
 
     def operand(self, prec):
         return self.xn_bf16 if prec == NR_PREC_BF16 else self.xn
+
+    def bwd_source(self, prec):
+        """(pointer tensor, ld) of this modality as the SOURCE operand of a backward contraction: fp32 tokens,
+        or the transposed bf16 copy [d, ld] built on first use."""
+        if prec != NR_PREC_BF16:
+            return self.xn, 0
+        if self.xnT_bf16 is None:
+            ld = (self.rows + 7) // 8 * 8
+            self.xnT_bf16 = torch.empty(self.d, ld, dtype=torch.bfloat16, device=self.xn.device)
+            _call("nr_transpose_tokens_bf16", _p(self.xn_bf16), self.rows, self.d, _p(self.xnT_bf16), ld, _stream())
+        return self.xnT_bf16, self.xnT_bf16.shape[1]
 
     def backward(self, dxn, add_vec=None):
         if self.inv_norm is None:
@@ -181,14 +193,16 @@ class MaxSimFunction(torch.autograd.Function):
         dvw = torch.zeros_like(vw) if need_vw else None
         # direction 1: X = text, Y = video, dH[rx=a, ry=b] = 0.5 g[a,b]
         if need_t:
-            _call("nr_maxsim_bwd_x", prec, _p(V.operand(prec)), _p(tw), _p(tm), _p(vm), _p(y1), _p(g), B, 1, 0.5,
+            vs, vld = V.bwd_source(prec)
+            _call("nr_maxsim_bwd_x", prec, _p(vs), vld, _p(tw), _p(tm), _p(vm), _p(y1), _p(g), B, 1, 0.5,
                   A, T.n, B, V.n, T.d, _p(dtn), st)
-            _call("nr_maxsim_bwd_y", prec, _p(V.operand(prec)), _p(vw), _p(vm), _p(tm), _p(y2), _p(g), 1, B, 0.5,
+            _call("nr_maxsim_bwd_y", prec, _p(vs), vld, _p(vw), _p(vm), _p(tm), _p(y2), _p(g), 1, B, 0.5,
                   B, V.n, A, T.n, T.d, _p(dtn), st)
         if need_v:
-            _call("nr_maxsim_bwd_y", prec, _p(T.operand(prec)), _p(tw), _p(tm), _p(vm), _p(y1), _p(g), B, 1, 0.5,
+            ts, tld = T.bwd_source(prec)
+            _call("nr_maxsim_bwd_y", prec, _p(ts), tld, _p(tw), _p(tm), _p(vm), _p(y1), _p(g), B, 1, 0.5,
                   A, T.n, B, V.n, T.d, _p(dvn), st)
-            _call("nr_maxsim_bwd_x", prec, _p(T.operand(prec)), _p(vw), _p(vm), _p(tm), _p(y2), _p(g), 1, B, 0.5,
+            _call("nr_maxsim_bwd_x", prec, _p(ts), tld, _p(vw), _p(vm), _p(tm), _p(y2), _p(g), 1, B, 0.5,
                   B, V.n, A, T.n, T.d, _p(dvn), st)
         if need_tw:
             _call("nr_maxsim_bwd_w", _p(p1), _p(g), B, 1, 0.5, A, T.n, B, _p(dtw), st)
