@@ -65,7 +65,8 @@ int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* 
  * wx [Rx,Nx] f32, mx [Rx,Nx] / my [Ry,Ny] int64 (nullable = all ones).
  * out[rx*out_sr + ry*out_sc] = alpha*H (+ previous value if accumulate);  out2 likewise (nullable),
  * so S and S^T can be produced by the same launch.
- * pmax [Rx,Ry,Nx] f32 and ystar [Rx,Ry,Nx] u8 (both nullable) keep max / arg-max for backward. */
+ * pmax [Rx,Ry,Nx] f32 and ystar [Rx,Ry,Nx] u8 (both nullable) keep max / arg-max for backward; ystar == 255
+ * marks "no gradient" (masked X token, or the max is a masked pair, which is exactly 0). */
 int nr_maxsim_fwd(int precision, const void* xn, const void* yn, const float* wx, const int64_t* mx,
                   const int64_t* my, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float alpha,
                   float* out, int64_t out_sr, int64_t out_sc, float* out2, int64_t out2_sr, int64_t out2_sc,

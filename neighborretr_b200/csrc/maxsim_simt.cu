@@ -94,11 +94,13 @@ maxsim_fwd_simt_kernel(MaxsimArgs a) {
     const bool mxv = a.mx ? (a.mx[(int64_t)rx * a.Nx + x] != 0) : true;
     float best = NR_NEG_INF;
     int bi = 0;
+    bool bmask = true;
     for (int y = 0; y < a.Ny; ++y) {
       const bool myv = a.my ? (a.my[(int64_t)ry * a.Ny + y] != 0) : true;
       float v = (mxv && myv) ? Rs[x * (NYTP + 1) + cy * a.Ny + y] : 0.f;   // masked pairs are exactly 0
-      if (v > best) { best = v; bi = y; }
+      if (v > best) { best = v; bi = y; bmask = myv; }
     }
+    if (!mxv || !bmask) bi = 255;     // arg-max byte 255 = "no gradient" (masked token / masked winning pair)
     Ps[x * a.CY + cy] = best * a.wx[(int64_t)rx * a.Nx + x];
     int64_t o = ((int64_t)rx * a.Ry + ry) * a.Nx + x;
     if (a.pmax) a.pmax[o] = best;
@@ -142,7 +144,7 @@ maxsim_bwd_x_simt_kernel(MaxsimBwdArgs a) {
   for (int i = 0; i < BX_XT; ++i) {
     int x = x0 + i;
     bool ok = x < a.Nx && (a.mx ? a.mx[(int64_t)rx * a.Nx + x] != 0 : true);
-    coefx[i] = ok ? a.wx[(int64_t)rx * a.Nx + x] : 0.f;
+    coefx[i] = ok ? a.wx[(int64_t)rx * a.Nx + x] : 0.f;   // (masked tokens also carry ystar == 255)
 #pragma unroll
     for (int v = 0; v < BX_MAXV; ++v) acc[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -154,7 +156,7 @@ maxsim_bwd_x_simt_kernel(MaxsimBwdArgs a) {
     for (int i = 0; i < BX_XT; ++i) {
       if (coefx[i] == 0.f) continue;
       const int y = ys[x0 + i];
-      if (a.my && a.my[(int64_t)ry * a.Ny + y] == 0) continue;
+      if (y == 255) continue;
       const float cf = g * coefx[i];
       const float* src = a.src + ((int64_t)ry * a.Ny + y) * d;
 #pragma unroll
@@ -198,9 +200,8 @@ maxsim_bwd_y_simt_kernel(MaxsimBwdArgs a) {
     if (g == 0.f) continue;
     const uint8_t* ys = a.ystar + ((int64_t)rx * a.Ry + ry) * a.Nx;
     for (int x = 0; x < a.Nx; ++x) {
-      if (a.mx && a.mx[(int64_t)rx * a.Nx + x] == 0) continue;
       const int y = ys[x];
-      if (a.my && a.my[(int64_t)ry * a.Ny + y] == 0) continue;
+      if (y == 255) continue;
       const float cf = g * a.wx[(int64_t)rx * a.Nx + x];
       const float* src = a.src + ((int64_t)rx * a.Nx + x) * d;
       float* dstrow = accsm + y * d;

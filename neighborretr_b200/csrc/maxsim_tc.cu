@@ -170,7 +170,9 @@ maxsim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           float f = ((mb >> y) & 1ull) ? __uint_as_float(v[y]) : 0.f;      // masked pairs are exactly 0
           if (f > best) { best = f; bi = y; }
         }
-        if (!mxv) { best = 0.f; bi = 0; }
+        // arg-max byte 255 = "no gradient": masked X token, or the max is a masked (exactly 0) pair
+        if (!mxv) { best = 0.f; bi = 255; }
+        else if (!((mb >> bi) & 1ull)) bi = 255;
         hpb[r * a.hp_ld + sy] = wxv * best;
         if (row_ok) {
           const int64_t o = ((int64_t)rx * a.Ry + (ry0 + sy)) * a.Nx + x;
@@ -428,13 +430,8 @@ maxsim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const TcBwdArgs a)
       const int g = mt * TC_BM + m;                    // global output token
       const bool valid = g < a.out_tokens;
       const int ro = valid ? g / No : 0, o = valid ? g - ro * No : 0;   // (sample, token) of the output row
-      float coefx = 0.f;                               // side 0: wx*mx*scale of this X token
-      bool myv = false;                                // side 1: mask of this Y token
-      if (SIDE == 0) {
-        if (valid && (a.mx ? a.mx[g] != 0 : true)) coefx = a.wx[g] * a.dh_scale;
-      } else {
-        myv = valid && (a.my ? a.my[g] != 0 : true);
-      }
+      float coefx = 0.f;                               // side 0: wx*scale of this X token
+      if (SIDE == 0 && valid) coefx = a.wx[g] * a.dh_scale;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -448,31 +445,52 @@ maxsim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const TcBwdArgs a)
         if (SIDE == 0) {
           if (coefx != 0.f) {
             const int ry_lo = t0 / a.Ny, ry_hi = min(a.Ry - 1, (t0 + TC_BK - 1) / a.Ny);
-            for (int ry = ry_lo; ry <= ry_hi; ++ry) {
-              const int y = a.ystar[((int64_t)ro * a.Ry + ry) * a.Nx + o];
-              const int t = ry * a.Ny + y - t0;
-              if (t >= 0 && t < TC_BK && (a.my ? a.my[(int64_t)ry * a.Ny + y] != 0 : true)) {
-                const float v = a.dH[(int64_t)ro * a.dh_sr + (int64_t)ry * a.dh_sc] * coefx;
-                *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
-                    __float2bfloat16_rn(v);
+            for (int rb = ry_lo; rb <= ry_hi; rb += 8) {          // 8 independent loads in flight
+              int yv[8]; float gv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int ry = min(rb + i, ry_hi);
+                yv[i] = a.ystar[((int64_t)ro * a.Ry + ry) * a.Nx + o];
+                gv[i] = a.dH[(int64_t)ro * a.dh_sr + (int64_t)ry * a.dh_sc];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int ry = rb + i;
+                const int t = ry * a.Ny + yv[i] - t0;
+                if (ry <= ry_hi && yv[i] != 255 && t >= 0 && t < TC_BK)
+                  *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
+                      __float2bfloat16_rn(gv[i] * coefx);
               }
             }
           }
         } else {
-          if (myv) {
-            int rx = t0 / a.Nx, x = t0 - rx * a.Nx;
-            const int jmax = min(TC_BK, a.src_tokens - t0);
-            for (int j = 0; j < jmax; ++j) {
-              const int ys = a.ystar[((int64_t)rx * a.Ry + ro) * a.Nx + x];
-              if (ys == o) {
-                const int64_t tx = (int64_t)rx * a.Nx + x;
-                if (a.mx ? a.mx[tx] != 0 : true) {
-                  const float v = a.dH[(int64_t)rx * a.dh_sr + (int64_t)ro * a.dh_sc] * a.dh_scale * a.wx[tx];
-                  *reinterpret_cast<__nv_bfloat16*>(srow + (((j >> 3) ^ (m & 7)) << 4) + (j & 7) * 2) =
-                      __float2bfloat16_rn(v);
-                }
+          // pair scatter: thread = (source token j, every other partner sample of this output tile); the single
+          // non-zero of pair (j, ry) lands in row (ry, y*) of the tile
+          asm volatile("bar.sync 1, 128;" ::: "memory");       // all rows zeroed before foreign-row stores
+          const int et = threadIdx.x - 64;
+          const int j = et & 63;
+          const int tsrc = t0 + j;
+          if (tsrc < a.src_tokens) {
+            const int rx = tsrc / a.Nx, x = tsrc - rx * a.Nx;
+            const float cw = a.wx[tsrc] * a.dh_scale;
+            const int row0 = mt * TC_BM;
+            const int ry_lo = row0 / a.Ny, ry_hi = min(a.Ry - 1, (row0 + TC_BM - 1) / a.Ny);
+            for (int rb = ry_lo + (et >> 6); rb <= ry_hi; rb += 16) {
+              int yv[8]; float gv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int ry = min(rb + 2 * i, ry_hi);
+                yv[i] = a.ystar[((int64_t)rx * a.Ry + ry) * a.Nx + x];
+                gv[i] = a.dH[(int64_t)rx * a.dh_sr + (int64_t)ry * a.dh_sc];
               }
-              if (++x == a.Nx) { x = 0; ++rx; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int ry = rb + 2 * i;
+                const int mm = ry * a.Ny + yv[i] - row0;
+                if (ry <= ry_hi && yv[i] != 255 && mm >= 0 && mm < TC_BM)
+                  *reinterpret_cast<__nv_bfloat16*>(sa + mm * 128 + (((j >> 3) ^ (mm & 7)) << 4) + (j & 7) * 2) =
+                      __float2bfloat16_rn(gv[i] * cw);
+              }
             }
           }
         }

@@ -83,9 +83,108 @@ sinkhorn_kernel(const float* __restrict__ G, const float* __restrict__ GT, int B
   }
 }
 
+// ---- single-cluster variant (B <= ~600): the whole problem lives in the shared memory of one thread-block
+// cluster (<= 16 CTAs); the dual vectors are replicated in every CTA's shared memory and updated with DSMEM
+// stores, and half-iterations are separated by the hardware cluster barrier instead of a global-memory one.
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ float warp_row_lse_smem(const float* __restrict__ row, const float* __restrict__ vec,
+                                                   int B, int lane) {
+  float m = NR_NEG_INF;
+  for (int j = lane; j < B; j += 32) m = fmaxf(m, row[j] + vec[j]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = lane; j < B; j += 32) s += expf(row[j] + vec[j] - m);
+  s = warp_sum(s);
+  return m + logf(s);
+}
+
+__global__ void __launch_bounds__(SK_THREADS)
+sinkhorn_cluster_kernel(const float* __restrict__ G, const float* __restrict__ GT, int B, int iters,
+                        int rows_per_cta, float* u1, float* v1, float* u2, float* v2) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float sm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = (int)cluster.block_rank(), ncta = (int)cluster.num_blocks();
+  const int r0 = rank * rows_per_cta;
+  const int nr = max(0, min(rows_per_cta, B - r0));
+  float* Gs = sm;
+  float* GTs = Gs + (size_t)rows_per_cta * B;
+  float* vec = GTs + (size_t)rows_per_cta * B;      // [4][B]: u1, v1, u2, v2 (replica of the full vectors)
+  for (int e = tid; e < nr * B; e += SK_THREADS) {
+    Gs[e] = G[(size_t)r0 * B + e];
+    GTs[e] = GT[(size_t)r0 * B + e];
+  }
+  for (int e = tid; e < 4 * B; e += SK_THREADS) vec[e] = 0.f;
+  const float nu = -logf(2.0f * (float)B);
+  cluster.sync();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      // half 0: u1 <- rows of G with v1, u2 <- rows of GT with v2;  half 1: v1 <- rows of GT with u1, v2 <- rows of G with u2
+      for (int w = warp; w < 2 * nr; w += SK_WARPS) {
+        const int r = w >> 1, chain = w & 1;
+        const float* row = ((chain ^ half) ? GTs : Gs) + (size_t)r * B;
+        const int src = chain * 2 + (half ? 0 : 1), dst = chain * 2 + (half ? 1 : 0);
+        const float val = nu - warp_row_lse_smem(row, vec + src * B, B, lane);
+        for (int c = lane; c < ncta; c += 32) {
+          float* remote = cluster.map_shared_rank(vec, c);
+          remote[dst * B + r0 + r] = val;
+        }
+      }
+      cluster.sync();
+    }
+  }
+  for (int r = tid; r < nr; r += SK_THREADS) {
+    u1[r0 + r] = vec[0 * B + r0 + r];
+    v1[r0 + r] = vec[1 * B + r0 + r];
+    u2[r0 + r] = vec[2 * B + r0 + r];
+    v2[r0 + r] = vec[3 * B + r0 + r];
+  }
+}
+
 }  // namespace nr
 
 using namespace nr;
+
+static int sinkhorn_cluster_launch(const float* G, const float* GT, int B, int iters, float* u1, float* v1,
+                                   float* u2, float* v2, cudaStream_t s, bool* launched) {
+  *launched = false;
+  for (int cs = 16; cs >= 8; cs >>= 1) {
+    int rows_per_cta = (B + cs - 1) / cs;
+    size_t smem = ((size_t)2 * rows_per_cta * B + (size_t)4 * B) * sizeof(float);
+    if (smem > 200 * 1024) continue;
+    if (cs > 8 && cudaFuncSetAttribute(sinkhorn_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+                      cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    if (smem > 48 * 1024)
+      NR_CUDA(cudaFuncSetAttribute(sinkhorn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(cs);
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, sinkhorn_cluster_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      continue;
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, sinkhorn_cluster_kernel, G, GT, B, iters, rows_per_cta, u1, v1, u2, v2);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    *launched = true;
+    return 0;
+  }
+  return 0;
+}
 
 extern "C" size_t nr_sinkhorn_workspace_bytes(int64_t B) { (void)B; return 256; }
 
@@ -94,6 +193,11 @@ extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters
   NR_CHECK_ARG(G && GT && u1 && v1 && u2 && v2 && workspace && B > 0 && iters >= 0, "nr_sinkhorn: bad arguments");
   NR_CHECK_ARG(workspace_bytes >= 256, "nr_sinkhorn: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
+  {
+    bool launched = false;
+    if (int e = sinkhorn_cluster_launch(G, GT, (int)B, iters, u1, v1, u2, v2, s, &launched)) return e;
+    if (launched) return 0;
+  }
   int dev = 0, sms = 0, coop = 0;
   NR_CUDA(cudaGetDevice(&dev));
   NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -21,11 +21,12 @@ def similarity_matrix(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list,
         t_mask = t_mask_list.view(-1, t_mask_list.shape[-1])
         v_mask = v_mask_list.view(-1, v_mask_list.shape[-1])
         chunk = max(int(mini_batch), 1) * 64
-        tw = torch.cat([_token_weights(model.text_weight_fc, f, m)
-                        for f, m in zip(torch.split(t_feat_list, chunk), torch.split(t_mask, chunk))])
-        vw = torch.cat([_token_weights(model.video_weight_fc, f, m)
-                        for f, m in zip(torch.split(v_feat_list, chunk), torch.split(v_mask, chunk))])
         prec = model._head_precision() if hasattr(model, "_head_precision") else "fp32"
+        lowp = prec == "bf16"
+        tw = torch.cat([_token_weights(model.text_weight_fc, f, m, lowp)
+                        for f, m in zip(torch.split(t_feat_list, chunk), torch.split(t_mask, chunk))])
+        vw = torch.cat([_token_weights(model.video_weight_fc, f, m, lowp)
+                        for f, m in zip(torch.split(v_feat_list, chunk), torch.split(v_mask, chunk))])
         s, _ = ops.maxsim(t_feat_list, v_feat_list, tw, vw, t_mask, v_mask, prec)
     return s
 

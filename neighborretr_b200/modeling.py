@@ -30,9 +30,11 @@ allgather2 = AllGather2.apply
 DEFAULT_PRECISION = os.environ.get("NR_HEAD_PRECISION", "bf16")
 
 
-def _token_weights(mlp, feat, mask):
-    """softmax over tokens of the MLP logits, masked tokens filled with -9e15 (reference :485-492)."""
-    logit = mlp(feat).squeeze(2)
+def _token_weights(mlp, feat, mask, lowp=False):
+    """softmax over tokens of the MLP logits, masked tokens filled with -9e15 (reference :485-492).
+    lowp: run the Linear layers as TF32 tensor-core GEMMs (cuBLAS) in both passes — the bf16 head mode;
+    otherwise plain fp32 GEMMs.  The softmax stays fp32."""
+    logit = ops.token_mlp_logits(mlp, feat, lowp)
     if mask is not None:
         logit = logit.masked_fill((1 - mask).to(torch.bool), float(-9e15))
     return torch.softmax(logit, dim=-1)
@@ -53,8 +55,9 @@ class HeadMixin:
 
     # --- a1: local_level (reference :483-514) -------------------------------------------------------
     def local_level(self, text_feat, video_feat, text_mask, video_mask):
-        tw = _token_weights(self.text_weight_fc, text_feat, text_mask)
-        vw = _token_weights(self.video_weight_fc, video_feat, video_mask)
+        lowp = self._head_precision() == "bf16"
+        tw = _token_weights(self.text_weight_fc, text_feat, text_mask, lowp)
+        vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp)
         s, st = ops.maxsim(text_feat, video_feat, tw, vw, text_mask, video_mask, self._head_precision(),
                            self._head_bwd_precision())
         return s, st

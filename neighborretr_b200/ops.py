@@ -222,6 +222,58 @@ def maxsim(text_feat, video_feat, tw, vw, text_mask, video_mask, precision="fp32
 
 
 # ------------------------------------------------------------------------------------------------
+# token-weight MLP logits: Linear(D,2D) - ReLU - Linear(2D,1)  (reference modeling.py:148-153)
+# ------------------------------------------------------------------------------------------------
+class _tf32:
+    """Scoped TF32 for the library GEMMs of the weight MLP (both passes), without touching global state."""
+
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        if self.on:
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *a):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+class TokenMLPFunction(torch.autograd.Function):
+    """logits [T] = relu(x W1^T + b1) w2 + b2 as plain cuBLAS GEMMs (fp32, or TF32 tensor cores when `tf32`)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, tf32):
+        shape = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        with _tf32(tf32):
+            h = torch.addmm(b1, x2, w1.t()).relu_()
+            out = torch.addmv(b2.expand(h.shape[0]), h, w2.reshape(-1))
+        ctx.tf32 = tf32
+        ctx.save_for_backward(x2, h, w1, w2)
+        ctx.shape = x.shape
+        return out.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, h, w1, w2 = ctx.saved_tensors
+        d = dout.reshape(-1, 1).float()
+        with _tf32(ctx.tf32):
+            dh = (d * w2.reshape(1, -1)) * (h > 0)
+            dw2 = (d.t() @ h) if ctx.needs_input_grad[3] else None
+            db2 = d.sum().reshape(1) if ctx.needs_input_grad[4] else None
+            dw1 = (dh.t() @ x2) if ctx.needs_input_grad[1] else None
+            db1 = dh.sum(0) if ctx.needs_input_grad[2] else None
+            dx = (dh @ w1).reshape(ctx.shape) if ctx.needs_input_grad[0] else None
+        return dx, dw1, db1, dw2, db2, None
+
+
+def token_mlp_logits(mlp, feat, tf32):
+    """mlp: nn.Sequential(Linear, ReLU, Linear) with the reference's parameter names."""
+    return TokenMLPFunction.apply(feat, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, bool(tf32))
+
+
+# ------------------------------------------------------------------------------------------------
 # centrality weights (reference modeling.py:403-430)
 # ------------------------------------------------------------------------------------------------
 class CentralityWeightsFunction(torch.autograd.Function):
