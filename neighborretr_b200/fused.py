@@ -1,0 +1,208 @@
+"""The whole retrieval head below the token-weight MLPs as ONE autograd node.
+
+`_compute_losses` of the reference (NeighborRetr/models/modeling.py:314-360) expands into ~400 ATen launches per
+step; at b=128 the head is launch-bound, so the fused node issues the ~60 C-ABI launches of a step back to back
+with no autograd bookkeeping in between, which also makes the step capturable in a CUDA graph (graph.py).
+
+Data flow (W = 1: the row block is the full batch; r0/rows are already threaded through for row sharding):
+  prep(text, video, bank_t, bank_v)                      -> normalised fp32 + bf16 operand copies, column sums
+  S, S^T           = 1/2 (H(text,video) + H(video,text)^T)                       2 max-sim launches
+  mb_t2v, mb_v2t   = bank similarities [B,M]                                      4 max-sim launches
+  c_t2v, c_v2t     = row means (bank centrality, until_module.py:181)
+  G, G^T           = gT gV^T (library GEMM), Sinkhorn duals for both directions   1 cluster launch
+  w_t, w_v         = centrality weights (column mean + GEMV)
+  row losses       = both directions, all four losses in one pass per row         2 launches
+Backward mirrors it: row backward -> dS, dG, dc, dw, dls; tensor-core routing products for the batch pair and
+the four bank pairs (the bank gradient dH is the rank-1 broadcast dc[b]/M, passed as a stride-0 view).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import (NR_LOSS_CENTRALITY, NR_LOSS_KL, NR_LOSS_NEIGHBOR, NR_LOSS_UNIFORM, NR_NSAVE, NR_PREC_BF16)
+from .ops import Prepared, _call, _f32c, _mask, _p, _req_cuda, _stream
+
+ALL_LOSSES = NR_LOSS_CENTRALITY | NR_LOSS_NEIGHBOR | NR_LOSS_KL | NR_LOSS_UNIFORM
+
+
+def _fwd_dir(prec, X, Y, wx, mx, my, out, sr, sc, out2, sr2, sc2, acc):
+    return ops._maxsim_dir_fwd(prec, X, Y, wx, mx, my, 0.5, out, sr, sc, out2, sr2, sc2, acc, True)
+
+
+_M54 = {}
+
+
+def _combine_matrix(B, wu, wn, wkl, dev):
+    """[total, centrality, uniform, neighbor, kl] = M54 @ raw row sums {centrality, neighbour, kl, uniform}
+    (means over B rows — B^2 entries for KL — and over the two directions; reference modeling.py:353-358).
+    Cached: creating it costs a host->device copy, which must not happen inside a CUDA-graph capture."""
+    key = (B, wu, wn, wkl, str(dev))
+    m = _M54.get(key)
+    if m is None:
+        c1, c2 = 0.5 / B, 0.5 / (B * B)
+        m = torch.tensor([[c1, wn * c1, wkl * c2, wu * c1], [c1, 0, 0, 0], [0, 0, 0, c1], [0, c1, 0, 0],
+                          [0, 0, c2, 0]], dtype=torch.float32, device=dev)
+        _M54[key] = m
+    return m
+
+
+class HeadFunction(torch.autograd.Function):
+    """(text, video, gT, gV, tw, vw, tw_mb, vw_mb, logit_scale) -> [total, centrality, uniform, neighbor, kl]."""
+
+    @staticmethod
+    def forward(ctx, text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, text_mask, video_mask, mb_feat_t,
+                mb_feat_v, mb_mask_t, mb_mask_v, hp):
+        cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
+        _req_cuda(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, mb_feat_t, mb_feat_v)
+        dev = text.device
+        st = _stream()
+        tw, vw, tw_mb, vw_mb = _f32c(tw), _f32c(vw), _f32c(tw_mb), _f32c(vw_mb)
+        tm, vm, mtm, mvm = _mask(text_mask), _mask(video_mask), _mask(mb_mask_t), _mask(mb_mask_v)
+        bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
+        T = Prepared(text, bf16=bf, colsum=True)
+        V = Prepared(video, bf16=bf, colsum=True)
+        MT = Prepared(mb_feat_t, bf16=bf)
+        MV = Prepared(mb_feat_v, bf16=bf)
+        B, M, d = T.r, MT.r, T.d
+        if V.r != B or MV.r != M:
+            raise RuntimeError("text/video batch sizes (or bank sizes) differ")
+        f32 = dict(dtype=torch.float32, device=dev)
+        S = torch.empty(B, B, **f32); ST = torch.empty(B, B, **f32)
+        mb_t2v = torch.empty(B, M, **f32); mb_v2t = torch.empty(B, M, **f32)
+        p1, y1 = _fwd_dir(prec, T, V, tw, tm, vm, S, B, 1, ST, 1, B, 0)
+        p2, y2 = _fwd_dir(prec, V, T, vw, vm, tm, S, 1, B, ST, B, 1, 1)
+        pA, yA = _fwd_dir(prec, T, MV, tw, tm, mvm, mb_t2v, M, 1, None, 0, 0, 0)        # H(text, bank_v)
+        pB, yB = _fwd_dir(prec, MV, T, vw_mb, mvm, tm, mb_t2v, 1, M, None, 0, 0, 1)     # H(bank_v, text)^T
+        pD, yD = _fwd_dir(prec, V, MT, vw, vm, mtm, mb_v2t, M, 1, None, 0, 0, 0)        # H(video, bank_t)
+        pC, yC = _fwd_dir(prec, MT, V, tw_mb, mtm, vm, mb_v2t, 1, M, None, 0, 0, 1)     # H(bank_t, video)^T
+        cb = torch.empty(2, B, **f32)                    # [c_t2v ; c_v2t]
+        _call("nr_row_mean", _p(mb_t2v), M, B, M, _p(cb[0]), st)
+        _call("nr_row_mean", _p(mb_v2t), M, B, M, _p(cb[1]), st)
+        # global similarity: one token per sample -> plain dot products (library GEMM, fp32)
+        g2, v2 = _f32c(gt).reshape(B, d), _f32c(gv).reshape(B, d)
+        G = g2 @ v2.t()
+        GT = v2 @ g2.t()
+        duals = torch.empty(4, B, **f32)
+        lib_ws = torch.empty(256, dtype=torch.uint8, device=dev)
+        _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]), _p(duals[3]),
+              _p(lib_ws), 256, st)
+        # centrality weights
+        mean = torch.empty(2, d, **f32); gn = torch.empty(2, B, d, **f32)
+        ginv = torch.empty(2, B, **f32); w = torch.empty(2, B, **f32)
+        _call("nr_centrality_fwd", _p(T.partials), T.partials.shape[0], T.rows, _p(g2), B, d, cs, _p(mean[0]),
+              _p(gn[0]), _p(ginv[0]), _p(w[0]), st, launches=2)
+        _call("nr_centrality_fwd", _p(V.partials), V.partials.shape[0], V.rows, _p(v2), B, d, cs, _p(mean[1]),
+              _p(gn[1]), _p(ginv[1]), _p(w[1]), st, launches=2)
+        # row losses, both directions
+        ls = _f32c(logit_scale).reshape(1)
+        row_out = torch.zeros(2, 4, B, **f32)
+        nbr = torch.empty(2, B, k, dtype=torch.int32, device=dev)
+        saved = torch.empty(2, B, NR_NSAVE, **f32)
+        _call("nr_row_losses_fwd", _p(S), B, _p(G), B, _p(cb[1]), _p(w[0]), _p(duals[0]), _p(duals[1]), B, B, 0,
+              _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[0]), _p(nbr[0]), _p(saved[0]), st)
+        _call("nr_row_losses_fwd", _p(ST), B, _p(GT), B, _p(cb[0]), _p(w[1]), _p(duals[2]), _p(duals[3]), B, B, 0,
+              _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[1]), _p(nbr[1]), _p(saved[1]), st)
+        sums = torch.empty(8, **f32)
+        _call("nr_vec_sums", _p(row_out), 8, B, None, _p(sums), st)
+        # [total, centrality, uniform, neighbor, kl] = M54 @ (sums_dir1 + sums_dir2);  sums order: c, n, kl, u
+        m54 = _combine_matrix(B, wu, wn, wkl, dev)
+        out5 = m54 @ (sums[:4] + sums[4:])
+        ctx.hp = hp
+        ctx.objs = (T, V, MT, MV)
+        ctx.save_for_backward(tw, vw, tw_mb, vw_mb, tm, vm, mtm, mvm, S, ST, G, GT, cb, duals, w, ls, nbr, saved, mean,
+                              gn, ginv, g2, v2, m54, p1, y1, p2, y2, pA, yA, pB, yB, pC, yC, pD, yD)
+        ctx.gshape = (gt.shape, gv.shape)
+        ctx.nbr = nbr
+        ctx.mark_non_differentiable(nbr)
+        return out5, nbr
+
+    @staticmethod
+    def backward(ctx, g5, _gn):
+        (tw, vw, tw_mb, vw_mb, tm, vm, mtm, mvm, S, ST, G, GT, cb, duals, w, ls, nbr, saved, mean, gn, ginv, g2, v2, m54,
+         p1, y1, p2, y2, pA, yA, pB, yB, pC, yC, pD, yD) = ctx.saved_tensors
+        cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = ctx.hp
+        T, V, MT, MV = ctx.objs
+        B, M, d = T.r, MT.r, T.d
+        dev = S.device
+        st = _stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        gscale = m54.t() @ _f32c(g5)                                  # upstream multipliers of the raw row terms
+        z = torch.zeros(2 * B + 1 + 2 * B, **f32)                      # [dc_t2v | dc_v2t | dls | dw_t | dw_v]
+        dc, dls, dw = z[:2 * B].view(2, B), z[2 * B:2 * B + 1], z[2 * B + 1:].view(2, B)
+        dS1 = torch.empty(B, B, **f32); dS2 = torch.empty(B, B, **f32)
+        dG1 = torch.empty(B, B, **f32); dG2 = torch.empty(B, B, **f32)
+        _call("nr_row_losses_bwd", _p(S), B, _p(G), B, _p(cb[1]), _p(w[0]), _p(duals[0]), _p(duals[1]), B, B, 0, _p(ls),
+              k, tau, tau, beta, ALL_LOSSES, _p(nbr[0]), _p(saved[0]), _p(gscale), _p(dS1), B, _p(dG1), B, _p(dc[1]),
+              _p(dw[0]), _p(dls), st)
+        _call("nr_row_losses_bwd", _p(ST), B, _p(GT), B, _p(cb[0]), _p(w[1]), _p(duals[2]), _p(duals[3]), B, B, 0,
+              _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(nbr[1]), _p(saved[1]), _p(gscale), _p(dS2), B, _p(dG2), B,
+              _p(dc[0]), _p(dw[1]), _p(dls), st)
+        dS = torch.empty(B, B, **f32); dG = torch.empty(B, B, **f32)
+        _call("nr_transpose_add", _p(dS1), B, _p(dS2), B, _p(dS), B, B, B, 1.0, 1.0, st)
+        _call("nr_transpose_add", _p(dG1), B, _p(dG2), B, _p(dG), B, B, B, 1.0, 1.0, st)
+        need = ctx.needs_input_grad
+        dgt = (dG @ v2) if need[2] else None
+        dgv = (dG.t() @ g2) if need[3] else None
+        dmean = torch.empty(2, d, **f32)
+        _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs, T.rows, _p(dgt),
+              1, _p(dmean[0]), st, launches=2)
+        _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows, _p(dgv),
+              1, _p(dmean[1]), st, launches=2)
+        # ---- token-pair products ----
+        zt = torch.zeros(T.rows * d + V.rows * d, **f32)
+        dtn, dvn = zt[:T.rows * d], zt[T.rows * d:]
+        wz = torch.zeros(tw.numel() + vw.numel() + tw_mb.numel() + vw_mb.numel(), **f32)
+        o1, o2, o3 = tw.numel(), tw.numel() + vw.numel(), tw.numel() + vw.numel() + tw_mb.numel()
+        dtw, dvw, dtw_mb, dvw_mb = wz[:o1], wz[o1:o2], wz[o2:o3], wz[o3:]
+        vs, vld = V.bwd_source(bprec); ts, tld = T.bwd_source(bprec)
+        mvs, mvld = MV.bwd_source(bprec); mts, mtld = MT.bwd_source(bprec)
+        nt, nv = T.n, V.n
+        if need[0]:
+            # text <- batch pair (both orientations) and the text-vs-bank-video pair
+            _call("nr_maxsim_bwd_x", bprec, _p(vs), vld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt, B, nv,
+                  d, _p(dtn), st)
+            _call("nr_maxsim_bwd_y", bprec, _p(vs), vld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv, B, nt,
+                  d, _p(dtn), st)
+            _call("nr_maxsim_bwd_x", bprec, _p(mvs), mvld, _p(tw), _p(tm), _p(mvm), _p(yA), _p(dc[0]), 1, 0, 0.5 / M, B,
+                  nt, M, nv, d, _p(dtn), st)
+            _call("nr_maxsim_bwd_y", bprec, _p(mvs), mvld, _p(vw_mb), _p(mvm), _p(tm), _p(yB), _p(dc[0]), 0, 1, 0.5 / M,
+                  M, nv, B, nt, d, _p(dtn), st)
+        if need[1]:
+            _call("nr_maxsim_bwd_y", bprec, _p(ts), tld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt, B, nv,
+                  d, _p(dvn), st)
+            _call("nr_maxsim_bwd_x", bprec, _p(ts), tld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv, B, nt,
+                  d, _p(dvn), st)
+            _call("nr_maxsim_bwd_x", bprec, _p(mts), mtld, _p(vw), _p(vm), _p(mtm), _p(yD), _p(dc[1]), 1, 0, 0.5 / M, B,
+                  nv, M, nt, d, _p(dvn), st)
+            _call("nr_maxsim_bwd_y", bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm), _p(yC), _p(dc[1]), 0, 1, 0.5 / M,
+                  M, nt, B, nv, d, _p(dvn), st)
+        # token-weight gradients (batch pair + bank pairs)
+        if need[4]:
+            _call("nr_maxsim_bwd_w", _p(p1), _p(dS), B, 1, 0.5, B, nt, B, _p(dtw), st)
+            _call("nr_maxsim_bwd_w", _p(pA), _p(dc[0]), 1, 0, 0.5 / M, B, nt, M, _p(dtw), st)
+        if need[5]:
+            _call("nr_maxsim_bwd_w", _p(p2), _p(dS), 1, B, 0.5, B, nv, B, _p(dvw), st)
+            _call("nr_maxsim_bwd_w", _p(pD), _p(dc[1]), 1, 0, 0.5 / M, B, nv, M, _p(dvw), st)
+        if need[6]:
+            _call("nr_maxsim_bwd_w", _p(pC), _p(dc[1]), 0, 1, 0.5 / M, M, nt, B, _p(dtw_mb), st)
+        if need[7]:
+            _call("nr_maxsim_bwd_w", _p(pB), _p(dc[0]), 0, 1, 0.5 / M, M, nv, B, _p(dvw_mb), st)
+        dtext = T.backward(dtn, add_vec=dmean[0]) if need[0] else None
+        dvideo = V.backward(dvn, add_vec=dmean[1]) if need[1] else None
+        ctx.objs = None
+        gs_t, gs_v = ctx.gshape
+        return (dtext, dvideo, dgt.reshape(gs_t) if need[2] else None, dgv.reshape(gs_v) if need[3] else None,
+                dtw.view_as(tw) if need[4] else None, dvw.view_as(vw) if need[5] else None,
+                dtw_mb.view_as(tw_mb) if need[6] else None, dvw_mb.view_as(vw_mb) if need[7] else None,
+                dls.reshape(()) if need[8] else None, None, None, None, None, None, None, None)
+
+
+def fused_head(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, text_mask, video_mask, mb_feat_t, mb_feat_v,
+               mb_mask_t, mb_mask_v, *, centrality_scale, beta, num_neighbors, temperature, uniform_weight,
+               neighbor_weight, kl_weight, precision="bf16", bwd_precision=None, iters=50):
+    hp = (float(centrality_scale), float(beta), int(num_neighbors), float(temperature), int(iters),
+          float(uniform_weight), float(neighbor_weight), float(kl_weight), ops.PRECISIONS[precision],
+          ops.PRECISIONS[bwd_precision or precision])
+    return HeadFunction.apply(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, text_mask, video_mask,
+                              mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp)

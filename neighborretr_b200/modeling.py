@@ -139,6 +139,37 @@ class HeadMixin:
     def _compute_losses(self, text_feat, video_feat, text_mask, video_mask, mb_feat_t, mb_feat_v, mb_mask_t,
                         mb_mask_v, centrality_scale, beta, num_neighbors, temperature, logit_scale,
                         global_feats=None):
+        cfg = self.config
+        fused_ok = getattr(self, "head_fused", getattr(cfg, "head_fused", True))
+        if fused_ok:
+            if global_feats is None:
+                global_feats = self.merge_global_features(text_feat, video_feat, text_mask, video_mask)
+            gtf, gvf = global_feats
+            fused_ok = gtf.shape[1] == 1 and gvf.shape[1] == 1
+        if fused_ok:
+            # one autograd node for everything below the weight MLPs (fused.py)
+            if mb_feat_v.dim() != 3 or mb_feat_v.shape[0] == 0:
+                raise RuntimeError("memory bank is empty: prefill it (MemoryBankManager.load_memory_bank) or call "
+                                   "update_memory_bank before the first training step")
+            if text_feat.shape[0] < num_neighbors + 2:
+                raise IndexError(f"neighbor loss needs batch >= num_neighbors + 2 (got {text_feat.shape[0]}, "
+                                 f"k={num_neighbors})")
+            from .fused import fused_head
+            lowp = self._head_precision() == "bf16"
+            tw = _token_weights(self.text_weight_fc, text_feat, text_mask, lowp)
+            vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp)
+            tw_mb = _token_weights(self.text_weight_fc, mb_feat_t, mb_mask_t, lowp)
+            vw_mb = _token_weights(self.video_weight_fc, mb_feat_v, mb_mask_v, lowp)
+            ls = logit_scale if torch.is_tensor(logit_scale) else torch.tensor(float(logit_scale),
+                                                                               device=text_feat.device)
+            out5, nbr = fused_head(text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, ls, text_mask, video_mask,
+                                   mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, centrality_scale=centrality_scale,
+                                   beta=beta, num_neighbors=num_neighbors, temperature=temperature,
+                                   uniform_weight=cfg.uniform_weight, neighbor_weight=cfg.neighbor_weight,
+                                   kl_weight=cfg.kl_weight, precision=self._head_precision(),
+                                   bwd_precision=self._head_bwd_precision())
+            self.last_neighbors = (nbr[0], nbr[1])
+            return tuple(out5.unbind(0))
         local_t2v_logits, local_v2t_logits = self.local_level(text_feat, video_feat, text_mask, video_mask)
         uniform_loss, global_text_feat, global_video_feat, g, gt = self.compute_uniform_loss(
             text_feat, video_feat, text_mask, video_mask, temperature, beta, global_feats=global_feats)

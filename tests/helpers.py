@@ -15,7 +15,7 @@ def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
 
 
-def make_head(d, cfg, params, precision="fp32", bwd_precision=None, device="cuda"):
+def make_head(d, cfg, params, precision="fp32", bwd_precision=None, device="cuda", fused=True):
     from neighborretr_b200.modeling import NeighborRetr
     m = NeighborRetr(cfg, width=d)
     for name, sd in params.items():
@@ -23,6 +23,7 @@ def make_head(d, cfg, params, precision="fp32", bwd_precision=None, device="cuda
     m.clip.logit_scale.data.fill_(LOG100)
     m.head_precision = precision
     m.head_bwd_precision = bwd_precision
+    m.head_fused = fused
     return m.to(device)
 
 

@@ -118,13 +118,15 @@ def test_centrality_weights():
         assert rel_l2(a.grad, b.grad) < 1e-4
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", ["small", "small_k8", "cfg1"])
-def test_compute_losses_fp32(name):
-    """Full head fwd+bwd in fp32 mode vs golden (reference) losses and oracle gradients."""
+def test_compute_losses_fp32(name, fused):
+    """Full head fwd+bwd in fp32 mode vs golden (reference) losses and oracle gradients; both the fused
+    single-node path and the per-module path."""
     c = CASES[name]
     gold = load_golden(name)
     h, bank, params, cfg = make_case(c)
-    m = make_head(c["d"], cfg, params, "fp32")
+    m = make_head(c["d"], cfg, params, "fp32", fused=fused)
     set_bank(m, bank)
     losses, grads = cuda_losses(m, h, cfg)
     np.testing.assert_allclose(losses.numpy(), gold["losses"], rtol=1e-4)        # north_star: 1e-4 in fp32
