@@ -1,0 +1,91 @@
+"""Whole-step CUDA graph of the retrieval head: head_forward (losses) + backward (gradients of the features, the
+global features, the token-weight MLPs and logit_scale) + memory-bank FIFO update, captured once for fixed shapes
+and replayed with one launch.  At b=128 the head is launch-bound (~100 small kernels per step), so the graph is
+what turns GPU time into steps/s.
+
+    step = GraphedHeadStep(model, example_batch)            # model: neighborretr_b200.modeling.NeighborRetr (cuda)
+    losses = step(text_feat, video_feat, text_mask, video_mask, idx, global_text, global_video)
+    step.grads["text_feat"], model.text_weight_fc[0].weight.grad, ...   # static tensors, overwritten per replay
+
+Inputs may live in (pinned) host memory: they are copied into the static device buffers on the replay stream.
+The memory bank is advanced IN PLACE inside the graph (cat(new, old)[:capacity], reference modeling.py:235-249),
+so `model.mb_*` keep their storage across replays.  Single-GPU only (world_size == 1).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+FIELDS = ("text_feat", "video_feat", "text_mask", "video_mask", "idx", "global_text", "global_video")
+GRAD_FIELDS = ("text_feat", "video_feat", "global_text", "global_video")
+
+
+class GraphedHeadStep:
+    def __init__(self, model, example, warmup=3):
+        if getattr(model.config, "world_size", 1) != 1:
+            raise RuntimeError("GraphedHeadStep: single-process capture only")
+        self.model = model
+        dev = next(model.parameters()).device
+        self.static = {}
+        for f, t in zip(FIELDS, example):
+            s = t.detach().to(dev).clone()
+            if f in GRAD_FIELDS:
+                s.requires_grad_(True)
+            self.static[f] = s
+        self.bank_names = ("mb_ind", "mb_feat_t", "mb_feat_v", "mb_mask_t", "mb_mask_v")
+        for n in self.bank_names:                       # own the bank storage
+            setattr(model, n, getattr(model, n).detach().to(dev).clone())
+        bank0 = {n: getattr(model, n).clone() for n in self.bank_names}
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._zero_grads()
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._zero_grads()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES["count"]
+        with torch.cuda.graph(self.graph):
+            self.losses = self._body()
+        self.launches_per_replay = ops.LAUNCHES["count"] - n0
+        for n in self.bank_names:                       # warm-up steps advanced the bank: restore it in place
+            getattr(model, n).copy_(bank0[n])
+        self.grads = {f: self.static[f].grad for f in GRAD_FIELDS}
+
+    def _zero_grads(self):
+        for t in list(self.static.values()) + self.params:
+            t.grad = None
+
+    def _body(self):
+        m, s = self.model, self.static
+        cfg = m.config
+        logit_scale = m.clip.logit_scale.exp()
+        losses = m._compute_losses(s["text_feat"], s["video_feat"], s["text_mask"], s["video_mask"], m.mb_feat_t,
+                                   m.mb_feat_v, m.mb_mask_t, m.mb_mask_v, cfg.centrality_scale, cfg.beta,
+                                   cfg.num_neighbors, cfg.temperature, logit_scale,
+                                   global_feats=(s["global_text"], s["global_video"]))
+        losses[0].backward()
+        with torch.no_grad():
+            cap = m.mb_feat_v.shape[0]
+            for name, new in (("mb_ind", s["idx"]), ("mb_feat_t", s["text_feat"]), ("mb_feat_v", s["video_feat"]),
+                              ("mb_mask_t", s["text_mask"]), ("mb_mask_v", s["video_mask"])):
+                bank = getattr(m, name)
+                bank.copy_(ops.fifo_update(new.detach().to(bank.dtype), bank, cap))
+        return torch.stack([x.detach() for x in losses])
+
+    def __call__(self, *batch, sync_losses_to=None):
+        """Copy the batch into the static buffers (H2D if it lives on the host), replay, return the static
+        [total, centrality, uniform, neighbor, kl] tensor (or copy it into the pinned host tensor given)."""
+        for f, t in zip(FIELDS, batch):
+            self.static[f].data.copy_(t, non_blocking=True)
+        self.graph.replay()
+        ops.LAUNCHES["count"] += self.launches_per_replay
+        if sync_losses_to is not None:
+            sync_losses_to.copy_(self.losses, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return sync_losses_to
+        return self.losses

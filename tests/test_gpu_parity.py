@@ -215,3 +215,29 @@ def test_no_cpu_fallback():
     from neighborretr_b200 import until_module as U
     with pytest.raises(RuntimeError):
         U.KLDivergenceLoss()(torch.randn(8, 8), torch.randn(8, 8))
+
+
+def test_cuda_graph_step_matches_eager():
+    """GraphedHeadStep (one graph launch per step) reproduces the eager module path: same losses, same gradients,
+    and the in-graph memory-bank FIFO equals update_memory_bank."""
+    from neighborretr_b200.graph import FIELDS, GraphedHeadStep
+    c = CASES["cfg1"]
+    h, bank, params, cfg = make_case(c)
+    batches = [synth.make_batch(c["b"], c["nt"], c["nv"], d=c["d"], seed=1234 + i).to("cuda") for i in range(3)]
+    eager = make_head(c["d"], cfg, params, "bf16"); set_bank(eager, bank)
+    graphed = make_head(c["d"], cfg, params, "bf16"); set_bank(graphed, bank)
+    step = GraphedHeadStep(graphed, [getattr(batches[0], f) for f in FIELDS])
+    for hb in batches:
+        text = hb.text_feat.clone().requires_grad_(True); video = hb.video_feat.clone().requires_grad_(True)
+        gt = hb.global_text.clone().requires_grad_(True); gv = hb.global_video.clone().requires_grad_(True)
+        eager.zero_grad(set_to_none=True)
+        le = eager.head_forward(text, video, hb.text_mask, hb.video_mask, hb.idx, global_feats=(gt, gv))
+        le[0].backward()
+        lg = step(*[getattr(hb, f) for f in FIELDS])
+        torch.testing.assert_close(lg, torch.stack([x.detach() for x in le]), rtol=1e-5, atol=1e-6)
+        assert rel_l2(step.grads["text_feat"], text.grad) < 1e-4      # fp32 atomics reorder sums: not bitwise
+        assert rel_l2(step.grads["video_feat"], video.grad) < 1e-4
+        assert rel_l2(graphed.text_weight_fc[0].weight.grad, eager.text_weight_fc[0].weight.grad) < 1e-4
+        assert rel_l2(graphed.clip.logit_scale.grad, eager.clip.logit_scale.grad) < 1e-4
+        assert torch.equal(graphed.mb_ind, eager.mb_ind)
+        assert torch.equal(graphed.mb_feat_v, eager.mb_feat_v)
