@@ -143,6 +143,60 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def eval_cpu_baseline(nq=1000):
+    """Reference eval path on the host: 64x64-tiled local_level + compute_metrics x2 (oracle port)."""
+    from oracle import head as O
+    from oracle import metrics as OM
+    nt, nv, _ = synth.SHAPES["msrvtt"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    h = synth.make_batch(nq, nt, nv, d=D, seed=77)
+    params = synth.make_mlp_params(d=D)
+    t0 = time.perf_counter()
+    sim, sim_t = O.eval_similarity(h.text_feat, h.video_feat, h.text_mask, h.video_mask, params)
+    r1 = OM.compute_metrics(sim); r2 = OM.compute_metrics(sim_t)
+    return (time.perf_counter() - t0) * 1e3, r1["R1"], r2["R1"]
+
+
+def run_eval_bench(model, dev, steps, nq=1000):
+    """Eval sim + R@K latency (BASELINE.json configs[3]): 1k x 1k MSR-VTT-shaped test set, t2v and v2t."""
+    from neighborretr_b200 import ops
+    from neighborretr_b200.evaluator import _run_on_single_gpu, similarity_matrix
+    from neighborretr_b200.metrics import RetrievalMetrics, metrics_from_counts
+    nt, nv, _ = synth.SHAPES["msrvtt"]
+    host = synth.make_batch(nq, nt, nv, d=D, seed=77)
+    pin = {f: getattr(host, f).pin_memory() for f in ("text_feat", "video_feat", "text_mask", "video_mask")}
+    res = {k: v.to(dev) for k, v in pin.items()}
+    model.eval()
+
+    def resident():
+        s = similarity_matrix(model, res["text_mask"], res["video_mask"], res["text_feat"], res["video_feat"])
+        g1, e1 = ops.rank_counts(s)
+        g2, e2 = ops.rank_counts(s.t().contiguous())
+        c = torch.stack([g1, e1, g2, e2]).cpu().numpy()
+        return metrics_from_counts(c[0], c[1]), metrics_from_counts(c[2], c[3])
+
+    def e2e():      # the reference-facing calls: host features in, numpy sim out, metrics dicts
+        d = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+        sim, sim_t = _run_on_single_gpu(model, d["text_mask"], d["video_mask"], d["text_feat"], d["video_feat"])
+        return RetrievalMetrics.compute_metrics(sim), RetrievalMetrics.compute_metrics(sim_t)
+
+    out = {}
+    for name, fn in (("resident_ms", resident), ("e2e_ms", e2e)):
+        for _ in range(3):
+            r = fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = fn()
+        torch.cuda.synchronize()
+        out[name] = (time.perf_counter() - t0) * 1e3 / steps
+    out.update({"queries": nq, "gallery": nq, "t2v_R1": r[0]["R1"], "v2t_R1": r[1]["R1"], "unit": "ms",
+                "what": "similarity matrix (token-weight MLPs + max-sim) + t2v and v2t R@1/5/10/50, MdR, MeanR",
+                "flops": flops_maxsim(nq, nq, nt, nv)})
+    model.train()
+    return out
+
+
 def workload_config(shape, world, precision):
     nt, nv, mrows = synth.SHAPES[shape]
     return {"workload": f"{shape}_head_b{B_PER_GPU}_per_gpu", "per_gpu_batch": B_PER_GPU,
@@ -301,7 +355,12 @@ def run_ours(args):
                      "timed_in": "eager steps on the launching stream (events cannot be read inside a graph replay)",
                      "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside the step)"},
     }
+    if world == 1:
+        line["eval"] = run_eval_bench(model, dev, 10)
     if world == 1 and not args.no_cpu_baseline:
+        ems, er1, er2 = eval_cpu_baseline()
+        line["eval"]["cpu_baseline_ms"] = ems
+        line["eval"]["cpu_t2v_R1"] = er1
         sps, ms, threads = cpu_reference_steps(args.shape, 4, 1)
         line["cpu_baseline"] = {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
                                 "sample": "4 fwd+bwd steps (after 1 warm-up) of oracle/head.py compute_losses on the "

@@ -60,8 +60,17 @@ class _KernelTimer:
 
     def collect(self):
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in self.events)
+        ms = sum(a.elapsed_time(b) for _, a, b in self.events)
         return {"ms": ms, "launches": len(self.events)}
+
+    def table(self):
+        """Per-entry-point totals (name -> (calls, ms)) when enabled with "*"."""
+        torch.cuda.synchronize()
+        out = {}
+        for n, a, b in self.events:
+            c, t = out.get(n, (0, 0.0))
+            out[n] = (c + 1, t + a.elapsed_time(b))
+        return out
 
 
 KERNEL_TIMER = _KernelTimer()
@@ -69,12 +78,12 @@ KERNEL_TIMER = _KernelTimer()
 
 def _call(name, *args, launches=1):
     fn = getattr(_lib.load(), name)
-    if KERNEL_TIMER.name == name:
+    if KERNEL_TIMER.name == name or KERNEL_TIMER.name == "*":
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
-        KERNEL_TIMER.events.append((e0, e1))
+        KERNEL_TIMER.events.append((name, e0, e1))
     else:
         rc = fn(*args)
     check(rc, name)
