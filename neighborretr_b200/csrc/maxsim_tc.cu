@@ -23,7 +23,9 @@
 namespace nr {
 using namespace tc;
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 192;            // backward kernel: TMA warp, MMA warp, 4 generator/epilogue warps
+constexpr int TCF_THREADS = 320;           // forward kernel: TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int TCF_EPI = TCF_THREADS - 64;
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int TC_MAX_STAGES = 4;
@@ -41,8 +43,40 @@ struct TcFwdArgs {
   int hp_ld;                               // leading dimension (floats) of the weighted-partial buffer
 };
 
+// masked max / arg-max over the NY accumulator columns of one Y sample, as two balanced trees (depth log2 NY)
+// instead of a serial compare-select chain; ties -> lowest y, exactly like a left-to-right strict '>' scan.
+template <int N>
+struct TreeRed {
+  static __device__ __forceinline__ float fmax_(const float* t) {
+    return fmaxf(TreeRed<N / 2>::fmax_(t), TreeRed<N - N / 2>::fmax_(t + N / 2));
+  }
+  // lowest index y (offset by base) whose value equals m, 255 if none
+  static __device__ __forceinline__ int first_eq(const float* t, float m, int base) {
+    return min(TreeRed<N / 2>::first_eq(t, m, base), TreeRed<N - N / 2>::first_eq(t + N / 2, m, base + N / 2));
+  }
+};
+template <>
+struct TreeRed<1> {
+  static __device__ __forceinline__ float fmax_(const float* t) { return t[0]; }
+  static __device__ __forceinline__ int first_eq(const float* t, float m, int base) { return t[0] == m ? base : 255; }
+};
+
 template <int NY>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__device__ __forceinline__ void sample_argmax(const uint32_t* v, uint64_t mb, bool full, float& best, int& bi) {
+  float f[NY];
+  if (full) {
+#pragma unroll
+    for (int y = 0; y < NY; ++y) f[y] = __uint_as_float(v[y]);
+  } else {
+#pragma unroll
+    for (int y = 0; y < NY; ++y) f[y] = ((mb >> y) & 1ull) ? __uint_as_float(v[y]) : 0.f;   // masked pairs are exactly 0
+  }
+  best = TreeRed<NY>::fmax_(f);
+  bi = TreeRed<NY>::first_eq(f, best, 0);
+}
+
+template <int NY>
+__global__ void __launch_bounds__(TCF_THREADS, 1)
 maxsim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                      const TcFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -65,7 +99,7 @@ maxsim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmy);
     for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, TCF_EPI); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -123,10 +157,12 @@ maxsim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                    // the two warps of a quarter take alternate Y samples
     const int r = q * 32 + lane;                         // accumulator row = X token of the tile
-    const int et = threadIdx.x - 64;                     // 0..127
+    const int et = threadIdx.x - 64;                     // 0..255
+    const uint64_t fullmask = NY == 64 ? ~0ull : ((1ull << NY) - 1ull);
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / a.n_nt, nt = tile % a.n_nt;
@@ -138,13 +174,12 @@ maxsim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       float* hpb = hp + (size_t)acc * TC_BM * a.hp_ld;
       // column masks of this tile, one bit per Y token
       if (et < sy_n) {
-        uint64_t bits = 0;
+        uint64_t bits = fullmask;
         if (a.my) {
+          bits = 0;
           const int64_t* mrow = a.my + (int64_t)(ry0 + et) * NY;
 #pragma unroll
           for (int y = 0; y < NY; ++y) bits |= (uint64_t)(mrow[y] != 0) << y;
-        } else {
-          bits = ~0ull;
         }
         cm[et] = bits;
       }
@@ -153,38 +188,57 @@ maxsim_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       const bool row_ok = (r < a.MU) && (rx < a.Rx);
       const bool mxv = row_ok && (a.mx ? (a.mx[(int64_t)rx * a.Nx + x] != 0) : true);
       const float wxv = row_ok ? a.wx[(int64_t)rx * a.Nx + x] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int64_t obase = ((int64_t)rx * a.Ry + ry0) * a.Nx + x;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tfull + acc, acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_ACC_COLS);
-      for (int sy = 0; sy < sy_n; ++sy) {
-        uint32_t v[NY];
-        tmem_ld_cols<NY>(taddr + (uint32_t)(sy * NY), v);
-        tmem_ld_wait();
-        reg_fence<NY>(v);
-        float best = NR_NEG_INF;
-        int bi = 0;
+      auto finish = [&](const uint32_t* v, int sy) {
         const uint64_t mb = cm[sy];
-#pragma unroll
-        for (int y = 0; y < NY; ++y) {
-          float f = ((mb >> y) & 1ull) ? __uint_as_float(v[y]) : 0.f;      // masked pairs are exactly 0
-          if (f > best) { best = f; bi = y; }
-        }
+        float best; int bi;
+        sample_argmax<NY>(v, mb, mb == fullmask, best, bi);
         // arg-max byte 255 = "no gradient": masked X token, or the max is a masked (exactly 0) pair
         if (!mxv) { best = 0.f; bi = 255; }
         else if (!((mb >> bi) & 1ull)) bi = 255;
         hpb[r * a.hp_ld + sy] = wxv * best;
         if (row_ok) {
-          const int64_t o = ((int64_t)rx * a.Ry + (ry0 + sy)) * a.Nx + x;
+          const int64_t o = obase + (int64_t)sy * a.Nx;
           if (a.pmax) a.pmax[o] = best;
           if (a.ystar) a.ystar[o] = (uint8_t)bi;
+        }
+      };
+      if constexpr (NY <= 32) {
+        // two register buffers: the TMEM load of the next sample is in flight while this one is reduced
+        uint32_t va[NY], vb[NY];
+        int sy = half;
+        if (sy < sy_n) tmem_ld_cols<NY>(taddr + (uint32_t)(sy * NY), va);
+        for (; sy < sy_n; sy += 4) {
+          tmem_ld_wait();
+          reg_fence<NY>(va);
+          const int sy2 = sy + 2;
+          if (sy2 < sy_n) tmem_ld_cols<NY>(taddr + (uint32_t)(sy2 * NY), vb);
+          finish(va, sy);
+          if (sy2 < sy_n) {
+            tmem_ld_wait();
+            reg_fence<NY>(vb);
+            if (sy + 4 < sy_n) tmem_ld_cols<NY>(taddr + (uint32_t)((sy + 4) * NY), va);
+            finish(vb, sy2);
+          }
+        }
+      } else {
+        for (int sy = half; sy < sy_n; sy += 2) {
+          uint32_t v[NY];
+          tmem_ld_cols<NY>(taddr + (uint32_t)(sy * NY), v);
+          tmem_ld_wait();
+          reg_fence<NY>(v);
+          finish(v, sy);
         }
       }
       tc_fence_before();
       mbar_arrive(tempty + acc);                         // TMEM stage may be overwritten
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       // segmented sum over the Nx rows of each X sample
-      for (int e = et; e < a.SX * sy_n; e += 128) {
+      for (int e = et; e < a.SX * sy_n; e += TCF_EPI) {
         const int s = e / sy_n, sy = e - s * sy_n;
         const int rxx = mt * a.SX + s;
         if (rxx < a.Rx) {
@@ -247,7 +301,7 @@ template <int NY>
 static int launch_fwd(const CUtensorMap& tmx, const CUtensorMap& tmy, const TcFwdArgs& a, size_t smem, int grid,
                       cudaStream_t stream) {
   NR_CUDA(cudaFuncSetAttribute(maxsim_fwd_tc_kernel<NY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  maxsim_fwd_tc_kernel<NY><<<grid, TC_THREADS, smem, stream>>>(tmx, tmy, a);
+  maxsim_fwd_tc_kernel<NY><<<grid, TCF_THREADS, smem, stream>>>(tmx, tmy, a);
   NR_CHECK_LAUNCH("nr_maxsim_fwd(bf16)");
   return 0;
 }

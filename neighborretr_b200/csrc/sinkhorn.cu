@@ -10,6 +10,8 @@
 // half-iteration and share the resident slabs.
 // Roofline: resident => latency/barrier bound at B <= ~1500; beyond that 100 * 2 * 4 * B^2 bytes of L2/HBM.
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "nrhead_internal.h"
 
@@ -143,6 +145,205 @@ sinkhorn_cluster_kernel(const float* __restrict__ G, const float* __restrict__ G
   }
 }
 
+// ---- single-CTA variant (B <= 168): K = exp(G - max G) and its transpose stay in shared memory and the
+// recursion runs in the SCALING domain, alpha = 1/(K beta), beta = 1/(K^T alpha): no transcendental and no
+// cross-CTA barrier inside the 100 half-iterations, only 4 FMAs + a warp reduction per row and __syncthreads.
+// With alpha = e^u / e^(nu - gmax) and beta = e^v this is exactly u = nu - LSE_row(G + v), v = nu - LSE_col(G + u)
+// (until_module.py:248-250).  The scaling domain needs a bounded dynamic range: when max G - min G > 30 the same
+// kernel runs the log-domain recursion instead (identical to the reference in every regime).
+constexpr int SKC_THREADS = 1024;
+constexpr int SKC_WARPS = SKC_THREADS / 32;
+
+__global__ void __launch_bounds__(SKC_THREADS)
+sinkhorn_cta_kernel(const float* __restrict__ G, const float* __restrict__ GT, int B, int iters, float* u1, float* v1,
+                    float* u2, float* v2) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  float* K = sm;                       // [B][B]  rows of G
+  float* KT = sm + (size_t)B * B;      // [B][B]  rows of G^T
+  float* vec = KT + (size_t)B * B;     // [4][B]  chain 1: (alpha|u, beta|v), chain 2: (alpha|u, beta|v)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = NR_NEG_INF, mn = INFINITY;
+  for (int e = tid; e < B * B; e += SKC_THREADS) {
+    float g = G[e];
+    K[e] = g;
+    KT[e] = GT[e];
+    mx = fmaxf(mx, g);
+    mn = fminf(mn, g);
+  }
+  mx = block_max(mx, red);
+  mn = -block_max(-mn, red);
+  const float nu = -logf(2.0f * (float)B);
+  const bool scaling = (mx - mn) <= 30.f;
+  if (scaling) {
+    for (int e = tid; e < B * B; e += SKC_THREADS) { K[e] = expf(K[e] - mx); KT[e] = expf(KT[e] - mx); }
+    for (int e = tid; e < 4 * B; e += SKC_THREADS) vec[e] = 1.f;       // beta = e^0
+  } else {
+    for (int e = tid; e < 4 * B; e += SKC_THREADS) vec[e] = 0.f;       // u = v = 0
+  }
+  __syncthreads();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      for (int w = warp; w < 2 * B; w += SKC_WARPS) {
+        const int chain = w >= B, r = w - chain * B;
+        const float* row = ((chain ^ half) ? KT : K) + (size_t)r * B;
+        const float* src = vec + (chain * 2 + (half ? 0 : 1)) * B;
+        float* dst = vec + (chain * 2 + (half ? 1 : 0)) * B;
+        if (scaling) {
+          float s = 0.f;
+          for (int j = lane; j < B; j += 32) s = fmaf(row[j], src[j], s);
+          s = warp_sum(s);
+          if (lane == 0) dst[r] = 1.0f / s;
+        } else {
+          float m = NR_NEG_INF;
+          for (int j = lane; j < B; j += 32) m = fmaxf(m, row[j] + src[j]);
+          m = warp_max(m);
+          float s = 0.f;
+          for (int j = lane; j < B; j += 32) s += expf(row[j] + src[j] - m);
+          s = warp_sum(s);
+          if (lane == 0) dst[r] = nu - (m + logf(s));
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = tid; r < B; r += SKC_THREADS) {
+    if (scaling) {
+      u1[r] = (nu - mx) + logf(vec[0 * B + r]); v1[r] = logf(vec[1 * B + r]);
+      u2[r] = (nu - mx) + logf(vec[2 * B + r]); v2[r] = logf(vec[3 * B + r]);
+    } else {
+      u1[r] = vec[0 * B + r]; v1[r] = vec[1 * B + r]; u2[r] = vec[2 * B + r]; v2[r] = vec[3 * B + r];
+    }
+  }
+}
+
+// ---- register-resident single-CTA variant (B <= 128): warp w owns rows {w, w+32, ...} of K = exp(G - max G) and
+// of K^T, NB x NB values each, IN REGISTERS for all 100 half-iterations; only the four length-B scaling vectors
+// live in shared memory.  A half-iteration is 2*NB*NB FMAs + 2*NB warp reductions per thread and one
+// __syncthreads: no shared/L2 matrix traffic at all, no cross-CTA barrier.
+template <int NB>
+__global__ void __launch_bounds__(1024)
+sinkhorn_reg_kernel(const float* __restrict__ G, const float* __restrict__ GT, int B, int iters, float* u1, float* v1,
+                    float* u2, float* v2) {
+  __shared__ float vec[4][32 * NB];
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float k[NB][NB], kt[NB][NB];
+  float mx = NR_NEG_INF, mn = INFINITY;
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int r = warp + 32 * i, c = lane + 32 * j;
+      const bool ok = r < B && c < B;
+      k[i][j] = ok ? G[(size_t)r * B + c] : NR_NEG_INF;
+      kt[i][j] = ok ? GT[(size_t)r * B + c] : NR_NEG_INF;
+      if (ok) { mx = fmaxf(mx, k[i][j]); mn = fminf(mn, k[i][j]); }
+    }
+  mx = block_max(mx, red);
+  mn = -block_max(-mn, red);
+  const float nu = -logf(2.0f * (float)B);
+  const bool scaling = (mx - mn) <= 30.f;
+  if (scaling) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { k[i][j] = expf(k[i][j] - mx); kt[i][j] = expf(kt[i][j] - mx); }   // exp(-inf) = 0
+  }
+  for (int e = tid; e < 4 * 32 * NB; e += 1024) (&vec[0][0])[e] = scaling ? 1.f : 0.f;
+  __syncthreads();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      // half 0: alpha1 <- rows of K with beta1, alpha2 <- rows of K^T with beta2
+      // half 1: beta1  <- rows of K^T with alpha1, beta2 <- rows of K with alpha2
+      const float* s1 = vec[half ? 0 : 1];
+      const float* s2 = vec[half ? 2 : 3];
+      float a1[NB], a2[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) { a1[j] = s1[lane + 32 * j]; a2[j] = s2[lane + 32 * j]; }
+      if (scaling) {
+        float V[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) V[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          float x1 = 0.f, x2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            x1 = fmaf(half ? kt[i][j] : k[i][j], a1[j], x1);
+            x2 = fmaf(half ? k[i][j] : kt[i][j], a2[j], x2);
+          }
+          V[i] = x1; V[4 + i] = x2;
+        }
+        // transposed warp reduction of the 8 partial sums: 9 shuffles instead of 40; lane l ends up with the
+        // total of value (l >> 2)
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        float W[4], X[2], Y;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = b4 ? V[i] : V[i + 4], keep = b4 ? V[i + 4] : V[i];
+          W[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = b3 ? W[i] : W[i + 2], keep = b3 ? W[i + 2] : W[i];
+          X[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+          const float send = b2 ? X[0] : X[1], keep = b2 ? X[1] : X[0];
+          Y = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        Y += __shfl_xor_sync(0xffffffffu, Y, 2);
+        Y += __shfl_xor_sync(0xffffffffu, Y, 1);
+        if ((lane & 3) == 0) {
+          const int idx = lane >> 2, i = idx & 3, r = warp + 32 * i;
+          if (i < NB && r < B) vec[(idx < 4) ? (half ? 1 : 0) : (half ? 3 : 2)][r] = 1.0f / Y;
+        }
+      } else {
+        float r1[NB], r2[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          float m1 = NR_NEG_INF, m2 = NR_NEG_INF;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            m1 = fmaxf(m1, (half ? kt[i][j] : k[i][j]) + a1[j]);
+            m2 = fmaxf(m2, (half ? k[i][j] : kt[i][j]) + a2[j]);
+          }
+          m1 = warp_max(m1); m2 = warp_max(m2);
+          float x1 = 0.f, x2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            x1 += expf((half ? kt[i][j] : k[i][j]) + a1[j] - m1);
+            x2 += expf((half ? k[i][j] : kt[i][j]) + a2[j] - m2);
+          }
+          x1 = warp_sum(x1); x2 = warp_sum(x2);
+          r1[i] = nu - (m1 + logf(x1)); r2[i] = nu - (m2 + logf(x2));
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            if (warp + 32 * i < B) {
+              vec[half ? 1 : 0][warp + 32 * i] = r1[i];
+              vec[half ? 3 : 2][warp + 32 * i] = r2[i];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = tid; r < B; r += 1024) {
+    if (scaling) {
+      u1[r] = (nu - mx) + logf(vec[0][r]); v1[r] = logf(vec[1][r]);
+      u2[r] = (nu - mx) + logf(vec[2][r]); v2[r] = logf(vec[3][r]);
+    } else {
+      u1[r] = vec[0][r]; v1[r] = vec[1][r]; u2[r] = vec[2][r]; v2[r] = vec[3][r];
+    }
+  }
+}
+
 }  // namespace nr
 
 using namespace nr;
@@ -194,6 +395,30 @@ extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters
   NR_CHECK_ARG(workspace_bytes >= 256, "nr_sinkhorn: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   {
+    const size_t smem1 = ((size_t)2 * B * B + (size_t)4 * B) * sizeof(float);
+    const char* var = getenv("NR_SINKHORN_VARIANT");      // tuning knob: "cta" | "cluster" | "grid"
+    const bool want_cta = var && !strcmp(var, "cta");
+    if (B <= 128 && (!var || !strcmp(var, "reg"))) {
+      const int nb = (int)((B + 31) / 32);
+      switch (nb) {
+        case 1: sinkhorn_reg_kernel<1><<<1, 1024, 0, s>>>(G, GT, (int)B, iters, u1, v1, u2, v2); break;
+        case 2: sinkhorn_reg_kernel<2><<<1, 1024, 0, s>>>(G, GT, (int)B, iters, u1, v1, u2, v2); break;
+        case 3: sinkhorn_reg_kernel<3><<<1, 1024, 0, s>>>(G, GT, (int)B, iters, u1, v1, u2, v2); break;
+        default: sinkhorn_reg_kernel<4><<<1, 1024, 0, s>>>(G, GT, (int)B, iters, u1, v1, u2, v2); break;
+      }
+      NR_CHECK_LAUNCH("nr_sinkhorn(reg)");
+      return 0;
+    }
+    if (smem1 <= 225 * 1024 && iters >= 1 && want_cta) {
+      if (smem1 > 48 * 1024)
+        NR_CUDA(cudaFuncSetAttribute(sinkhorn_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      sinkhorn_cta_kernel<<<1, SKC_THREADS, smem1, s>>>(G, GT, (int)B, iters, u1, v1, u2, v2);
+      NR_CHECK_LAUNCH("nr_sinkhorn(cta)");
+      return 0;
+    }
+  }
+  const char* var2 = getenv("NR_SINKHORN_VARIANT");
+  if (!var2 || strcmp(var2, "grid")) {
     bool launched = false;
     if (int e = sinkhorn_cluster_launch(G, GT, (int)B, iters, u1, v1, u2, v2, s, &launched)) return e;
     if (launched) return 0;

@@ -266,13 +266,21 @@ class TokenMLPFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         x2, h, w1, w2 = ctx.saved_tensors
-        d = dout.reshape(-1, 1).float()
+        d = _f32c(dout).reshape(-1)
+        T, H = h.shape
+        st = _stream()
+        # one pass over h: dh, and per-CTA partials of db1 / dw2 (summed deterministically below)
+        dh = torch.empty_like(h)
+        nch = _lib.load().nr_mlp_chunks(T)
+        partials = torch.empty(2 * H, nch, dtype=torch.float32, device=h.device)
+        _call("nr_mlp_hidden_bwd", _p(h), _p(d), _p(_f32c(w2).reshape(-1)), T, H, _p(dh), _p(partials), st)
+        sums = torch.empty(2 * H, dtype=torch.float32, device=h.device)
+        _call("nr_vec_sums", _p(partials), 2 * H, nch, None, _p(sums), st)
+        db1 = sums[:H] if ctx.needs_input_grad[2] else None
+        dw2 = sums[H:].reshape(1, H) if ctx.needs_input_grad[3] else None
+        db2 = d.sum().reshape(1) if ctx.needs_input_grad[4] else None
         with _tf32(ctx.tf32):
-            dh = (d * w2.reshape(1, -1)) * (h > 0)
-            dw2 = (d.t() @ h) if ctx.needs_input_grad[3] else None
-            db2 = d.sum().reshape(1) if ctx.needs_input_grad[4] else None
             dw1 = (dh.t() @ x2) if ctx.needs_input_grad[1] else None
-            db1 = dh.sum(0) if ctx.needs_input_grad[2] else None
             dx = (dh @ w1).reshape(ctx.shape) if ctx.needs_input_grad[0] else None
         return dx, dw1, db1, dw2, db2, None
 
