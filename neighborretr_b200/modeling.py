@@ -30,11 +30,11 @@ allgather2 = AllGather2.apply
 DEFAULT_PRECISION = os.environ.get("NR_HEAD_PRECISION", "bf16")
 
 
-def _token_weights(mlp, feat, mask, lowp=False):
+def _token_weights(mlp, feat, mask, lowp=False, sum_param_grads=False):
     """softmax over tokens of the MLP logits, masked tokens filled with -9e15 (reference :485-492).
     lowp: run the Linear layers as TF32 tensor-core GEMMs (cuBLAS) in both passes — the bf16 head mode;
     otherwise plain fp32 GEMMs.  The softmax stays fp32."""
-    logit = ops.token_mlp_logits(mlp, feat, lowp)
+    logit = ops.token_mlp_logits(mlp, feat, lowp, sum_param_grads)
     if mask is not None:
         logit = logit.masked_fill((1 - mask).to(torch.bool), float(-9e15))
     return torch.softmax(logit, dim=-1)
@@ -205,8 +205,36 @@ class HeadMixin:
         self.mb_mask_v = ops.fifo_update(video_mask.to(self.mb_mask_v.dtype), self.mb_mask_v, cap)
 
     # --- everything of reference forward() below the encoders (:269-312) -----------------------------
+    def _head_forward_sharded(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats):
+        """W > 1: row-block sharded head (sharded.py) on the LOCAL batch; gathers happen inside."""
+        from .sharded import sharded_head
+        cfg = self.config
+        lowp = self._head_precision() == "bf16"
+        tw = _token_weights(self.text_weight_fc, text_feat, text_mask, lowp, True)
+        vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp, True)
+        tw_mb = _token_weights(self.text_weight_fc, self.mb_feat_t, self.mb_mask_t, lowp, True)
+        vw_mb = _token_weights(self.video_weight_fc, self.mb_feat_v, self.mb_mask_v, lowp, True)
+        gtf, gvf = global_feats
+        out5, nbr, text_all, video_all, tm_all, vm_all = sharded_head(
+            text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, self.clip.logit_scale.exp(), text_mask, video_mask,
+            self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v, centrality_scale=cfg.centrality_scale,
+            beta=cfg.beta, num_neighbors=cfg.num_neighbors, temperature=cfg.temperature,
+            uniform_weight=cfg.uniform_weight, neighbor_weight=cfg.neighbor_weight, kl_weight=cfg.kl_weight,
+            precision=self._head_precision(), bwd_precision=self._head_bwd_precision())
+        self.last_neighbors = (nbr[0], nbr[1])
+        with torch.no_grad():
+            self.update_memory_bank(allgather(idx, cfg), text_all, video_all, tm_all, vm_all)
+        return tuple(out5.unbind(0))
+
     def head_forward(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats=None):
         cfg = self.config
+        if (getattr(cfg, "world_size", 1) > 1 and getattr(self, "head_sharded", getattr(cfg, "head_sharded", True))
+                and torch.distributed.is_available() and torch.distributed.is_initialized()):
+            if global_feats is None:
+                global_feats = self.merge_global_features(text_feat, video_feat, text_mask, video_mask)
+            if global_feats[0].shape[1] == 1 and global_feats[1].shape[1] == 1 and self.mb_feat_v.dim() == 3 \
+                    and self.mb_feat_v.shape[0] > 0:
+                return self._head_forward_sharded(text_feat, video_feat, text_mask, video_mask, idx, global_feats)
         if getattr(cfg, "world_size", 1) > 1:
             idx = allgather(idx, cfg)
             text_feat = allgather(text_feat, cfg)

@@ -97,7 +97,7 @@ class Prepared:
     """L2-normalised tokens of one modality: fp32 copy (backward / fp32 mode), optional bf16 operand
     copy (tensor-core mode), inverse norms and per-CTA column-sum partials."""
 
-    __slots__ = ("xn", "xn_bf16", "xnT_bf16", "inv_norm", "partials", "rows", "n", "d", "r")
+    __slots__ = ("xn", "xn_bf16", "xnT_bf16", "inv_norm", "partials", "rows", "n", "d", "r", "_parent", "_lo")
 
     def __init__(self, x, bf16=False, colsum=False, normalize=True):
         _req_cuda(x)
@@ -105,6 +105,7 @@ class Prepared:
         self.r, self.n, self.d = x.shape
         self.rows = self.r * self.n
         self.xnT_bf16 = None
+        self._parent, self._lo = None, 0
         dev = x.device
         if not normalize:        # global_level: raw dot products (reference modeling.py:525), fp32 only
             self.xn, self.xn_bf16, self.inv_norm, self.partials = x, None, None, None
@@ -125,11 +126,30 @@ class Prepared:
         or the transposed bf16 copy [d, ld] built on first use."""
         if prec != NR_PREC_BF16:
             return self.xn, 0
+        parent = getattr(self, "_parent", None)
+        if parent is not None:          # block view: columns [lo*n, (lo+rows)) of the parent's transposed copy
+            pt, ld = parent.bwd_source(prec)
+            if (self._lo * self.n) % 8:
+                raise RuntimeError("row block offset must keep the transposed operand 16-byte aligned")
+            return pt[:, self._lo * self.n:], ld
         if self.xnT_bf16 is None:
             ld = (self.rows + 7) // 8 * 8
             self.xnT_bf16 = torch.empty(self.d, ld, dtype=torch.bfloat16, device=self.xn.device)
             _call("nr_transpose_tokens_bf16", _p(self.xn_bf16), self.rows, self.d, _p(self.xnT_bf16), ld, _stream())
         return self.xnT_bf16, self.xnT_bf16.shape[1]
+
+    def block(self, lo, n):
+        """View of samples [lo, lo+n) (a rank's rows of the gathered batch) usable wherever a Prepared is:
+        same storage, pointer offsets only."""
+        v = Prepared.__new__(Prepared)
+        v.r, v.n, v.d, v.rows = n, self.n, self.d, n * self.n
+        v.xn = self.xn[lo:lo + n]
+        v.xn_bf16 = self.xn_bf16[lo:lo + n] if self.xn_bf16 is not None else None
+        v.inv_norm = self.inv_norm[lo * self.n:(lo + n) * self.n] if self.inv_norm is not None else None
+        v.partials = None
+        v.xnT_bf16 = None
+        v._parent, v._lo = self, lo
+        return v
 
     def backward(self, dxn, add_vec=None):
         if self.inv_norm is None:
@@ -285,9 +305,14 @@ class TokenMLPFunction(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, None
 
 
-def token_mlp_logits(mlp, feat, tf32):
-    """mlp: nn.Sequential(Linear, ReLU, Linear) with the reference's parameter names."""
-    return TokenMLPFunction.apply(feat, mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias, bool(tf32))
+def token_mlp_logits(mlp, feat, tf32, sum_param_grads=False):
+    """mlp: nn.Sequential(Linear, ReLU, Linear) with the reference's parameter names.  sum_param_grads: the
+    parameter gradients are all-reduced (SUM) over ranks in backward (row-sharded head, sharded.py)."""
+    ps = (mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias)
+    if sum_param_grads:
+        from .sharded import SumGradAcrossRanks
+        ps = tuple(SumGradAcrossRanks.apply(p) for p in ps)
+    return TokenMLPFunction.apply(feat, *ps, bool(tf32))
 
 
 # ------------------------------------------------------------------------------------------------

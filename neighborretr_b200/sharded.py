@@ -1,0 +1,240 @@
+"""Row-block sharded retrieval head for W > 1 ranks.
+
+The reference replicates the whole [B,B] head on every rank after the gather (modeling.py:274-312).  Here rank r
+owns rows r*b.. of S (text->video direction) and of S^T (video->text direction): two [b,B] blocks plus its rows of
+the two bank similarities, so all per-row work (top-k, min/max, log-sum-exps, KL, InfoNCE, neighbour loss) is
+rank-local.  Exchanges: all_gather of the (features, masks, global features, token weights) and of the bank
+centrality vectors c [b]->[B]; all_reduce of the 8 loss partial sums; in backward all_reduce of dc / d logit_scale
+and reduce_scatter(SUM) of the gradients w.r.t. the gathered tensors.  Every rank returns the GLOBAL loss values;
+its feature gradients equal rows [r*b,(r+1)*b) of the single-process full-batch gradient (what AllGather.backward
+yields in the reference), and head-parameter gradients equal the full gradients once summed over ranks
+(`SumGradAcrossRanks`), as in the reference where every rank holds the full head gradient.
+
+Sinkhorn and the global similarity G [B,B] are replicated (2*B^2*D flops, no exchange inside the 100 iterations).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import NR_NSAVE, NR_PREC_BF16
+from .fused import ALL_LOSSES, _combine_matrix, _fwd_dir
+from .ops import Prepared, _call, _f32c, _mask, _p, _req_cuda, _stream
+
+
+# ---- collectives (contiguous buffers, default process group) ------------------------------------------------------
+def _gather(t):
+    t = t.contiguous()
+    w = dist.get_world_size()
+    out = torch.empty((w * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    return out
+
+
+def _reduce_scatter(t, b):
+    """Sum over ranks of t [W*b, ...] and return this rank's rows [b, ...]."""
+    t = t.contiguous()
+    out = torch.empty((b,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    if dist.get_backend() == "nccl":
+        dist.reduce_scatter_tensor(out, t, op=dist.ReduceOp.SUM)
+    else:                                   # gloo on CUDA tensors (single-GPU emulation in tests)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        r = dist.get_rank()
+        out.copy_(t[r * b:(r + 1) * b])
+    return out
+
+
+class SumGradAcrossRanks(torch.autograd.Function):
+    """Identity whose backward all-reduces (SUM) the gradient: applied to the head parameters so that every rank
+    ends up with the FULL parameter gradient, like the reference's replicated head."""
+
+    @staticmethod
+    def forward(ctx, p):
+        return p.view_as(p)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return g
+
+
+class ShardedHeadFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale, tm_l, vm_l, mb_feat_t,
+                mb_feat_v, mb_mask_t, mb_mask_v, hp):
+        cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
+        _req_cuda(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale)
+        W, r = dist.get_world_size(), dist.get_rank()
+        dev = text_l.device
+        st = _stream()
+        b = text_l.shape[0]
+        B, lo = W * b, r * b
+        d = text_l.shape[-1]
+        # ---- exchange 1: features, masks, global features, token weights
+        text, video = _gather(_f32c(text_l)), _gather(_f32c(video_l))
+        tm, vm = _gather(_mask(tm_l)), _gather(_mask(vm_l))
+        g2, v2 = _gather(_f32c(gt_l).reshape(b, d)), _gather(_f32c(gv_l).reshape(b, d))
+        tw, vw = _gather(_f32c(tw_l)), _gather(_f32c(vw_l))
+        tw_mb, vw_mb = _f32c(tw_mb), _f32c(vw_mb)
+        mtm, mvm = _mask(mb_mask_t), _mask(mb_mask_v)
+        bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
+        T = Prepared(text, bf16=bf, colsum=True)
+        V = Prepared(video, bf16=bf, colsum=True)
+        MT = Prepared(mb_feat_t, bf16=bf)
+        MV = Prepared(mb_feat_v, bf16=bf)
+        Tl, Vl = T.block(lo, b), V.block(lo, b)
+        M = MT.r
+        nt, nv = T.n, V.n
+        tw_lc, vw_lc, tm_lc, vm_lc = tw[lo:lo + b], vw[lo:lo + b], tm[lo:lo + b], vm[lo:lo + b]
+        f32 = dict(dtype=torch.float32, device=dev)
+        S_row = torch.empty(b, B, **f32); S_col = torch.empty(b, B, **f32)
+        mb_t2v = torch.empty(b, M, **f32); mb_v2t = torch.empty(b, M, **f32)
+        p1, y1 = _fwd_dir(prec, Tl, V, tw_lc, tm_lc, vm, S_row, B, 1, None, 0, 0, 0)      # H(text_l, video)
+        p2, y2 = _fwd_dir(prec, V, Tl, vw, vm, tm_lc, S_row, 1, B, None, 0, 0, 1)         # H(video, text_l)^T
+        p3, y3 = _fwd_dir(prec, Vl, T, vw_lc, vm_lc, tm, S_col, B, 1, None, 0, 0, 0)      # H(video_l, text)
+        p4, y4 = _fwd_dir(prec, T, Vl, tw, tm, vm_lc, S_col, 1, B, None, 0, 0, 1)         # H(text, video_l)^T
+        pA, yA = _fwd_dir(prec, Tl, MV, tw_lc, tm_lc, mvm, mb_t2v, M, 1, None, 0, 0, 0)
+        pB, yB = _fwd_dir(prec, MV, Tl, vw_mb, mvm, tm_lc, mb_t2v, 1, M, None, 0, 0, 1)
+        pD, yD = _fwd_dir(prec, Vl, MT, vw_lc, vm_lc, mtm, mb_v2t, M, 1, None, 0, 0, 0)
+        pC, yC = _fwd_dir(prec, MT, Vl, tw_mb, mtm, vm_lc, mb_v2t, 1, M, None, 0, 0, 1)
+        c_l = torch.empty(2, b, **f32)
+        _call("nr_row_mean", _p(mb_t2v), M, b, M, _p(c_l[0]), st)
+        _call("nr_row_mean", _p(mb_v2t), M, b, M, _p(c_l[1]), st)
+        # ---- exchange 2: bank centrality of every sample (indexed by COLUMN in the neighbour loss)
+        cb = _gather(c_l.unsqueeze(0)).permute(1, 0, 2).reshape(2, B).contiguous()       # [c_t2v ; c_v2t]
+        G = g2 @ v2.t()
+        GT = v2 @ g2.t()
+        duals = torch.empty(4, B, **f32)
+        ws = torch.empty(256, dtype=torch.uint8, device=dev)
+        _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]), _p(duals[3]),
+              _p(ws), 256, st)
+        mean = torch.empty(2, d, **f32); gn = torch.empty(2, b, d, **f32)
+        ginv = torch.empty(2, b, **f32); w = torch.empty(2, b, **f32)
+        _call("nr_centrality_fwd", _p(T.partials), T.partials.shape[0], T.rows, _p(g2[lo:lo + b]), b, d, cs,
+              _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), st, launches=2)
+        _call("nr_centrality_fwd", _p(V.partials), V.partials.shape[0], V.rows, _p(v2[lo:lo + b]), b, d, cs,
+              _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), st, launches=2)
+        ls = _f32c(logit_scale).reshape(1)
+        row_out = torch.zeros(2, 4, b, **f32)
+        nbr = torch.empty(2, b, k, dtype=torch.int32, device=dev)
+        saved = torch.empty(2, b, NR_NSAVE, **f32)
+        _call("nr_row_losses_fwd", _p(S_row), B, _p(G[lo:lo + b]), B, _p(cb[1]), _p(w[0]), _p(duals[0][lo:lo + b]),
+              _p(duals[1]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[0]), _p(nbr[0]), _p(saved[0]), st)
+        _call("nr_row_losses_fwd", _p(S_col), B, _p(GT[lo:lo + b]), B, _p(cb[0]), _p(w[1]), _p(duals[2][lo:lo + b]),
+              _p(duals[3]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[1]), _p(nbr[1]), _p(saved[1]), st)
+        sums = torch.empty(8, **f32)
+        _call("nr_vec_sums", _p(row_out), 8, b, None, _p(sums), st)
+        # ---- exchange 3: loss partial sums
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        m54 = _combine_matrix(B, wu, wn, wkl, dev)
+        out5 = m54 @ (sums[:4] + sums[4:])
+        ctx.hp, ctx.dims = hp, (W, r, b, B, lo, M, d, nt, nv)
+        ctx.objs = (T, V, MT, MV, Tl, Vl)
+        ctx.save_for_backward(tw, vw, tw_mb, vw_mb, tm, vm, mtm, mvm, S_row, S_col, G, GT, cb, duals, w, ls, nbr, saved,
+                              mean, gn, ginv, g2, v2, m54, p1, y1, p2, y2, p3, y3, p4, y4, pA, yA, pB, yB, pC, yC, pD, yD)
+        ctx.gshape = (gt_l.shape, gv_l.shape)
+        ctx.mark_non_differentiable(nbr, text, video, tm, vm)
+        # the gathered batch is also what the memory-bank FIFO stores (reference modeling.py:309-310)
+        return out5, nbr, text, video, tm, vm
+
+    @staticmethod
+    def backward(ctx, g5, _gn, _g1, _g2, _g3, _g4):
+        (tw, vw, tw_mb, vw_mb, tm, vm, mtm, mvm, S_row, S_col, G, GT, cb, duals, w, ls, nbr, saved, mean, gn, ginv, g2,
+         v2, m54, p1, y1, p2, y2, p3, y3, p4, y4, pA, yA, pB, yB, pC, yC, pD, yD) = ctx.saved_tensors
+        cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = ctx.hp
+        W, r, b, B, lo, M, d, nt, nv = ctx.dims
+        T, V, MT, MV, Tl, Vl = ctx.objs
+        dev = S_row.device
+        st = _stream()
+        f32 = dict(dtype=torch.float32, device=dev)
+        gscale = m54.t() @ _f32c(g5)
+        z = torch.zeros(2 * B + 1 + 2 * b, **f32)                      # [dc_t2v | dc_v2t | dls | dw_t | dw_v]
+        dcs, dls, dw = z[:2 * B + 1], z[2 * B:2 * B + 1], z[2 * B + 1:].view(2, b)
+        dc = z[:2 * B].view(2, B)
+        dS_row = torch.empty(b, B, **f32); dS_col = torch.empty(b, B, **f32)
+        dG1 = torch.empty(b, B, **f32); dG2 = torch.empty(b, B, **f32)
+        _call("nr_row_losses_bwd", _p(S_row), B, _p(G[lo:lo + b]), B, _p(cb[1]), _p(w[0]), _p(duals[0][lo:lo + b]),
+              _p(duals[1]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(nbr[0]), _p(saved[0]), _p(gscale),
+              _p(dS_row), B, _p(dG1), B, _p(dc[1]), _p(dw[0]), _p(dls), st)
+        _call("nr_row_losses_bwd", _p(S_col), B, _p(GT[lo:lo + b]), B, _p(cb[0]), _p(w[1]), _p(duals[2][lo:lo + b]),
+              _p(duals[3]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(nbr[1]), _p(saved[1]), _p(gscale),
+              _p(dS_col), B, _p(dG2), B, _p(dc[0]), _p(dw[1]), _p(dls), st)
+        # ---- exchange 4: gradients of the gathered bank-centrality vectors and of logit_scale (tiny)
+        dist.all_reduce(dcs, op=dist.ReduceOp.SUM)
+        dc_l = dc[:, lo:lo + b].contiguous()                           # this rank's samples
+        # global similarity: dG has a row block (direction 1) and a column block (direction 2) on this rank
+        dG = torch.zeros(B, B, **f32)
+        dG[lo:lo + b] += dG1
+        dG[:, lo:lo + b] += dG2.t()
+        dg_all = dG @ v2                                               # partial over ranks
+        dv_all = dG.t() @ g2
+        dmean = torch.empty(2, d, **f32)
+        dgl = torch.empty(2, b, d, **f32)
+        _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), b, d, cs, T.rows,
+              _p(dgl[0]), 0, _p(dmean[0]), st, launches=2)
+        _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), b, d, cs, V.rows,
+              _p(dgl[1]), 0, _p(dmean[1]), st, launches=2)
+        dg_all[lo:lo + b] += dgl[0]
+        dv_all[lo:lo + b] += dgl[1]
+        # ---- token-pair products into full-size (gathered) gradient buffers
+        dtn = torch.zeros(T.rows, d, **f32); dvn = torch.zeros(V.rows, d, **f32)
+        dtw = torch.zeros(B, nt, **f32); dvw = torch.zeros(B, nv, **f32)
+        dtw_mb = torch.zeros_like(tw_mb); dvw_mb = torch.zeros_like(vw_mb)
+        dtn_l, dvn_l = dtn[lo * nt:(lo + b) * nt], dvn[lo * nv:(lo + b) * nv]
+        dtw_l, dvw_l = dtw[lo:lo + b], dvw[lo:lo + b]
+        tw_l, vw_l, tm_l, vm_l = tw[lo:lo + b], vw[lo:lo + b], tm[lo:lo + b], vm[lo:lo + b]
+        vs, vld = V.bwd_source(bprec); ts, tld = T.bwd_source(bprec)
+        vls, vlld = Vl.bwd_source(bprec); tls, tlld = Tl.bwd_source(bprec)
+        mvs, mvld = MV.bwd_source(bprec); mts, mtld = MT.bwd_source(bprec)
+        X, Y, Wg = "nr_maxsim_bwd_x", "nr_maxsim_bwd_y", "nr_maxsim_bwd_w"
+        # H1 = H(text_l, video): dH1[a_l, bb] = .5 dS_row
+        _call(X, bprec, _p(vs), vld, _p(tw_l), _p(tm_l), _p(vm), _p(y1), _p(dS_row), B, 1, 0.5, b, nt, B, nv, d, _p(dtn_l), st)
+        _call(Y, bprec, _p(tls), tlld, _p(tw_l), _p(tm_l), _p(vm), _p(y1), _p(dS_row), B, 1, 0.5, b, nt, B, nv, d, _p(dvn), st)
+        _call(Wg, _p(p1), _p(dS_row), B, 1, 0.5, b, nt, B, _p(dtw_l), st)
+        # H2 = H(video, text_l): dH2[bb, a_l] = .5 dS_row[a_l, bb]
+        _call(X, bprec, _p(tls), tlld, _p(vw), _p(vm), _p(tm_l), _p(y2), _p(dS_row), 1, B, 0.5, B, nv, b, nt, d, _p(dvn), st)
+        _call(Y, bprec, _p(vs), vld, _p(vw), _p(vm), _p(tm_l), _p(y2), _p(dS_row), 1, B, 0.5, B, nv, b, nt, d, _p(dtn_l), st)
+        _call(Wg, _p(p2), _p(dS_row), 1, B, 0.5, B, nv, b, _p(dvw), st)
+        # H3 = H(video_l, text): dH3[v_l, a] = .5 dS_col
+        _call(X, bprec, _p(ts), tld, _p(vw_l), _p(vm_l), _p(tm), _p(y3), _p(dS_col), B, 1, 0.5, b, nv, B, nt, d, _p(dvn_l), st)
+        _call(Y, bprec, _p(vls), vlld, _p(vw_l), _p(vm_l), _p(tm), _p(y3), _p(dS_col), B, 1, 0.5, b, nv, B, nt, d, _p(dtn), st)
+        _call(Wg, _p(p3), _p(dS_col), B, 1, 0.5, b, nv, B, _p(dvw_l), st)
+        # H4 = H(text, video_l): dH4[a, v_l] = .5 dS_col[v_l, a]
+        _call(X, bprec, _p(vls), vlld, _p(tw), _p(tm), _p(vm_l), _p(y4), _p(dS_col), 1, B, 0.5, B, nt, b, nv, d, _p(dtn), st)
+        _call(Y, bprec, _p(ts), tld, _p(tw), _p(tm), _p(vm_l), _p(y4), _p(dS_col), 1, B, 0.5, B, nt, b, nv, d, _p(dvn_l), st)
+        _call(Wg, _p(p4), _p(dS_col), 1, B, 0.5, B, nt, b, _p(dtw), st)
+        # bank pairs of this rank's samples: dH = dc_l[a]/M broadcast over the bank rows (stride 0)
+        sc = 0.5 / M
+        _call(X, bprec, _p(mvs), mvld, _p(tw_l), _p(tm_l), _p(mvm), _p(yA), _p(dc_l[0]), 1, 0, sc, b, nt, M, nv, d, _p(dtn_l), st)
+        _call(Wg, _p(pA), _p(dc_l[0]), 1, 0, sc, b, nt, M, _p(dtw_l), st)
+        _call(Y, bprec, _p(mvs), mvld, _p(vw_mb), _p(mvm), _p(tm_l), _p(yB), _p(dc_l[0]), 0, 1, sc, M, nv, b, nt, d, _p(dtn_l), st)
+        _call(Wg, _p(pB), _p(dc_l[0]), 0, 1, sc, M, nv, b, _p(dvw_mb), st)
+        _call(X, bprec, _p(mts), mtld, _p(vw_l), _p(vm_l), _p(mtm), _p(yD), _p(dc_l[1]), 1, 0, sc, b, nv, M, nt, d, _p(dvn_l), st)
+        _call(Wg, _p(pD), _p(dc_l[1]), 1, 0, sc, b, nv, M, _p(dvw_l), st)
+        _call(Y, bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm_l), _p(yC), _p(dc_l[1]), 0, 1, sc, M, nt, b, nv, d, _p(dvn_l), st)
+        _call(Wg, _p(pC), _p(dc_l[1]), 0, 1, sc, M, nt, b, _p(dtw_mb), st)
+        dtext_all = T.backward(dtn, add_vec=dmean[0])
+        dvideo_all = V.backward(dvn, add_vec=dmean[1])
+        # ---- exchange 5: sum the partial gradients of the gathered tensors, keep this rank's rows
+        dtext = _reduce_scatter(dtext_all, b)
+        dvideo = _reduce_scatter(dvideo_all, b)
+        dgt = _reduce_scatter(dg_all, b)
+        dgv = _reduce_scatter(dv_all, b)
+        dtw_o = _reduce_scatter(dtw, b)
+        dvw_o = _reduce_scatter(dvw, b)
+        ctx.objs = None
+        gs_t, gs_v = ctx.gshape
+        return (dtext, dvideo, dgt.reshape(gs_t), dgv.reshape(gs_v), dtw_o, dvw_o, dtw_mb, dvw_mb, dls.reshape(()),
+                None, None, None, None, None, None, None)
+
+
+def sharded_head(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale, tm_l, vm_l, mb_feat_t, mb_feat_v,
+                 mb_mask_t, mb_mask_v, *, centrality_scale, beta, num_neighbors, temperature, uniform_weight,
+                 neighbor_weight, kl_weight, precision="bf16", bwd_precision=None, iters=50):
+    hp = (float(centrality_scale), float(beta), int(num_neighbors), float(temperature), int(iters),
+          float(uniform_weight), float(neighbor_weight), float(kl_weight), ops.PRECISIONS[precision],
+          ops.PRECISIONS[bwd_precision or precision])
+    return ShardedHeadFunction.apply(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale, tm_l, vm_l,
+                                     mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp)
