@@ -287,7 +287,7 @@ def run_ours(args):
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step(resident, False)
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph
     gstep = None
     if use_graph:
         from neighborretr_b200.graph import FIELDS, GraphedHeadStep
@@ -321,9 +321,21 @@ def run_ours(args):
     timed(lambda: step(resident, False), ksteps)
     kt = ops.KERNEL_TIMER.collect()
     ops.KERNEL_TIMER.disable()
-    if rank != 0:
+    def finish():
+        """Multi-rank exit: captured NCCL work keeps the communicator busy, and destroy_process_group() then
+        blocks; release the graph, synchronise, and leave without tearing NCCL down."""
         if world > 1:
-            dist.destroy_process_group()
+            nonlocal gstep
+            if gstep is not None:
+                gstep.graph.reset()
+                gstep = None
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     B = B_PER_GPU * world
@@ -366,11 +378,13 @@ def run_ours(args):
                                 "sample": "4 fwd+bwd steps (after 1 warm-up) of oracle/head.py compute_losses on the "
                                           f"same {args.shape} b={B_PER_GPU} batch, torch CPU fp32"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
+    if os.environ.get("NR_DEBUG_HANG"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["NR_DEBUG_HANG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -23,8 +23,7 @@ GRAD_FIELDS = ("text_feat", "video_feat", "global_text", "global_video")
 
 class GraphedHeadStep:
     def __init__(self, model, example, warmup=3):
-        if getattr(model.config, "world_size", 1) != 1:
-            raise RuntimeError("GraphedHeadStep: single-process capture only")
+        self.world = getattr(model.config, "world_size", 1)
         self.model = model
         dev = next(model.parameters()).device
         self.static = {}
@@ -49,7 +48,8 @@ class GraphedHeadStep:
         self._zero_grads()
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES["count"]
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads (the NCCL watchdog polling events) may keep making CUDA calls during capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.losses = self._body()
         self.launches_per_replay = ops.LAUNCHES["count"] - n0
         for n in self.bank_names:                       # warm-up steps advanced the bank: restore it in place
@@ -63,16 +63,22 @@ class GraphedHeadStep:
     def _body(self):
         m, s = self.model, self.static
         cfg = m.config
-        logit_scale = m.clip.logit_scale.exp()
-        losses = m._compute_losses(s["text_feat"], s["video_feat"], s["text_mask"], s["video_mask"], m.mb_feat_t,
-                                   m.mb_feat_v, m.mb_mask_t, m.mb_mask_v, cfg.centrality_scale, cfg.beta,
-                                   cfg.num_neighbors, cfg.temperature, logit_scale,
-                                   global_feats=(s["global_text"], s["global_video"]))
+        if self.world == 1:
+            logit_scale = m.clip.logit_scale.exp()
+            losses = m._compute_losses(s["text_feat"], s["video_feat"], s["text_mask"], s["video_mask"], m.mb_feat_t,
+                                       m.mb_feat_v, m.mb_mask_t, m.mb_mask_v, cfg.centrality_scale, cfg.beta,
+                                       cfg.num_neighbors, cfg.temperature, logit_scale,
+                                       global_feats=(s["global_text"], s["global_video"]))
+            new_rows = (s["idx"], s["text_feat"], s["video_feat"], s["text_mask"], s["video_mask"])
+        else:       # row-block sharded head; the NCCL collectives are captured in the graph
+            from .until_module import _gather_contiguous
+            losses, (ta, va, tma, vma) = m._sharded_losses(s["text_feat"], s["video_feat"], s["text_mask"],
+                                                           s["video_mask"], (s["global_text"], s["global_video"]))
+            new_rows = (_gather_contiguous(s["idx"], self.world), ta, va, tma, vma)
         losses[0].backward()
         with torch.no_grad():
             cap = m.mb_feat_v.shape[0]
-            for name, new in (("mb_ind", s["idx"]), ("mb_feat_t", s["text_feat"]), ("mb_feat_v", s["video_feat"]),
-                              ("mb_mask_t", s["text_mask"]), ("mb_mask_v", s["video_mask"])):
+            for name, new in zip(("mb_ind", "mb_feat_t", "mb_feat_v", "mb_mask_t", "mb_mask_v"), new_rows):
                 bank = getattr(m, name)
                 bank.copy_(ops.fifo_update(new.detach().to(bank.dtype), bank, cap))
         return torch.stack([x.detach() for x in losses])

@@ -205,8 +205,9 @@ class HeadMixin:
         self.mb_mask_v = ops.fifo_update(video_mask.to(self.mb_mask_v.dtype), self.mb_mask_v, cap)
 
     # --- everything of reference forward() below the encoders (:269-312) -----------------------------
-    def _head_forward_sharded(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats):
-        """W > 1: row-block sharded head (sharded.py) on the LOCAL batch; gathers happen inside."""
+    def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats):
+        """W > 1: row-block sharded head (sharded.py) on the LOCAL batch; gathers happen inside.
+        Returns (5 losses, gathered (text, video, text_mask, video_mask))."""
         from .sharded import sharded_head
         cfg = self.config
         lowp = self._head_precision() == "bf16"
@@ -222,9 +223,14 @@ class HeadMixin:
             uniform_weight=cfg.uniform_weight, neighbor_weight=cfg.neighbor_weight, kl_weight=cfg.kl_weight,
             precision=self._head_precision(), bwd_precision=self._head_bwd_precision())
         self.last_neighbors = (nbr[0], nbr[1])
+        return tuple(out5.unbind(0)), (text_all, video_all, tm_all, vm_all)
+
+    def _head_forward_sharded(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats):
+        losses, (text_all, video_all, tm_all, vm_all) = self._sharded_losses(text_feat, video_feat, text_mask,
+                                                                             video_mask, global_feats)
         with torch.no_grad():
-            self.update_memory_bank(allgather(idx, cfg), text_all, video_all, tm_all, vm_all)
-        return tuple(out5.unbind(0))
+            self.update_memory_bank(allgather(idx, self.config), text_all, video_all, tm_all, vm_all)
+        return losses
 
     def head_forward(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats=None):
         cfg = self.config
