@@ -34,54 +34,89 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-// LSE over j of (row[j] + vec[j]); vec is read through L2 (written by other CTAs this launch)
-__device__ __forceinline__ float warp_row_lse(const float* __restrict__ row, const float* vec, int B, int lane) {
+// Grid variant (any B): every CTA keeps its slab of rows of K = exp(G - max G) and of K^T in shared memory (or
+// streams them from L2 when they do not fit), the four scaling vectors live in global memory and are staged
+// into shared memory once per half-iteration (one coalesced L2 read instead of a dependent load per element).
+// Scaling domain alpha = 1/(K beta), beta = 1/(K^T alpha) when max G - min G <= 30, log domain otherwise.
+__device__ __forceinline__ float warp_dot(const float* __restrict__ row, const float* __restrict__ vec, int B, int lane) {
+  float s = 0.f;
+  for (int j = lane; j < B; j += 32) s = fmaf(row[j], vec[j], s);
+  return warp_sum(s);
+}
+__device__ __forceinline__ float warp_lse(const float* __restrict__ row, const float* __restrict__ vec, int B, int lane) {
   float m = NR_NEG_INF;
-  for (int j = lane; j < B; j += 32) m = fmaxf(m, row[j] + __ldcg(vec + j));
+  for (int j = lane; j < B; j += 32) m = fmaxf(m, row[j] + vec[j]);
   m = warp_max(m);
   float s = 0.f;
-  for (int j = lane; j < B; j += 32) s += expf(row[j] + __ldcg(vec + j) - m);
+  for (int j = lane; j < B; j += 32) s += expf(row[j] + vec[j] - m);
   s = warp_sum(s);
   return m + logf(s);
 }
 
 __global__ void __launch_bounds__(SK_THREADS)
 sinkhorn_kernel(const float* __restrict__ G, const float* __restrict__ GT, int B, int iters, int rows_per_cta,
-                int resident, float* u1, float* v1, float* u2, float* v2, unsigned int* counter) {
+                int resident, float* u1, float* v1, float* u2, float* v2, unsigned int* counter, float* gstat) {
   extern __shared__ float sm[];
+  __shared__ float red[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = blockIdx.x * rows_per_cta;
   const int nr = max(0, min(rows_per_cta, B - r0));
-  float* Gs = sm;
-  float* GTs = sm + (size_t)rows_per_cta * B;
-  if (resident) {
-    for (int e = tid; e < nr * B; e += SK_THREADS) {
-      Gs[e] = G[(size_t)r0 * B + e];
-      GTs[e] = GT[(size_t)r0 * B + e];
-    }
+  float* vs = sm;                                   // [2][B] staged source vectors (chain 1, chain 2)
+  float* Gs = sm + 2 * (size_t)B;
+  float* GTs = Gs + (size_t)rows_per_cta * B;
+  // global max / min of G: per-CTA partials through global memory, combined after the first barrier
+  float mx = NR_NEG_INF, mn = INFINITY;
+  for (int e = tid; e < nr * B; e += SK_THREADS) {
+    const float g = G[(size_t)r0 * B + e];
+    mx = fmaxf(mx, g); mn = fminf(mn, g);
+    if (resident) { Gs[e] = g; GTs[e] = GT[(size_t)r0 * B + e]; }
   }
-  // duals start at zero (until_module.py:243)
-  for (int r = tid; r < nr; r += SK_THREADS) { u1[r0 + r] = 0.f; v1[r0 + r] = 0.f; u2[r0 + r] = 0.f; v2[r0 + r] = 0.f; }
-  const float nu = -logf(2.0f * (float)B);
+  mx = block_max(mx, red);
+  mn = -block_max(-mn, red);
+  if (tid == 0) { gstat[2 * blockIdx.x] = mx; gstat[2 * blockIdx.x + 1] = mn; }
   unsigned int bar = 0;
   grid_barrier(counter, (++bar) * gridDim.x);
+  mx = NR_NEG_INF; mn = INFINITY;
+  for (int c = tid; c < (int)gridDim.x; c += SK_THREADS) {
+    mx = fmaxf(mx, __ldcg(gstat + 2 * c)); mn = fminf(mn, __ldcg(gstat + 2 * c + 1));
+  }
+  mx = block_max(mx, red);
+  mn = -block_max(-mn, red);
+  const float nu = -logf(2.0f * (float)B);
+  const bool scaling = resident && (mx - mn) <= 30.f;
+  if (scaling)
+    for (int e = tid; e < nr * B; e += SK_THREADS) { Gs[e] = expf(Gs[e] - mx); GTs[e] = expf(GTs[e] - mx); }
+  float* vecs[4] = {u1, v1, u2, v2};
+  for (int r = tid; r < nr; r += SK_THREADS) {
+    const float init = scaling ? 1.f : 0.f;
+    u1[r0 + r] = init; v1[r0 + r] = init; u2[r0 + r] = init; v2[r0 + r] = init;
+  }
+  grid_barrier(counter, (++bar) * gridDim.x);
   for (int it = 0; it < iters; ++it) {
-    // half-iteration A: u1 = nu - LSE_b(G[r,b] + v1[b]);   u2 = nu - LSE_b(GT[r,b] + v2[b])
-    for (int w = warp; w < 2 * nr; w += SK_WARPS) {
-      const int r = w >> 1, chain = w & 1;
-      const float* row = resident ? ((chain ? GTs : Gs) + (size_t)r * B) : ((chain ? GT : G) + (size_t)(r0 + r) * B);
-      float l = warp_row_lse(row, chain ? v2 : v1, B, lane);
-      if (lane == 0) (chain ? u2 : u1)[r0 + r] = nu - l;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      // half 0: (u1 <- rows of G with v1, u2 <- rows of G^T with v2); half 1: (v1 <- G^T with u1, v2 <- G with u2)
+      const float* s1 = vecs[half ? 0 : 1];
+      const float* s2 = vecs[half ? 2 : 3];
+      for (int j = tid; j < B; j += SK_THREADS) { vs[j] = __ldcg(s1 + j); vs[B + j] = __ldcg(s2 + j); }
+      __syncthreads();
+      for (int w = warp; w < 2 * nr; w += SK_WARPS) {
+        const int r = w >> 1, chain = w & 1;
+        const bool useT = (chain ^ half) != 0;
+        const float* row = resident ? ((useT ? GTs : Gs) + (size_t)r * B) : ((useT ? GT : G) + (size_t)(r0 + r) * B);
+        float val;
+        if (scaling) val = 1.0f / warp_dot(row, vs + chain * B, B, lane);
+        else val = nu - warp_lse(row, vs + chain * B, B, lane);
+        if (lane == 0) vecs[chain * 2 + (half ? 1 : 0)][r0 + r] = val;
+      }
+      grid_barrier(counter, (++bar) * gridDim.x);
     }
-    grid_barrier(counter, (++bar) * gridDim.x);
-    // half-iteration B: v1[r] = nu - LSE_a(G[a,r] + u1[a]) = rows of GT;   v2[r] = rows of G with u2
-    for (int w = warp; w < 2 * nr; w += SK_WARPS) {
-      const int r = w >> 1, chain = w & 1;
-      const float* row = resident ? ((chain ? Gs : GTs) + (size_t)r * B) : ((chain ? G : GT) + (size_t)(r0 + r) * B);
-      float l = warp_row_lse(row, chain ? u2 : u1, B, lane);
-      if (lane == 0) (chain ? v2 : v1)[r0 + r] = nu - l;
+  }
+  if (scaling) {        // back to the log duals: u = (nu - max G) + log alpha, v = log beta
+    for (int r = tid; r < nr; r += SK_THREADS) {
+      u1[r0 + r] = (nu - mx) + logf(u1[r0 + r]); v1[r0 + r] = logf(v1[r0 + r]);
+      u2[r0 + r] = (nu - mx) + logf(u2[r0 + r]); v2[r0 + r] = logf(v2[r0 + r]);
     }
-    grid_barrier(counter, (++bar) * gridDim.x);
   }
 }
 
@@ -387,12 +422,12 @@ static int sinkhorn_cluster_launch(const float* G, const float* GT, int B, int i
   return 0;
 }
 
-extern "C" size_t nr_sinkhorn_workspace_bytes(int64_t B) { (void)B; return 256; }
+extern "C" size_t nr_sinkhorn_workspace_bytes(int64_t B) { (void)B; return 256 + 2 * 1024 * sizeof(float); }
 
 extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
                            float* v2, void* workspace, size_t workspace_bytes, void* stream) {
   NR_CHECK_ARG(G && GT && u1 && v1 && u2 && v2 && workspace && B > 0 && iters >= 0, "nr_sinkhorn: bad arguments");
-  NR_CHECK_ARG(workspace_bytes >= 256, "nr_sinkhorn: workspace too small");
+  NR_CHECK_ARG(workspace_bytes >= nr_sinkhorn_workspace_bytes(B), "nr_sinkhorn: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   {
     const size_t smem1 = ((size_t)2 * B * B + (size_t)4 * B) * sizeof(float);
@@ -418,7 +453,7 @@ extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters
     }
   }
   const char* var2 = getenv("NR_SINKHORN_VARIANT");
-  if (!var2 || strcmp(var2, "grid")) {
+  if (var2 && !strcmp(var2, "cluster")) {
     bool launched = false;
     if (int e = sinkhorn_cluster_launch(G, GT, (int)B, iters, u1, v1, u2, v2, s, &launched)) return e;
     if (launched) return 0;
@@ -428,24 +463,29 @@ extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters
   NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   NR_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   NR_CHECK_ARG(coop, "nr_sinkhorn: device lacks cooperative launch");
-  // one warp per (row, chain): aim at SK_WARPS/2 rows per CTA, capped by the SM count
-  int rows_per_cta = SK_WARPS / 2;
+  // few CTAs keep the device-wide barrier cheap: at most 64 CTAs (more only if the slabs would not fit otherwise)
+  int rows_per_cta = (int)((B + 63) / 64);
+  if (rows_per_cta < 4) rows_per_cta = 4;
+  while (rows_per_cta > 4 && ((size_t)2 * rows_per_cta * B + (size_t)2 * B) * sizeof(float) > 200 * 1024 &&
+         (B + rows_per_cta - 2) / (rows_per_cta - 1) <= sms)
+    --rows_per_cta;
   int grid = (int)((B + rows_per_cta - 1) / rows_per_cta);
   if (grid > sms) {
     grid = sms;
     rows_per_cta = (int)((B + grid - 1) / grid);
     grid = (int)((B + rows_per_cta - 1) / rows_per_cta);
   }
-  size_t smem = (size_t)2 * rows_per_cta * B * sizeof(float);
+  size_t smem = ((size_t)2 * rows_per_cta * B + (size_t)2 * B) * sizeof(float);
   int resident = smem <= 200 * 1024;
-  if (!resident) smem = 0;
+  if (!resident) smem = (size_t)2 * B * sizeof(float);
   if (smem > 48 * 1024)
     NR_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NR_CUDA(cudaMemsetAsync(workspace, 0, 256, s));
   int Bi = (int)B;
   unsigned int* counter = (unsigned int*)workspace;
+  float* gstat = (float*)((char*)workspace + 256);
   void* args[] = {(void*)&G, (void*)&GT, (void*)&Bi, (void*)&iters, (void*)&rows_per_cta, (void*)&resident,
-                  (void*)&u1, (void*)&v1, (void*)&u2, (void*)&v2, (void*)&counter};
+                  (void*)&u1, (void*)&v1, (void*)&u2, (void*)&v2, (void*)&counter, (void*)&gstat};
   NR_CUDA(cudaLaunchCooperativeKernel((void*)sinkhorn_kernel, dim3(grid), dim3(SK_THREADS), args, smem, s));
   return 0;
 }

@@ -84,9 +84,9 @@ class HeadFunction(torch.autograd.Function):
         G = g2 @ v2.t()
         GT = v2 @ g2.t()
         duals = torch.empty(4, B, **f32)
-        lib_ws = torch.empty(256, dtype=torch.uint8, device=dev)
+        lib_ws, nws = ops.sinkhorn_workspace(B, dev)
         _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]), _p(duals[3]),
-              _p(lib_ws), 256, st)
+              _p(lib_ws), nws, st)
         # centrality weights
         mean = torch.empty(2, d, **f32); gn = torch.empty(2, B, d, **f32)
         ginv = torch.empty(2, B, **f32); w = torch.empty(2, B, **f32)

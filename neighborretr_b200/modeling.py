@@ -30,11 +30,11 @@ allgather2 = AllGather2.apply
 DEFAULT_PRECISION = os.environ.get("NR_HEAD_PRECISION", "bf16")
 
 
-def _token_weights(mlp, feat, mask, lowp=False, sum_param_grads=False):
+def _token_weights(mlp, feat, mask, lowp=False):
     """softmax over tokens of the MLP logits, masked tokens filled with -9e15 (reference :485-492).
     lowp: run the Linear layers as TF32 tensor-core GEMMs (cuBLAS) in both passes — the bf16 head mode;
     otherwise plain fp32 GEMMs.  The softmax stays fp32."""
-    logit = ops.token_mlp_logits(mlp, feat, lowp, sum_param_grads)
+    logit = ops.token_mlp_logits(mlp, feat, lowp)
     if mask is not None:
         logit = logit.masked_fill((1 - mask).to(torch.bool), float(-9e15))
     return torch.softmax(logit, dim=-1)
@@ -208,13 +208,17 @@ class HeadMixin:
     def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats):
         """W > 1: row-block sharded head (sharded.py) on the LOCAL batch; gathers happen inside.
         Returns (5 losses, gathered (text, video, text_mask, video_mask))."""
-        from .sharded import sharded_head
+        from .sharded import SumGradsAcrossRanks, sharded_head
         cfg = self.config
         lowp = self._head_precision() == "bf16"
-        tw = _token_weights(self.text_weight_fc, text_feat, text_mask, lowp, True)
-        vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp, True)
-        tw_mb = _token_weights(self.text_weight_fc, self.mb_feat_t, self.mb_mask_t, lowp, True)
-        vw_mb = _token_weights(self.video_weight_fc, self.mb_feat_v, self.mb_mask_v, lowp, True)
+        # each rank differentiates only its share of the loss: sum the head-parameter gradients over ranks
+        # (one flat all_reduce in backward) so that every rank holds the full gradient, as in the reference
+        ps = SumGradsAcrossRanks.apply(*ops.mlp_params(self.text_weight_fc), *ops.mlp_params(self.video_weight_fc))
+        tmlp, vmlp = ps[:4], ps[4:]
+        tw = _token_weights(tmlp, text_feat, text_mask, lowp)
+        vw = _token_weights(vmlp, video_feat, video_mask, lowp)
+        tw_mb = _token_weights(tmlp, self.mb_feat_t, self.mb_mask_t, lowp)
+        vw_mb = _token_weights(vmlp, self.mb_feat_v, self.mb_mask_v, lowp)
         gtf, gvf = global_feats
         out5, nbr, text_all, video_all, tm_all, vm_all = sharded_head(
             text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, self.clip.logit_scale.exp(), text_mask, video_mask,

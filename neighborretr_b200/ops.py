@@ -305,13 +305,14 @@ class TokenMLPFunction(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, None
 
 
-def token_mlp_logits(mlp, feat, tf32, sum_param_grads=False):
-    """mlp: nn.Sequential(Linear, ReLU, Linear) with the reference's parameter names.  sum_param_grads: the
-    parameter gradients are all-reduced (SUM) over ranks in backward (row-sharded head, sharded.py)."""
-    ps = (mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias)
-    if sum_param_grads:
-        from .sharded import SumGradAcrossRanks
-        ps = tuple(SumGradAcrossRanks.apply(p) for p in ps)
+def mlp_params(mlp):
+    return (mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias)
+
+
+def token_mlp_logits(mlp, feat, tf32):
+    """mlp: nn.Sequential(Linear, ReLU, Linear) with the reference's parameter names, or its 4 parameters
+    (W1, b1, W2, b2) as a tuple (e.g. wrapped by sharded.SumGradsAcrossRanks)."""
+    ps = mlp if isinstance(mlp, (tuple, list)) else mlp_params(mlp)
     return TokenMLPFunction.apply(feat, *ps, bool(tf32))
 
 
@@ -363,6 +364,11 @@ def centrality_weights(feat, gfeat, cs):
 # ------------------------------------------------------------------------------------------------
 # Sinkhorn duals (no grad; reference until_module.py:222-251)
 # ------------------------------------------------------------------------------------------------
+def sinkhorn_workspace(B, dev):
+    n = _lib.load().nr_sinkhorn_workspace_bytes(B)
+    return torch.empty(n, dtype=torch.uint8, device=dev), n
+
+
 def sinkhorn_duals(G, GT, iters=50):
     """Both directions in one cooperative launch: returns (u1, v1, u2, v2); chain 1 on G, chain 2 on G^T."""
     _req_cuda(G, GT)

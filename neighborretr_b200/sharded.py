@@ -45,19 +45,32 @@ def _reduce_scatter(t, b):
     return out
 
 
-class SumGradAcrossRanks(torch.autograd.Function):
-    """Identity whose backward all-reduces (SUM) the gradient: applied to the head parameters so that every rank
-    ends up with the FULL parameter gradient, like the reference's replicated head."""
+class SumGradsAcrossRanks(torch.autograd.Function):
+    """Identity on a group of parameters whose backward all-reduces (SUM) their gradients in ONE flat collective:
+    applied to the head parameters so that every rank ends up with the FULL parameter gradient, like the
+    reference's replicated head."""
 
     @staticmethod
-    def forward(ctx, p):
-        return p.view_as(p)
+    def forward(ctx, *ps):
+        ctx.shapes = [p.shape for p in ps]
+        return tuple(p.view_as(p) for p in ps)
 
     @staticmethod
-    def backward(ctx, g):
-        g = g.contiguous().clone()
-        dist.all_reduce(g, op=dist.ReduceOp.SUM)
-        return g
+    def backward(ctx, *gs):
+        sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
+        ref = next(g for g in gs if g is not None)
+        flat = torch.zeros(sum(sizes), dtype=ref.dtype, device=ref.device)
+        o = 0
+        for g, n in zip(gs, sizes):
+            if g is not None:
+                flat[o:o + n].copy_(g.reshape(-1))
+            o += n
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        out, o = [], 0
+        for shp, n in zip(ctx.shapes, sizes):
+            out.append(flat[o:o + n].view(shp))
+            o += n
+        return tuple(out)
 
 
 class ShardedHeadFunction(torch.autograd.Function):
@@ -74,9 +87,13 @@ class ShardedHeadFunction(torch.autograd.Function):
         d = text_l.shape[-1]
         # ---- exchange 1: features, masks, global features, token weights
         text, video = _gather(_f32c(text_l)), _gather(_f32c(video_l))
-        tm, vm = _gather(_mask(tm_l)), _gather(_mask(vm_l))
-        g2, v2 = _gather(_f32c(gt_l).reshape(b, d)), _gather(_f32c(gv_l).reshape(b, d))
-        tw, vw = _gather(_f32c(tw_l)), _gather(_f32c(vw_l))
+        nt_, nv_ = text_l.shape[1], video_l.shape[1]
+        masks = _gather(torch.cat([_mask(tm_l), _mask(vm_l)], dim=1))                       # [B, Nt+Nv] int64
+        tm, vm = masks[:, :nt_].contiguous(), masks[:, nt_:].contiguous()
+        small = _gather(torch.cat([_f32c(gt_l).reshape(b, d), _f32c(gv_l).reshape(b, d), _f32c(tw_l), _f32c(vw_l)],
+                                  dim=1))                                                  # [B, 2D+Nt+Nv]
+        g2, v2 = small[:, :d].contiguous(), small[:, d:2 * d].contiguous()
+        tw, vw = small[:, 2 * d:2 * d + nt_].contiguous(), small[:, 2 * d + nt_:].contiguous()
         tw_mb, vw_mb = _f32c(tw_mb), _f32c(vw_mb)
         mtm, mvm = _mask(mb_mask_t), _mask(mb_mask_v)
         bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
@@ -107,9 +124,9 @@ class ShardedHeadFunction(torch.autograd.Function):
         G = g2 @ v2.t()
         GT = v2 @ g2.t()
         duals = torch.empty(4, B, **f32)
-        ws = torch.empty(256, dtype=torch.uint8, device=dev)
+        ws, nws = ops.sinkhorn_workspace(B, dev)
         _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]), _p(duals[3]),
-              _p(ws), 256, st)
+              _p(ws), nws, st)
         mean = torch.empty(2, d, **f32); gn = torch.empty(2, b, d, **f32)
         ginv = torch.empty(2, b, **f32); w = torch.empty(2, b, **f32)
         _call("nr_centrality_fwd", _p(T.partials), T.partials.shape[0], T.rows, _p(g2[lo:lo + b]), b, d, cs,
@@ -220,10 +237,9 @@ class ShardedHeadFunction(torch.autograd.Function):
         # ---- exchange 5: sum the partial gradients of the gathered tensors, keep this rank's rows
         dtext = _reduce_scatter(dtext_all, b)
         dvideo = _reduce_scatter(dvideo_all, b)
-        dgt = _reduce_scatter(dg_all, b)
-        dgv = _reduce_scatter(dv_all, b)
-        dtw_o = _reduce_scatter(dtw, b)
-        dvw_o = _reduce_scatter(dvw, b)
+        small = _reduce_scatter(torch.cat([dg_all, dv_all, dtw, dvw], dim=1), b)            # one collective
+        dgt, dgv = small[:, :d], small[:, d:2 * d]
+        dtw_o, dvw_o = small[:, 2 * d:2 * d + nt], small[:, 2 * d + nt:]
         ctx.objs = None
         gs_t, gs_v = ctx.gshape
         return (dtext, dvideo, dgt.reshape(gs_t), dgv.reshape(gs_v), dtw_o, dvw_o, dtw_mb, dvw_mb, dls.reshape(()),
