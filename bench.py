@@ -340,9 +340,12 @@ def run_ours(args):
 
     B = B_PER_GPU * world
     pk = peaks()
-    # dominant kernel = nr_maxsim_fwd (6 launches / step): algorithmic flops 2*Rx*Ry*Nt*Nv*D per launch,
-    # every S / bank entry needs both orientations, each launch is one orientation => half of the pair's flops
-    flops_step = 0.5 * 2 * (flops_maxsim(B, B, nt, nv) + 2 * flops_maxsim(B, mrows, nt, nv))
+    # dominant kernel = nr_maxsim_fwd.  Algorithmic flops of a rank-step's forward contractions:
+    # every S entry and every bank entry counted ONCE globally, un-padded tokens only:
+    #   2*Nt*Nv*D * (b*B + 2*b*M)   with b = per-rank rows.
+    # Executed MMA work is higher: each entry takes one launch per orientation (x2) and, for W > 1, a rank computes
+    # both a row block and a column block of S (x2 on the b*B term).
+    flops_step = flops_maxsim(B_PER_GPU, B, nt, nv) + 2 * flops_maxsim(B_PER_GPU, mrows, nt, nv)
     n_l = max(kt["launches"], 1)
     achieved = flops_step * ksteps / (kt["ms"] * 1e-3) / 1e12 if kt["ms"] > 0 else 0.0
     peak = pk["bf16_sustained"]
@@ -361,7 +364,10 @@ def run_ours(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "nr_maxsim_fwd", "bound": "tensor", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": 9.56e6 if (world == 1 and args.shape == "msrvtt") else None,
+                     "traffic_note": "dram bytes read+written per launch of the text x bank-video block, ncu --set "
+                                     "full (profiles/r1_k1_fwd_ncu_full.txt); algorithmic operand bytes 9.4e6",
                      "launches_timed": n_l, "avg_launch_ms": kt["ms"] / n_l,
                      "share_of_step": (kt["ms"] / ksteps) / (ms_total / args.steps) if ms_total else None,
                      "timed_in": "eager steps on the launching stream (events cannot be read inside a graph replay)",

@@ -35,3 +35,50 @@ def _run_on_single_gpu(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list
     s = similarity_matrix(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, mini_batch)
     sim_matrix = s.cpu().numpy()
     return sim_matrix, sim_matrix.T
+
+
+def sharded_retrieval(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, topk=10):
+    """Column-sharded evaluation over the default process group: every rank has all features
+    (as after the reference's gather, training/evaluator.py:173-189), computes only S[:, cols_r] for its shard of
+    the video gallery and never materialises the full matrix.  Exact global ranks come from per-shard counts
+    (all_reduce of int32 vectors) against the positive's score; top-k lists are merged across shards
+    (ties -> lower global index).  Returns (t2v metrics, v2t metrics, (topk values, topk video ids) [Q,k])."""
+    import torch.distributed as dist
+    from .metrics import metrics_from_counts
+    W, r = dist.get_world_size(), dist.get_rank()
+    Q, N = t_feat_list.shape[0], v_feat_list.shape[0]
+    if Q != N:
+        raise ValueError("sharded_retrieval: compute_metrics needs a square query x gallery problem")
+    n = (N + W - 1) // W
+    c0, c1 = min(r * n, N), min((r + 1) * n, N)
+    s = similarity_matrix(model, t_mask_list, v_mask_list[c0:c1], t_feat_list, v_feat_list[c0:c1])   # [Q, c1-c0]
+    dev = s.device
+    # positives' scores: owned by the rank whose shard holds column q
+    diag = torch.zeros(Q, dtype=torch.float32, device=dev)
+    if c1 > c0:
+        diag[c0:c1] = s[c0:c1].diagonal()
+    dist.all_reduce(diag, op=dist.ReduceOp.SUM)
+    cnt = torch.zeros(2, Q, dtype=torch.int32, device=dev)
+    if c1 > c0:
+        ops.rank_counts(s, diag=diag, gt=cnt[0], eq=cnt[1])
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    # video -> text: rows of S^T for this rank's videos are complete locally
+    cnt_v = torch.zeros(2, W * n, dtype=torch.int32, device=dev)
+    if c1 > c0:
+        st = s.t().contiguous()                                       # [c1-c0, Q]
+        ops.rank_counts(st, diag_col0=c0, gt=cnt_v[0, c0:c1], eq=cnt_v[1, c0:c1])
+    dist.all_reduce(cnt_v, op=dist.ReduceOp.SUM)
+    # top-k video ids per text query
+    k = min(topk, n)
+    vals = torch.full((Q, k), float("-inf"), device=dev)
+    idx = torch.full((Q, k), -1, dtype=torch.int32, device=dev)
+    if c1 > c0:
+        kk = min(k, c1 - c0)
+        v_, i_ = ops.topk_rows(s, kk, col_offset=c0)
+        vals[:, :kk], idx[:, :kk] = v_, i_
+    allv = torch.empty(W, Q, k, device=dev); alli = torch.empty(W, Q, k, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(allv, vals)
+    dist.all_gather_into_tensor(alli, idx)
+    tv, ti = ops.topk_merge(allv, alli)
+    c = cnt.cpu().numpy(); cv = cnt_v[:, :N].cpu().numpy()
+    return metrics_from_counts(c[0], c[1]), metrics_from_counts(cv[0], cv[1]), (tv, ti)

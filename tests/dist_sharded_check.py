@@ -71,6 +71,18 @@ def main():
     n1 = sh.last_neighbors[0].cpu(); n1f = full.last_neighbors[0][sl].cpu()
     if a.precision == "fp32":
         ok = ok and torch.equal(n1, n1f)
+    # ---- column-sharded evaluation vs the single-process matrix + compute_metrics
+    from neighborretr_b200.evaluator import sharded_retrieval, similarity_matrix
+    from neighborretr_b200.metrics import RetrievalMetrics
+    ev = synth.make_batch(101, nt, nv, d=d, seed=77).to(dev)            # 101: ragged last shard
+    full.eval()
+    S = similarity_matrix(full, ev.text_mask, ev.video_mask, ev.text_feat, ev.video_feat)
+    m_t2v, m_v2t = RetrievalMetrics.compute_metrics(S), RetrievalMetrics.compute_metrics(S.t().contiguous())
+    s_t2v, s_v2t, (tv, ti) = sharded_retrieval(full, ev.text_mask, ev.video_mask, ev.text_feat, ev.video_feat, topk=10)
+    ref_i = torch.sort(S, dim=1, descending=True, stable=True)[1][:, :10]
+    ok_eval = s_t2v == m_t2v and s_v2t == m_v2t and torch.equal(ti.long(), ref_i)
+    errs["eval"] = 0.0 if ok_eval else 1.0
+    ok = ok and ok_eval
     print(f"rank {rank}/{world} {'OK' if ok else 'FAIL'} {errs}", flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
