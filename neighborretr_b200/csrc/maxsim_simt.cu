@@ -229,6 +229,7 @@ maxsim_bwd_w_kernel(const float* __restrict__ pmax, const float* __restrict__ dH
   const int x = tid % Nx, l = tid / Nx;
   float s = 0.f;
   if (l < lanes) {
+#pragma unroll 8
     for (int ry = l; ry < Ry; ry += lanes)
       s += dH[(int64_t)rx * dh_sr + (int64_t)ry * dh_sc] * pmax[((int64_t)rx * Ry + ry) * Nx + x];
   }

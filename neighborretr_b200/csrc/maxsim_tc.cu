@@ -599,24 +599,42 @@ static int make_tmap_srcT(CUtensorMap* m, const void* base, int64_t d, int64_t t
   return 0;
 }
 
-// tiled transpose of the bf16 operand copy: in [rows, d] -> out [d, ld]
-__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int rows, int d,
-                                      __nv_bfloat16* __restrict__ out, int64_t ld) {
-  __shared__ __nv_bfloat16 tile[64][66];
-  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
-    int r = r0 + i;
-    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
-      int c = c0 + j;
-      tile[i][j] = (r < rows && c < d) ? in[(int64_t)r * d + c] : __float2bfloat16_rn(0.f);
+// tiled transpose of the bf16 operand copy: in [rows, d] -> out [d, ld]; 64x64 tiles, 8-byte accesses both ways
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int rows, int d, __nv_bfloat16* __restrict__ out,
+                      int64_t ld) {
+  __shared__ __nv_bfloat16 tile[64][68];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64, tid = threadIdx.x;
+  const bool vec_in = (d % 4 == 0), vec_out = (ld % 4 == 0);
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int e = it * 256 + tid, i = e >> 4, j = (e & 15) * 4;       // row i, columns j..j+3 of the tile
+    const int r = r0 + i, c = c0 + j;
+    __nv_bfloat16 v[4];
+    if (r < rows && vec_in && c + 3 < d) {
+      *reinterpret_cast<uint2*>(v) = *reinterpret_cast<const uint2*>(in + (int64_t)r * d + c);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = (r < rows && c + q < d) ? in[(int64_t)r * d + c + q] : __float2bfloat16_rn(0.f);
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tile[i][j + q] = v[q];
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 64; i += blockDim.y) {
-    int c = c0 + i;
-    for (int j = threadIdx.x; j < 64; j += blockDim.x) {
-      int r = r0 + j;
-      if (c < d && r < rows) out[(int64_t)c * ld + r] = tile[j][i];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int e = it * 256 + tid, i = e >> 4, j = (e & 15) * 4;       // out row (column c0+i), tokens r0+j..r0+j+3
+    const int c = c0 + i, r = r0 + j;
+    if (c >= d) continue;
+    __nv_bfloat16 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = tile[j + q][i];
+    if (vec_out && r + 3 < rows) {
+      *reinterpret_cast<uint2*>(out + (int64_t)c * ld + r) = *reinterpret_cast<uint2*>(v);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (r + q < rows) out[(int64_t)c * ld + r + q] = v[q];
     }
   }
 }
@@ -630,8 +648,8 @@ extern "C" int nr_transpose_tokens_bf16(const void* xn_bf16, int64_t rows, int64
   NR_CHECK_ARG(xn_bf16 && out && rows > 0 && d > 0, "nr_transpose_tokens_bf16: bad arguments");
   NR_CHECK_ARG(ld >= rows && ld % 8 == 0, "nr_transpose_tokens_bf16: ld=%lld must be >= rows and a multiple of 8",
                (long long)ld);
-  dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((d + 63) / 64)), block(32, 8);
-  transpose_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xn_bf16, (int)rows, (int)d,
+  dim3 grid((unsigned)((rows + 63) / 64), (unsigned)((d + 63) / 64));
+  transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)xn_bf16, (int)rows, (int)d,
                                                                  (__nv_bfloat16*)out, ld);
   NR_CHECK_LAUNCH("nr_transpose_tokens_bf16");
   return 0;

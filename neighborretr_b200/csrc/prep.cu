@@ -112,13 +112,22 @@ prep_tokens_bwd_kernel(const float* __restrict__ xn, const float* __restrict__ i
   }
 }
 
+// block (32, 8): 32 columns x 8 interleaved partial rows, combined through shared memory
 __global__ void mean_vec_kernel(const float* __restrict__ partials, int n_partials, int d, float inv_rows,
                                 float* __restrict__ mean_vec) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int p = 0; p < n_partials; ++p) s += partials[(int64_t)p * d + c];
-  mean_vec[c] = s * inv_rows;
+  if (c < d)
+    for (int p = threadIdx.y; p < n_partials; p += 8) s += partials[(int64_t)p * d + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[q][threadIdx.x];
+    mean_vec[c] = t * inv_rows;
+  }
 }
 
 // one warp per global-feature row: gn = normalize(g), w = exp(cs * <gn, mean>)
@@ -167,11 +176,19 @@ centrality_rows_bwd_kernel(const float* __restrict__ mean_vec, const float* __re
 __global__ void centrality_dmean_kernel(const float* __restrict__ gn, const float* __restrict__ w,
                                         const float* __restrict__ dw, int B, int d, float cs, float inv_rows,
                                         float* __restrict__ dmean) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int a = 0; a < B; ++a) s += cs * w[a] * dw[a] * gn[(int64_t)a * d + c];
-  dmean[c] = s * inv_rows;
+  if (c < d)
+    for (int a = threadIdx.y; a < B; a += 8) s += cs * w[a] * dw[a] * gn[(int64_t)a * d + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < d) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sm[q][threadIdx.x];
+    dmean[c] = t * inv_rows;
+  }
 }
 
 }  // namespace nr
@@ -214,8 +231,8 @@ extern "C" int nr_centrality_fwd(const float* colsum_partials, int64_t n_partial
                    d > 0,
                "nr_centrality_fwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  mean_vec_kernel<<<(unsigned)((d + 255) / 256), 256, 0, s>>>(colsum_partials, (int)n_partials, (int)d,
-                                                             1.0f / (float)rows_total, mean_vec);
+  mean_vec_kernel<<<(unsigned)((d + 31) / 32), dim3(32, 8), 0, s>>>(colsum_partials, (int)n_partials, (int)d,
+                                                                   1.0f / (float)rows_total, mean_vec);
   NR_CHECK_LAUNCH("nr_centrality_fwd(mean)");
   centrality_rows_kernel<<<(unsigned)((B + PREP_WARPS - 1) / PREP_WARPS), PREP_WARPS * 32, 0, s>>>(
       g, mean_vec, (int)B, (int)d, cs, gn, ginv, w);
@@ -235,8 +252,8 @@ extern "C" int nr_centrality_bwd(const float* mean_vec, const float* gn, const f
     NR_CHECK_LAUNCH("nr_centrality_bwd(rows)");
   }
   if (dmean) {
-    centrality_dmean_kernel<<<(unsigned)((d + 127) / 128), 128, 0, s>>>(gn, w, dw, (int)B, (int)d, cs,
-                                                                       1.0f / (float)rows_total, dmean);
+    centrality_dmean_kernel<<<(unsigned)((d + 31) / 32), dim3(32, 8), 0, s>>>(gn, w, dw, (int)B, (int)d, cs,
+                                                                             1.0f / (float)rows_total, dmean);
     NR_CHECK_LAUNCH("nr_centrality_bwd(dmean)");
   }
   return 0;

@@ -269,62 +269,67 @@ row_losses_bwd_kernel(RowArgs a, const int32_t* __restrict__ nbr_idx, const floa
   }
   __syncthreads();
 
-  if ((a.flags & NR_LOSS_NEIGHBOR) && tid == 0) {
-    // sparse part: k+1 extended entries plus the arg-min / arg-max of the non-neighbours
-    const int k = a.k;
+  if ((a.flags & NR_LOSS_NEIGHBOR) && tid < 32) {
+    // sparse part on one warp (lane strides over the k neighbours): k+1 extended entries plus the arg-min /
+    // arg-max of the non-neighbours
+    const int k = a.k, lane = tid;
     const int32_t* nb = nbr_idx + (int64_t)i * k;
     const float lo_x = sv[6], hi_x = sv[7], lo_c = sv[8], hi_c = sv[9], lse_ext = sv[10], den = sv[11];
     const int i_lo = __float_as_int(sv[12]), i_hi = __float_as_int(sv[13]);
     const int j_lo = __float_as_int(sv[14]), j_hi = __float_as_int(sv[15]);
     const float rx = hi_x - lo_x, rc = hi_c - lo_c;
     float ma = NR_NEG_INF;
-    for (int r = 0; r < k; ++r) {
-      int j = nb[r];
-      float av = (x[j] - lo_x) / rx - (a.cbank[j] - lo_c) / rc;
-      ma = fmaxf(ma, a.tau_nbr * av);
+    for (int r = lane; r < k; r += 32) {
+      const int j = nb[r];
+      ma = fmaxf(ma, a.tau_nbr * ((x[j] - lo_x) / rx - (a.cbank[j] - lo_c) / rc));
     }
+    ma = warp_max(ma);
     float sa = 0.f;
-    for (int r = 0; r < k; ++r) {
-      int j = nb[r];
-      float av = (x[j] - lo_x) / rx - (a.cbank[j] - lo_c) / rc;
-      sa += expf(a.tau_nbr * av - ma);
+    for (int r = lane; r < k; r += 32) {
+      const int j = nb[r];
+      sa += expf(a.tau_nbr * ((x[j] - lo_x) / rx - (a.cbank[j] - lo_c) / rc) - ma);
     }
-    // dL/dp_r = -lp_r/den ; softmax Jacobian
-    float mean_dp = 0.f;
-    for (int r = 0; r < k; ++r) {
-      int j = nb[r];
-      float av = (x[j] - lo_x) / rx - (a.cbank[j] - lo_c) / rc;
-      float p = expf(a.tau_nbr * av - ma) / sa;
+    sa = warp_sum(sa);
+    float mean_dp = 0.f;            // sum_r p_r * dL/dp_r,  dL/dp_r = -lp_r/den
+    for (int r = lane; r < k; r += 32) {
+      const int j = nb[r];
+      const float p = expf(a.tau_nbr * ((x[j] - lo_x) / rx - (a.cbank[j] - lo_c) / rc) - ma) / sa;
       mean_dp += p * (-(x[j] - lse_ext) / den);
     }
-    float sum_dlp = -1.f / den;      // sum_j dL/dlp_j over ext (diag has weight 1)
-    float g_lo_x = 0.f, g_hi_x = 0.f, g_lo_c = 0.f, g_hi_c = 0.f;
-    for (int r = 0; r < k; ++r) {
-      int j = nb[r];
-      float nxv = (x[j] - lo_x) / rx, ncv = (a.cbank[j] - lo_c) / rc;
-      float p = expf(a.tau_nbr * (nxv - ncv) - ma) / sa;
-      float dlp = -p / den;
+    mean_dp = warp_sum(mean_dp);
+    float sum_dlp = 0.f, g_lo_x = 0.f, g_hi_x = 0.f, g_lo_c = 0.f, g_hi_c = 0.f;
+    for (int r = lane; r < k; r += 32) {
+      const int j = nb[r];
+      const float nxv = (x[j] - lo_x) / rx, ncv = (a.cbank[j] - lo_c) / rc;
+      const float p = expf(a.tau_nbr * (nxv - ncv) - ma) / sa;
+      const float dlp = -p / den;
       sum_dlp += dlp;
-      float ga = a.tau_nbr * p * (-(x[j] - lse_ext) / den - mean_dp);
-      dx[j] += gs_n * (dlp + ga / rx);
+      const float ga = a.tau_nbr * p * (-(x[j] - lse_ext) / den - mean_dp);
+      dx[j] += gs_n * (dlp + ga / rx);          // neighbour columns are distinct: no race
       g_lo_x += ga * (nxv - 1.f) / rx;
       g_hi_x += -ga * nxv / rx;
       if (dc) atomicAdd(dc + j, gs_n * (-ga / rc));
       g_lo_c += -ga * (ncv - 1.f) / rc;
       g_hi_c += ga * ncv / rc;
     }
-    dx[gi] += gs_n * (-1.f / den);
-    // -q_i * sum_dlp over ext
-    for (int r = 0; r < k; ++r) {
-      int j = nb[r];
+    sum_dlp = warp_sum(sum_dlp) - 1.f / den;    // + the diagonal (weight 1)
+    g_lo_x = warp_sum(g_lo_x); g_hi_x = warp_sum(g_hi_x);
+    g_lo_c = warp_sum(g_lo_c); g_hi_c = warp_sum(g_hi_c);
+    __syncwarp();
+    // -q_i * sum_dlp over the extended set
+    for (int r = lane; r < k; r += 32) {
+      const int j = nb[r];
       dx[j] -= gs_n * expf(x[j] - lse_ext) * sum_dlp;
     }
-    dx[gi] -= gs_n * expf(x[gi] - lse_ext) * sum_dlp;
-    dx[i_lo] += gs_n * g_lo_x;
-    dx[i_hi] += gs_n * g_hi_x;
-    if (dc) {
-      atomicAdd(dc + j_lo, gs_n * g_lo_c);
-      atomicAdd(dc + j_hi, gs_n * g_hi_c);
+    __syncwarp();
+    if (lane == 0) {
+      dx[gi] += gs_n * (-1.f / den) - gs_n * expf(x[gi] - lse_ext) * sum_dlp;
+      dx[i_lo] += gs_n * g_lo_x;
+      dx[i_hi] += gs_n * g_hi_x;
+      if (dc) {
+        atomicAdd(dc + j_lo, gs_n * g_lo_c);
+        atomicAdd(dc + j_hi, gs_n * g_hi_c);
+      }
     }
   }
   __syncthreads();

@@ -76,9 +76,9 @@ def sharded_retrieval(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list,
         kk = min(k, c1 - c0)
         v_, i_ = ops.topk_rows(s, kk, col_offset=c0)
         vals[:, :kk], idx[:, :kk] = v_, i_
-    allv = torch.empty(W, Q, k, device=dev); alli = torch.empty(W, Q, k, dtype=torch.int32, device=dev)
+    allv = torch.empty(W * Q, k, device=dev); alli = torch.empty(W * Q, k, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(allv, vals)
     dist.all_gather_into_tensor(alli, idx)
-    tv, ti = ops.topk_merge(allv, alli)
+    tv, ti = ops.topk_merge(allv.view(W, Q, k), alli.view(W, Q, k))
     c = cnt.cpu().numpy(); cv = cnt_v[:, :N].cpu().numpy()
     return metrics_from_counts(c[0], c[1]), metrics_from_counts(cv[0], cv[1]), (tv, ti)
