@@ -48,15 +48,20 @@ int nr_device_supported(void);
 /* ---- token preparation: F.normalize(x, dim=-1) (modeling.py:495-496, :415-418) -------------
  * x [rows, d] f32 -> xn_f32 [rows, d] (nullable), xn_bf16 [rows, d] (nullable),
  * inv_norm [rows] = 1/max(||x||, 1e-12), colsum_partials [nr_prep_partials(rows), d] (nullable):
- * per-CTA partial column sums of the normalised rows (for the centrality mean, modeling.py:419-424). */
+ * per-CTA partial column sums of the normalised rows (for the centrality mean, modeling.py:419-424).
+ * mask [rows] int64 (nullable): tokens with mask == 0 become ZERO rows of xn_bf16 only (so that their token
+ * pairs are exactly 0 in the tensor-core contraction, as after the reference's mask multiplies,
+ * modeling.py:500-501); xn_f32, inv_norm and the column sums are unaffected (compute_centrality_weights
+ * uses padded tokens too, modeling.py:415-424). */
 int64_t nr_prep_partials(int64_t rows);
 int nr_prep_tokens(const float* x, int64_t rows, int64_t d, float* xn_f32, void* xn_bf16, float* inv_norm,
-                   float* colsum_partials, void* stream);
+                   float* colsum_partials, const int64_t* mask, void* stream);
 /* backward of the normalisation: dx = (dxn + add_vec - xn <xn, dxn + add_vec>) * inv_norm.
  * add_vec [d] (nullable) is a gradient broadcast to every row (centrality mean path).
+ * mask [rows] int64 (nullable): rows with mask == 0 ignore dxn (a masked token has no max-sim gradient).
  * accumulate != 0: dx += ... */
 int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* dxn, const float* add_vec,
-                       int64_t rows, int64_t d, float* dx, int accumulate, void* stream);
+                       const int64_t* mask, int64_t rows, int64_t d, float* dx, int accumulate, void* stream);
 
 /* ---- token-weight MLP (modeling.py:148-153), hidden-layer backward in one pass ----------------
  * h [T,H] post-ReLU activations, dlogit [T], w2 [H]  ->  dh [T,H] = dlogit*w2*(h>0) and per-CTA partials
@@ -79,6 +84,42 @@ int nr_maxsim_fwd(int precision, const void* xn, const void* yn, const float* wx
                   const int64_t* my, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float alpha,
                   float* out, int64_t out_sr, int64_t out_sc, float* out2, int64_t out2_sr, int64_t out2_sc,
                   int accumulate, float* pmax, uint8_t* ystar, void* stream);
+/* ---- both directions of local_level from one accumulator tile (modeling.py:495-512), tensor cores only ------
+ *   out[rx,ry] = alpha * ( sum_x wx[rx,x] max_y R + sum_y wy[ry,y] max_x R ),  R[rx,ry,x,y] = <x tokens, y tokens>
+ * x_bf16 [Rx*Nx, d], y_bf16 [Ry*Ny, d]: L2-normalised bf16 tokens with masked tokens zeroed (nr_prep_tokens with a
+ * mask), so no mask arguments exist here.  wx [Rx,Nx], wy [Ry,Ny] f32 token weights (0 for masked tokens).
+ * out / out2 (nullable) are written as out[rx*sr + ry*sc]: S and S^T from the same launch.
+ * Saved for backward (all nullable): pmax_x [Rx,Ry,Nx] f32 / ystar [Rx,Ry,Nx] u8 = max / arg-max over y for every
+ * x token; pmax_y [Rx,Ry,Ny] f32 / xstar [Rx,Ry,Ny] u8 = max / arg-max over x for every y token (pmax_y carries
+ * 3 fewer mantissa bits: the column arg-max travels in the low bits of the value).  Ties -> lower index.
+ * Up to 4 problems with the same (Nx, Ny, d) share one persistent launch. */
+typedef struct {
+  const void* x_bf16; const void* y_bf16;
+  const float* wx; const float* wy;
+  int64_t Rx, Ry;
+  float alpha;
+  float* out; int64_t out_sr, out_sc;
+  float* out2; int64_t out2_sr, out2_sc;
+  float* pmax_x; uint8_t* ystar;
+  float* pmax_y; uint8_t* xstar;
+} nr_maxsim2_problem;
+int nr_maxsim2_supported(int64_t Nx, int64_t Ny, int64_t d);
+int nr_maxsim2_fwd(const nr_maxsim2_problem* problems, int n_problems, int64_t Nx, int64_t Ny, int64_t d,
+                   void* stream);
+/* backward of nr_maxsim2_fwd w.r.t. the normalised tokens: with g[rx,ry] = dH[rx*dh_sr + ry*dh_sc] * dh_scale
+ * (dh_scale carries alpha) and the routing matrix
+ *   C[(rx,x),(ry,y)] = g[rx,ry] * ( wx[rx,x] [y == ystar[rx,ry,x]] + wy[ry,y] [x == xstar[rx,ry,y]] ),
+ * side 0: dst [Rx*Nx, d] += C   * Y tokens   (srcT = transposed bf16 Y tokens [d, src_ld]),
+ * side 1: dst [Ry*Ny, d] += C^T * X tokens   (srcT = transposed bf16 X tokens [d, src_ld]).
+ * dst is fp32, zero- or partially-filled: split-K partials are combined with red.global.add. */
+int nr_maxsim2_bwd(int side, const void* srcT, int64_t src_ld, const float* wx, const float* wy, const uint8_t* ystar,
+                   const uint8_t* xstar, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale, int64_t Rx,
+                   int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dst, void* stream);
+/* ... w.r.t. the token weights (either output nullable):
+ *   dwx[rx,x] += sum_ry g[rx,ry] pmax_x[rx,ry,x],   dwy[ry,y] += sum_rx g[rx,ry] pmax_y[rx,ry,y] */
+int nr_maxsim2_bwd_w(const float* pmax_x, const float* pmax_y, const float* dH, int64_t dh_sr, int64_t dh_sc,
+                     float dh_scale, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, float* dwx, float* dwy,
+                     void* stream);
 /* bf16 operand copy [rows, d] -> transposed [d, ld] (ld >= rows, multiple of 8): the K-major source
  * operand of the tensor-core backward contractions. */
 int nr_transpose_tokens_bf16(const void* xn_bf16, int64_t rows, int64_t d, void* out, int64_t ld, void* stream);

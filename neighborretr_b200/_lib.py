@@ -23,12 +23,16 @@ SIGNATURES = {
     "nr_last_error": (ctypes.c_char_p, []),
     "nr_device_supported": (_I, []),
     "nr_prep_partials": (_I64, [_I64]),
-    "nr_prep_tokens": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P]),
-    "nr_prep_tokens_bwd": (_I, [_P, _P, _P, _P, _I64, _I64, _P, _I, _P]),
+    "nr_prep_tokens": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
+    "nr_prep_tokens_bwd": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I, _P]),
     "nr_mlp_chunks": (_I64, [_I64]),
     "nr_mlp_hidden_bwd": (_I, [_P, _P, _P, _I64, _I64, _P, _P, _P]),
     "nr_maxsim_fwd": (_I, [_I, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _P, _I64, _I64, _P, _I64,
                            _I64, _I, _P, _P, _P]),
+    "nr_maxsim2_supported": (_I, [_I64, _I64, _I64]),
+    "nr_maxsim2_fwd": (_I, [_P, _I, _I64, _I64, _I64, _P]),
+    "nr_maxsim2_bwd": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "nr_maxsim2_bwd_w": (_I, [_P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "nr_transpose_tokens_bf16": (_I, [_P, _I64, _I64, _P, _I64, _P]),
     "nr_maxsim_bwd_x": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
     "nr_maxsim_bwd_y": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
@@ -49,6 +53,15 @@ SIGNATURES = {
     "nr_topk_rows": (_I, [_P, _I64, _I64, _I64, _I, ctypes.c_int32, _P, _P, _P]),
     "nr_topk_merge": (_I, [_P, _P, _I64, _I64, _I, _P, _P, _P]),
 }
+
+
+
+class MaxSim2Problem(ctypes.Structure):
+    """nr_maxsim2_problem of include/nrhead.h (field order and types must match)."""
+    _fields_ = [("x_bf16", _P), ("y_bf16", _P), ("wx", _P), ("wy", _P), ("Rx", _I64), ("Ry", _I64), ("alpha", _F),
+                ("out", _P), ("out_sr", _I64), ("out_sc", _I64), ("out2", _P), ("out2_sr", _I64), ("out2_sc", _I64),
+                ("pmax_x", _P), ("ystar", _P), ("pmax_y", _P), ("xstar", _P)]
+
 
 NR_LOSS_CENTRALITY, NR_LOSS_NEIGHBOR, NR_LOSS_KL, NR_LOSS_UNIFORM = 1, 2, 4, 8
 NR_NSAVE = 16

@@ -1,0 +1,399 @@
+// Both directions of the masked max-sim late interaction from ONE accumulator tile (NR_PREC_BF16).
+//
+//   S[rx, ry] = alpha * ( sum_x wx[rx,x] * max_y R[rx,ry,x,y]  +  sum_y wy[ry,y] * max_x R[rx,ry,x,y] )
+//   R[rx,ry,x,y] = < xn[rx,x,:], yn[ry,y,:] >           (masked tokens are zero rows of the bf16 operands, so
+//                                                         masked pairs are exactly 0 and take part in the max)
+//
+// = the whole of NeighborRetr.local_level below the token-weight MLPs (reference
+// NeighborRetr/models/modeling.py:495-512: einsum, two mask multiplies, max over v, max over t, two weighted
+// sums, average) — the reference materialises the 4-D [A,B,Nt,Nv] tensor and makes >= 7 passes over it.
+// The one-direction kernel (maxsim_tc.cu) needs two launches and computes every token pair twice; here a tile's
+// fp32 accumulator is read from TMEM once and reduced in BOTH directions:
+//   row direction    (max over the Ny columns of a Y sample): one accumulator row per thread, in registers;
+//   column direction (max over the Nx rows of an X sample):  rows live in different lanes -> (value, row) keys
+//                    (fp32 bits of v+2 with the low log2(GL) bits replaced by the row index) are reduced by a
+//                    halving butterfly over aligned groups of GL lanes (GL columns in, one column per lane out),
+//                    the 128/GL group partials go to shared memory and are combined per X sample afterwards.
+// Up to 4 independent (X, Y) problems with the same token counts share a launch (the batch pair and the two bank
+// pairs of a head step), so the persistent grid sees one long tile list.
+//
+// Persistent warp-specialised kernel, one CTA per SM: warp 0 TMA producer, warp 1 tcgen05.mma issuer (M=128,
+// N<=256, K=16 bf16 -> fp32 TMEM, two accumulator stages), warps 2..9 epilogue.
+// Roofline: tensor pipe; algorithmic flops per problem 2*Rx*Nx*Ry*Ny*D, every token pair multiplied ONCE.
+#include "common.cuh"
+#include "nrhead_internal.h"
+#include "tc_common.cuh"
+
+namespace nr {
+using namespace tc;
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t d, int box_rows);
+
+constexpr int T2_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int T2_EPI = T2_THREADS - 64;
+constexpr int T2_BM = 128;
+constexpr int T2_BK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int T2_MAX_STAGES = 4;
+constexpr int T2_A_BYTES = T2_BM * 128;    // 16 KB
+constexpr int T2_ACC_COLS = 256;           // TMEM columns per accumulator stage
+constexpr int T2_MAX_PROB = 4;
+
+struct Tc2Prob {
+  const float* wx; const float* wy;
+  int Rx, Ry;
+  float alpha; int tile0;
+  float* out; int64_t out_sr, out_sc; float* out2; int64_t out2_sr, out2_sc;
+  float* pmax_x; uint8_t* ystar; float* pmax_y; uint8_t* xstar;
+  int n_mt, n_nt;
+};
+
+struct alignas(64) Tc2Args {
+  CUtensorMap tmx[T2_MAX_PROB];
+  CUtensorMap tmy[T2_MAX_PROB];
+  Tc2Prob p[T2_MAX_PROB];
+  int nprob, n_tiles;
+  int Nx, SX, MU, SY, UN, num_kb, stages, b_bytes, hp_ld, kg_ld;
+};
+
+__host__ __device__ constexpr int t2_gcd(int a, int b) { return b == 0 ? a : t2_gcd(b, a % b); }
+__host__ __device__ constexpr int t2_lcm(int a, int b) { return a / t2_gcd(a, b) * b; }
+
+// GL keys of one lane (GL accumulator columns of its row) -> the maximum over the GL lanes of its aligned
+// group for ONE column: lane l ends up with column (l & (GL-1)).  3 (GL=8) / 2 (GL=4) halving exchange stages.
+template <int GL>
+__device__ __forceinline__ uint32_t group_colmax(uint32_t* k, int lane) {
+#pragma unroll
+  for (int w = GL / 2; w >= 1; w >>= 1) {
+    const bool hi = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const uint32_t send = hi ? k[i] : k[i + w];
+      const uint32_t keep = hi ? k[i + w] : k[i];
+      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, w);
+      k[i] = keep > recv ? keep : recv;
+    }
+  }
+  return k[0];
+}
+
+template <int NY, int GL>
+__global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __grid_constant__ Tc2Args a) {
+  constexpr int CH = t2_lcm(NY, GL);       // accumulator columns per epilogue chunk: whole samples, whole groups
+  constexpr int SPC = CH / NY;             // Y samples per chunk
+  constexpr uint32_t LOWM = GL - 1;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] [hp 2 x 128 x hp_ld f32] [keyG (128/GL) x kg_ld u32] [colw SX x UN f32] [barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = T2_A_BYTES + a.b_bytes;
+  float* hp = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes);
+  uint32_t* keyG = reinterpret_cast<uint32_t*>(hp + 2 * T2_BM * a.hp_ld);
+  float* colw = reinterpret_cast<float*>(keyG + (T2_BM / GL) * a.kg_ld);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(colw + ((a.SX * a.UN + 1) & ~1));
+  uint64_t* full = bars;                          // [stages]  TMA -> MMA
+  uint64_t* empty = bars + T2_MAX_STAGES;         // [stages]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * T2_MAX_STAGES;     // [2]       MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                   // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int p = 0; p < a.nprob; ++p) { tma_prefetch_desc(&a.tmx[p]); tma_prefetch_desc(&a.tmy[p]); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, T2_EPI); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile index -> (problem, m-tile, n-tile); n fastest so that concurrently running CTAs share the X box in L2
+  auto decode = [&](int tile, int& p, int& mt, int& nt) {
+    p = 0;
+    while (p + 1 < a.nprob && tile >= a.p[p + 1].tile0) ++p;
+    const int local = tile - a.p[p].tile0;
+    mt = local / a.p[p].n_nt;
+    nt = local - mt * a.p[p].n_nt;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(a.MU + a.SY * NY) * 128u;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        int p, mt, nt;
+        decode(tile, p, mt, nt);
+        const int row_x = mt * a.MU, row_y = nt * a.SY * NY;
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(full + stage, tx_bytes);
+          tma_load_2d(sa, &a.tmx[p], full + stage, kb * T2_BK, row_x);
+          tma_load_2d(sa + T2_A_BYTES, &a.tmy[p], full + stage, kb * T2_BK, row_y);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(T2_BM, a.UN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty + acc, acc_phase ^ 1);          // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * T2_ACC_COLS);
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + T2_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < T2_BK / 16; ++k)           // advance 32 B (16 bf16) inside the swizzle row
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          umma_commit(empty + stage);                    // smem slot free when these MMAs retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull + acc);                        // accumulator ready for the epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;                    // the two warps of a quarter take alternate chunks
+    const int r = q * 32 + lane;                         // accumulator row = X token of the tile
+    const int et = threadIdx.x - 64;                     // 0..255
+    const int Nx = a.Nx;
+    const int sx = r / Nx, x = r - sx * Nx;
+    const uint32_t low = LOWM - ((uint32_t)lane & LOWM);
+    uint32_t* kg_row = keyG + (r / GL) * a.kg_ld + (lane & (int)LOWM);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      int pi, mt, nt;
+      decode(tile, pi, mt, nt);
+      const Tc2Prob& P = a.p[pi];
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int ry0 = nt * a.SY;
+      const int sy_n = min(a.SY, P.Ry - ry0);
+      const int sx_n = min(a.SX, P.Rx - mt * a.SX);
+      const int n_ch = (sy_n + SPC - 1) / SPC;
+      float* hpb = hp + (size_t)acc * T2_BM * a.hp_ld;
+      const int rx = mt * a.SX + sx;
+      const bool row_ok = (r < a.MU) && (rx < P.Rx);
+      const float wxv = row_ok ? P.wx[(int64_t)rx * Nx + x] : 0.f;
+      const int64_t obase = ((int64_t)rx * P.Ry + ry0) * Nx + x;
+      float* const pmx = row_ok ? P.pmax_x : nullptr;
+      uint8_t* const yst = row_ok ? P.ystar : nullptr;
+      mbar_wait(tfull + acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_ACC_COLS);
+      auto process = [&](const uint32_t* v, int ch) {
+        // row direction: max / arg-max over the NY columns of each Y sample of the chunk
+#pragma unroll
+        for (int s2 = 0; s2 < SPC; ++s2) {
+          const int sy = ch * SPC + s2;
+          float f[NY];
+#pragma unroll
+          for (int y = 0; y < NY; ++y) f[y] = __uint_as_float(v[s2 * NY + y]);
+          const float best = TreeRed<NY>::fmax_(f);
+          const int bi = TreeRed<NY>::first_eq(f, best, 0);
+          if (sy < sy_n) {
+            hpb[r * a.hp_ld + sy] = wxv * best;
+            const int64_t o = obase + (int64_t)sy * Nx;
+            if (pmx) pmx[o] = best;
+            if (yst) yst[o] = (uint8_t)bi;
+          }
+        }
+        // column direction: group partial of (value, row) keys, one column per lane
+#pragma unroll
+        for (int g = 0; g < CH / GL; ++g) {
+          uint32_t k[GL];
+#pragma unroll
+          for (int j = 0; j < GL; ++j) k[j] = (__float_as_uint(__uint_as_float(v[g * GL + j]) + 2.0f) & ~LOWM) | low;
+          kg_row[ch * CH + g * GL] = group_colmax<GL>(k, lane);
+        }
+      };
+      if constexpr (CH <= 32) {
+        // two register buffers: the TMEM load of the next chunk is in flight while this one is reduced
+        uint32_t va[CH], vb[CH];
+        int ch = half;
+        if (ch < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)(ch * CH), va);
+        for (; ch < n_ch; ch += 4) {
+          tmem_ld_wait();
+          reg_fence<CH>(va);
+          const int ch2 = ch + 2;
+          if (ch2 < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)(ch2 * CH), vb);
+          process(va, ch);
+          if (ch2 < n_ch) {
+            tmem_ld_wait();
+            reg_fence<CH>(vb);
+            if (ch + 4 < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)((ch + 4) * CH), va);
+            process(vb, ch2);
+          }
+        }
+      } else {
+        for (int ch = half; ch < n_ch; ch += 2) {
+          uint32_t v[CH];
+          tmem_ld_cols<CH>(taddr + (uint32_t)(ch * CH), v);
+          tmem_ld_wait();
+          reg_fence<CH>(v);
+          process(v, ch);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty + acc);                         // TMEM stage may be overwritten
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // F1: combine the Nx/GL group partials of each (X sample, column): value, arg-max row, weighted value
+      {
+        const int ncols = sy_n * NY, ng = Nx / GL;
+        for (int e = et; e < sx_n * ncols; e += T2_EPI) {
+          const int s = e / ncols, c = e - s * ncols;
+          const uint32_t* kp = keyG + (s * ng) * a.kg_ld + c;
+          uint32_t best = kp[0]; int bg = 0;
+          for (int gi = 1; gi < ng; ++gi) {
+            const uint32_t kk = kp[gi * a.kg_ld];
+            if ((kk & ~LOWM) > (best & ~LOWM)) { best = kk; bg = gi; }   // equal values: the lower group stays
+          }
+          const float val = __uint_as_float(best & ~LOWM) - 2.0f;
+          const int xs = bg * GL + (int)(LOWM - (best & LOWM));
+          const int64_t o = ((int64_t)(mt * a.SX + s) * P.Ry + ry0) * NY + c;
+          if (P.pmax_y) P.pmax_y[o] = val;
+          if (P.xstar) P.xstar[o] = (uint8_t)xs;
+          colw[s * a.UN + c] = P.wy[(int64_t)ry0 * NY + c] * val;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // F2: S[rx, ry] = alpha * (sum over the Nx rows of hp + sum over the NY columns of colw)
+      for (int e = et; e < sx_n * sy_n; e += T2_EPI) {
+        const int s = e / sy_n, sy = e - s * sy_n;
+        float h = 0.f;
+        for (int xx = 0; xx < Nx; ++xx) h += hpb[(s * Nx + xx) * a.hp_ld + sy];
+        const float* cw = colw + s * a.UN + sy * NY;
+#pragma unroll
+        for (int y = 0; y < NY; ++y) h += cw[y];
+        h *= P.alpha;
+        const int rxx = mt * a.SX + s, ry = ry0 + sy;
+        P.out[(int64_t)rxx * P.out_sr + (int64_t)ry * P.out_sc] = h;
+        if (P.out2) P.out2[(int64_t)rxx * P.out2_sr + (int64_t)ry * P.out2_sc] = h;
+      }
+      // colw / keyG are rewritten only after the next tile's first barrier, hp is double-buffered
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NY, int GL>
+static int launch2(const Tc2Args& a, size_t smem, int grid, cudaStream_t stream) {
+  NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  maxsim2_fwd_tc_kernel<NY, GL><<<grid, T2_THREADS, smem, stream>>>(a);
+  NR_CHECK_LAUNCH("nr_maxsim2_fwd");
+  return 0;
+}
+
+template <int GL>
+static int dispatch_ny(int Ny, const Tc2Args& a, size_t smem, int grid, cudaStream_t stream) {
+  switch (Ny) {
+    case 4: return launch2<4, GL>(a, smem, grid, stream);
+    case 8: return launch2<8, GL>(a, smem, grid, stream);
+    case 12: return launch2<12, GL>(a, smem, grid, stream);
+    case 16: return launch2<16, GL>(a, smem, grid, stream);
+    case 24: return launch2<24, GL>(a, smem, grid, stream);
+    case 32: return launch2<32, GL>(a, smem, grid, stream);
+    case 48: return launch2<48, GL>(a, smem, grid, stream);
+    case 64: return launch2<64, GL>(a, smem, grid, stream);
+    default:
+      nr::set_error("nr_maxsim2_fwd: Ny=%d has no tensor-core instantiation (4,8,12,16,24,32,48,64)", Ny);
+      return -3;
+  }
+}
+
+}  // namespace nr
+
+using namespace nr;
+
+extern "C" int nr_maxsim2_supported(int64_t Nx, int64_t Ny, int64_t d) {
+  const bool ny_ok = Ny == 4 || Ny == 8 || Ny == 12 || Ny == 16 || Ny == 24 || Ny == 32 || Ny == 48 || Ny == 64;
+  return (ny_ok && Nx % 4 == 0 && Nx >= 4 && Nx <= 128 && d % T2_BK == 0 && d > 0) ? 1 : 0;
+}
+
+extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
+                              void* stream) {
+  NR_CHECK_ARG(probs && nprob >= 1 && nprob <= T2_MAX_PROB, "nr_maxsim2_fwd: 1..%d problems per launch (got %d)",
+               T2_MAX_PROB, nprob);
+  NR_CHECK_ARG(nr_maxsim2_supported(Nx, Ny, d),
+               "nr_maxsim2_fwd: unsupported shape Nx=%lld (multiple of 4, <=128) Ny=%lld (4,8,12,16,24,32,48,64) "
+               "d=%lld (multiple of %d)", (long long)Nx, (long long)Ny, (long long)d, T2_BK);
+  const int GL = (Nx % 8 == 0) ? 8 : 4;
+  const int CH = t2_lcm((int)Ny, GL), SPC = CH / (int)Ny;
+  int64_t max_rx = 0, max_ry = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const nr_maxsim2_problem& q = probs[i];
+    NR_CHECK_ARG(q.x_bf16 && q.y_bf16 && q.wx && q.wy && q.out && q.Rx > 0 && q.Ry > 0,
+                 "nr_maxsim2_fwd: problem %d has a null pointer or an empty side", i);
+    NR_CHECK_ARG(((uintptr_t)q.x_bf16 & 15) == 0 && ((uintptr_t)q.y_bf16 & 15) == 0,
+                 "nr_maxsim2_fwd: operands must be 16-byte aligned");
+    if (q.Rx > max_rx) max_rx = q.Rx;
+    if (q.Ry > max_ry) max_ry = q.Ry;
+  }
+  Tc2Args a{};
+  a.nprob = nprob;
+  a.Nx = (int)Nx;
+  a.SX = T2_BM / (int)Nx;
+  if (a.SX > max_rx) a.SX = (int)max_rx;
+  a.MU = a.SX * (int)Nx;
+  a.SY = (256 / (int)Ny) / SPC * SPC;
+  if (a.SY > max_ry) a.SY = (int)((max_ry + SPC - 1) / SPC * SPC);
+  a.UN = (a.SY * (int)Ny + 15) / 16 * 16;
+  a.num_kb = (int)(d / T2_BK);
+  a.b_bytes = (a.UN * 128 + 1023) / 1024 * 1024;
+  a.hp_ld = a.SY | 1;
+  a.kg_ld = a.UN;
+  if (GL == 8) { while (a.kg_ld % 32 != 8 && a.kg_ld % 32 != 24) a.kg_ld += 8; }
+  else { while (a.kg_ld % 8 != 4) a.kg_ld += 4; }
+  int tiles = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const nr_maxsim2_problem& q = probs[i];
+    Tc2Prob& P = a.p[i];
+    P.wx = q.wx; P.wy = q.wy; P.Rx = (int)q.Rx; P.Ry = (int)q.Ry; P.alpha = q.alpha;
+    P.out = q.out; P.out_sr = q.out_sr; P.out_sc = q.out_sc;
+    P.out2 = q.out2; P.out2_sr = q.out2_sr; P.out2_sc = q.out2_sc;
+    P.pmax_x = q.pmax_x; P.ystar = q.ystar; P.pmax_y = q.pmax_y; P.xstar = q.xstar;
+    P.n_mt = (int)((q.Rx + a.SX - 1) / a.SX);
+    P.n_nt = (int)((q.Ry + a.SY - 1) / a.SY);
+    P.tile0 = tiles;
+    tiles += P.n_mt * P.n_nt;
+    if (int e = make_tmap_bf16(&a.tmx[i], q.x_bf16, q.Rx * Nx, d, a.MU)) return e;
+    if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny)) return e;
+  }
+  a.n_tiles = tiles;
+  const size_t tail = (size_t)2 * T2_BM * a.hp_ld * 4 + (size_t)(T2_BM / GL) * a.kg_ld * 4 +
+                      (size_t)((a.SX * a.UN + 1) & ~1) * 4 + 256;
+  const size_t budget = 227 * 1024 - 1024;   // alignment slack
+  int stages = (int)((budget - tail) / (size_t)(T2_A_BYTES + a.b_bytes));
+  if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;
+  NR_CHECK_ARG(stages >= 2, "nr_maxsim2_fwd: tile does not fit shared memory");
+  a.stages = stages;
+  const size_t smem = (size_t)stages * (T2_A_BYTES + a.b_bytes) + tail + 1024;
+  int dev = 0, sms = 0;
+  NR_CUDA(cudaGetDevice(&dev));
+  NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = tiles < sms ? tiles : sms;
+  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, (cudaStream_t)stream);
+  return dispatch_ny<4>((int)Ny, a, smem, grid, (cudaStream_t)stream);
+}

@@ -43,24 +43,6 @@ struct TcFwdArgs {
   int hp_ld;                               // leading dimension (floats) of the weighted-partial buffer
 };
 
-// masked max / arg-max over the NY accumulator columns of one Y sample, as two balanced trees (depth log2 NY)
-// instead of a serial compare-select chain; ties -> lowest y, exactly like a left-to-right strict '>' scan.
-template <int N>
-struct TreeRed {
-  static __device__ __forceinline__ float fmax_(const float* t) {
-    return fmaxf(TreeRed<N / 2>::fmax_(t), TreeRed<N - N / 2>::fmax_(t + N / 2));
-  }
-  // lowest index y (offset by base) whose value equals m, 255 if none
-  static __device__ __forceinline__ int first_eq(const float* t, float m, int base) {
-    return min(TreeRed<N / 2>::first_eq(t, m, base), TreeRed<N - N / 2>::first_eq(t + N / 2, m, base + N / 2));
-  }
-};
-template <>
-struct TreeRed<1> {
-  static __device__ __forceinline__ float fmax_(const float* t) { return t[0]; }
-  static __device__ __forceinline__ int first_eq(const float* t, float m, int base) { return t[0] == m ? base : 255; }
-};
-
 template <int NY>
 __device__ __forceinline__ void sample_argmax(const uint32_t* v, uint64_t mb, bool full, float& best, int& bi) {
   float f[NY];
@@ -584,7 +566,7 @@ maxsim_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const TcBwdArgs a)
 }
 
 // 2-D bf16 [d, ld] (transposed tokens) -> boxes {64 tokens, box_rows d-rows}, 128B swizzle
-static int make_tmap_srcT(CUtensorMap* m, const void* base, int64_t d, int64_t tokens, int64_t ld, int box_rows) {
+int make_tmap_srcT(CUtensorMap* m, const void* base, int64_t d, int64_t tokens, int64_t ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   NR_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
   cuuint64_t gdim[2] = {(cuuint64_t)tokens, (cuuint64_t)d};

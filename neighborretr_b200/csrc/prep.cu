@@ -19,7 +19,7 @@ constexpr int PREP_MAX_BLOCKS = 296;  // 2 CTAs per SM
 __global__ void __launch_bounds__(PREP_WARPS * 32)
 prep_tokens_kernel(const float* __restrict__ x, int rows, int d, float* __restrict__ xn_f32,
                    __nv_bfloat16* __restrict__ xn_bf16, float* __restrict__ inv_norm,
-                   float* __restrict__ partials) {
+                   float* __restrict__ partials, const int64_t* __restrict__ mask) {
   __shared__ float colsm[PREP_WARPS][128 * PREP_MAXQ];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 acc[PREP_MAXQ];
@@ -40,6 +40,9 @@ prep_tokens_kernel(const float* __restrict__ x, int rows, int d, float* __restri
     ss = warp_sum(ss);
     const float denom = fmaxf(sqrtf(ss), 1e-12f);    // F.normalize eps
     if (lane == 0 && inv_norm) inv_norm[row] = 1.0f / denom;
+    // masked tokens become zero rows of the bf16 operand copy: their token pairs are then exactly 0, which is
+    // what the reference's mask multiplies produce (modeling.py:500-501); fp32 copy and column sums keep them
+    const bool live = mask ? (mask[row] != 0) : true;
 #pragma unroll
     for (int q = 0; q < PREP_MAXQ; ++q) {
       int c = q * 128 + lane * 4;
@@ -49,8 +52,8 @@ prep_tokens_kernel(const float* __restrict__ x, int rows, int d, float* __restri
         if (xn_bf16) {
           __nv_bfloat162 lo = __floats2bfloat162_rn(n.x, n.y), hi = __floats2bfloat162_rn(n.z, n.w);
           uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          pk.x = live ? *reinterpret_cast<uint32_t*>(&lo) : 0u;
+          pk.y = live ? *reinterpret_cast<uint32_t*>(&hi) : 0u;
           *reinterpret_cast<uint2*>(xn_bf16 + (int64_t)row * d + c) = pk;
         }
         acc[q].x += n.x; acc[q].y += n.y; acc[q].z += n.z; acc[q].w += n.w;
@@ -75,12 +78,13 @@ prep_tokens_kernel(const float* __restrict__ x, int rows, int d, float* __restri
 
 __global__ void __launch_bounds__(PREP_WARPS * 32)
 prep_tokens_bwd_kernel(const float* __restrict__ xn, const float* __restrict__ inv_norm,
-                       const float* __restrict__ dxn, const float* __restrict__ add_vec, int rows, int d,
-                       float* __restrict__ dx, int accumulate) {
+                       const float* __restrict__ dxn, const float* __restrict__ add_vec,
+                       const int64_t* __restrict__ mask, int rows, int d, float* __restrict__ dx, int accumulate) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = blockIdx.x * PREP_WARPS + warp;
   if (row >= rows) return;
   const float* nr_ = xn + (int64_t)row * d;
+  const bool live = mask ? (mask[row] != 0) : true;     // masked tokens take no max-sim gradient (dxn), only add_vec
   float4 n[PREP_MAXQ], t[PREP_MAXQ];
   float dot = 0.f;
 #pragma unroll
@@ -88,7 +92,8 @@ prep_tokens_bwd_kernel(const float* __restrict__ xn, const float* __restrict__ i
     int c = q * 128 + lane * 4;
     if (c < d) {
       n[q] = *reinterpret_cast<const float4*>(nr_ + c);
-      t[q] = dxn ? *reinterpret_cast<const float4*>(dxn + (int64_t)row * d + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      t[q] = (dxn && live) ? *reinterpret_cast<const float4*>(dxn + (int64_t)row * d + c)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
       if (add_vec) {
         float4 a = *reinterpret_cast<const float4*>(add_vec + c);
         t[q].x += a.x; t[q].y += a.y; t[q].z += a.z; t[q].w += a.w;
@@ -201,24 +206,24 @@ extern "C" int64_t nr_prep_partials(int64_t rows) {
 }
 
 extern "C" int nr_prep_tokens(const float* x, int64_t rows, int64_t d, float* xn_f32, void* xn_bf16,
-                              float* inv_norm, float* colsum_partials, void* stream) {
+                              float* inv_norm, float* colsum_partials, const int64_t* mask, void* stream) {
   NR_CHECK_ARG(x && rows > 0, "nr_prep_tokens: bad arguments");
   NR_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 128 * PREP_MAXQ, "nr_prep_tokens: d=%lld must be a multiple of 4, <= %d",
                (long long)d, 128 * PREP_MAXQ);
   int grid = (int)nr_prep_partials(rows);
   prep_tokens_kernel<<<grid, PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      x, (int)rows, (int)d, xn_f32, (__nv_bfloat16*)xn_bf16, inv_norm, colsum_partials);
+      x, (int)rows, (int)d, xn_f32, (__nv_bfloat16*)xn_bf16, inv_norm, colsum_partials, mask);
   NR_CHECK_LAUNCH("nr_prep_tokens");
   return 0;
 }
 
 extern "C" int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* dxn,
-                                  const float* add_vec, int64_t rows, int64_t d, float* dx, int accumulate,
-                                  void* stream) {
+                                  const float* add_vec, const int64_t* mask, int64_t rows, int64_t d, float* dx,
+                                  int accumulate, void* stream) {
   NR_CHECK_ARG(xn_f32 && inv_norm && dx && rows > 0 && (dxn || add_vec), "nr_prep_tokens_bwd: bad arguments");
   NR_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 128 * PREP_MAXQ, "nr_prep_tokens_bwd: unsupported d=%lld", (long long)d);
   int grid = (int)((rows + PREP_WARPS - 1) / PREP_WARPS);
-  prep_tokens_bwd_kernel<<<grid, PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(xn_f32, inv_norm, dxn, add_vec,
+  prep_tokens_bwd_kernel<<<grid, PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(xn_f32, inv_norm, dxn, add_vec, mask,
                                                                             (int)rows, (int)d, dx, accumulate);
   NR_CHECK_LAUNCH("nr_prep_tokens_bwd");
   return 0;

@@ -149,5 +149,23 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// masked max / arg-max over the NY accumulator columns of one Y sample, as two balanced trees (depth log2 NY)
+// instead of a serial compare-select chain; ties -> lowest y, exactly like a left-to-right strict '>' scan.
+template <int N>
+struct TreeRed {
+  static __device__ __forceinline__ float fmax_(const float* t) {
+    return fmaxf(TreeRed<N / 2>::fmax_(t), TreeRed<N - N / 2>::fmax_(t + N / 2));
+  }
+  // lowest index y (offset by base) whose value equals m, 255 if none
+  static __device__ __forceinline__ int first_eq(const float* t, float m, int base) {
+    return min(TreeRed<N / 2>::first_eq(t, m, base), TreeRed<N - N / 2>::first_eq(t + N / 2, m, base + N / 2));
+  }
+};
+template <>
+struct TreeRed<1> {
+  static __device__ __forceinline__ float fmax_(const float* t) { return t[0]; }
+  static __device__ __forceinline__ int first_eq(const float* t, float m, int base) { return t[0] == m ? base : 255; }
+};
+
 }  // namespace tc
 }  // namespace nr

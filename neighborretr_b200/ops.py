@@ -97,15 +97,18 @@ class Prepared:
     """L2-normalised tokens of one modality: fp32 copy (backward / fp32 mode), optional bf16 operand
     copy (tensor-core mode), inverse norms and per-CTA column-sum partials."""
 
-    __slots__ = ("xn", "xn_bf16", "xnT_bf16", "inv_norm", "partials", "rows", "n", "d", "r", "_parent", "_lo")
+    __slots__ = ("xn", "xn_bf16", "xnT_bf16", "inv_norm", "partials", "rows", "n", "d", "r", "_parent", "_lo", "mask")
 
-    def __init__(self, x, bf16=False, colsum=False, normalize=True):
+    def __init__(self, x, bf16=False, colsum=False, normalize=True, mask=None):
+        """mask [r, n] int64 (optional): masked tokens become zero rows of the bf16 operand copy (and of its
+        transposed copy) and take no max-sim gradient in backward(); required by the fused two-direction kernel."""
         _req_cuda(x)
         x = _f32c(x)
         self.r, self.n, self.d = x.shape
         self.rows = self.r * self.n
         self.xnT_bf16 = None
         self._parent, self._lo = None, 0
+        self.mask = _mask(mask)
         dev = x.device
         if not normalize:        # global_level: raw dot products (reference modeling.py:525), fp32 only
             self.xn, self.xn_bf16, self.inv_norm, self.partials = x, None, None, None
@@ -116,7 +119,7 @@ class Prepared:
         npart = _lib.load().nr_prep_partials(self.rows)
         self.partials = torch.empty(npart, self.d, dtype=torch.float32, device=dev) if colsum else None
         _call("nr_prep_tokens", _p(x), self.rows, self.d, _p(self.xn), _p(self.xn_bf16), _p(self.inv_norm),
-              _p(self.partials), _stream())
+              _p(self.partials), _p(self.mask), _stream())
 
     def operand(self, prec):
         return self.xn_bf16 if prec == NR_PREC_BF16 else self.xn
@@ -149,14 +152,15 @@ class Prepared:
         v.partials = None
         v.xnT_bf16 = None
         v._parent, v._lo = self, lo
+        v.mask = self.mask[lo:lo + n] if self.mask is not None else None
         return v
 
     def backward(self, dxn, add_vec=None):
         if self.inv_norm is None:
             return dxn
         dx = torch.empty_like(self.xn)
-        _call("nr_prep_tokens_bwd", _p(self.xn), _p(self.inv_norm), _p(dxn), _p(add_vec), self.rows, self.d, _p(dx),
-              0, _stream())
+        _call("nr_prep_tokens_bwd", _p(self.xn), _p(self.inv_norm), _p(dxn), _p(add_vec), _p(self.mask), self.rows,
+              self.d, _p(dx), 0, _stream())
         return dx
 
 
@@ -173,6 +177,74 @@ def _maxsim_dir_fwd(prec, X: Prepared, Y: Prepared, wx, mx, my, alpha, out, sr, 
     return pmax, ystar
 
 
+def maxsim2_supported(nx, ny, d):
+    return bool(_lib.load().nr_maxsim2_supported(nx, ny, d))
+
+
+def maxsim2_fwd(problems, keep=True):
+    """Fused two-direction max-sim (nr_maxsim2_fwd) of up to 4 problems in ONE launch.  Each problem is a dict with
+    X, Y (Prepared with zeroed masked tokens), wx, wy, alpha, out, strides=(sr, sc) and optionally out2, strides2.
+    Returns per problem (pmax_x, ystar, pmax_y, xstar) (None if not keep)."""
+    arr = (_lib.MaxSim2Problem * len(problems))()
+    saved = []
+    nx, ny, d = problems[0]["X"].n, problems[0]["Y"].n, problems[0]["X"].d
+    for i, q in enumerate(problems):
+        X, Y = q["X"], q["Y"]
+        if (X.n, Y.n, X.d, Y.d) != (nx, ny, d, d):
+            raise RuntimeError("maxsim2_fwd: all problems of a launch must share (Nx, Ny, d)")
+        if X.xn_bf16 is None or Y.xn_bf16 is None:
+            raise RuntimeError("maxsim2_fwd: bf16 operand copies required (Prepared(..., bf16=True, mask=...))")
+        dev = X.xn.device
+        if keep:
+            sv = (torch.empty(X.r, Y.r, nx, dtype=torch.float32, device=dev),
+                  torch.empty(X.r, Y.r, nx, dtype=torch.uint8, device=dev),
+                  torch.empty(X.r, Y.r, ny, dtype=torch.float32, device=dev),
+                  torch.empty(X.r, Y.r, ny, dtype=torch.uint8, device=dev))
+        else:
+            sv = (None, None, None, None)
+        saved.append(sv)
+        a = arr[i]
+        a.x_bf16, a.y_bf16 = X.xn_bf16.data_ptr(), Y.xn_bf16.data_ptr()
+        a.wx, a.wy = q["wx"].data_ptr(), q["wy"].data_ptr()
+        a.Rx, a.Ry, a.alpha = X.r, Y.r, float(q["alpha"])
+        a.out, (a.out_sr, a.out_sc) = q["out"].data_ptr(), q["strides"]
+        o2 = q.get("out2")
+        a.out2 = o2.data_ptr() if o2 is not None else None
+        a.out2_sr, a.out2_sc = q.get("strides2", (0, 0))
+        a.pmax_x, a.ystar, a.pmax_y, a.xstar = [t.data_ptr() if t is not None else None for t in sv]
+    _call("nr_maxsim2_fwd", ctypes.cast(arr, ctypes.c_void_p), len(problems), nx, ny, d, _stream())
+    return saved
+
+
+def maxsim2_bwd(side, src, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, nx, ry, ny, d, dst):
+    """dst += (routing matrix of the fused max-sim, or its transpose) x the tokens of `src` (a Prepared whose
+    transposed bf16 copy is the staged operand); side 0: dst = X-token gradient, side 1: Y-token gradient."""
+    s, ld = src.bwd_source(NR_PREC_BF16)
+    _call("nr_maxsim2_bwd", side, _p(s), ld, _p(wx), _p(wy), _p(ystar), _p(xstar), _p(g), g_sr, g_sc, scale, rx, nx, ry,
+          ny, d, _p(dst), _stream())
+
+
+def maxsim2_bwd_w(pmax_x, pmax_y, g, g_sr, g_sc, scale, rx, nx, ry, ny, dwx, dwy):
+    _call("nr_maxsim2_bwd_w", _p(pmax_x), _p(pmax_y), _p(g), g_sr, g_sc, scale, rx, nx, ry, ny, _p(dwx), _p(dwy),
+          _stream())
+
+
+# the fused two-direction kernels are the bf16 path; tests flip this to compare against the one-direction kernels
+USE_FUSED_MAXSIM = True
+
+
+def _fused_orientation(nt, nv, d):
+    """Which modality plays X in the fused kernel (its column-direction butterfly wants Nx % 4 == 0):
+    False = text, True = video, None = neither orientation is supported."""
+    if not USE_FUSED_MAXSIM:
+        return None
+    if maxsim2_supported(nt, nv, d):
+        return False
+    if maxsim2_supported(nv, nt, d):
+        return True
+    return None
+
+
 class MaxSimFunction(torch.autograd.Function):
     """local_level's token-pair part (reference modeling.py:495-512) given the token weights:
     returns (S, S^T) as two contiguous tensors.  bwd_prec selects the arithmetic of the backward
@@ -186,13 +258,32 @@ class MaxSimFunction(torch.autograd.Function):
         if not normalize:
             prec = bwd_prec = NR_PREC_FP32
         need_bf16 = prec == NR_PREC_BF16 or bwd_prec == NR_PREC_BF16
+        keep = any(ctx.needs_input_grad[:4])
+        swap = None
+        if prec == NR_PREC_BF16 and bwd_prec == NR_PREC_BF16:
+            swap = _fused_orientation(text_feat.shape[1], video_feat.shape[1], text_feat.shape[2])
+        ctx.fused = swap is not None
+        if ctx.fused:
+            # one launch: both directions from the same accumulator tile, masks folded into the operand copies
+            T = Prepared(text_feat, bf16=True, mask=tm)
+            V = Prepared(video_feat, bf16=True, mask=vm)
+            A, B = T.r, V.r
+            S = torch.empty(A, B, dtype=torch.float32, device=T.xn.device)
+            ST = torch.empty(B, A, dtype=torch.float32, device=T.xn.device)
+            if swap:
+                q = dict(X=V, Y=T, wx=vw, wy=tw, alpha=0.5, out=S, strides=(1, B), out2=ST, strides2=(A, 1))
+            else:
+                q = dict(X=T, Y=V, wx=tw, wy=vw, alpha=0.5, out=S, strides=(B, 1), out2=ST, strides2=(1, A))
+            sv = maxsim2_fwd([q], keep=keep)[0]
+            ctx.T, ctx.V, ctx.prec, ctx.swap = T, V, bwd_prec, swap
+            ctx.save_for_backward(tw, vw, tm, vm, *sv)
+            return S, ST
         T = Prepared(text_feat, bf16=need_bf16, normalize=normalize)
         V = Prepared(video_feat, bf16=need_bf16, normalize=normalize)
         A, B = T.r, V.r
         dev = T.xn.device
         S = torch.empty(A, B, dtype=torch.float32, device=dev)
         ST = torch.empty(B, A, dtype=torch.float32, device=dev)
-        keep = any(ctx.needs_input_grad[:4])
         p1, y1 = _maxsim_dir_fwd(prec, T, V, tw, tm, vm, 0.5, S, B, 1, ST, 1, A, 0, keep)
         p2, y2 = _maxsim_dir_fwd(prec, V, T, vw, vm, tm, 0.5, S, 1, B, ST, A, 1, 1, keep)
         ctx.T, ctx.V, ctx.prec = T, V, bwd_prec
@@ -220,6 +311,29 @@ class MaxSimFunction(torch.autograd.Function):
         dvn = torch.zeros_like(V.xn) if need_v else None
         dtw = torch.zeros_like(tw) if need_tw else None
         dvw = torch.zeros_like(vw) if need_vw else None
+        if ctx.fused:
+            if ctx.swap:      # X = video, Y = text: g(rx=b, ry=a) = g[a,b]
+                dims = (B, V.n, A, T.n, T.d)
+                gs = (1, B)
+                args = (vw, tw, y1, y2)
+                side_t, side_v, src_t, src_v = 1, 0, V, T
+                dwx, dwy = dvw, dtw
+            else:
+                dims = (A, T.n, B, V.n, T.d)
+                gs = (B, 1)
+                args = (tw, vw, y1, y2)
+                side_t, side_v, src_t, src_v = 0, 1, V, T
+                dwx, dwy = dtw, dvw
+            if need_t:
+                maxsim2_bwd(side_t, src_t, *args, g, gs[0], gs[1], 0.5, *dims, dtn)
+            if need_v:
+                maxsim2_bwd(side_v, src_v, *args, g, gs[0], gs[1], 0.5, *dims, dvn)
+            if dwx is not None or dwy is not None:
+                maxsim2_bwd_w(p1, p2, g, gs[0], gs[1], 0.5, *dims[:4], dwx, dwy)
+            dtext = T.backward(dtn) if need_t else None
+            dvideo = V.backward(dvn) if need_v else None
+            ctx.T = ctx.V = None
+            return dtext, dvideo, dtw, dvw, None, None, None, None, None
         # direction 1: X = text, Y = video, dH[rx=a, ry=b] = 0.5 g[a,b]
         if need_t:
             vs, vld = V.bwd_source(prec)
