@@ -84,6 +84,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+K1_TRAFFIC = {}
+
+
 def flops_maxsim(rx, ry, nt, nv, d=D):
     return 2.0 * rx * ry * nt * nv * d
 
@@ -316,7 +320,8 @@ def run_ours(args):
     for _ in range(2):
         step(pinned, True)
     ms_e2e_eager = timed(lambda: step(pinned, True), args.steps)
-    ops.KERNEL_TIMER.enable("nr_maxsim_fwd")
+    kname = "nr_maxsim2_fwd" if (args.precision == "bf16" and (args.bwd_precision or "bf16") == "bf16") else "nr_maxsim_fwd"
+    ops.KERNEL_TIMER.enable(kname)
     ksteps = min(args.steps, 10)
     timed(lambda: step(resident, False), ksteps)
     kt = ops.KERNEL_TIMER.collect()
@@ -340,11 +345,12 @@ def run_ours(args):
 
     B = B_PER_GPU * world
     pk = peaks()
-    # dominant kernel = nr_maxsim_fwd.  Algorithmic flops of a rank-step's forward contractions:
-    # every S entry and every bank entry counted ONCE globally, un-padded tokens only:
+    # dominant kernel = nr_maxsim2_fwd: ONE launch per step holding the batch pair(s) and both bank pairs, both
+    # max directions from the same accumulator tile.  Algorithmic flops of a rank-step's forward contractions
+    # (SURVEY.md §8(d)): every S entry and every bank entry counted ONCE globally, un-padded tokens only:
     #   2*Nt*Nv*D * (b*B + 2*b*M)   with b = per-rank rows.
-    # Executed MMA work is higher: each entry takes one launch per orientation (x2) and, for W > 1, a rank computes
-    # both a row block and a column block of S (x2 on the b*B term).
+    # Executed MMA work: x 128/120 * 256/240 tile padding at 24/12 tokens and, for W > 1, a rank computes both a row
+    # block and a column block of S (x2 on the b*B term).
     flops_step = flops_maxsim(B_PER_GPU, B, nt, nv) + 2 * flops_maxsim(B_PER_GPU, mrows, nt, nv)
     n_l = max(kt["launches"], 1)
     achieved = flops_step * ksteps / (kt["ms"] * 1e-3) / 1e12 if kt["ms"] > 0 else 0.0
@@ -363,11 +369,12 @@ def run_ours(args):
         "cuda_graph": bool(use_graph),
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "nr_maxsim_fwd", "bound": "tensor", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": 9.56e6 if (world == 1 and args.shape == "msrvtt") else None,
-                     "traffic_note": "dram bytes read+written per launch of the text x bank-video block, ncu --set "
-                                     "full (profiles/r1_k1_fwd_ncu_full.txt); algorithmic operand bytes 9.4e6",
+                     "traffic": K1_TRAFFIC.get((world, args.shape, kname)),
+                     "traffic_note": "dram bytes read+written per launch, ncu --set full of tools/k2_only.py "
+                                     "(profiles/r1_k2_fwd_ncu_full.txt); operands 22.0e6 B + saved max/arg-max and "
+                                     "similarities 26.9e6 B",
                      "launches_timed": n_l, "avg_launch_ms": kt["ms"] / n_l,
                      "share_of_step": (kt["ms"] / ksteps) / (ms_total / args.steps) if ms_total else None,
                      "timed_in": "eager steps on the launching stream (events cannot be read inside a graph replay)",

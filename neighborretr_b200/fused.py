@@ -60,22 +60,37 @@ class HeadFunction(torch.autograd.Function):
         tw, vw, tw_mb, vw_mb = _f32c(tw), _f32c(vw), _f32c(tw_mb), _f32c(vw_mb)
         tm, vm, mtm, mvm = _mask(text_mask), _mask(video_mask), _mask(mb_mask_t), _mask(mb_mask_v)
         bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
-        T = Prepared(text, bf16=bf, colsum=True)
-        V = Prepared(video, bf16=bf, colsum=True)
-        MT = Prepared(mb_feat_t, bf16=bf)
-        MV = Prepared(mb_feat_v, bf16=bf)
+        # bf16: masks are folded into the operand copies (masked tokens = zero rows) for the two-direction kernel
+        fusedk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
+                  and ops.maxsim2_supported(text.shape[1], video.shape[1], text.shape[2]))
+        T = Prepared(text, bf16=bf, colsum=True, mask=tm if fusedk else None)
+        V = Prepared(video, bf16=bf, colsum=True, mask=vm if fusedk else None)
+        MT = Prepared(mb_feat_t, bf16=bf, mask=mtm if fusedk else None)
+        MV = Prepared(mb_feat_v, bf16=bf, mask=mvm if fusedk else None)
         B, M, d = T.r, MT.r, T.d
         if V.r != B or MV.r != M:
             raise RuntimeError("text/video batch sizes (or bank sizes) differ")
         f32 = dict(dtype=torch.float32, device=dev)
         S = torch.empty(B, B, **f32); ST = torch.empty(B, B, **f32)
         mb_t2v = torch.empty(B, M, **f32); mb_v2t = torch.empty(B, M, **f32)
-        p1, y1 = _fwd_dir(prec, T, V, tw, tm, vm, S, B, 1, ST, 1, B, 0)
-        p2, y2 = _fwd_dir(prec, V, T, vw, vm, tm, S, 1, B, ST, B, 1, 1)
-        pA, yA = _fwd_dir(prec, T, MV, tw, tm, mvm, mb_t2v, M, 1, None, 0, 0, 0)        # H(text, bank_v)
-        pB, yB = _fwd_dir(prec, MV, T, vw_mb, mvm, tm, mb_t2v, 1, M, None, 0, 0, 1)     # H(bank_v, text)^T
-        pD, yD = _fwd_dir(prec, V, MT, vw, vm, mtm, mb_v2t, M, 1, None, 0, 0, 0)        # H(video, bank_t)
-        pC, yC = _fwd_dir(prec, MT, V, tw_mb, mtm, vm, mb_v2t, 1, M, None, 0, 0, 1)     # H(bank_t, video)^T
+        if fusedk:
+            # ONE launch: the batch pair and both bank pairs, each token pair multiplied once (the larger problems
+            # first so that the tail of the persistent tile list is the small one)
+            svA, svC, sv1 = ops.maxsim2_fwd([
+                dict(X=T, Y=MV, wx=tw, wy=vw_mb, alpha=0.5, out=mb_t2v, strides=(M, 1)),      # S(text, bank_v)
+                dict(X=MT, Y=V, wx=tw_mb, wy=vw, alpha=0.5, out=mb_v2t, strides=(1, M)),      # S(bank_t, video)^T
+                dict(X=T, Y=V, wx=tw, wy=vw, alpha=0.5, out=S, strides=(B, 1), out2=ST, strides2=(1, B))])
+            p1, y1, p2, y2 = sv1          # pmax_x, ystar, pmax_y, xstar of the batch pair
+            pA, yA, pB, yB = svA
+            pC, yC, pD, yD = svC
+        else:
+            p1, y1 = _fwd_dir(prec, T, V, tw, tm, vm, S, B, 1, ST, 1, B, 0)
+            p2, y2 = _fwd_dir(prec, V, T, vw, vm, tm, S, 1, B, ST, B, 1, 1)
+            pA, yA = _fwd_dir(prec, T, MV, tw, tm, mvm, mb_t2v, M, 1, None, 0, 0, 0)        # H(text, bank_v)
+            pB, yB = _fwd_dir(prec, MV, T, vw_mb, mvm, tm, mb_t2v, 1, M, None, 0, 0, 1)     # H(bank_v, text)^T
+            pD, yD = _fwd_dir(prec, V, MT, vw, vm, mtm, mb_v2t, M, 1, None, 0, 0, 0)        # H(video, bank_t)
+            pC, yC = _fwd_dir(prec, MT, V, tw_mb, mtm, vm, mb_v2t, 1, M, None, 0, 0, 1)     # H(bank_t, video)^T
+        ctx.fusedk = fusedk
         cb = torch.empty(2, B, **f32)                    # [c_t2v ; c_v2t]
         _call("nr_row_mean", _p(mb_t2v), M, B, M, _p(cb[0]), st)
         _call("nr_row_mean", _p(mb_v2t), M, B, M, _p(cb[1]), st)
@@ -158,36 +173,55 @@ class HeadFunction(torch.autograd.Function):
         vs, vld = V.bwd_source(bprec); ts, tld = T.bwd_source(bprec)
         mvs, mvld = MV.bwd_source(bprec); mts, mtld = MT.bwd_source(bprec)
         nt, nv = T.n, V.n
-        if need[0]:
-            # text <- batch pair (both orientations) and the text-vs-bank-video pair
-            _call("nr_maxsim_bwd_x", bprec, _p(vs), vld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt, B, nv,
-                  d, _p(dtn), st)
-            _call("nr_maxsim_bwd_y", bprec, _p(vs), vld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv, B, nt,
-                  d, _p(dtn), st)
-            _call("nr_maxsim_bwd_x", bprec, _p(mvs), mvld, _p(tw), _p(tm), _p(mvm), _p(yA), _p(dc[0]), 1, 0, 0.5 / M, B,
-                  nt, M, nv, d, _p(dtn), st)
-            _call("nr_maxsim_bwd_y", bprec, _p(mvs), mvld, _p(vw_mb), _p(mvm), _p(tm), _p(yB), _p(dc[0]), 0, 1, 0.5 / M,
-                  M, nv, B, nt, d, _p(dtn), st)
-        if need[1]:
-            _call("nr_maxsim_bwd_y", bprec, _p(ts), tld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt, B, nv,
-                  d, _p(dvn), st)
-            _call("nr_maxsim_bwd_x", bprec, _p(ts), tld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv, B, nt,
-                  d, _p(dvn), st)
-            _call("nr_maxsim_bwd_x", bprec, _p(mts), mtld, _p(vw), _p(vm), _p(mtm), _p(yD), _p(dc[1]), 1, 0, 0.5 / M, B,
-                  nv, M, nt, d, _p(dvn), st)
-            _call("nr_maxsim_bwd_y", bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm), _p(yC), _p(dc[1]), 0, 1, 0.5 / M,
-                  M, nt, B, nv, d, _p(dvn), st)
-        # token-weight gradients (batch pair + bank pairs)
-        if need[4]:
-            _call("nr_maxsim_bwd_w", _p(p1), _p(dS), B, 1, 0.5, B, nt, B, _p(dtw), st)
-            _call("nr_maxsim_bwd_w", _p(pA), _p(dc[0]), 1, 0, 0.5 / M, B, nt, M, _p(dtw), st)
-        if need[5]:
-            _call("nr_maxsim_bwd_w", _p(p2), _p(dS), 1, B, 0.5, B, nv, B, _p(dvw), st)
-            _call("nr_maxsim_bwd_w", _p(pD), _p(dc[1]), 1, 0, 0.5 / M, B, nv, M, _p(dvw), st)
-        if need[6]:
-            _call("nr_maxsim_bwd_w", _p(pC), _p(dc[1]), 0, 1, 0.5 / M, M, nt, B, _p(dtw_mb), st)
-        if need[7]:
-            _call("nr_maxsim_bwd_w", _p(pB), _p(dc[0]), 0, 1, 0.5 / M, M, nv, B, _p(dvw_mb), st)
+        if ctx.fusedk:
+            # one routing matrix per pair, applied from either side: 4 contraction + 3 weight launches
+            sc = 0.5 / M
+            if need[0]:
+                ops.maxsim2_bwd(0, V, tw, vw, y1, y2, dS, B, 1, 0.5, B, nt, B, nv, d, dtn)
+                ops.maxsim2_bwd(0, MV, tw, vw_mb, yA, yB, dc[0], 1, 0, sc, B, nt, M, nv, d, dtn)
+            if need[1]:
+                ops.maxsim2_bwd(1, T, tw, vw, y1, y2, dS, B, 1, 0.5, B, nt, B, nv, d, dvn)
+                ops.maxsim2_bwd(1, MT, tw_mb, vw, yC, yD, dc[1], 0, 1, sc, M, nt, B, nv, d, dvn)
+            if need[4] or need[5]:
+                ops.maxsim2_bwd_w(p1, p2, dS, B, 1, 0.5, B, nt, B, nv, dtw if need[4] else None,
+                                  dvw if need[5] else None)
+            if need[4] or need[7]:
+                ops.maxsim2_bwd_w(pA, pB, dc[0], 1, 0, sc, B, nt, M, nv, dtw if need[4] else None,
+                                  dvw_mb if need[7] else None)
+            if need[6] or need[5]:
+                ops.maxsim2_bwd_w(pC, pD, dc[1], 0, 1, sc, M, nt, B, nv, dtw_mb if need[6] else None,
+                                  dvw if need[5] else None)
+        else:
+            if need[0]:
+                # text <- batch pair (both orientations) and the text-vs-bank-video pair
+                _call("nr_maxsim_bwd_x", bprec, _p(vs), vld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt, B, nv,
+                      d, _p(dtn), st)
+                _call("nr_maxsim_bwd_y", bprec, _p(vs), vld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv, B, nt,
+                      d, _p(dtn), st)
+                _call("nr_maxsim_bwd_x", bprec, _p(mvs), mvld, _p(tw), _p(tm), _p(mvm), _p(yA), _p(dc[0]), 1, 0, 0.5 / M, B,
+                      nt, M, nv, d, _p(dtn), st)
+                _call("nr_maxsim_bwd_y", bprec, _p(mvs), mvld, _p(vw_mb), _p(mvm), _p(tm), _p(yB), _p(dc[0]), 0, 1, 0.5 / M,
+                      M, nv, B, nt, d, _p(dtn), st)
+            if need[1]:
+                _call("nr_maxsim_bwd_y", bprec, _p(ts), tld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt, B, nv,
+                      d, _p(dvn), st)
+                _call("nr_maxsim_bwd_x", bprec, _p(ts), tld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv, B, nt,
+                      d, _p(dvn), st)
+                _call("nr_maxsim_bwd_x", bprec, _p(mts), mtld, _p(vw), _p(vm), _p(mtm), _p(yD), _p(dc[1]), 1, 0, 0.5 / M, B,
+                      nv, M, nt, d, _p(dvn), st)
+                _call("nr_maxsim_bwd_y", bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm), _p(yC), _p(dc[1]), 0, 1, 0.5 / M,
+                      M, nt, B, nv, d, _p(dvn), st)
+            # token-weight gradients (batch pair + bank pairs)
+            if need[4]:
+                _call("nr_maxsim_bwd_w", _p(p1), _p(dS), B, 1, 0.5, B, nt, B, _p(dtw), st)
+                _call("nr_maxsim_bwd_w", _p(pA), _p(dc[0]), 1, 0, 0.5 / M, B, nt, M, _p(dtw), st)
+            if need[5]:
+                _call("nr_maxsim_bwd_w", _p(p2), _p(dS), 1, B, 0.5, B, nv, B, _p(dvw), st)
+                _call("nr_maxsim_bwd_w", _p(pD), _p(dc[1]), 1, 0, 0.5 / M, B, nv, M, _p(dvw), st)
+            if need[6]:
+                _call("nr_maxsim_bwd_w", _p(pC), _p(dc[1]), 0, 1, 0.5 / M, M, nt, B, _p(dtw_mb), st)
+            if need[7]:
+                _call("nr_maxsim_bwd_w", _p(pB), _p(dc[0]), 0, 1, 0.5 / M, M, nv, B, _p(dvw_mb), st)
         dtext = T.backward(dtn, add_vec=dmean[0]) if need[0] else None
         dvideo = V.backward(dvn, add_vec=dmean[1]) if need[1] else None
         ctx.objs = None

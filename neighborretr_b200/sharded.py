@@ -97,10 +97,12 @@ class ShardedHeadFunction(torch.autograd.Function):
         tw_mb, vw_mb = _f32c(tw_mb), _f32c(vw_mb)
         mtm, mvm = _mask(mb_mask_t), _mask(mb_mask_v)
         bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
-        T = Prepared(text, bf16=bf, colsum=True)
-        V = Prepared(video, bf16=bf, colsum=True)
-        MT = Prepared(mb_feat_t, bf16=bf)
-        MV = Prepared(mb_feat_v, bf16=bf)
+        fusedk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
+                  and ops.maxsim2_supported(nt_, nv_, d))
+        T = Prepared(text, bf16=bf, colsum=True, mask=tm if fusedk else None)
+        V = Prepared(video, bf16=bf, colsum=True, mask=vm if fusedk else None)
+        MT = Prepared(mb_feat_t, bf16=bf, mask=mtm if fusedk else None)
+        MV = Prepared(mb_feat_v, bf16=bf, mask=mvm if fusedk else None)
         Tl, Vl = T.block(lo, b), V.block(lo, b)
         M = MT.r
         nt, nv = T.n, V.n
@@ -108,14 +110,28 @@ class ShardedHeadFunction(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         S_row = torch.empty(b, B, **f32); S_col = torch.empty(b, B, **f32)
         mb_t2v = torch.empty(b, M, **f32); mb_v2t = torch.empty(b, M, **f32)
-        p1, y1 = _fwd_dir(prec, Tl, V, tw_lc, tm_lc, vm, S_row, B, 1, None, 0, 0, 0)      # H(text_l, video)
-        p2, y2 = _fwd_dir(prec, V, Tl, vw, vm, tm_lc, S_row, 1, B, None, 0, 0, 1)         # H(video, text_l)^T
-        p3, y3 = _fwd_dir(prec, Vl, T, vw_lc, vm_lc, tm, S_col, B, 1, None, 0, 0, 0)      # H(video_l, text)
-        p4, y4 = _fwd_dir(prec, T, Vl, tw, tm, vm_lc, S_col, 1, B, None, 0, 0, 1)         # H(text, video_l)^T
-        pA, yA = _fwd_dir(prec, Tl, MV, tw_lc, tm_lc, mvm, mb_t2v, M, 1, None, 0, 0, 0)
-        pB, yB = _fwd_dir(prec, MV, Tl, vw_mb, mvm, tm_lc, mb_t2v, 1, M, None, 0, 0, 1)
-        pD, yD = _fwd_dir(prec, Vl, MT, vw_lc, vm_lc, mtm, mb_v2t, M, 1, None, 0, 0, 0)
-        pC, yC = _fwd_dir(prec, MT, Vl, tw_mb, mtm, vm_lc, mb_v2t, 1, M, None, 0, 0, 1)
+        if fusedk:
+            # ONE launch, 4 problems, every token pair of a block multiplied once:
+            #   S_row = S(text_l, video) [b,B];  S_col[v_l, a] = S(text, video_l)[a, v_l];  the two bank blocks
+            sv1, sv2, svA, svC = ops.maxsim2_fwd([
+                dict(X=Tl, Y=V, wx=tw_lc, wy=vw, alpha=0.5, out=S_row, strides=(B, 1)),
+                dict(X=T, Y=Vl, wx=tw, wy=vw_lc, alpha=0.5, out=S_col, strides=(1, B)),
+                dict(X=Tl, Y=MV, wx=tw_lc, wy=vw_mb, alpha=0.5, out=mb_t2v, strides=(M, 1)),
+                dict(X=MT, Y=Vl, wx=tw_mb, wy=vw_lc, alpha=0.5, out=mb_v2t, strides=(1, M))])
+            p1, y1, p2, y2 = sv1          # (pmax_x, ystar, pmax_y, xstar) of each pair
+            p3, y3, p4, y4 = sv2
+            pA, yA, pB, yB = svA
+            pC, yC, pD, yD = svC
+        else:
+            p1, y1 = _fwd_dir(prec, Tl, V, tw_lc, tm_lc, vm, S_row, B, 1, None, 0, 0, 0)      # H(text_l, video)
+            p2, y2 = _fwd_dir(prec, V, Tl, vw, vm, tm_lc, S_row, 1, B, None, 0, 0, 1)         # H(video, text_l)^T
+            p3, y3 = _fwd_dir(prec, Vl, T, vw_lc, vm_lc, tm, S_col, B, 1, None, 0, 0, 0)      # H(video_l, text)
+            p4, y4 = _fwd_dir(prec, T, Vl, tw, tm, vm_lc, S_col, 1, B, None, 0, 0, 1)         # H(text, video_l)^T
+            pA, yA = _fwd_dir(prec, Tl, MV, tw_lc, tm_lc, mvm, mb_t2v, M, 1, None, 0, 0, 0)
+            pB, yB = _fwd_dir(prec, MV, Tl, vw_mb, mvm, tm_lc, mb_t2v, 1, M, None, 0, 0, 1)
+            pD, yD = _fwd_dir(prec, Vl, MT, vw_lc, vm_lc, mtm, mb_v2t, M, 1, None, 0, 0, 0)
+            pC, yC = _fwd_dir(prec, MT, Vl, tw_mb, mtm, vm_lc, mb_v2t, 1, M, None, 0, 0, 1)
+        ctx.fusedk = fusedk
         c_l = torch.empty(2, b, **f32)
         _call("nr_row_mean", _p(mb_t2v), M, b, M, _p(c_l[0]), st)
         _call("nr_row_mean", _p(mb_v2t), M, b, M, _p(c_l[1]), st)
@@ -205,33 +221,49 @@ class ShardedHeadFunction(torch.autograd.Function):
         vs, vld = V.bwd_source(bprec); ts, tld = T.bwd_source(bprec)
         vls, vlld = Vl.bwd_source(bprec); tls, tlld = Tl.bwd_source(bprec)
         mvs, mvld = MV.bwd_source(bprec); mts, mtld = MT.bwd_source(bprec)
-        X, Y, Wg = "nr_maxsim_bwd_x", "nr_maxsim_bwd_y", "nr_maxsim_bwd_w"
-        # H1 = H(text_l, video): dH1[a_l, bb] = .5 dS_row
-        _call(X, bprec, _p(vs), vld, _p(tw_l), _p(tm_l), _p(vm), _p(y1), _p(dS_row), B, 1, 0.5, b, nt, B, nv, d, _p(dtn_l), st)
-        _call(Y, bprec, _p(tls), tlld, _p(tw_l), _p(tm_l), _p(vm), _p(y1), _p(dS_row), B, 1, 0.5, b, nt, B, nv, d, _p(dvn), st)
-        _call(Wg, _p(p1), _p(dS_row), B, 1, 0.5, b, nt, B, _p(dtw_l), st)
-        # H2 = H(video, text_l): dH2[bb, a_l] = .5 dS_row[a_l, bb]
-        _call(X, bprec, _p(tls), tlld, _p(vw), _p(vm), _p(tm_l), _p(y2), _p(dS_row), 1, B, 0.5, B, nv, b, nt, d, _p(dvn), st)
-        _call(Y, bprec, _p(vs), vld, _p(vw), _p(vm), _p(tm_l), _p(y2), _p(dS_row), 1, B, 0.5, B, nv, b, nt, d, _p(dtn_l), st)
-        _call(Wg, _p(p2), _p(dS_row), 1, B, 0.5, B, nv, b, _p(dvw), st)
-        # H3 = H(video_l, text): dH3[v_l, a] = .5 dS_col
-        _call(X, bprec, _p(ts), tld, _p(vw_l), _p(vm_l), _p(tm), _p(y3), _p(dS_col), B, 1, 0.5, b, nv, B, nt, d, _p(dvn_l), st)
-        _call(Y, bprec, _p(vls), vlld, _p(vw_l), _p(vm_l), _p(tm), _p(y3), _p(dS_col), B, 1, 0.5, b, nv, B, nt, d, _p(dtn), st)
-        _call(Wg, _p(p3), _p(dS_col), B, 1, 0.5, b, nv, B, _p(dvw_l), st)
-        # H4 = H(text, video_l): dH4[a, v_l] = .5 dS_col[v_l, a]
-        _call(X, bprec, _p(vls), vlld, _p(tw), _p(tm), _p(vm_l), _p(y4), _p(dS_col), 1, B, 0.5, B, nt, b, nv, d, _p(dtn), st)
-        _call(Y, bprec, _p(ts), tld, _p(tw), _p(tm), _p(vm_l), _p(y4), _p(dS_col), 1, B, 0.5, B, nt, b, nv, d, _p(dvn_l), st)
-        _call(Wg, _p(p4), _p(dS_col), 1, B, 0.5, B, nt, b, _p(dtw), st)
-        # bank pairs of this rank's samples: dH = dc_l[a]/M broadcast over the bank rows (stride 0)
-        sc = 0.5 / M
-        _call(X, bprec, _p(mvs), mvld, _p(tw_l), _p(tm_l), _p(mvm), _p(yA), _p(dc_l[0]), 1, 0, sc, b, nt, M, nv, d, _p(dtn_l), st)
-        _call(Wg, _p(pA), _p(dc_l[0]), 1, 0, sc, b, nt, M, _p(dtw_l), st)
-        _call(Y, bprec, _p(mvs), mvld, _p(vw_mb), _p(mvm), _p(tm_l), _p(yB), _p(dc_l[0]), 0, 1, sc, M, nv, b, nt, d, _p(dtn_l), st)
-        _call(Wg, _p(pB), _p(dc_l[0]), 0, 1, sc, M, nv, b, _p(dvw_mb), st)
-        _call(X, bprec, _p(mts), mtld, _p(vw_l), _p(vm_l), _p(mtm), _p(yD), _p(dc_l[1]), 1, 0, sc, b, nv, M, nt, d, _p(dvn_l), st)
-        _call(Wg, _p(pD), _p(dc_l[1]), 1, 0, sc, b, nv, M, _p(dvw_l), st)
-        _call(Y, bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm_l), _p(yC), _p(dc_l[1]), 0, 1, sc, M, nt, b, nv, d, _p(dvn_l), st)
-        _call(Wg, _p(pC), _p(dc_l[1]), 0, 1, sc, M, nt, b, _p(dtw_mb), st)
+        if ctx.fusedk:
+            sc = 0.5 / M
+            # S_row = S(text_l, video): g = dS_row [b,B]
+            ops.maxsim2_bwd(0, V, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, nt, B, nv, d, dtn_l)
+            ops.maxsim2_bwd(1, Tl, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, nt, B, nv, d, dvn)
+            ops.maxsim2_bwd_w(p1, p2, dS_row, B, 1, 0.5, b, nt, B, nv, dtw_l, dvw)
+            # S_col[v_l, a] = S(text, video_l)[a, v_l]: g(rx=a, ry=v_l) = dS_col[v_l, a]
+            ops.maxsim2_bwd(0, Vl, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, nt, b, nv, d, dtn)
+            ops.maxsim2_bwd(1, T, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, nt, b, nv, d, dvn_l)
+            ops.maxsim2_bwd_w(p3, p4, dS_col, 1, B, 0.5, B, nt, b, nv, dtw, dvw_l)
+            # bank pairs of this rank's samples: g = dc_l[.]/M broadcast over the bank rows (stride 0)
+            ops.maxsim2_bwd(0, MV, tw_l, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, nt, M, nv, d, dtn_l)
+            ops.maxsim2_bwd_w(pA, pB, dc_l[0], 1, 0, sc, b, nt, M, nv, dtw_l, dvw_mb)
+            ops.maxsim2_bwd(1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, nt, b, nv, d, dvn_l)
+            ops.maxsim2_bwd_w(pC, pD, dc_l[1], 0, 1, sc, M, nt, b, nv, dtw_mb, dvw_l)
+        else:
+            X, Y, Wg = "nr_maxsim_bwd_x", "nr_maxsim_bwd_y", "nr_maxsim_bwd_w"
+            # H1 = H(text_l, video): dH1[a_l, bb] = .5 dS_row
+            _call(X, bprec, _p(vs), vld, _p(tw_l), _p(tm_l), _p(vm), _p(y1), _p(dS_row), B, 1, 0.5, b, nt, B, nv, d, _p(dtn_l), st)
+            _call(Y, bprec, _p(tls), tlld, _p(tw_l), _p(tm_l), _p(vm), _p(y1), _p(dS_row), B, 1, 0.5, b, nt, B, nv, d, _p(dvn), st)
+            _call(Wg, _p(p1), _p(dS_row), B, 1, 0.5, b, nt, B, _p(dtw_l), st)
+            # H2 = H(video, text_l): dH2[bb, a_l] = .5 dS_row[a_l, bb]
+            _call(X, bprec, _p(tls), tlld, _p(vw), _p(vm), _p(tm_l), _p(y2), _p(dS_row), 1, B, 0.5, B, nv, b, nt, d, _p(dvn), st)
+            _call(Y, bprec, _p(vs), vld, _p(vw), _p(vm), _p(tm_l), _p(y2), _p(dS_row), 1, B, 0.5, B, nv, b, nt, d, _p(dtn_l), st)
+            _call(Wg, _p(p2), _p(dS_row), 1, B, 0.5, B, nv, b, _p(dvw), st)
+            # H3 = H(video_l, text): dH3[v_l, a] = .5 dS_col
+            _call(X, bprec, _p(ts), tld, _p(vw_l), _p(vm_l), _p(tm), _p(y3), _p(dS_col), B, 1, 0.5, b, nv, B, nt, d, _p(dvn_l), st)
+            _call(Y, bprec, _p(vls), vlld, _p(vw_l), _p(vm_l), _p(tm), _p(y3), _p(dS_col), B, 1, 0.5, b, nv, B, nt, d, _p(dtn), st)
+            _call(Wg, _p(p3), _p(dS_col), B, 1, 0.5, b, nv, B, _p(dvw_l), st)
+            # H4 = H(text, video_l): dH4[a, v_l] = .5 dS_col[v_l, a]
+            _call(X, bprec, _p(vls), vlld, _p(tw), _p(tm), _p(vm_l), _p(y4), _p(dS_col), 1, B, 0.5, B, nt, b, nv, d, _p(dtn), st)
+            _call(Y, bprec, _p(ts), tld, _p(tw), _p(tm), _p(vm_l), _p(y4), _p(dS_col), 1, B, 0.5, B, nt, b, nv, d, _p(dvn_l), st)
+            _call(Wg, _p(p4), _p(dS_col), 1, B, 0.5, B, nt, b, _p(dtw), st)
+            # bank pairs of this rank's samples: dH = dc_l[a]/M broadcast over the bank rows (stride 0)
+            sc = 0.5 / M
+            _call(X, bprec, _p(mvs), mvld, _p(tw_l), _p(tm_l), _p(mvm), _p(yA), _p(dc_l[0]), 1, 0, sc, b, nt, M, nv, d, _p(dtn_l), st)
+            _call(Wg, _p(pA), _p(dc_l[0]), 1, 0, sc, b, nt, M, _p(dtw_l), st)
+            _call(Y, bprec, _p(mvs), mvld, _p(vw_mb), _p(mvm), _p(tm_l), _p(yB), _p(dc_l[0]), 0, 1, sc, M, nv, b, nt, d, _p(dtn_l), st)
+            _call(Wg, _p(pB), _p(dc_l[0]), 0, 1, sc, M, nv, b, _p(dvw_mb), st)
+            _call(X, bprec, _p(mts), mtld, _p(vw_l), _p(vm_l), _p(mtm), _p(yD), _p(dc_l[1]), 1, 0, sc, b, nv, M, nt, d, _p(dvn_l), st)
+            _call(Wg, _p(pD), _p(dc_l[1]), 1, 0, sc, b, nv, M, _p(dvw_l), st)
+            _call(Y, bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm_l), _p(yC), _p(dc_l[1]), 0, 1, sc, M, nt, b, nv, d, _p(dvn_l), st)
+            _call(Wg, _p(pC), _p(dc_l[1]), 0, 1, sc, M, nt, b, _p(dtw_mb), st)
         dtext_all = T.backward(dtn, add_vec=dmean[0])
         dvideo_all = V.backward(dvn, add_vec=dmean[1])
         # ---- exchange 5: sum the partial gradients of the gathered tensors, keep this rank's rows
