@@ -48,7 +48,10 @@ def _combine_matrix(B, wu, wn, wkl, dev):
 
 
 class HeadFunction(torch.autograd.Function):
-    """(text, video, gT, gV, tw, vw, tw_mb, vw_mb, logit_scale) -> [total, centrality, uniform, neighbor, kl]."""
+    """(text, video, gT, gV, tw, vw, tw_mb, vw_mb, logit_scale) -> [total, centrality, uniform, neighbor, kl].
+
+    Independent launch groups run on forked streams (ops.ForkJoin): inside a CUDA graph they become parallel
+    branches, which matters at b=128 where most kernels fill a fraction of the GPU."""
 
     @staticmethod
     def forward(ctx, text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, text_mask, video_mask, mb_feat_t,
@@ -56,23 +59,66 @@ class HeadFunction(torch.autograd.Function):
         cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
         _req_cuda(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, mb_feat_t, mb_feat_v)
         dev = text.device
-        st = _stream()
         tw, vw, tw_mb, vw_mb = _f32c(tw), _f32c(vw), _f32c(tw_mb), _f32c(vw_mb)
         tm, vm, mtm, mvm = _mask(text_mask), _mask(video_mask), _mask(mb_mask_t), _mask(mb_mask_v)
         bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
         # bf16: masks are folded into the operand copies (masked tokens = zero rows) for the two-direction kernel
         fusedk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
                   and ops.maxsim2_supported(text.shape[1], video.shape[1], text.shape[2]))
-        T = Prepared(text, bf16=bf, colsum=True, mask=tm if fusedk else None)
-        V = Prepared(video, bf16=bf, colsum=True, mask=vm if fusedk else None)
-        MT = Prepared(mb_feat_t, bf16=bf, mask=mtm if fusedk else None)
-        MV = Prepared(mb_feat_v, bf16=bf, mask=mvm if fusedk else None)
+        # ---- every buffer of the forward is allocated here, on the main stream, before any fork
+        T = Prepared(text, bf16=bf, colsum=True, mask=tm if fusedk else None, defer=True)
+        V = Prepared(video, bf16=bf, colsum=True, mask=vm if fusedk else None, defer=True)
+        MT = Prepared(mb_feat_t, bf16=bf, mask=mtm if fusedk else None, defer=True)
+        MV = Prepared(mb_feat_v, bf16=bf, mask=mvm if fusedk else None, defer=True)
         B, M, d = T.r, MT.r, T.d
         if V.r != B or MV.r != M:
             raise RuntimeError("text/video batch sizes (or bank sizes) differ")
         f32 = dict(dtype=torch.float32, device=dev)
         S = torch.empty(B, B, **f32); ST = torch.empty(B, B, **f32)
-        mb_t2v = torch.empty(B, M, **f32); mb_v2t = torch.empty(B, M, **f32)
+        mb = torch.empty(2, B, M, **f32)                  # [mb_t2v ; mb_v2t]
+        mb_t2v, mb_v2t = mb[0], mb[1]
+        cb = torch.empty(2, B, **f32)                     # [c_t2v ; c_v2t]
+        g2, v2 = _f32c(gt).reshape(B, d), _f32c(gv).reshape(B, d)
+        GG = torch.empty(2, B, B, **f32)
+        G, GT = GG[0], GG[1]
+        duals = torch.empty(4, B, **f32)
+        lib_ws, nws = ops.sinkhorn_workspace(B, dev)
+        mean = torch.empty(2, d, **f32); gn = torch.empty(2, B, d, **f32)
+        ginv = torch.empty(2, B, **f32); w = torch.empty(2, B, **f32)
+        ls = _f32c(logit_scale).reshape(1)
+        row_out = torch.empty(2, 4, B, **f32)
+        nbr = torch.empty(2, B, k, dtype=torch.int32, device=dev)
+        saved = torch.empty(2, B, NR_NSAVE, **f32)
+        sums = torch.empty(8, **f32)
+        m54 = _combine_matrix(B, wu, wn, wkl, dev)
+        if bf:
+            for P in (T, V, MT, MV):
+                P.alloc_transposed()
+        # ---- fork 1: token preparation (x4), centrality weights, global similarity + Sinkhorn
+        with ops.ForkJoin(3) as fj:
+            need = ctx.needs_input_grad
+            MT.run()
+            T.run()
+            if bf and need[1]:                 # sources of the video-side backward contraction, off its critical path
+                MT.bwd_source(bprec); T.bwd_source(bprec)
+            _call("nr_centrality_fwd", _p(T.partials), T.partials.shape[0], T.rows, _p(g2), B, d, cs, _p(mean[0]),
+                  _p(gn[0]), _p(ginv[0]), _p(w[0]), _stream(), launches=2)
+            with fj.on(0):
+                MV.run()
+                V.run()
+                if bf and need[0]:
+                    MV.bwd_source(bprec); V.bwd_source(bprec)
+                _call("nr_centrality_fwd", _p(V.partials), V.partials.shape[0], V.rows, _p(v2), B, d, cs, _p(mean[1]),
+                      _p(gn[1]), _p(ginv[1]), _p(w[1]), _stream(), launches=2)
+            with fj.on(1):
+                # global similarity: one token per sample -> plain dot products (library GEMM, fp32)
+                torch.mm(g2, v2.t(), out=G)
+                torch.mm(v2, g2.t(), out=GT)
+                _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]),
+                      _p(duals[3]), _p(lib_ws), nws, _stream())
+            with fj.on(2):
+                row_out.zero_()
+        st = _stream()
         if fusedk:
             # ONE launch: the batch pair and both bank pairs, each token pair multiplied once (the larger problems
             # first so that the tail of the persistent tile list is the small one)
@@ -91,37 +137,16 @@ class HeadFunction(torch.autograd.Function):
             pD, yD = _fwd_dir(prec, V, MT, vw, vm, mtm, mb_v2t, M, 1, None, 0, 0, 0)        # H(video, bank_t)
             pC, yC = _fwd_dir(prec, MT, V, tw_mb, mtm, vm, mb_v2t, 1, M, None, 0, 0, 1)     # H(bank_t, video)^T
         ctx.fusedk = fusedk
-        cb = torch.empty(2, B, **f32)                    # [c_t2v ; c_v2t]
-        _call("nr_row_mean", _p(mb_t2v), M, B, M, _p(cb[0]), st)
-        _call("nr_row_mean", _p(mb_v2t), M, B, M, _p(cb[1]), st)
-        # global similarity: one token per sample -> plain dot products (library GEMM, fp32)
-        g2, v2 = _f32c(gt).reshape(B, d), _f32c(gv).reshape(B, d)
-        G = g2 @ v2.t()
-        GT = v2 @ g2.t()
-        duals = torch.empty(4, B, **f32)
-        lib_ws, nws = ops.sinkhorn_workspace(B, dev)
-        _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]), _p(duals[3]),
-              _p(lib_ws), nws, st)
-        # centrality weights
-        mean = torch.empty(2, d, **f32); gn = torch.empty(2, B, d, **f32)
-        ginv = torch.empty(2, B, **f32); w = torch.empty(2, B, **f32)
-        _call("nr_centrality_fwd", _p(T.partials), T.partials.shape[0], T.rows, _p(g2), B, d, cs, _p(mean[0]),
-              _p(gn[0]), _p(ginv[0]), _p(w[0]), st, launches=2)
-        _call("nr_centrality_fwd", _p(V.partials), V.partials.shape[0], V.rows, _p(v2), B, d, cs, _p(mean[1]),
-              _p(gn[1]), _p(ginv[1]), _p(w[1]), st, launches=2)
-        # row losses, both directions
-        ls = _f32c(logit_scale).reshape(1)
-        row_out = torch.zeros(2, 4, B, **f32)
-        nbr = torch.empty(2, B, k, dtype=torch.int32, device=dev)
-        saved = torch.empty(2, B, NR_NSAVE, **f32)
-        _call("nr_row_losses_fwd", _p(S), B, _p(G), B, _p(cb[1]), _p(w[0]), _p(duals[0]), _p(duals[1]), B, B, 0,
-              _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[0]), _p(nbr[0]), _p(saved[0]), st)
-        _call("nr_row_losses_fwd", _p(ST), B, _p(GT), B, _p(cb[0]), _p(w[1]), _p(duals[2]), _p(duals[3]), B, B, 0,
-              _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[1]), _p(nbr[1]), _p(saved[1]), st)
-        sums = torch.empty(8, **f32)
+        _call("nr_row_mean", _p(mb), M, 2 * B, M, _p(cb), st)                # both bank centralities at once
+        # ---- fork 2: row losses, the two directions side by side
+        with ops.ForkJoin(1) as fj:
+            _call("nr_row_losses_fwd", _p(S), B, _p(G), B, _p(cb[1]), _p(w[0]), _p(duals[0]), _p(duals[1]), B, B, 0,
+                  _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[0]), _p(nbr[0]), _p(saved[0]), _stream())
+            with fj.on(0):
+                _call("nr_row_losses_fwd", _p(ST), B, _p(GT), B, _p(cb[0]), _p(w[1]), _p(duals[2]), _p(duals[3]), B, B,
+                      0, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[1]), _p(nbr[1]), _p(saved[1]), _stream())
         _call("nr_vec_sums", _p(row_out), 8, B, None, _p(sums), st)
         # [total, centrality, uniform, neighbor, kl] = M54 @ (sums_dir1 + sums_dir2);  sums order: c, n, kl, u
-        m54 = _combine_matrix(B, wu, wn, wkl, dev)
         out5 = m54 @ (sums[:4] + sums[4:])
         ctx.hp = hp
         ctx.objs = (T, V, MT, MV)
@@ -140,90 +165,120 @@ class HeadFunction(torch.autograd.Function):
         T, V, MT, MV = ctx.objs
         B, M, d = T.r, MT.r, T.d
         dev = S.device
-        st = _stream()
+        need = ctx.needs_input_grad
+        nt, nv = T.n, V.n
         f32 = dict(dtype=torch.float32, device=dev)
+        # ---- every buffer of the backward, allocated on the main stream before any fork
         gscale = m54.t() @ _f32c(g5)                                  # upstream multipliers of the raw row terms
-        z = torch.zeros(2 * B + 1 + 2 * B, **f32)                      # [dc_t2v | dc_v2t | dls | dw_t | dw_v]
-        dc, dls, dw = z[:2 * B].view(2, B), z[2 * B:2 * B + 1], z[2 * B + 1:].view(2, B)
+        # one zero-fill: [dtn | dvn | dc_t2v | dc_v2t | dw_t | dw_v | dtw | dvw | dtw_mb | dvw_mb | dls]
+        # (the token gradients first: their red.global.add.v4 needs 16-byte alignment)
+        nw = tw.numel() + vw.numel() + tw_mb.numel() + vw_mb.numel()
+        ntok = (T.rows + V.rows) * d
+        z = torch.zeros(ntok + 4 * B + nw + 1, **f32)
+        dtn, dvn = z[:T.rows * d], z[T.rows * d:ntok]
+        dc, dw = z[ntok:ntok + 2 * B].view(2, B), z[ntok + 2 * B:ntok + 4 * B].view(2, B)
+        o = ntok + 4 * B
+        dtw = z[o:o + tw.numel()]; o += tw.numel()
+        dvw = z[o:o + vw.numel()]; o += vw.numel()
+        dtw_mb = z[o:o + tw_mb.numel()]; o += tw_mb.numel()
+        dvw_mb = z[o:o + vw_mb.numel()]; o += vw_mb.numel()
+        dls = z[o:o + 1]
         dS1 = torch.empty(B, B, **f32); dS2 = torch.empty(B, B, **f32)
         dG1 = torch.empty(B, B, **f32); dG2 = torch.empty(B, B, **f32)
-        _call("nr_row_losses_bwd", _p(S), B, _p(G), B, _p(cb[1]), _p(w[0]), _p(duals[0]), _p(duals[1]), B, B, 0, _p(ls),
-              k, tau, tau, beta, ALL_LOSSES, _p(nbr[0]), _p(saved[0]), _p(gscale), _p(dS1), B, _p(dG1), B, _p(dc[1]),
-              _p(dw[0]), _p(dls), st)
-        _call("nr_row_losses_bwd", _p(ST), B, _p(GT), B, _p(cb[0]), _p(w[1]), _p(duals[2]), _p(duals[3]), B, B, 0,
-              _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(nbr[1]), _p(saved[1]), _p(gscale), _p(dS2), B, _p(dG2), B,
-              _p(dc[0]), _p(dw[1]), _p(dls), st)
         dS = torch.empty(B, B, **f32); dG = torch.empty(B, B, **f32)
-        _call("nr_transpose_add", _p(dS1), B, _p(dS2), B, _p(dS), B, B, B, 1.0, 1.0, st)
-        _call("nr_transpose_add", _p(dG1), B, _p(dG2), B, _p(dG), B, B, B, 1.0, 1.0, st)
-        need = ctx.needs_input_grad
-        dgt = (dG @ v2) if need[2] else None
-        dgv = (dG.t() @ g2) if need[3] else None
+        dgt = torch.empty(B, d, **f32) if need[2] else None
+        dgv = torch.empty(B, d, **f32) if need[3] else None
         dmean = torch.empty(2, d, **f32)
-        _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs, T.rows, _p(dgt),
-              1, _p(dmean[0]), st, launches=2)
-        _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows, _p(dgv),
-              1, _p(dmean[1]), st, launches=2)
-        # ---- token-pair products ----
-        zt = torch.zeros(T.rows * d + V.rows * d, **f32)
-        dtn, dvn = zt[:T.rows * d], zt[T.rows * d:]
-        wz = torch.zeros(tw.numel() + vw.numel() + tw_mb.numel() + vw_mb.numel(), **f32)
-        o1, o2, o3 = tw.numel(), tw.numel() + vw.numel(), tw.numel() + vw.numel() + tw_mb.numel()
-        dtw, dvw, dtw_mb, dvw_mb = wz[:o1], wz[o1:o2], wz[o2:o3], wz[o3:]
-        vs, vld = V.bwd_source(bprec); ts, tld = T.bwd_source(bprec)
-        mvs, mvld = MV.bwd_source(bprec); mts, mtld = MT.bwd_source(bprec)
-        nt, nv = T.n, V.n
-        if ctx.fusedk:
-            # one routing matrix per pair, applied from either side: 4 contraction + 3 weight launches
-            sc = 0.5 / M
+        dtext = torch.empty_like(T.xn) if need[0] else None
+        dvideo = torch.empty_like(V.xn) if need[1] else None
+        # ---- fork 1: row-loss backward, both directions
+        with ops.ForkJoin(1) as fj:
+            _call("nr_row_losses_bwd", _p(S), B, _p(G), B, _p(cb[1]), _p(w[0]), _p(duals[0]), _p(duals[1]), B, B, 0,
+                  _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(nbr[0]), _p(saved[0]), _p(gscale), _p(dS1), B, _p(dG1), B,
+                  _p(dc[1]), _p(dw[0]), _p(dls), _stream())
+            with fj.on(0):
+                _call("nr_row_losses_bwd", _p(ST), B, _p(GT), B, _p(cb[0]), _p(w[1]), _p(duals[2]), _p(duals[3]), B, B,
+                      0, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(nbr[1]), _p(saved[1]), _p(gscale), _p(dS2), B,
+                      _p(dG2), B, _p(dc[0]), _p(dw[1]), _p(dls), _stream())
+        # ---- fork 2: token-pair contractions (main: text side, side 0: video side), global path (side 1),
+        #      token-weight gradients (side 2)
+        with ops.ForkJoin(3) as fj:
+            _call("nr_transpose_add", _p(dS1), B, _p(dS2), B, _p(dS), B, B, B, 1.0, 1.0, _stream())
+            ev_dS = torch.cuda.Event()
+            ev_dS.record()
+            with fj.on(1):
+                _call("nr_transpose_add", _p(dG1), B, _p(dG2), B, _p(dG), B, B, B, 1.0, 1.0, _stream())
+                if need[2]:
+                    torch.mm(dG, v2, out=dgt)
+                if need[3]:
+                    torch.mm(dG.t(), g2, out=dgv)
+                _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs, T.rows,
+                      _p(dgt), 1, _p(dmean[0]), _stream(), launches=2)
+                _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows,
+                      _p(dgv), 1, _p(dmean[1]), _stream(), launches=2)
+            if ctx.fusedk:
+                # one routing matrix per pair, applied from either side: 4 contraction + 3 weight launches
+                sc = 0.5 / M
+                if need[0]:
+                    ops.maxsim2_bwd(0, V, tw, vw, y1, y2, dS, B, 1, 0.5, B, nt, B, nv, d, dtn)
+                    ops.maxsim2_bwd(0, MV, tw, vw_mb, yA, yB, dc[0], 1, 0, sc, B, nt, M, nv, d, dtn)
+                with fj.on(0):
+                    torch.cuda.current_stream().wait_event(ev_dS)
+                    if need[1]:
+                        ops.maxsim2_bwd(1, T, tw, vw, y1, y2, dS, B, 1, 0.5, B, nt, B, nv, d, dvn)
+                        ops.maxsim2_bwd(1, MT, tw_mb, vw, yC, yD, dc[1], 0, 1, sc, M, nt, B, nv, d, dvn)
+                with fj.on(2):
+                    torch.cuda.current_stream().wait_event(ev_dS)
+                    if need[4] or need[5]:
+                        ops.maxsim2_bwd_w(p1, p2, dS, B, 1, 0.5, B, nt, B, nv, dtw if need[4] else None,
+                                          dvw if need[5] else None)
+                    if need[4] or need[7]:
+                        ops.maxsim2_bwd_w(pA, pB, dc[0], 1, 0, sc, B, nt, M, nv, dtw if need[4] else None,
+                                          dvw_mb if need[7] else None)
+                    if need[6] or need[5]:
+                        ops.maxsim2_bwd_w(pC, pD, dc[1], 0, 1, sc, M, nt, B, nv, dtw_mb if need[6] else None,
+                                          dvw if need[5] else None)
+            else:
+                st = _stream()
+                vs, vld = V.bwd_source(bprec); ts, tld = T.bwd_source(bprec)
+                mvs, mvld = MV.bwd_source(bprec); mts, mtld = MT.bwd_source(bprec)
+                if need[0]:
+                    # text <- batch pair (both orientations) and the text-vs-bank-video pair
+                    _call("nr_maxsim_bwd_x", bprec, _p(vs), vld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt,
+                          B, nv, d, _p(dtn), st)
+                    _call("nr_maxsim_bwd_y", bprec, _p(vs), vld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv,
+                          B, nt, d, _p(dtn), st)
+                    _call("nr_maxsim_bwd_x", bprec, _p(mvs), mvld, _p(tw), _p(tm), _p(mvm), _p(yA), _p(dc[0]), 1, 0,
+                          0.5 / M, B, nt, M, nv, d, _p(dtn), st)
+                    _call("nr_maxsim_bwd_y", bprec, _p(mvs), mvld, _p(vw_mb), _p(mvm), _p(tm), _p(yB), _p(dc[0]), 0, 1,
+                          0.5 / M, M, nv, B, nt, d, _p(dtn), st)
+                if need[1]:
+                    _call("nr_maxsim_bwd_y", bprec, _p(ts), tld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt,
+                          B, nv, d, _p(dvn), st)
+                    _call("nr_maxsim_bwd_x", bprec, _p(ts), tld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv,
+                          B, nt, d, _p(dvn), st)
+                    _call("nr_maxsim_bwd_x", bprec, _p(mts), mtld, _p(vw), _p(vm), _p(mtm), _p(yD), _p(dc[1]), 1, 0,
+                          0.5 / M, B, nv, M, nt, d, _p(dvn), st)
+                    _call("nr_maxsim_bwd_y", bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm), _p(yC), _p(dc[1]), 0, 1,
+                          0.5 / M, M, nt, B, nv, d, _p(dvn), st)
+                # token-weight gradients (batch pair + bank pairs)
+                if need[4]:
+                    _call("nr_maxsim_bwd_w", _p(p1), _p(dS), B, 1, 0.5, B, nt, B, _p(dtw), st)
+                    _call("nr_maxsim_bwd_w", _p(pA), _p(dc[0]), 1, 0, 0.5 / M, B, nt, M, _p(dtw), st)
+                if need[5]:
+                    _call("nr_maxsim_bwd_w", _p(p2), _p(dS), 1, B, 0.5, B, nv, B, _p(dvw), st)
+                    _call("nr_maxsim_bwd_w", _p(pD), _p(dc[1]), 1, 0, 0.5 / M, B, nv, M, _p(dvw), st)
+                if need[6]:
+                    _call("nr_maxsim_bwd_w", _p(pC), _p(dc[1]), 0, 1, 0.5 / M, M, nt, B, _p(dtw_mb), st)
+                if need[7]:
+                    _call("nr_maxsim_bwd_w", _p(pB), _p(dc[0]), 0, 1, 0.5 / M, M, nv, B, _p(dvw_mb), st)
+        # ---- fork 3: normalisation backward of the two modalities
+        with ops.ForkJoin(1) as fj:
             if need[0]:
-                ops.maxsim2_bwd(0, V, tw, vw, y1, y2, dS, B, 1, 0.5, B, nt, B, nv, d, dtn)
-                ops.maxsim2_bwd(0, MV, tw, vw_mb, yA, yB, dc[0], 1, 0, sc, B, nt, M, nv, d, dtn)
-            if need[1]:
-                ops.maxsim2_bwd(1, T, tw, vw, y1, y2, dS, B, 1, 0.5, B, nt, B, nv, d, dvn)
-                ops.maxsim2_bwd(1, MT, tw_mb, vw, yC, yD, dc[1], 0, 1, sc, M, nt, B, nv, d, dvn)
-            if need[4] or need[5]:
-                ops.maxsim2_bwd_w(p1, p2, dS, B, 1, 0.5, B, nt, B, nv, dtw if need[4] else None,
-                                  dvw if need[5] else None)
-            if need[4] or need[7]:
-                ops.maxsim2_bwd_w(pA, pB, dc[0], 1, 0, sc, B, nt, M, nv, dtw if need[4] else None,
-                                  dvw_mb if need[7] else None)
-            if need[6] or need[5]:
-                ops.maxsim2_bwd_w(pC, pD, dc[1], 0, 1, sc, M, nt, B, nv, dtw_mb if need[6] else None,
-                                  dvw if need[5] else None)
-        else:
-            if need[0]:
-                # text <- batch pair (both orientations) and the text-vs-bank-video pair
-                _call("nr_maxsim_bwd_x", bprec, _p(vs), vld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt, B, nv,
-                      d, _p(dtn), st)
-                _call("nr_maxsim_bwd_y", bprec, _p(vs), vld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv, B, nt,
-                      d, _p(dtn), st)
-                _call("nr_maxsim_bwd_x", bprec, _p(mvs), mvld, _p(tw), _p(tm), _p(mvm), _p(yA), _p(dc[0]), 1, 0, 0.5 / M, B,
-                      nt, M, nv, d, _p(dtn), st)
-                _call("nr_maxsim_bwd_y", bprec, _p(mvs), mvld, _p(vw_mb), _p(mvm), _p(tm), _p(yB), _p(dc[0]), 0, 1, 0.5 / M,
-                      M, nv, B, nt, d, _p(dtn), st)
-            if need[1]:
-                _call("nr_maxsim_bwd_y", bprec, _p(ts), tld, _p(tw), _p(tm), _p(vm), _p(y1), _p(dS), B, 1, 0.5, B, nt, B, nv,
-                      d, _p(dvn), st)
-                _call("nr_maxsim_bwd_x", bprec, _p(ts), tld, _p(vw), _p(vm), _p(tm), _p(y2), _p(dS), 1, B, 0.5, B, nv, B, nt,
-                      d, _p(dvn), st)
-                _call("nr_maxsim_bwd_x", bprec, _p(mts), mtld, _p(vw), _p(vm), _p(mtm), _p(yD), _p(dc[1]), 1, 0, 0.5 / M, B,
-                      nv, M, nt, d, _p(dvn), st)
-                _call("nr_maxsim_bwd_y", bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm), _p(yC), _p(dc[1]), 0, 1, 0.5 / M,
-                      M, nt, B, nv, d, _p(dvn), st)
-            # token-weight gradients (batch pair + bank pairs)
-            if need[4]:
-                _call("nr_maxsim_bwd_w", _p(p1), _p(dS), B, 1, 0.5, B, nt, B, _p(dtw), st)
-                _call("nr_maxsim_bwd_w", _p(pA), _p(dc[0]), 1, 0, 0.5 / M, B, nt, M, _p(dtw), st)
-            if need[5]:
-                _call("nr_maxsim_bwd_w", _p(p2), _p(dS), 1, B, 0.5, B, nv, B, _p(dvw), st)
-                _call("nr_maxsim_bwd_w", _p(pD), _p(dc[1]), 1, 0, 0.5 / M, B, nv, M, _p(dvw), st)
-            if need[6]:
-                _call("nr_maxsim_bwd_w", _p(pC), _p(dc[1]), 0, 1, 0.5 / M, M, nt, B, _p(dtw_mb), st)
-            if need[7]:
-                _call("nr_maxsim_bwd_w", _p(pB), _p(dc[0]), 0, 1, 0.5 / M, M, nv, B, _p(dvw_mb), st)
-        dtext = T.backward(dtn, add_vec=dmean[0]) if need[0] else None
-        dvideo = V.backward(dvn, add_vec=dmean[1]) if need[1] else None
+                T.backward(dtn, add_vec=dmean[0], out=dtext)
+            with fj.on(0):
+                if need[1]:
+                    V.backward(dvn, add_vec=dmean[1], out=dvideo)
         ctx.objs = None
         gs_t, gs_v = ctx.gshape
         return (dtext, dvideo, dgt.reshape(gs_t) if need[2] else None, dgv.reshape(gs_v) if need[3] else None,

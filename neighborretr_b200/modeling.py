@@ -156,10 +156,20 @@ class HeadMixin:
                                  f"k={num_neighbors})")
             from .fused import fused_head
             lowp = self._head_precision() == "bf16"
-            tw = _token_weights(self.text_weight_fc, text_feat, text_mask, lowp)
-            vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp)
-            tw_mb = _token_weights(self.text_weight_fc, mb_feat_t, mb_mask_t, lowp)
-            vw_mb = _token_weights(self.video_weight_fc, mb_feat_v, mb_mask_v, lowp)
+            # the four weight-MLP evaluations are independent: forked streams (parallel graph branches); autograd
+            # runs each backward on its forward stream, so the MLP backward GEMMs overlap as well
+            with ops.ForkJoin(3) as fj:
+                main = fj.main
+                tw_mb = _token_weights(self.text_weight_fc, mb_feat_t, mb_mask_t, lowp)
+                with fj.on(0):
+                    vw_mb = _token_weights(self.video_weight_fc, mb_feat_v, mb_mask_v, lowp)
+                    vw_mb.record_stream(main)
+                with fj.on(1):
+                    tw = _token_weights(self.text_weight_fc, text_feat, text_mask, lowp)
+                    tw.record_stream(main)
+                with fj.on(2):
+                    vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp)
+                    vw.record_stream(main)
             ls = logit_scale if torch.is_tensor(logit_scale) else torch.tensor(float(logit_scale),
                                                                                device=text_feat.device)
             out5, nbr = fused_head(text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, ls, text_mask, video_mask,

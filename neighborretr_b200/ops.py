@@ -46,6 +46,44 @@ def _mask(t):
     return t.contiguous()
 
 
+_SIDE_STREAMS = {}
+
+
+class ForkJoin:
+    """Independent launch groups on side streams, joined back into the current stream on exit:
+
+        with ForkJoin(2) as fj:
+            ...                       # current stream
+            with fj.on(0): ...        # side stream 0 (ordered after everything enqueued before the fork)
+            with fj.on(1): ...
+
+    Under CUDA-graph capture the side streams become parallel branches of the graph.  Callers allocate every buffer
+    a branch touches BEFORE the fork, on the main stream (the caching allocator tracks one stream per block)."""
+
+    def __init__(self, n):
+        self.main = torch.cuda.current_stream()
+        key = (self.main.device.index, n)
+        lst = _SIDE_STREAMS.get(self.main.device.index, [])
+        while len(lst) < n:
+            lst.append(torch.cuda.Stream(device=self.main.device))
+        _SIDE_STREAMS[self.main.device.index] = lst
+        self.side = lst[:n]
+        del key
+
+    def __enter__(self):
+        for s in self.side:
+            s.wait_stream(self.main)
+        return self
+
+    def on(self, i):
+        return torch.cuda.stream(self.side[i])
+
+    def __exit__(self, *exc):
+        for s in self.side:
+            self.main.wait_stream(s)
+        return False
+
+
 class _KernelTimer:
     """CUDA-event timing of one C-ABI entry point on the launching stream (bench.py roofline)."""
 
@@ -97,9 +135,10 @@ class Prepared:
     """L2-normalised tokens of one modality: fp32 copy (backward / fp32 mode), optional bf16 operand
     copy (tensor-core mode), inverse norms and per-CTA column-sum partials."""
 
-    __slots__ = ("xn", "xn_bf16", "xnT_bf16", "inv_norm", "partials", "rows", "n", "d", "r", "_parent", "_lo", "mask")
+    __slots__ = ("xn", "xn_bf16", "xnT_bf16", "inv_norm", "partials", "rows", "n", "d", "r", "_parent", "_lo", "mask",
+                 "_x", "_t_ready")
 
-    def __init__(self, x, bf16=False, colsum=False, normalize=True, mask=None):
+    def __init__(self, x, bf16=False, colsum=False, normalize=True, mask=None, defer=False):
         """mask [r, n] int64 (optional): masked tokens become zero rows of the bf16 operand copy (and of its
         transposed copy) and take no max-sim gradient in backward(); required by the fused two-direction kernel."""
         _req_cuda(x)
@@ -108,6 +147,7 @@ class Prepared:
         self.rows = self.r * self.n
         self.xnT_bf16 = None
         self._parent, self._lo = None, 0
+        self._x, self._t_ready = None, True
         self.mask = _mask(mask)
         dev = x.device
         if not normalize:        # global_level: raw dot products (reference modeling.py:525), fp32 only
@@ -118,8 +158,23 @@ class Prepared:
         self.inv_norm = torch.empty(self.rows, dtype=torch.float32, device=dev)
         npart = _lib.load().nr_prep_partials(self.rows)
         self.partials = torch.empty(npart, self.d, dtype=torch.float32, device=dev) if colsum else None
-        _call("nr_prep_tokens", _p(x), self.rows, self.d, _p(self.xn), _p(self.xn_bf16), _p(self.inv_norm),
+        self._x = x
+        if not defer:
+            self.run()
+
+    def run(self):
+        """Enqueue the preparation kernel on the current stream (buffers were allocated by the constructor)."""
+        _call("nr_prep_tokens", _p(self._x), self.rows, self.d, _p(self.xn), _p(self.xn_bf16), _p(self.inv_norm),
               _p(self.partials), _p(self.mask), _stream())
+        self._x = None
+        return self
+
+    def alloc_transposed(self):
+        """Allocate (not fill) the transposed bf16 copy on the current stream; bwd_source() fills it on first use."""
+        if self.xnT_bf16 is None and self.xn_bf16 is not None and self._parent is None:
+            ld = (self.rows + 7) // 8 * 8
+            self.xnT_bf16 = torch.empty(self.d, ld, dtype=torch.bfloat16, device=self.xn.device)
+            self._t_ready = False
 
     def operand(self, prec):
         return self.xn_bf16 if prec == NR_PREC_BF16 else self.xn
@@ -136,9 +191,11 @@ class Prepared:
                 raise RuntimeError("row block offset must keep the transposed operand 16-byte aligned")
             return pt[:, self._lo * self.n:], ld
         if self.xnT_bf16 is None:
-            ld = (self.rows + 7) // 8 * 8
-            self.xnT_bf16 = torch.empty(self.d, ld, dtype=torch.bfloat16, device=self.xn.device)
-            _call("nr_transpose_tokens_bf16", _p(self.xn_bf16), self.rows, self.d, _p(self.xnT_bf16), ld, _stream())
+            self.alloc_transposed()
+        if not self._t_ready:
+            _call("nr_transpose_tokens_bf16", _p(self.xn_bf16), self.rows, self.d, _p(self.xnT_bf16),
+                  self.xnT_bf16.shape[1], _stream())
+            self._t_ready = True
         return self.xnT_bf16, self.xnT_bf16.shape[1]
 
     def block(self, lo, n):
@@ -151,14 +208,15 @@ class Prepared:
         v.inv_norm = self.inv_norm[lo * self.n:(lo + n) * self.n] if self.inv_norm is not None else None
         v.partials = None
         v.xnT_bf16 = None
+        v._x, v._t_ready = None, True
         v._parent, v._lo = self, lo
         v.mask = self.mask[lo:lo + n] if self.mask is not None else None
         return v
 
-    def backward(self, dxn, add_vec=None):
+    def backward(self, dxn, add_vec=None, out=None):
         if self.inv_norm is None:
             return dxn
-        dx = torch.empty_like(self.xn)
+        dx = torch.empty_like(self.xn) if out is None else out
         _call("nr_prep_tokens_bwd", _p(self.xn), _p(self.inv_norm), _p(dxn), _p(add_vec), _p(self.mask), self.rows,
               self.d, _p(dx), 0, _stream())
         return dx
