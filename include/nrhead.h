@@ -153,6 +153,11 @@ int nr_centrality_bwd(const float* mean_vec, const float* gn, const float* ginv,
                       int64_t B, int64_t d, float cs, int64_t rows_total, float* dg, int accumulate,
                       float* dmean, void* stream);
 
+/* ---- global similarity with one global token per sample (modeling.py:516-539 at Gt = Gv = 1):
+ * out [Ra,Rb] = a [Ra,d] b[Rb,d]^T in exact fp32, outT [Rb,Ra] (nullable) its transpose from the same launch. */
+int nr_gram_f32(const float* a, const float* b, int64_t Ra, int64_t Rb, int64_t d, float* out, float* outT,
+                void* stream);
+
 /* ---- row-block losses (until_module.py:56-211, :263-291, :303-328, :339-359) ----------------
  * X [rows,B] rows row0..row0+rows of the local similarity (t2v) or of its transpose (v2t);
  * G likewise for the global similarity; cbank [B] bank centrality by column (until_module.py:181);

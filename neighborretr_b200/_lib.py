@@ -39,6 +39,7 @@ SIGNATURES = {
     "nr_maxsim_bwd_w": (_I, [_P, _P, _I64, _I64, _F, _I64, _I64, _I64, _P, _P]),
     "nr_centrality_fwd": (_I, [_P, _I64, _I64, _P, _I64, _I64, _F, _P, _P, _P, _P, _P]),
     "nr_centrality_bwd": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _P, _I, _P, _P]),
+    "nr_gram_f32": (_I, [_P, _P, _I64, _I64, _I64, _P, _P, _P]),
     "nr_row_losses_fwd": (_I, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P, _I, _F, _F, _F, _I, _P,
                                _P, _P, _P]),
     "nr_row_losses_bwd": (_I, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I64, _P, _I, _F, _F, _F, _I, _P,

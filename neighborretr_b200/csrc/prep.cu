@@ -264,6 +264,56 @@ extern "C" int nr_centrality_bwd(const float* mean_vec, const float* gn, const f
   return 0;
 }
 
+// ---- global similarity for one global token per sample: G = gT gV^T and its transpose (modeling.py:516-539 with
+// Gt = Gv = 1, where the softmax over a single token is 1).  Exact fp32 FMA; 32x32 output tile per CTA, 2x2
+// outputs per thread, k-chunks of 32 staged in shared memory.  At B=128 the library picks a 32x32x16 SIMT
+// kernel that takes 67 us for these 17 MFLOP; this one is latency-sized (16 CTAs x 16 k-steps).
+namespace nr {
+__global__ void __launch_bounds__(256)
+gram_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, int Ra, int Rb, int d,
+                float* __restrict__ out, float* __restrict__ outT) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < d; k0 += 32) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = it * 256 + threadIdx.x, r = e >> 5, c = e & 31;
+      As[r][c] = (i0 + r < Ra && k0 + c < d) ? a[(int64_t)(i0 + r) * d + k0 + c] : 0.f;
+      Bs[r][c] = (j0 + r < Rb && k0 + c < d) ? b[(int64_t)(j0 + r) * d + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[ty * 2][k], a1 = As[ty * 2 + 1][k], b0 = Bs[tx * 2][k], b1 = Bs[tx * 2 + 1][k];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = i0 + ty * 2 + p, j = j0 + tx * 2 + q;
+      if (i < Ra && j < Rb) {
+        out[(int64_t)i * Rb + j] = acc[p][q];
+        if (outT) outT[(int64_t)j * Ra + i] = acc[p][q];
+      }
+    }
+}
+}  // namespace nr
+
+extern "C" int nr_gram_f32(const float* a, const float* b, int64_t Ra, int64_t Rb, int64_t d, float* out, float* outT,
+                           void* stream) {
+  NR_CHECK_ARG(a && b && out && Ra > 0 && Rb > 0 && d > 0, "nr_gram_f32: bad arguments");
+  dim3 grid((unsigned)((Rb + 31) / 32), (unsigned)((Ra + 31) / 32));
+  nr::gram_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, (int)Ra, (int)Rb, (int)d, out, outT);
+  NR_CHECK_LAUNCH("nr_gram_f32");
+  return 0;
+}
+
 // ---- token-weight MLP backward, hidden layer (reference modeling.py:148-153: Linear-ReLU-Linear(2D,1)) --------
 // One streaming pass over the post-ReLU hidden activations h [T,H]:
 //   dh[t,j] = dlogit[t] * w2[j] * (h[t,j] > 0)      (input of the dW1 / dx library GEMMs)

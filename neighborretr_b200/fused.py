@@ -47,6 +47,82 @@ def _combine_matrix(B, wu, wn, wkl, dev):
     return m
 
 
+class HeadPrologue:
+    """Everything of a head step that does not depend on the token-weight MLPs: token preparation (x4, with the
+    transposed operand copies of the backward), centrality weights, global similarity and the Sinkhorn duals.
+    The constructor only ALLOCATES (on the current = main stream); the three run_* groups are independent and may
+    be enqueued on forked streams next to the MLP evaluations (modeling._compute_losses)."""
+
+    def __init__(self, text, video, gt, gv, text_mask, video_mask, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp,
+                 need_text_grad=True, need_video_grad=True):
+        cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
+        _req_cuda(text, video, gt, gv, mb_feat_t, mb_feat_v)
+        dev = text.device
+        self.hp = hp
+        self.tm, self.vm = _mask(text_mask), _mask(video_mask)
+        self.mtm, self.mvm = _mask(mb_mask_t), _mask(mb_mask_v)
+        self.bf = bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
+        # bf16: masks are folded into the operand copies (masked tokens = zero rows) for the two-direction kernel
+        self.fusedk = fk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
+                            and ops.maxsim2_supported(text.shape[1], video.shape[1], text.shape[2]))
+        self.T = Prepared(text.detach(), bf16=bf, colsum=True, mask=self.tm if fk else None, defer=True)
+        self.V = Prepared(video.detach(), bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True)
+        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True)
+        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True)
+        B, M, d = self.T.r, self.MT.r, self.T.d
+        if self.V.r != B or self.MV.r != M:
+            raise RuntimeError("text/video batch sizes (or bank sizes) differ")
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.g2, self.v2 = _f32c(gt.detach()).reshape(B, d), _f32c(gv.detach()).reshape(B, d)
+        self.GG = torch.empty(2, B, B, **f32)              # [G ; G^T]
+        self.duals = torch.empty(4, B, **f32)
+        self.lib_ws, self.nws = ops.sinkhorn_workspace(B, dev)
+        self.mean = torch.empty(2, d, **f32); self.gn = torch.empty(2, B, d, **f32)
+        self.ginv = torch.empty(2, B, **f32); self.w = torch.empty(2, B, **f32)
+        self.need_t, self.need_v = need_text_grad, need_video_grad
+        if bf:
+            for P in (self.T, self.V, self.MT, self.MV):
+                P.alloc_transposed()
+
+    def _centrality(self, P, g, i):
+        B, d, cs = self.T.r, self.T.d, self.hp[0]
+        _call("nr_centrality_fwd", _p(P.partials), P.partials.shape[0], P.rows, _p(g), B, d, cs, _p(self.mean[i]),
+              _p(self.gn[i]), _p(self.ginv[i]), _p(self.w[i]), _stream(), launches=2)
+
+    def run_text_side(self):
+        bprec = self.hp[9]
+        self.MT.run()
+        self.T.run()
+        if self.bf and self.need_v:        # sources of the video-side backward contraction, off its critical path
+            self.MT.bwd_source(bprec); self.T.bwd_source(bprec)
+        self._centrality(self.T, self.g2, 0)
+
+    def run_video_side(self):
+        bprec = self.hp[9]
+        self.MV.run()
+        self.V.run()
+        if self.bf and self.need_t:
+            self.MV.bwd_source(bprec); self.V.bwd_source(bprec)
+        self._centrality(self.V, self.v2, 1)
+
+    def run_global(self):
+        # global similarity: one token per sample -> plain dot products (library GEMM, fp32), then the Sinkhorn duals
+        B, iters = self.T.r, int(self.hp[4])
+        _call("nr_gram_f32", _p(self.g2), _p(self.v2), B, B, self.T.d, _p(self.GG[0]), _p(self.GG[1]), _stream())
+        d_ = self.duals
+        _call("nr_sinkhorn", _p(self.GG[0]), _p(self.GG[1]), B, iters, _p(d_[0]), _p(d_[1]), _p(d_[2]), _p(d_[3]),
+              _p(self.lib_ws), self.nws, _stream())
+
+    def run_forked(self):
+        with ops.ForkJoin(2) as fj:
+            self.run_text_side()
+            with fj.on(0):
+                self.run_video_side()
+            with fj.on(1):
+                self.run_global()
+        return self
+
+
 class HeadFunction(torch.autograd.Function):
     """(text, video, gT, gV, tw, vw, tw_mb, vw_mb, logit_scale) -> [total, centrality, uniform, neighbor, kl].
 
@@ -55,69 +131,32 @@ class HeadFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, text_mask, video_mask, mb_feat_t,
-                mb_feat_v, mb_mask_t, mb_mask_v, hp):
+                mb_feat_v, mb_mask_t, mb_mask_v, hp, pro=None):
         cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
         _req_cuda(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, mb_feat_t, mb_feat_v)
         dev = text.device
         tw, vw, tw_mb, vw_mb = _f32c(tw), _f32c(vw), _f32c(tw_mb), _f32c(vw_mb)
-        tm, vm, mtm, mvm = _mask(text_mask), _mask(video_mask), _mask(mb_mask_t), _mask(mb_mask_v)
-        bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
-        # bf16: masks are folded into the operand copies (masked tokens = zero rows) for the two-direction kernel
-        fusedk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
-                  and ops.maxsim2_supported(text.shape[1], video.shape[1], text.shape[2]))
-        # ---- every buffer of the forward is allocated here, on the main stream, before any fork
-        T = Prepared(text, bf16=bf, colsum=True, mask=tm if fusedk else None, defer=True)
-        V = Prepared(video, bf16=bf, colsum=True, mask=vm if fusedk else None, defer=True)
-        MT = Prepared(mb_feat_t, bf16=bf, mask=mtm if fusedk else None, defer=True)
-        MV = Prepared(mb_feat_v, bf16=bf, mask=mvm if fusedk else None, defer=True)
+        if pro is None:                 # stand-alone use: the prologue runs here (already-joined when passed in)
+            need = ctx.needs_input_grad
+            pro = HeadPrologue(text, video, gt, gv, text_mask, video_mask, mb_feat_t, mb_feat_v, mb_mask_t,
+                               mb_mask_v, hp, need[0], need[1]).run_forked()
+        T, V, MT, MV = pro.T, pro.V, pro.MT, pro.MV
+        tm, vm, mtm, mvm = pro.tm, pro.vm, pro.mtm, pro.mvm
+        fusedk = pro.fusedk
         B, M, d = T.r, MT.r, T.d
-        if V.r != B or MV.r != M:
-            raise RuntimeError("text/video batch sizes (or bank sizes) differ")
+        g2, v2, G, GT, duals = pro.g2, pro.v2, pro.GG[0], pro.GG[1], pro.duals
+        mean, gn, ginv, w = pro.mean, pro.gn, pro.ginv, pro.w
         f32 = dict(dtype=torch.float32, device=dev)
         S = torch.empty(B, B, **f32); ST = torch.empty(B, B, **f32)
         mb = torch.empty(2, B, M, **f32)                  # [mb_t2v ; mb_v2t]
         mb_t2v, mb_v2t = mb[0], mb[1]
         cb = torch.empty(2, B, **f32)                     # [c_t2v ; c_v2t]
-        g2, v2 = _f32c(gt).reshape(B, d), _f32c(gv).reshape(B, d)
-        GG = torch.empty(2, B, B, **f32)
-        G, GT = GG[0], GG[1]
-        duals = torch.empty(4, B, **f32)
-        lib_ws, nws = ops.sinkhorn_workspace(B, dev)
-        mean = torch.empty(2, d, **f32); gn = torch.empty(2, B, d, **f32)
-        ginv = torch.empty(2, B, **f32); w = torch.empty(2, B, **f32)
         ls = _f32c(logit_scale).reshape(1)
-        row_out = torch.empty(2, 4, B, **f32)
+        row_out = torch.zeros(2, 4, B, **f32)
         nbr = torch.empty(2, B, k, dtype=torch.int32, device=dev)
         saved = torch.empty(2, B, NR_NSAVE, **f32)
         sums = torch.empty(8, **f32)
         m54 = _combine_matrix(B, wu, wn, wkl, dev)
-        if bf:
-            for P in (T, V, MT, MV):
-                P.alloc_transposed()
-        # ---- fork 1: token preparation (x4), centrality weights, global similarity + Sinkhorn
-        with ops.ForkJoin(3) as fj:
-            need = ctx.needs_input_grad
-            MT.run()
-            T.run()
-            if bf and need[1]:                 # sources of the video-side backward contraction, off its critical path
-                MT.bwd_source(bprec); T.bwd_source(bprec)
-            _call("nr_centrality_fwd", _p(T.partials), T.partials.shape[0], T.rows, _p(g2), B, d, cs, _p(mean[0]),
-                  _p(gn[0]), _p(ginv[0]), _p(w[0]), _stream(), launches=2)
-            with fj.on(0):
-                MV.run()
-                V.run()
-                if bf and need[0]:
-                    MV.bwd_source(bprec); V.bwd_source(bprec)
-                _call("nr_centrality_fwd", _p(V.partials), V.partials.shape[0], V.rows, _p(v2), B, d, cs, _p(mean[1]),
-                      _p(gn[1]), _p(ginv[1]), _p(w[1]), _stream(), launches=2)
-            with fj.on(1):
-                # global similarity: one token per sample -> plain dot products (library GEMM, fp32)
-                torch.mm(g2, v2.t(), out=G)
-                torch.mm(v2, g2.t(), out=GT)
-                _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]),
-                      _p(duals[3]), _p(lib_ws), nws, _stream())
-            with fj.on(2):
-                row_out.zero_()
         st = _stream()
         if fusedk:
             # ONE launch: the batch pair and both bank pairs, each token pair multiplied once (the larger problems
@@ -284,14 +323,20 @@ class HeadFunction(torch.autograd.Function):
         return (dtext, dvideo, dgt.reshape(gs_t) if need[2] else None, dgv.reshape(gs_v) if need[3] else None,
                 dtw.view_as(tw) if need[4] else None, dvw.view_as(vw) if need[5] else None,
                 dtw_mb.view_as(tw_mb) if need[6] else None, dvw_mb.view_as(vw_mb) if need[7] else None,
-                dls.reshape(()) if need[8] else None, None, None, None, None, None, None, None)
+                dls.reshape(()) if need[8] else None, None, None, None, None, None, None, None, None)
 
 
 def fused_head(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, text_mask, video_mask, mb_feat_t, mb_feat_v,
                mb_mask_t, mb_mask_v, *, centrality_scale, beta, num_neighbors, temperature, uniform_weight,
-               neighbor_weight, kl_weight, precision="bf16", bwd_precision=None, iters=50):
-    hp = (float(centrality_scale), float(beta), int(num_neighbors), float(temperature), int(iters),
-          float(uniform_weight), float(neighbor_weight), float(kl_weight), ops.PRECISIONS[precision],
-          ops.PRECISIONS[bwd_precision or precision])
+               neighbor_weight, kl_weight, precision="bf16", bwd_precision=None, iters=50, prologue=None):
+    hp = head_hparams(centrality_scale, beta, num_neighbors, temperature, uniform_weight, neighbor_weight, kl_weight,
+                      precision, bwd_precision, iters)
     return HeadFunction.apply(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, text_mask, video_mask,
-                              mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp)
+                              mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp, prologue)
+
+
+def head_hparams(centrality_scale, beta, num_neighbors, temperature, uniform_weight, neighbor_weight, kl_weight,
+                 precision="bf16", bwd_precision=None, iters=50):
+    return (float(centrality_scale), float(beta), int(num_neighbors), float(temperature), int(iters),
+            float(uniform_weight), float(neighbor_weight), float(kl_weight), ops.PRECISIONS[precision],
+            ops.PRECISIONS[bwd_precision or precision])

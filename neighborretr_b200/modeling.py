@@ -154,11 +154,19 @@ class HeadMixin:
             if text_feat.shape[0] < num_neighbors + 2:
                 raise IndexError(f"neighbor loss needs batch >= num_neighbors + 2 (got {text_feat.shape[0]}, "
                                  f"k={num_neighbors})")
-            from .fused import fused_head
+            from .fused import HeadFunction, HeadPrologue, head_hparams
             lowp = self._head_precision() == "bf16"
-            # the four weight-MLP evaluations are independent: forked streams (parallel graph branches); autograd
-            # runs each backward on its forward stream, so the MLP backward GEMMs overlap as well
-            with ops.ForkJoin(3) as fj:
+            ls = logit_scale if torch.is_tensor(logit_scale) else torch.tensor(float(logit_scale),
+                                                                               device=text_feat.device)
+            hp = head_hparams(centrality_scale, beta, num_neighbors, temperature, cfg.uniform_weight,
+                              cfg.neighbor_weight, cfg.kl_weight, self._head_precision(), self._head_bwd_precision())
+            # everything that does not need the token weights (token preparation, centrality weights, global
+            # similarity + Sinkhorn) is allocated here and enqueued on forked streams NEXT TO the four independent
+            # weight-MLP evaluations: parallel branches of the step's CUDA graph.  Autograd runs each MLP backward on
+            # its forward stream, so the backward GEMMs overlap as well.
+            pro = HeadPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, mb_feat_t, mb_feat_v,
+                               mb_mask_t, mb_mask_v, hp, text_feat.requires_grad, video_feat.requires_grad)
+            with ops.ForkJoin(6) as fj:
                 main = fj.main
                 tw_mb = _token_weights(self.text_weight_fc, mb_feat_t, mb_mask_t, lowp)
                 with fj.on(0):
@@ -170,15 +178,16 @@ class HeadMixin:
                 with fj.on(2):
                     vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp)
                     vw.record_stream(main)
-            ls = logit_scale if torch.is_tensor(logit_scale) else torch.tensor(float(logit_scale),
-                                                                               device=text_feat.device)
-            out5, nbr = fused_head(text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, ls, text_mask, video_mask,
-                                   mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, centrality_scale=centrality_scale,
-                                   beta=beta, num_neighbors=num_neighbors, temperature=temperature,
-                                   uniform_weight=cfg.uniform_weight, neighbor_weight=cfg.neighbor_weight,
-                                   kl_weight=cfg.kl_weight, precision=self._head_precision(),
-                                   bwd_precision=self._head_bwd_precision())
+                with fj.on(3):
+                    pro.run_text_side()
+                with fj.on(4):
+                    pro.run_video_side()
+                with fj.on(5):
+                    pro.run_global()
+            out5, nbr = HeadFunction.apply(text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, ls, text_mask,
+                                           video_mask, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp, pro)
             self.last_neighbors = (nbr[0], nbr[1])
+            self.last_out5 = out5               # [total, centrality, uniform, neighbor, kl] as one tensor (graph.py)
             return tuple(out5.unbind(0))
         local_t2v_logits, local_v2t_logits = self.local_level(text_feat, video_feat, text_mask, video_mask)
         uniform_loss, global_text_feat, global_video_feat, g, gt = self.compute_uniform_loss(

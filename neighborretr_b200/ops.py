@@ -448,7 +448,7 @@ class TokenMLPFunction(torch.autograd.Function):
         shape = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         with _tf32(tf32):
-            h = torch.addmm(b1, x2, w1.t()).relu_()
+            h = torch._addmm_activation(b1, x2, w1.t(), use_gelu=False)     # bias + ReLU in the GEMM epilogue
             out = torch.addmv(b2.expand(h.shape[0]), h, w2.reshape(-1))
         ctx.tf32 = tf32
         ctx.save_for_backward(x2, h, w1, w2)
