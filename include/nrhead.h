@@ -92,7 +92,8 @@ int nr_maxsim_fwd(int precision, const void* xn, const void* yn, const float* wx
  * Saved for backward (all nullable): pmax_x [Rx,Ry,Nx] f32 / ystar [Rx,Ry,Nx] u8 = max / arg-max over y for every
  * x token; pmax_y [Rx,Ry,Ny] f32 / xstar [Rx,Ry,Ny] u8 = max / arg-max over x for every y token (pmax_y carries
  * 3 fewer mantissa bits: the column arg-max travels in the low bits of the value).  Ties -> lower index.
- * Up to 4 problems with the same (Nx, Ny, d) share one persistent launch. */
+ * Up to 4 problems with the same (Nx, Ny, d) share one persistent launch.  workspace: >= 16 bytes of device memory
+ * (zeroed by the library on `stream`): the tile counter of the dynamic scheduler. */
 typedef struct {
   const void* x_bf16; const void* y_bf16;
   const float* wx; const float* wy;
@@ -105,7 +106,7 @@ typedef struct {
 } nr_maxsim2_problem;
 int nr_maxsim2_supported(int64_t Nx, int64_t Ny, int64_t d);
 int nr_maxsim2_fwd(const nr_maxsim2_problem* problems, int n_problems, int64_t Nx, int64_t Ny, int64_t d,
-                   void* stream);
+                   void* workspace, void* stream);
 /* backward of nr_maxsim2_fwd w.r.t. the normalised tokens: with g[rx,ry] = dH[rx*dh_sr + ry*dh_sc] * dh_scale
  * (dh_scale carries alpha) and the routing matrix
  *   C[(rx,x),(ry,y)] = g[rx,ry] * ( wx[rx,x] [y == ystar[rx,ry,x]] + wy[ry,y] [x == xstar[rx,ry,y]] ),

@@ -37,6 +37,7 @@ constexpr int T2_MAX_STAGES = 4;
 constexpr int T2_A_BYTES = T2_BM * 128;    // 16 KB
 constexpr int T2_ACC_COLS = 256;           // TMEM columns per accumulator stage
 constexpr int T2_MAX_PROB = 4;
+constexpr int T2_RING = 4;                 // depth of the tile-index ring between the scheduler and its consumers
 
 struct Tc2Prob {
   const float* wx; const float* wy;
@@ -53,6 +54,7 @@ struct alignas(64) Tc2Args {
   Tc2Prob p[T2_MAX_PROB];
   int nprob, n_tiles;
   int Nx, SX, MU, SY, UN, num_kb, stages, b_bytes, hp_ld, kg_ld;
+  unsigned int* tile_counter;              // zeroed per launch: dynamic tile scheduler
 };
 
 __host__ __device__ constexpr int t2_gcd(int a, int b) { return b == 0 ? a : t2_gcd(b, a % b); }
@@ -93,7 +95,10 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
   uint64_t* empty = bars + T2_MAX_STAGES;         // [stages]  MMA -> TMA
   uint64_t* tfull = bars + 2 * T2_MAX_STAGES;     // [2]       MMA -> epilogue
   uint64_t* tempty = tfull + 2;                   // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rfull = tempty + 2;                   // [4]       tile scheduler (TMA warp) -> MMA + epilogue
+  uint64_t* rempty = rfull + T2_RING;             // [4]       MMA + epilogue -> tile scheduler
+  int* ring = reinterpret_cast<int*>(rempty + T2_RING);   // [4] tile index, -1 = no more tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + T2_RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
     for (int p = 0; p < a.nprob; ++p) { tma_prefetch_desc(&a.tmx[p]); tma_prefetch_desc(&a.tmy[p]); }
     for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, T2_EPI); }
+    for (int s = 0; s < T2_RING; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, 1 + T2_EPI); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -126,7 +132,16 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)(a.MU + a.SY * NY) * 128u;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      // Dynamic tile scheduler: tiles are claimed from a global counter, so a CTA whose SM was still busy with
+      // another kernel of the step graph (the persistent grid is one CTA per SM) simply takes fewer tiles.
+      for (int n = 0;; ++n) {
+        const int slot = n & (T2_RING - 1);
+        mbar_wait(rempty + slot, ((uint32_t)(n / T2_RING) & 1u) ^ 1u);
+        int tile = (int)atomicAdd(a.tile_counter, 1u);
+        if (tile >= a.n_tiles) tile = -1;
+        ring[slot] = tile;
+        mbar_arrive(rfull + slot);                       // release: the ring entry is visible to the waiters
+        if (tile < 0) break;
         int p, mt, nt;
         decode(tile, p, mt, nt);
         const int row_x = mt * a.MU, row_y = nt * a.SY * NY;
@@ -145,8 +160,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(T2_BM, a.UN);
       int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+      for (int it = 0;; ++it) {
+        const int slot = it & (T2_RING - 1);
+        mbar_wait(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
+        const int tile = ring[slot];
+        mbar_arrive(rempty + slot);
+        if (tile < 0) break;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty + acc, acc_phase ^ 1);          // epilogue drained this accumulator
@@ -177,8 +196,12 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
     const int sx = r / Nx, x = r - sx * Nx;
     const uint32_t low = LOWM - ((uint32_t)lane & LOWM);
     uint32_t* kg_row = keyG + (r / GL) * a.kg_ld + (lane & (int)LOWM);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0;; ++it) {
+      const int slot = it & (T2_RING - 1);
+      mbar_wait(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
+      const int tile = ring[slot];
+      mbar_arrive(rempty + slot);
+      if (tile < 0) break;
       int pi, mt, nt;
       decode(tile, pi, mt, nt);
       const Tc2Prob& P = a.p[pi];
@@ -333,7 +356,8 @@ extern "C" int nr_maxsim2_supported(int64_t Nx, int64_t Ny, int64_t d) {
 }
 
 extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
-                              void* stream) {
+                              void* workspace, void* stream) {
+  NR_CHECK_ARG(workspace && ((uintptr_t)workspace & 3) == 0, "nr_maxsim2_fwd: workspace (>= 16 bytes, 4-byte aligned) required");
   NR_CHECK_ARG(probs && nprob >= 1 && nprob <= T2_MAX_PROB, "nr_maxsim2_fwd: 1..%d problems per launch (got %d)",
                T2_MAX_PROB, nprob);
   NR_CHECK_ARG(nr_maxsim2_supported(Nx, Ny, d),
@@ -382,8 +406,10 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
     if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny)) return e;
   }
   a.n_tiles = tiles;
+  a.tile_counter = (unsigned int*)workspace;
+  NR_CUDA(cudaMemsetAsync(workspace, 0, 16, (cudaStream_t)stream));
   const size_t tail = (size_t)2 * T2_BM * a.hp_ld * 4 + (size_t)(T2_BM / GL) * a.kg_ld * 4 +
-                      (size_t)((a.SX * a.UN + 1) & ~1) * 4 + 256;
+                      (size_t)((a.SX * a.UN + 1) & ~1) * 4 + 512;
   const size_t budget = 227 * 1024 - 1024;   // alignment slack
   int stages = (int)((budget - tail) / (size_t)(T2_A_BYTES + a.b_bytes));
   if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;

@@ -80,6 +80,7 @@ class HeadPrologue:
         self.mean = torch.empty(2, d, **f32); self.gn = torch.empty(2, B, d, **f32)
         self.ginv = torch.empty(2, B, **f32); self.w = torch.empty(2, B, **f32)
         self.need_t, self.need_v = need_text_grad, need_video_grad
+        self.global_done = None            # event of a still-running run_global() branch (see modeling.py)
         if bf:
             for P in (self.T, self.V, self.MT, self.MV):
                 P.alloc_transposed()
@@ -177,6 +178,9 @@ class HeadFunction(torch.autograd.Function):
             pC, yC = _fwd_dir(prec, MT, V, tw_mb, mtm, vm, mb_v2t, 1, M, None, 0, 0, 1)     # H(bank_t, video)^T
         ctx.fusedk = fusedk
         _call("nr_row_mean", _p(mb), M, 2 * B, M, _p(cb), st)                # both bank centralities at once
+        if pro.global_done is not None:                  # G, G^T and the Sinkhorn duals from the detached branch
+            torch.cuda.current_stream().wait_event(pro.global_done)
+            pro.global_done = None
         # ---- fork 2: row losses, the two directions side by side
         with ops.ForkJoin(1) as fj:
             _call("nr_row_losses_fwd", _p(S), B, _p(G), B, _p(cb[1]), _p(w[0]), _p(duals[0]), _p(duals[1]), B, B, 0,

@@ -184,6 +184,9 @@ class HeadMixin:
                     pro.run_video_side()
                 with fj.on(5):
                     pro.run_global()
+                # the Sinkhorn duals are first needed by the row losses, after the token-pair contraction: the
+                # head node waits on this event there instead of joining the branch here
+                pro.global_done = fj.detach(5)
             out5, nbr = HeadFunction.apply(text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, ls, text_mask,
                                            video_mask, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp, pro)
             self.last_neighbors = (nbr[0], nbr[1])

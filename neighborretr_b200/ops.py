@@ -68,6 +68,7 @@ class ForkJoin:
             lst.append(torch.cuda.Stream(device=self.main.device))
         _SIDE_STREAMS[self.main.device.index] = lst
         self.side = lst[:n]
+        self.detached = set()
         del key
 
     def __enter__(self):
@@ -78,9 +79,18 @@ class ForkJoin:
     def on(self, i):
         return torch.cuda.stream(self.side[i])
 
+    def detach(self, i):
+        """Do not join side stream i at exit: returns an event marking the end of what it has been given so far;
+        the caller makes the consuming stream wait on it later (the branch keeps overlapping what follows)."""
+        ev = torch.cuda.Event()
+        ev.record(self.side[i])
+        self.detached.add(i)
+        return ev
+
     def __exit__(self, *exc):
-        for s in self.side:
-            self.main.wait_stream(s)
+        for i, s in enumerate(self.side):
+            if i not in self.detached:
+                self.main.wait_stream(s)
         return False
 
 
@@ -270,7 +280,8 @@ def maxsim2_fwd(problems, keep=True):
         a.out2 = o2.data_ptr() if o2 is not None else None
         a.out2_sr, a.out2_sc = q.get("strides2", (0, 0))
         a.pmax_x, a.ystar, a.pmax_y, a.xstar = [t.data_ptr() if t is not None else None for t in sv]
-    _call("nr_maxsim2_fwd", ctypes.cast(arr, ctypes.c_void_p), len(problems), nx, ny, d, _stream())
+    ws = torch.empty(4, dtype=torch.int32, device=dev)          # tile counter of the dynamic scheduler
+    _call("nr_maxsim2_fwd", ctypes.cast(arr, ctypes.c_void_p), len(problems), nx, ny, d, _p(ws), _stream())
     return saved
 
 
