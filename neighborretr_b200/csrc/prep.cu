@@ -321,6 +321,105 @@ extern "C" int nr_gram_f32(const float* a, const float* b, int64_t Ra, int64_t R
 // replaces four ATen elementwise/reduction passes over [T,H]; HBM-bound: 8*T*H bytes.
 namespace nr {
 constexpr int MLPB_ROWS = 32;      // rows per CTA
+
+// Second layer + masked softmax over the tokens of a sample (reference modeling.py:485-492):
+//   logit[t] = <h[t,:], w2> + b2;  logit[masked] = -9e15;  w[r,:] = softmax_n(logit[r,:])
+// One CTA per sample, one warp per token row (float4 loads of the post-ReLU activations), softmax by warp 0.
+// Samples [0,Ra) take their mask from mask_a, samples [Ra,R) from mask_b (batch and bank tokens of one modality
+// share the launch).  HBM-bound: 4*T*H bytes read.
+__global__ void __launch_bounds__(256)
+token_weights_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2,
+                         const int64_t* __restrict__ mask_a, const int64_t* __restrict__ mask_b, int Ra, int N, int H,
+                         float* __restrict__ w) {
+  __shared__ float logit[NR_MAX_TOKENS];
+  const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t* mrow = r < Ra ? (mask_a ? mask_a + (int64_t)r * N : nullptr)
+                               : (mask_b ? mask_b + (int64_t)(r - Ra) * N : nullptr);
+  const float bias = b2[0];
+  for (int n = warp; n < N; n += 8) {
+    const float* hr = h + ((int64_t)r * N + n) * H;
+    float s = 0.f;
+    for (int c = lane * 4; c < H; c += 128) {
+      const float4 hv = *reinterpret_cast<const float4*>(hr + c);
+      const float4 wv = *reinterpret_cast<const float4*>(w2 + c);
+      s += hv.x * wv.x + hv.y * wv.y + hv.z * wv.z + hv.w * wv.w;
+    }
+    s = warp_sum(s);
+    if (lane == 0) logit[n] = (mrow && mrow[n] == 0) ? -9e15f : s + bias;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = NR_NEG_INF;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, logit[n]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < N; n += 32) sum += expf(logit[n] - mx);
+    sum = warp_sum(sum);
+    for (int n = lane; n < N; n += 32) w[(int64_t)r * N + n] = expf(logit[n] - mx) / sum;
+  }
+}
+
+// Backward of the same node down to the hidden layer, one streaming pass over h [T,H]:
+//   dlogit[t] = w[t] * (dw[t] - sum_m w[r,m] dw[r,m])          (softmax; masked tokens have w = 0)
+//   dh[t,j] = dlogit[t] * w2[j] * (h[t,j] > 0),  partials of db1[j] = sum_t dh[t,j], dw2[j] = sum_t dlogit[t] h[t,j],
+//   db2 = sum_t dlogit[t]  (row 2H of the partials).   dw of samples [0,Ra) comes from dw_a, the rest from dw_b
+//   (nullable = no gradient reached those weights).
+__global__ void __launch_bounds__(256)
+token_weights_bwd_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ dw_a,
+                         const float* __restrict__ dw_b, int Ra, int N, const float* __restrict__ w2, int T, int H,
+                         float* __restrict__ dh, float* __restrict__ partials, int nchunks) {
+  __shared__ float dl[MLPB_ROWS];
+  const int chunk = blockIdx.x, t0 = chunk * MLPB_ROWS, t1 = min(T, t0 + MLPB_ROWS);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = warp; i < t1 - t0; i += 8) {
+    const int t = t0 + i, r = t / N, n = t - r * N;
+    const float* dwr = r < Ra ? (dw_a ? dw_a + (int64_t)r * N : nullptr) : (dw_b ? dw_b + (int64_t)(r - Ra) * N : nullptr);
+    float v = 0.f;
+    if (dwr) {
+      const float* wr = w + (int64_t)r * N;
+      float s = 0.f;
+      for (int m = lane; m < N; m += 32) s += wr[m] * dwr[m];
+      s = warp_sum(s);
+      v = wr[n] * (dwr[n] - s);
+    }
+    if (lane == 0) dl[i] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float s = (lane < t1 - t0) ? dl[lane] : 0.f;
+    s = warp_sum(s);
+    if (lane == 0) partials[(int64_t)(2 * H) * nchunks + chunk] = s;
+  }
+  for (int c = threadIdx.x * 4; c < H; c += 256 * 4) {
+    const float4 wv = *reinterpret_cast<const float4*>(w2 + c);
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sw = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tb = t0; tb < t1; tb += 8) {                 // 8 independent 16-byte loads in flight per thread
+      float4 hv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = min(tb + i, t1 - 1);
+        hv[i] = *reinterpret_cast<const float4*>(h + (int64_t)t * H + c);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (tb + i < t1) {
+          const float d = dl[tb + i - t0];
+          float4 o;
+          o.x = hv[i].x > 0.f ? d * wv.x : 0.f; o.y = hv[i].y > 0.f ? d * wv.y : 0.f;
+          o.z = hv[i].z > 0.f ? d * wv.z : 0.f; o.w = hv[i].w > 0.f ? d * wv.w : 0.f;
+          *reinterpret_cast<float4*>(dh + (int64_t)(tb + i) * H + c) = o;
+          sb.x += o.x; sb.y += o.y; sb.z += o.z; sb.w += o.w;
+          sw.x += d * hv[i].x; sw.y += d * hv[i].y; sw.z += d * hv[i].z; sw.w += d * hv[i].w;
+        }
+      }
+    }
+    float* pb = partials + (int64_t)c * nchunks + chunk;
+    pb[0] = sb.x; pb[nchunks] = sb.y; pb[2 * (int64_t)nchunks] = sb.z; pb[3 * (int64_t)nchunks] = sb.w;
+    float* pw = partials + (int64_t)(H + c) * nchunks + chunk;
+    pw[0] = sw.x; pw[nchunks] = sw.y; pw[2 * (int64_t)nchunks] = sw.z; pw[3 * (int64_t)nchunks] = sw.w;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 mlp_hidden_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dlogit, const float* __restrict__ w2,
                       int T, int H, float* __restrict__ dh, float* __restrict__ partials, int nchunks) {
@@ -367,5 +466,29 @@ extern "C" int nr_mlp_hidden_bwd(const float* h, const float* dlogit, const floa
   nr::mlp_hidden_bwd_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(h, dlogit, w2, (int)T, (int)H, dh, partials,
                                                                       nchunks);
   NR_CHECK_LAUNCH("nr_mlp_hidden_bwd");
+  return 0;
+}
+
+extern "C" int nr_token_weights_fwd(const float* h, const float* w2, const float* b2, const int64_t* mask_a,
+                                    const int64_t* mask_b, int64_t Ra, int64_t R, int64_t N, int64_t H, float* w,
+                                    void* stream) {
+  NR_CHECK_ARG(h && w2 && b2 && w && R > 0 && Ra >= 0 && Ra <= R && N > 0 && N <= NR_MAX_TOKENS && H > 0 && H % 4 == 0,
+               "nr_token_weights_fwd: bad arguments");
+  nr::token_weights_fwd_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(h, w2, b2, mask_a, mask_b, (int)Ra, (int)N,
+                                                                             (int)H, w);
+  NR_CHECK_LAUNCH("nr_token_weights_fwd");
+  return 0;
+}
+
+extern "C" int nr_token_weights_bwd(const float* h, const float* w, const float* dw_a, const float* dw_b, int64_t Ra,
+                                    int64_t R, int64_t N, const float* w2, int64_t H, float* dh, float* partials,
+                                    void* stream) {
+  NR_CHECK_ARG(h && w && w2 && dh && partials && R > 0 && Ra >= 0 && Ra <= R && N > 0 && H > 0 && H % 4 == 0,
+               "nr_token_weights_bwd: bad arguments");
+  const int64_t T = R * N;
+  const int nchunks = (int)nr_mlp_chunks(T);
+  nr::token_weights_bwd_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(h, w, dw_a, dw_b, (int)Ra, (int)N, w2, (int)T,
+                                                                         (int)H, dh, partials, nchunks);
+  NR_CHECK_LAUNCH("nr_token_weights_bwd");
   return 0;
 }

@@ -34,10 +34,7 @@ def _token_weights(mlp, feat, mask, lowp=False):
     """softmax over tokens of the MLP logits, masked tokens filled with -9e15 (reference :485-492).
     lowp: run the Linear layers as TF32 tensor-core GEMMs (cuBLAS) in both passes — the bf16 head mode;
     otherwise plain fp32 GEMMs.  The softmax stays fp32."""
-    logit = ops.token_mlp_logits(mlp, feat, lowp)
-    if mask is not None:
-        logit = logit.masked_fill((1 - mask).to(torch.bool), float(-9e15))
-    return torch.softmax(logit, dim=-1)
+    return ops.token_weights(mlp, feat, mask, lowp)[0]
 
 
 class HeadMixin:
@@ -166,27 +163,23 @@ class HeadMixin:
             # its forward stream, so the backward GEMMs overlap as well.
             pro = HeadPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, mb_feat_t, mb_feat_v,
                                mb_mask_t, mb_mask_v, hp, text_feat.requires_grad, video_feat.requires_grad)
-            with ops.ForkJoin(6) as fj:
+            with ops.ForkJoin(4) as fj:
                 main = fj.main
-                tw_mb = _token_weights(self.text_weight_fc, mb_feat_t, mb_mask_t, lowp)
+                # one node per modality: batch tokens and bank tokens share the hidden buffer and the kernels
+                tw, tw_mb = ops.token_weights(self.text_weight_fc, text_feat, text_mask, lowp, mb_feat_t, mb_mask_t)
                 with fj.on(0):
-                    vw_mb = _token_weights(self.video_weight_fc, mb_feat_v, mb_mask_v, lowp)
-                    vw_mb.record_stream(main)
-                with fj.on(1):
-                    tw = _token_weights(self.text_weight_fc, text_feat, text_mask, lowp)
-                    tw.record_stream(main)
-                with fj.on(2):
-                    vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp)
+                    vw, vw_mb = ops.token_weights(self.video_weight_fc, video_feat, video_mask, lowp, mb_feat_v,
+                                                  mb_mask_v)
                     vw.record_stream(main)
-                with fj.on(3):
+                with fj.on(1):
                     pro.run_text_side()
-                with fj.on(4):
+                with fj.on(2):
                     pro.run_video_side()
-                with fj.on(5):
+                with fj.on(3):
                     pro.run_global()
                 # the Sinkhorn duals are first needed by the row losses, after the token-pair contraction: the
                 # head node waits on this event there instead of joining the branch here
-                pro.global_done = fj.detach(5)
+                pro.global_done = fj.detach(3)
             out5, nbr = HeadFunction.apply(text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, ls, text_mask,
                                            video_mask, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp, pro)
             self.last_neighbors = (nbr[0], nbr[1])
@@ -237,10 +230,8 @@ class HeadMixin:
         # (one flat all_reduce in backward) so that every rank holds the full gradient, as in the reference
         ps = SumGradsAcrossRanks.apply(*ops.mlp_params(self.text_weight_fc), *ops.mlp_params(self.video_weight_fc))
         tmlp, vmlp = ps[:4], ps[4:]
-        tw = _token_weights(tmlp, text_feat, text_mask, lowp)
-        vw = _token_weights(vmlp, video_feat, video_mask, lowp)
-        tw_mb = _token_weights(tmlp, self.mb_feat_t, self.mb_mask_t, lowp)
-        vw_mb = _token_weights(vmlp, self.mb_feat_v, self.mb_mask_v, lowp)
+        tw, tw_mb = ops.token_weights(tmlp, text_feat, text_mask, lowp, self.mb_feat_t, self.mb_mask_t)
+        vw, vw_mb = ops.token_weights(vmlp, video_feat, video_mask, lowp, self.mb_feat_v, self.mb_mask_v)
         gtf, gvf = global_feats
         out5, nbr, text_all, video_all, tm_all, vm_all = sharded_head(
             text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, self.clip.logit_scale.exp(), text_mask, video_mask,

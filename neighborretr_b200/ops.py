@@ -488,6 +488,79 @@ class TokenMLPFunction(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, None
 
 
+class TokenWeightsFunction(torch.autograd.Function):
+    """softmax over tokens of the masked weight-MLP logits (reference modeling.py:485-492) as ONE autograd node
+    for the batch tokens and, optionally, the memory-bank tokens of the same modality:
+        forward : first layer = library GEMM with bias+ReLU epilogue (TF32 in bf16 head mode) into one hidden
+                  buffer, then nr_token_weights_fwd (second layer + mask + softmax, one pass over h);
+        backward: nr_token_weights_bwd (softmax + second layer + ReLU backward, one pass over h) and the dW1 / dx
+                  library GEMMs; bank tokens take no dx.
+    Replaces ~10 ATen launches per evaluation and the parameter-gradient accumulation of two separate nodes."""
+
+    @staticmethod
+    def forward(ctx, xa, ma, xb, mb, w1, b1, w2, b2, tf32):
+        _req_cuda(xa, xb, w1, b1, w2, b2)
+        Ra, N, D = xa.shape
+        Rb = xb.shape[0] if xb is not None else 0
+        if Rb and tuple(xb.shape[1:]) != (N, D):
+            raise RuntimeError("token_weights: batch and bank tokens differ in shape")
+        H = w1.shape[0]
+        Ta, Tb = Ra * N, Rb * N
+        xa2 = _f32c(xa).reshape(Ta, D)
+        xb2 = _f32c(xb).reshape(Tb, D) if Rb else None
+        ma, mb = _mask(ma), (_mask(mb) if Rb else None)
+        h = torch.empty(Ta + Tb, H, dtype=torch.float32, device=xa.device)
+        w = torch.empty(Ra + Rb, N, dtype=torch.float32, device=xa.device)
+        w2c, b2c = _f32c(w2).reshape(-1), _f32c(b2).reshape(-1)
+        with _tf32(tf32):
+            torch._addmm_activation(b1, xa2, w1.t(), use_gelu=False, out=h[:Ta])     # bias + ReLU in the epilogue
+            if Rb:
+                torch._addmm_activation(b1, xb2, w1.t(), use_gelu=False, out=h[Ta:])
+        _call("nr_token_weights_fwd", _p(h), _p(w2c), _p(b2c), _p(ma), _p(mb), Ra, Ra + Rb, N, H, _p(w), _stream())
+        ctx.tf32, ctx.dims = tf32, (Ra, Rb, N, D, H)
+        ctx.save_for_backward(xa2, xb2, h, w, w1, w2c)
+        ctx.xshape = xa.shape
+        wa = w[:Ra]
+        if Rb:
+            return wa, w[Ra:]
+        return wa, None
+
+    @staticmethod
+    def backward(ctx, dwa, dwb):
+        xa2, xb2, h, w, w1, w2c = ctx.saved_tensors
+        Ra, Rb, N, D, H = ctx.dims
+        Ta, Tb = Ra * N, Rb * N
+        need = ctx.needs_input_grad
+        dwa = _f32c(dwa) if dwa is not None else None
+        dwb = _f32c(dwb) if (dwb is not None and Rb) else None
+        dh = torch.empty_like(h)
+        nch = _lib.load().nr_mlp_chunks(Ta + Tb)
+        partials = torch.empty(2 * H + 1, nch, dtype=torch.float32, device=h.device)
+        sums = torch.empty(2 * H + 1, dtype=torch.float32, device=h.device)
+        st = _stream()
+        _call("nr_token_weights_bwd", _p(h), _p(w), _p(dwa), _p(dwb), Ra, Ra + Rb, N, _p(w2c), H, _p(dh), _p(partials), st)
+        _call("nr_vec_sums", _p(partials), 2 * H + 1, nch, None, _p(sums), st)
+        db1 = sums[:H] if need[5] else None
+        dw2 = sums[H:2 * H].reshape(1, H) if need[6] else None
+        db2 = sums[2 * H:] if need[7] else None
+        dw1 = dx = None
+        with _tf32(ctx.tf32):
+            if need[4]:
+                dw1 = dh[:Ta].t() @ xa2
+                if Rb:
+                    dw1.addmm_(dh[Ta:].t(), xb2)
+            if need[0]:
+                dx = (dh[:Ta] @ w1).reshape(ctx.xshape)
+        return dx, None, None, None, dw1, db1, dw2, db2, None
+
+
+def token_weights(mlp, feat, mask, tf32, bank_feat=None, bank_mask=None):
+    """mlp: nn.Sequential(Linear, ReLU, Linear) with the reference's parameter names, or its 4 parameters
+    (W1, b1, W2, b2) as a tuple.  Returns the token weights of `feat` [R,N] and of `bank_feat` (or None)."""
+    ps = mlp if isinstance(mlp, (tuple, list)) else mlp_params(mlp)
+    return TokenWeightsFunction.apply(feat, mask, bank_feat, bank_mask, *ps, bool(tf32))
+
+
 def mlp_params(mlp):
     return (mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias)
 
