@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "nrhead_internal.h"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace nr {
 using namespace tc;
@@ -37,6 +38,7 @@ struct Tc2BwdArgs {
   int Ro, No, Rs, Ns, D;
   float* dst;
   int out_tokens, src_tokens, n_mt, num_kb, KS, kb_per_split, n_half, half_cols, stages;
+  int debug;                                  // timing experiments only (NR_B2_DEBUG): 1 no red.add, 2 no generator, 4 no TMA
 };
 
 __device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float c, float d) {
@@ -85,9 +87,12 @@ maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* sb = smem + (size_t)stage * stage_bytes + B2_A_BYTES;
+          if (a.debug & 4) { mbar_arrive(b_full + stage); }
+          else {
           mbar_expect_tx(b_full + stage, tx_bytes);
           for (int h = 0; h < a.n_half; ++h)
             tma_load_2d(sb + h * B2_B_HALF_BYTES, &tms, b_full + stage, kb * B2_BK, h * 256);
+          }
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -138,9 +143,47 @@ maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs 
       const int ro = valid ? g / No : 0, o = valid ? g - ro * No : 0;   // (sample, token) of the output row
       const float coefo = valid ? a.wO[g] * a.scale : 0.f;
       const int ro_lo = row0 / No, ro_hi = min(a.Ro - 1, (row0 + B2_BM - 1) / No);   // out samples touching this tile
+      // Routing data (arg-max bytes, upstream gradients) of a k-block is loaded one k-block AHEAD into registers: the
+      // dependent global loads would otherwise sit on the generator's critical path (2 stages cannot hide them).
+      // Slots cover 8 partner samples per row / 8 out samples per column thread; longer ranges (tiny Ns / No) take
+      // the direct-load remainder loops below.
+      const int j = et & 63, jh = et >> 6;               // scatter side: source column and which half of the out samples
+      const uint8_t* stO = a.starO + (int64_t)ro * a.aO_o + o;
+      const float* gpO = a.dH + (int64_t)ro * a.g_o;
+      struct Pre { int sv[8]; float gv[8]; int ov[8]; float hv[8]; float cw; };
+      auto load_pre = [&](int kb, Pre& P) {
+        const int t0 = kb * B2_BK;
+        const int rs_lo = t0 / Ns, rs_hi = min(a.Rs - 1, (t0 + B2_BK - 1) / Ns);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rs = min(rs_lo + i, rs_hi);
+          P.sv[i] = (coefo != 0.f) ? (int)stO[(int64_t)rs * a.aO_s] : 0;
+          P.gv[i] = (coefo != 0.f) ? gpO[(int64_t)rs * a.g_s] : 0.f;
+        }
+        const int tsrc = min(t0 + j, a.src_tokens - 1);
+        const int rs = tsrc / Ns, sidx = tsrc - rs * Ns;
+        P.cw = (t0 + j < a.src_tokens) ? a.wS[tsrc] * a.scale : 0.f;
+        const uint8_t* st = a.starS + (int64_t)rs * a.aS_s + sidx;
+        const float* gp = a.dH + (int64_t)rs * a.g_s;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r2 = min(ro_lo + jh + 2 * i, ro_hi);
+          P.ov[i] = (P.cw != 0.f) ? (int)st[(int64_t)r2 * a.aS_o] : 0;
+          P.hv[i] = (P.cw != 0.f) ? gp[(int64_t)r2 * a.g_o] : 0.f;
+        }
+      };
+      Pre cur, nxt;
+      if (kb0 < kb1) load_pre(kb0, cur);
       for (int kb = kb0; kb < kb1; ++kb) {
+        if (kb + 1 < kb1) load_pre(kb + 1, nxt);
         mbar_wait(empty + stage, phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * stage_bytes;
+        if (a.debug & 2) {
+          fence_proxy_async();
+          mbar_arrive(a_full + stage);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         // cooperative zero fill of this warp's 32 rows (512 contiguous bytes per store instruction)
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -151,63 +194,51 @@ maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs 
         if (coefo != 0.f) {
           uint8_t* srow = sa + m * 128;
           const int rs_lo = t0 / Ns, rs_hi = min(a.Rs - 1, (t0 + B2_BK - 1) / Ns);
-          const uint8_t* st = a.starO + (int64_t)ro * a.aO_o + o;
-          const float* gp = a.dH + (int64_t)ro * a.g_o;
-          for (int rb = rs_lo; rb <= rs_hi; rb += 8) {          // 8 independent loads in flight
-            int sv[8]; float gv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rs = min(rb + i, rs_hi);
-              sv[i] = st[(int64_t)rs * a.aO_s];
-              gv[i] = gp[(int64_t)rs * a.g_s];
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rs = rb + i;
-              const int t = rs * Ns + sv[i] - t0;
-              if (rs <= rs_hi && t >= 0 && t < B2_BK)
-                *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
-                    __float2bfloat16_rn(gv[i] * coefo);
-            }
+          for (int i = 0; i < 8; ++i) {
+            const int rs = rs_lo + i;
+            const int t = rs * Ns + cur.sv[i] - t0;
+            if (rs <= rs_hi && t >= 0 && t < B2_BK)
+              *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
+                  __float2bfloat16_rn(cur.gv[i] * coefo);
+          }
+          for (int rs = rs_lo + 8; rs <= rs_hi; ++rs) {          // remainder (Ns < 10 only)
+            const int t = rs * Ns + (int)stO[(int64_t)rs * a.aO_s] - t0;
+            if (t >= 0 && t < B2_BK)
+              *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
+                  __float2bfloat16_rn(gpO[(int64_t)rs * a.g_s] * coefo);
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");         // rows zeroed and side-(1) entries in place
         // (2) source-token side: column j, one entry per out sample of this tile; lands in row (ro, o*) and is
         //     ADDED to whatever side (1) put there (mutual arg-max pairs)
-        {
-          const int j = et & 63;
-          const int tsrc = t0 + j;
-          if (tsrc < a.src_tokens) {
-            const int rs = tsrc / Ns, s = tsrc - rs * Ns;
-            const float cw = a.wS[tsrc] * a.scale;
-            if (cw != 0.f) {
-              const uint8_t* st = a.starS + (int64_t)rs * a.aS_s + s;
-              const float* gp = a.dH + (int64_t)rs * a.g_s;
-              for (int rb = ro_lo + (et >> 6); rb <= ro_hi; rb += 16) {
-                int ov[8]; float gv[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int r2 = min(rb + 2 * i, ro_hi);
-                  ov[i] = st[(int64_t)r2 * a.aS_o];
-                  gv[i] = gp[(int64_t)r2 * a.g_o];
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const int r2 = rb + 2 * i;
-                  const int mm = r2 * No + ov[i] - row0;
-                  if (r2 <= ro_hi && mm >= 0 && mm < B2_BM) {
-                    __nv_bfloat16* e =
-                        reinterpret_cast<__nv_bfloat16*>(sa + mm * 128 + (((j >> 3) ^ (mm & 7)) << 4) + (j & 7) * 2);
-                    *e = __float2bfloat16_rn(__bfloat162float(*e) + gv[i] * cw);
-                  }
-                }
-              }
+        if (cur.cw != 0.f) {
+          auto put = [&](int r2, int ostar, float gval) {
+            const int mm = r2 * No + ostar - row0;
+            if (mm >= 0 && mm < B2_BM) {
+              __nv_bfloat16* e =
+                  reinterpret_cast<__nv_bfloat16*>(sa + mm * 128 + (((j >> 3) ^ (mm & 7)) << 4) + (j & 7) * 2);
+              *e = __float2bfloat16_rn(__bfloat162float(*e) + gval * cur.cw);
             }
+          };
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r2 = ro_lo + jh + 2 * i;
+            if (r2 <= ro_hi) put(r2, cur.ov[i], cur.hv[i]);
+          }
+          if (ro_lo + jh + 16 <= ro_hi) {                        // remainder (No < 10 only)
+            const int tsrc = t0 + j;
+            const int rs = tsrc / Ns, sidx = tsrc - rs * Ns;
+            const uint8_t* st = a.starS + (int64_t)rs * a.aS_s + sidx;
+            const float* gp = a.dH + (int64_t)rs * a.g_s;
+            for (int r2 = ro_lo + jh + 16; r2 <= ro_hi; r2 += 2)
+              put(r2, (int)st[(int64_t)r2 * a.aS_o], gp[(int64_t)r2 * a.g_o]);
           }
         }
         fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core
         mbar_arrive(a_full + stage);
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        cur = nxt;
       }
       // ---- epilogue: TMEM -> red.global.add ----
       mbar_wait(acc_full, (uint32_t)(it & 1));
@@ -220,7 +251,7 @@ maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs 
           tmem_ld16(taddr + (uint32_t)((c >> 8) * 256 + (c & 255)), v);
           tmem_ld_wait();
           reg_fence<16>(v);
-          if (valid) {
+          if (valid && !(a.debug & 1)) {
 #pragma unroll
             for (int e = 0; e < 16; e += 4)
               red_add_v4_(drow + c + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
@@ -328,6 +359,11 @@ extern "C" int nr_maxsim2_bwd(int side, const void* srcT, int64_t src_ld, const 
   a.kb_per_split = (a.num_kb + ks - 1) / ks;
   a.KS = (a.num_kb + a.kb_per_split - 1) / a.kb_per_split;
   a.stages = 2;
+  if (const char* dbg = getenv("NR_B2_DEBUG")) a.debug = atoi(dbg);
+  if (const char* ksv = getenv("NR_B2_KS")) {
+    int k2 = atoi(ksv);
+    if (k2 >= 1 && k2 <= a.num_kb) { a.kb_per_split = (a.num_kb + k2 - 1) / k2; a.KS = (a.num_kb + a.kb_per_split - 1) / a.kb_per_split; }
+  }
   const size_t stage_bytes = (size_t)B2_A_BYTES + (size_t)a.n_half * B2_B_HALF_BYTES;
   const size_t smem = a.stages * stage_bytes + 256 + 1024;
   CUtensorMap tms;

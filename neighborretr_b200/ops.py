@@ -546,12 +546,23 @@ class TokenWeightsFunction(torch.autograd.Function):
         dw1 = dx = None
         with _tf32(ctx.tf32):
             if need[4]:
-                dw1 = dh[:Ta].t() @ xa2
+                dw1 = _dw1_splitk(dh[:Ta], xa2)
                 if Rb:
-                    dw1.addmm_(dh[Ta:].t(), xb2)
+                    dw1 += _dw1_splitk(dh[Ta:], xb2)
             if need[0]:
                 dx = (dh[:Ta] @ w1).reshape(ctx.xshape)
         return dx, None, None, None, dw1, db1, dw2, db2, None
+
+
+def _dw1_splitk(dh, x):
+    """dh^T @ x for dh [T,H], x [T,D] with T >> H, D: the library runs this [H,D] output as 64 CTAs over the whole
+    K = T; a batched product over K-chunks (split-K) fills the GPU, the chunk sum is one small reduction."""
+    T = x.shape[0]
+    for parts in (8, 6, 4, 3, 2):
+        if T % parts == 0 and T // parts >= 1024:
+            c = T // parts
+            return torch.bmm(dh.view(parts, c, dh.shape[1]).transpose(1, 2), x.view(parts, c, x.shape[1])).sum(0)
+    return dh.t() @ x
 
 
 def token_weights(mlp, feat, mask, tf32, bank_feat=None, bank_mask=None):
