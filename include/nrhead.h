@@ -120,15 +120,24 @@ typedef struct {
 int nr_maxsim2_supported(int64_t Nx, int64_t Ny, int64_t d);
 int nr_maxsim2_fwd(const nr_maxsim2_problem* problems, int n_problems, int64_t Nx, int64_t Ny, int64_t d,
                    void* workspace, void* stream);
-/* backward of nr_maxsim2_fwd w.r.t. the normalised tokens: with g[rx,ry] = dH[rx*dh_sr + ry*dh_sc] * dh_scale
- * (dh_scale carries alpha) and the routing matrix
+/* backward of nr_maxsim2_fwd w.r.t. the normalised tokens.  For one pair with g[rx,ry] = dH[rx*dh_sr + ry*dh_sc] *
+ * dh_scale (dh_scale carries alpha) and the routing matrix
  *   C[(rx,x),(ry,y)] = g[rx,ry] * ( wx[rx,x] [y == ystar[rx,ry,x]] + wy[ry,y] [x == xstar[rx,ry,y]] ),
  * side 0: dst [Rx*Nx, d] += C   * Y tokens   (srcT = transposed bf16 Y tokens [d, src_ld]),
  * side 1: dst [Ry*Ny, d] += C^T * X tokens   (srcT = transposed bf16 X tokens [d, src_ld]).
- * dst is fp32, zero- or partially-filled: split-K partials are combined with red.global.add. */
-int nr_maxsim2_bwd(int side, const void* srcT, int64_t src_ld, const float* wx, const float* wy, const uint8_t* ystar,
-                   const uint8_t* xstar, const float* dH, int64_t dh_sr, int64_t dh_sc, float dh_scale, int64_t Rx,
-                   int64_t Nx, int64_t Ry, int64_t Ny, int64_t d, float* dst, void* stream);
+ * dst is fp32, zero- or partially-filled: split-K partials are combined with red.global.add.
+ * Up to 6 such jobs share ONE launch; jobs with the same dst (e.g. the text gradient from the batch pair and from
+ * the bank pair) are accumulated in the same pass over their concatenated source tokens. */
+typedef struct {
+  int side;
+  const void* srcT; int64_t src_ld;
+  const float* wx; const float* wy;
+  const uint8_t* ystar; const uint8_t* xstar;
+  const float* dH; int64_t dh_sr, dh_sc; float dh_scale;
+  int64_t Rx, Ry;
+  float* dst;
+} nr_maxsim2_bwd_job;
+int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int n_jobs, int64_t Nx, int64_t Ny, int64_t d, void* stream);
 /* ... w.r.t. the token weights (either output nullable):
  *   dwx[rx,x] += sum_ry g[rx,ry] pmax_x[rx,ry,x],   dwy[ry,y] += sum_rx g[rx,ry] pmax_y[rx,ry,y] */
 int nr_maxsim2_bwd_w(const float* pmax_x, const float* pmax_y, const float* dH, int64_t dh_sr, int64_t dh_sc,

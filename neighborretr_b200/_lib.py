@@ -33,7 +33,7 @@ SIGNATURES = {
                            _I64, _I, _P, _P, _P]),
     "nr_maxsim2_supported": (_I, [_I64, _I64, _I64]),
     "nr_maxsim2_fwd": (_I, [_P, _I, _I64, _I64, _I64, _P, _P]),
-    "nr_maxsim2_bwd": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
+    "nr_maxsim2_bwd": (_I, [_P, _I, _I64, _I64, _I64, _P]),
     "nr_maxsim2_bwd_w": (_I, [_P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "nr_transpose_tokens_bf16": (_I, [_P, _I64, _I64, _P, _I64, _P]),
     "nr_maxsim_bwd_x": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
@@ -64,6 +64,12 @@ class MaxSim2Problem(ctypes.Structure):
     _fields_ = [("x_bf16", _P), ("y_bf16", _P), ("wx", _P), ("wy", _P), ("Rx", _I64), ("Ry", _I64), ("alpha", _F),
                 ("out", _P), ("out_sr", _I64), ("out_sc", _I64), ("out2", _P), ("out2_sr", _I64), ("out2_sc", _I64),
                 ("pmax_x", _P), ("ystar", _P), ("pmax_y", _P), ("xstar", _P)]
+
+
+class MaxSim2BwdJob(ctypes.Structure):
+    """nr_maxsim2_bwd_job of include/nrhead.h (field order and types must match)."""
+    _fields_ = [("side", _I), ("srcT", _P), ("src_ld", _I64), ("wx", _P), ("wy", _P), ("ystar", _P), ("xstar", _P),
+                ("dH", _P), ("dh_sr", _I64), ("dh_sc", _I64), ("dh_scale", _F), ("Rx", _I64), ("Ry", _I64), ("dst", _P)]
 
 
 NR_LOSS_CENTRALITY, NR_LOSS_NEIGHBOR, NR_LOSS_KL, NR_LOSS_UNIFORM = 1, 2, 4, 8

@@ -23,22 +23,37 @@ using namespace tc;
 
 int make_tmap_srcT(CUtensorMap* m, const void* base, int64_t d, int64_t tokens, int64_t ld, int box_rows);
 
-constexpr int B2_THREADS = 192;               // TMA warp, MMA warp, 4 generator/epilogue warps
+constexpr int B2_THREADS = 320;               // TMA warp, MMA warp, 2 generator/epilogue groups of 4 warps
+constexpr int B2_GROUP = 128;
 constexpr int B2_BM = 128;
 constexpr int B2_BK = 64;
 constexpr int B2_A_BYTES = B2_BM * 128;       // 16 KB
 constexpr int B2_B_HALF_BYTES = 256 * 128;    // one d-half of a source k-block: 256 rows x 128 B
+constexpr int B2_MAX_JOBS = 6;
+constexpr int B2_MAX_SIDES = 4;
+constexpr int B2_MAX_SRC = 3;
 
-// "out" side O (rows of C / of the result), "source" side S (columns of C / rows of the staged operand)
-struct Tc2BwdArgs {
-  const float* wO; const float* wS;           // token weights [Ro,No], [Rs,Ns]
-  const uint8_t* starO; int64_t aO_o, aO_s;   // arg-max over source tokens per out token:  starO[ro*aO_o + rs*aO_s + o]
-  const uint8_t* starS; int64_t aS_o, aS_s;   // arg-max over out tokens per source token:  starS[ro*aS_o + rs*aS_s + s]
-  const float* dH; int64_t g_o, g_s; float scale;   // g(ro,rs) = dH[ro*g_o + rs*g_s] * scale
-  int Ro, No, Rs, Ns, D;
-  float* dst;
-  int out_tokens, src_tokens, n_mt, num_kb, KS, kb_per_split, n_half, half_cols, stages;
-  int debug;                                  // timing experiments only (NR_B2_DEBUG): 1 no red.add, 2 no generator, 4 no TMA
+// One job = one source operand S contributing to the gradient of one output operand O ("side"):
+//   starO[ro*aO_o + rs*aO_s + o] arg-max over the source tokens for out token o of the pair (ro, rs)
+//   starS[ro*aS_o + rs*aS_s + s] arg-max over the out tokens for source token s
+//   g(ro, rs) = dH[ro*g_o + rs*g_s] * scale
+struct B2Src {
+  const float* wS;
+  const uint8_t* starO; int64_t aO_o, aO_s;
+  const uint8_t* starS; int64_t aS_o, aS_s;
+  const float* dH; int64_t g_o, g_s; float scale;
+  int Rs, Ns, src_tokens, num_kb, kb0;        // kb0: first k-block of this source in the side's concatenated K range
+};
+struct B2Side {
+  const float* wO; float* dst;
+  int Ro, No, out_tokens, n_mt, nsrc, kb_total, KS, kb_per_split, item0;
+  int src[B2_MAX_SRC];                        // indices into srcs[] / tms[]
+};
+struct alignas(64) B2Args {
+  CUtensorMap tms[B2_MAX_JOBS];
+  B2Src srcs[B2_MAX_JOBS];
+  B2Side sides[B2_MAX_SIDES];
+  int nsides, n_items, D, n_half, half_cols, debug;
 };
 
 __device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float c, float d) {
@@ -46,26 +61,28 @@ __device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float
                : "memory");
 }
 
-__global__ void __launch_bounds__(B2_THREADS, 1)
-maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs a) {
+// All gradient contractions of a step in ONE launch: an item = (side, 128-token output tile, K-split), where the K
+// range of a side is the concatenation of its sources (e.g. text gradient: video tokens then bank-video tokens), so
+// one accumulator pass and ONE red.add epilogue serve every pair that feeds the same output rows.
+__global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __grid_constant__ B2Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = B2_A_BYTES + a.n_half * B2_B_HALF_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
-  uint64_t* b_full = bars;            // [stages] TMA -> MMA
-  uint64_t* a_full = bars + 4;        // [stages] generators -> MMA
-  uint64_t* empty = bars + 8;         // [stages] MMA -> TMA + generators
-  uint64_t* acc_full = bars + 12;     // MMA -> epilogue
-  uint64_t* acc_empty = bars + 13;    // epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)2 * stage_bytes);
+  uint64_t* b_full = bars;            // [2] TMA -> MMA
+  uint64_t* a_full = bars + 2;        // [2] generator group s -> MMA
+  uint64_t* empty = bars + 4;         // [2] MMA -> TMA + generator group s
+  uint64_t* acc_full = bars + 6;      // MMA -> epilogue
+  uint64_t* acc_empty = bars + 7;     // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = a.n_mt * a.KS;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tms);
-    for (int s = 0; s < a.stages; ++s) { mbar_init(b_full + s, 1); mbar_init(a_full + s, 128); mbar_init(empty + s, 1); }
+    for (int s = 0; s < a.nsides; ++s)
+      for (int q = 0; q < a.sides[s].nsrc; ++q) tma_prefetch_desc(&a.tms[a.sides[s].src[q]]);
+    for (int s = 0; s < 2; ++s) { mbar_init(b_full + s, 1); mbar_init(a_full + s, B2_GROUP); mbar_init(empty + s, 1); }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    mbar_init(acc_empty, 2 * B2_GROUP);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -77,39 +94,59 @@ maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // item -> (side, output tile, concatenated k-block range)
+  auto decode = [&](int item, int& sd, int& mt, int& kbA, int& kbB) {
+    sd = 0;
+    while (sd + 1 < a.nsides && item >= a.sides[sd + 1].item0) ++sd;
+    const B2Side& S = a.sides[sd];
+    const int local = item - S.item0;
+    mt = local / S.KS;
+    const int ks = local - mt * S.KS;
+    kbA = ks * S.kb_per_split;
+    kbB = min(S.kb_total, kbA + S.kb_per_split);
+  };
+  // concatenated k-block -> index of its source within the side
+  auto which_src = [&](const B2Side& S, int kb) {
+    int q = 0;
+    while (q + 1 < S.nsrc && kb >= a.srcs[S.src[q + 1]].kb0) ++q;
+    return q;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)a.n_half * (uint32_t)a.half_cols * 128u;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ks = item % a.KS;
-        const int kb0 = ks * a.kb_per_split, kb1 = min(a.num_kb, kb0 + a.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty + stage, phase ^ 1);
+      uint32_t c = 0;                                     // k-blocks issued by this CTA so far: stage = c & 1
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int sd, mt, kbA, kbB;
+        decode(item, sd, mt, kbA, kbB);
+        const B2Side& S = a.sides[sd];
+        for (int kb = kbA; kb < kbB; ++kb, ++c) {
+          const int stage = c & 1;
+          const int ji = S.src[which_src(S, kb)];
+          mbar_wait(empty + stage, ((c >> 1) & 1u) ^ 1u);
           uint8_t* sb = smem + (size_t)stage * stage_bytes + B2_A_BYTES;
-          if (a.debug & 4) { mbar_arrive(b_full + stage); }
-          else {
+          if (a.debug & 4) { mbar_arrive(b_full + stage); continue; }
           mbar_expect_tx(b_full + stage, tx_bytes);
           for (int h = 0; h < a.n_half; ++h)
-            tma_load_2d(sb + h * B2_B_HALF_BYTES, &tms, b_full + stage, kb * B2_BK, h * 256);
-          }
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            tma_load_2d(sb + h * B2_B_HALF_BYTES, &a.tms[ji], b_full + stage, (kb - a.srcs[ji].kb0) * B2_BK, h * 256);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(B2_BM, a.half_cols);
-      int stage = 0; uint32_t phase = 0;
+      uint32_t c = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int ks = item % a.KS;
-        const int kb0 = ks * a.kb_per_split, kb1 = min(a.num_kb, kb0 + a.kb_per_split);
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+        int sd, mt, kbA, kbB;
+        decode(item, sd, mt, kbA, kbB);
         mbar_wait(acc_empty, (uint32_t)(it & 1) ^ 1);
         tc_fence_after();
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(a_full + stage, phase);
-          mbar_wait(b_full + stage, phase);
+        for (int kb = kbA; kb < kbB; ++kb, ++c) {
+          const int stage = c & 1;
+          const uint32_t par = (c >> 1) & 1u;
+          mbar_wait(a_full + stage, par);
+          mbar_wait(b_full + stage, par);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
@@ -118,82 +155,91 @@ maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs 
 #pragma unroll
             for (int k = 0; k < B2_BK / 16; ++k)
               umma_bf16(tmem_base + (uint32_t)(h * 256), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                        (kb > kb0 || k > 0) ? 1u : 0u);
+                        (kb > kbA || k > 0) ? 1u : 0u);
           }
           umma_commit(empty + stage);
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(acc_full);
       }
     }
   } else {
-    // ===================== generators + epilogue (warps 2..5) =====================
-    const int q = warp & 3;
+    // ===================== generator / epilogue groups (warps 2..5 = group 0 -> stage 0, 6..9 = group 1 -> stage 1)
+    // Each group builds every other k-block (its own stage), so two routing tiles are under construction at any time
+    // and the tensor core is fed at twice the single-group rate.
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;                            // TMEM lane quarter
     const int m = q * 32 + lane;                       // row of the output tile / TMEM lane
-    const int et = threadIdx.x - 64;                   // 0..127
-    int stage = 0; uint32_t phase = 0;
+    const int et = (threadIdx.x - 64) & (B2_GROUP - 1);   // 0..127 within the group
+    const int j = et & 63, jh = et >> 6;               // source-token side: column, and which half of the out samples
+    uint8_t* const sa = smem + (size_t)grp * stage_bytes;
+    uint32_t c = 0;
     int it = 0;
-    const int No = a.No, Ns = a.Ns;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int mt = item / a.KS, ks = item % a.KS;
-      const int kb0 = ks * a.kb_per_split, kb1 = min(a.num_kb, kb0 + a.kb_per_split);
+    struct Pre { int sv[8]; float gv[8]; int ov[8]; float hv[8]; float cw; };
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+      int sd, mt, kbA, kbB;
+      decode(item, sd, mt, kbA, kbB);
+      const B2Side& S = a.sides[sd];
+      const int No = S.No;
       const int row0 = mt * B2_BM;
       const int g = row0 + m;                          // global output token
-      const bool valid = g < a.out_tokens;
+      const bool valid = g < S.out_tokens;
       const int ro = valid ? g / No : 0, o = valid ? g - ro * No : 0;   // (sample, token) of the output row
-      const float coefo = valid ? a.wO[g] * a.scale : 0.f;
-      const int ro_lo = row0 / No, ro_hi = min(a.Ro - 1, (row0 + B2_BM - 1) / No);   // out samples touching this tile
-      // Routing data (arg-max bytes, upstream gradients) of a k-block is loaded one k-block AHEAD into registers: the
-      // dependent global loads would otherwise sit on the generator's critical path (2 stages cannot hide them).
-      // Slots cover 8 partner samples per row / 8 out samples per column thread; longer ranges (tiny Ns / No) take
-      // the direct-load remainder loops below.
-      const int j = et & 63, jh = et >> 6;               // scatter side: source column and which half of the out samples
-      const uint8_t* stO = a.starO + (int64_t)ro * a.aO_o + o;
-      const float* gpO = a.dH + (int64_t)ro * a.g_o;
-      struct Pre { int sv[8]; float gv[8]; int ov[8]; float hv[8]; float cw; };
+      const float wo = valid ? S.wO[g] : 0.f;
+      const int ro_lo = row0 / No, ro_hi = min(S.Ro - 1, (row0 + B2_BM - 1) / No);   // out samples touching this tile
+      // Routing data (arg-max bytes, upstream gradients) of a k-block is loaded into registers while the group's
+      // previous k-block is being built.  Slots cover 8 partner samples per row / 8 out samples per column thread;
+      // longer ranges (tiny Ns / No) take the direct-load remainder loops below.
       auto load_pre = [&](int kb, Pre& P) {
-        const int t0 = kb * B2_BK;
-        const int rs_lo = t0 / Ns, rs_hi = min(a.Rs - 1, (t0 + B2_BK - 1) / Ns);
+        const B2Src& J = a.srcs[S.src[which_src(S, kb)]];
+        const int Ns = J.Ns;
+        const int t0 = (kb - J.kb0) * B2_BK;
+        const int rs_lo = t0 / Ns, rs_hi = min(J.Rs - 1, (t0 + B2_BK - 1) / Ns);
+        const uint8_t* stO = J.starO + (int64_t)ro * J.aO_o + o;
+        const float* gpO = J.dH + (int64_t)ro * J.g_o;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rs = min(rs_lo + i, rs_hi);
-          P.sv[i] = (coefo != 0.f) ? (int)stO[(int64_t)rs * a.aO_s] : 0;
-          P.gv[i] = (coefo != 0.f) ? gpO[(int64_t)rs * a.g_s] : 0.f;
+          P.sv[i] = (wo != 0.f) ? (int)stO[(int64_t)rs * J.aO_s] : 0;
+          P.gv[i] = (wo != 0.f) ? gpO[(int64_t)rs * J.g_s] : 0.f;
         }
-        const int tsrc = min(t0 + j, a.src_tokens - 1);
+        const int tsrc = min(t0 + j, J.src_tokens - 1);
         const int rs = tsrc / Ns, sidx = tsrc - rs * Ns;
-        P.cw = (t0 + j < a.src_tokens) ? a.wS[tsrc] * a.scale : 0.f;
-        const uint8_t* st = a.starS + (int64_t)rs * a.aS_s + sidx;
-        const float* gp = a.dH + (int64_t)rs * a.g_s;
+        P.cw = (t0 + j < J.src_tokens) ? J.wS[tsrc] * J.scale : 0.f;
+        const uint8_t* st = J.starS + (int64_t)rs * J.aS_s + sidx;
+        const float* gp = J.dH + (int64_t)rs * J.g_s;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int r2 = min(ro_lo + jh + 2 * i, ro_hi);
-          P.ov[i] = (P.cw != 0.f) ? (int)st[(int64_t)r2 * a.aS_o] : 0;
-          P.hv[i] = (P.cw != 0.f) ? gp[(int64_t)r2 * a.g_o] : 0.f;
+          P.ov[i] = (P.cw != 0.f) ? (int)st[(int64_t)r2 * J.aS_o] : 0;
+          P.hv[i] = (P.cw != 0.f) ? gp[(int64_t)r2 * J.g_o] : 0.f;
         }
       };
+      // this group's k-blocks of the item: those whose CTA-wide counter has parity grp
+      int kb = kbA + (int)((grp - (int)c) & 1);
+      uint32_t cc = c + (uint32_t)(kb - kbA);
       Pre cur, nxt;
-      if (kb0 < kb1) load_pre(kb0, cur);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        if (kb + 1 < kb1) load_pre(kb + 1, nxt);
-        mbar_wait(empty + stage, phase ^ 1);
-        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+      if (kb < kbB) load_pre(kb, cur);
+      for (; kb < kbB; kb += 2, cc += 2) {
+        if (kb + 2 < kbB) load_pre(kb + 2, nxt);
+        mbar_wait(empty + grp, ((cc >> 1) & 1u) ^ 1u);
         if (a.debug & 2) {
           fence_proxy_async();
-          mbar_arrive(a_full + stage);
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          mbar_arrive(a_full + grp);
           continue;
         }
+        const B2Src& J = a.srcs[S.src[which_src(S, kb)]];
+        const int Ns = J.Ns;
+        const float coefo = wo * J.scale;
         // cooperative zero fill of this warp's 32 rows (512 contiguous bytes per store instruction)
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<uint4*>(sa + (q * 32 + i * 4) * 128 + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
-        const int t0 = kb * B2_BK;
+        const int t0 = (kb - J.kb0) * B2_BK;
         // (1) out-token side: row m, one entry per source sample overlapping this k-block
         if (coefo != 0.f) {
           uint8_t* srow = sa + m * 128;
-          const int rs_lo = t0 / Ns, rs_hi = min(a.Rs - 1, (t0 + B2_BK - 1) / Ns);
+          const int rs_lo = t0 / Ns, rs_hi = min(J.Rs - 1, (t0 + B2_BK - 1) / Ns);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rs = rs_lo + i;
@@ -202,14 +248,19 @@ maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs 
               *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
                   __float2bfloat16_rn(cur.gv[i] * coefo);
           }
-          for (int rs = rs_lo + 8; rs <= rs_hi; ++rs) {          // remainder (Ns < 10 only)
-            const int t = rs * Ns + (int)stO[(int64_t)rs * a.aO_s] - t0;
-            if (t >= 0 && t < B2_BK)
-              *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
-                  __float2bfloat16_rn(gpO[(int64_t)rs * a.g_s] * coefo);
+          if (rs_lo + 8 <= rs_hi) {                                // remainder (Ns < 10 only)
+            const uint8_t* stO = J.starO + (int64_t)ro * J.aO_o + o;
+            const float* gpO = J.dH + (int64_t)ro * J.g_o;
+            for (int rs = rs_lo + 8; rs <= rs_hi; ++rs) {
+              const int t = rs * Ns + (int)stO[(int64_t)rs * J.aO_s] - t0;
+              if (t >= 0 && t < B2_BK)
+                *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
+                    __float2bfloat16_rn(gpO[(int64_t)rs * J.g_s] * coefo);
+            }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");         // rows zeroed and side-(1) entries in place
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // rows zeroed and side-(1) entries in place
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         // (2) source-token side: column j, one entry per out sample of this tile; lands in row (ro, o*) and is
         //     ADDED to whatever side (1) put there (mutual arg-max pairs)
         if (cur.cw != 0.f) {
@@ -229,32 +280,33 @@ maxsim2_bwd_tc_kernel(const __grid_constant__ CUtensorMap tms, const Tc2BwdArgs 
           if (ro_lo + jh + 16 <= ro_hi) {                        // remainder (No < 10 only)
             const int tsrc = t0 + j;
             const int rs = tsrc / Ns, sidx = tsrc - rs * Ns;
-            const uint8_t* st = a.starS + (int64_t)rs * a.aS_s + sidx;
-            const float* gp = a.dH + (int64_t)rs * a.g_s;
+            const uint8_t* st = J.starS + (int64_t)rs * J.aS_s + sidx;
+            const float* gp = J.dH + (int64_t)rs * J.g_s;
             for (int r2 = ro_lo + jh + 16; r2 <= ro_hi; r2 += 2)
-              put(r2, (int)st[(int64_t)r2 * a.aS_o], gp[(int64_t)r2 * a.g_o]);
+              put(r2, (int)st[(int64_t)r2 * J.aS_o], gp[(int64_t)r2 * J.g_o]);
           }
         }
         fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core
-        mbar_arrive(a_full + stage);
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        mbar_arrive(a_full + grp);
         cur = nxt;
       }
-      // ---- epilogue: TMEM -> red.global.add ----
+      c += (uint32_t)(kbB - kbA);
+      // ---- epilogue: TMEM -> red.global.add; group 0 takes the lower half of the d columns, group 1 the upper
       mbar_wait(acc_full, (uint32_t)(it & 1));
       tc_fence_after();
-      if (kb1 > kb0) {
+      {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* drow = a.dst + (int64_t)g * a.D;
-        for (int c = 0; c < a.D; c += 16) {
+        float* drow = S.dst + (int64_t)g * a.D;
+        const int c_lo = grp * (a.D / 2), c_hi = c_lo + a.D / 2;
+        for (int cidx = c_lo; cidx < c_hi; cidx += 16) {
           uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)((c >> 8) * 256 + (c & 255)), v);
+          tmem_ld16(taddr + (uint32_t)cidx, v);
           tmem_ld_wait();
           reg_fence<16>(v);
           if (valid && !(a.debug & 1)) {
 #pragma unroll
             for (int e = 0; e < 16; e += 4)
-              red_add_v4_(drow + c + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+              red_add_v4_(drow + cidx + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
                           __uint_as_float(v[e + 3]));
           }
         }
@@ -317,61 +369,96 @@ maxsim2_bwd_w_kernel(const float* __restrict__ pmax_x, const float* __restrict__
 
 using namespace nr;
 
-/* side 0: gradient w.r.t. the X tokens (srcT = transposed Y tokens), side 1: w.r.t. the Y tokens (srcT = X). */
-extern "C" int nr_maxsim2_bwd(int side, const void* srcT, int64_t src_ld, const float* wx, const float* wy,
-                              const uint8_t* ystar, const uint8_t* xstar, const float* dH, int64_t dh_sr,
-                              int64_t dh_sc, float dh_scale, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, int64_t d,
-                              float* dst, void* stream) {
-  NR_CHECK_ARG(srcT && wx && wy && ystar && xstar && dH && dst, "nr_maxsim2_bwd: null pointer");
-  NR_CHECK_ARG(Rx > 0 && Ry > 0 && Nx >= 1 && Nx <= NR_MAX_TOKENS && Ny >= 1 && Ny <= NR_MAX_TOKENS,
-               "nr_maxsim2_bwd: bad sizes Rx=%lld Nx=%lld Ry=%lld Ny=%lld", (long long)Rx, (long long)Nx, (long long)Ry,
-               (long long)Ny);
-  NR_CHECK_ARG(d % 16 == 0 && d <= 512 && (d <= 256 || d == 512),
-               "nr_maxsim2_bwd: d=%lld unsupported (multiple of 16 up to 256, or 512)", (long long)d);
-  NR_CHECK_ARG(src_ld % 8 == 0 && ((uintptr_t)srcT & 15) == 0, "nr_maxsim2_bwd: srcT must be 16B aligned, ld %% 8 == 0");
-  Tc2BwdArgs a{};
-  if (side == 0) {
-    a.wO = wx; a.wS = wy;
-    a.starO = ystar; a.aO_o = Ry * Nx; a.aO_s = Nx;
-    a.starS = xstar; a.aS_o = Ry * Ny; a.aS_s = Ny;
-    a.g_o = dh_sr; a.g_s = dh_sc;
-    a.Ro = (int)Rx; a.No = (int)Nx; a.Rs = (int)Ry; a.Ns = (int)Ny;
-  } else {
-    a.wO = wy; a.wS = wx;
-    a.starO = xstar; a.aO_o = Ny; a.aO_s = Ry * Ny;
-    a.starS = ystar; a.aS_o = Nx; a.aS_s = Ry * Nx;
-    a.g_o = dh_sc; a.g_s = dh_sr;
-    a.Ro = (int)Ry; a.No = (int)Ny; a.Rs = (int)Rx; a.Ns = (int)Nx;
-  }
-  a.dH = dH; a.scale = dh_scale; a.D = (int)d; a.dst = dst;
-  a.out_tokens = a.Ro * a.No;
-  a.src_tokens = a.Rs * a.Ns;
-  a.n_mt = (a.out_tokens + B2_BM - 1) / B2_BM;
-  a.num_kb = (a.src_tokens + B2_BK - 1) / B2_BK;
+/* All token-gradient contractions of a step in one launch; jobs that share `dst` are accumulated in one pass. */
+extern "C" int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int njobs, int64_t Nx, int64_t Ny, int64_t d,
+                              void* stream) {
+  NR_CHECK_ARG(jobs && njobs >= 1 && njobs <= B2_MAX_JOBS, "nr_maxsim2_bwd: 1..%d jobs per launch (got %d)",
+               B2_MAX_JOBS, njobs);
+  NR_CHECK_ARG(Nx >= 1 && Nx <= NR_MAX_TOKENS && Ny >= 1 && Ny <= NR_MAX_TOKENS, "nr_maxsim2_bwd: bad Nx=%lld Ny=%lld",
+               (long long)Nx, (long long)Ny);
+  NR_CHECK_ARG(d % 32 == 0 && d <= 512 && (d <= 256 || d == 512),
+               "nr_maxsim2_bwd: d=%lld unsupported (multiple of 32 up to 256, or 512)", (long long)d);
+  B2Args a{};
+  a.D = (int)d;
   a.n_half = d > 256 ? 2 : 1;
   a.half_cols = d > 256 ? 256 : (int)d;
+  if (const char* dbg = getenv("NR_B2_DEBUG")) a.debug = atoi(dbg);
+  for (int i = 0; i < njobs; ++i) {
+    const nr_maxsim2_bwd_job& jb = jobs[i];
+    NR_CHECK_ARG(jb.srcT && jb.wx && jb.wy && jb.ystar && jb.xstar && jb.dH && jb.dst && jb.Rx > 0 && jb.Ry > 0 &&
+                     (jb.side == 0 || jb.side == 1),
+                 "nr_maxsim2_bwd: job %d has a null pointer, an empty side or a bad side flag", i);
+    NR_CHECK_ARG(jb.src_ld % 8 == 0 && ((uintptr_t)jb.srcT & 15) == 0 && ((uintptr_t)jb.dst & 15) == 0,
+                 "nr_maxsim2_bwd: job %d: srcT / dst must be 16B aligned, ld %% 8 == 0", i);
+    B2Src& J = a.srcs[i];
+    const float* wO;
+    int Ro, No;
+    const int64_t Rx = jb.Rx, Ry = jb.Ry;
+    if (jb.side == 0) {
+      wO = jb.wx; J.wS = jb.wy;
+      J.starO = jb.ystar; J.aO_o = Ry * Nx; J.aO_s = Nx;
+      J.starS = jb.xstar; J.aS_o = Ry * Ny; J.aS_s = Ny;
+      J.g_o = jb.dh_sr; J.g_s = jb.dh_sc;
+      Ro = (int)Rx; No = (int)Nx; J.Rs = (int)Ry; J.Ns = (int)Ny;
+    } else {
+      wO = jb.wy; J.wS = jb.wx;
+      J.starO = jb.xstar; J.aO_o = Ny; J.aO_s = Ry * Ny;
+      J.starS = jb.ystar; J.aS_o = Nx; J.aS_s = Ry * Nx;
+      J.g_o = jb.dh_sc; J.g_s = jb.dh_sr;
+      Ro = (int)Ry; No = (int)Ny; J.Rs = (int)Rx; J.Ns = (int)Nx;
+    }
+    J.dH = jb.dH; J.scale = jb.dh_scale;
+    J.src_tokens = J.Rs * J.Ns;
+    J.num_kb = (J.src_tokens + B2_BK - 1) / B2_BK;
+    if (int e = make_tmap_srcT(&a.tms[i], jb.srcT, d, J.src_tokens, jb.src_ld, a.half_cols)) return e;
+    // side = jobs with the same output rows
+    int sd = -1;
+    for (int s = 0; s < a.nsides; ++s)
+      if (a.sides[s].dst == jb.dst && a.sides[s].Ro == Ro && a.sides[s].No == No && a.sides[s].wO == wO) sd = s;
+    if (sd < 0) {
+      NR_CHECK_ARG(a.nsides < B2_MAX_SIDES, "nr_maxsim2_bwd: more than %d distinct outputs in one launch", B2_MAX_SIDES);
+      sd = a.nsides++;
+      B2Side& S = a.sides[sd];
+      S.wO = wO; S.dst = jb.dst; S.Ro = Ro; S.No = No; S.out_tokens = Ro * No;
+      S.n_mt = (S.out_tokens + B2_BM - 1) / B2_BM;
+    }
+    B2Side& S = a.sides[sd];
+    NR_CHECK_ARG(S.nsrc < B2_MAX_SRC, "nr_maxsim2_bwd: more than %d sources for one output", B2_MAX_SRC);
+    J.kb0 = S.kb_total;
+    S.src[S.nsrc++] = i;
+    S.kb_total += J.num_kb;
+  }
   int dev = 0, sms = 0;
   NR_CUDA(cudaGetDevice(&dev));
   NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  int ks = (sms + a.n_mt / 2) / a.n_mt;           // split-K so that n_mt*KS ~ one wave
-  if (ks < 1) ks = 1;
-  if (ks > a.num_kb) ks = a.num_kb;
-  a.kb_per_split = (a.num_kb + ks - 1) / ks;
-  a.KS = (a.num_kb + a.kb_per_split - 1) / a.kb_per_split;
-  a.stages = 2;
-  if (const char* dbg = getenv("NR_B2_DEBUG")) a.debug = atoi(dbg);
-  if (const char* ksv = getenv("NR_B2_KS")) {
-    int k2 = atoi(ksv);
-    if (k2 >= 1 && k2 <= a.num_kb) { a.kb_per_split = (a.num_kb + k2 - 1) / k2; a.KS = (a.num_kb + a.kb_per_split - 1) / a.kb_per_split; }
+  // split-K per side so that all items have about the same number of k-blocks and fit one wave
+  int64_t work = 0;
+  int min_items = 0;
+  for (int s = 0; s < a.nsides; ++s) { work += (int64_t)a.sides[s].n_mt * a.sides[s].kb_total; min_items += a.sides[s].n_mt; }
+  int per = (int)((work + sms - 1) / sms);
+  if (per < 1) per = 1;
+  if (const char* pv = getenv("NR_B2_PER")) { int p2 = atoi(pv); if (p2 >= 1) per = p2; }
+  for (;;) {
+    int items = 0;
+    for (int s = 0; s < a.nsides; ++s) {
+      B2Side& S = a.sides[s];
+      int ks = (S.kb_total + per / 2) / per;
+      if (ks < 1) ks = 1;
+      if (ks > S.kb_total) ks = S.kb_total;
+      S.kb_per_split = (S.kb_total + ks - 1) / ks;
+      S.KS = (S.kb_total + S.kb_per_split - 1) / S.kb_per_split;
+      S.item0 = items;
+      items += S.n_mt * S.KS;
+    }
+    a.n_items = items;
+    if (items <= sms || min_items > sms || getenv("NR_B2_PER")) break;
+    ++per;
   }
   const size_t stage_bytes = (size_t)B2_A_BYTES + (size_t)a.n_half * B2_B_HALF_BYTES;
-  const size_t smem = a.stages * stage_bytes + 256 + 1024;
-  CUtensorMap tms;
-  if (int e = make_tmap_srcT(&tms, srcT, d, a.src_tokens, src_ld, a.half_cols)) return e;
-  const int items = a.n_mt * a.KS;
-  const int grid = items < sms ? items : sms;
+  const size_t smem = 2 * stage_bytes + 256 + 1024;
+  const int grid = a.n_items < sms ? a.n_items : sms;
   NR_CUDA(cudaFuncSetAttribute(maxsim2_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  maxsim2_bwd_tc_kernel<<<grid, B2_THREADS, smem, (cudaStream_t)stream>>>(tms, a);
+  maxsim2_bwd_tc_kernel<<<grid, B2_THREADS, smem, (cudaStream_t)stream>>>(a);
   NR_CHECK_LAUNCH("nr_maxsim2_bwd");
   return 0;
 }

@@ -260,16 +260,18 @@ class HeadFunction(torch.autograd.Function):
                 _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows,
                       _p(dgv), 1, _p(dmean[1]), _stream(), launches=2)
             if ctx.fusedk:
-                # one routing matrix per pair, applied from either side: 4 contraction + 3 weight launches
+                # one routing matrix per pair, applied from either side; ALL contractions in one launch (the text
+                # gradient accumulates over [video ; bank-video] sources, the video gradient over [text ; bank-text])
                 sc = 0.5 / M
+                jobs = []
                 if need[0]:
-                    ops.maxsim2_bwd(0, V, tw, vw, y1, y2, dS, B, 1, 0.5, B, nt, B, nv, d, dtn)
-                    ops.maxsim2_bwd(0, MV, tw, vw_mb, yA, yB, dc[0], 1, 0, sc, B, nt, M, nv, d, dtn)
-                with fj.on(0):
-                    torch.cuda.current_stream().wait_event(ev_dS)
-                    if need[1]:
-                        ops.maxsim2_bwd(1, T, tw, vw, y1, y2, dS, B, 1, 0.5, B, nt, B, nv, d, dvn)
-                        ops.maxsim2_bwd(1, MT, tw_mb, vw, yC, yD, dc[1], 0, 1, sc, M, nt, B, nv, d, dvn)
+                    jobs += [(0, V, tw, vw, y1, y2, dS, B, 1, 0.5, B, B, dtn),
+                             (0, MV, tw, vw_mb, yA, yB, dc[0], 1, 0, sc, B, M, dtn)]
+                if need[1]:
+                    jobs += [(1, T, tw, vw, y1, y2, dS, B, 1, 0.5, B, B, dvn),
+                             (1, MT, tw_mb, vw, yC, yD, dc[1], 0, 1, sc, M, B, dvn)]
+                if jobs:
+                    ops.maxsim2_bwd_multi(jobs, nt, nv, d)
                 with fj.on(2):
                     torch.cuda.current_stream().wait_event(ev_dS)
                     if need[4] or need[5]:

@@ -285,12 +285,28 @@ def maxsim2_fwd(problems, keep=True):
     return saved
 
 
+def maxsim2_bwd_multi(jobs, nx, ny, d):
+    """All token-gradient contractions of a step in ONE launch (nr_maxsim2_bwd).  jobs: tuples
+    (side, src Prepared, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, ry, dst); side 0: dst = X-token gradient
+    (src = the Y tokens), side 1: dst = Y-token gradient (src = the X tokens).  Jobs with the same dst are
+    accumulated in one pass."""
+    arr = (_lib.MaxSim2BwdJob * len(jobs))()
+    keep = []
+    for i, (side, src, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, ry, dst) in enumerate(jobs):
+        s, ld = src.bwd_source(NR_PREC_BF16)
+        keep.append(s)
+        a = arr[i]
+        a.side, a.srcT, a.src_ld = side, s.data_ptr(), ld
+        a.wx, a.wy, a.ystar, a.xstar = wx.data_ptr(), wy.data_ptr(), ystar.data_ptr(), xstar.data_ptr()
+        a.dH, a.dh_sr, a.dh_sc, a.dh_scale = g.data_ptr(), g_sr, g_sc, float(scale)
+        a.Rx, a.Ry, a.dst = rx, ry, dst.data_ptr()
+    _call("nr_maxsim2_bwd", ctypes.cast(arr, ctypes.c_void_p), len(jobs), nx, ny, d, _stream())
+
+
 def maxsim2_bwd(side, src, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, nx, ry, ny, d, dst):
     """dst += (routing matrix of the fused max-sim, or its transpose) x the tokens of `src` (a Prepared whose
     transposed bf16 copy is the staged operand); side 0: dst = X-token gradient, side 1: Y-token gradient."""
-    s, ld = src.bwd_source(NR_PREC_BF16)
-    _call("nr_maxsim2_bwd", side, _p(s), ld, _p(wx), _p(wy), _p(ystar), _p(xstar), _p(g), g_sr, g_sc, scale, rx, nx, ry,
-          ny, d, _p(dst), _stream())
+    maxsim2_bwd_multi([(side, src, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, ry, dst)], nx, ny, d)
 
 
 def maxsim2_bwd_w(pmax_x, pmax_y, g, g_sr, g_sc, scale, rx, nx, ry, ny, dwx, dwy):

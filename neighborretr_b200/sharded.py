@@ -223,18 +223,19 @@ class ShardedHeadFunction(torch.autograd.Function):
         mvs, mvld = MV.bwd_source(bprec); mts, mtld = MT.bwd_source(bprec)
         if ctx.fusedk:
             sc = 0.5 / M
-            # S_row = S(text_l, video): g = dS_row [b,B]
-            ops.maxsim2_bwd(0, V, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, nt, B, nv, d, dtn_l)
-            ops.maxsim2_bwd(1, Tl, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, nt, B, nv, d, dvn)
+            # S_row = S(text_l, video): g = dS_row [b,B];  S_col[v_l, a] = S(text, video_l)[a, v_l]: g(rx=a, ry=v_l) =
+            # dS_col[v_l, a];  bank pairs of this rank's samples: g = dc_l[.]/M broadcast over the bank rows (stride 0).
+            # ONE launch; jobs with the same destination share an accumulator pass.
+            ops.maxsim2_bwd_multi([
+                (0, V, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, B, dtn_l),
+                (0, MV, tw_l, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
+                (1, Tl, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, B, dvn),
+                (0, Vl, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, b, dtn),
+                (1, T, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, b, dvn_l),
+                (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
             ops.maxsim2_bwd_w(p1, p2, dS_row, B, 1, 0.5, b, nt, B, nv, dtw_l, dvw)
-            # S_col[v_l, a] = S(text, video_l)[a, v_l]: g(rx=a, ry=v_l) = dS_col[v_l, a]
-            ops.maxsim2_bwd(0, Vl, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, nt, b, nv, d, dtn)
-            ops.maxsim2_bwd(1, T, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, nt, b, nv, d, dvn_l)
             ops.maxsim2_bwd_w(p3, p4, dS_col, 1, B, 0.5, B, nt, b, nv, dtw, dvw_l)
-            # bank pairs of this rank's samples: g = dc_l[.]/M broadcast over the bank rows (stride 0)
-            ops.maxsim2_bwd(0, MV, tw_l, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, nt, M, nv, d, dtn_l)
             ops.maxsim2_bwd_w(pA, pB, dc_l[0], 1, 0, sc, b, nt, M, nv, dtw_l, dvw_mb)
-            ops.maxsim2_bwd(1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, nt, b, nv, d, dvn_l)
             ops.maxsim2_bwd_w(pC, pD, dc_l[1], 0, 1, sc, M, nt, b, nv, dtw_mb, dvw_l)
         else:
             X, Y, Wg = "nr_maxsim_bwd_x", "nr_maxsim_bwd_y", "nr_maxsim_bwd_w"

@@ -1,4 +1,5 @@
-"""Launch only the fused backward contraction (nr_maxsim2_bwd) for one (X, Y) pair: `side rx nx ry ny`."""
+"""Launch only the fused backward contraction (nr_maxsim2_bwd) for one (X, Y) pair: `side rx nx ry ny`
+(tools/b2_step.py runs the four contractions of a whole step in one launch)."""
 import os
 import sys
 
