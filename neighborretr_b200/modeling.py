@@ -223,22 +223,36 @@ class HeadMixin:
     def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats):
         """W > 1: row-block sharded head (sharded.py) on the LOCAL batch; gathers happen inside.
         Returns (5 losses, gathered (text, video, text_mask, video_mask))."""
-        from .sharded import SumGradsAcrossRanks, sharded_head
+        from .fused import head_hparams
+        from .sharded import ShardedHeadFunction, ShardedPrologue, SumGradsAcrossRanks
         cfg = self.config
         lowp = self._head_precision() == "bf16"
         # each rank differentiates only its share of the loss: sum the head-parameter gradients over ranks
         # (one flat all_reduce in backward) so that every rank holds the full gradient, as in the reference
         ps = SumGradsAcrossRanks.apply(*ops.mlp_params(self.text_weight_fc), *ops.mlp_params(self.video_weight_fc))
         tmlp, vmlp = ps[:4], ps[4:]
-        tw, tw_mb = ops.token_weights(tmlp, text_feat, text_mask, lowp, self.mb_feat_t, self.mb_mask_t)
-        vw, vw_mb = ops.token_weights(vmlp, video_feat, video_mask, lowp, self.mb_feat_v, self.mb_mask_v)
         gtf, gvf = global_feats
-        out5, nbr, text_all, video_all, tm_all, vm_all = sharded_head(
+        hp = head_hparams(cfg.centrality_scale, cfg.beta, cfg.num_neighbors, cfg.temperature, cfg.uniform_weight,
+                          cfg.neighbor_weight, cfg.kl_weight, self._head_precision(), self._head_bwd_precision())
+        # gathers, token preparation, centrality weights, global similarity + Sinkhorn: forked next to the MLPs
+        pro = ShardedPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, self.mb_feat_t, self.mb_feat_v,
+                              self.mb_mask_t, self.mb_mask_v, hp)
+        with ops.ForkJoin(4) as fj:
+            main = fj.main
+            tw, tw_mb = ops.token_weights(tmlp, text_feat, text_mask, lowp, self.mb_feat_t, self.mb_mask_t)
+            with fj.on(0):
+                vw, vw_mb = ops.token_weights(vmlp, video_feat, video_mask, lowp, self.mb_feat_v, self.mb_mask_v)
+                vw.record_stream(main)
+            with fj.on(1):
+                pro.run_text_side()
+            with fj.on(2):
+                pro.run_video_side()
+            with fj.on(3):
+                pro.run_global()
+            pro.global_done = fj.detach(3)
+        out5, nbr, text_all, video_all, tm_all, vm_all = ShardedHeadFunction.apply(
             text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, self.clip.logit_scale.exp(), text_mask, video_mask,
-            self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v, centrality_scale=cfg.centrality_scale,
-            beta=cfg.beta, num_neighbors=cfg.num_neighbors, temperature=cfg.temperature,
-            uniform_weight=cfg.uniform_weight, neighbor_weight=cfg.neighbor_weight, kl_weight=cfg.kl_weight,
-            precision=self._head_precision(), bwd_precision=self._head_bwd_precision())
+            self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v, hp, pro)
         self.last_neighbors = (nbr[0], nbr[1])
         return tuple(out5.unbind(0)), (text_all, video_all, tm_all, vm_all)
 

@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 from . import ops
 from ._lib import NR_NSAVE, NR_PREC_BF16
-from .fused import ALL_LOSSES, _combine_matrix, _fwd_dir
+from .fused import ALL_LOSSES, _combine_matrix, _fwd_dir, head_hparams
 from .ops import Prepared, _call, _f32c, _mask, _p, _req_cuda, _stream
 
 
@@ -73,43 +73,122 @@ class SumGradsAcrossRanks(torch.autograd.Function):
         return tuple(out)
 
 
+class ShardedPrologue:
+    """Everything of a sharded step that does not depend on the token-weight MLPs: the feature / mask / global-feature
+    gathers, token preparation of the gathered batch and of the bank, centrality weights of the local rows, the
+    replicated global similarity and its Sinkhorn duals.  The constructor allocates (and gathers the masks, which
+    the preparation needs); the three run_* groups are independent and are enqueued on forked streams next to the
+    MLP evaluations (modeling._sharded_losses) — the NCCL collectives overlap them."""
+
+    def __init__(self, text_l, video_l, gt_l, gv_l, tm_l, vm_l, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp):
+        cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
+        _req_cuda(text_l, video_l, gt_l, gv_l, mb_feat_t, mb_feat_v)
+        self.hp = hp
+        self.W, self.r = W, r = dist.get_world_size(), dist.get_rank()
+        dev = text_l.device
+        self.b = b = text_l.shape[0]
+        self.B, self.lo = B, lo = W * b, r * b
+        nt, nv, d = text_l.shape[1], video_l.shape[1], text_l.shape[2]
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.text_l, self.video_l = _f32c(text_l.detach()), _f32c(video_l.detach())
+        self.text = torch.empty(B, nt, d, **f32)
+        self.video = torch.empty(B, nv, d, **f32)
+        self.g_l = (_f32c(gt_l.detach()).reshape(b, d).contiguous(), _f32c(gv_l.detach()).reshape(b, d).contiguous())
+        self.gl = torch.stack(self.g_l, 1)                                                    # [b,2,d]
+        self.gall = torch.empty(B, 2, d, **f32)
+        self.g2, self.v2 = torch.empty(B, d, **f32), torch.empty(B, d, **f32)
+        # ---- exchange 0: masks (the operand preparation needs them)
+        masks = _gather(torch.cat([_mask(tm_l), _mask(vm_l)], dim=1))                       # [B, Nt+Nv] int64
+        self.tm, self.vm = masks[:, :nt].contiguous(), masks[:, nt:].contiguous()
+        self.mtm, self.mvm = _mask(mb_mask_t), _mask(mb_mask_v)
+        self.bf = bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
+        self.fusedk = fk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
+                            and ops.maxsim2_supported(nt, nv, d))
+        self.T = Prepared(self.text, bf16=bf, colsum=True, mask=self.tm if fk else None, defer=True)
+        self.V = Prepared(self.video, bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True)
+        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True)
+        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True)
+        self.Tl, self.Vl = self.T.block(lo, b), self.V.block(lo, b)
+        self.GG = torch.empty(2, B, B, **f32)              # [G ; G^T], replicated
+        self.duals = torch.empty(4, B, **f32)
+        self.lib_ws, self.nws = ops.sinkhorn_workspace(B, dev)
+        self.mean = torch.empty(2, d, **f32); self.gn = torch.empty(2, b, d, **f32)
+        self.ginv = torch.empty(2, b, **f32); self.w = torch.empty(2, b, **f32)
+        self.global_done = None
+        if bf:
+            for P in (self.T, self.V, self.MT, self.MV):
+                P.alloc_transposed()
+
+    def _centrality(self, P, i):
+        b, d, cs = self.b, self.T.d, self.hp[0]
+        _call("nr_centrality_fwd", _p(P.partials), P.partials.shape[0], P.rows, _p(self.g_l[i]), b, d, cs,
+              _p(self.mean[i]), _p(self.gn[i]), _p(self.ginv[i]), _p(self.w[i]), _stream(), launches=2)
+
+    def run_text_side(self):
+        bprec = self.hp[9]
+        dist.all_gather_into_tensor(self.text, self.text_l)          # exchange 1a
+        self.MT.run()
+        self.T.run()
+        if self.bf:
+            self.MT.bwd_source(bprec); self.T.bwd_source(bprec)
+        self._centrality(self.T, 0)
+
+    def run_video_side(self):
+        bprec = self.hp[9]
+        dist.all_gather_into_tensor(self.video, self.video_l)        # exchange 1b
+        self.MV.run()
+        self.V.run()
+        if self.bf:
+            self.MV.bwd_source(bprec); self.V.bwd_source(bprec)
+        self._centrality(self.V, 1)
+
+    def run_global(self):
+        B, iters = self.B, int(self.hp[4])
+        dist.all_gather_into_tensor(self.gall, self.gl)              # exchange 1c
+        self.g2.copy_(self.gall[:, 0]); self.v2.copy_(self.gall[:, 1])
+        _call("nr_gram_f32", _p(self.g2), _p(self.v2), B, B, self.T.d, _p(self.GG[0]), _p(self.GG[1]), _stream())
+        d_ = self.duals
+        _call("nr_sinkhorn", _p(self.GG[0]), _p(self.GG[1]), B, iters, _p(d_[0]), _p(d_[1]), _p(d_[2]), _p(d_[3]),
+              _p(self.lib_ws), self.nws, _stream())
+
+    def run_forked(self):
+        with ops.ForkJoin(2) as fj:
+            self.run_text_side()
+            with fj.on(0):
+                self.run_video_side()
+            with fj.on(1):
+                self.run_global()
+        return self
+
+
 class ShardedHeadFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale, tm_l, vm_l, mb_feat_t,
-                mb_feat_v, mb_mask_t, mb_mask_v, hp):
+                mb_feat_v, mb_mask_t, mb_mask_v, hp, pro=None):
         cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
         _req_cuda(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale)
-        W, r = dist.get_world_size(), dist.get_rank()
+        if pro is None:
+            pro = ShardedPrologue(text_l, video_l, gt_l, gv_l, tm_l, vm_l, mb_feat_t, mb_feat_v, mb_mask_t,
+                                  mb_mask_v, hp).run_forked()
+        W, r, b, B, lo = pro.W, pro.r, pro.b, pro.B, pro.lo
         dev = text_l.device
         st = _stream()
-        b = text_l.shape[0]
-        B, lo = W * b, r * b
         d = text_l.shape[-1]
-        # ---- exchange 1: features, masks, global features, token weights
-        text, video = _gather(_f32c(text_l)), _gather(_f32c(video_l))
         nt_, nv_ = text_l.shape[1], video_l.shape[1]
-        masks = _gather(torch.cat([_mask(tm_l), _mask(vm_l)], dim=1))                       # [B, Nt+Nv] int64
-        tm, vm = masks[:, :nt_].contiguous(), masks[:, nt_:].contiguous()
-        small = _gather(torch.cat([_f32c(gt_l).reshape(b, d), _f32c(gv_l).reshape(b, d), _f32c(tw_l), _f32c(vw_l)],
-                                  dim=1))                                                  # [B, 2D+Nt+Nv]
-        g2, v2 = small[:, :d].contiguous(), small[:, d:2 * d].contiguous()
-        tw, vw = small[:, 2 * d:2 * d + nt_].contiguous(), small[:, 2 * d + nt_:].contiguous()
+        text, video, tm, vm, mtm, mvm = pro.text, pro.video, pro.tm, pro.vm, pro.mtm, pro.mvm
+        T, V, MT, MV, Tl, Vl = pro.T, pro.V, pro.MT, pro.MV, pro.Tl, pro.Vl
+        fusedk = pro.fusedk
+        # ---- exchange 2: token weights of the local rows (the only gather that needs the MLPs)
+        small = _gather(torch.cat([_f32c(tw_l), _f32c(vw_l)], dim=1))                        # [B, Nt+Nv]
+        tw, vw = small[:, :nt_].contiguous(), small[:, nt_:].contiguous()
         tw_mb, vw_mb = _f32c(tw_mb), _f32c(vw_mb)
-        mtm, mvm = _mask(mb_mask_t), _mask(mb_mask_v)
-        bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
-        fusedk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
-                  and ops.maxsim2_supported(nt_, nv_, d))
-        T = Prepared(text, bf16=bf, colsum=True, mask=tm if fusedk else None)
-        V = Prepared(video, bf16=bf, colsum=True, mask=vm if fusedk else None)
-        MT = Prepared(mb_feat_t, bf16=bf, mask=mtm if fusedk else None)
-        MV = Prepared(mb_feat_v, bf16=bf, mask=mvm if fusedk else None)
-        Tl, Vl = T.block(lo, b), V.block(lo, b)
         M = MT.r
         nt, nv = T.n, V.n
         tw_lc, vw_lc, tm_lc, vm_lc = tw[lo:lo + b], vw[lo:lo + b], tm[lo:lo + b], vm[lo:lo + b]
         f32 = dict(dtype=torch.float32, device=dev)
         S_row = torch.empty(b, B, **f32); S_col = torch.empty(b, B, **f32)
-        mb_t2v = torch.empty(b, M, **f32); mb_v2t = torch.empty(b, M, **f32)
+        mbb = torch.empty(2, b, M, **f32)
+        mb_t2v, mb_v2t = mbb[0], mbb[1]
         if fusedk:
             # ONE launch, 4 problems, every token pair of a block multiplied once:
             #   S_row = S(text_l, video) [b,B];  S_col[v_l, a] = S(text, video_l)[a, v_l];  the two bank blocks
@@ -133,33 +212,29 @@ class ShardedHeadFunction(torch.autograd.Function):
             pC, yC = _fwd_dir(prec, MT, Vl, tw_mb, mtm, vm_lc, mb_v2t, 1, M, None, 0, 0, 1)
         ctx.fusedk = fusedk
         c_l = torch.empty(2, b, **f32)
-        _call("nr_row_mean", _p(mb_t2v), M, b, M, _p(c_l[0]), st)
-        _call("nr_row_mean", _p(mb_v2t), M, b, M, _p(c_l[1]), st)
-        # ---- exchange 2: bank centrality of every sample (indexed by COLUMN in the neighbour loss)
+        _call("nr_row_mean", _p(mbb), M, 2 * b, M, _p(c_l), st)
+        # ---- exchange 3: bank centrality of every sample (indexed by COLUMN in the neighbour loss)
         cb = _gather(c_l.unsqueeze(0)).permute(1, 0, 2).reshape(2, B).contiguous()       # [c_t2v ; c_v2t]
-        G = g2 @ v2.t()
-        GT = v2 @ g2.t()
-        duals = torch.empty(4, B, **f32)
-        ws, nws = ops.sinkhorn_workspace(B, dev)
-        _call("nr_sinkhorn", _p(G), _p(GT), B, int(iters), _p(duals[0]), _p(duals[1]), _p(duals[2]), _p(duals[3]),
-              _p(ws), nws, st)
-        mean = torch.empty(2, d, **f32); gn = torch.empty(2, b, d, **f32)
-        ginv = torch.empty(2, b, **f32); w = torch.empty(2, b, **f32)
-        _call("nr_centrality_fwd", _p(T.partials), T.partials.shape[0], T.rows, _p(g2[lo:lo + b]), b, d, cs,
-              _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), st, launches=2)
-        _call("nr_centrality_fwd", _p(V.partials), V.partials.shape[0], V.rows, _p(v2[lo:lo + b]), b, d, cs,
-              _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), st, launches=2)
+        if pro.global_done is not None:                  # G, G^T and the Sinkhorn duals from the detached branch
+            torch.cuda.current_stream().wait_event(pro.global_done)
+            pro.global_done = None
+        g2, v2, G, GT, duals = pro.g2, pro.v2, pro.GG[0], pro.GG[1], pro.duals
+        mean, gn, ginv, w = pro.mean, pro.gn, pro.ginv, pro.w
         ls = _f32c(logit_scale).reshape(1)
         row_out = torch.zeros(2, 4, b, **f32)
         nbr = torch.empty(2, b, k, dtype=torch.int32, device=dev)
         saved = torch.empty(2, b, NR_NSAVE, **f32)
-        _call("nr_row_losses_fwd", _p(S_row), B, _p(G[lo:lo + b]), B, _p(cb[1]), _p(w[0]), _p(duals[0][lo:lo + b]),
-              _p(duals[1]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[0]), _p(nbr[0]), _p(saved[0]), st)
-        _call("nr_row_losses_fwd", _p(S_col), B, _p(GT[lo:lo + b]), B, _p(cb[0]), _p(w[1]), _p(duals[2][lo:lo + b]),
-              _p(duals[3]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[1]), _p(nbr[1]), _p(saved[1]), st)
         sums = torch.empty(8, **f32)
+        with ops.ForkJoin(1) as fj:
+            _call("nr_row_losses_fwd", _p(S_row), B, _p(G[lo:lo + b]), B, _p(cb[1]), _p(w[0]), _p(duals[0][lo:lo + b]),
+                  _p(duals[1]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[0]), _p(nbr[0]),
+                  _p(saved[0]), _stream())
+            with fj.on(0):
+                _call("nr_row_losses_fwd", _p(S_col), B, _p(GT[lo:lo + b]), B, _p(cb[0]), _p(w[1]),
+                      _p(duals[2][lo:lo + b]), _p(duals[3]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES,
+                      _p(row_out[1]), _p(nbr[1]), _p(saved[1]), _stream())
         _call("nr_vec_sums", _p(row_out), 8, b, None, _p(sums), st)
-        # ---- exchange 3: loss partial sums
+        # ---- exchange 4: loss partial sums
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         m54 = _combine_matrix(B, wu, wn, wkl, dev)
         out5 = m54 @ (sums[:4] + sums[4:])
@@ -276,14 +351,13 @@ class ShardedHeadFunction(torch.autograd.Function):
         ctx.objs = None
         gs_t, gs_v = ctx.gshape
         return (dtext, dvideo, dgt.reshape(gs_t), dgv.reshape(gs_v), dtw_o, dvw_o, dtw_mb, dvw_mb, dls.reshape(()),
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 def sharded_head(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale, tm_l, vm_l, mb_feat_t, mb_feat_v,
                  mb_mask_t, mb_mask_v, *, centrality_scale, beta, num_neighbors, temperature, uniform_weight,
-                 neighbor_weight, kl_weight, precision="bf16", bwd_precision=None, iters=50):
-    hp = (float(centrality_scale), float(beta), int(num_neighbors), float(temperature), int(iters),
-          float(uniform_weight), float(neighbor_weight), float(kl_weight), ops.PRECISIONS[precision],
-          ops.PRECISIONS[bwd_precision or precision])
+                 neighbor_weight, kl_weight, precision="bf16", bwd_precision=None, iters=50, prologue=None):
+    hp = head_hparams(centrality_scale, beta, num_neighbors, temperature, uniform_weight, neighbor_weight, kl_weight,
+                      precision, bwd_precision, iters)
     return ShardedHeadFunction.apply(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale, tm_l, vm_l,
-                                     mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp)
+                                     mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp, prologue)

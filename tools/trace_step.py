@@ -19,8 +19,14 @@ ap.add_argument("--b", type=int, default=128)
 ap.add_argument("--out", default=None)
 a = ap.parse_args()
 nt, nv, mrows = synth.SHAPES[a.shape]
-dev = torch.device("cuda")
-m = NeighborRetr(synth.default_config(), width=512)
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:      # torchrun --nproc-per-node W tools/trace_step.py: the row-block sharded step with captured NCCL
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+m = NeighborRetr(synth.default_config(world_size=world, local_rank=local, rank=rank), width=512)
 for n, sd in synth.make_mlp_params().items():
     getattr(m, n).load_state_dict(sd)
 m.clip.logit_scale.data.fill_(4.6052)
@@ -28,7 +34,7 @@ m = m.to(dev).train()
 bank = synth.make_bank(mrows, nt, nv)
 for n in ("mb_ind", "mb_feat_t", "mb_feat_v", "mb_mask_t", "mb_mask_v"):
     setattr(m, n, getattr(bank, n).to(dev))
-h = synth.make_batch(a.b, nt, nv).to(dev)
+h = synth.make_batch(a.b, nt, nv, seed=1234, rank=rank).to(dev)
 batch = [getattr(h, f) for f in FIELDS]
 g = GraphedHeadStep(m, batch)
 for _ in range(3):
@@ -52,7 +58,13 @@ for e in evs:
     lines.append(f"{s - t0:9.1f} {t - s:8.1f}  {e.name[:110]}")
 lines.append(f"# GPU busy (union of kernel intervals) {busy:.1f} us of {end - t0:.1f} us")
 txt = "\n".join(lines)
+if rank != 0:
+    torch.cuda.synchronize()
+    os._exit(0)
 if a.out:
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
     open(a.out, "w").write(txt + "\n")
 print(txt)
+if world > 1:
+    sys.stdout.flush()
+    os._exit(0)
