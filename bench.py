@@ -85,7 +85,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
-K1_TRAFFIC = {}
+K1_TRAFFIC = {(1, "msrvtt", "nr_maxsim2_fwd"): 23.73e6 + 0.73e6}
 
 
 def flops_maxsim(rx, ry, nt, nv, d=D):
@@ -373,8 +373,8 @@ def run_ours(args):
                      "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": K1_TRAFFIC.get((world, args.shape, kname)),
                      "traffic_note": "dram bytes read+written per launch, ncu --set full of tools/k2_only.py "
-                                     "(profiles/r1_k2_fwd_ncu_full.txt); operands 22.0e6 B + saved max/arg-max and "
-                                     "similarities 26.9e6 B",
+                                     "(profiles/r1_k2_fwd_ncu_full.txt): the 23.6e6 B of bf16 operands are read from "
+                                     "HBM once, the 27e6 B of saved max/arg-max and similarities stay in L2",
                      "launches_timed": n_l, "avg_launch_ms": kt["ms"] / n_l,
                      "share_of_step": (kt["ms"] / ksteps) / (ms_total / args.steps) if ms_total else None,
                      "timed_in": "eager steps on the launching stream (events cannot be read inside a graph replay)",

@@ -37,6 +37,7 @@ constexpr int T2_MAX_STAGES = 4;
 constexpr int T2_A_BYTES = T2_BM * 128;    // 16 KB
 constexpr int T2_ACC_COLS = 256;           // TMEM columns per accumulator stage
 constexpr int T2_MAX_PROB = 4;
+constexpr int T2_SET = 128;                // threads of one epilogue set
 constexpr int T2_RING = 4;                 // depth of the tile-index ring between the scheduler and its consumers
 
 struct Tc2Prob {
@@ -78,19 +79,26 @@ __device__ __forceinline__ uint32_t group_colmax(uint32_t* k, int lane) {
   return k[0];
 }
 
+__device__ __forceinline__ void set_barrier(int set) {      // named barrier 1 / 2: the 128 threads of one epilogue set
+  if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
 template <int NY, int GL>
 __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __grid_constant__ Tc2Args a) {
   constexpr int CH = t2_lcm(NY, GL);       // accumulator columns per epilogue chunk: whole samples, whole groups
   constexpr int SPC = CH / NY;             // Y samples per chunk
   constexpr uint32_t LOWM = GL - 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A | B)] [hp 2 x 128 x hp_ld f32] [keyG (128/GL) x kg_ld u32] [colw SX x UN f32] [barriers]
+  // carve: [stages x (A | B)] then per epilogue set: [hp 128 x hp_ld f32] [keyG (128/GL) x kg_ld u32]
+  // [colw SX x UN f32] [wy UN f32], then the barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = T2_A_BYTES + a.b_bytes;
   float* hp = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes);
   uint32_t* keyG = reinterpret_cast<uint32_t*>(hp + 2 * T2_BM * a.hp_ld);
-  float* colw = reinterpret_cast<float*>(keyG + (T2_BM / GL) * a.kg_ld);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(colw + ((a.SX * a.UN + 1) & ~1));
+  float* colw = reinterpret_cast<float*>(keyG + 2 * (T2_BM / GL) * a.kg_ld);
+  float* wyst = colw + 2 * a.SX * a.UN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wyst + 2 * a.UN);
   uint64_t* full = bars;                          // [stages]  TMA -> MMA
   uint64_t* empty = bars + T2_MAX_STAGES;         // [stages]  MMA -> TMA
   uint64_t* tfull = bars + 2 * T2_MAX_STAGES;     // [2]       MMA -> epilogue
@@ -105,8 +113,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < a.nprob; ++p) { tma_prefetch_desc(&a.tmx[p]); tma_prefetch_desc(&a.tmy[p]); }
     for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, T2_EPI); }
-    for (int s = 0; s < T2_RING; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, 1 + T2_EPI); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, T2_SET); }
+    for (int s = 0; s < T2_RING; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, 1 + T2_SET); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -141,7 +149,13 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
         if (tile >= a.n_tiles) tile = -1;
         ring[slot] = tile;
         mbar_arrive(rfull + slot);                       // release: the ring entry is visible to the waiters
-        if (tile < 0) break;
+        if (tile < 0) {                                  // the other epilogue set reads the NEXT slot: end it too
+          const int slot2 = (n + 1) & (T2_RING - 1);
+          mbar_wait(rempty + slot2, ((uint32_t)((n + 1) / T2_RING) & 1u) ^ 1u);
+          ring[slot2] = -1;
+          mbar_arrive(rfull + slot2);
+          break;
+        }
         int p, mt, nt;
         decode(tile, p, mt, nt);
         const int row_x = mt * a.MU, row_y = nt * a.SY * NY;
@@ -187,16 +201,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue: two ping-pong sets (warps 2..5 = set 0, 6..9 = set 1) =====================
+    // Set s owns TMEM accumulator stage s, i.e. every other tile of this CTA, with its own staging buffers: while
+    // one set is in the latency-bound tail of a tile (group combine, output), the other drains the next accumulator.
+    const int set = (warp - 2) >> 2;
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;                    // the two warps of a quarter take alternate chunks
     const int r = q * 32 + lane;                         // accumulator row = X token of the tile
-    const int et = threadIdx.x - 64;                     // 0..255
+    const int et = (threadIdx.x - 64) & (T2_SET - 1);    // 0..127 within the set
     const int Nx = a.Nx;
     const int sx = r / Nx, x = r - sx * Nx;
     const uint32_t low = LOWM - ((uint32_t)lane & LOWM);
-    uint32_t* kg_row = keyG + (r / GL) * a.kg_ld + (lane & (int)LOWM);
-    for (int it = 0;; ++it) {
+    float* const hpb = hp + (size_t)set * T2_BM * a.hp_ld;
+    uint32_t* const kgs = keyG + (size_t)set * (T2_BM / GL) * a.kg_ld;
+    float* const cws = colw + (size_t)set * a.SX * a.UN;
+    float* const wys = wyst + (size_t)set * a.UN;
+    uint32_t* const kg_row = kgs + (r / GL) * a.kg_ld + (lane & (int)LOWM);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * T2_ACC_COLS);
+    for (int it = set;; it += 2) {
       const int slot = it & (T2_RING - 1);
       mbar_wait(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
       const int tile = ring[slot];
@@ -205,22 +226,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
       int pi, mt, nt;
       decode(tile, pi, mt, nt);
       const Tc2Prob& P = a.p[pi];
-      const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int ry0 = nt * a.SY;
       const int sy_n = min(a.SY, P.Ry - ry0);
       const int sx_n = min(a.SX, P.Rx - mt * a.SX);
       const int n_ch = (sy_n + SPC - 1) / SPC;
-      float* hpb = hp + (size_t)acc * T2_BM * a.hp_ld;
+      const int ncols = sy_n * NY;
       const int rx = mt * a.SX + sx;
       const bool row_ok = (r < a.MU) && (rx < P.Rx);
       const float wxv = row_ok ? P.wx[(int64_t)rx * Nx + x] : 0.f;
       const int64_t obase = ((int64_t)rx * P.Ry + ry0) * Nx + x;
       float* const pmx = row_ok ? P.pmax_x : nullptr;
       uint8_t* const yst = row_ok ? P.ystar : nullptr;
-      mbar_wait(tfull + acc, acc_phase);
+      // the Y token weights of this tile, staged while the MMAs of the tile are still running (the set's previous
+      // tile finished with a set barrier after its last read of wys)
+      for (int c = et; c < ncols; c += T2_SET) wys[c] = P.wy[(int64_t)ry0 * NY + c];
+      mbar_wait(tfull + set, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_ACC_COLS);
       auto process = [&](const uint32_t* v, int ch) {
         // row direction: max / arg-max over the NY columns of each Y sample of the chunk
 #pragma unroll
@@ -250,23 +272,23 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
       if constexpr (CH <= 32) {
         // two register buffers: the TMEM load of the next chunk is in flight while this one is reduced
         uint32_t va[CH], vb[CH];
-        int ch = half;
+        int ch = 0;
         if (ch < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)(ch * CH), va);
-        for (; ch < n_ch; ch += 4) {
+        for (; ch < n_ch; ch += 2) {
           tmem_ld_wait();
           reg_fence<CH>(va);
-          const int ch2 = ch + 2;
+          const int ch2 = ch + 1;
           if (ch2 < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)(ch2 * CH), vb);
           process(va, ch);
           if (ch2 < n_ch) {
             tmem_ld_wait();
             reg_fence<CH>(vb);
-            if (ch + 4 < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)((ch + 4) * CH), va);
+            if (ch + 2 < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)((ch + 2) * CH), va);
             process(vb, ch2);
           }
         }
       } else {
-        for (int ch = half; ch < n_ch; ch += 2) {
+        for (int ch = 0; ch < n_ch; ++ch) {
           uint32_t v[CH];
           tmem_ld_cols<CH>(taddr + (uint32_t)(ch * CH), v);
           tmem_ld_wait();
@@ -275,14 +297,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty + acc);                         // TMEM stage may be overwritten
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_arrive(tempty + set);                         // TMEM stage may be overwritten
+      set_barrier(set);
       // F1: combine the Nx/GL group partials of each (X sample, column): value, arg-max row, weighted value
       {
-        const int ncols = sy_n * NY, ng = Nx / GL;
-        for (int e = et; e < sx_n * ncols; e += T2_EPI) {
+        const int ng = Nx / GL;
+        for (int e = et; e < sx_n * ncols; e += T2_SET) {
           const int s = e / ncols, c = e - s * ncols;
-          const uint32_t* kp = keyG + (s * ng) * a.kg_ld + c;
+          const uint32_t* kp = kgs + (s * ng) * a.kg_ld + c;
           uint32_t best = kp[0]; int bg = 0;
           for (int gi = 1; gi < ng; ++gi) {
             const uint32_t kk = kp[gi * a.kg_ld];
@@ -293,24 +315,30 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
           const int64_t o = ((int64_t)(mt * a.SX + s) * P.Ry + ry0) * NY + c;
           if (P.pmax_y) P.pmax_y[o] = val;
           if (P.xstar) P.xstar[o] = (uint8_t)xs;
-          colw[s * a.UN + c] = P.wy[(int64_t)ry0 * NY + c] * val;
+          cws[s * a.UN + c] = wys[c] * val;
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      set_barrier(set);
       // F2: S[rx, ry] = alpha * (sum over the Nx rows of hp + sum over the NY columns of colw)
-      for (int e = et; e < sx_n * sy_n; e += T2_EPI) {
+      for (int e = et; e < sx_n * sy_n; e += T2_SET) {
         const int s = e / sy_n, sy = e - s * sy_n;
-        float h = 0.f;
-        for (int xx = 0; xx < Nx; ++xx) h += hpb[(s * Nx + xx) * a.hp_ld + sy];
-        const float* cw = colw + s * a.UN + sy * NY;
+        const float* hrow = hpb + (s * Nx) * a.hp_ld + sy;
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;     // independent chains: the loads pipeline
+        int xx = 0;
+        for (; xx + 4 <= Nx; xx += 4) {
+          h0 += hrow[(xx + 0) * a.hp_ld]; h1 += hrow[(xx + 1) * a.hp_ld];
+          h2 += hrow[(xx + 2) * a.hp_ld]; h3 += hrow[(xx + 3) * a.hp_ld];
+        }
+        for (; xx < Nx; ++xx) h0 += hrow[xx * a.hp_ld];
+        const float* cw = cws + s * a.UN + sy * NY;
 #pragma unroll
-        for (int y = 0; y < NY; ++y) h += cw[y];
-        h *= P.alpha;
+        for (int y = 0; y < NY; y += 4) { h0 += cw[y]; h1 += cw[y + 1]; h2 += cw[y + 2]; h3 += cw[y + 3]; }
+        const float h = ((h0 + h1) + (h2 + h3)) * P.alpha;
         const int rxx = mt * a.SX + s, ry = ry0 + sy;
         P.out[(int64_t)rxx * P.out_sr + (int64_t)ry * P.out_sc] = h;
         if (P.out2) P.out2[(int64_t)rxx * P.out2_sr + (int64_t)ry * P.out2_sc] = h;
       }
-      // colw / keyG are rewritten only after the next tile's first barrier, hp is double-buffered
+      set_barrier(set);       // the set's staging buffers (hp, keyG, colw, wys) are free for its next tile
     }
   }
   tc_fence_before();
@@ -408,8 +436,8 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
   a.n_tiles = tiles;
   a.tile_counter = (unsigned int*)workspace;
   NR_CUDA(cudaMemsetAsync(workspace, 0, 16, (cudaStream_t)stream));
-  const size_t tail = (size_t)2 * T2_BM * a.hp_ld * 4 + (size_t)(T2_BM / GL) * a.kg_ld * 4 +
-                      (size_t)((a.SX * a.UN + 1) & ~1) * 4 + 512;
+  const size_t tail = (size_t)2 * T2_BM * a.hp_ld * 4 + (size_t)2 * (T2_BM / GL) * a.kg_ld * 4 +
+                      (size_t)2 * a.SX * a.UN * 4 + (size_t)2 * a.UN * 4 + 512;
   const size_t budget = 227 * 1024 - 1024;   // alignment slack
   int stages = (int)((budget - tail) / (size_t)(T2_A_BYTES + a.b_bytes));
   if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;

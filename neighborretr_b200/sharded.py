@@ -301,6 +301,13 @@ class ShardedHeadFunction(torch.autograd.Function):
             # S_row = S(text_l, video): g = dS_row [b,B];  S_col[v_l, a] = S(text, video_l)[a, v_l]: g(rx=a, ry=v_l) =
             # dS_col[v_l, a];  bank pairs of this rank's samples: g = dc_l[.]/M broadcast over the bank rows (stride 0).
             # ONE launch; jobs with the same destination share an accumulator pass.
+            fjw = ops.ForkJoin(1)
+            fjw.__enter__()
+            with fjw.on(0):                          # weight gradients NEXT TO the contraction, not after it
+                ops.maxsim2_bwd_w(p1, p2, dS_row, B, 1, 0.5, b, nt, B, nv, dtw_l, dvw)
+                ops.maxsim2_bwd_w(p3, p4, dS_col, 1, B, 0.5, B, nt, b, nv, dtw, dvw_l)
+                ops.maxsim2_bwd_w(pA, pB, dc_l[0], 1, 0, sc, b, nt, M, nv, dtw_l, dvw_mb)
+                ops.maxsim2_bwd_w(pC, pD, dc_l[1], 0, 1, sc, M, nt, b, nv, dtw_mb, dvw_l)
             ops.maxsim2_bwd_multi([
                 (0, V, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, B, dtn_l),
                 (0, MV, tw_l, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
@@ -308,10 +315,7 @@ class ShardedHeadFunction(torch.autograd.Function):
                 (0, Vl, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, b, dtn),
                 (1, T, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, b, dvn_l),
                 (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
-            ops.maxsim2_bwd_w(p1, p2, dS_row, B, 1, 0.5, b, nt, B, nv, dtw_l, dvw)
-            ops.maxsim2_bwd_w(p3, p4, dS_col, 1, B, 0.5, B, nt, b, nv, dtw, dvw_l)
-            ops.maxsim2_bwd_w(pA, pB, dc_l[0], 1, 0, sc, b, nt, M, nv, dtw_l, dvw_mb)
-            ops.maxsim2_bwd_w(pC, pD, dc_l[1], 0, 1, sc, M, nt, b, nv, dtw_mb, dvw_l)
+            fjw.__exit__(None, None, None)
         else:
             X, Y, Wg = "nr_maxsim_bwd_x", "nr_maxsim_bwd_y", "nr_maxsim_bwd_w"
             # H1 = H(text_l, video): dH1[a_l, bb] = .5 dS_row
@@ -340,8 +344,11 @@ class ShardedHeadFunction(torch.autograd.Function):
             _call(Wg, _p(pD), _p(dc_l[1]), 1, 0, sc, b, nv, M, _p(dvw_l), st)
             _call(Y, bprec, _p(mts), mtld, _p(tw_mb), _p(mtm), _p(vm_l), _p(yC), _p(dc_l[1]), 0, 1, sc, M, nt, b, nv, d, _p(dvn_l), st)
             _call(Wg, _p(pC), _p(dc_l[1]), 0, 1, sc, M, nt, b, _p(dtw_mb), st)
-        dtext_all = T.backward(dtn, add_vec=dmean[0])
-        dvideo_all = V.backward(dvn, add_vec=dmean[1])
+        dtext_all = torch.empty_like(T.xn); dvideo_all = torch.empty_like(V.xn)
+        with ops.ForkJoin(1) as fj:
+            T.backward(dtn, add_vec=dmean[0], out=dtext_all)
+            with fj.on(0):
+                V.backward(dvn, add_vec=dmean[1], out=dvideo_all)
         # ---- exchange 5: sum the partial gradients of the gathered tensors, keep this rank's rows
         dtext = _reduce_scatter(dtext_all, b)
         dvideo = _reduce_scatter(dvideo_all, b)
