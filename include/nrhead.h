@@ -72,17 +72,18 @@ int nr_mlp_hidden_bwd(const float* h, const float* dlogit, const float* w2, int6
                       float* partials, void* stream);
 
 /* ---- token weights (modeling.py:485-492): second layer + masked softmax over the tokens of each sample --------
- * h [R*N, H] post-ReLU hidden activations (first layer = library GEMM), w2 [H], b2 [1] device scalars.
+ * h [R*N, H] post-ReLU hidden activations (first layer = library GEMM; f32, or bf16 when h_bf16 != 0 — then dh of
+ * the backward is bf16 as well), w2 [H], b2 [1] device scalars.
  *   logit[r,n] = <h[r,n,:], w2> + b2,  masked tokens -9e15,  w [R,N] = softmax over n.
  * Samples [0,Ra) read mask_a [Ra,N], samples [Ra,R) read mask_b [R-Ra,N] (int64, nullable): the batch tokens and
  * the memory-bank tokens of one modality share the launch. */
-int nr_token_weights_fwd(const float* h, const float* w2, const float* b2, const int64_t* mask_a,
+int nr_token_weights_fwd(const void* h, int h_bf16, const float* w2, const float* b2, const int64_t* mask_a,
                          const int64_t* mask_b, int64_t Ra, int64_t R, int64_t N, int64_t H, float* w, void* stream);
 /* backward down to the hidden layer in one pass over h: dw_a [Ra,N] / dw_b [R-Ra,N] (nullable = zero) are the
  * gradients of w; dh [R*N,H] = dlogit * w2 * (h > 0); partials [2H+1, nr_mlp_chunks(R*N)] whose row sums are
  * db1 (rows 0..H), dw2 (rows H..2H) and db2 (row 2H). */
-int nr_token_weights_bwd(const float* h, const float* w, const float* dw_a, const float* dw_b, int64_t Ra, int64_t R,
-                         int64_t N, const float* w2, int64_t H, float* dh, float* partials, void* stream);
+int nr_token_weights_bwd(const void* h, int h_bf16, const float* w, const float* dw_a, const float* dw_b, int64_t Ra,
+                         int64_t R, int64_t N, const float* w2, int64_t H, void* dh, float* partials, void* stream);
 
 /* ---- masked max-sim late interaction: one direction of local_level (modeling.py:499-509) ----
  *   H[rx, ry] = sum_x wx[rx,x] * max_y ( <xn[rx,x,:], yn[ry,y,:]> * mx[rx,x] * my[ry,y] )

@@ -322,13 +322,31 @@ extern "C" int nr_gram_f32(const float* a, const float* b, int64_t Ra, int64_t R
 namespace nr {
 constexpr int MLPB_ROWS = 32;      // rows per CTA
 
+// hidden activations are fp32 (fp32 / TF32 first layer) or bf16 (bf16 first layer): 4 consecutive elements per access
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&a);
+  u.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
 // Second layer + masked softmax over the tokens of a sample (reference modeling.py:485-492):
 //   logit[t] = <h[t,:], w2> + b2;  logit[masked] = -9e15;  w[r,:] = softmax_n(logit[r,:])
 // One CTA per sample, one warp per token row (float4 loads of the post-ReLU activations), softmax by warp 0.
 // Samples [0,Ra) take their mask from mask_a, samples [Ra,R) from mask_b (batch and bank tokens of one modality
 // share the launch).  HBM-bound: 4*T*H bytes read.
+template <typename HT>
 __global__ void __launch_bounds__(256)
-token_weights_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2,
+token_weights_fwd_kernel(const HT* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2,
                          const int64_t* __restrict__ mask_a, const int64_t* __restrict__ mask_b, int Ra, int N, int H,
                          float* __restrict__ w) {
   __shared__ float logit[NR_MAX_TOKENS];
@@ -337,10 +355,10 @@ token_weights_fwd_kernel(const float* __restrict__ h, const float* __restrict__ 
                                : (mask_b ? mask_b + (int64_t)(r - Ra) * N : nullptr);
   const float bias = b2[0];
   for (int n = warp; n < N; n += 8) {
-    const float* hr = h + ((int64_t)r * N + n) * H;
+    const HT* hr = h + ((int64_t)r * N + n) * H;
     float s = 0.f;
     for (int c = lane * 4; c < H; c += 128) {
-      const float4 hv = *reinterpret_cast<const float4*>(hr + c);
+      const float4 hv = ld4(hr + c);
       const float4 wv = *reinterpret_cast<const float4*>(w2 + c);
       s += hv.x * wv.x + hv.y * wv.y + hv.z * wv.z + hv.w * wv.w;
     }
@@ -364,10 +382,11 @@ token_weights_fwd_kernel(const float* __restrict__ h, const float* __restrict__ 
 //   dh[t,j] = dlogit[t] * w2[j] * (h[t,j] > 0),  partials of db1[j] = sum_t dh[t,j], dw2[j] = sum_t dlogit[t] h[t,j],
 //   db2 = sum_t dlogit[t]  (row 2H of the partials).   dw of samples [0,Ra) comes from dw_a, the rest from dw_b
 //   (nullable = no gradient reached those weights).
+template <typename HT>
 __global__ void __launch_bounds__(256)
-token_weights_bwd_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ dw_a,
+token_weights_bwd_kernel(const HT* __restrict__ h, const float* __restrict__ w, const float* __restrict__ dw_a,
                          const float* __restrict__ dw_b, int Ra, int N, const float* __restrict__ w2, int T, int H,
-                         float* __restrict__ dh, float* __restrict__ partials, int nchunks) {
+                         HT* __restrict__ dh, float* __restrict__ partials, int nchunks) {
   __shared__ float dl[MLPB_ROWS];
   const int chunk = blockIdx.x, t0 = chunk * MLPB_ROWS, t1 = min(T, t0 + MLPB_ROWS);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -398,7 +417,7 @@ token_weights_bwd_kernel(const float* __restrict__ h, const float* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int t = min(tb + i, t1 - 1);
-        hv[i] = *reinterpret_cast<const float4*>(h + (int64_t)t * H + c);
+        hv[i] = ld4(h + (int64_t)t * H + c);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -407,7 +426,7 @@ token_weights_bwd_kernel(const float* __restrict__ h, const float* __restrict__ 
           float4 o;
           o.x = hv[i].x > 0.f ? d * wv.x : 0.f; o.y = hv[i].y > 0.f ? d * wv.y : 0.f;
           o.z = hv[i].z > 0.f ? d * wv.z : 0.f; o.w = hv[i].w > 0.f ? d * wv.w : 0.f;
-          *reinterpret_cast<float4*>(dh + (int64_t)(tb + i) * H + c) = o;
+          st4(dh + (int64_t)(tb + i) * H + c, o);
           sb.x += o.x; sb.y += o.y; sb.z += o.z; sb.w += o.w;
           sw.x += d * hv[i].x; sw.y += d * hv[i].y; sw.z += d * hv[i].z; sw.w += d * hv[i].w;
         }
@@ -469,26 +488,34 @@ extern "C" int nr_mlp_hidden_bwd(const float* h, const float* dlogit, const floa
   return 0;
 }
 
-extern "C" int nr_token_weights_fwd(const float* h, const float* w2, const float* b2, const int64_t* mask_a,
+extern "C" int nr_token_weights_fwd(const void* h, int h_bf16, const float* w2, const float* b2, const int64_t* mask_a,
                                     const int64_t* mask_b, int64_t Ra, int64_t R, int64_t N, int64_t H, float* w,
                                     void* stream) {
   NR_CHECK_ARG(h && w2 && b2 && w && R > 0 && Ra >= 0 && Ra <= R && N > 0 && N <= NR_MAX_TOKENS && H > 0 && H % 4 == 0,
                "nr_token_weights_fwd: bad arguments");
-  nr::token_weights_fwd_kernel<<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(h, w2, b2, mask_a, mask_b, (int)Ra, (int)N,
-                                                                             (int)H, w);
+  if (h_bf16)
+    nr::token_weights_fwd_kernel<__nv_bfloat16><<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)h, w2, b2, mask_a, mask_b, (int)Ra, (int)N, (int)H, w);
+  else
+    nr::token_weights_fwd_kernel<float><<<(unsigned)R, 256, 0, (cudaStream_t)stream>>>((const float*)h, w2, b2, mask_a,
+                                                                                      mask_b, (int)Ra, (int)N, (int)H, w);
   NR_CHECK_LAUNCH("nr_token_weights_fwd");
   return 0;
 }
 
-extern "C" int nr_token_weights_bwd(const float* h, const float* w, const float* dw_a, const float* dw_b, int64_t Ra,
-                                    int64_t R, int64_t N, const float* w2, int64_t H, float* dh, float* partials,
-                                    void* stream) {
+extern "C" int nr_token_weights_bwd(const void* h, int h_bf16, const float* w, const float* dw_a, const float* dw_b,
+                                    int64_t Ra, int64_t R, int64_t N, const float* w2, int64_t H, void* dh,
+                                    float* partials, void* stream) {
   NR_CHECK_ARG(h && w && w2 && dh && partials && R > 0 && Ra >= 0 && Ra <= R && N > 0 && H > 0 && H % 4 == 0,
                "nr_token_weights_bwd: bad arguments");
   const int64_t T = R * N;
   const int nchunks = (int)nr_mlp_chunks(T);
-  nr::token_weights_bwd_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(h, w, dw_a, dw_b, (int)Ra, (int)N, w2, (int)T,
-                                                                         (int)H, dh, partials, nchunks);
+  if (h_bf16)
+    nr::token_weights_bwd_kernel<__nv_bfloat16><<<nchunks, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)h, w, dw_a, dw_b, (int)Ra, (int)N, w2, (int)T, (int)H, (__nv_bfloat16*)dh, partials, nchunks);
+  else
+    nr::token_weights_bwd_kernel<float><<<nchunks, 256, 0, (cudaStream_t)stream>>>(
+        (const float*)h, w, dw_a, dw_b, (int)Ra, (int)N, w2, (int)T, (int)H, (float*)dh, partials, nchunks);
   NR_CHECK_LAUNCH("nr_token_weights_bwd");
   return 0;
 }

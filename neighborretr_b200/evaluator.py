@@ -22,7 +22,7 @@ def similarity_matrix(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list,
         v_mask = v_mask_list.view(-1, v_mask_list.shape[-1])
         chunk = max(int(mini_batch), 1) * 64
         prec = model._head_precision() if hasattr(model, "_head_precision") else "fp32"
-        lowp = prec == "bf16"
+        lowp = model._mlp_precision() if hasattr(model, "_mlp_precision") else ("tf32" if prec == "bf16" else "fp32")
         tw = torch.cat([_token_weights(model.text_weight_fc, f, m, lowp)
                         for f, m in zip(torch.split(t_feat_list, chunk), torch.split(t_mask, chunk))])
         vw = torch.cat([_token_weights(model.video_weight_fc, f, m, lowp)

@@ -32,7 +32,7 @@ DEFAULT_PRECISION = os.environ.get("NR_HEAD_PRECISION", "bf16")
 
 def _token_weights(mlp, feat, mask, lowp=False):
     """softmax over tokens of the MLP logits, masked tokens filled with -9e15 (reference :485-492).
-    lowp: run the Linear layers as TF32 tensor-core GEMMs (cuBLAS) in both passes — the bf16 head mode;
+    lowp: GEMM arithmetic of the Linear layers, "fp32" | "tf32" | "bf16" (ops.mlp_mode) in both passes;
     otherwise plain fp32 GEMMs.  The softmax stays fp32."""
     return ops.token_weights(mlp, feat, mask, lowp)[0]
 
@@ -45,6 +45,15 @@ class HeadMixin:
         cfg = getattr(self, "config", None)
         return getattr(self, "head_precision", None) or getattr(cfg, "head_precision", None) or DEFAULT_PRECISION
 
+    def _mlp_precision(self):
+        """GEMM arithmetic of the token-weight MLPs: "fp32" in the exact mode; in the bf16 head mode "bf16"
+        (default) or "tf32" (`head_mlp_precision`)."""
+        if self._head_precision() != "bf16":
+            return "fp32"
+        cfg = getattr(self, "config", None)
+        return (getattr(self, "head_mlp_precision", None) or getattr(cfg, "head_mlp_precision", None)
+                or os.environ.get("NR_HEAD_MLP_PRECISION", "bf16"))
+
     def _head_bwd_precision(self):
         cfg = getattr(self, "config", None)
         return (getattr(self, "head_bwd_precision", None) or getattr(cfg, "head_bwd_precision", None)
@@ -52,7 +61,7 @@ class HeadMixin:
 
     # --- a1: local_level (reference :483-514) -------------------------------------------------------
     def local_level(self, text_feat, video_feat, text_mask, video_mask):
-        lowp = self._head_precision() == "bf16"
+        lowp = self._mlp_precision()
         tw = _token_weights(self.text_weight_fc, text_feat, text_mask, lowp)
         vw = _token_weights(self.video_weight_fc, video_feat, video_mask, lowp)
         s, st = ops.maxsim(text_feat, video_feat, tw, vw, text_mask, video_mask, self._head_precision(),
@@ -152,7 +161,7 @@ class HeadMixin:
                 raise IndexError(f"neighbor loss needs batch >= num_neighbors + 2 (got {text_feat.shape[0]}, "
                                  f"k={num_neighbors})")
             from .fused import HeadFunction, HeadPrologue, head_hparams
-            lowp = self._head_precision() == "bf16"
+            lowp = self._mlp_precision()
             ls = logit_scale if torch.is_tensor(logit_scale) else torch.tensor(float(logit_scale),
                                                                                device=text_feat.device)
             hp = head_hparams(centrality_scale, beta, num_neighbors, temperature, cfg.uniform_weight,
@@ -226,7 +235,7 @@ class HeadMixin:
         from .fused import head_hparams
         from .sharded import ShardedHeadFunction, ShardedPrologue, SumGradsAcrossRanks
         cfg = self.config
-        lowp = self._head_precision() == "bf16"
+        lowp = self._mlp_precision()
         # each rank differentiates only its share of the loss: sum the head-parameter gradients over ranks
         # (one flat all_reduce in backward) so that every rank holds the full gradient, as in the reference
         ps = SumGradsAcrossRanks.apply(*ops.mlp_params(self.text_weight_fc), *ops.mlp_params(self.video_weight_fc))

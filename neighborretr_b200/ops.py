@@ -504,17 +504,29 @@ class TokenMLPFunction(torch.autograd.Function):
         return dx, dw1, db1, dw2, db2, None
 
 
+MLP_FP32, MLP_TF32, MLP_BF16 = 0, 1, 2
+
+
+def mlp_mode(v):
+    """Arithmetic of the weight-MLP GEMMs: False / "fp32" -> exact fp32, True / "tf32" -> TF32 tensor cores,
+    "bf16" -> bf16 operands (inputs, W1, hidden activations and their gradients stored in bf16, fp32 accumulation
+    and fp32 parameter gradients)."""
+    if isinstance(v, str):
+        return {"fp32": MLP_FP32, "tf32": MLP_TF32, "bf16": MLP_BF16}[v]
+    return int(v)
+
+
 class TokenWeightsFunction(torch.autograd.Function):
     """softmax over tokens of the masked weight-MLP logits (reference modeling.py:485-492) as ONE autograd node
     for the batch tokens and, optionally, the memory-bank tokens of the same modality:
-        forward : first layer = library GEMM with bias+ReLU epilogue (TF32 in bf16 head mode) into one hidden
-                  buffer, then nr_token_weights_fwd (second layer + mask + softmax, one pass over h);
+        forward : first layer = library GEMM with bias+ReLU epilogue into one hidden buffer, then
+                  nr_token_weights_fwd (second layer + mask + softmax, one pass over h);
         backward: nr_token_weights_bwd (softmax + second layer + ReLU backward, one pass over h) and the dW1 / dx
                   library GEMMs; bank tokens take no dx.
     Replaces ~10 ATen launches per evaluation and the parameter-gradient accumulation of two separate nodes."""
 
     @staticmethod
-    def forward(ctx, xa, ma, xb, mb, w1, b1, w2, b2, tf32):
+    def forward(ctx, xa, ma, xb, mb, w1, b1, w2, b2, mode):
         _req_cuda(xa, xb, w1, b1, w2, b2)
         Ra, N, D = xa.shape
         Rb = xb.shape[0] if xb is not None else 0
@@ -522,19 +534,27 @@ class TokenWeightsFunction(torch.autograd.Function):
             raise RuntimeError("token_weights: batch and bank tokens differ in shape")
         H = w1.shape[0]
         Ta, Tb = Ra * N, Rb * N
+        lp = mode == MLP_BF16
+        cdt = torch.bfloat16 if lp else torch.float32
         xa2 = _f32c(xa).reshape(Ta, D)
         xb2 = _f32c(xb).reshape(Tb, D) if Rb else None
+        w1c, b1c = w1, b1
+        if lp:                                  # operand copies; the GEMMs accumulate in fp32
+            xa2 = xa2.to(cdt)
+            xb2 = xb2.to(cdt) if Rb else None
+            w1c, b1c = w1.to(cdt), b1.to(cdt)
         ma, mb = _mask(ma), (_mask(mb) if Rb else None)
-        h = torch.empty(Ta + Tb, H, dtype=torch.float32, device=xa.device)
+        h = torch.empty(Ta + Tb, H, dtype=cdt, device=xa.device)
         w = torch.empty(Ra + Rb, N, dtype=torch.float32, device=xa.device)
         w2c, b2c = _f32c(w2).reshape(-1), _f32c(b2).reshape(-1)
-        with _tf32(tf32):
-            torch._addmm_activation(b1, xa2, w1.t(), use_gelu=False, out=h[:Ta])     # bias + ReLU in the epilogue
+        with _tf32(mode == MLP_TF32):
+            torch._addmm_activation(b1c, xa2, w1c.t(), use_gelu=False, out=h[:Ta])     # bias + ReLU in the epilogue
             if Rb:
-                torch._addmm_activation(b1, xb2, w1.t(), use_gelu=False, out=h[Ta:])
-        _call("nr_token_weights_fwd", _p(h), _p(w2c), _p(b2c), _p(ma), _p(mb), Ra, Ra + Rb, N, H, _p(w), _stream())
-        ctx.tf32, ctx.dims = tf32, (Ra, Rb, N, D, H)
-        ctx.save_for_backward(xa2, xb2, h, w, w1, w2c)
+                torch._addmm_activation(b1c, xb2, w1c.t(), use_gelu=False, out=h[Ta:])
+        _call("nr_token_weights_fwd", _p(h), int(lp), _p(w2c), _p(b2c), _p(ma), _p(mb), Ra, Ra + Rb, N, H, _p(w),
+              _stream())
+        ctx.mode, ctx.dims = mode, (Ra, Rb, N, D, H)
+        ctx.save_for_backward(xa2, xb2, h, w, w1c, w2c)
         ctx.xshape = xa.shape
         wa = w[:Ra]
         if Rb:
@@ -543,9 +563,10 @@ class TokenWeightsFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dwa, dwb):
-        xa2, xb2, h, w, w1, w2c = ctx.saved_tensors
+        xa2, xb2, h, w, w1c, w2c = ctx.saved_tensors
         Ra, Rb, N, D, H = ctx.dims
         Ta, Tb = Ra * N, Rb * N
+        lp = ctx.mode == MLP_BF16
         need = ctx.needs_input_grad
         dwa = _f32c(dwa) if dwa is not None else None
         dwb = _f32c(dwb) if (dwb is not None and Rb) else None
@@ -554,19 +575,20 @@ class TokenWeightsFunction(torch.autograd.Function):
         partials = torch.empty(2 * H + 1, nch, dtype=torch.float32, device=h.device)
         sums = torch.empty(2 * H + 1, dtype=torch.float32, device=h.device)
         st = _stream()
-        _call("nr_token_weights_bwd", _p(h), _p(w), _p(dwa), _p(dwb), Ra, Ra + Rb, N, _p(w2c), H, _p(dh), _p(partials), st)
-        _call("nr_vec_sums", _p(partials), 2 * H + 1, nch, None, _p(sums), st)
-        db1 = sums[:H] if need[5] else None
-        dw2 = sums[H:2 * H].reshape(1, H) if need[6] else None
-        db2 = sums[2 * H:] if need[7] else None
+        _call("nr_token_weights_bwd", _p(h), int(lp), _p(w), _p(dwa), _p(dwb), Ra, Ra + Rb, N, _p(w2c), H, _p(dh),
+              _p(partials), st)
         dw1 = dx = None
-        with _tf32(ctx.tf32):
+        with _tf32(ctx.mode == MLP_TF32):
             if need[4]:
                 dw1 = _dw1_splitk(dh[:Ta], xa2)
                 if Rb:
                     dw1 += _dw1_splitk(dh[Ta:], xb2)
             if need[0]:
-                dx = (dh[:Ta] @ w1).reshape(ctx.xshape)
+                dx = (torch.mm(dh[:Ta], w1c, out_dtype=torch.float32) if lp else dh[:Ta] @ w1c).reshape(ctx.xshape)
+        _call("nr_vec_sums", _p(partials), 2 * H + 1, nch, None, _p(sums), st)
+        db1 = sums[:H] if need[5] else None
+        dw2 = sums[H:2 * H].reshape(1, H) if need[6] else None
+        db2 = sums[2 * H:] if need[7] else None
         return dx, None, None, None, dw1, db1, dw2, db2, None
 
 
@@ -574,18 +596,21 @@ def _dw1_splitk(dh, x):
     """dh^T @ x for dh [T,H], x [T,D] with T >> H, D: the library runs this [H,D] output as 64 CTAs over the whole
     K = T; a batched product over K-chunks (split-K) fills the GPU, the chunk sum is one small reduction."""
     T = x.shape[0]
+    lp = dh.dtype != torch.float32                  # bf16 operands: fp32 accumulation AND fp32 output
     for parts in (8, 6, 4, 3, 2):
         if T % parts == 0 and T // parts >= 1024:
             c = T // parts
-            return torch.bmm(dh.view(parts, c, dh.shape[1]).transpose(1, 2), x.view(parts, c, x.shape[1])).sum(0)
-    return dh.t() @ x
+            a3, b3 = dh.view(parts, c, dh.shape[1]).transpose(1, 2), x.view(parts, c, x.shape[1])
+            return (torch.bmm(a3, b3, out_dtype=torch.float32) if lp else torch.bmm(a3, b3)).sum(0)
+    return torch.mm(dh.t(), x, out_dtype=torch.float32) if lp else dh.t() @ x
 
 
-def token_weights(mlp, feat, mask, tf32, bank_feat=None, bank_mask=None):
+def token_weights(mlp, feat, mask, mode, bank_feat=None, bank_mask=None):
     """mlp: nn.Sequential(Linear, ReLU, Linear) with the reference's parameter names, or its 4 parameters
-    (W1, b1, W2, b2) as a tuple.  Returns the token weights of `feat` [R,N] and of `bank_feat` (or None)."""
+    (W1, b1, W2, b2) as a tuple; mode: see mlp_mode().  Returns the token weights of `feat` [R,N] and of
+    `bank_feat` (or None)."""
     ps = mlp if isinstance(mlp, (tuple, list)) else mlp_params(mlp)
-    return TokenWeightsFunction.apply(feat, mask, bank_feat, bank_mask, *ps, bool(tf32))
+    return TokenWeightsFunction.apply(feat, mask, bank_feat, bank_mask, *ps, mlp_mode(mode))
 
 
 def mlp_params(mlp):

@@ -144,14 +144,18 @@ def test_compute_losses_fp32(name, fused):
     assert np.array_equal(mask.numpy(), gold["nbr_mask"])
 
 
+@pytest.mark.parametrize("mlp", ["bf16", "tf32"])
 @pytest.mark.parametrize("bwd", ["fp32", "bf16"])
-def test_compute_losses_bf16(bwd):
+def test_compute_losses_bf16(bwd, mlp):
     """Full head with the tcgen05 bf16 contraction: losses within 1e-2 relative of the reference (north_star),
-    measured ~1e-4; feature gradients rel-L2 < 3e-2 (bf16 operand rounding gives ~1e-2)."""
+    measured ~1e-4; feature gradients rel-L2 < 3e-2 (bf16 operand rounding gives ~1e-2).
+    Token-weight MLP parameters: < 3e-2 with TF32 GEMMs; < 6e-2 with the default bf16 GEMMs (measured 3.5e-2: dW1 =
+    dh^T x sums ~15k strongly cancelling token terms, so the 2^-9 operand rounding is amplified)."""
     c = CASES["cfg1"]
     gold = load_golden("cfg1")
     h, bank, params, cfg = make_case(c)
     m = make_head(c["d"], cfg, params, "bf16", bwd)
+    m.head_mlp_precision = mlp
     set_bank(m, bank)
     losses, grads = cuda_losses(m, h, cfg)
     np.testing.assert_allclose(losses.numpy(), gold["losses"], rtol=1e-2)
@@ -159,10 +163,10 @@ def test_compute_losses_bf16(bwd):
     for k in ("text", "video", "gt", "gv"):
         assert rel_l2(grads[k], ograds[k]) < 3e-2, (k, rel_l2(grads[k], ograds[k]))
     for k in ("text_weight_fc.0.weight", "video_weight_fc.0.weight"):
-        assert rel_l2(grads[k], ograds[k]) < 3e-2, (k, rel_l2(grads[k], ograds[k]))
+        assert rel_l2(grads[k], ograds[k]) < (6e-2 if mlp == "bf16" else 3e-2), (k, rel_l2(grads[k], ograds[k]))
     np.testing.assert_allclose(grads["logit_scale"].item(), gold["g_logit_scale"], rtol=1e-2)
     print("bf16 loss rel err", np.abs(losses.numpy() / gold["losses"] - 1).max(),
-          {k: rel_l2(grads[k], ograds[k]) for k in ("text", "video")})
+          {k: rel_l2(grads[k], ograds[k]) for k in ("text", "video", "text_weight_fc.0.weight")})
 
 
 def test_eval_similarity_and_metrics():
