@@ -193,7 +193,10 @@ class HeadFunction(torch.autograd.Function):
         out5 = m54 @ (sums[:4] + sums[4:])
         ctx.hp = hp
         ctx.objs = (T, V, MT, MV)
-        ctx.save_for_backward(tw, vw, tw_mb, vw_mb, tm, vm, mtm, mvm, S, ST, G, GT, cb, duals, w, ls, nbr, saved, mean,
+        # the masks are only read by the one-direction backward kernels (the fused path folded them into the operand
+        # copies); not saving them also keeps the bank masks free for an in-place FIFO update before the backward
+        sm = (None, None, None, None) if fusedk else (tm, vm, mtm, mvm)
+        ctx.save_for_backward(tw, vw, tw_mb, vw_mb, *sm, S, ST, G, GT, cb, duals, w, ls, nbr, saved, mean,
                               gn, ginv, g2, v2, m54, p1, y1, p2, y2, pA, yA, pB, yB, pC, yC, pD, yD)
         ctx.gshape = (gt.shape, gv.shape)
         ctx.nbr = nbr

@@ -38,6 +38,7 @@ class GraphedHeadStep:
         bank0 = {n: getattr(model, n).clone() for n in self.bank_names}
         self.params = [p for p in model.parameters() if p.requires_grad]
         self._e0 = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.0], device=dev)
+        self._fifo_stream = torch.cuda.Stream(device=dev)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -76,6 +77,14 @@ class GraphedHeadStep:
             losses, (ta, va, tma, vma) = m._sharded_losses(s["text_feat"], s["video_feat"], s["text_mask"],
                                                            s["video_mask"], (s["global_text"], s["global_video"]))
             new_rows = (_gather_contiguous(s["idx"], self.world), ta, va, tma, vma)
+        # With bf16 weight-MLP GEMMs the backward reads bf16 copies, never the bank itself: the FIFO update can then
+        # leave the critical path and run on its own branch next to the backward.
+        early_fifo = self.world == 1 and m._mlp_precision() == "bf16"
+        if early_fifo:
+            main = torch.cuda.current_stream()
+            self._fifo_stream.wait_stream(main)
+            with torch.cuda.stream(self._fifo_stream):
+                self._fifo(new_rows)
         out5 = getattr(m, "last_out5", None) if self.world == 1 else None
         if out5 is not None and out5.requires_grad:
             # d total / d out5 = e0: skips the unbind/stack bookkeeping kernels of losses[0].backward()
@@ -84,12 +93,20 @@ class GraphedHeadStep:
         else:
             out5 = None
             losses[0].backward()
+        if early_fifo:
+            main.wait_stream(self._fifo_stream)
+        else:
+            self._fifo(new_rows)
+        return out5.detach() if out5 is not None else torch.stack([x.detach() for x in losses])
+
+    def _fifo(self, new_rows):
+        """bank <- cat(new, bank)[:capacity] in place (reference modeling.py:235-249)."""
+        m = self.model
         with torch.no_grad():
             cap = m.mb_feat_v.shape[0]
             for name, new in zip(("mb_ind", "mb_feat_t", "mb_feat_v", "mb_mask_t", "mb_mask_v"), new_rows):
                 bank = getattr(m, name)
                 bank.copy_(ops.fifo_update(new.detach().to(bank.dtype), bank, cap))
-        return out5.detach() if out5 is not None else torch.stack([x.detach() for x in losses])
 
     def __call__(self, *batch, sync_losses_to=None):
         """Copy the batch into the static buffers (H2D if it lives on the host), replay, return the static
