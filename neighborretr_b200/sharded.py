@@ -45,6 +45,20 @@ def _reduce_scatter(t, b):
     return out
 
 
+def _all_to_all_blocks(send):
+    """send [W, ...]: chunk q goes to rank q; returns recv [W, ...] whose chunk r came from rank r."""
+    send = send.contiguous()
+    recv = torch.empty_like(send)
+    if dist.get_backend() == "nccl":
+        dist.all_to_all_single(recv, send)
+    else:                                   # gloo on CUDA tensors (single-GPU emulation in tests)
+        W, r = dist.get_world_size(), dist.get_rank()
+        allb = torch.empty((W * send.shape[0],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(allb, send)
+        recv.copy_(allb.view((W,) + tuple(send.shape))[:, r])
+    return recv
+
+
 class SumGradsAcrossRanks(torch.autograd.Function):
     """Identity on a group of parameters whose backward all-reduces (SUM) their gradients in ONE flat collective:
     applied to the head parameters so that every rank ends up with the FULL parameter gradient, like the
@@ -104,11 +118,23 @@ class ShardedPrologue:
         self.bf = bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
         self.fusedk = fk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
                             and ops.maxsim2_supported(nt, nv, d))
-        self.T = Prepared(self.text, bf16=bf, colsum=True, mask=self.tm if fk else None, defer=True)
+        # Fused (bf16) path = "exchange" design: a rank contracts only ITS text rows against all videos (P = S[rows_r,
+        # :]); the column block the video->text direction needs is assembled from the other ranks' P by an
+        # all-to-all of [b,b] blocks.  Other ranks' text tokens are then needed by the bank FIFO only.
+        self.a2a = fk
+        if fk:
+            self.T = None
+            self.Tl = Prepared(self.text_l, bf16=True, colsum=True, mask=self.tm[lo:lo + b], defer=True)
+            self.tsum_l = torch.empty(1, d, **f32)
+            self.tsum = torch.empty(W, d, **f32)
+        else:
+            self.T = Prepared(self.text, bf16=bf, colsum=True, mask=None, defer=True)
+            self.Tl = self.T.block(lo, b)
         self.V = Prepared(self.video, bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True)
         self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True)
         self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True)
-        self.Tl, self.Vl = self.T.block(lo, b), self.V.block(lo, b)
+        self.Vl = self.V.block(lo, b)
+        self.t_rows = B * nt
         self.GG = torch.empty(2, B, B, **f32)              # [G ; G^T], replicated
         self.duals = torch.empty(4, B, **f32)
         self.lib_ws, self.nws = ops.sinkhorn_workspace(B, dev)
@@ -116,22 +142,32 @@ class ShardedPrologue:
         self.ginv = torch.empty(2, b, **f32); self.w = torch.empty(2, b, **f32)
         self.global_done = None
         if bf:
-            for P in (self.T, self.V, self.MT, self.MV):
+            for P in (self.T if self.T is not None else self.Tl, self.V, self.MT, self.MV):
                 P.alloc_transposed()
 
-    def _centrality(self, P, i):
-        b, d, cs = self.b, self.T.d, self.hp[0]
-        _call("nr_centrality_fwd", _p(P.partials), P.partials.shape[0], P.rows, _p(self.g_l[i]), b, d, cs,
+    def _centrality(self, partials, rows_total, i):
+        b, d, cs = self.b, self.V.d, self.hp[0]
+        _call("nr_centrality_fwd", _p(partials), partials.shape[0], rows_total, _p(self.g_l[i]), b, d, cs,
               _p(self.mean[i]), _p(self.gn[i]), _p(self.ginv[i]), _p(self.w[i]), _stream(), launches=2)
 
     def run_text_side(self):
         bprec = self.hp[9]
+        if self.a2a:
+            self.MT.run()
+            self.Tl.run()
+            self.MT.bwd_source(bprec); self.Tl.bwd_source(bprec)
+            # column mean over ALL text tokens (modeling.py:419-424) from per-rank column sums
+            torch.sum(self.Tl.partials, dim=0, keepdim=True, out=self.tsum_l)
+            dist.all_gather_into_tensor(self.tsum, self.tsum_l)      # exchange 1a' ([W, D])
+            self._centrality(self.tsum, self.t_rows, 0)
+            dist.all_gather_into_tensor(self.text, self.text_l)      # exchange 1a: only the bank FIFO reads it
+            return
         dist.all_gather_into_tensor(self.text, self.text_l)          # exchange 1a
         self.MT.run()
         self.T.run()
         if self.bf:
             self.MT.bwd_source(bprec); self.T.bwd_source(bprec)
-        self._centrality(self.T, 0)
+        self._centrality(self.T.partials, self.T.rows, 0)
 
     def run_video_side(self):
         bprec = self.hp[9]
@@ -140,13 +176,13 @@ class ShardedPrologue:
         self.V.run()
         if self.bf:
             self.MV.bwd_source(bprec); self.V.bwd_source(bprec)
-        self._centrality(self.V, 1)
+        self._centrality(self.V.partials, self.V.rows, 1)
 
     def run_global(self):
         B, iters = self.B, int(self.hp[4])
         dist.all_gather_into_tensor(self.gall, self.gl)              # exchange 1c
         self.g2.copy_(self.gall[:, 0]); self.v2.copy_(self.gall[:, 1])
-        _call("nr_gram_f32", _p(self.g2), _p(self.v2), B, B, self.T.d, _p(self.GG[0]), _p(self.GG[1]), _stream())
+        _call("nr_gram_f32", _p(self.g2), _p(self.v2), B, B, self.V.d, _p(self.GG[0]), _p(self.GG[1]), _stream())
         d_ = self.duals
         _call("nr_sinkhorn", _p(self.GG[0]), _p(self.GG[1]), B, iters, _p(d_[0]), _p(d_[1]), _p(d_[2]), _p(d_[3]),
               _p(self.lib_ws), self.nws, _stream())
@@ -179,28 +215,38 @@ class ShardedHeadFunction(torch.autograd.Function):
         T, V, MT, MV, Tl, Vl = pro.T, pro.V, pro.MT, pro.MV, pro.Tl, pro.Vl
         fusedk = pro.fusedk
         # ---- exchange 2: token weights of the local rows (the only gather that needs the MLPs)
-        small = _gather(torch.cat([_f32c(tw_l), _f32c(vw_l)], dim=1))                        # [B, Nt+Nv]
-        tw, vw = small[:, :nt_].contiguous(), small[:, nt_:].contiguous()
+        a2a = pro.a2a
+        if a2a:                                   # other ranks never touch this rank's text weights
+            vw = _gather(_f32c(vw_l))                                                        # [B, Nv]
+            tw = _f32c(tw_l)                                                                 # [b, Nt]
+            tw_lc = tw
+        else:
+            small = _gather(torch.cat([_f32c(tw_l), _f32c(vw_l)], dim=1))                    # [B, Nt+Nv]
+            tw, vw = small[:, :nt_].contiguous(), small[:, nt_:].contiguous()
+            tw_lc = tw[lo:lo + b]
         tw_mb, vw_mb = _f32c(tw_mb), _f32c(vw_mb)
         M = MT.r
-        nt, nv = T.n, V.n
-        tw_lc, vw_lc, tm_lc, vm_lc = tw[lo:lo + b], vw[lo:lo + b], tm[lo:lo + b], vm[lo:lo + b]
+        nt, nv = Tl.n, V.n
+        vw_lc, tm_lc, vm_lc = vw[lo:lo + b], tm[lo:lo + b], vm[lo:lo + b]
         f32 = dict(dtype=torch.float32, device=dev)
         S_row = torch.empty(b, B, **f32); S_col = torch.empty(b, B, **f32)
         mbb = torch.empty(2, b, M, **f32)
         mb_t2v, mb_v2t = mbb[0], mbb[1]
         if fusedk:
-            # ONE launch, 4 problems, every token pair of a block multiplied once:
-            #   S_row = S(text_l, video) [b,B];  S_col[v_l, a] = S(text, video_l)[a, v_l];  the two bank blocks
-            sv1, sv2, svA, svC = ops.maxsim2_fwd([
-                dict(X=Tl, Y=V, wx=tw_lc, wy=vw, alpha=0.5, out=S_row, strides=(B, 1)),
-                dict(X=T, Y=Vl, wx=tw, wy=vw_lc, alpha=0.5, out=S_col, strides=(1, B)),
+            # ONE launch, 3 problems, every token pair multiplied once: S_row = S(text_l, video) [b,B] (and its
+            # transpose [B,b], whose [b,b] row chunks are what the other ranks need) and the two bank blocks
+            PT = torch.empty(B, b, **f32)
+            sv1, svA, svC = ops.maxsim2_fwd([
+                dict(X=Tl, Y=V, wx=tw_lc, wy=vw, alpha=0.5, out=S_row, strides=(B, 1), out2=PT, strides2=(1, b)),
                 dict(X=Tl, Y=MV, wx=tw_lc, wy=vw_mb, alpha=0.5, out=mb_t2v, strides=(M, 1)),
                 dict(X=MT, Y=Vl, wx=tw_mb, wy=vw_lc, alpha=0.5, out=mb_v2t, strides=(1, M))])
             p1, y1, p2, y2 = sv1          # (pmax_x, ystar, pmax_y, xstar) of each pair
-            p3, y3, p4, y4 = sv2
+            p3 = y3 = p4 = y4 = None
             pA, yA, pB, yB = svA
             pC, yC, pD, yD = svC
+            # ---- exchange 2b: S_col[v_l, (q, a)] = S[(q, a), lo + v_l] = chunk r of rank q's transposed block
+            recv = _all_to_all_blocks(PT.view(W, b, b))                                      # [q, v_l, a]
+            S_col.view(b, W, b).copy_(recv.permute(1, 0, 2))
         else:
             p1, y1 = _fwd_dir(prec, Tl, V, tw_lc, tm_lc, vm, S_row, B, 1, None, 0, 0, 0)      # H(text_l, video)
             p2, y2 = _fwd_dir(prec, V, Tl, vw, vm, tm_lc, S_row, 1, B, None, 0, 0, 1)         # H(video, text_l)^T
@@ -240,6 +286,7 @@ class ShardedHeadFunction(torch.autograd.Function):
         out5 = m54 @ (sums[:4] + sums[4:])
         ctx.hp, ctx.dims = hp, (W, r, b, B, lo, M, d, nt, nv)
         ctx.objs = (T, V, MT, MV, Tl, Vl)
+        ctx.a2a = a2a
         ctx.save_for_backward(tw, vw, tw_mb, vw_mb, tm, vm, mtm, mvm, S_row, S_col, G, GT, cb, duals, w, ls, nbr, saved,
                               mean, gn, ginv, g2, v2, m54, p1, y1, p2, y2, p3, y3, p4, y4, pA, yA, pB, yB, pC, yC, pD, yD)
         ctx.gshape = (gt_l.shape, gv_l.shape)
@@ -258,9 +305,10 @@ class ShardedHeadFunction(torch.autograd.Function):
         st = _stream()
         f32 = dict(dtype=torch.float32, device=dev)
         gscale = m54.t() @ _f32c(g5)
-        z = torch.zeros(2 * B + 1 + 2 * b, **f32)                      # [dc_t2v | dc_v2t | dls | dw_t | dw_v]
-        dcs, dls, dw = z[:2 * B + 1], z[2 * B:2 * B + 1], z[2 * B + 1:].view(2, b)
-        dc = z[:2 * B].view(2, B)
+        # [dmean_text | dc_t2v | dc_v2t | dls | dw_t | dw_v]  (dmean first: it is read with 16-byte loads)
+        z = torch.zeros(d + 2 * B + 1 + 2 * b, **f32)
+        dcs, dls, dw = z[d:d + 2 * B + 1], z[d + 2 * B:d + 2 * B + 1], z[d + 2 * B + 1:].view(2, b)
+        dc = z[d:d + 2 * B].view(2, B)
         dS_row = torch.empty(b, B, **f32); dS_col = torch.empty(b, B, **f32)
         dG1 = torch.empty(b, B, **f32); dG2 = torch.empty(b, B, **f32)
         _call("nr_row_losses_bwd", _p(S_row), B, _p(G[lo:lo + b]), B, _p(cb[1]), _p(w[0]), _p(duals[0][lo:lo + b]),
@@ -269,6 +317,14 @@ class ShardedHeadFunction(torch.autograd.Function):
         _call("nr_row_losses_bwd", _p(S_col), B, _p(GT[lo:lo + b]), B, _p(cb[0]), _p(w[1]), _p(duals[2][lo:lo + b]),
               _p(duals[3]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(nbr[1]), _p(saved[1]), _p(gscale),
               _p(dS_col), B, _p(dG2), B, _p(dc[0]), _p(dw[1]), _p(dls), st)
+        if ctx.a2a:
+            dtext, dvideo, dgt, dgv, dtw_o, dvw_o, dtw_mb, dvw_mb = _backward_exchange(
+                ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, v2, p1, y1, p2, y2, pA, yA, pB, yB, pC, yC, pD,
+                yD, z, dc, dw, dS_row, dS_col, dG1, dG2)
+            ctx.objs = None
+            gs_t, gs_v = ctx.gshape
+            return (dtext, dvideo, dgt.reshape(gs_t), dgv.reshape(gs_v), dtw_o, dvw_o, dtw_mb, dvw_mb,
+                    dls.reshape(()), None, None, None, None, None, None, None, None)
         # ---- exchange 4: gradients of the gathered bank-centrality vectors and of logit_scale (tiny)
         dist.all_reduce(dcs, op=dist.ReduceOp.SUM)
         dc_l = dc[:, lo:lo + b].contiguous()                           # this rank's samples
@@ -359,6 +415,69 @@ class ShardedHeadFunction(torch.autograd.Function):
         gs_t, gs_v = ctx.gshape
         return (dtext, dvideo, dgt.reshape(gs_t), dgv.reshape(gs_v), dtw_o, dvw_o, dtw_mb, dvw_mb, dls.reshape(()),
                 None, None, None, None, None, None, None, None)
+
+
+def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, v2, p1, y1, p2, y2, pA, yA, pB, yB, pC, yC,
+                       pD, yD, z, dc, dw, dS_row, dS_col, dG1, dG2):
+    """Backward of the exchange design (after the two row-loss backward launches): gradients w.r.t. S entries owned
+    by other ranks travel back by the inverse all-to-all; text-side gradients are then complete locally, only the
+    video side (all B videos on every rank) is reduce-scattered."""
+    cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = ctx.hp
+    W, r, b, B, lo, M, d, nt, nv = ctx.dims
+    _T, V, MT, MV, Tl, Vl = ctx.objs
+    dev = dS_row.device
+    f32 = dict(dtype=torch.float32, device=dev)
+    st = _stream()
+    # centrality backward first: its text-side dmean rides on the same all_reduce as dc / d logit_scale
+    dmean_v = torch.empty(d, **f32)
+    dmean_t = z[:d]
+    dgl = torch.empty(2, b, d, **f32)
+    _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), b, d, cs, B * nt, _p(dgl[0]),
+          0, _p(dmean_t), st, launches=2)
+    _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), b, d, cs, V.rows, _p(dgl[1]),
+          0, _p(dmean_v), st, launches=2)
+    # ---- exchange 4: dc, d logit_scale, d mean_text (every rank's centrality weights read the global text mean)
+    dist.all_reduce(z[:d + 2 * B + 1], op=dist.ReduceOp.SUM)
+    dc_l = dc[:, lo:lo + b].contiguous()                           # this rank's samples
+    # ---- exchange 4b: dS_col entries belong to the text rows of other ranks: inverse all-to-all, then
+    #      dP[a, (r, v)] = dS_row[a, (r, v)] + recv[r, v, a]
+    recv = _all_to_all_blocks(dS_col.view(b, W, b).permute(1, 0, 2))                         # [r, v, a]
+    dP = dS_row.view(b, W, b) + recv.permute(2, 0, 1)
+    dP = dP.view(b, B)
+    # global similarity: dG has a row block (direction 1) and a column block (direction 2) on this rank
+    dG = torch.zeros(B, B, **f32)
+    dG[lo:lo + b] += dG1
+    dG[:, lo:lo + b] += dG2.t()
+    dg_all = dG @ v2                                               # partial over ranks
+    dv_all = dG.t() @ g2
+    dg_all[lo:lo + b] += dgl[0]
+    dv_all[lo:lo + b] += dgl[1]
+    # ---- token-pair products: text rows complete locally, video rows partial over ranks
+    dtn_l = torch.zeros(Tl.rows, d, **f32); dvn = torch.zeros(V.rows, d, **f32)
+    dtw_l = torch.zeros(b, nt, **f32); dvw = torch.zeros(B, nv, **f32)
+    dtw_mb = torch.zeros_like(tw_mb); dvw_mb = torch.zeros_like(vw_mb)
+    dvn_l, dvw_l = dvn[lo * nv:(lo + b) * nv], dvw[lo:lo + b]
+    vw_l = vw[lo:lo + b]
+    dtext = torch.empty_like(Tl.xn); dvideo_all = torch.empty_like(V.xn)
+    sc = 0.5 / M
+    with ops.ForkJoin(1) as fj:
+        with fj.on(0):                           # weight gradients NEXT TO the contraction, not after it
+            ops.maxsim2_bwd_w(p1, p2, dP, B, 1, 0.5, b, nt, B, nv, dtw_l, dvw)
+            ops.maxsim2_bwd_w(pA, pB, dc_l[0], 1, 0, sc, b, nt, M, nv, dtw_l, dvw_mb)
+            ops.maxsim2_bwd_w(pC, pD, dc_l[1], 0, 1, sc, M, nt, b, nv, dtw_mb, dvw_l)
+        ops.maxsim2_bwd_multi([
+            (0, V, tw, vw, y1, y2, dP, B, 1, 0.5, b, B, dtn_l),
+            (0, MV, tw, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
+            (1, Tl, tw, vw, y1, y2, dP, B, 1, 0.5, b, B, dvn),
+            (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
+    with ops.ForkJoin(1) as fj:
+        Tl.backward(dtn_l, add_vec=dmean_t, out=dtext)
+        with fj.on(0):
+            V.backward(dvn, add_vec=dmean_v, out=dvideo_all)
+    # ---- exchange 5: sum the partial video-side gradients, keep this rank's rows
+    dvideo = _reduce_scatter(dvideo_all, b)
+    small = _reduce_scatter(torch.cat([dg_all, dv_all, dvw], dim=1), b)                      # one collective
+    return dtext, dvideo, small[:, :d], small[:, d:2 * d], dtw_l, small[:, 2 * d:], dtw_mb, dvw_mb
 
 
 def sharded_head(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale, tm_l, vm_l, mb_feat_t, mb_feat_v,
