@@ -96,6 +96,8 @@ class GraphedHeadStep:
         if early_fifo:
             main.wait_stream(self._fifo_stream)
         else:
+            if self.world > 1:
+                m.wait_gathered_text()
             self._fifo(new_rows)
         return out5.detach() if out5 is not None else torch.stack([x.detach() for x in losses])
 

@@ -248,29 +248,39 @@ class HeadMixin:
                               self.mb_mask_t, self.mb_mask_v, hp)
         with ops.ForkJoin(4) as fj:
             main = fj.main
+            with fj.on(3):
+                pro.run_global()             # first: its small gather must not queue behind the feature gathers
+            pro.global_done = fj.detach(3)
+            with fj.on(2):
+                pro.run_video_side()
+            with fj.on(1):
+                pro.run_text_side()
             tw, tw_mb = ops.token_weights(tmlp, text_feat, text_mask, lowp, self.mb_feat_t, self.mb_mask_t)
             with fj.on(0):
                 vw, vw_mb = ops.token_weights(vmlp, video_feat, video_mask, lowp, self.mb_feat_v, self.mb_mask_v)
                 vw.record_stream(main)
-            with fj.on(1):
-                pro.run_text_side()
-            with fj.on(2):
-                pro.run_video_side()
-            with fj.on(3):
-                pro.run_global()
-            pro.global_done = fj.detach(3)
         out5, nbr, text_all, video_all, tm_all, vm_all = ShardedHeadFunction.apply(
             text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, self.clip.logit_scale.exp(), text_mask, video_mask,
             self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v, hp, pro)
         self.last_neighbors = (nbr[0], nbr[1])
+        self._text_ready = pro.text_ready          # event of the deferred text gather (None: already joined)
         return tuple(out5.unbind(0)), (text_all, video_all, tm_all, vm_all)
 
     def _head_forward_sharded(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats):
         losses, (text_all, video_all, tm_all, vm_all) = self._sharded_losses(text_feat, video_feat, text_mask,
                                                                              video_mask, global_feats)
         with torch.no_grad():
+            self.wait_gathered_text()
             self.update_memory_bank(allgather(idx, self.config), text_all, video_all, tm_all, vm_all)
         return losses
+
+    def wait_gathered_text(self):
+        """The sharded head gathers the other ranks' text tokens asynchronously (only the bank FIFO reads them):
+        make the current stream wait for that gather before touching the gathered text."""
+        ev = getattr(self, "_text_ready", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self._text_ready = None
 
     def head_forward(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats=None):
         cfg = self.config

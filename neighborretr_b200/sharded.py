@@ -87,6 +87,16 @@ class SumGradsAcrossRanks(torch.autograd.Function):
         return tuple(out)
 
 
+_TEXT_STREAMS = {}
+
+
+def _text_stream(device):
+    st = _TEXT_STREAMS.get(device.index)
+    if st is None:
+        st = _TEXT_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
 class ShardedPrologue:
     """Everything of a sharded step that does not depend on the token-weight MLPs: the feature / mask / global-feature
     gathers, token preparation of the gathered batch and of the bank, centrality weights of the local rows, the
@@ -141,6 +151,7 @@ class ShardedPrologue:
         self.mean = torch.empty(2, d, **f32); self.gn = torch.empty(2, b, d, **f32)
         self.ginv = torch.empty(2, b, **f32); self.w = torch.empty(2, b, **f32)
         self.global_done = None
+        self.text_ready = None
         if bf:
             for P in (self.T if self.T is not None else self.Tl, self.V, self.MT, self.MV):
                 P.alloc_transposed()
@@ -160,14 +171,24 @@ class ShardedPrologue:
             torch.sum(self.Tl.partials, dim=0, keepdim=True, out=self.tsum_l)
             dist.all_gather_into_tensor(self.tsum, self.tsum_l)      # exchange 1a' ([W, D])
             self._centrality(self.tsum, self.t_rows, 0)
-            dist.all_gather_into_tensor(self.text, self.text_l)      # exchange 1a: only the bank FIFO reads it
-            return
+            return                                                   # the text gather is deferred: gather_text_async()
         dist.all_gather_into_tensor(self.text, self.text_l)          # exchange 1a
         self.MT.run()
         self.T.run()
         if self.bf:
             self.MT.bwd_source(bprec); self.T.bwd_source(bprec)
         self._centrality(self.T.partials, self.T.rows, 0)
+
+    def gather_text_async(self):
+        """Exchange design only: other ranks' text tokens feed nothing but the memory-bank FIFO, so their gather is
+        issued at the END of the forward on its own stream; consumers wait on `text_ready`."""
+        main = torch.cuda.current_stream()
+        side = _text_stream(main.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dist.all_gather_into_tensor(self.text, self.text_l)      # exchange 1a
+            self.text_ready = torch.cuda.Event()
+            self.text_ready.record(side)
 
     def run_video_side(self):
         bprec = self.hp[9]
@@ -189,11 +210,11 @@ class ShardedPrologue:
 
     def run_forked(self):
         with ops.ForkJoin(2) as fj:
-            self.run_text_side()
+            with fj.on(1):
+                self.run_global()            # first: its small gather must not queue behind the feature gathers
             with fj.on(0):
                 self.run_video_side()
-            with fj.on(1):
-                self.run_global()
+            self.run_text_side()
         return self
 
 
@@ -284,6 +305,8 @@ class ShardedHeadFunction(torch.autograd.Function):
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         m54 = _combine_matrix(B, wu, wn, wkl, dev)
         out5 = m54 @ (sums[:4] + sums[4:])
+        if a2a:
+            pro.gather_text_async()
         ctx.hp, ctx.dims = hp, (W, r, b, B, lo, M, d, nt, nv)
         ctx.objs = (T, V, MT, MV, Tl, Vl)
         ctx.a2a = a2a
