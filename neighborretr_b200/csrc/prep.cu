@@ -272,25 +272,46 @@ namespace nr {
 __global__ void __launch_bounds__(256)
 gram_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, int Ra, int Rb, int d,
                 float* __restrict__ out, float* __restrict__ outT) {
-  __shared__ float As[32][33], Bs[32][33];
+  __shared__ float As[2][32][33], Bs[2][32][33];
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int k0 = 0; k0 < d; k0 += 32) {
+  // global -> registers one k-chunk ahead, registers -> the other smem buffer: one barrier per chunk and the
+  // global-load latency overlaps the FMAs of the previous chunk
+  float ra[4], rb[4];
+  auto gload = [&](int k0) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int e = it * 256 + threadIdx.x, r = e >> 5, c = e & 31;
-      As[r][c] = (i0 + r < Ra && k0 + c < d) ? a[(int64_t)(i0 + r) * d + k0 + c] : 0.f;
-      Bs[r][c] = (j0 + r < Rb && k0 + c < d) ? b[(int64_t)(j0 + r) * d + k0 + c] : 0.f;
+      ra[it] = (i0 + r < Ra && k0 + c < d) ? a[(int64_t)(i0 + r) * d + k0 + c] : 0.f;
+      rb[it] = (j0 + r < Rb && k0 + c < d) ? b[(int64_t)(j0 + r) * d + k0 + c] : 0.f;
     }
-    __syncthreads();
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = it * 256 + threadIdx.x, r = e >> 5, c = e & 31;
+      As[buf][r][c] = ra[it];
+      Bs[buf][r][c] = rb[it];
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < d; k0 += 32) {
+    const bool more = k0 + 32 < d;
+    if (more) gload(k0 + 32);
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-      const float a0 = As[ty * 2][k], a1 = As[ty * 2 + 1][k], b0 = Bs[tx * 2][k], b1 = Bs[tx * 2 + 1][k];
+      const float a0 = As[buf][ty * 2][k], a1 = As[buf][ty * 2 + 1][k];
+      const float b0 = Bs[buf][tx * 2][k], b1 = Bs[buf][tx * 2 + 1][k];
       acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
       acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
     }
+    if (more) sstore(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
   for (int p = 0; p < 2; ++p)
