@@ -120,6 +120,101 @@ sinkhorn_kernel(const float* __restrict__ G, const float* __restrict__ GT, int B
   }
 }
 
+// ---- grid variant with data-carrying exchange (the default for 128 < B when the slabs are resident) ---------
+// Same slabs and arithmetic as sinkhorn_kernel, but the half-iterations are not separated by a device-wide barrier:
+// every scaling/dual value is published as one aligned 8-byte {value, epoch} word and its consumers spin on the
+// word itself until the epoch of the previous half-iteration shows up.  One L2 round trip per half-iteration
+// instead of three (barrier atomic, barrier poll, vector load).  No slot is rewritten before every CTA has
+// consumed it: a CTA writes epoch e+2 into a slot only after it has read all values of epoch e+1, which exist
+// only after every CTA has read all values of epoch e.  The tag area is zeroed per launch (epochs start at 1).
+constexpr int SKT_THREADS = 512;
+constexpr int SKT_WARPS = SKT_THREADS / 32;
+
+__device__ __forceinline__ float wait_tagged(const uint2* slot, unsigned int epoch) {
+  uint2 w;
+  do {
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(slot) : "memory");
+  } while (w.y != epoch);
+  return __uint_as_float(w.x);
+}
+__device__ __forceinline__ void publish_tagged(uint2* slot, float v, unsigned int epoch) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+
+__global__ void __launch_bounds__(SKT_THREADS)
+sinkhorn_tag_kernel(const float* __restrict__ G, const float* __restrict__ GT, int B, int iters, int rows_per_cta,
+                    float* u1, float* v1, float* u2, float* v2, unsigned int* counter, float* gstat, uint2* tv) {
+  extern __shared__ float sm[];
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int nr = max(0, min(rows_per_cta, B - r0));
+  float* vs = sm;                                   // [2][B] staged source vectors (chain 1, chain 2)
+  float* mine = sm + 2 * (size_t)B;                 // [4][rows_per_cta] this CTA's latest u1, v1, u2, v2
+  float* Gs = mine + 4 * (size_t)rows_per_cta;
+  float* GTs = Gs + (size_t)rows_per_cta * B;
+  float mx = NR_NEG_INF, mn = INFINITY;
+  for (int e = tid; e < nr * B; e += SKT_THREADS) {
+    const float g = G[(size_t)r0 * B + e];
+    mx = fmaxf(mx, g); mn = fminf(mn, g);
+    Gs[e] = g; GTs[e] = GT[(size_t)r0 * B + e];
+  }
+  mx = block_max(mx, red);
+  mn = -block_max(-mn, red);
+  if (tid == 0) { gstat[2 * blockIdx.x] = mx; gstat[2 * blockIdx.x + 1] = mn; }
+  grid_barrier(counter, gridDim.x);                 // the only device-wide barrier: global max / min of G
+  mx = NR_NEG_INF; mn = INFINITY;
+  for (int c = tid; c < (int)gridDim.x; c += SKT_THREADS) {
+    mx = fmaxf(mx, __ldcg(gstat + 2 * c)); mn = fminf(mn, __ldcg(gstat + 2 * c + 1));
+  }
+  mx = block_max(mx, red);
+  mn = -block_max(-mn, red);
+  const float nu = -logf(2.0f * (float)B);
+  const bool scaling = (mx - mn) <= 30.f;
+  if (scaling)
+    for (int e = tid; e < nr * B; e += SKT_THREADS) { Gs[e] = expf(Gs[e] - mx); GTs[e] = expf(GTs[e] - mx); }
+  const float init = scaling ? 1.f : 0.f;
+  for (int e = tid; e < 4 * rows_per_cta; e += SKT_THREADS) mine[e] = init;
+  __syncthreads();
+  unsigned int epoch = 0;                           // epoch of the values the next half-iteration consumes
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      // half 0: (u1 <- rows of G with v1, u2 <- rows of G^T with v2); half 1: (v1 <- G^T with u1, v2 <- G with u2)
+      const uint2* s1 = tv + (size_t)(half ? 0 : 1) * B;
+      const uint2* s2 = tv + (size_t)(half ? 2 : 3) * B;
+      if (epoch == 0) {
+        for (int j = tid; j < B; j += SKT_THREADS) { vs[j] = init; vs[B + j] = init; }
+      } else {
+        for (int j = tid; j < B; j += SKT_THREADS) { vs[j] = wait_tagged(s1 + j, epoch); vs[B + j] = wait_tagged(s2 + j, epoch); }
+      }
+      __syncthreads();
+      ++epoch;
+      for (int w = warp; w < 2 * nr; w += SKT_WARPS) {
+        const int r = w >> 1, chain = w & 1;
+        const bool useT = (chain ^ half) != 0;
+        const float* row = (useT ? GTs : Gs) + (size_t)r * B;
+        float val;
+        if (scaling) val = 1.0f / warp_dot(row, vs + chain * B, B, lane);
+        else val = nu - warp_lse(row, vs + chain * B, B, lane);
+        if (lane == 0) {
+          const int which = chain * 2 + (half ? 1 : 0);
+          publish_tagged(tv + (size_t)which * B + r0 + r, val, epoch);
+          mine[which * rows_per_cta + r] = val;
+        }
+      }
+      __syncthreads();                              // vs is rewritten by the next half-iteration
+    }
+  }
+  // own rows of the duals; scaling domain -> log duals: u = (nu - max G) + log alpha, v = log beta
+  for (int r = tid; r < nr; r += SKT_THREADS) {
+    const float a1 = mine[0 * rows_per_cta + r], b1 = mine[1 * rows_per_cta + r];
+    const float a2 = mine[2 * rows_per_cta + r], b2 = mine[3 * rows_per_cta + r];
+    u1[r0 + r] = scaling ? (nu - mx) + logf(a1) : a1; v1[r0 + r] = scaling ? logf(b1) : b1;
+    u2[r0 + r] = scaling ? (nu - mx) + logf(a2) : a2; v2[r0 + r] = scaling ? logf(b2) : b2;
+  }
+}
+
 // ---- single-cluster variant (B <= ~600): the whole problem lives in the shared memory of one thread-block
 // cluster (<= 16 CTAs); the dual vectors are replicated in every CTA's shared memory and updated with DSMEM
 // stores, and half-iterations are separated by the hardware cluster barrier instead of a global-memory one.
@@ -422,7 +517,10 @@ static int sinkhorn_cluster_launch(const float* G, const float* GT, int B, int i
   return 0;
 }
 
-extern "C" size_t nr_sinkhorn_workspace_bytes(int64_t B) { (void)B; return 256 + 2 * 1024 * sizeof(float); }
+// [0,256): barrier counter; [256, 256+8K): per-CTA max/min; then 4*B tagged {value, epoch} words
+extern "C" size_t nr_sinkhorn_workspace_bytes(int64_t B) {
+  return 256 + 2 * 1024 * sizeof(float) + (size_t)4 * (size_t)B * 8;
+}
 
 extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
                            float* v2, void* workspace, size_t workspace_bytes, void* stream) {
@@ -477,13 +575,26 @@ extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters
   }
   size_t smem = ((size_t)2 * rows_per_cta * B + (size_t)2 * B) * sizeof(float);
   int resident = smem <= 200 * 1024;
+  int Bi = (int)B;
+  unsigned int* counter = (unsigned int*)workspace;
+  float* gstat = (float*)((char*)workspace + 256);
+  const char* var3 = getenv("NR_SINKHORN_VARIANT");
+  if (resident && grid <= 1024 && !(var3 && !strcmp(var3, "grid"))) {
+    // data-carrying exchange instead of device-wide barriers (sinkhorn_tag_kernel)
+    uint2* tv = (uint2*)((char*)workspace + 256 + 2 * 1024 * sizeof(float));
+    const size_t smem_t = smem + (size_t)4 * rows_per_cta * sizeof(float);
+    if (smem_t > 48 * 1024)
+      NR_CUDA(cudaFuncSetAttribute(sinkhorn_tag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    NR_CUDA(cudaMemsetAsync(workspace, 0, nr_sinkhorn_workspace_bytes(B), s));      // counter and every epoch tag
+    void* targs[] = {(void*)&G, (void*)&GT, (void*)&Bi, (void*)&iters, (void*)&rows_per_cta, (void*)&u1, (void*)&v1,
+                     (void*)&u2, (void*)&v2, (void*)&counter, (void*)&gstat, (void*)&tv};
+    NR_CUDA(cudaLaunchCooperativeKernel((void*)sinkhorn_tag_kernel, dim3(grid), dim3(SKT_THREADS), targs, smem_t, s));
+    return 0;
+  }
   if (!resident) smem = (size_t)2 * B * sizeof(float);
   if (smem > 48 * 1024)
     NR_CUDA(cudaFuncSetAttribute(sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NR_CUDA(cudaMemsetAsync(workspace, 0, 256, s));
-  int Bi = (int)B;
-  unsigned int* counter = (unsigned int*)workspace;
-  float* gstat = (float*)((char*)workspace + 256);
   void* args[] = {(void*)&G, (void*)&GT, (void*)&Bi, (void*)&iters, (void*)&rows_per_cta, (void*)&resident,
                   (void*)&u1, (void*)&v1, (void*)&u2, (void*)&v2, (void*)&counter, (void*)&gstat};
   NR_CUDA(cudaLaunchCooperativeKernel((void*)sinkhorn_kernel, dim3(grid), dim3(SK_THREADS), args, smem, s));
