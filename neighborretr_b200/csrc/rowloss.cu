@@ -201,6 +201,186 @@ row_losses_fwd_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------
+// forward, warp-per-row variant (B <= 32*VPL <= 1024): the row of X (and of G) lives in the registers of ONE warp,
+// VPL values per lane (column j = lane + 32*q), so every reduction is a shuffle tree and the k top-k rounds need
+// no block barrier at all; 4 rows (warps) per CTA.  Same arithmetic, same tie rules, same saved scalars as
+// row_losses_fwd_kernel (sums are taken in a different order: results agree to fp32 rounding).
+// ------------------------------------------------------------------------------------------
+constexpr int ROWW_WARPS = 4;
+
+template <int VPL>
+__global__ void __launch_bounds__(ROWW_WARPS * 32)
+row_losses_fwd_warp_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __restrict__ nbr_idx,
+                           float* __restrict__ saved) {
+  __shared__ float nb_x_s[ROWW_WARPS][NR_MAX_K], nb_a_s[ROWW_WARPS][NR_MAX_K];
+  __shared__ int nb_j_s[ROWW_WARPS][NR_MAX_K];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * ROWW_WARPS + warp;
+  if (i >= a.rows) return;                             // whole warp leaves together; no block-level barriers below
+  const int B = a.B, gi = a.row0 + i, rows = a.rows;
+  float* nb_x = nb_x_s[warp]; float* nb_a = nb_a_s[warp]; int* nb_j = nb_j_s[warp];
+  const bool need_g = (a.flags & (NR_LOSS_KL | NR_LOSS_UNIFORM)) != 0;
+  const float* Xr = a.X + (int64_t)i * a.ldx;
+  const float* Gr = need_g ? a.G + (int64_t)i * a.ldg : nullptr;
+  float x[VPL], g[VPL];
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    const int j = lane + 32 * q;
+    x[q] = j < B ? Xr[j] : NR_NEG_INF;
+    g[q] = (need_g && j < B) ? Gr[j] : NR_NEG_INF;
+  }
+  float* sv = saved + (int64_t)i * NR_NSAVE;
+  float* ro = row_out;
+  const float ls = load_ls(a.logit_scale);
+  float xdiag = 0.f;                                   // x[gi]: the lane holding it broadcasts (q unrolled: no dynamic indexing)
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    const float t = __shfl_sync(0xffffffffu, x[q], gi & 31);
+    if (q == (gi >> 5)) xdiag = t;
+  }
+  // ---- maxima and log-sum-exps
+  float mx = NR_NEG_INF, mg = NR_NEG_INF;
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) { mx = fmaxf(mx, x[q]); mg = fmaxf(mg, g[q]); }
+  mx = warp_max(mx);
+  mg = warp_max(mg);
+  float s_c = 0.f, s_x = 0.f, s_g = 0.f, s_tg = 0.f;
+#pragma unroll
+  for (int q = 0; q < VPL; ++q) {
+    if (lane + 32 * q < B) {
+      const float dx = x[q] - mx;
+      s_c += expf(ls * dx);
+      s_x += expf(dx);
+      if (need_g) {
+        const float dg = g[q] - mg;
+        s_g += expf(dg);
+        s_tg += expf(a.tau_uni * dg);
+      }
+    }
+  }
+  s_c = warp_sum(s_c); s_x = warp_sum(s_x);
+  const float lse_c = ls * mx + logf(s_c);
+  const float lse_x = mx + logf(s_x);
+  float lse_g = 0.f, lse_tg = 0.f;
+  if (need_g) {
+    s_g = warp_sum(s_g); s_tg = warp_sum(s_tg);
+    lse_g = mg + logf(s_g);
+    lse_tg = a.tau_uni * mg + logf(s_tg);
+  }
+  // ---- centrality-weighted InfoNCE row (until_module.py:315-324)
+  if ((a.flags & NR_LOSS_CENTRALITY) && lane == 0) {
+    const float wv = a.w ? a.w[i] : 1.f;
+    ro[0 * rows + i] = -wv * (ls * xdiag - lse_c);
+    sv[0] = lse_c;
+  }
+  // ---- KL row (until_module.py:351-357) and uniform cross-entropy with the Sinkhorn target (:253-291)
+  if (need_g) {
+    float klrow = 0.f, lurow = 0.f, sumT = 0.f;
+    const float nu = -logf(2.0f * (float)B);
+    const float ui = (a.flags & NR_LOSS_UNIFORM) ? a.sk_u[i] : 0.f;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int j = lane + 32 * q;
+      if (j < B) {
+        const float lp = x[q] - lse_x, lq = g[q] - lse_g;
+        klrow += expf(lp) * (lp - lq);
+        if (a.flags & NR_LOSS_UNIFORM) {
+          const float t = a.beta * expf(g[q] + ui + a.sk_v[j] - nu) + ((j == gi) ? (1.f - a.beta) : 0.f);
+          sumT += t;
+          lurow -= t * (a.tau_uni * g[q] - lse_tg);
+        }
+      }
+    }
+    klrow = warp_sum(klrow);
+    if (a.flags & NR_LOSS_UNIFORM) { lurow = warp_sum(lurow); sumT = warp_sum(sumT); }
+    if (lane == 0) {
+      if (a.flags & NR_LOSS_KL) ro[2 * rows + i] = klrow;
+      if (a.flags & NR_LOSS_UNIFORM) ro[3 * rows + i] = lurow;
+      sv[1] = lse_x; sv[2] = lse_g; sv[3] = klrow; sv[4] = lse_tg; sv[5] = sumT;
+    }
+  }
+  // ---- neighbour-adjusting row (until_module.py:161-211)
+  if (a.flags & NR_LOSS_NEIGHBOR) {
+    const int k = a.k;
+    uint32_t alive = 0;                                  // bit q: column lane+32q is still a candidate
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      const int j = lane + 32 * q;
+      if (j < B && j != gi) alive |= 1u << q;
+    }
+    // top-k of the off-diagonal entries: k rounds of warp arg-max, ties -> lower column
+    for (int r = 0; r < k; ++r) {
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int q = 0; q < VPL; ++q) {
+        if ((alive >> q) & 1u) {
+          const unsigned long long key = argmax_key(x[q], (uint32_t)(lane + 32 * q));
+          best = key > best ? key : best;
+        }
+      }
+      best = warp_max_u64(best);
+      const int jsel = (int)key_index(best);
+      if ((jsel & 31) == lane) alive &= ~(1u << (jsel >> 5));
+      if (lane == 0) {
+        nb_j[r] = jsel;
+        nb_x[r] = argmax_key_value(best);
+        nbr_idx[(int64_t)i * k + r] = jsel;
+      }
+    }
+    // min / max over the NON-extended entries of x and of the bank centrality c (until_module.py:77-85)
+    unsigned long long klo = 0ull, khi = 0ull, clo = 0ull, chi = 0ull;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+      if ((alive >> q) & 1u) {
+        const int j = lane + 32 * q;
+        const float v = x[q], c = a.cbank[j];
+        unsigned long long t;
+        t = argmin_key(v, j); klo = t > klo ? t : klo;
+        t = argmax_key(v, j); khi = t > khi ? t : khi;
+        t = argmin_key(c, j); clo = t > clo ? t : clo;
+        t = argmax_key(c, j); chi = t > chi ? t : chi;
+      }
+    }
+    klo = warp_max_u64(klo); khi = warp_max_u64(khi); clo = warp_max_u64(clo); chi = warp_max_u64(chi);
+    const float lo_x = argmin_key_value(klo), hi_x = argmax_key_value(khi);
+    const float lo_c = argmin_key_value(clo), hi_c = argmax_key_value(chi);
+    __syncwarp();
+    for (int r = lane; r < k; r += 32) {
+      const int j = nb_j[r];
+      const float nx = (nb_x[r] - lo_x) / (hi_x - lo_x);
+      const float nc = (a.cbank[j] - lo_c) / (hi_c - lo_c);
+      nb_a[r] = nx - nc;                                     // Eq. 5: de-centrality similarity
+    }
+    __syncwarp();
+    // softmax over the neighbours and the extended-set log-softmax, one neighbour per lane (strided for k > 32)
+    float ma = NR_NEG_INF, mext = xdiag;
+    for (int r = lane; r < k; r += 32) { ma = fmaxf(ma, a.tau_nbr * nb_a[r]); mext = fmaxf(mext, nb_x[r]); }
+    ma = warp_max(ma); mext = warp_max(mext);
+    float sa = 0.f, sext = 0.f;
+    for (int r = lane; r < k; r += 32) { sa += expf(a.tau_nbr * nb_a[r] - ma); sext += expf(nb_x[r] - mext); }
+    sa = warp_sum(sa);
+    sext = warp_sum(sext) + expf(xdiag - mext);
+    const float lse_ext = mext + logf(sext);
+    float num = 0.f, den = 0.f;
+    for (int r = lane; r < k; r += 32) {
+      const float p = expf(a.tau_nbr * nb_a[r] - ma) / sa;
+      num += p * (nb_x[r] - lse_ext);
+      den += p;
+    }
+    num = warp_sum(num) + (xdiag - lse_ext);               // diagonal weight 1 (until_module.py:157)
+    den = warp_sum(den) + 1.f;
+    if (lane == 0) {
+      ro[1 * rows + i] = -num / den;
+      sv[6] = lo_x; sv[7] = hi_x; sv[8] = lo_c; sv[9] = hi_c; sv[10] = lse_ext; sv[11] = den;
+      sv[12] = __int_as_float((int)key_index(klo));
+      sv[13] = __int_as_float((int)key_index(khi));
+      sv[14] = __int_as_float((int)key_index(clo));
+      sv[15] = __int_as_float((int)key_index(chi));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward: dX (dense row), dG (dense row), dc (atomic over rows), dw, d logit_scale
 // gscale[4] = upstream multipliers of the per-row terms {centrality, neighbour, kl, uniform}
 // ------------------------------------------------------------------------------------------
@@ -418,6 +598,16 @@ extern "C" int nr_row_losses_fwd(const float* X, int64_t ldx, const float* G, in
   if (flags & NR_LOSS_NEIGHBOR) NR_CHECK_ARG(nbr_idx != nullptr, "nr_row_losses_fwd: nbr_idx is null");
   RowArgs a{X, ldx, G, ldg, cbank, w, sk_u, sk_v, (int)rows, (int)B, (int)row0, logit_scale, k, tau_nbr,
             tau_uni, beta, flags};
+  if (B <= 1024) {        // the row fits the registers of one warp: no shared-memory staging, no block barriers
+    const unsigned grid = (unsigned)((rows + ROWW_WARPS - 1) / ROWW_WARPS);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 128) row_losses_fwd_warp_kernel<4><<<grid, ROWW_WARPS * 32, 0, st>>>(a, row_out, nbr_idx, saved);
+    else if (B <= 256) row_losses_fwd_warp_kernel<8><<<grid, ROWW_WARPS * 32, 0, st>>>(a, row_out, nbr_idx, saved);
+    else if (B <= 512) row_losses_fwd_warp_kernel<16><<<grid, ROWW_WARPS * 32, 0, st>>>(a, row_out, nbr_idx, saved);
+    else row_losses_fwd_warp_kernel<32><<<grid, ROWW_WARPS * 32, 0, st>>>(a, row_out, nbr_idx, saved);
+    NR_CHECK_LAUNCH("nr_row_losses_fwd(warp)");
+    return 0;
+  }
   size_t smem = row_smem((int)B);
   if (smem > 48 * 1024)
     NR_CUDA(cudaFuncSetAttribute(row_losses_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -67,8 +67,8 @@ class HeadPrologue:
                             and ops.maxsim2_supported(text.shape[1], video.shape[1], text.shape[2]))
         self.T = Prepared(text.detach(), bf16=bf, colsum=True, mask=self.tm if fk else None, defer=True)
         self.V = Prepared(video.detach(), bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True)
-        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True)
-        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True)
+        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk)
+        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk)
         B, M, d = self.T.r, self.MT.r, self.T.d
         if self.V.r != B or self.MV.r != M:
             raise RuntimeError("text/video batch sizes (or bank sizes) differ")

@@ -141,8 +141,8 @@ class ShardedPrologue:
             self.T = Prepared(self.text, bf16=bf, colsum=True, mask=None, defer=True)
             self.Tl = self.T.block(lo, b)
         self.V = Prepared(self.video, bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True)
-        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True)
-        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True)
+        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk)
+        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk)
         self.Vl = self.V.block(lo, b)
         self.t_rows = B * nt
         self.GG = torch.empty(2, B, B, **f32)              # [G ; G^T], replicated
