@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "nrhead_internal.h"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace nr {
 using namespace tc;
@@ -84,7 +85,11 @@ __device__ __forceinline__ void set_barrier(int set) {      // named barrier 1 /
   else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 
-template <int NY, int GL>
+// CL2 (opt-in, see nr_maxsim2_fwd): CTA pairs (clusters of 2).  The two CTAs of a pair work on the SAME Y box and
+// adjacent X boxes; each loads half of the Y box and multicasts it to both, which halves the L2 reads of the dominant
+// operand.  The leader CTA claims pair-tiles and publishes them into both rings; smem stages are released by both
+// MMA issuers.
+template <int NY, int GL, bool CL2>
 __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __grid_constant__ Tc2Args a) {
   constexpr int CH = t2_lcm(NY, GL);       // accumulator columns per epilogue chunk: whole samples, whole groups
   constexpr int SPC = CH / NY;             // Y samples per chunk
@@ -109,12 +114,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring + T2_RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cr = CL2 ? cluster_ctarank() : 0u;       // rank in the CTA pair; 0 = leader
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < a.nprob; ++p) { tma_prefetch_desc(&a.tmx[p]); tma_prefetch_desc(&a.tmy[p]); }
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CL2 ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, T2_SET); }
-    for (int s = 0; s < T2_RING; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, 1 + T2_SET); }
+    // ring: filled by the (leader's) scheduler; released by the MMA issuer and one epilogue set of every CTA of the
+    // pair, plus the non-leader's TMA producer
+    for (int s = 0; s < T2_RING; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, CL2 ? 2 * (1 + T2_SET) + 1 : 1 + T2_SET); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -123,8 +131,19 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();                            // the peer's barriers are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // consumers of a ring slot: read the tile, release the slot on the LEADER's barrier
+  auto ring_take = [&](int it) {
+    const int slot = it & (T2_RING - 1);
+    if (CL2) mbar_wait_cluster(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
+    else mbar_wait(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
+    const int tile = ring[slot];
+    if (CL2) mbar_arrive_remote(rempty + slot, 0);
+    else mbar_arrive(rempty + slot);
+    return tile;
+  };
 
   // tile index -> (problem, m-tile, n-tile); n fastest so that concurrently running CTAs share the X box in L2
   auto decode = [&](int tile, int& p, int& mt, int& nt) {
@@ -133,6 +152,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
     const int local = tile - a.p[p].tile0;
     mt = local / a.p[p].n_nt;
     nt = local - mt * a.p[p].n_nt;
+    if (CL2) mt = 2 * mt + (int)cr;                      // a pair-tile = two adjacent X boxes against one Y box
   };
 
   if (warp == 0) {
@@ -144,27 +164,53 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
       // another kernel of the step graph (the persistent grid is one CTA per SM) simply takes fewer tiles.
       for (int n = 0;; ++n) {
         const int slot = n & (T2_RING - 1);
-        mbar_wait(rempty + slot, ((uint32_t)(n / T2_RING) & 1u) ^ 1u);
-        int tile = (int)atomicAdd(a.tile_counter, 1u);
-        if (tile >= a.n_tiles) tile = -1;
-        ring[slot] = tile;
-        mbar_arrive(rfull + slot);                       // release: the ring entry is visible to the waiters
-        if (tile < 0) {                                  // the other epilogue set reads the NEXT slot: end it too
-          const int slot2 = (n + 1) & (T2_RING - 1);
-          mbar_wait(rempty + slot2, ((uint32_t)((n + 1) / T2_RING) & 1u) ^ 1u);
-          ring[slot2] = -1;
-          mbar_arrive(rfull + slot2);
-          break;
+        int tile;
+        if (!CL2 || cr == 0) {
+          if (CL2) mbar_wait_cluster(rempty + slot, ((uint32_t)(n / T2_RING) & 1u) ^ 1u);
+          else mbar_wait(rempty + slot, ((uint32_t)(n / T2_RING) & 1u) ^ 1u);
+          tile = (int)atomicAdd(a.tile_counter, 1u);
+          if (tile >= a.n_tiles) tile = -1;
+          ring[slot] = tile;
+          if (CL2) {
+            st_remote_u32(ring + slot, 1, (uint32_t)tile);
+            mbar_arrive_remote(rfull + slot, 1);
+            mbar_arrive_remote(rfull + slot, 0);
+          } else {
+            mbar_arrive(rfull + slot);                     // release: the ring entry is visible to the waiters
+          }
+          if (tile < 0) {                                  // the other epilogue set reads the NEXT slot: end it too
+            const int slot2 = (n + 1) & (T2_RING - 1);
+            if (CL2) mbar_wait_cluster(rempty + slot2, ((uint32_t)((n + 1) / T2_RING) & 1u) ^ 1u);
+            else mbar_wait(rempty + slot2, ((uint32_t)((n + 1) / T2_RING) & 1u) ^ 1u);
+            ring[slot2] = -1;
+            if (CL2) {
+              st_remote_u32(ring + slot2, 1, (uint32_t)-1);
+              mbar_arrive_remote(rfull + slot2, 1);
+              mbar_arrive_remote(rfull + slot2, 0);
+            } else {
+              mbar_arrive(rfull + slot2);
+            }
+            break;
+          }
+        } else {                                           // non-leader producer: a consumer of the leader's ring
+          tile = ring_take(n);
+          if (tile < 0) { ring_take(n + 1); break; }       // the second end marker frees its slot like the others
         }
         int p, mt, nt;
         decode(tile, p, mt, nt);
         const int row_x = mt * a.MU, row_y = nt * a.SY * NY;
         for (int kb = 0; kb < a.num_kb; ++kb) {
-          mbar_wait(empty + stage, phase ^ 1);
+          mbar_wait(empty + stage, phase ^ 1);             // CL2: released by BOTH MMA issuers (count 2)
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           mbar_expect_tx(full + stage, tx_bytes);
           tma_load_2d(sa, &a.tmx[p], full + stage, kb * T2_BK, row_x);
-          tma_load_2d(sa + T2_A_BYTES, &a.tmy[p], full + stage, kb * T2_BK, row_y);
+          if (CL2) {                                       // my half of the Y box, to both CTAs of the pair
+            const int hb = a.SY * NY / 2;
+            tma_load_2d_mc(sa + T2_A_BYTES + (size_t)cr * hb * 128, &a.tmy[p], full + stage, kb * T2_BK,
+                           row_y + (int)cr * hb, (uint16_t)3);
+          } else {
+            tma_load_2d(sa + T2_A_BYTES, &a.tmy[p], full + stage, kb * T2_BK, row_y);
+          }
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -175,11 +221,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
       const uint32_t idesc = umma_idesc_bf16(T2_BM, a.UN);
       int stage = 0; uint32_t phase = 0;
       for (int it = 0;; ++it) {
-        const int slot = it & (T2_RING - 1);
-        mbar_wait(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
-        const int tile = ring[slot];
-        mbar_arrive(rempty + slot);
-        if (tile < 0) break;
+        const int tile = ring_take(it);
+        if (tile < 0) { if (CL2) ring_take(it + 1); break; }
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(tempty + acc, acc_phase ^ 1);          // epilogue drained this accumulator
@@ -194,7 +237,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
 #pragma unroll
           for (int k = 0; k < T2_BK / 16; ++k)           // advance 32 B (16 bf16) inside the swizzle row
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          umma_commit(empty + stage);                    // smem slot free when these MMAs retire
+          if (CL2) umma_commit_mc(empty + stage, (uint16_t)3);   // the peer multicasts into this stage too
+          else umma_commit(empty + stage);               // smem slot free when these MMAs retire
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull + acc);                        // accumulator ready for the epilogue
@@ -218,10 +262,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
     uint32_t* const kg_row = kgs + (r / GL) * a.kg_ld + (lane & (int)LOWM);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * T2_ACC_COLS);
     for (int it = set;; it += 2) {
-      const int slot = it & (T2_RING - 1);
-      mbar_wait(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
-      const int tile = ring[slot];
-      mbar_arrive(rempty + slot);
+      const int tile = ring_take(it);
       if (tile < 0) break;
       int pi, mt, nt;
       decode(tile, pi, mt, nt);
@@ -229,7 +270,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
       const uint32_t acc_phase = (it >> 1) & 1;
       const int ry0 = nt * a.SY;
       const int sy_n = min(a.SY, P.Ry - ry0);
-      const int sx_n = min(a.SX, P.Rx - mt * a.SX);
+      const int sx_n = max(0, min(a.SX, P.Rx - mt * a.SX));    // 0: the odd X box of the last pair-tile
       const int n_ch = (sy_n + SPC - 1) / SPC;
       const int ncols = sy_n * NY;
       const int rx = mt * a.SX + sx;
@@ -343,6 +384,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
@@ -350,24 +392,42 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
 }
 
 template <int NY, int GL>
-static int launch2(const Tc2Args& a, size_t smem, int grid, cudaStream_t stream) {
-  NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  maxsim2_fwd_tc_kernel<NY, GL><<<grid, T2_THREADS, smem, stream>>>(a);
+static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, cudaStream_t stream) {
+  if (pair) {
+    // CTA pairs: thread-block clusters of 2 (same TPC), multicast of the shared Y box
+    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(T2_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NR_CUDA(cudaLaunchKernelEx(&cfg, maxsim2_fwd_tc_kernel<NY, GL, true>, a));
+    return 0;
+  }
+  NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  maxsim2_fwd_tc_kernel<NY, GL, false><<<grid, T2_THREADS, smem, stream>>>(a);
   NR_CHECK_LAUNCH("nr_maxsim2_fwd");
   return 0;
 }
 
 template <int GL>
-static int dispatch_ny(int Ny, const Tc2Args& a, size_t smem, int grid, cudaStream_t stream) {
+static int dispatch_ny(int Ny, const Tc2Args& a, size_t smem, int grid, bool pair, cudaStream_t stream) {
   switch (Ny) {
-    case 4: return launch2<4, GL>(a, smem, grid, stream);
-    case 8: return launch2<8, GL>(a, smem, grid, stream);
-    case 12: return launch2<12, GL>(a, smem, grid, stream);
-    case 16: return launch2<16, GL>(a, smem, grid, stream);
-    case 24: return launch2<24, GL>(a, smem, grid, stream);
-    case 32: return launch2<32, GL>(a, smem, grid, stream);
-    case 48: return launch2<48, GL>(a, smem, grid, stream);
-    case 64: return launch2<64, GL>(a, smem, grid, stream);
+    case 4: return launch2<4, GL>(a, smem, grid, pair, stream);
+    case 8: return launch2<8, GL>(a, smem, grid, pair, stream);
+    case 12: return launch2<12, GL>(a, smem, grid, pair, stream);
+    case 16: return launch2<16, GL>(a, smem, grid, pair, stream);
+    case 24: return launch2<24, GL>(a, smem, grid, pair, stream);
+    case 32: return launch2<32, GL>(a, smem, grid, pair, stream);
+    case 48: return launch2<48, GL>(a, smem, grid, pair, stream);
+    case 64: return launch2<64, GL>(a, smem, grid, pair, stream);
     default:
       nr::set_error("nr_maxsim2_fwd: Ny=%d has no tensor-core instantiation (4,8,12,16,24,32,48,64)", Ny);
       return -3;
@@ -418,6 +478,19 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
   a.kg_ld = a.UN;
   if (GL == 8) { while (a.kg_ld % 32 != 8 && a.kg_ld % 32 != 24) a.kg_ld += 8; }
   else { while (a.kg_ld % 8 != 4) a.kg_ld += 4; }
+  // CTA pairs when the Y box splits into two swizzle-aligned halves and there is more than a wave of work
+  int dev = 0, sms = 0;
+  NR_CUDA(cudaGetDevice(&dev));
+  NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int64_t est_tiles = 0;
+  for (int i = 0; i < nprob; ++i)
+    est_tiles += ((probs[i].Rx + a.SX - 1) / a.SX) * ((probs[i].Ry + a.SY - 1) / a.SY);
+  // Opt-in (NR_TC2_PAIR=1): measured SLOWER than independent CTAs on B200 (MSR-VTT step 80 vs 75 us, b=1024 812 vs 760 us,
+  // ActivityNet tiles 554 vs 486 us): the multicast halves the L2 slice reads but every SM still ingests the whole
+  // Y box, and the shared stage release couples the two CTAs' pipelines.  Kept for the cta_group::2 follow-up.
+  bool pair = false;
+  if (const char* ev = getenv("NR_TC2_PAIR"))
+    pair = atoi(ev) != 0 && (a.SY * (int)Ny) % 16 == 0 && a.UN == a.SY * (int)Ny && est_tiles >= 2 * sms;
   int tiles = 0;
   for (int i = 0; i < nprob; ++i) {
     const nr_maxsim2_problem& q = probs[i];
@@ -429,9 +502,9 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
     P.n_mt = (int)((q.Rx + a.SX - 1) / a.SX);
     P.n_nt = (int)((q.Ry + a.SY - 1) / a.SY);
     P.tile0 = tiles;
-    tiles += P.n_mt * P.n_nt;
+    tiles += (pair ? (P.n_mt + 1) / 2 : P.n_mt) * P.n_nt;        // pair-tiles: two adjacent X boxes x one Y box
     if (int e = make_tmap_bf16(&a.tmx[i], q.x_bf16, q.Rx * Nx, d, a.MU)) return e;
-    if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny)) return e;
+    if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny / (pair ? 2 : 1))) return e;
   }
   a.n_tiles = tiles;
   a.tile_counter = (unsigned int*)workspace;
@@ -444,10 +517,8 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
   NR_CHECK_ARG(stages >= 2, "nr_maxsim2_fwd: tile does not fit shared memory");
   a.stages = stages;
   const size_t smem = (size_t)stages * (T2_A_BYTES + a.b_bytes) + tail + 1024;
-  int dev = 0, sms = 0;
-  NR_CUDA(cudaGetDevice(&dev));
-  NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = tiles < sms ? tiles : sms;
-  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, (cudaStream_t)stream);
-  return dispatch_ny<4>((int)Ny, a, smem, grid, (cudaStream_t)stream);
+  int grid = tiles < sms ? tiles : sms;
+  if (pair) grid = 2 * (tiles < sms / 2 ? tiles : sms / 2);
+  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, pair, (cudaStream_t)stream);
+  return dispatch_ny<4>((int)Ny, a, smem, grid, pair, (cudaStream_t)stream);
 }

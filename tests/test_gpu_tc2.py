@@ -66,6 +66,13 @@ def test_fused_forward_matches_emulation(rx, nx, ry, ny):
     _check_problem(X, Y, wx, wy, 0.5, out, out2, saved[0])
 
 
+def test_fused_forward_cta_pair_multicast(monkeypatch):
+    """Opt-in CTA-pair variant (clusters of 2, TMA multicast of the shared Y box): same results."""
+    monkeypatch.setenv("NR_TC2_PAIR", "1")
+    test_fused_forward_matches_emulation(128, 24, 512, 12)
+    test_fused_forward_matches_emulation(131, 24, 300, 12)       # odd number of X boxes: a dummy half pair-tile
+
+
 def test_fused_forward_three_problems_one_launch():
     """The batch pair and the two bank pairs of a head step as one tile list."""
     d, nt, nv, b, m = 512, 24, 12, 50, 70
