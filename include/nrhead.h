@@ -107,7 +107,8 @@ int nr_maxsim_fwd(int precision, const void* xn, const void* yn, const float* wx
  * x token; pmax_y [Rx,Ry,Ny] f32 / xstar [Rx,Ry,Ny] u8 = max / arg-max over x for every y token (pmax_y carries
  * 3 fewer mantissa bits: the column arg-max travels in the low bits of the value).  Ties -> lower index.
  * Up to 4 problems with the same (Nx, Ny, d) share one persistent launch.  workspace: >= 16 bytes of device memory
- * (zeroed by the library on `stream`): the tile counter of the dynamic scheduler. */
+ * holding the counters of the dynamic tile scheduler: ZERO before the first launch that uses it; every launch leaves
+ * it zeroed again (no memset between launches).  One workspace per concurrently used stream. */
 typedef struct {
   const void* x_bf16; const void* y_bf16;
   const float* wx; const float* wy;

@@ -190,6 +190,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
             } else {
               mbar_arrive(rfull + slot2);
             }
+            // the workspace resets itself: the last claimer to finish (every claimer has made its final claim by
+            // then) zeroes both counters, so no memset has to precede the next launch
+            const unsigned int claimers = CL2 ? gridDim.x / 2 : gridDim.x;
+            if (atomicAdd(a.tile_counter + 1, 1u) == claimers - 1) {
+              atomicExch(a.tile_counter, 0u);
+              atomicExch(a.tile_counter + 1, 0u);
+              __threadfence();
+            }
             break;
           }
         } else {                                           // non-leader producer: a consumer of the leader's ring
@@ -507,8 +515,7 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
     if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny / (pair ? 2 : 1))) return e;
   }
   a.n_tiles = tiles;
-  a.tile_counter = (unsigned int*)workspace;
-  NR_CUDA(cudaMemsetAsync(workspace, 0, 16, (cudaStream_t)stream));
+  a.tile_counter = (unsigned int*)workspace;        // {next tile, finished claimers}: zero on entry, zero again on exit
   const size_t tail = (size_t)2 * T2_BM * a.hp_ld * 4 + (size_t)2 * (T2_BM / GL) * a.kg_ld * 4 +
                       (size_t)2 * a.SX * a.UN * 4 + (size_t)2 * a.UN * 4 + 512;
   const size_t budget = 227 * 1024 - 1024;   // alignment slack

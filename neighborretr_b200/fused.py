@@ -252,9 +252,10 @@ class HeadFunction(torch.autograd.Function):
             _call("nr_transpose_add", _p(dS1), B, _p(dS2), B, _p(dS), B, B, B, 1.0, 1.0, _stream())
             ev_dS = torch.cuda.Event()
             ev_dS.record()
-            with fj.on(1):
+
+            def global_path():
                 _call("nr_transpose_add", _p(dG1), B, _p(dG2), B, _p(dG), B, B, B, 1.0, 1.0, _stream())
-                if need[2]:
+                if need[2]:       # dgT = dG gV, dgV = dG^T gT (library GEMMs, fp32)
                     torch.mm(dG, v2, out=dgt)
                 if need[3]:
                     torch.mm(dG.t(), g2, out=dgv)
@@ -262,6 +263,9 @@ class HeadFunction(torch.autograd.Function):
                       _p(dgt), 1, _p(dmean[0]), _stream(), launches=2)
                 _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows,
                       _p(dgv), 1, _p(dmean[1]), _stream(), launches=2)
+
+            with fj.on(1):
+                global_path()
             if ctx.fusedk:
                 # one routing matrix per pair, applied from either side; ALL contractions in one launch (the text
                 # gradient accumulates over [video ; bank-video] sources, the video gradient over [text ; bank-text])

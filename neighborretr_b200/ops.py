@@ -254,6 +254,18 @@ def maxsim2_supported(nx, ny, d):
     return bool(_lib.load().nr_maxsim2_supported(nx, ny, d))
 
 
+_TILE_WS = {}
+
+
+def _tile_workspace(dev):
+    """Persistent, self-resetting scheduler counters: one zero-initialised 16-byte buffer per (device, stream)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _TILE_WS.get(key)
+    if ws is None:
+        ws = _TILE_WS[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+    return ws
+
+
 def maxsim2_fwd(problems, keep=True):
     """Fused two-direction max-sim (nr_maxsim2_fwd) of up to 4 problems in ONE launch.  Each problem is a dict with
     X, Y (Prepared with zeroed masked tokens), wx, wy, alpha, out, strides=(sr, sc) and optionally out2, strides2.
@@ -285,7 +297,7 @@ def maxsim2_fwd(problems, keep=True):
         a.out2 = o2.data_ptr() if o2 is not None else None
         a.out2_sr, a.out2_sc = q.get("strides2", (0, 0))
         a.pmax_x, a.ystar, a.pmax_y, a.xstar = [t.data_ptr() if t is not None else None for t in sv]
-    ws = torch.empty(4, dtype=torch.int32, device=dev)          # tile counter of the dynamic scheduler
+    ws = _tile_workspace(dev)                                   # counters of the dynamic tile scheduler
     _call("nr_maxsim2_fwd", ctypes.cast(arr, ctypes.c_void_p), len(problems), nx, ny, d, _p(ws), _stream())
     return saved
 
