@@ -196,6 +196,45 @@ __global__ void centrality_dmean_kernel(const float* __restrict__ gn, const floa
   }
 }
 
+// both parts of the centrality backward in ONE launch: blocks [0, nrb) = the per-row gradient w.r.t. the global
+// features (centrality_rows_bwd_kernel), the remaining blocks = the gradient w.r.t. the token mean (32 columns each)
+__global__ void __launch_bounds__(PREP_WARPS * 32)
+centrality_bwd_kernel(const float* __restrict__ mean_vec, const float* __restrict__ gn, const float* __restrict__ ginv,
+                      const float* __restrict__ w, const float* __restrict__ dw, int B, int d, float cs, float inv_rows,
+                      float* __restrict__ dg, int accumulate, float* __restrict__ dmean, int nrb) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x < nrb) {
+    const int row = blockIdx.x * PREP_WARPS + warp;
+    if (row >= B) return;
+    const float dcv = cs * w[row] * dw[row];
+    const float* nrow = gn + (int64_t)row * d;
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32) dot += nrow[c] * mean_vec[c];
+    dot = warp_sum(dot) * dcv;               // <gn, dgn>, dgn = dc * mean
+    const float inv = ginv[row];
+    if (inv >= 1e12f) dot = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float o = (dcv * mean_vec[c] - nrow[c] * dot) * inv;
+      float* p = dg + (int64_t)row * d + c;
+      *p = accumulate ? (*p + o) : o;
+    }
+  } else {
+    __shared__ float sm[PREP_WARPS][33];
+    const int c = ((int)blockIdx.x - nrb) * 32 + lane;
+    float s = 0.f;
+    if (c < d)
+      for (int a = warp; a < B; a += PREP_WARPS) s += cs * w[a] * dw[a] * gn[(int64_t)a * d + c];
+    sm[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && c < d) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < PREP_WARPS; ++q) t += sm[q][lane];
+      dmean[c] = t * inv_rows;
+    }
+  }
+}
+
 }  // namespace nr
 
 using namespace nr;
@@ -251,6 +290,13 @@ extern "C" int nr_centrality_bwd(const float* mean_vec, const float* gn, const f
   NR_CHECK_ARG(mean_vec && gn && ginv && w && dw && B > 0 && d > 0 && rows_total > 0,
                "nr_centrality_bwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
+  if (dg && dmean) {
+    const int nrb = (int)((B + PREP_WARPS - 1) / PREP_WARPS);
+    centrality_bwd_kernel<<<(unsigned)(nrb + (d + 31) / 32), PREP_WARPS * 32, 0, s>>>(
+        mean_vec, gn, ginv, w, dw, (int)B, (int)d, cs, 1.0f / (float)rows_total, dg, accumulate, dmean, nrb);
+    NR_CHECK_LAUNCH("nr_centrality_bwd");
+    return 0;
+  }
   if (dg) {
     centrality_rows_bwd_kernel<<<(unsigned)((B + PREP_WARPS - 1) / PREP_WARPS), PREP_WARPS * 32, 0, s>>>(
         mean_vec, gn, ginv, w, dw, (int)B, (int)d, cs, dg, accumulate);

@@ -248,24 +248,34 @@ class HeadFunction(torch.autograd.Function):
                       _p(dG2), B, _p(dc[0]), _p(dw[1]), _p(dls), _stream())
         # ---- fork 2: token-pair contractions (main: text side, side 0: video side), global path (side 1),
         #      token-weight gradients (side 2)
-        with ops.ForkJoin(3) as fj:
+        with ops.ForkJoin(4) as fj:
             _call("nr_transpose_add", _p(dS1), B, _p(dS2), B, _p(dS), B, B, B, 1.0, 1.0, _stream())
             ev_dS = torch.cuda.Event()
             ev_dS.record()
 
-            def global_path():
-                _call("nr_transpose_add", _p(dG1), B, _p(dG2), B, _p(dG), B, B, B, 1.0, 1.0, _stream())
-                if need[2]:       # dgT = dG gV, dgV = dG^T gT (library GEMMs, fp32)
-                    torch.mm(dG, v2, out=dgt)
+            def global_path(ev_dG=None):
+                # dgT = dG gV, dgV = dG^T gT (library GEMMs, fp32), each followed by its centrality backward; the video
+                # half runs on its own branch once dG exists
+                if ev_dG is None:
+                    _call("nr_transpose_add", _p(dG1), B, _p(dG2), B, _p(dG), B, B, B, 1.0, 1.0, _stream())
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    if need[2]:
+                        torch.mm(dG, v2, out=dgt)
+                    _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs,
+                          T.rows, _p(dgt), 1, _p(dmean[0]), _stream())
+                    return ev
+                torch.cuda.current_stream().wait_event(ev_dG)
                 if need[3]:
                     torch.mm(dG.t(), g2, out=dgv)
-                _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs, T.rows,
-                      _p(dgt), 1, _p(dmean[0]), _stream(), launches=2)
                 _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows,
-                      _p(dgv), 1, _p(dmean[1]), _stream(), launches=2)
+                      _p(dgv), 1, _p(dmean[1]), _stream())
+                return None
 
             with fj.on(1):
-                global_path()
+                ev_dG = global_path()
+            with fj.on(3):
+                global_path(ev_dG)
             if ctx.fusedk:
                 # one routing matrix per pair, applied from either side; ALL contractions in one launch (the text
                 # gradient accumulates over [video ; bank-video] sources, the video gradient over [text ; bank-text])

@@ -595,14 +595,16 @@ class TokenWeightsFunction(torch.autograd.Function):
         _call("nr_token_weights_bwd", _p(h), int(lp), _p(w), _p(dwa), _p(dwb), Ra, Ra + Rb, N, _p(w2c), H, _p(dh),
               _p(partials), st)
         dw1 = dx = None
-        with _tf32(ctx.mode == MLP_TF32):
-            if need[4]:
-                dw1 = _dw1_splitk(dh[:Ta], xa2)
-                if Rb:
-                    dw1 += _dw1_splitk(dh[Ta:], xb2)
-            if need[0]:
-                dx = (torch.mm(dh[:Ta], w1c, out_dtype=torch.float32) if lp else dh[:Ta] @ w1c).reshape(ctx.xshape)
-        _call("nr_vec_sums", _p(partials), 2 * H + 1, nch, None, _p(sums), st)
+        with ForkJoin(1) as fj:
+            with fj.on(0):                        # bias / second-layer gradients next to the GEMMs
+                _call("nr_vec_sums", _p(partials), 2 * H + 1, nch, None, _p(sums), _stream())
+            with _tf32(ctx.mode == MLP_TF32):
+                if need[4]:
+                    dw1 = _dw1_splitk(dh[:Ta], xa2)
+                    if Rb:
+                        dw1 += _dw1_splitk(dh[Ta:], xb2)
+                if need[0]:
+                    dx = (torch.mm(dh[:Ta], w1c, out_dtype=torch.float32) if lp else dh[:Ta] @ w1c).reshape(ctx.xshape)
         db1 = sums[:H] if need[5] else None
         dw2 = sums[H:2 * H].reshape(1, H) if need[6] else None
         db2 = sums[2 * H:] if need[7] else None
