@@ -467,14 +467,18 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
     recv = _all_to_all_blocks(dS_col.view(b, W, b).permute(1, 0, 2))                         # [r, v, a]
     dP = dS_row.view(b, W, b) + recv.permute(2, 0, 1)
     dP = dP.view(b, B)
-    # global similarity: dG has a row block (direction 1) and a column block (direction 2) on this rank
+    # global similarity: dG has a row block (direction 1) and a column block (direction 2) on this rank; its two
+    # library GEMMs run on their own branch next to the contraction (buffers allocated here, before the fork)
     dG = torch.zeros(B, B, **f32)
-    dG[lo:lo + b] += dG1
-    dG[:, lo:lo + b] += dG2.t()
-    dg_all = dG @ v2                                               # partial over ranks
-    dv_all = dG.t() @ g2
-    dg_all[lo:lo + b] += dgl[0]
-    dv_all[lo:lo + b] += dgl[1]
+    dg_all = torch.empty(B, d, **f32); dv_all = torch.empty(B, d, **f32)
+
+    def global_path():
+        dG[lo:lo + b] += dG1
+        dG[:, lo:lo + b] += dG2.t()
+        torch.mm(dG, v2, out=dg_all)                               # partial over ranks
+        torch.mm(dG.t(), g2, out=dv_all)
+        dg_all[lo:lo + b] += dgl[0]
+        dv_all[lo:lo + b] += dgl[1]
     # ---- token-pair products: text rows complete locally, video rows partial over ranks
     dtn_l = torch.zeros(Tl.rows, d, **f32); dvn = torch.zeros(V.rows, d, **f32)
     dtw_l = torch.zeros(b, nt, **f32); dvw = torch.zeros(B, nv, **f32)
@@ -483,7 +487,9 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
     vw_l = vw[lo:lo + b]
     dtext = torch.empty_like(Tl.xn); dvideo_all = torch.empty_like(V.xn)
     sc = 0.5 / M
-    with ops.ForkJoin(1) as fj:
+    with ops.ForkJoin(2) as fj:
+        with fj.on(1):
+            global_path()
         with fj.on(0):                           # weight gradients NEXT TO the contraction, not after it
             ops.maxsim2_bwd_w(p1, p2, dP, B, 1, 0.5, b, nt, B, nv, dtw_l, dvw)
             ops.maxsim2_bwd_w(pA, pB, dc_l[0], 1, 0, sc, b, nt, M, nv, dtw_l, dvw_mb)
