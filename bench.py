@@ -349,8 +349,8 @@ def run_ours(args):
     # max directions from the same accumulator tile.  Algorithmic flops of a rank-step's forward contractions
     # (SURVEY.md §8(d)): every S entry and every bank entry counted ONCE globally, un-padded tokens only:
     #   2*Nt*Nv*D * (b*B + 2*b*M)   with b = per-rank rows.
-    # Executed MMA work: x 128/120 * 256/240 tile padding at 24/12 tokens and, for W > 1, a rank computes both a row
-    # block and a column block of S (x2 on the b*B term).
+    # Executed MMA work: x 128/120 * 256/240 tile padding at 24/12 tokens; for W > 1 a rank contracts only its text rows
+    # (the column block arrives by an all-to-all of [b,b] similarity blocks), so executed = algorithmic there too.
     flops_step = flops_maxsim(B_PER_GPU, B, nt, nv) + 2 * flops_maxsim(B_PER_GPU, mrows, nt, nv)
     n_l = max(kt["launches"], 1)
     achieved = flops_step * ksteps / (kt["ms"] * 1e-3) / 1e12 if kt["ms"] > 0 else 0.0

@@ -63,13 +63,8 @@ int nr_prep_tokens(const float* x, int64_t rows, int64_t d, float* xn_f32, void*
 int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* dxn, const float* add_vec,
                        const int64_t* mask, int64_t rows, int64_t d, float* dx, int accumulate, void* stream);
 
-/* ---- token-weight MLP (modeling.py:148-153), hidden-layer backward in one pass ----------------
- * h [T,H] post-ReLU activations, dlogit [T], w2 [H]  ->  dh [T,H] = dlogit*w2*(h>0) and per-CTA partials
- * [2H, nr_mlp_chunks(T)] whose row sums are db1 (rows 0..H) and dw2 (rows H..2H).  The GEMMs of the MLP stay
- * library calls (cuBLAS). */
+/* chunks of 32 token rows: column count of the partial-sum buffer of nr_token_weights_bwd */
 int64_t nr_mlp_chunks(int64_t T);
-int nr_mlp_hidden_bwd(const float* h, const float* dlogit, const float* w2, int64_t T, int64_t H, float* dh,
-                      float* partials, void* stream);
 
 /* ---- token weights (modeling.py:485-492): second layer + masked softmax over the tokens of each sample --------
  * h [R*N, H] post-ReLU hidden activations (first layer = library GEMM; f32, or bf16 when h_bf16 != 0 — then dh of

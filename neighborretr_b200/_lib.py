@@ -26,7 +26,6 @@ SIGNATURES = {
     "nr_prep_tokens": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "nr_prep_tokens_bwd": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I, _P]),
     "nr_mlp_chunks": (_I64, [_I64]),
-    "nr_mlp_hidden_bwd": (_I, [_P, _P, _P, _I64, _I64, _P, _P, _P]),
     "nr_token_weights_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
     "nr_token_weights_bwd": (_I, [_P, _I, _P, _P, _P, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
     "nr_maxsim_fwd": (_I, [_I, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _P, _I64, _I64, _P, _I64,

@@ -506,54 +506,10 @@ token_weights_bwd_kernel(const HT* __restrict__ h, const float* __restrict__ w, 
   }
 }
 
-__global__ void __launch_bounds__(256)
-mlp_hidden_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dlogit, const float* __restrict__ w2,
-                      int T, int H, float* __restrict__ dh, float* __restrict__ partials, int nchunks) {
-  const int chunk = blockIdx.x, t0 = chunk * MLPB_ROWS, t1 = min(T, t0 + MLPB_ROWS);
-  for (int c = threadIdx.x * 4; c < H; c += 256 * 4) {
-    const float4 w = *reinterpret_cast<const float4*>(w2 + c);
-    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sw = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int tb = t0; tb < t1; tb += 8) {                 // 8 independent 16-byte loads in flight per thread
-      float4 hv[8]; float dv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int t = min(tb + i, t1 - 1);
-        dv[i] = __ldg(dlogit + t);
-        hv[i] = *reinterpret_cast<const float4*>(h + (int64_t)t * H + c);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (tb + i < t1) {
-          const float d = dv[i];
-          float4 o;
-          o.x = hv[i].x > 0.f ? d * w.x : 0.f; o.y = hv[i].y > 0.f ? d * w.y : 0.f;
-          o.z = hv[i].z > 0.f ? d * w.z : 0.f; o.w = hv[i].w > 0.f ? d * w.w : 0.f;
-          *reinterpret_cast<float4*>(dh + (int64_t)(tb + i) * H + c) = o;
-          sb.x += o.x; sb.y += o.y; sb.z += o.z; sb.w += o.w;
-          sw.x += d * hv[i].x; sw.y += d * hv[i].y; sw.z += d * hv[i].z; sw.w += d * hv[i].w;
-        }
-      }
-    }
-    // partials [2H, nchunks]: row j = db1[j], row H+j = dw2[j]
-    float* pb = partials + (int64_t)c * nchunks + chunk;
-    pb[0] = sb.x; pb[nchunks] = sb.y; pb[2 * (int64_t)nchunks] = sb.z; pb[3 * (int64_t)nchunks] = sb.w;
-    float* pw = partials + (int64_t)(H + c) * nchunks + chunk;
-    pw[0] = sw.x; pw[nchunks] = sw.y; pw[2 * (int64_t)nchunks] = sw.z; pw[3 * (int64_t)nchunks] = sw.w;
-  }
-}
 }  // namespace nr
 
 extern "C" int64_t nr_mlp_chunks(int64_t T) { return (T + nr::MLPB_ROWS - 1) / nr::MLPB_ROWS; }
 
-extern "C" int nr_mlp_hidden_bwd(const float* h, const float* dlogit, const float* w2, int64_t T, int64_t H,
-                                 float* dh, float* partials, void* stream) {
-  NR_CHECK_ARG(h && dlogit && w2 && dh && partials && T > 0 && H > 0 && H % 4 == 0, "nr_mlp_hidden_bwd: bad arguments");
-  const int nchunks = (int)nr_mlp_chunks(T);
-  nr::mlp_hidden_bwd_kernel<<<nchunks, 256, 0, (cudaStream_t)stream>>>(h, dlogit, w2, (int)T, (int)H, dh, partials,
-                                                                      nchunks);
-  NR_CHECK_LAUNCH("nr_mlp_hidden_bwd");
-  return 0;
-}
 
 extern "C" int nr_token_weights_fwd(const void* h, int h_bf16, const float* w2, const float* b2, const int64_t* mask_a,
                                     const int64_t* mask_b, int64_t Ra, int64_t R, int64_t N, int64_t H, float* w,

@@ -484,43 +484,6 @@ class _tf32:
         torch.backends.cuda.matmul.allow_tf32 = self.prev
 
 
-class TokenMLPFunction(torch.autograd.Function):
-    """logits [T] = relu(x W1^T + b1) w2 + b2 as plain cuBLAS GEMMs (fp32, or TF32 tensor cores when `tf32`)."""
-
-    @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, tf32):
-        shape = x.shape[:-1]
-        x2 = x.reshape(-1, x.shape[-1])
-        with _tf32(tf32):
-            h = torch._addmm_activation(b1, x2, w1.t(), use_gelu=False)     # bias + ReLU in the GEMM epilogue
-            out = torch.addmv(b2.expand(h.shape[0]), h, w2.reshape(-1))
-        ctx.tf32 = tf32
-        ctx.save_for_backward(x2, h, w1, w2)
-        ctx.shape = x.shape
-        return out.reshape(shape)
-
-    @staticmethod
-    def backward(ctx, dout):
-        x2, h, w1, w2 = ctx.saved_tensors
-        d = _f32c(dout).reshape(-1)
-        T, H = h.shape
-        st = _stream()
-        # one pass over h: dh, and per-CTA partials of db1 / dw2 (summed deterministically below)
-        dh = torch.empty_like(h)
-        nch = _lib.load().nr_mlp_chunks(T)
-        partials = torch.empty(2 * H, nch, dtype=torch.float32, device=h.device)
-        _call("nr_mlp_hidden_bwd", _p(h), _p(d), _p(_f32c(w2).reshape(-1)), T, H, _p(dh), _p(partials), st)
-        sums = torch.empty(2 * H, dtype=torch.float32, device=h.device)
-        _call("nr_vec_sums", _p(partials), 2 * H, nch, None, _p(sums), st)
-        db1 = sums[:H] if ctx.needs_input_grad[2] else None
-        dw2 = sums[H:].reshape(1, H) if ctx.needs_input_grad[3] else None
-        db2 = d.sum().reshape(1) if ctx.needs_input_grad[4] else None
-        with _tf32(ctx.tf32):
-            dw1 = (dh.t() @ x2) if ctx.needs_input_grad[1] else None
-            dx = (dh @ w1).reshape(ctx.shape) if ctx.needs_input_grad[0] else None
-        return dx, dw1, db1, dw2, db2, None
-
-
 MLP_FP32, MLP_TF32, MLP_BF16 = 0, 1, 2
 
 
@@ -634,13 +597,6 @@ def token_weights(mlp, feat, mask, mode, bank_feat=None, bank_mask=None):
 
 def mlp_params(mlp):
     return (mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias)
-
-
-def token_mlp_logits(mlp, feat, tf32):
-    """mlp: nn.Sequential(Linear, ReLU, Linear) with the reference's parameter names, or its 4 parameters
-    (W1, b1, W2, b2) as a tuple (e.g. wrapped by sharded.SumGradsAcrossRanks)."""
-    ps = mlp if isinstance(mlp, (tuple, list)) else mlp_params(mlp)
-    return TokenMLPFunction.apply(feat, *ps, bool(tf32))
 
 
 # ------------------------------------------------------------------------------------------------
