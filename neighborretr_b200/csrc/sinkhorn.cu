@@ -561,10 +561,10 @@ extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters
   NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   NR_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   NR_CHECK_ARG(coop, "nr_sinkhorn: device lacks cooperative launch");
-  // up to 128 CTAs of >= 4 rows: with the data-carrying exchange the row work per CTA, not the number of CTAs, sets
-  // the pace of a half-iteration (B=1024: 270 us with 8 rows per CTA, 322 us with 16)
-  int rows_per_cta = (int)((B + 127) / 128);
-  if (rows_per_cta < 4) rows_per_cta = 4;
+  // rows per CTA, measured on B200 with the data-carrying exchange (us at 4 / 8 / 16 rows): B=256 142 / 148 / 172,
+  // B=512 335 / 185 / 217, B=1024 319 / 265 / 336 -> 4 rows up to B=383, 8 rows beyond (more if the grid would not
+  // be co-resident, see below)
+  int rows_per_cta = B < 384 ? 4 : 8;
   if (const char* rv = getenv("NR_SINKHORN_ROWS")) { int r2 = atoi(rv); if (r2 >= 1) rows_per_cta = r2; }   // tuning knob
   while (rows_per_cta > 4 && ((size_t)2 * rows_per_cta * B + (size_t)2 * B) * sizeof(float) > 200 * 1024 &&
          (B + rows_per_cta - 2) / (rows_per_cta - 1) <= sms)
