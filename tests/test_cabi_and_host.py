@@ -100,3 +100,34 @@ def test_reference_surface_names():
         for suf in ("0.weight", "0.bias", "2.weight", "2.bias"):
             assert f"{pre}.{suf}" in names
     assert "clip.logit_scale" in names
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """nr_maxsim2_problem / nr_maxsim2_bwd_job cross the C ABI by pointer: the ctypes mirrors in _lib.py must have
+    the size and field offsets a C compiler gives the declarations of include/nrhead.h."""
+    import ctypes
+    import shutil
+    import subprocess
+    from neighborretr_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {"nr_maxsim2_problem": _lib.MaxSim2Problem, "nr_maxsim2_bwd_job": _lib.MaxSim2BwdJob}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrhead.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call([gcc, "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    for line, (cname, cls) in zip(out, structs.items()):
+        parts = line.split()
+        assert parts[0] == cname
+        assert int(parts[1]) == ctypes.sizeof(cls), cname
+        assert [int(v) for v in parts[2:]] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
