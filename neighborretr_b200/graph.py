@@ -39,6 +39,7 @@ class GraphedHeadStep:
         self.params = [p for p in model.parameters() if p.requires_grad]
         self._e0 = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.0], device=dev)
         self._fifo_stream = torch.cuda.Stream(device=dev)
+        self._stage = None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -110,11 +111,41 @@ class GraphedHeadStep:
                 bank = getattr(m, name)
                 bank.copy_(ops.fifo_update(new.detach().to(bank.dtype), bank, cap))
 
-    def __call__(self, *batch, sync_losses_to=None):
+    # ---- input prefetch: the H2D copy of step i+1 overlaps the replay of step i --------------------------------
+    def prefetch(self, *batch):
+        """Start copying a batch (pinned host or device tensors) into the staging buffer on a copy stream; a later
+        __call__(prefetched=True) moves it into the static inputs with a device-to-device copy.  The copy waits until
+        the previous staging content has been consumed; use __call__(..., prefetch_next=batch) inside a loop."""
+        dev = self.static[FIELDS[0]].device
+        if self._stage is None:
+            self._stage = {f: torch.empty_like(self.static[f].data) for f in FIELDS}
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged = torch.cuda.Event()
+            self._stage_free = torch.cuda.Event()
+            self._stage_free.record()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free)       # the previous staging content has been consumed
+            for f, t in zip(FIELDS, batch):
+                self._stage[f].copy_(t, non_blocking=True)
+            self._staged.record(self._copy_stream)
+
+    def __call__(self, *batch, sync_losses_to=None, prefetched=False, prefetch_next=None):
         """Copy the batch into the static buffers (H2D if it lives on the host), replay, return the static
-        [total, centrality, uniform, neighbor, kl] tensor (or copy it into the pinned host tensor given)."""
-        for f, t in zip(FIELDS, batch):
-            self.static[f].data.copy_(t, non_blocking=True)
+        [total, centrality, uniform, neighbor, kl] tensor (or copy it into the pinned host tensor given).
+        prefetched=True: take the batch a previous prefetch() staged on the device instead; prefetch_next=batch
+        starts staging the following step's batch as soon as the staging buffer has been consumed, i.e. its H2D
+        copy runs under this step's replay."""
+        if prefetched:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._staged)
+            for f in FIELDS:
+                self.static[f].data.copy_(self._stage[f], non_blocking=True)
+            self._stage_free.record(cur)
+            if prefetch_next is not None:
+                self.prefetch(*prefetch_next)
+        else:
+            for f, t in zip(FIELDS, batch):
+                self.static[f].data.copy_(t, non_blocking=True)
         self.graph.replay()
         ops.LAUNCHES["count"] += self.launches_per_replay
         if sync_losses_to is not None:

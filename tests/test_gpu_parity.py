@@ -169,6 +169,28 @@ def test_compute_losses_bf16(bwd, mlp):
           {k: rel_l2(grads[k], ograds[k]) for k in ("text", "video", "text_weight_fc.0.weight")})
 
 
+def test_cuda_graph_step_prefetch_pipeline():
+    """The input pipeline of GraphedHeadStep (prefetch of step i+1 under the replay of step i, pinned host batches)
+    gives the same losses as feeding each batch directly."""
+    from neighborretr_b200.graph import FIELDS, GraphedHeadStep
+    c = CASES["cfg1"]
+    h, bank, params, cfg = make_case(c)
+    host = [synth.make_batch(c["b"], c["nt"], c["nv"], d=c["d"], seed=4321 + i) for i in range(4)]
+    pinned = [[getattr(hb, f).pin_memory() for f in FIELDS] for hb in host]
+    a = make_head(c["d"], cfg, params, "bf16"); set_bank(a, bank)
+    b = make_head(c["d"], cfg, params, "bf16"); set_bank(b, bank)
+    sa = GraphedHeadStep(a, [t.cuda() for t in pinned[0]])
+    sb = GraphedHeadStep(b, [t.cuda() for t in pinned[0]])
+    out = torch.empty(5).pin_memory()
+    sb.prefetch(*pinned[0])
+    for i in range(4):
+        want = sa(*pinned[i]).clone()
+        nxt = pinned[i + 1] if i + 1 < 4 else None
+        got = sb(sync_losses_to=out, prefetched=True, prefetch_next=nxt).clone()
+        torch.testing.assert_close(got, want.cpu(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(a.mb_feat_t, b.mb_feat_t) and torch.equal(a.mb_ind, b.mb_ind)
+
+
 def test_eval_similarity_and_metrics():
     from neighborretr_b200.evaluator import _run_on_single_gpu
     from neighborretr_b200.metrics import RetrievalMetrics
