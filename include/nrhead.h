@@ -226,6 +226,23 @@ int nr_topk_rows(const float* S, int64_t lds, int64_t Q, int64_t N, int k, int32
 int nr_topk_merge(const float* vals, const int32_t* idx, int64_t W, int64_t Q, int k, float* out_vals,
                   int32_t* out_idx, void* stream);
 
+/* ---- multi-sentence evaluation (utils/metrics.py:81-145, padding at training/evaluator.py:216-239) ----
+ * S [Q, N] (row stride lds) holds one caption per row; target[q] = GLOBAL column of caption q's video, the
+ * block covers global columns [col_offset, col_offset + N).  Score of the positive: diag[q] if diag != NULL
+ * (column-sharded galleries) else S[q, target[q] - col_offset].
+ * gt[q]        += #{j : S[q,j] > s or S[q,j] is NaN}           (torch's descending sort puts NaN first)
+ * eq_before[q] += #{j : S[q,j] == s and col_offset + j < target[q]}   (stable order of equal scores)
+ * so that rank(q) = gt + eq_before is the reference's double-argsort diagonal (metrics.py:97-103).
+ * valid[q] (optional) = 1 unless s is +-inf or NaN (metrics.py:106-109); invalid rows add nothing. */
+int nr_rank_count_target(const float* S, int64_t lds, int64_t Q, int64_t N, const int32_t* target,
+                         const float* diag, int64_t col_offset, int32_t* gt, int32_t* eq_before, int32_t* valid,
+                         void* stream);
+/* video->text similarity of a multi-sentence test set (metrics.py:124-145): captions of video group i are the
+ * rows [group_start[i], group_start[i+1]) of S [T, V]; out[j, i] = max over those rows of S[t, j] with NaN
+ * read as -inf (out row stride ldo >= G; an empty group gives -inf).  group_start: int32 [G+1] on the device. */
+int nr_group_max_t(const float* S, int64_t lds, int64_t T, int64_t V, const int32_t* group_start, int64_t G,
+                   float* out, int64_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,8 +4,9 @@ Public surface mirrors the reference's module names:
     neighborretr_b200.modeling.NeighborRetr / HeadMixin
     neighborretr_b200.until_module.{CentralityWeightingLoss, NeighborAdjustingLoss,
                                     UniformRegularizationLoss, KLDivergenceLoss, AllGather, AllGather2}
-    neighborretr_b200.metrics.RetrievalMetrics.compute_metrics
-    neighborretr_b200.evaluator._run_on_single_gpu
+    neighborretr_b200.metrics.RetrievalMetrics.{compute_metrics, tensor_text_to_video_metrics,
+                                                tensor_video_to_text_sim}
+    neighborretr_b200.evaluator.{_run_on_single_gpu, multi_sentence_metrics, gather_eval_features}
     neighborretr_b200.install(...)  -> rebind the above onto an imported reference checkout
 """
 __all__ = ["install"]
@@ -41,8 +42,9 @@ def install(reference_pkg=None):
     ref_modeling.allgather2 = um.AllGather2.apply
     ref_eval.AllGather = um.AllGather
     ref_eval.allgather = um.AllGather.apply
-    ref_metrics.RetrievalMetrics.compute_metrics = staticmethod(mt.RetrievalMetrics.compute_metrics)
+    for name in ("compute_metrics", "tensor_text_to_video_metrics", "tensor_video_to_text_sim"):
+        setattr(ref_metrics.RetrievalMetrics, name, staticmethod(getattr(mt.RetrievalMetrics, name)))
+        patched.append(f"NeighborRetr.utils.metrics.RetrievalMetrics.{name}")
     ref_eval._run_on_single_gpu = ev._run_on_single_gpu
-    patched += ["NeighborRetr.utils.metrics.RetrievalMetrics.compute_metrics",
-                "NeighborRetr.training.evaluator._run_on_single_gpu"]
+    patched += ["NeighborRetr.training.evaluator._run_on_single_gpu"]
     return patched

@@ -54,6 +54,8 @@ SIGNATURES = {
     "nr_rank_count": (_I, [_P, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
     "nr_topk_rows": (_I, [_P, _I64, _I64, _I64, _I, ctypes.c_int32, _P, _P, _P]),
     "nr_topk_merge": (_I, [_P, _P, _I64, _I64, _I, _P, _P, _P]),
+    "nr_rank_count_target": (_I, [_P, _I64, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P]),
+    "nr_group_max_t": (_I, [_P, _I64, _I64, _I64, _P, _I64, _P, _I64, _P]),
 }
 
 

@@ -82,3 +82,43 @@ def sharded_retrieval(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list,
     tv, ti = ops.topk_merge(allv.view(W, Q, k), alli.view(W, Q, k))
     c = cnt.cpu().numpy(); cv = cnt_v[:, :N].cpu().numpy()
     return metrics_from_counts(c[0], c[1]), metrics_from_counts(cv[0], cv[1]), (tv, ti)
+
+
+def multi_sentence_metrics(sim_matrix, cut_off_points):
+    """Multi-sentence branch of eval_epoch (reference training/evaluator.py:216-251): sim_matrix [T, V] caption x
+    video similarities (np.ndarray as returned by _run_on_single_gpu, or a CUDA tensor), cut_off_points[i] = index
+    of the last caption of video i.  Returns (text->video metrics, video->text metrics) with the reference's keys.
+
+    The reference pads the matrix to [V, maxlen, V] with -inf rows on the host, double-argsorts it and takes a
+    max over the padded axis; the same numbers come from the un-padded matrix in two passes over it — the rank
+    of every caption's own video (target-rank kernel) and the per-video max over its captions (group-max kernel,
+    written transposed) followed by the ordinary rank count."""
+    from . import metrics as mt
+    s = mt._to_cuda_f32(sim_matrix)
+    if s.dim() != 2:
+        raise ValueError(f"multi_sentence_metrics: need [T, V], got {tuple(s.shape)}")
+    T, V = s.shape
+    group_start, target = mt.group_layout(cut_off_points, total_rows=T)
+    if len(group_start) - 1 != V:
+        raise ValueError(f"multi_sentence_metrics: {len(group_start) - 1} cut-off points for {V} videos")
+    ranks, valid = mt.multi_sentence_ranks(s, torch.from_numpy(target).cuda())
+    order = mt.slot_major_order(group_start, target)
+    tv = mt.multi_sentence_rank_scalars(ranks[order][valid[order]])
+    v2t = ops.group_max_t(s, torch.from_numpy(group_start).cuda())              # [V videos, V caption groups]
+    vt = mt.RetrievalMetrics.compute_metrics(v2t)
+    return tv, vt
+
+
+def gather_eval_features(args, ids_t, mask_t, mask_v, feat_t, feat_v):
+    """Gather + reorder-by-id step of eval_epoch (reference training/evaluator.py:173-189): every rank holds a
+    shard of the test set with the dataset indices ``ids_t``; after the gather row ids_t[k] of each tensor is the
+    k-th gathered row, and the tensors are trimmed to max(id)+1 rows.  Pure data movement: contiguous
+    all_gather_into_tensor (until_module.AllGather) + one index_copy per tensor."""
+    from .until_module import AllGather
+    ids = AllGather.apply(ids_t, args).reshape(-1)
+    n = int(ids.max().item()) + 1
+    out = []
+    for t in (mask_t, mask_v, feat_t, feat_v):
+        g = AllGather.apply(t, args)
+        out.append(g.index_copy(0, ids, g)[:n])          # g[ids] = g.clone()  (evaluator.py:180-183)
+    return (ids, *out)

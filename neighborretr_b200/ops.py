@@ -793,3 +793,35 @@ def topk_merge(vals, idx):
     oi = torch.empty(Q, k, dtype=torch.int32, device=vals.device)
     _call("nr_topk_merge", _p(vals), _p(idx), W, Q, k, _p(ov), _p(oi), _stream())
     return ov, oi
+
+
+def rank_counts_target(S, target, diag=None, col_offset=0, gt=None, eq_before=None, want_valid=True):
+    """Multi-sentence text->video ranks (reference metrics.py:81-122): per caption row q of S [Q,N] with its
+    video in global column target[q], (#greater-or-NaN, #equal in a lower column, valid) — rank = sum of the
+    first two.  gt/eq_before accumulate when passed in (column shards)."""
+    _req_cuda(S, target, diag)
+    S = _f32c(S)
+    Q, N = S.shape
+    target = target.to(torch.int32).contiguous()
+    if target.numel() != Q:
+        raise ValueError(f"rank_counts_target: {target.numel()} targets for {Q} rows")
+    if gt is None:
+        gt = torch.zeros(Q, dtype=torch.int32, device=S.device)
+        eq_before = torch.zeros(Q, dtype=torch.int32, device=S.device)
+    valid = torch.empty(Q, dtype=torch.int32, device=S.device) if want_valid else None
+    _call("nr_rank_count_target", _p(S), N, Q, N, _p(target), _p(diag), int(col_offset), _p(gt), _p(eq_before),
+          _p(valid), _stream())
+    return gt, eq_before, valid
+
+
+def group_max_t(S, group_start):
+    """out[j, i] = max over caption rows [group_start[i], group_start[i+1]) of S[t, j], NaN read as -inf
+    (reference metrics.py:124-145).  S [T,V] CUDA, group_start int32 [G+1] CUDA -> [V, G] f32."""
+    _req_cuda(S, group_start)
+    S = _f32c(S)
+    T, V = S.shape
+    group_start = group_start.to(torch.int32).contiguous()
+    G = group_start.numel() - 1
+    out = torch.empty(V, G, dtype=torch.float32, device=S.device)
+    _call("nr_group_max_t", _p(S), V, T, V, _p(group_start), G, _p(out), G, _stream())
+    return out

@@ -13,6 +13,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from types import SimpleNamespace
 
+import numpy as np
 import torch
 
 SHAPES = {
@@ -87,3 +88,32 @@ def default_config(**kw):
              world_size=1, local_rank=0, rank=0)
     c.update(kw)
     return SimpleNamespace(**c)
+
+
+# ---- multi-sentence test sets (several captions per video, reference evaluator.py:216-251) ------------------
+MS_CASES = {
+    # name: (videos, max captions per video, integer-valued scores with many ties, NaN/inf entries, seed)
+    # ties only at V <= 16: the reference's torch.argsort (stable=False) keeps equal scores in column order
+    # there and in an implementation-defined order above (introsort), see oracle/metrics.py
+    "ties16": (16, 6, True, True, 11),
+    "plain150": (150, 6, False, False, 12),
+    "nan120": (120, 5, False, True, 13),
+}
+
+
+def make_multi_sentence_case(V, maxlen, ties, nonfinite, seed):
+    """Seeded caption x video matrix [T, V] + cut-off points (index of the last caption of every video)."""
+    rng = np.random.RandomState(seed)
+    lens = rng.randint(1, maxlen + 1, size=V)
+    T = int(lens.sum())
+    tgt = np.repeat(np.arange(V), lens)
+    if ties:
+        sim = rng.randint(0, 5, size=(T, V)).astype(np.float32)
+    else:
+        sim = rng.randn(T, V).astype(np.float32)
+        sim[np.arange(T), tgt] += 2.0
+    if nonfinite:
+        sim[rng.rand(T, V) < 0.01] = np.nan
+        sim[rng.rand(T, V) < 0.01] = np.inf
+        sim[rng.rand(T, V) < 0.01] = -np.inf
+    return sim, (np.cumsum(lens) - 1).astype(np.int64)

@@ -186,6 +186,29 @@ def run_eval(modeling, evaluator, metrics):
     print("eval ok")
 
 
+def run_multi_sentence(metrics):
+    """Multi-sentence metrics of the reference (utils/metrics.py:81-145) on the padded tensor built the way
+    eval_epoch builds it (training/evaluator.py:216-239; that code is inline in eval_epoch, so the padding is
+    restated in oracle.metrics.multi_sentence_reshape and only the metric functions are the reference's)."""
+    from oracle import metrics as OM
+    R = metrics.RetrievalMetrics
+    out = {}
+    for name, spec in synth.MS_CASES.items():
+        sim, cut = synth.make_multi_sentence_case(*spec)
+        pad = OM.multi_sentence_reshape(sim, cut)
+        tv = R.tensor_text_to_video_metrics(pad.copy())
+        v2t = R.tensor_video_to_text_sim(torch.tensor(pad.copy())).numpy()
+        vt = R.compute_metrics(v2t)
+        keys = ["R1", "R5", "R10", "R50", "MedianR", "MeanR", "Std_Rank", "MR"]
+        out[f"{name}_tv"] = np.asarray([tv[k] for k in keys], dtype=np.float64)
+        out[f"{name}_v2t_sim"] = v2t
+        out[f"{name}_vt_cols"] = np.asarray(vt["cols"], dtype=np.int64)
+        out[f"{name}_vt"] = np.asarray([vt[k] for k in ("R1", "R5", "R10", "R50", "MR", "MedianR", "MeanR")],
+                                       dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "multi_sentence.npz"), **out)
+    print("multi_sentence ok")
+
+
 def run_bank(modeling):
     c = dict(b=6, nt=4, nv=3, d=8, m=8, k=20)
     cfg = synth.default_config()
@@ -214,6 +237,7 @@ def main():
     run_act_piece(modeling)
     run_eval(modeling, evaluator, metrics)
     run_bank(modeling)
+    run_multi_sentence(metrics)
 
 
 if __name__ == "__main__":
