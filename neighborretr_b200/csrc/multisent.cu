@@ -15,6 +15,42 @@
 
 namespace nr {
 
+// counts of one row over the columns {first, first+stride, ...} (in float4 units where the row is 16-byte aligned)
+template <int STRIDE>
+__device__ __forceinline__ void count_row(const float* __restrict__ row, int N, float sd, int64_t c, int first,
+                                          int& g, int& e) {
+  const int n4 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (N / 4) : 0;
+#pragma unroll 4
+  for (int j = first; j < n4; j += STRIDE) {
+    float4 v = reinterpret_cast<const float4*>(row)[j];
+    const int64_t j0 = 4 * (int64_t)j;
+    g += (v.x > sd || v.x != v.x) + (v.y > sd || v.y != v.y) + (v.z > sd || v.z != v.z) + (v.w > sd || v.w != v.w);
+    e += (v.x == sd && j0 < c) + (v.y == sd && j0 + 1 < c) + (v.z == sd && j0 + 2 < c) + (v.w == sd && j0 + 3 < c);
+  }
+  for (int j = n4 * 4 + first; j < N; j += STRIDE) {
+    float v = row[j];
+    g += (v > sd || v != v);
+    e += (v == sd && j < c);
+  }
+}
+
+__device__ __forceinline__ float positive_score(const float* __restrict__ row, int N, const float* diag, int64_t q,
+                                                int64_t c) {
+  if (diag) return diag[q];
+  return (c >= 0 && c < N) ? row[c] : __int_as_float(0x7fc00000);   // outside the block: NaN -> invalid, counts 0
+}
+
+__device__ __forceinline__ void store_counts(int64_t q, float sd, int G, int E, int32_t* gt, int32_t* eq_before,
+                                             int32_t* valid) {
+  const bool ok = (sd == sd) && (fabsf(sd) != INFINITY);   // metrics.py:107-109: neither inf nor NaN
+  if (ok) {                   // one writer per q and stream-ordered launches: plain accumulate (column shards)
+    gt[q] += G;
+    eq_before[q] += E;
+  }
+  if (valid) valid[q] = ok ? 1 : 0;
+}
+
+// long rows: one CTA per caption row
 __global__ void __launch_bounds__(256)
 rank_target_kernel(const float* __restrict__ S, int64_t lds, int N, const int32_t* __restrict__ target,
                    const float* __restrict__ diag, int64_t col_offset, int32_t* __restrict__ gt,
@@ -23,22 +59,9 @@ rank_target_kernel(const float* __restrict__ S, int64_t lds, int N, const int32_
   const int q = blockIdx.x, tid = threadIdx.x;
   const float* row = S + (int64_t)q * lds;
   const int64_t c = (int64_t)target[q] - col_offset;       // positive's column inside this block of columns
-  float sd;
-  if (diag) sd = diag[q];
-  else sd = (c >= 0 && c < N) ? row[c] : __int_as_float(0x7fc00000);   // outside: NaN -> invalid, counts 0
+  const float sd = positive_score(row, N, diag, q, c);
   int g = 0, e = 0;
-  const int n4 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (N / 4) : 0;
-  for (int j = tid; j < n4; j += 256) {
-    float4 v = reinterpret_cast<const float4*>(row)[j];
-    const int64_t j0 = 4 * (int64_t)j;
-    g += (v.x > sd || v.x != v.x) + (v.y > sd || v.y != v.y) + (v.z > sd || v.z != v.z) + (v.w > sd || v.w != v.w);
-    e += (v.x == sd && j0 < c) + (v.y == sd && j0 + 1 < c) + (v.z == sd && j0 + 2 < c) + (v.w == sd && j0 + 3 < c);
-  }
-  for (int j = n4 * 4 + tid; j < N; j += 256) {
-    float v = row[j];
-    g += (v > sd || v != v);
-    e += (v == sd && j < c);
-  }
+  count_row<256>(row, N, sd, c, tid, g, e);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     g += __shfl_xor_sync(0xffffffffu, g, o);
@@ -49,12 +72,30 @@ rank_target_kernel(const float* __restrict__ S, int64_t lds, int N, const int32_
   if (tid == 0) {
     int G = 0, E = 0;
     for (int w = 0; w < 8; ++w) { G += red_g[w]; E += red_e[w]; }
-    const bool ok = (sd == sd) && (fabsf(sd) != INFINITY);   // metrics.py:107-109: neither inf nor NaN
-    if (!ok) { G = 0; E = 0; }
-    gt[q] += G;               // one CTA per q and stream-ordered launches: plain accumulate (column shards)
-    eq_before[q] += E;
-    if (valid) valid[q] = ok ? 1 : 0;
+    store_counts(q, sd, G, E, gt, eq_before, valid);
   }
+}
+
+// short rows (a few hundred to a few thousand videos, the usual test sets): one WARP per caption row, 8 rows per
+// CTA, shuffles only — a 256-thread CTA per 2.7 KB row would spend its time on launch and barrier overhead
+__global__ void __launch_bounds__(256)
+rank_target_warp_kernel(const float* __restrict__ S, int64_t lds, int64_t Q, int N,
+                        const int32_t* __restrict__ target, const float* __restrict__ diag, int64_t col_offset,
+                        int32_t* __restrict__ gt, int32_t* __restrict__ eq_before, int32_t* __restrict__ valid) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= Q) return;                                      // warp-uniform; no block-level barrier below
+  const float* row = S + q * lds;
+  const int64_t c = (int64_t)target[q] - col_offset;
+  const float sd = positive_score(row, N, diag, q, c);
+  int g = 0, e = 0;
+  count_row<32>(row, N, sd, c, lane, g, e);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    g += __shfl_xor_sync(0xffffffffu, g, o);
+    e += __shfl_xor_sync(0xffffffffu, e, o);
+  }
+  if (lane == 0) store_counts(q, sd, g, e, gt, eq_before, valid);
 }
 
 // one warp per caption group, 128 columns per CTA (4 per lane), 8 groups per CTA; the [8 x 128] tile of maxima
@@ -112,8 +153,12 @@ extern "C" int nr_rank_count_target(const float* S, int64_t lds, int64_t Q, int6
                                     int32_t* valid, void* stream) {
   NR_CHECK_ARG(S && target && gt && eq_before && Q > 0 && N > 0 && lds >= N, "nr_rank_count_target: bad arguments");
   NR_CHECK_ARG(Q <= 2147483647LL && N <= 2147483647LL, "nr_rank_count_target: sizes exceed int32");
-  rank_target_kernel<<<(unsigned)Q, 256, 0, (cudaStream_t)stream>>>(S, lds, (int)N, target, diag, col_offset, gt,
-                                                                   eq_before, valid);
+  if (N <= 4096)
+    rank_target_warp_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, lds, Q, (int)N, target, diag,
+                                                                                      col_offset, gt, eq_before, valid);
+  else
+    rank_target_kernel<<<(unsigned)Q, 256, 0, (cudaStream_t)stream>>>(S, lds, (int)N, target, diag, col_offset, gt,
+                                                                     eq_before, valid);
   NR_CHECK_LAUNCH("nr_rank_count_target");
   return 0;
 }

@@ -174,11 +174,13 @@ def test_gpu_multi_sentence_matches_reference_golden(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("V,maxlen,ties,nonfinite", [(670, 9, True, False), (672, 5, False, True), (1, 3, True, False),
-                                                     (131, 1, True, True), (257, 40, True, False)])
+                                                     (131, 1, True, True), (257, 40, True, False),
+                                                     (4101, 2, True, True)])
 def test_gpu_multi_sentence_kernels_vs_counting_oracle(V, maxlen, ties, nonfinite):
     """Kernels through ops (C ABI) against the numpy counting oracle at shapes covering the scalar (V % 4 != 0)
     and float4 paths, partial 128-column / 8-group tiles, one caption per video, one video, long caption groups,
-    ties (stable column order) and NaN/inf scores; plus the column-sharded accumulate form."""
+    ties (stable column order) and NaN/inf scores, rows above 4096 columns (CTA-per-row variant; warp-per-row
+    below); plus the column-sharded accumulate form."""
     from neighborretr_b200 import ops
     from neighborretr_b200.metrics import group_layout
     sim, cut = synth.make_multi_sentence_case(V, maxlen, ties, nonfinite, seed=100 + V)
