@@ -15,22 +15,29 @@
 
 namespace nr {
 
-// counts of one row over the columns {first, first+stride, ...} (in float4 units where the row is 16-byte aligned)
+// counts of one row over the columns {first, first+stride, ...}: scalar head up to the first 16-byte boundary of the
+// row (rows of a matrix whose width is not a multiple of 4 start at any 4-byte offset), float4 body, scalar tail
 template <int STRIDE>
 __device__ __forceinline__ void count_row(const float* __restrict__ row, int N, float sd, int64_t c, int first,
                                           int& g, int& e) {
-  const int n4 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (N / 4) : 0;
+  int head = (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(row) & 15)) & 15) >> 2);
+  head = head < N ? head : N;
+  const int n4 = (N - head) / 4;
+  const float4* body = reinterpret_cast<const float4*>(row + head);
 #pragma unroll 4
   for (int j = first; j < n4; j += STRIDE) {
-    float4 v = reinterpret_cast<const float4*>(row)[j];
-    const int64_t j0 = 4 * (int64_t)j;
+    float4 v = body[j];
+    const int64_t j0 = head + 4 * (int64_t)j;
     g += (v.x > sd || v.x != v.x) + (v.y > sd || v.y != v.y) + (v.z > sd || v.z != v.z) + (v.w > sd || v.w != v.w);
     e += (v.x == sd && j0 < c) + (v.y == sd && j0 + 1 < c) + (v.z == sd && j0 + 2 < c) + (v.w == sd && j0 + 3 < c);
   }
-  for (int j = n4 * 4 + first; j < N; j += STRIDE) {
-    float v = row[j];
+  // head columns [0, head) and tail columns [head + 4*n4, N): at most 3 + 3 elements
+  const int tail0 = head + 4 * n4;
+  for (int j = first; j < head + (N - tail0); j += STRIDE) {
+    const int col = j < head ? j : tail0 + (j - head);
+    float v = row[col];
     g += (v > sd || v != v);
-    e += (v == sd && j < c);
+    e += (v == sd && col < c);
   }
 }
 
@@ -107,10 +114,12 @@ group_max_t_kernel(const float* __restrict__ S, int64_t lds, int V, const int32_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * 128, i0 = blockIdx.y * 8, i = i0 + warp;
   float m0 = NR_NEG_INF, m1 = NR_NEG_INF, m2 = NR_NEG_INF, m3 = NR_NEG_INF;
+  bool interleaved = false;
   if (i < G) {
     const int t0 = group_start[i], t1 = group_start[i + 1];
     const int jl = j0 + lane * 4;
-    const bool vec = ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (jl + 3 < V);
+    // warp-uniform choice: the column mapping of the whole warp follows it
+    const bool vec = ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (j0 + 128 <= V);
     if (vec) {
       const float* p = S + (int64_t)t0 * lds + jl;
 #pragma unroll 4
@@ -121,22 +130,31 @@ group_max_t_kernel(const float* __restrict__ S, int64_t lds, int V, const int32_
         m2 = v.z > m2 ? v.z : m2;
         m3 = v.w > m3 ? v.w : m3;
       }
-    } else if (jl < V) {
-      const float* p = S + (int64_t)t0 * lds + jl;
-      const int nc = V - jl;              // 1..3 real columns (or 4 on an unaligned matrix)
+    } else {
+      // matrix rows not 16-byte aligned, or the last partial column tile: coalesced scalar loads, lane l
+      // takes columns j0 + l + 32*c; the tile index below follows the same mapping
+      const float* p = S + (int64_t)t0 * lds + j0 + lane;
+      const int nc = (V - j0 - lane + 31) / 32;          // columns of this lane inside the matrix (<= 0: none)
       for (int t = t0; t < t1; ++t, p += lds) {
-        float a = p[0];
-        m0 = a > m0 ? a : m0;
-        if (nc > 1) { float b = p[1]; m1 = b > m1 ? b : m1; }
-        if (nc > 2) { float c = p[2]; m2 = c > m2 ? c : m2; }
-        if (nc > 3) { float d = p[3]; m3 = d > m3 ? d : m3; }
+        if (nc > 0) { float a = p[0]; m0 = a > m0 ? a : m0; }
+        if (nc > 1) { float b = p[32]; m1 = b > m1 ? b : m1; }
+        if (nc > 2) { float c = p[64]; m2 = c > m2 ? c : m2; }
+        if (nc > 3) { float d = p[96]; m3 = d > m3 ? d : m3; }
       }
+      interleaved = true;
     }
   }
-  tile[warp][lane * 4 + 0] = m0;
-  tile[warp][lane * 4 + 1] = m1;
-  tile[warp][lane * 4 + 2] = m2;
-  tile[warp][lane * 4 + 3] = m3;
+  if (interleaved) {
+    tile[warp][lane] = m0;
+    tile[warp][lane + 32] = m1;
+    tile[warp][lane + 64] = m2;
+    tile[warp][lane + 96] = m3;
+  } else {
+    tile[warp][lane * 4 + 0] = m0;
+    tile[warp][lane * 4 + 1] = m1;
+    tile[warp][lane * 4 + 2] = m2;
+    tile[warp][lane * 4 + 3] = m3;
+  }
   __syncthreads();
   for (int e = threadIdx.x; e < 8 * 128; e += 256) {
     const int jj = e >> 3, ii = e & 7;

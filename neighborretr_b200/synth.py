@@ -117,3 +117,43 @@ def make_multi_sentence_case(V, maxlen, ties, nonfinite, seed):
         sim[rng.rand(T, V) < 0.01] = np.inf
         sim[rng.rand(T, V) < 0.01] = -np.inf
     return sim, (np.cumsum(lens) - 1).astype(np.int64)
+
+
+# ---- memory-bank prefill (reference utils/memory_bank.py:80-229) ------------------------------------------------
+class ToyEncoder(torch.nn.Module):
+    """Stand-in for the CLIP towers in prefill tests: deterministic features from the loader tensors, exposed as
+    ``get_text_video_feat`` like the reference model, plus the bank attributes the manager writes."""
+
+    def __init__(self, d=8):
+        super().__init__()
+        self.d = d
+        self.scale = torch.nn.Parameter(torch.tensor(0.5))
+        self.mb_ind = torch.tensor([], dtype=torch.long)
+        self.mb_feat_t = torch.empty((0, 0, 0))
+        self.mb_feat_v = torch.empty((0, 0, 0))
+        self.mb_mask_t = torch.empty((0, 0))
+        self.mb_mask_v = torch.empty((0, 0))
+        self.mb_batch = 0
+
+    def get_text_video_feat(self, text_ids, text_mask, video, video_mask, shaped=False):
+        ramp = torch.arange(1, self.d + 1, device=text_ids.device, dtype=torch.float32)
+        text = torch.sin(text_ids.float().unsqueeze(-1) * ramp * self.scale)
+        vid = torch.cos(video.float().mean(dim=-1, keepdim=True) * ramp)
+        return text.float(), vid.float()
+
+
+def make_prefill_loader(n_batches, b, nt=4, nv=3, seed=77, rank=0):
+    """List of loader batches ``(text_ids, text_mask, video, video_mask, inds, idx)`` (reference
+    dataloader_retrieval.py:343) with ragged prefix masks and dataset indices shaped [b, 1]."""
+    g = torch.Generator().manual_seed(seed + 1000 * rank)
+    out = []
+    for k in range(n_batches):
+        ids = torch.randint(0, 400, (b, nt), generator=g)
+        video = torch.randn(b, nv, 5, generator=g)
+        tl = torch.randint(1, nt + 1, (b,), generator=g)
+        vl = torch.randint(1, nv + 1, (b,), generator=g)
+        tm = (torch.arange(nt)[None, :] < tl[:, None]).long()
+        vm = (torch.arange(nv)[None, :] < vl[:, None]).long()
+        inds = (torch.arange(b) + (k + 10 * rank) * b).view(b, 1)
+        out.append((ids, tm, video, vm, inds, inds.clone()))
+    return out

@@ -209,6 +209,25 @@ def run_multi_sentence(metrics):
     print("multi_sentence ok")
 
 
+def run_prefill():
+    """MemoryBankManager.load_memory_bank / clear_memory_bank of the reference (utils/memory_bank.py) on a toy
+    encoder and a list-of-batches loader (CPU, single process): 6 loader batches, mb_batch = 4."""
+    import logging
+    from NeighborRetr.utils.memory_bank import MemoryBankManager
+    args = SimpleNamespace(logger=logging.getLogger("golden"), mb_batch=4, batch_size=5, distributed=False,
+                           world_size=1, local_rank=0)
+    model = synth.ToyEncoder(d=8)
+    n = MemoryBankManager(args).load_memory_bank(model, synth.make_prefill_loader(6, 5), "cpu", 0)
+    out = {"rows": np.asarray(n), "ind": model.mb_ind.numpy(), "feat_t": model.mb_feat_t.numpy(),
+           "feat_v": model.mb_feat_v.numpy(), "mask_t": model.mb_mask_t.numpy(), "mask_v": model.mb_mask_v.numpy(),
+           "mb_batch": np.asarray(model.mb_batch)}
+    MemoryBankManager(args).clear_memory_bank(model)
+    out["cleared_shapes"] = np.asarray([model.mb_ind.numel(), model.mb_feat_t.dim(), model.mb_mask_v.dim(),
+                                        model.mb_batch])
+    np.savez_compressed(os.path.join(OUT, "prefill.npz"), **out)
+    print("prefill ok", n)
+
+
 def run_bank(modeling):
     c = dict(b=6, nt=4, nv=3, d=8, m=8, k=20)
     cfg = synth.default_config()
@@ -238,6 +257,7 @@ def main():
     run_eval(modeling, evaluator, metrics)
     run_bank(modeling)
     run_multi_sentence(metrics)
+    run_prefill()
 
 
 if __name__ == "__main__":
