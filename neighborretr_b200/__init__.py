@@ -7,6 +7,7 @@ Public surface mirrors the reference's module names:
     neighborretr_b200.metrics.RetrievalMetrics.{compute_metrics, tensor_text_to_video_metrics,
                                                 tensor_video_to_text_sim}
     neighborretr_b200.evaluator.{_run_on_single_gpu, multi_sentence_metrics, gather_eval_features}
+    neighborretr_b200.memory_bank.MemoryBankManager
     neighborretr_b200.install(...)  -> rebind the above onto an imported reference checkout
 """
 __all__ = ["install"]
@@ -28,11 +29,11 @@ def install(reference_pkg=None):
     ref_eval = importlib.import_module("NeighborRetr.training.evaluator")
     patched = []
     cls = ref_modeling.NeighborRetr
-    for name in ("local_level", "global_level", "get_similarity_logits", "compute_centrality_weights",
-                 "compute_centrality_loss", "compute_neighbor_loss", "compute_uniform_loss", "_compute_losses",
-                 "update_memory_bank", "_head_precision", "_head_bwd_precision"):
-        setattr(cls, name, getattr(md.HeadMixin, name))
-        patched.append(f"NeighborRetr.models.modeling.NeighborRetr.{name}")
+    # every head method (public ones with the reference's names, plus the private helpers they call)
+    for name, fn in vars(md.HeadMixin).items():
+        if callable(fn) and not name.startswith("__"):
+            setattr(cls, name, fn)
+            patched.append(f"NeighborRetr.models.modeling.NeighborRetr.{name}")
     for name in ("CentralityWeightingLoss", "NeighborAdjustingLoss", "UniformRegularizationLoss",
                  "KLDivergenceLoss", "AllGather", "AllGather2"):
         for mod in (ref_until, ref_modeling):
@@ -47,4 +48,11 @@ def install(reference_pkg=None):
         patched.append(f"NeighborRetr.utils.metrics.RetrievalMetrics.{name}")
     ref_eval._run_on_single_gpu = ev._run_on_single_gpu
     patched += ["NeighborRetr.training.evaluator._run_on_single_gpu"]
+    # methods are rebound on the reference's class (main.py imports the class by name before this runs)
+    from . import memory_bank as mb
+    ref_mb = importlib.import_module("NeighborRetr.utils.memory_bank")
+    for name in ("load_memory_bank", "clear_memory_bank", "_info", "_error"):
+        setattr(ref_mb.MemoryBankManager, name, getattr(mb.MemoryBankManager, name))
+    patched += ["NeighborRetr.utils.memory_bank.MemoryBankManager.load_memory_bank",
+                "NeighborRetr.utils.memory_bank.MemoryBankManager.clear_memory_bank"]
     return patched
