@@ -4,8 +4,8 @@
 ``HeadMixin`` holds the head methods with the reference's names, positional order and return types:
 ``local_level``, ``global_level``, ``compute_centrality_weights``, ``compute_centrality_loss``,
 ``compute_neighbor_loss``, ``compute_uniform_loss``, ``_compute_losses``, ``update_memory_bank``,
-``get_similarity_logits``.  ``NeighborRetr`` is a weights-free standalone module built on it (encoders and
-token clustering are out of scope — SURVEY.md §2 rows 13/14 — and are injected by the caller);
+``get_similarity_logits``.  ``NeighborRetr`` is a weights-free standalone module built on it (the encoders are out of scope —
+SURVEY.md §2 row 14 — and are injected by the caller; the token-clustering layers of cluster.py are optional);
 ``neighborretr_b200.install()`` rebinds the same methods onto the reference's class so that the
 reference's ``main.py`` runs unchanged on the CUDA path.
 
@@ -319,20 +319,27 @@ class NeighborRetr(HeadMixin, nn.Module):
 
     ``encoder(text_ids, text_mask, video, video_mask) -> (text_feat [B,Nt,D], video_feat [B,Nv,D])`` and
     ``global_merger(text_feat, video_feat, text_mask, video_mask) -> (gT [B,1,D], gV [B,1,D])`` stand in for
-    the CLIP towers and the token-clustering blocks, both out of scope here.
+    the CLIP towers (out of scope) and the token-clustering blocks; ``token_clustering=True`` registers the
+    reference's eight CTM / TCBlock layers (cluster.py, same parameter names) and uses them instead of a callable.
     """
 
-    def __init__(self, config, encoder=None, global_merger=None, width=512):
+    def __init__(self, config, encoder=None, global_merger=None, width=512, token_clustering=False,
+                 cluster_heads=8):
         super().__init__()
         self.config = config
         self.transformer_width = width
         self.encoder = encoder
         self.global_merger = global_merger
+        self.token_clustering = bool(token_clustering)
         self._init_weighting_networks()
         self._init_loss_functions()
         self._init_memory_bank()
         self.clip = _LogitScale()
         self.apply(self._init_weights)
+        if self.token_clustering:
+            # reference :186-197 (created after the generic init there too: the blocks keep their own init)
+            from .cluster import init_token_clustering
+            init_token_clustering(self, dim=width, num_heads=cluster_heads, k=3)
 
     # reference :137-153 (all eight networks are kept so state_dicts load; four are unused, as there)
     def _init_weighting_networks(self):
@@ -366,11 +373,16 @@ class NeighborRetr(HeadMixin, nn.Module):
         if isinstance(module, nn.Linear) and module.bias is not None:
             module.bias.data.zero_()
 
-    def merge_global_features(self, text_feat, video_feat, text_mask, video_mask):
-        if self.global_merger is None:
-            raise NotImplementedError("token clustering (reference cluster.py CTM/TCBlock) is out of scope: pass "
-                                      "global_merger=... or global_feats=(gT, gV)")
-        return self.global_merger(text_feat, video_feat, text_mask, video_mask)
+    def merge_global_features(self, text_feat, video_feat, text_mask, video_mask, noise=None):
+        """Reference :446-481.  ``global_merger`` (a callable) wins; else the token-clustering layers of cluster.py
+        when the head was built with ``token_clustering=True``."""
+        if self.global_merger is not None:
+            return self.global_merger(text_feat, video_feat, text_mask, video_mask)
+        if self.token_clustering:
+            from .cluster import merge_global_features
+            return merge_global_features(self, text_feat, video_feat, text_mask, video_mask, noise=noise)
+        raise NotImplementedError("no global-feature producer: build the head with token_clustering=True, or pass "
+                                  "global_merger=... or global_feats=(gT, gV)")
 
     def get_text_video_feat(self, text_ids, text_mask, video, video_mask, shaped=False):
         if self.encoder is None:

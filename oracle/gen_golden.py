@@ -228,6 +228,48 @@ def run_prefill():
     print("prefill ok", n)
 
 
+CLUSTER_CASES = {
+    # name: (batch, words, frames, width, heads)
+    "msr": (12, 24, 12, 32, 8),        # merges to one global token per modality
+    "act": (6, 64, 64, 32, 4),         # 64 words / 64 frames: 3 text and 6 video global tokens
+}
+
+
+def run_cluster(modeling):
+    """Token clustering of the reference: ``NeighborRetr.merge_global_features`` (modeling.py:446-481) on a shell
+    whose eight CTM / TCBlock layers are the reference's own classes (cluster.py) at a small width.  Stores the
+    layers' state_dict, the outputs and gradients; the torch.rand tie-break noise is pinned by ``manual_seed``."""
+    from NeighborRetr.models import cluster as C
+    out = {}
+    for name, (b, nt, nv, d, heads) in CLUSTER_CASES.items():
+        torch.manual_seed(7)
+        shell = nn.Module()
+        for mod, (r0, r1) in (("text", (1 / 6, 1 / 4)), ("video", (1 / 4, 1 / 3))):     # modeling.py:186-197
+            setattr(shell, f"{mod}_ctm0", C.CTM(sample_ratio=r0, embed_dim=d, dim_out=d, k=3))
+            setattr(shell, f"{mod}_block0", C.TCBlock(dim=d, num_heads=heads))
+            setattr(shell, f"{mod}_ctm1", C.CTM(sample_ratio=r1, embed_dim=d, dim_out=d, k=3))
+            setattr(shell, f"{mod}_block1", C.TCBlock(dim=d, num_heads=heads))
+        for p in shell.parameters():              # non-trivial biases / LayerNorm gains
+            if p.dim() == 1:
+                p.data.add_(0.1 * torch.randn_like(p))
+        h = synth.make_batch(b, nt, nv, d=d, seed=2024)
+        text = (h.text_feat / 6).clone().requires_grad_(True)
+        video = (h.video_feat / 6).clone().requires_grad_(True)
+        torch.manual_seed(123)
+        gt, gv = modeling.NeighborRetr.merge_global_features(shell, text, video, h.text_mask, h.video_mask)
+        wt = torch.linspace(-1, 1, gt.numel()).view_as(gt)
+        wv = torch.linspace(1, -1, gv.numel()).view_as(gv)
+        ((gt * wt).sum() + (gv * wv).sum()).backward()
+        out[f"{name}_gt"], out[f"{name}_gv"] = gt.detach().numpy(), gv.detach().numpy()
+        out[f"{name}_dtext"], out[f"{name}_dvideo"] = text.grad.numpy(), video.grad.numpy()
+        for k, v in shell.state_dict().items():
+            out[f"{name}_p_{k}"] = v.numpy()
+        for k, p in shell.named_parameters():
+            out[f"{name}_g_{k}"] = p.grad.numpy() if p.grad is not None else np.zeros(0, np.float32)
+        print("cluster", name, tuple(gt.shape), tuple(gv.shape))
+    np.savez_compressed(os.path.join(OUT, "cluster.npz"), **out)
+
+
 def run_bank(modeling):
     c = dict(b=6, nt=4, nv=3, d=8, m=8, k=20)
     cfg = synth.default_config()
@@ -258,6 +300,7 @@ def main():
     run_bank(modeling)
     run_multi_sentence(metrics)
     run_prefill()
+    run_cluster(modeling)
 
 
 if __name__ == "__main__":
