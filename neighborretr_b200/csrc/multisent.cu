@@ -57,7 +57,7 @@ __device__ __forceinline__ void store_counts(int64_t q, float sd, int G, int E, 
   if (valid) valid[q] = ok ? 1 : 0;
 }
 
-// long rows: one CTA per caption row
+// few long rows: one CTA per caption row
 __global__ void __launch_bounds__(256)
 rank_target_kernel(const float* __restrict__ S, int64_t lds, int N, const int32_t* __restrict__ target,
                    const float* __restrict__ diag, int64_t col_offset, int32_t* __restrict__ gt,
@@ -83,8 +83,9 @@ rank_target_kernel(const float* __restrict__ S, int64_t lds, int N, const int32_
   }
 }
 
-// short rows (a few hundred to a few thousand videos, the usual test sets): one WARP per caption row, 8 rows per
-// CTA, shuffles only — a 256-thread CTA per 2.7 KB row would spend its time on launch and barrier overhead
+// short rows, or many rows (the usual test sets: thousands of captions x a few hundred to a few thousand videos):
+// one WARP per caption row, 8 rows per CTA, shuffles only — measured 243 us for 98k x 4096 (6.6 TB/s) against
+// 411 us with a 256-thread CTA per row, which spends its time on launch and barrier overhead
 __global__ void __launch_bounds__(256)
 rank_target_warp_kernel(const float* __restrict__ S, int64_t lds, int64_t Q, int N,
                         const int32_t* __restrict__ target, const float* __restrict__ diag, int64_t col_offset,
@@ -131,15 +132,20 @@ group_max_t_kernel(const float* __restrict__ S, int64_t lds, int V, const int32_
         m3 = v.w > m3 ? v.w : m3;
       }
     } else {
-      // matrix rows not 16-byte aligned, or the last partial column tile: coalesced scalar loads, lane l
-      // takes columns j0 + l + 32*c; the tile index below follows the same mapping
-      const float* p = S + (int64_t)t0 * lds + j0 + lane;
-      const int nc = (V - j0 - lane + 31) / 32;          // columns of this lane inside the matrix (<= 0: none)
+      // matrix rows not 16-byte aligned, or the last partial column tile: coalesced scalar loads, lane l takes
+      // columns j0 + l + 32*c (the tile index below follows the same mapping).  Columns past the matrix are
+      // clamped to its last column — loads stay unconditional (4 rows x 4 loads in flight per lane) and the
+      // results of clamped columns are never written
+      const int last = V - 1 - j0;
+      const int o0 = min(lane, last), o1 = min(lane + 32, last), o2 = min(lane + 64, last), o3 = min(lane + 96, last);
+      const float* p = S + (int64_t)t0 * lds + j0;
+#pragma unroll 4
       for (int t = t0; t < t1; ++t, p += lds) {
-        if (nc > 0) { float a = p[0]; m0 = a > m0 ? a : m0; }
-        if (nc > 1) { float b = p[32]; m1 = b > m1 ? b : m1; }
-        if (nc > 2) { float c = p[64]; m2 = c > m2 ? c : m2; }
-        if (nc > 3) { float d = p[96]; m3 = d > m3 ? d : m3; }
+        const float a = p[o0], b = p[o1], c = p[o2], d = p[o3];
+        m0 = a > m0 ? a : m0;
+        m1 = b > m1 ? b : m1;
+        m2 = c > m2 ? c : m2;
+        m3 = d > m3 ? d : m3;
       }
       interleaved = true;
     }
@@ -171,7 +177,8 @@ extern "C" int nr_rank_count_target(const float* S, int64_t lds, int64_t Q, int6
                                     int32_t* valid, void* stream) {
   NR_CHECK_ARG(S && target && gt && eq_before && Q > 0 && N > 0 && lds >= N, "nr_rank_count_target: bad arguments");
   NR_CHECK_ARG(Q <= 2147483647LL && N <= 2147483647LL, "nr_rank_count_target: sizes exceed int32");
-  if (N <= 4096)
+  // a warp per row needs enough rows to fill the machine (148 SMs x 64 warps); few long rows take a CTA per row
+  if (N <= 2048 || Q >= 4736)
     rank_target_warp_kernel<<<(unsigned)((Q + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, lds, Q, (int)N, target, diag,
                                                                                       col_offset, gt, eq_before, valid);
   else

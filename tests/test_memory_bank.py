@@ -63,7 +63,9 @@ def test_prefill_short_loader_ragged_batch_and_wrapped_model():
     assert MemoryBankManager(_args(mb_batch=0)).load_memory_bank(m3, big, "cpu", 0) == 0 and m3.mb_batch == 0
 
 
-def test_prefill_rejects_inconsistent_batches_and_missing_loader():
+def test_prefill_rejects_inconsistent_batches_and_missing_loader(monkeypatch):
+    import sys
+    monkeypatch.setitem(sys.modules, "NeighborRetr.dataloaders.data_dataloaders", None)   # reference not importable
     bad = synth.make_prefill_loader(2, 5)
     bad[1] = (bad[1][0][:, :3],) + bad[1][1:]                       # text ids with fewer words than the mask
     model = synth.ToyEncoder(d=8)

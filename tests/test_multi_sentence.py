@@ -210,6 +210,26 @@ def test_gpu_multi_sentence_kernels_vs_counting_oracle(V, maxlen, ties, nonfinit
 
 
 @pytest.mark.gpu
+def test_gpu_rank_target_few_long_rows():
+    """Few rows x many columns takes the CTA-per-row variant (Q < 4736 and N > 2048); unaligned row starts."""
+    from neighborretr_b200 import ops
+    rng = np.random.RandomState(3)
+    Q, N = 300, 5001
+    sim = rng.randint(0, 40, size=(Q, N)).astype(np.float32)
+    sim[rng.rand(Q, N) < 0.002] = np.nan
+    tgt = rng.randint(0, N, size=Q).astype(np.int32)
+    sim[5, tgt[5]] = np.inf                                               # an invalid row
+    gt, eqb, valid = ops.rank_counts_target(torch.from_numpy(sim).cuda(), torch.from_numpy(tgt).cuda())
+    sd = sim[np.arange(Q), tgt][:, None]
+    ok = np.isfinite(sd[:, 0])
+    want_g = ((sim > sd) | np.isnan(sim)).sum(1)
+    want_e = ((sim == sd) & (np.arange(N)[None, :] < tgt[:, None])).sum(1)
+    assert np.array_equal(valid.cpu().numpy().astype(bool), ok) and not ok[5]
+    assert np.array_equal(gt.cpu().numpy()[ok], want_g[ok]) and np.array_equal(eqb.cpu().numpy()[ok], want_e[ok])
+    assert gt[5].item() == 0 and eqb[5].item() == 0
+
+
+@pytest.mark.gpu
 def test_gpu_multi_sentence_rejects_bad_shapes():
     from neighborretr_b200 import ops
     from neighborretr_b200.evaluator import multi_sentence_metrics
