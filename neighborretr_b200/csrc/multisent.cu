@@ -115,12 +115,10 @@ group_max_t_kernel(const float* __restrict__ S, int64_t lds, int V, const int32_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j0 = blockIdx.x * 128, i0 = blockIdx.y * 8, i = i0 + warp;
   float m0 = NR_NEG_INF, m1 = NR_NEG_INF, m2 = NR_NEG_INF, m3 = NR_NEG_INF;
-  bool interleaved = false;
   if (i < G) {
     const int t0 = group_start[i], t1 = group_start[i + 1];
     const int jl = j0 + lane * 4;
-    // warp-uniform choice: the column mapping of the whole warp follows it
-    const bool vec = ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (j0 + 128 <= V);
+    const bool vec = ((lds & 3) == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (jl + 3 < V);
     if (vec) {
       const float* p = S + (int64_t)t0 * lds + jl;
 #pragma unroll 4
@@ -131,36 +129,25 @@ group_max_t_kernel(const float* __restrict__ S, int64_t lds, int V, const int32_
         m2 = v.z > m2 ? v.z : m2;
         m3 = v.w > m3 ? v.w : m3;
       }
-    } else {
-      // matrix rows not 16-byte aligned, or the last partial column tile: coalesced scalar loads, lane l takes
-      // columns j0 + l + 32*c (the tile index below follows the same mapping).  Columns past the matrix are
-      // clamped to its last column — loads stay unconditional (4 rows x 4 loads in flight per lane) and the
-      // results of clamped columns are never written
-      const int last = V - 1 - j0;
-      const int o0 = min(lane, last), o1 = min(lane + 32, last), o2 = min(lane + 64, last), o3 = min(lane + 96, last);
-      const float* p = S + (int64_t)t0 * lds + j0;
-#pragma unroll 4
+    } else if (jl < V) {
+      // rows not 16-byte aligned (matrix width not a multiple of 4) or the last partial float4 of a row: the same
+      // 4 consecutive columns per lane with scalar loads.  Measured on 98k x 4097: 356 us (4.7 TB/s); an interleaved
+      // mapping (lane l -> columns l, l+32, l+64, l+96) was slower (574 us), so this one stays
+      const float* p = S + (int64_t)t0 * lds + jl;
+      const int nc = V - jl;              // 1..3 real columns (or >= 4 on an unaligned matrix)
       for (int t = t0; t < t1; ++t, p += lds) {
-        const float a = p[o0], b = p[o1], c = p[o2], d = p[o3];
+        float a = p[0];
         m0 = a > m0 ? a : m0;
-        m1 = b > m1 ? b : m1;
-        m2 = c > m2 ? c : m2;
-        m3 = d > m3 ? d : m3;
+        if (nc > 1) { float b = p[1]; m1 = b > m1 ? b : m1; }
+        if (nc > 2) { float c = p[2]; m2 = c > m2 ? c : m2; }
+        if (nc > 3) { float d = p[3]; m3 = d > m3 ? d : m3; }
       }
-      interleaved = true;
     }
   }
-  if (interleaved) {
-    tile[warp][lane] = m0;
-    tile[warp][lane + 32] = m1;
-    tile[warp][lane + 64] = m2;
-    tile[warp][lane + 96] = m3;
-  } else {
-    tile[warp][lane * 4 + 0] = m0;
-    tile[warp][lane * 4 + 1] = m1;
-    tile[warp][lane * 4 + 2] = m2;
-    tile[warp][lane * 4 + 3] = m3;
-  }
+  tile[warp][lane * 4 + 0] = m0;
+  tile[warp][lane * 4 + 1] = m1;
+  tile[warp][lane * 4 + 2] = m2;
+  tile[warp][lane * 4 + 3] = m3;
   __syncthreads();
   for (int e = threadIdx.x; e < 8 * 128; e += 256) {
     const int jj = e >> 3, ii = e & 7;
