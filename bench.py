@@ -130,18 +130,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nt, nv, mrows = synth.SHAPES[args.shape]
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
-    sps, ms, threads = cpu_reference_steps(args.shape, steps, warm)
+    # the reference evaluates the WHOLE global batch on every rank, so the job at N GPUs is one head
+    # over B = 128*N samples: that is what the host cores are timed on, once (rank 0), with all their threads
+    world = max(1, args.gpus)
+    b_global = B_PER_GPU * world
+    steps = max(1, min(args.steps, 8 if world == 1 else (4 if world == 2 else 2)))
+    warm = max(1, min(args.warmup, 2 if world == 1 else 1))
+    sps, ms, threads = cpu_reference_steps(args.shape, steps, warm, b=b_global)
     line = {
         "impl": "reference", "metric": "head_fwd_bwd_steps_per_s", "value": sps, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.shape, 1, "fp32"),
+        "config": workload_config(args.shape, world),
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} fwd+bwd steps of oracle/head.py compute_losses (torch CPU, fp32), "
-                                   f"b={B_PER_GPU}, single-process batch (no gather)"},
+                         "sample": f"{steps} fwd+bwd steps (after {warm} warm-up) of oracle/head.py compute_losses "
+                                   f"(torch CPU, fp32) on the global batch B={b_global} in one process (the gathered "
+                                   f"batch every reference rank evaluates; no collective)"},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -201,11 +205,12 @@ def run_eval_bench(model, dev, steps, nq=1000):
     return out
 
 
-def workload_config(shape, world, precision):
+def workload_config(shape, world):
+    """The workload both arms run (the arithmetic type of an arm is its `dtype`, not part of the workload)."""
     nt, nv, mrows = synth.SHAPES[shape]
     return {"workload": f"{shape}_head_b{B_PER_GPU}_per_gpu", "per_gpu_batch": B_PER_GPU,
             "global_batch": B_PER_GPU * world, "words": nt, "frames": nv, "dim": D, "memory_rows": mrows,
-            "num_neighbors": 20, "sinkhorn_iters": 50, "precision": precision,
+            "num_neighbors": 20, "sinkhorn_iters": 50,
             "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"dp{world}"}
 
 
@@ -371,7 +376,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": workload_config(args.shape, world, args.precision),
+        "config": workload_config(args.shape, world), "head_precision": args.precision,
         "samples_per_s": args.steps * B / (ms_total * 1e-3),
         "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 20, "ms_per_step": ms_e2e / args.steps,
