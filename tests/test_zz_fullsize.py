@@ -1,0 +1,174 @@
+"""Parity at BASELINE.json's FULL sizes (GPU only).  The oracle (oracle/head.py, device-generic functional torch)
+runs on the same GPU in fp32 here — it is the checker, never the thing measured — because its 4-D token-pair
+tensor takes minutes on host cores at these sizes:
+
+  configs[1]  MSR-VTT-shaped head at global batch 1024 (what 8 ranks x 128 evaluate), 512 bank rows
+  configs[2]  ActivityNet-shaped head, 64 words x 64 frames, b = 128, 1024 bank rows
+  configs[3]  evaluation 1000 x 1000: similarity matrix + bit-exact t2v / v2t ranks
+  configs[4]  scaled sweep: 100k-video gallery (rank counts, column shards, top-k merge), global batch 8192
+              (row losses, Sinkhorn, top-k neighbours on [8192, 8192]; token-pair contraction block check)
+
+Tolerances (north_star): losses 1e-4 relative in fp32 and 1e-2 in bf16; gradients rel-L2 1e-3 (fp32) / 5e-2 (bf16);
+top-k neighbour indices and ranks bit-exact from the same fp32 matrix.  Measured values are printed (-rP)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import cuda_losses, make_head, oracle_losses, rel_l2, set_bank
+from neighborretr_b200 import synth
+from oracle import head as O
+from oracle import metrics as OM
+
+pytestmark = pytest.mark.gpu
+
+
+def _bank_cuda(bank):
+    return SimpleNamespace(**{k: v.cuda() for k, v in vars(bank).items()})
+
+
+def _params_cuda(params):
+    return {k: {n: v.cuda() for n, v in sd.items()} for k, sd in params.items()}
+
+
+def _head_case(b, shape, precision):
+    nt, nv, mrows = synth.SHAPES[shape]
+    h = synth.make_batch(b, nt, nv, d=512, seed=1234)
+    bank = synth.make_bank(mrows, nt, nv, d=512)
+    params = synth.make_mlp_params(d=512)
+    cfg = synth.default_config()
+    m = make_head(512, cfg, params, precision)
+    set_bank(m, bank)
+    losses, grads = cuda_losses(m, h, cfg)
+    ref, rgrads = oracle_losses(h.to("cuda"), _bank_cuda(bank), _params_cuda(params), cfg)    # oracle on the GPU
+    return losses, grads, ref.cpu(), {k: v.detach().cpu() for k, v in rgrads.items()}
+
+
+def _check_head(losses, grads, ref, rgrads, precision, tag):
+    ltol, gtol = (1e-4, 1e-3) if precision == "fp32" else (1e-2, 5e-2)
+    lerr = float((losses / ref - 1).abs().max())
+    gerr = {k: rel_l2(grads[k], rgrads[k]) for k in ("text", "video", "gt", "gv")}
+    print(f"{tag}[{precision}] losses {losses.tolist()} max rel err {lerr:.2e}; grad rel-L2 {gerr}")
+    np.testing.assert_allclose(losses.numpy(), ref.numpy(), rtol=ltol)
+    for k, e in gerr.items():
+        assert e < gtol, (k, e)
+    ls_err = abs(grads["logit_scale"].item() / rgrads["logit_scale"].item() - 1)
+    assert ls_err < (1e-3 if precision == "fp32" else 3e-2), ls_err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg2_msrvtt_head_global_batch_1024(precision):
+    _check_head(*_head_case(1024, "msrvtt", precision), precision, "cfg2 B=1024")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cfg3_activitynet_head_b128(precision):
+    _check_head(*_head_case(128, "activitynet", precision), precision, "cfg3 ACT b=128")
+
+
+def test_cfg4_eval_1000x1000_similarity_and_ranks():
+    from neighborretr_b200.evaluator import _run_on_single_gpu
+    from neighborretr_b200.metrics import RetrievalMetrics
+    n, nt, nv = 1000, 24, 12
+    h = synth.make_batch(n, nt, nv, d=512, seed=77).to("cuda")
+    params = synth.make_mlp_params(d=512)
+    cfg = synth.default_config()
+    m = make_head(512, cfg, params, "fp32").eval()
+    sim, sim_t = _run_on_single_gpu(m, h.text_mask, h.video_mask, h.text_feat, h.video_feat)
+    want, _ = O.eval_similarity(h.text_feat, h.video_feat, h.text_mask, h.video_mask, _params_cuda(params),
+                                mini_batch=250)
+    err = float(np.abs(sim - want).max())
+    print(f"cfg4 1000x1000 fp32 sim max abs err {err:.2e}")
+    assert sim.shape == (n, n) and err < 1e-5
+    for mat in (sim, np.ascontiguousarray(sim_t)):
+        got, ref = RetrievalMetrics.compute_metrics(mat), OM.compute_metrics(mat)      # same fp32 matrix
+        assert got["cols"] == ref["cols"]                                               # bit-exact ranks
+        for k in ("R1", "R5", "R10", "R50", "MR", "MedianR", "MeanR"):
+            assert got[k] == ref[k], k
+    mb = make_head(512, cfg, params, "bf16").eval()
+    sim_b, _ = _run_on_single_gpu(mb, h.text_mask, h.video_mask, h.text_feat, h.video_feat)
+    errb = float(np.abs(sim_b - want).max())
+    print(f"cfg4 1000x1000 bf16 sim max abs err {errb:.2e}")
+    assert errb < 1e-2
+
+
+def test_cfg5_gallery_100k_rank_counts_shards_and_topk():
+    from neighborretr_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Q, N, W = 2048, 100_000, 8
+    S = torch.randint(0, 1000, (Q, N), generator=g, device="cuda").float()            # many exact ties
+    d = S.diagonal().contiguous()
+    gt, eq = ops.rank_counts(S)
+    assert torch.equal(gt.long(), (S > d[:, None]).sum(1)) and torch.equal(eq.long(), (S == d[:, None]).sum(1))
+    g2 = torch.zeros(Q, dtype=torch.int32, device="cuda")
+    e2 = torch.zeros(Q, dtype=torch.int32, device="cuda")
+    n = N // W
+    for r in range(W):                                                                # 12 500 columns per shard
+        ops.rank_counts(S[:, r * n:(r + 1) * n].contiguous(), diag=d, gt=g2, eq=e2)
+    assert torch.equal(g2, gt) and torch.equal(e2, eq)
+    F = torch.randn(512, N, generator=g, device="cuda")
+    parts = [ops.topk_rows(F[:, r * n:(r + 1) * n].contiguous(), 10, col_offset=r * n) for r in range(W)]
+    v, i = ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    rv, ri = torch.sort(F, dim=1, descending=True, stable=True)
+    assert torch.equal(i.long(), ri[:, :10]) and torch.equal(v, rv[:, :10])
+
+
+def test_cfg5_batch_8192_row_losses_sinkhorn_and_neighbours():
+    from neighborretr_b200 import until_module as U
+    B, M = 8192, 512
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.nn.functional.normalize(torch.randn(B, 64, generator=g, device="cuda"), dim=-1)
+    y = torch.nn.functional.normalize(x + 0.5 * torch.randn(B, 64, generator=g, device="cuda"), dim=-1)
+    S = (x @ y.t()).contiguous()
+    G = (3.0 * S + 0.1 * torch.randn(B, B, generator=g, device="cuda")).contiguous()
+    Smb = 0.1 * torch.randn(B, M, generator=g, device="cuda")
+    w = torch.exp(0.3 * torch.rand(B, generator=g, device="cuda"))
+
+    def both(tag, fn_o, fn_c, tol, *tensors):
+        a = [t.clone().requires_grad_(True) for t in tensors]
+        b = [t.clone().requires_grad_(True) for t in tensors]
+        lo = fn_o(*a); lo.backward()
+        lc = fn_c(*b); lc.backward()
+        rel = abs(lc.item() / lo.item() - 1)
+        gerr = [float((q.grad - p.grad).double().norm() / p.grad.double().norm()) for p, q in zip(a, b)]
+        print(f"B=8192 {tag}: ours {lc.item():.6e} oracle {lo.item():.6e} rel {rel:.1e} grad rel-L2 {gerr}")
+        assert rel < tol, (tag, rel)
+        for e in gerr:
+            assert e < 1e-3, (tag, e)
+
+    both("centrality", lambda s, ww: O.centrality_weighting_loss(s * 100.0, ww),
+         lambda s, ww: U.CentralityWeightingLoss()(s * 100.0, ww), 1e-4, S, w)
+    nal = U.NeighborAdjustingLoss()
+    both("neighbour", lambda s, mb: O.neighbor_adjusting_loss(s, mb, 20, 3.0), lambda s, mb: nal(s, mb, 20, 3.0),
+         1e-4, S, Smb)
+    assert torch.equal(nal.last_neighbors.long(), O.neighbor_topk(S, 20))            # order and set, bit-exact
+    both("kl", O.kl_divergence_loss, lambda gg, s: U.KLDivergenceLoss()(gg, s), 1e-3, G, S)
+    both("uniform", lambda gg: O.uniform_regularization_loss(gg, 3.0, 0.7),
+         lambda gg: U.UniformRegularizationLoss()(gg, 3.0, 0.7), 1e-3, G)
+    # the Sinkhorn target matrix itself against the oracle's 50 log-domain iterations
+    t_ours = U.UniformRegularizationLoss().sinkhorn_algorithm(G, 0.7, 50)
+    t_ref = O.sinkhorn_targets(G, 0.7, 50)
+    err = float((t_ours - t_ref).abs().max() / t_ref.abs().max())
+    print(f"B=8192 sinkhorn target max err / max {err:.1e}")
+    assert err < 1e-3
+
+
+def test_cfg5_batch_8192_token_pair_contraction_blocks():
+    """[8192 x 8192] MSR-VTT-shaped similarity in one launch (the 4-D tensor of the reference would be 72 GiB): a
+    block of rows against the oracle, the transposed output, and invariance under the size of the launch."""
+    b, nt, nv = 8192, 24, 12
+    h = synth.make_batch(b, nt, nv, d=512, seed=31).to("cuda")
+    params = synth.make_mlp_params(d=512)
+    cfg = synth.default_config()
+    m = make_head(512, cfg, params, "bf16").eval()
+    with torch.no_grad():
+        s, st = m.local_level(h.text_feat, h.video_feat, h.text_mask, h.video_mask)
+        assert s.shape == (b, b) and torch.equal(st, s.t())
+        rows = slice(4096, 4128)
+        want, _ = O.local_level(h.text_feat[rows], h.video_feat, h.text_mask[rows], h.video_mask, _params_cuda(params))
+        err = float((s[rows] - want).abs().max())
+        part, _ = m.local_level(h.text_feat[rows], h.video_feat, h.text_mask[rows], h.video_mask)
+        inv = float((part - s[rows]).abs().max())
+    print(f"B=8192 bf16 block max abs err vs oracle {err:.2e}; same rows in a small launch differ by {inv:.2e}")
+    assert err < 5e-3 and inv < 1e-5
