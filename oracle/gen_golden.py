@@ -6,9 +6,12 @@ imports), builds a weights-free ``NeighborRetr`` shell, ex
 reference's own head functions on seeded synthetic inputs and stores their outputs.  The GPU box
 has no ``/root/reference``; tests only read the committed ``.npz`` files.
 
-The only intervention on the reference is replacing ``merge_global_features`` (token clustering
-with ``torch.rand`` noise, cluster.py:483-484 — out of scope) by a function
-returning the seeded global features, so that ``_compute_losses`` is deterministic.
+The only intervention on the reference in the head cases is replacing ``merge_global_features``
+(token clustering with ``torch.rand`` noise, cluster.py:483-484) by a function
+returning the seeded global features, so that ``_compute_losses`` is deterministic.  The token
+clustering itself is pinned separately (``run_cluster``: the reference's own CTM / TCBlock classes
+under ``torch.manual_seed``), as are the multi-sentence metrics (``run_multi_sentence``) and the
+memory-bank manager (``run_prefill``).
 """
 from __future__ import annotations
 
