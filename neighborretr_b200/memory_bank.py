@@ -21,9 +21,6 @@ import torch
 
 from .until_module import AllGather
 
-FIELDS = ("mb_ind", "mb_feat_t", "mb_mask_t", "mb_feat_v", "mb_mask_v")
-
-
 class _Staging:
     """Five row-major staging buffers filled batch by batch (allocated on the first batch)."""
 
