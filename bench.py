@@ -298,12 +298,27 @@ def run_ours(args):
         step(resident, False)
     use_graph = not args.no_graph
     gstep = None
+    parity = None
+    do_check = (world > 1) if args.check is None else bool(args.check)
     if use_graph:
         from neighborretr_b200.graph import FIELDS, GraphedHeadStep
         reset_bank()
         res_list = [resident[f] for f in FIELDS]
         pin_list = [pinned[f] for f in FIELDS]
         gstep = GraphedHeadStep(model, res_list, warmup=warm)
+        if do_check:
+            # the graph-captured step that is timed below, against the single-process full-batch head
+            from neighborretr_b200 import selfcheck
+            ref = selfcheck.full_batch_reference(dev, world, args.shape, B_PER_GPU, mrows, args.precision,
+                                                 args.bwd_precision)
+            out = gstep(*res_list)
+            err = selfcheck.compare_step(ref, rank, B_PER_GPU, out, gstep.grads, model)
+            ok, parity = selfcheck.check_all_ranks(err, args.precision, dev)
+            parity["step"] = "GraphedHeadStep replay (captured NCCL collectives)" if world > 1 else "GraphedHeadStep replay"
+            del ref
+            if not ok:
+                raise SystemExit(f"bench.py --check FAILED on rank {rank}: {err}")
+            gstep.set_bank(bank)
         run_value = lambda: gstep(*res_list)
         run_e2e_serial = lambda: gstep(*pin_list, sync_losses_to=loss_host)
 
@@ -315,6 +330,26 @@ def run_ours(args):
 
         gstep.prefetch(*pin_list)               # fill the pipeline: the first timed step finds its batch staged
     else:
+        if do_check:
+            from neighborretr_b200 import selfcheck
+            ref = selfcheck.full_batch_reference(dev, world, args.shape, B_PER_GPU, mrows, args.precision,
+                                                 args.bwd_precision)
+            reset_bank()
+            t = resident
+            leaves = {f: t[f].detach().clone().requires_grad_(True)
+                      for f in ("text_feat", "video_feat", "global_text", "global_video")}
+            model.zero_grad(set_to_none=True)
+            ls_ = model.head_forward(leaves["text_feat"], leaves["video_feat"], t["text_mask"], t["video_mask"], t["idx"],
+                                     global_feats=(leaves["global_text"], leaves["global_video"]))
+            ls_[0].backward()
+            err = selfcheck.compare_step(ref, rank, B_PER_GPU, torch.stack([x.detach() for x in ls_]),
+                                         {f: v.grad for f, v in leaves.items()}, model)
+            ok, parity = selfcheck.check_all_ranks(err, args.precision, dev)
+            parity["step"] = "eager head_forward + backward"
+            del ref
+            if not ok:
+                raise SystemExit(f"bench.py --check FAILED on rank {rank}: {err}")
+            reset_bank()
         run_value = lambda: step(resident, False)
         run_e2e = run_e2e_serial = lambda: step(pinned, True)
     for _ in range(warm):
@@ -387,6 +422,7 @@ def run_ours(args):
                 "serial_note": "same call without prefetch: H2D copy, replay, D2H read strictly one after the other",
                 "eager_module_api_steps_per_s": args.steps / (ms_e2e_eager * 1e-3)},
         "cuda_graph": bool(use_graph),
+        "parity_checked": parity,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak,
@@ -428,6 +464,10 @@ def main():
     ap.add_argument("--bwd-precision", default=os.environ.get("NR_HEAD_BWD_PRECISION"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the eager module API instead of the CUDA graph")
+    ap.add_argument("--check", dest="check", action="store_const", const=1, default=None,
+                    help="before timing, compare the (graph-captured) step with the single-process full-batch head "
+                         "(default: on when N > 1)")
+    ap.add_argument("--no-check", dest="check", action="store_const", const=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,6 +56,13 @@ int nr_device_supported(void);
 int64_t nr_prep_partials(int64_t rows);
 int nr_prep_tokens(const float* x, int64_t rows, int64_t d, float* xn_f32, void* xn_bf16, float* inv_norm,
                    float* colsum_partials, const int64_t* mask, void* stream);
+/* Split-bf16 operand of the fp32-accurate tensor-core mode (NR_PREC_BF16X3; same reference lines): every
+ * normalised value n is written as hi = bf16(n), lo = bf16(n - hi) into xs_bf16 [rows, 3d]:
+ *   role 1 (X side of nr_maxsim2_fwd): [hi | lo | hi]      role 2 (Y side): [hi | hi | lo]
+ * so that nr_maxsim2_fwd with d' = 3d contracts hi.hi + lo.hi + hi.lo (error ~2^-17 per product instead of 2^-9).
+ * Its transposed copy (nr_transpose_tokens_bf16 with d' = 3d) holds hi^T and lo^T for nr_maxsim2_bwd. */
+int nr_prep_tokens_split(const float* x, int64_t rows, int64_t d, float* xn_f32, void* xs_bf16, int role,
+                         float* inv_norm, float* colsum_partials, const int64_t* mask, void* stream);
 /* backward of the normalisation: dx = (dxn + add_vec - xn <xn, dxn + add_vec>) * inv_norm.
  * add_vec [d] (nullable) is a gradient broadcast to every row (centrality mean path).
  * mask [rows] int64 (nullable): rows with mask == 0 ignore dxn (a masked token has no max-sim gradient).
@@ -123,7 +130,7 @@ int nr_maxsim2_fwd(const nr_maxsim2_problem* problems, int n_problems, int64_t N
  * side 0: dst [Rx*Nx, d] += C   * Y tokens   (srcT = transposed bf16 Y tokens [d, src_ld]),
  * side 1: dst [Ry*Ny, d] += C^T * X tokens   (srcT = transposed bf16 X tokens [d, src_ld]).
  * dst is fp32, zero- or partially-filled: split-K partials are combined with red.global.add.
- * Up to 6 such jobs share ONE launch; jobs with the same dst (e.g. the text gradient from the batch pair and from
+ * Up to 12 such jobs share ONE launch; jobs with the same dst (e.g. the text gradient from the batch pair and from
  * the bank pair) are accumulated in the same pass over their concatenated source tokens. */
 typedef struct {
   int side;
@@ -133,6 +140,11 @@ typedef struct {
   const float* dH; int64_t dh_sr, dh_sc; float dh_scale;
   int64_t Rx, Ry;
   float* dst;
+  /* 0: the routing tile as plain bf16 (NR_PREC_BF16).  NR_PREC_BF16X3: every routing coefficient c (the exact fp32
+   * sum of its two possible contributions) is split as hi = bf16(c), lo = bf16(c - hi): 2 = this job multiplies
+   * the hi tile, 3 = the lo tile.  A pair then takes three jobs on the same dst: (2, hi^T source), (3, hi^T source),
+   * (2, lo^T source). */
+  int part;
 } nr_maxsim2_bwd_job;
 int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int n_jobs, int64_t Nx, int64_t Ny, int64_t d, void* stream);
 /* ... w.r.t. the token weights (either output nullable):

@@ -10,12 +10,36 @@ Public surface mirrors the reference's module names:
     neighborretr_b200.memory_bank.MemoryBankManager
     neighborretr_b200.install(...)  -> rebind the above onto an imported reference checkout
 """
-__all__ = ["install"]
+__all__ = ["install", "bind_head"]
 
 
-def install(reference_pkg=None):
+def bind_head(cls, graph=True, precision=None):
+    """Rebind the head onto ONE class with the reference model's shape (``get_text_video_feat``,
+    ``merge_global_features``, ``config``, ``clip.logit_scale``, the two token-weight MLPs and the mb_* attributes —
+    reference modeling.py:137-197, :541-585): every HeadMixin method plus ``forward``.  install() calls this on the
+    reference's NeighborRetr; tests call it on a from-scratch stand-in.  Returns the rebound method names."""
+    from . import modeling as md
+    names = []
+    for name, fn in vars(md.HeadMixin).items():
+        if callable(fn) and not name.startswith("__"):
+            setattr(cls, name, fn)
+            names.append(name)
+    cls.forward = md.installed_forward
+    cls.head_graph = bool(graph)
+    cls.head_precision = precision or md.INSTALL_PRECISION
+    return names + ["forward"]
+
+
+def install(reference_pkg=None, graph=True, precision=None):
     """Rebind the CUDA head onto the already-importable reference package ``NeighborRetr`` so that the
-    reference's main.py / training loop run unchanged.  Returns the list of patched names."""
+    reference's main.py / training loop run unchanged.  Returns the list of patched names.
+
+    ``forward`` itself is replaced (reference modeling.py:251-312): the reference's encoders, then
+    ``head_forward`` — the row-block sharded head at world_size > 1 instead of five gathers + a replicated head.
+    graph=True: every training step of the head (forward + backward + bank FIFO) is one CUDA-graph replay whose
+    gradients are handed to autograd by ``loss.backward()`` (graph.GraphedHead).
+    precision: arithmetic of the token-pair contraction for the installed class, "bf16x3" (default: split-bf16
+    tensor-core products, fp32-accurate), "bf16" (fastest, 1e-2 loss tolerance) or "fp32" (CUDA cores)."""
     import importlib
 
     from . import evaluator as ev
@@ -29,11 +53,8 @@ def install(reference_pkg=None):
     ref_eval = importlib.import_module("NeighborRetr.training.evaluator")
     patched = []
     cls = ref_modeling.NeighborRetr
-    # every head method (public ones with the reference's names, plus the private helpers they call)
-    for name, fn in vars(md.HeadMixin).items():
-        if callable(fn) and not name.startswith("__"):
-            setattr(cls, name, fn)
-            patched.append(f"NeighborRetr.models.modeling.NeighborRetr.{name}")
+    # every head method (public ones with the reference's names, plus the private helpers they call) and forward
+    patched += [f"NeighborRetr.models.modeling.NeighborRetr.{n}" for n in bind_head(cls, graph, precision)]
     for name in ("CentralityWeightingLoss", "NeighborAdjustingLoss", "UniformRegularizationLoss",
                  "KLDivergenceLoss", "AllGather", "AllGather2"):
         for mod in (ref_until, ref_modeling):

@@ -24,6 +24,7 @@ SIGNATURES = {
     "nr_device_supported": (_I, []),
     "nr_prep_partials": (_I64, [_I64]),
     "nr_prep_tokens": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
+    "nr_prep_tokens_split": (_I, [_P, _I64, _I64, _P, _P, _I, _P, _P, _P, _P]),
     "nr_prep_tokens_bwd": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I, _P]),
     "nr_mlp_chunks": (_I64, [_I64]),
     "nr_token_weights_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
@@ -70,12 +71,13 @@ class MaxSim2Problem(ctypes.Structure):
 class MaxSim2BwdJob(ctypes.Structure):
     """nr_maxsim2_bwd_job of include/nrhead.h (field order and types must match)."""
     _fields_ = [("side", _I), ("srcT", _P), ("src_ld", _I64), ("wx", _P), ("wy", _P), ("ystar", _P), ("xstar", _P),
-                ("dH", _P), ("dh_sr", _I64), ("dh_sc", _I64), ("dh_scale", _F), ("Rx", _I64), ("Ry", _I64), ("dst", _P)]
+                ("dH", _P), ("dh_sr", _I64), ("dh_sc", _I64), ("dh_scale", _F), ("Rx", _I64), ("Ry", _I64), ("dst", _P),
+                ("part", _I)]
 
 
 NR_LOSS_CENTRALITY, NR_LOSS_NEIGHBOR, NR_LOSS_KL, NR_LOSS_UNIFORM = 1, 2, 4, 8
 NR_NSAVE = 16
-NR_PREC_FP32, NR_PREC_BF16 = 0, 1
+NR_PREC_FP32, NR_PREC_BF16, NR_PREC_BF16X3 = 0, 1, 2
 
 _lock = threading.Lock()
 _lib = None

@@ -29,9 +29,9 @@ constexpr int B2_BM = 128;
 constexpr int B2_BK = 64;
 constexpr int B2_A_BYTES = B2_BM * 128;       // 16 KB
 constexpr int B2_B_HALF_BYTES = 256 * 128;    // one d-half of a source k-block: 256 rows x 128 B
-constexpr int B2_MAX_JOBS = 6;
+constexpr int B2_MAX_JOBS = 12;
 constexpr int B2_MAX_SIDES = 4;
-constexpr int B2_MAX_SRC = 3;
+constexpr int B2_MAX_SRC = 6;
 
 // One job = one source operand S contributing to the gradient of one output operand O ("side"):
 //   starO[ro*aO_o + rs*aO_s + o] arg-max over the source tokens for out token o of the pair (ro, rs)
@@ -43,6 +43,7 @@ struct B2Src {
   const uint8_t* starS; int64_t aS_o, aS_s;
   const float* dH; int64_t g_o, g_s; float scale;
   int Rs, Ns, src_tokens, num_kb, kb0;        // kb0: first k-block of this source in the side's concatenated K range
+  int part;                                   // 0 plain bf16 tile; 2 / 3: hi / lo tile of the exact fp32 coefficient
 };
 struct B2Side {
   const float* wO; float* dst;
@@ -55,6 +56,12 @@ struct alignas(64) B2Args {
   B2Side sides[B2_MAX_SIDES];
   int nsides, n_items, D, n_half, half_cols, debug;
 };
+
+// plain bf16 coefficient (part 0 / 2) or the remainder of its bf16 rounding (part 3)
+__device__ __forceinline__ __nv_bfloat16 coef_part(float c, int part) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(c);
+  return part == 3 ? __float2bfloat16_rn(c - __bfloat162float(hi)) : hi;
+}
 
 __device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float c, float d) {
   asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
             const int t = rs * Ns + cur.sv[i] - t0;
             if (rs <= rs_hi && t >= 0 && t < B2_BK)
               *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
-                  __float2bfloat16_rn(cur.gv[i] * coefo);
+                  coef_part(cur.gv[i] * coefo, J.part);
           }
           if (rs_lo + 8 <= rs_hi) {                                // remainder (Ns < 10 only)
             const uint8_t* stO = J.starO + (int64_t)ro * J.aO_o + o;
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
               const int t = rs * Ns + (int)stO[(int64_t)rs * J.aO_s] - t0;
               if (t >= 0 && t < B2_BK)
                 *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
-                    __float2bfloat16_rn(gpO[(int64_t)rs * J.g_s] * coefo);
+                    coef_part(gpO[(int64_t)rs * J.g_s] * coefo, J.part);
             }
           }
         }
@@ -264,12 +271,23 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
         // (2) source-token side: column j, one entry per out sample of this tile; lands in row (ro, o*) and is
         //     ADDED to whatever side (1) put there (mutual arg-max pairs)
         if (cur.cw != 0.f) {
+          const int tsrc_j = t0 + j;                     // cur.cw != 0 implies tsrc_j < src_tokens
+          const int rs_j = tsrc_j / Ns, sidx_j = tsrc_j - rs_j * Ns;
           auto put = [&](int r2, int ostar, float gval) {
             const int mm = r2 * No + ostar - row0;
             if (mm >= 0 && mm < B2_BM) {
               __nv_bfloat16* e =
                   reinterpret_cast<__nv_bfloat16*>(sa + mm * 128 + (((j >> 3) ^ (mm & 7)) << 4) + (j & 7) * 2);
-              *e = __float2bfloat16_rn(__bfloat162float(*e) + gval * cur.cw);
+              if (J.part == 0) {
+                *e = __float2bfloat16_rn(__bfloat162float(*e) + gval * cur.cw);
+              } else {
+                // exact coefficient: the out-token-side contribution of this element (a mutual arg-max pair) is
+                // recomputed in fp32 instead of being read back rounded, then the hi or lo part overwrites it
+                const int go = r2 * No + ostar;
+                const bool mutual = (int)J.starO[(int64_t)r2 * J.aO_o + (int64_t)rs_j * J.aO_s + ostar] == sidx_j;
+                const float c1 = mutual ? gval * (S.wO[go] * J.scale) : 0.f;
+                *e = coef_part(c1 + gval * cur.cw, J.part);
+              }
             }
           };
 #pragma unroll
@@ -408,6 +426,8 @@ extern "C" int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int njobs, int64_t
       Ro = (int)Ry; No = (int)Ny; J.Rs = (int)Rx; J.Ns = (int)Nx;
     }
     J.dH = jb.dH; J.scale = jb.dh_scale;
+    NR_CHECK_ARG(jb.part == 0 || jb.part == 2 || jb.part == 3, "nr_maxsim2_bwd: job %d: part must be 0, 2 or 3", i);
+    J.part = jb.part;
     J.src_tokens = J.Rs * J.Ns;
     J.num_kb = (J.src_tokens + B2_BK - 1) / B2_BK;
     if (int e = make_tmap_srcT(&a.tms[i], jb.srcT, d, J.src_tokens, jb.src_ld, a.half_cols)) return e;

@@ -30,15 +30,14 @@ using namespace tc;
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t d, int box_rows);
 
-constexpr int T2_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
-constexpr int T2_EPI = T2_THREADS - 64;
+// threads: TMA warp, MMA warp, then two epilogue sets of HS x 4 warps (HS = 1: 320 threads, HS = 2: 576 threads)
+__host__ __device__ constexpr int t2_threads(int hs) { return 64 + 2 * 128 * hs; }
 constexpr int T2_BM = 128;
 constexpr int T2_BK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int T2_MAX_STAGES = 4;
 constexpr int T2_A_BYTES = T2_BM * 128;    // 16 KB
 constexpr int T2_ACC_COLS = 256;           // TMEM columns per accumulator stage
 constexpr int T2_MAX_PROB = 4;
-constexpr int T2_SET = 128;                // threads of one epilogue set
 constexpr int T2_RING = 4;                 // depth of the tile-index ring between the scheduler and its consumers
 
 struct Tc2Prob {
@@ -80,17 +79,22 @@ __device__ __forceinline__ uint32_t group_colmax(uint32_t* k, int lane) {
   return k[0];
 }
 
-__device__ __forceinline__ void set_barrier(int set) {      // named barrier 1 / 2: the 128 threads of one epilogue set
-  if (set == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-  else asm volatile("bar.sync 2, 128;" ::: "memory");
+template <int N>
+__device__ __forceinline__ void set_barrier(int set) {      // named barrier 1 / 2: the N threads of one epilogue set
+  if (set == 0) asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
+  else asm volatile("bar.sync 2, %0;" ::"n"(N) : "memory");
 }
 
 // CL2 (opt-in, see nr_maxsim2_fwd): CTA pairs (clusters of 2).  The two CTAs of a pair work on the SAME Y box and
 // adjacent X boxes; each loads half of the Y box and multicasts it to both, which halves the L2 reads of the dominant
 // operand.  The leader CTA claims pair-tiles and publishes them into both rings; smem stages are released by both
 // MMA issuers.
-template <int NY, int GL, bool CL2>
-__global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __grid_constant__ Tc2Args a) {
+// HS = 2: each epilogue set has 8 warps; the two warps that share a TMEM lane quarter split the accumulator
+// columns of the tile (chunks [0, n/2) and [n/2, n)), which doubles the warps available to hide the latency of the
+// shuffle / shared-memory / global-store chains of the reduction (ncu: 0.6 eligible warps per scheduler with HS = 1).
+template <int NY, int GL, bool CL2, int HS>
+__global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const __grid_constant__ Tc2Args a) {
+  constexpr int T2_SET = 128 * HS;         // threads of one epilogue set
   constexpr int CH = t2_lcm(NY, GL);       // accumulator columns per epilogue chunk: whole samples, whole groups
   constexpr int SPC = CH / NY;             // Y samples per chunk
   constexpr uint32_t LOWM = GL - 1;
@@ -256,10 +260,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
     // ===================== epilogue: two ping-pong sets (warps 2..5 = set 0, 6..9 = set 1) =====================
     // Set s owns TMEM accumulator stage s, i.e. every other tile of this CTA, with its own staging buffers: while
     // one set is in the latency-bound tail of a tile (group combine, output), the other drains the next accumulator.
-    const int set = (warp - 2) >> 2;
+    const int set = (warp - 2) / (4 * HS);
+    const int half = ((warp - 2) >> 2) & (HS - 1);       // which part of the tile's columns this warp reduces
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                         // accumulator row = X token of the tile
-    const int et = (threadIdx.x - 64) & (T2_SET - 1);    // 0..127 within the set
+    const int et = (int)threadIdx.x - 64 - set * T2_SET; // 0..T2_SET-1 within the set
     const int Nx = a.Nx;
     const int sx = r / Nx, x = r - sx * Nx;
     const uint32_t low = LOWM - ((uint32_t)lane & LOWM);
@@ -318,26 +323,28 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
           kg_row[ch * CH + g * GL] = group_colmax<GL>(k, lane);
         }
       };
-      if constexpr (CH <= 32) {
+      const int ch_per = (n_ch + HS - 1) / HS;
+      const int ch_lo = half * ch_per, ch_hi = min(n_ch, ch_lo + ch_per);
+      if constexpr (CH <= 32 && HS == 1) {
         // two register buffers: the TMEM load of the next chunk is in flight while this one is reduced
         uint32_t va[CH], vb[CH];
-        int ch = 0;
-        if (ch < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)(ch * CH), va);
-        for (; ch < n_ch; ch += 2) {
+        int ch = ch_lo;
+        if (ch < ch_hi) tmem_ld_cols<CH>(taddr + (uint32_t)(ch * CH), va);
+        for (; ch < ch_hi; ch += 2) {
           tmem_ld_wait();
           reg_fence<CH>(va);
           const int ch2 = ch + 1;
-          if (ch2 < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)(ch2 * CH), vb);
+          if (ch2 < ch_hi) tmem_ld_cols<CH>(taddr + (uint32_t)(ch2 * CH), vb);
           process(va, ch);
-          if (ch2 < n_ch) {
+          if (ch2 < ch_hi) {
             tmem_ld_wait();
             reg_fence<CH>(vb);
-            if (ch + 2 < n_ch) tmem_ld_cols<CH>(taddr + (uint32_t)((ch + 2) * CH), va);
+            if (ch + 2 < ch_hi) tmem_ld_cols<CH>(taddr + (uint32_t)((ch + 2) * CH), va);
             process(vb, ch2);
           }
         }
       } else {
-        for (int ch = 0; ch < n_ch; ++ch) {
+        for (int ch = ch_lo; ch < ch_hi; ++ch) {
           uint32_t v[CH];
           tmem_ld_cols<CH>(taddr + (uint32_t)(ch * CH), v);
           tmem_ld_wait();
@@ -347,7 +354,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
       }
       tc_fence_before();
       mbar_arrive(tempty + set);                         // TMEM stage may be overwritten
-      set_barrier(set);
+      set_barrier<T2_SET>(set);
       // F1: combine the Nx/GL group partials of each (X sample, column): value, arg-max row, weighted value
       {
         const int ng = Nx / GL;
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
           cws[s * a.UN + c] = wys[c] * val;
         }
       }
-      set_barrier(set);
+      set_barrier<T2_SET>(set);
       // F2: S[rx, ry] = alpha * (sum over the Nx rows of hp + sum over the NY columns of colw)
       for (int e = et; e < sx_n * sy_n; e += T2_SET) {
         const int s = e / sy_n, sy = e - s * sy_n;
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
         P.out[(int64_t)rxx * P.out_sr + (int64_t)ry * P.out_sc] = h;
         if (P.out2) P.out2[(int64_t)rxx * P.out2_sr + (int64_t)ry * P.out2_sc] = h;
       }
-      set_barrier(set);       // the set's staging buffers (hp, keyG, colw, wys) are free for its next tile
+      set_barrier<T2_SET>(set);       // the set's staging buffers (hp, keyG, colw, wys) are free for its next tile
     }
   }
   tc_fence_before();
@@ -400,14 +407,21 @@ __global__ void __launch_bounds__(T2_THREADS, 1) maxsim2_fwd_tc_kernel(const __g
 }
 
 template <int NY, int GL>
-static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, cudaStream_t stream) {
+static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, int halves, cudaStream_t stream) {
+  if (halves == 2 && !pair) {
+    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    maxsim2_fwd_tc_kernel<NY, GL, false, 2><<<grid, t2_threads(2), smem, stream>>>(a);
+    NR_CHECK_LAUNCH("nr_maxsim2_fwd");
+    return 0;
+  }
   if (pair) {
     // CTA pairs: thread-block clusters of 2 (same TPC), multicast of the shared Y box
-    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(T2_THREADS);
+    cfg.blockDim = dim3(t2_threads(1));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -415,27 +429,27 @@ static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, cudaStrea
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NR_CUDA(cudaLaunchKernelEx(&cfg, maxsim2_fwd_tc_kernel<NY, GL, true>, a));
+    NR_CUDA(cudaLaunchKernelEx(&cfg, maxsim2_fwd_tc_kernel<NY, GL, true, 1>, a));
     return 0;
   }
-  NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  maxsim2_fwd_tc_kernel<NY, GL, false><<<grid, T2_THREADS, smem, stream>>>(a);
+  maxsim2_fwd_tc_kernel<NY, GL, false, 1><<<grid, t2_threads(1), smem, stream>>>(a);
   NR_CHECK_LAUNCH("nr_maxsim2_fwd");
   return 0;
 }
 
 template <int GL>
-static int dispatch_ny(int Ny, const Tc2Args& a, size_t smem, int grid, bool pair, cudaStream_t stream) {
+static int dispatch_ny(int Ny, const Tc2Args& a, size_t smem, int grid, bool pair, int halves, cudaStream_t stream) {
   switch (Ny) {
-    case 4: return launch2<4, GL>(a, smem, grid, pair, stream);
-    case 8: return launch2<8, GL>(a, smem, grid, pair, stream);
-    case 12: return launch2<12, GL>(a, smem, grid, pair, stream);
-    case 16: return launch2<16, GL>(a, smem, grid, pair, stream);
-    case 24: return launch2<24, GL>(a, smem, grid, pair, stream);
-    case 32: return launch2<32, GL>(a, smem, grid, pair, stream);
-    case 48: return launch2<48, GL>(a, smem, grid, pair, stream);
-    case 64: return launch2<64, GL>(a, smem, grid, pair, stream);
+    case 4: return launch2<4, GL>(a, smem, grid, pair, halves, stream);
+    case 8: return launch2<8, GL>(a, smem, grid, pair, halves, stream);
+    case 12: return launch2<12, GL>(a, smem, grid, pair, halves, stream);
+    case 16: return launch2<16, GL>(a, smem, grid, pair, halves, stream);
+    case 24: return launch2<24, GL>(a, smem, grid, pair, halves, stream);
+    case 32: return launch2<32, GL>(a, smem, grid, pair, halves, stream);
+    case 48: return launch2<48, GL>(a, smem, grid, pair, halves, stream);
+    case 64: return launch2<64, GL>(a, smem, grid, pair, halves, stream);
     default:
       nr::set_error("nr_maxsim2_fwd: Ny=%d has no tensor-core instantiation (4,8,12,16,24,32,48,64)", Ny);
       return -3;
@@ -526,6 +540,9 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
   const size_t smem = (size_t)stages * (T2_A_BYTES + a.b_bytes) + tail + 1024;
   int grid = tiles < sms ? tiles : sms;
   if (pair) grid = 2 * (tiles < sms / 2 ? tiles : sms / 2);
-  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, pair, (cudaStream_t)stream);
-  return dispatch_ny<4>((int)Ny, a, smem, grid, pair, (cudaStream_t)stream);
+  // epilogue warps per set: 8 (two column halves per TMEM lane quarter) unless NR_TC2_HALVES=1
+  int halves = 2;
+  if (const char* hv = getenv("NR_TC2_HALVES")) halves = atoi(hv) == 1 ? 1 : 2;
+  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, pair, halves, (cudaStream_t)stream);
+  return dispatch_ny<4>((int)Ny, a, smem, grid, pair, halves, (cudaStream_t)stream);
 }

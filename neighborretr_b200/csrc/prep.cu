@@ -19,7 +19,7 @@ constexpr int PREP_MAX_BLOCKS = 296;  // 2 CTAs per SM
 __global__ void __launch_bounds__(PREP_WARPS * 32)
 prep_tokens_kernel(const float* __restrict__ x, int rows, int d, float* __restrict__ xn_f32,
                    __nv_bfloat16* __restrict__ xn_bf16, float* __restrict__ inv_norm,
-                   float* __restrict__ partials, const int64_t* __restrict__ mask) {
+                   float* __restrict__ partials, const int64_t* __restrict__ mask, int split) {
   __shared__ float colsm[PREP_WARPS][128 * PREP_MAXQ];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 acc[PREP_MAXQ];
@@ -49,12 +49,28 @@ prep_tokens_kernel(const float* __restrict__ x, int rows, int d, float* __restri
       if (c < d) {
         float4 n = make_float4(v[q].x / denom, v[q].y / denom, v[q].z / denom, v[q].w / denom);
         if (xn_f32) *reinterpret_cast<float4*>(xn_f32 + (int64_t)row * d + c) = n;
-        if (xn_bf16) {
+        if (xn_bf16 && !split) {
           __nv_bfloat162 lo = __floats2bfloat162_rn(n.x, n.y), hi = __floats2bfloat162_rn(n.z, n.w);
           uint2 pk;
           pk.x = live ? *reinterpret_cast<uint32_t*>(&lo) : 0u;
           pk.y = live ? *reinterpret_cast<uint32_t*>(&hi) : 0u;
           *reinterpret_cast<uint2*>(xn_bf16 + (int64_t)row * d + c) = pk;
+        } else if (xn_bf16) {
+          // split operand [rows, 3d]: n = hi + lo (+ 2^-17 |n|), hi = bf16(n), lo = bf16(n - hi).
+          // role 1 (X side): [hi | lo | hi], role 2 (Y side): [hi | hi | lo], so that the K = 3d contraction of an
+          // X-role row with a Y-role row is  hi.hi + lo.hi + hi.lo  (the lo.lo term, ~2^-18, is dropped)
+          const float f[4] = {n.x, n.y, n.z, n.w};
+          __nv_bfloat16 h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h[e] = __float2bfloat16_rn(live ? f[e] : 0.f);
+            l[e] = __float2bfloat16_rn(live ? f[e] - __bfloat162float(h[e]) : 0.f);
+          }
+          __nv_bfloat16* o = xn_bf16 + (int64_t)row * 3 * d + c;
+          const uint2 ph = *reinterpret_cast<uint2*>(h), pl = *reinterpret_cast<uint2*>(l);
+          *reinterpret_cast<uint2*>(o) = ph;
+          *reinterpret_cast<uint2*>(o + d) = (split == 1) ? pl : ph;
+          *reinterpret_cast<uint2*>(o + 2 * d) = (split == 1) ? ph : pl;
         }
         acc[q].x += n.x; acc[q].y += n.y; acc[q].z += n.z; acc[q].w += n.w;
       }
@@ -251,8 +267,20 @@ extern "C" int nr_prep_tokens(const float* x, int64_t rows, int64_t d, float* xn
                (long long)d, 128 * PREP_MAXQ);
   int grid = (int)nr_prep_partials(rows);
   prep_tokens_kernel<<<grid, PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      x, (int)rows, (int)d, xn_f32, (__nv_bfloat16*)xn_bf16, inv_norm, colsum_partials, mask);
+      x, (int)rows, (int)d, xn_f32, (__nv_bfloat16*)xn_bf16, inv_norm, colsum_partials, mask, 0);
   NR_CHECK_LAUNCH("nr_prep_tokens");
+  return 0;
+}
+
+extern "C" int nr_prep_tokens_split(const float* x, int64_t rows, int64_t d, float* xn_f32, void* xs_bf16, int role,
+                                    float* inv_norm, float* colsum_partials, const int64_t* mask, void* stream) {
+  NR_CHECK_ARG(x && xs_bf16 && rows > 0 && (role == 1 || role == 2), "nr_prep_tokens_split: bad arguments (role 1 = X, 2 = Y)");
+  NR_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 128 * PREP_MAXQ, "nr_prep_tokens_split: d=%lld must be a multiple of 4, <= %d",
+               (long long)d, 128 * PREP_MAXQ);
+  int grid = (int)nr_prep_partials(rows);
+  prep_tokens_kernel<<<grid, PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      x, (int)rows, (int)d, xn_f32, (__nv_bfloat16*)xs_bf16, inv_norm, colsum_partials, mask, role);
+  NR_CHECK_LAUNCH("nr_prep_tokens_split");
   return 0;
 }
 

@@ -20,7 +20,8 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from ._lib import (NR_LOSS_CENTRALITY, NR_LOSS_KL, NR_LOSS_NEIGHBOR, NR_LOSS_UNIFORM, NR_NSAVE, NR_PREC_BF16)
+from ._lib import (NR_LOSS_CENTRALITY, NR_LOSS_KL, NR_LOSS_NEIGHBOR, NR_LOSS_UNIFORM, NR_NSAVE, NR_PREC_BF16,
+                   NR_PREC_BF16X3)
 from .ops import Prepared, _call, _f32c, _mask, _p, _req_cuda, _stream
 
 ALL_LOSSES = NR_LOSS_CENTRALITY | NR_LOSS_NEIGHBOR | NR_LOSS_KL | NR_LOSS_UNIFORM
@@ -61,14 +62,18 @@ class HeadPrologue:
         self.hp = hp
         self.tm, self.vm = _mask(text_mask), _mask(video_mask)
         self.mtm, self.mvm = _mask(mb_mask_t), _mask(mb_mask_v)
-        self.bf = bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
+        self.bf = bf = prec in ops.TC_PRECISIONS or bprec in ops.TC_PRECISIONS
+        x3 = prec == NR_PREC_BF16X3
         # bf16: masks are folded into the operand copies (masked tokens = zero rows) for the two-direction kernel
-        self.fusedk = fk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
-                            and ops.maxsim2_supported(text.shape[1], video.shape[1], text.shape[2]))
-        self.T = Prepared(text.detach(), bf16=bf, colsum=True, mask=self.tm if fk else None, defer=True)
-        self.V = Prepared(video.detach(), bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True)
-        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk)
-        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk)
+        self.fusedk = fk = (prec in ops.TC_PRECISIONS and bprec == prec and ops.USE_FUSED_MAXSIM
+                            and ops.maxsim2_supported(text.shape[1], video.shape[1], text.shape[2] * (3 if x3 else 1)))
+        if x3 and not fk:
+            raise RuntimeError("precision 'bf16x3' needs the fused two-direction kernel for these token counts")
+        rx, ry = (ops.ROLE_X, ops.ROLE_Y) if x3 else (0, 0)      # the text side is X, the video side Y (HeadFunction)
+        self.T = Prepared(text.detach(), bf16=bf, colsum=True, mask=self.tm if fk else None, defer=True, split=rx)
+        self.V = Prepared(video.detach(), bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True, split=ry)
+        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk, split=rx)
+        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk, split=ry)
         B, M, d = self.T.r, self.MT.r, self.T.d
         if self.V.r != B or self.MV.r != M:
             raise RuntimeError("text/video batch sizes (or bank sizes) differ")
@@ -360,6 +365,7 @@ def fused_head(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, text_mask
 
 def head_hparams(centrality_scale, beta, num_neighbors, temperature, uniform_weight, neighbor_weight, kl_weight,
                  precision="bf16", bwd_precision=None, iters=50):
+    prec = ops.PRECISIONS[precision]
+    bprec = prec if prec == NR_PREC_BF16X3 else ops.PRECISIONS[bwd_precision or precision]
     return (float(centrality_scale), float(beta), int(num_neighbors), float(temperature), int(iters),
-            float(uniform_weight), float(neighbor_weight), float(kl_weight), ops.PRECISIONS[precision],
-            ops.PRECISIONS[bwd_precision or precision])
+            float(uniform_weight), float(neighbor_weight), float(kl_weight), prec, bprec)

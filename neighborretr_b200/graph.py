@@ -9,7 +9,12 @@ what turns GPU time into steps/s.
 
 Inputs may live in (pinned) host memory: they are copied into the static device buffers on the replay stream.
 The memory bank is advanced IN PLACE inside the graph (cat(new, old)[:capacity], reference modeling.py:235-249),
-so `model.mb_*` keep their storage across replays.  Single-GPU only (world_size == 1).
+so `model.mb_*` keep their storage across replays.
+
+world_size > 1: the body is the row-block sharded head (sharded.py); its NCCL collectives (gathers, the [b,b]
+all-to-all, loss / gradient reductions) are captured in the same graph, so every rank must construct and replay
+its GraphedHeadStep in lockstep.  Parity of the replayed step against the single-process full-batch head:
+selfcheck.py (bench.py --check, tests/dist_graph_check.py).
 """
 from __future__ import annotations
 
@@ -21,11 +26,22 @@ FIELDS = ("text_feat", "video_feat", "text_mask", "video_mask", "idx", "global_t
 GRAD_FIELDS = ("text_feat", "video_feat", "global_text", "global_video")
 
 
+def head_params(model):
+    """The parameters the head itself differentiates: the two token-weight MLPs and logit_scale."""
+    return list(model.text_weight_fc.parameters()) + list(model.video_weight_fc.parameters()) + [model.clip.logit_scale]
+
+
 class GraphedHeadStep:
-    def __init__(self, model, example, warmup=3):
+    def __init__(self, model, example, warmup=3, explicit_grads=False):
+        """explicit_grads: capture torch.autograd.grad(...) instead of .backward(): the gradients of the four
+        differentiable inputs and of head_params(model) are kept as static tensors (`grad_list`) and no .grad
+        attribute is touched — what the trainer-compatible wrapper (GraphedHead) hands back to autograd."""
         self.world = getattr(model.config, "world_size", 1)
+        if self.world > 1 and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = 1
         self.model = model
-        dev = next(model.parameters()).device
+        self.explicit = bool(explicit_grads)
+        dev = example[0].device if example[0].is_cuda else next(model.parameters()).device
         self.static = {}
         for f, t in zip(FIELDS, example):
             s = t.detach().to(dev).clone()
@@ -36,7 +52,8 @@ class GraphedHeadStep:
         for n in self.bank_names:                       # own the bank storage
             setattr(model, n, getattr(model, n).detach().to(dev).clone())
         bank0 = {n: getattr(model, n).clone() for n in self.bank_names}
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.params = head_params(model) if self.explicit else [p for p in model.parameters() if p.requires_grad]
+        self.grad_list = None
         self._e0 = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.0], device=dev)
         self._fifo_stream = torch.cuda.Stream(device=dev)
         self._stage = None
@@ -57,9 +74,21 @@ class GraphedHeadStep:
         self.launches_per_replay = ops.LAUNCHES["count"] - n0
         for n in self.bank_names:                       # warm-up steps advanced the bank: restore it in place
             getattr(model, n).copy_(bank0[n])
-        self.grads = {f: self.static[f].grad for f in GRAD_FIELDS}
+        if self.explicit:
+            self.grads = dict(zip(GRAD_FIELDS, self.grad_list[:len(GRAD_FIELDS)]))
+        else:
+            self.grads = {f: self.static[f].grad for f in GRAD_FIELDS}
+
+    def set_bank(self, bank):
+        """Overwrite the memory bank IN PLACE (the captured graph holds the storage): `bank` has mb_ind, mb_feat_t,
+        mb_feat_v, mb_mask_t, mb_mask_v (any device)."""
+        with torch.no_grad():
+            for n in self.bank_names:
+                getattr(self.model, n).copy_(getattr(bank, n))
 
     def _zero_grads(self):
+        if self.explicit:                 # torch.autograd.grad never touches a .grad attribute
+            return
         for t in list(self.static.values()) + self.params:
             t.grad = None
 
@@ -87,12 +116,20 @@ class GraphedHeadStep:
             with torch.cuda.stream(self._fifo_stream):
                 self._fifo(new_rows)
         out5 = getattr(m, "last_out5", None) if self.world == 1 else None
-        if out5 is not None and out5.requires_grad:
+        if out5 is not None and not out5.requires_grad:
+            out5 = None
+        if self.explicit:
+            leaves = [s[f] for f in GRAD_FIELDS] + self.params
+            if out5 is not None:
+                self.grad_list = torch.autograd.grad(out5, leaves, grad_outputs=self._e0, allow_unused=True)
+            else:
+                self.grad_list = torch.autograd.grad(losses[0], leaves, allow_unused=True)
+            m.last_out5 = None
+        elif out5 is not None:
             # d total / d out5 = e0: skips the unbind/stack bookkeeping kernels of losses[0].backward()
             out5.backward(gradient=self._e0)
             m.last_out5 = None
         else:
-            out5 = None
             losses[0].backward()
         if early_fifo:
             main.wait_stream(self._fifo_stream)
@@ -153,3 +190,90 @@ class GraphedHeadStep:
             torch.cuda.current_stream().synchronize()
             return sync_losses_to
         return self.losses
+
+
+# ---- trainer-compatible wrapper: model(...) returns losses whose .backward() hands out the captured gradients ----
+class _ReplayFunction(torch.autograd.Function):
+    """forward: copy the batch into the static buffers and replay the captured forward + backward + bank FIFO;
+    backward: d total * (the gradients the replay already produced).  Only `total` carries a gradient — the four
+    component losses are returned detached (the reference's trainer only logs them, training/trainer.py:84-125)."""
+
+    @staticmethod
+    def forward(ctx, runner, text_mask, video_mask, idx, text, video, gt, gv, *params):
+        step = runner.step
+        with torch.no_grad():
+            for f, t in zip(FIELDS, (text, video, text_mask, video_mask, idx, gt, gv)):
+                step.static[f].data.copy_(t.reshape(step.static[f].shape), non_blocking=True)
+        step.graph.replay()
+        ops.LAUNCHES["count"] += step.launches_per_replay
+        ctx.runner = runner
+        ctx.token = runner.replays = runner.replays + 1
+        ctx.meta = [(t.dtype, t.shape) for t in (text, video, gt, gv)]
+        return step.losses.clone()
+
+    @staticmethod
+    def backward(ctx, g5):
+        r = ctx.runner
+        if ctx.token != r.replays:
+            raise RuntimeError("GraphedHead: backward() of a step whose static gradients were overwritten by a later "
+                               "forward; call loss.backward() before the next model(...) (or set head_graph=False)")
+        s = g5[0]
+        out = []
+        for g, (dt, shp) in zip(r.step.grad_list[:4], ctx.meta):
+            out.append(None if g is None else (s * g).to(dt).reshape(shp))
+        for g in r.step.grad_list[4:]:
+            out.append(None if g is None else s * g)
+        return (None, None, None, None, *out)
+
+
+class GraphedHead:
+    """Per-model cache of captured head steps keyed by the batch / bank shapes (HeadMixin.head_forward uses it when
+    `head_graph` is on).  The bank lives in static storage owned by the captured graph: tensors assigned to
+    `model.mb_*` from outside (MemoryBankManager.load_memory_bank, reference utils/memory_bank.py:206-211) are
+    detected by identity, copied into the static storage and re-pointed at it."""
+    MAX_SHAPES = 4
+
+    def __init__(self, model):
+        self.runners = {}
+        self.model = model
+
+    def _key(self, text, video, gt, gv, tm, vm):
+        m = self.model
+        return (tuple(text.shape), tuple(video.shape), tuple(gt.shape), tuple(gv.shape), tuple(tm.shape), tuple(vm.shape),
+                tuple(m.mb_feat_t.shape), tuple(m.mb_feat_v.shape), m.mb_feat_t.dtype, m.mb_mask_t.dtype,
+                m.mb_ind.dtype, getattr(m.config, "world_size", 1), m._head_precision(), m._head_bwd_precision(),
+                m._mlp_precision(), text.device.index)
+
+    def __call__(self, text, video, tm, vm, idx, gt, gv):
+        m = self.model
+        key = self._key(text, video, gt, gv, tm, vm)
+        r = self.runners.get(key)
+        if r is None:
+            if len(self.runners) >= self.MAX_SHAPES:
+                return None                                   # too many distinct shapes: the caller runs eagerly
+            r = self.runners[key] = _Runner(m, (text, video, tm, vm, idx, gt, gv))
+        r.sync_bank(m)
+        out5 = _ReplayFunction.apply(r, tm, vm, idx, text, video, gt, gv, *r.step.params)
+        m.last_neighbors = r.neighbors
+        total = out5[0]
+        c, u, n, k = out5.detach()[1:].unbind(0)
+        return total, c, u, n, k
+
+
+class _Runner:
+    def __init__(self, model, example):
+        bank_in = {n: getattr(model, n) for n in ("mb_ind", "mb_feat_t", "mb_feat_v", "mb_mask_t", "mb_mask_v")}
+        self.step = GraphedHeadStep(model, [t.detach() for t in example], explicit_grads=True)
+        self.neighbors = getattr(model, "last_neighbors", None)
+        self.bank = {n: getattr(model, n) for n in self.step.bank_names}     # the static storage
+        self.replays = 0
+        del bank_in
+
+    def sync_bank(self, model):
+        """Static bank storage <- whatever was assigned to model.mb_* since the last step (identity check)."""
+        for n, st in self.bank.items():
+            cur = getattr(model, n)
+            if cur is not st:
+                with torch.no_grad():
+                    st.copy_(cur)
+                setattr(model, n, st)

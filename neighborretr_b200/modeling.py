@@ -28,6 +28,9 @@ allgather = AllGather.apply
 allgather2 = AllGather2.apply
 
 DEFAULT_PRECISION = os.environ.get("NR_HEAD_PRECISION", "bf16")
+# what install() puts on the reference class: the reference head is fp32 (modeling.py:548,564-565), so the drop-in
+# defaults to the fp32-accurate tensor-core mode; plain bf16 (1e-2 loss tolerance) is an explicit opt-in
+INSTALL_PRECISION = os.environ.get("NR_INSTALL_PRECISION", "bf16x3")
 
 
 def _token_weights(mlp, feat, mask, lowp=False):
@@ -48,14 +51,17 @@ class HeadMixin:
     def _mlp_precision(self):
         """GEMM arithmetic of the token-weight MLPs: "fp32" in the exact mode; in the bf16 head mode "bf16"
         (default) or "tf32" (`head_mlp_precision`)."""
-        if self._head_precision() != "bf16":
+        hp = self._head_precision()
+        if hp not in ("bf16", "bf16x3"):
             return "fp32"
         cfg = getattr(self, "config", None)
         return (getattr(self, "head_mlp_precision", None) or getattr(cfg, "head_mlp_precision", None)
-                or os.environ.get("NR_HEAD_MLP_PRECISION", "bf16"))
+                or os.environ.get("NR_HEAD_MLP_PRECISION", "bf16" if hp == "bf16" else "tf32"))
 
     def _head_bwd_precision(self):
         cfg = getattr(self, "config", None)
+        if self._head_precision() == "bf16x3":
+            return "bf16x3"
         return (getattr(self, "head_bwd_precision", None) or getattr(cfg, "head_bwd_precision", None)
                 or self._head_precision())
 
@@ -222,9 +228,11 @@ class HeadMixin:
             self.mb_batch = idx.size(0)
             return
         cap = self.mb_feat_v.size(0)
-        self.mb_ind = ops.fifo_update(idx, self.mb_ind, cap)
-        self.mb_feat_v = ops.fifo_update(video_feat.detach(), self.mb_feat_v, cap)
-        self.mb_feat_t = ops.fifo_update(text_feat.detach(), self.mb_feat_t, cap)
+        # new rows take the bank's dtype (the reference's torch.cat promotes; an encoder under autocast may hand
+        # fp16/bf16 rows to an fp32 bank, or the other way round)
+        self.mb_ind = ops.fifo_update(idx.to(self.mb_ind.dtype), self.mb_ind, cap)
+        self.mb_feat_v = ops.fifo_update(video_feat.detach().to(self.mb_feat_v.dtype), self.mb_feat_v, cap)
+        self.mb_feat_t = ops.fifo_update(text_feat.detach().to(self.mb_feat_t.dtype), self.mb_feat_t, cap)
         self.mb_mask_t = ops.fifo_update(text_mask.to(self.mb_mask_t.dtype), self.mb_mask_t, cap)
         self.mb_mask_v = ops.fifo_update(video_mask.to(self.mb_mask_v.dtype), self.mb_mask_v, cap)
 
@@ -282,8 +290,38 @@ class HeadMixin:
             torch.cuda.current_stream().wait_event(ev)
             self._text_ready = None
 
+    def _graph_enabled(self):
+        cfg = getattr(self, "config", None)
+        v = getattr(self, "head_graph", None)
+        if v is None:
+            v = getattr(cfg, "head_graph", None)
+        if v is None:
+            v = os.environ.get("NR_HEAD_GRAPH", "0") not in ("0", "", "false")
+        return bool(v)
+
     def head_forward(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats=None):
+        """Everything of the reference's forward() below the encoders (modeling.py:269-312): gathers, the five losses,
+        the bank FIFO.  With `head_graph` on (install() turns it on) the whole step — forward, backward and FIFO —
+        is ONE CUDA-graph replay per call (graph.GraphedHead); `.backward()` on the returned total loss hands the
+        already computed gradients to autograd, so the reference's trainer loop runs unchanged."""
         cfg = self.config
+        if (self._graph_enabled() and text_feat.is_cuda and torch.is_grad_enabled() and self.mb_feat_v.dim() == 3
+                and self.mb_feat_v.shape[0] > 0 and not torch.cuda.is_current_stream_capturing()):
+            if global_feats is None:
+                global_feats = self.merge_global_features(text_feat, video_feat, text_mask, video_mask)
+            gtf, gvf = global_feats
+            W = getattr(cfg, "world_size", 1)
+            if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+                W = 1
+            if gtf.shape[1] == 1 and gvf.shape[1] == 1 and text_feat.shape[0] * W >= cfg.num_neighbors + 2:
+                gh = self.__dict__.get("_graphed_head")
+                if gh is None:
+                    from .graph import GraphedHead
+                    gh = GraphedHead(self)
+                    object.__setattr__(self, "_graphed_head", gh)        # not a submodule / parameter
+                out = gh(text_feat, video_feat, text_mask, video_mask, idx, gtf, gvf)
+                if out is not None:
+                    return out
         if (getattr(cfg, "world_size", 1) > 1 and getattr(self, "head_sharded", getattr(cfg, "head_sharded", True))
                 and torch.distributed.is_available() and torch.distributed.is_initialized()):
             if global_feats is None:
@@ -397,3 +435,20 @@ class NeighborRetr(HeadMixin, nn.Module):
         if not self.training:
             return None
         return self.head_forward(text_feat, video_feat, text_mask, video_mask, idx)
+
+
+def installed_forward(self, text_ids, text_mask, video, video_mask=None, idx=None, global_step=0, logger=None):
+    """Replacement for the reference's NeighborRetr.forward (modeling.py:251-312), bound onto the reference class by
+    neighborretr_b200.install(): same arguments, same return (None in eval mode, the 5-tuple of losses in training).
+    The encoders stay the reference's own (`get_text_video_feat`, called with the frames flattened to
+    [b * frames, C, H, W] as the reference does); everything below them is head_forward — per-rank row blocks instead
+    of the reference's five gathers + barrier + replicated head at world_size > 1."""
+    text_ids = text_ids.view(-1, text_ids.shape[-1])
+    text_mask = text_mask.view(-1, text_mask.shape[-1])
+    video_mask = video_mask.view(-1, video_mask.shape[-1])
+    video = torch.as_tensor(video).float()
+    video = video.view(-1, *video.shape[-3:])          # [b, frames, C, H, W] or [b, pair, bs, ts, C, H, W]
+    text_feat, video_feat = self.get_text_video_feat(text_ids, text_mask, video, video_mask, shaped=True)
+    if not self.training:
+        return None
+    return self.head_forward(text_feat, video_feat, text_mask, video_mask, idx)

@@ -11,9 +11,14 @@ import torch
 
 from . import _lib
 from ._lib import (NR_LOSS_CENTRALITY, NR_LOSS_KL, NR_LOSS_NEIGHBOR, NR_LOSS_UNIFORM, NR_NSAVE, NR_PREC_BF16,
-                   NR_PREC_FP32, check)
+                   NR_PREC_BF16X3, NR_PREC_FP32, check)
 
-PRECISIONS = {"fp32": NR_PREC_FP32, "bf16": NR_PREC_BF16}
+# "bf16x3": fp32-accurate tensor-core mode — every normalised token value is split into hi + lo bf16 parts and the
+# contraction runs hi.hi + lo.hi + hi.lo on the same tcgen05 kernels with K = 3d (forward) / three routing jobs per
+# pair (backward); only the fused two-direction kernels implement it
+PRECISIONS = {"fp32": NR_PREC_FP32, "bf16": NR_PREC_BF16, "bf16x3": NR_PREC_BF16X3}
+TC_PRECISIONS = (NR_PREC_BF16, NR_PREC_BF16X3)
+ROLE_X, ROLE_Y = 1, 2
 # kernel launches issued through the C ABI since the last reset (bench.py reports it as gpu_launches)
 LAUNCHES = {"count": 0}
 
@@ -146,11 +151,13 @@ class Prepared:
     copy (tensor-core mode), inverse norms and per-CTA column-sum partials."""
 
     __slots__ = ("xn", "xn_bf16", "xnT_bf16", "inv_norm", "partials", "rows", "n", "d", "r", "_parent", "_lo", "mask",
-                 "_x", "_t_ready", "device")
+                 "_x", "_t_ready", "device", "split")
 
-    def __init__(self, x, bf16=False, colsum=False, normalize=True, mask=None, defer=False, f32=True):
+    def __init__(self, x, bf16=False, colsum=False, normalize=True, mask=None, defer=False, f32=True, split=0):
         """mask [r, n] int64 (optional): masked tokens become zero rows of the bf16 operand copy (and of its
-        transposed copy) and take no max-sim gradient in backward(); required by the fused two-direction kernel."""
+        transposed copy) and take no max-sim gradient in backward(); required by the fused two-direction kernel.
+        split: 0, or ROLE_X / ROLE_Y — the bf16 operand copy is the split-bf16 operand [r, n, 3d] of the bf16x3
+        mode for that side of the fused kernel (nr_prep_tokens_split)."""
         _req_cuda(x)
         x = _f32c(x)
         self.r, self.n, self.d = x.shape
@@ -159,6 +166,7 @@ class Prepared:
         self._parent, self._lo = None, 0
         self._x, self._t_ready = None, True
         self.mask = _mask(mask)
+        self.split = int(split)
         dev = x.device
         self.device = dev
         if not normalize:        # global_level: raw dot products (reference modeling.py:525), fp32 only
@@ -168,7 +176,8 @@ class Prepared:
         # bank: saves 4 of the 6 bytes the preparation writes per element)
         self.xn = torch.empty_like(x) if f32 else None
         self.device = dev
-        self.xn_bf16 = torch.empty(x.shape, dtype=torch.bfloat16, device=dev) if bf16 else None
+        oshape = (self.r, self.n, 3 * self.d) if self.split else x.shape
+        self.xn_bf16 = torch.empty(oshape, dtype=torch.bfloat16, device=dev) if (bf16 or self.split) else None
         self.inv_norm = torch.empty(self.rows, dtype=torch.float32, device=dev)
         npart = _lib.load().nr_prep_partials(self.rows)
         self.partials = torch.empty(npart, self.d, dtype=torch.float32, device=dev) if colsum else None
@@ -178,25 +187,34 @@ class Prepared:
 
     def run(self):
         """Enqueue the preparation kernel on the current stream (buffers were allocated by the constructor)."""
-        _call("nr_prep_tokens", _p(self._x), self.rows, self.d, _p(self.xn), _p(self.xn_bf16), _p(self.inv_norm),
-              _p(self.partials), _p(self.mask), _stream())
+        if self.split:
+            _call("nr_prep_tokens_split", _p(self._x), self.rows, self.d, _p(self.xn), _p(self.xn_bf16), self.split,
+                  _p(self.inv_norm), _p(self.partials), _p(self.mask), _stream())
+        else:
+            _call("nr_prep_tokens", _p(self._x), self.rows, self.d, _p(self.xn), _p(self.xn_bf16), _p(self.inv_norm),
+                  _p(self.partials), _p(self.mask), _stream())
         self._x = None
         return self
+
+    @property
+    def kd(self):
+        """Contraction length of the bf16 operand copy (3d for the split operand)."""
+        return 3 * self.d if self.split else self.d
 
     def alloc_transposed(self):
         """Allocate (not fill) the transposed bf16 copy on the current stream; bwd_source() fills it on first use."""
         if self.xnT_bf16 is None and self.xn_bf16 is not None and self._parent is None:
             ld = (self.rows + 7) // 8 * 8
-            self.xnT_bf16 = torch.empty(self.d, ld, dtype=torch.bfloat16, device=self.xn_bf16.device)
+            self.xnT_bf16 = torch.empty(self.kd, ld, dtype=torch.bfloat16, device=self.xn_bf16.device)
             self._t_ready = False
 
     def operand(self, prec):
-        return self.xn_bf16 if prec == NR_PREC_BF16 else self.xn
+        return self.xn_bf16 if prec in TC_PRECISIONS else self.xn
 
     def bwd_source(self, prec):
         """(pointer tensor, ld) of this modality as the SOURCE operand of a backward contraction: fp32 tokens,
         or the transposed bf16 copy [d, ld] built on first use."""
-        if prec != NR_PREC_BF16:
+        if prec not in TC_PRECISIONS:
             return self.xn, 0
         parent = getattr(self, "_parent", None)
         if parent is not None:          # block view: columns [lo*n, (lo+rows)) of the parent's transposed copy
@@ -207,7 +225,7 @@ class Prepared:
         if self.xnT_bf16 is None:
             self.alloc_transposed()
         if not self._t_ready:
-            _call("nr_transpose_tokens_bf16", _p(self.xn_bf16), self.rows, self.d, _p(self.xnT_bf16),
+            _call("nr_transpose_tokens_bf16", _p(self.xn_bf16), self.rows, self.kd, _p(self.xnT_bf16),
                   self.xnT_bf16.shape[1], _stream())
             self._t_ready = True
         return self.xnT_bf16, self.xnT_bf16.shape[1]
@@ -225,8 +243,17 @@ class Prepared:
         v.xnT_bf16 = None
         v._x, v._t_ready = None, True
         v._parent, v._lo = self, lo
+        v.split = self.split
         v.mask = self.mask[lo:lo + n] if self.mask is not None else None
         return v
+
+    def hi_lo_sources(self):
+        """Split operand only: (hi^T, lo^T, ld) views of the transposed copy [3d, ld] (segments: role X = hi|lo|hi,
+        role Y = hi|hi|lo)."""
+        t, ld = self.bwd_source(NR_PREC_BF16X3)
+        d = self.d
+        lo = t[d:2 * d] if self.split == ROLE_X else t[2 * d:3 * d]
+        return t[:d], lo, ld
 
     def backward(self, dxn, add_vec=None, out=None):
         if self.inv_norm is None:
@@ -272,13 +299,15 @@ def maxsim2_fwd(problems, keep=True):
     Returns per problem (pmax_x, ystar, pmax_y, xstar) (None if not keep)."""
     arr = (_lib.MaxSim2Problem * len(problems))()
     saved = []
-    nx, ny, d = problems[0]["X"].n, problems[0]["Y"].n, problems[0]["X"].d
+    nx, ny, d = problems[0]["X"].n, problems[0]["Y"].n, problems[0]["X"].kd
     for i, q in enumerate(problems):
         X, Y = q["X"], q["Y"]
-        if (X.n, Y.n, X.d, Y.d) != (nx, ny, d, d):
+        if (X.n, Y.n, X.kd, Y.kd) != (nx, ny, d, d):
             raise RuntimeError("maxsim2_fwd: all problems of a launch must share (Nx, Ny, d)")
         if X.xn_bf16 is None or Y.xn_bf16 is None:
             raise RuntimeError("maxsim2_fwd: bf16 operand copies required (Prepared(..., bf16=True, mask=...))")
+        if (X.split, Y.split) not in ((0, 0), (ROLE_X, ROLE_Y)):
+            raise RuntimeError("maxsim2_fwd: split operands must be prepared as (ROLE_X, ROLE_Y)")
         dev = X.device
         if keep:
             sv = (torch.empty(X.r, Y.r, nx, dtype=torch.float32, device=dev),
@@ -307,17 +336,23 @@ def maxsim2_bwd_multi(jobs, nx, ny, d):
     (side, src Prepared, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, ry, dst); side 0: dst = X-token gradient
     (src = the Y tokens), side 1: dst = Y-token gradient (src = the X tokens).  Jobs with the same dst are
     accumulated in one pass."""
-    arr = (_lib.MaxSim2BwdJob * len(jobs))()
-    keep = []
-    for i, (side, src, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, ry, dst) in enumerate(jobs):
-        s, ld = src.bwd_source(NR_PREC_BF16)
-        keep.append(s)
+    flat = []
+    for job in jobs:
+        src = job[1]
+        if src.split:       # bf16x3: (hi tile, hi^T), (lo tile, hi^T), (hi tile, lo^T) on the same destination
+            hiT, loT, ld = src.hi_lo_sources()
+            flat += [(job, hiT, ld, 2), (job, hiT, ld, 3), (job, loT, ld, 2)]
+        else:
+            s, ld = src.bwd_source(NR_PREC_BF16)
+            flat.append((job, s, ld, 0))
+    arr = (_lib.MaxSim2BwdJob * len(flat))()
+    for i, ((side, src, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, ry, dst), s, ld, part) in enumerate(flat):
         a = arr[i]
         a.side, a.srcT, a.src_ld = side, s.data_ptr(), ld
         a.wx, a.wy, a.ystar, a.xstar = wx.data_ptr(), wy.data_ptr(), ystar.data_ptr(), xstar.data_ptr()
         a.dH, a.dh_sr, a.dh_sc, a.dh_scale = g.data_ptr(), g_sr, g_sc, float(scale)
-        a.Rx, a.Ry, a.dst = rx, ry, dst.data_ptr()
-    _call("nr_maxsim2_bwd", ctypes.cast(arr, ctypes.c_void_p), len(jobs), nx, ny, d, _stream())
+        a.Rx, a.Ry, a.dst, a.part = rx, ry, dst.data_ptr(), part
+    _call("nr_maxsim2_bwd", ctypes.cast(arr, ctypes.c_void_p), len(flat), nx, ny, d, _stream())
 
 
 def maxsim2_bwd(side, src, wx, wy, ystar, xstar, g, g_sr, g_sc, scale, rx, nx, ry, ny, d, dst):
@@ -359,16 +394,22 @@ class MaxSimFunction(torch.autograd.Function):
         tm, vm = _mask(text_mask), _mask(video_mask)
         if not normalize:
             prec = bwd_prec = NR_PREC_FP32
+        x3 = prec == NR_PREC_BF16X3
+        if x3:
+            bwd_prec = NR_PREC_BF16X3
         need_bf16 = prec == NR_PREC_BF16 or bwd_prec == NR_PREC_BF16
         keep = any(ctx.needs_input_grad[:4])
         swap = None
-        if prec == NR_PREC_BF16 and bwd_prec == NR_PREC_BF16:
-            swap = _fused_orientation(text_feat.shape[1], video_feat.shape[1], text_feat.shape[2])
+        if prec in TC_PRECISIONS and bwd_prec == prec:
+            swap = _fused_orientation(text_feat.shape[1], video_feat.shape[1], text_feat.shape[2] * (3 if x3 else 1))
+        if x3 and swap is None:
+            raise RuntimeError("precision 'bf16x3' needs the fused two-direction kernel (token counts 4..128 with one "
+                               "side a multiple of 4 and the other in {4,8,12,16,24,32,48,64}, d % 64 == 0)")
         ctx.fused = swap is not None
         if ctx.fused:
             # one launch: both directions from the same accumulator tile, masks folded into the operand copies
-            T = Prepared(text_feat, bf16=True, mask=tm)
-            V = Prepared(video_feat, bf16=True, mask=vm)
+            T = Prepared(text_feat, bf16=True, mask=tm, split=(ROLE_Y if swap else ROLE_X) if x3 else 0)
+            V = Prepared(video_feat, bf16=True, mask=vm, split=(ROLE_X if swap else ROLE_Y) if x3 else 0)
             A, B = T.r, V.r
             S = torch.empty(A, B, dtype=torch.float32, device=T.xn.device)
             ST = torch.empty(B, A, dtype=torch.float32, device=T.xn.device)

@@ -18,7 +18,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from ._lib import NR_NSAVE, NR_PREC_BF16
+from ._lib import NR_NSAVE, NR_PREC_BF16, NR_PREC_BF16X3
 from .fused import ALL_LOSSES, _combine_matrix, _fwd_dir, head_hparams
 from .ops import Prepared, _call, _f32c, _mask, _p, _req_cuda, _stream
 
@@ -121,28 +121,38 @@ class ShardedPrologue:
         self.gl = torch.stack(self.g_l, 1)                                                    # [b,2,d]
         self.gall = torch.empty(B, 2, d, **f32)
         self.g2, self.v2 = torch.empty(B, d, **f32), torch.empty(B, d, **f32)
+        x3 = prec == NR_PREC_BF16X3
+        bf_ = prec in ops.TC_PRECISIONS or bprec in ops.TC_PRECISIONS
+        fk_ = (prec in ops.TC_PRECISIONS and bprec == prec and ops.USE_FUSED_MAXSIM
+               and ops.maxsim2_supported(nt, nv, d * (3 if x3 else 1)))
+        if x3 and not fk_:
+            raise RuntimeError("precision 'bf16x3' needs the fused two-direction kernel for these token counts")
+        rx, ry = (ops.ROLE_X, ops.ROLE_Y) if x3 else (0, 0)
+        if bf_ and not fk_ and ((b * nt) % 8 or (b * nv) % 8):
+            # the one-direction bf16 backward reads row blocks of the transposed operand copies through 16-byte
+            # aligned column offsets; decided from (b, Nt, Nv) alone so that EVERY rank raises before any collective
+            raise RuntimeError(f"sharded head, bf16 one-direction kernels: per-rank batch x tokens must be a multiple "
+                               f"of 8 (b={b}, Nt={nt}, Nv={nv}); use head_bwd_precision='fp32' or an even batch")
         # ---- exchange 0: masks (the operand preparation needs them)
         masks = _gather(torch.cat([_mask(tm_l), _mask(vm_l)], dim=1))                       # [B, Nt+Nv] int64
         self.tm, self.vm = masks[:, :nt].contiguous(), masks[:, nt:].contiguous()
         self.mtm, self.mvm = _mask(mb_mask_t), _mask(mb_mask_v)
-        self.bf = bf = prec == NR_PREC_BF16 or bprec == NR_PREC_BF16
-        self.fusedk = fk = (prec == NR_PREC_BF16 and bprec == NR_PREC_BF16 and ops.USE_FUSED_MAXSIM
-                            and ops.maxsim2_supported(nt, nv, d))
+        self.bf, self.fusedk = bf, fk = bf_, fk_
         # Fused (bf16) path = "exchange" design: a rank contracts only ITS text rows against all videos (P = S[rows_r,
         # :]); the column block the video->text direction needs is assembled from the other ranks' P by an
         # all-to-all of [b,b] blocks.  Other ranks' text tokens are then needed by the bank FIFO only.
         self.a2a = fk
         if fk:
             self.T = None
-            self.Tl = Prepared(self.text_l, bf16=True, colsum=True, mask=self.tm[lo:lo + b], defer=True)
+            self.Tl = Prepared(self.text_l, bf16=True, colsum=True, mask=self.tm[lo:lo + b], defer=True, split=rx)
             self.tsum_l = torch.empty(1, d, **f32)
             self.tsum = torch.empty(W, d, **f32)
         else:
             self.T = Prepared(self.text, bf16=bf, colsum=True, mask=None, defer=True)
             self.Tl = self.T.block(lo, b)
-        self.V = Prepared(self.video, bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True)
-        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk)
-        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk)
+        self.V = Prepared(self.video, bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True, split=ry)
+        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk, split=rx)
+        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk, split=ry)
         self.Vl = self.V.block(lo, b)
         self.t_rows = B * nt
         self.GG = torch.empty(2, B, B, **f32)              # [G ; G^T], replicated
@@ -375,27 +385,9 @@ class ShardedHeadFunction(torch.autograd.Function):
         vs, vld = V.bwd_source(bprec); ts, tld = T.bwd_source(bprec)
         vls, vlld = Vl.bwd_source(bprec); tls, tlld = Tl.bwd_source(bprec)
         mvs, mvld = MV.bwd_source(bprec); mts, mtld = MT.bwd_source(bprec)
-        if ctx.fusedk:
-            sc = 0.5 / M
-            # S_row = S(text_l, video): g = dS_row [b,B];  S_col[v_l, a] = S(text, video_l)[a, v_l]: g(rx=a, ry=v_l) =
-            # dS_col[v_l, a];  bank pairs of this rank's samples: g = dc_l[.]/M broadcast over the bank rows (stride 0).
-            # ONE launch; jobs with the same destination share an accumulator pass.
-            fjw = ops.ForkJoin(1)
-            fjw.__enter__()
-            with fjw.on(0):                          # weight gradients NEXT TO the contraction, not after it
-                ops.maxsim2_bwd_w(p1, p2, dS_row, B, 1, 0.5, b, nt, B, nv, dtw_l, dvw)
-                ops.maxsim2_bwd_w(p3, p4, dS_col, 1, B, 0.5, B, nt, b, nv, dtw, dvw_l)
-                ops.maxsim2_bwd_w(pA, pB, dc_l[0], 1, 0, sc, b, nt, M, nv, dtw_l, dvw_mb)
-                ops.maxsim2_bwd_w(pC, pD, dc_l[1], 0, 1, sc, M, nt, b, nv, dtw_mb, dvw_l)
-            ops.maxsim2_bwd_multi([
-                (0, V, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, B, dtn_l),
-                (0, MV, tw_l, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
-                (1, Tl, tw_l, vw, y1, y2, dS_row, B, 1, 0.5, b, B, dvn),
-                (0, Vl, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, b, dtn),
-                (1, T, tw, vw_l, y3, y4, dS_col, 1, B, 0.5, B, b, dvn_l),
-                (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
-            fjw.__exit__(None, None, None)
-        else:
+        # (the fused two-direction kernels imply the exchange design, which returned above: only the one-direction
+        # kernels are left here)
+        if True:
             X, Y, Wg = "nr_maxsim_bwd_x", "nr_maxsim_bwd_y", "nr_maxsim_bwd_w"
             # H1 = H(text_l, video): dH1[a_l, bb] = .5 dS_row
             _call(X, bprec, _p(vs), vld, _p(tw_l), _p(tm_l), _p(vm), _p(y1), _p(dS_row), B, 1, 0.5, b, nt, B, nv, d, _p(dtn_l), st)

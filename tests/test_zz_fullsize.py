@@ -49,7 +49,8 @@ def _check_head(losses, grads, ref, rgrads, precision, tag):
     # bf16 feature gradients: measured 5.0e-2 at B=1024 and 4.1e-2 at the ActivityNet shape (1.0-1.6e-2 at B=128):
     # the gradient of a max is routed to ONE token, and with more candidates per row more arg-maxima flip under the
     # 2^-9 operand rounding; losses stay within 5e-5
-    ltol, gtol = (1e-4, 1e-3) if precision == "fp32" else (1e-2, 8e-2)
+    # bf16x3 (split-bf16 tensor-core products): north_star's fp32/tf32 bar — losses 1e-4, feature gradients 5e-3
+    ltol, gtol = {"fp32": (1e-4, 1e-3), "bf16x3": (1e-4, 5e-3)}.get(precision, (1e-2, 8e-2))
     lerr = float((losses / ref - 1).abs().max())
     gerr = {k: rel_l2(grads[k], rgrads[k]) for k in ("text", "video", "gt", "gv")}
     print(f"{tag}[{precision}] losses {losses.tolist()} max rel err {lerr:.2e}; grad rel-L2 {gerr}")
@@ -57,15 +58,15 @@ def _check_head(losses, grads, ref, rgrads, precision, tag):
     for k, e in gerr.items():
         assert e < gtol, (k, e)
     ls_err = abs(grads["logit_scale"].item() / rgrads["logit_scale"].item() - 1)
-    assert ls_err < (1e-3 if precision == "fp32" else 3e-2), ls_err
+    assert ls_err < (3e-2 if precision == "bf16" else 1e-3), ls_err
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_cfg2_msrvtt_head_global_batch_1024(precision):
     _check_head(*_head_case(1024, "msrvtt", precision), precision, "cfg2 B=1024")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_cfg3_activitynet_head_b128(precision):
     _check_head(*_head_case(128, "activitynet", precision), precision, "cfg3 ACT b=128")
 
