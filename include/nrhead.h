@@ -70,6 +70,25 @@ int nr_prep_tokens_split(const float* x, int64_t rows, int64_t d, float* xn_f32,
 int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* dxn, const float* add_vec,
                        const int64_t* mask, int64_t rows, int64_t d, float* dx, int accumulate, void* stream);
 
+/* ---- tcgen05 GEMMs of the token-weight MLPs (reference modeling.py:137-153, used :485-492) -------------------------
+ * Linear(D -> H) + ReLU + Linear(H -> 1) per token, then masked softmax over the tokens of a sample.  bf16
+ * operands, fp32 accumulation; operands are consumed AS STORED (K-major or MN-major TMA tiles), no transposes.
+ * nr_cast_bf16: fp32 -> bf16 operand copy (x, W1).
+ * nr_mlp_fwd : h = relu(x W1^T + b1) written as bf16 [T, H] (h_bf16 nullable: evaluation keeps nothing), and
+ *              logits[t] += <h[t,:], w2>  (fp32 h, before the bf16 rounding; logits must be zero on entry).
+ * nr_token_softmax: w = softmax_over_tokens(mask_fill(logits + b2, -9e15)); rows [0,Ra) use mask_a, the rest
+ *              mask_b (batch tokens and bank tokens of one modality share the buffers; masks nullable).
+ * nr_mlp_bwd_dx : dx [T, D] (+)= dh [T, H] W1 [H, D]       (accumulate != 0: split-K with red.add into dx)
+ * nr_mlp_bwd_dw1: dw1 [H, D] += dh^T [H, T] x [T, D]       (split-K over the tokens, red.add: zero dw1 first) */
+int nr_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+int nr_mlp_fwd(const void* x_bf16, int64_t T, int64_t D, const void* w1_bf16, int64_t H, const float* b1,
+               const float* w2, void* h_bf16, float* logits, void* stream);
+int nr_token_softmax(const float* logits, const float* b2, const int64_t* mask_a, const int64_t* mask_b, int64_t Ra,
+                     int64_t R, int64_t N, float* w, void* stream);
+int nr_mlp_bwd_dx(const void* dh_bf16, int64_t T, int64_t H, const void* w1_bf16, int64_t D, float* dx, int accumulate,
+                  void* stream);
+int nr_mlp_bwd_dw1(const void* dh_bf16, int64_t T, int64_t H, const void* x_bf16, int64_t D, float* dw1, void* stream);
+
 /* chunks of 32 token rows: column count of the partial-sum buffer of nr_token_weights_bwd */
 int64_t nr_mlp_chunks(int64_t T);
 

@@ -1,0 +1,428 @@
+// tcgen05 GEMM of the token-weight MLPs (reference NeighborRetr/models/modeling.py:137-153, used :485-492):
+//   forward   h = relu(x W1^T + b1)  [T,1024]   with the second layer's dot product  logits[t] += <h[t,:], w2>
+//             folded into the epilogue (the hidden activations are written once, as bf16, only when a backward
+//             will need them; in evaluation they never leave the SM);
+//   backward  dx  = dh W1            [T,512]    (A = dh K-major, B = W1 as stored: MN-major)
+//             dW1 = dh^T x           [1024,512] (both operands as stored: MN-major; split-K over the tokens)
+// One kernel: C[M,N] (+)= A[M,K] * B[N,K]^T with bf16 operands staged by TMA (128B swizzle) either K-major
+// (rows of 64 k-elements) or MN-major (rows of 64 m/n-elements, one row per k: what a row-major [K, M] array
+// gives without any transposed copy), fp32 accumulation in TMEM.
+//
+// Persistent, warp-specialised, one CTA per SM: warp 0 = TMA producer (4-stage mbarrier ring of 48 KB stages),
+// warp 1 = single-thread tcgen05.mma issuer (M=128 x N=256 x K=16, two 256-column TMEM accumulators so that the
+// next tile's MMAs run under this tile's epilogue), warps 2..9 = epilogue (the two warps of a TMEM lane quarter
+// split the 256 columns).  Work items = (m-tile, n-tile, k-split) in a static round-robin over the grid; split-K
+// partials are combined with red.global.add.f32 into a zero-initialised output.
+// Roofline: tensor pipe; 2*M*N*K flops per problem; operands are read from HBM once (they fit L2).
+#include "common.cuh"
+#include "nrhead_internal.h"
+#include "tc_common.cuh"
+
+namespace nr {
+using namespace tc;
+
+typedef CUresult (*EncodeTiledFnG)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFnG gemm_get_encode() {
+  static EncodeTiledFnG fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFnG)p;
+  }
+  return fn;
+}
+
+constexpr int G_BM = 128, G_BN = 256, G_BK = 64;
+constexpr int G_STAGES = 4;
+constexpr int G_A_BYTES = G_BM * 128;          // 16 KB
+constexpr int G_B_BYTES = G_BN * 128;          // 32 KB
+constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_THREADS = 64 + 256;            // TMA warp, MMA warp, 8 epilogue warps
+constexpr int G_EPI = 256;
+
+enum { G_EPI_STORE_F32 = 0, G_EPI_RED_F32 = 1, G_EPI_RELU_BF16 = 2 };
+
+struct alignas(64) GemmArgs {
+  CUtensorMap tma, tmb;
+  int M, N, K;
+  int a_mn, b_mn;                // operand stored MN-major ([K, M] / [K, N] row-major) instead of K-major
+  int n_mt, n_nt, ksplit, kb_per_split, num_kb, n_items;
+  int bn;                        // MMA N of this problem (<= 256, multiple of 16)
+  int epi;
+  float* c_f32; int64_t ldc;     // G_EPI_STORE_F32 / G_EPI_RED_F32
+  __nv_bfloat16* h_bf16;         // G_EPI_RELU_BF16: hidden activations [M, ldc] (nullable: evaluation)
+  const float* bias; const float* w2; float* logits;
+};
+
+// MN-major operand tile: 64-element (128 B) rows, one per k; 8-row groups 1024 B apart (SBO), the next 64 m/n
+// elements 64 rows = 8192 B further (LBO)
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;              // LBO: stride between 64-element atoms along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;              // SBO: stride between 8-row groups along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ GemmArgs a) {
+  extern __shared__ __align__(1024) uint8_t g_smem_raw[];
+  // keep the shared-space provenance of the pointer (offset add, no integer round trip): STS/LDS, not generic ST/LD
+  uint8_t* smem = g_smem_raw + ((1024u - (smem_u32(g_smem_raw) & 1023u)) & 1023u);
+  float* sbias = reinterpret_cast<float*>(smem + (size_t)G_STAGES * G_STAGE_BYTES);     // [2][256]
+  float* sw2 = sbias + 2 * G_BN;                                                          // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sw2 + 2 * G_BN);
+  uint64_t* full = bars;                    // [4] TMA -> MMA
+  uint64_t* empty = bars + G_STAGES;        // [4] MMA -> TMA
+  uint64_t* tfull = bars + 2 * G_STAGES;    // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;             // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tma); tma_prefetch_desc(&a.tmb);
+    for (int s = 0; s < G_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, G_EPI); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (m-tile, n-tile, k-block range); n fastest so that concurrently running CTAs share the A tile in L2
+  auto decode = [&](int item, int& mt, int& nt, int& kbA, int& kbB) {
+    const int ks = item % a.ksplit;
+    const int t = item / a.ksplit;
+    nt = t % a.n_nt;
+    mt = t / a.n_nt;
+    kbA = ks * a.kb_per_split;
+    kbB = min(a.num_kb, kbA + a.kb_per_split);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const int a_boxes = a.a_mn ? G_BM / 64 : 1;
+      const int b_boxes = a.b_mn ? (a.bn + 63) / 64 : 1;
+      // bytes landing per stage: full boxes (TMA zero-fills rows / columns beyond the tensor)
+      const uint32_t tx = (uint32_t)(a.a_mn ? a_boxes * 64 * 128 : G_BM * 128) +
+                          (uint32_t)(a.b_mn ? b_boxes * 64 * 128 : a.bn * 128);
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int mt, nt, kbA, kbB;
+        decode(item, mt, nt, kbA, kbB);
+        for (int kb = kbA; kb < kbB; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * G_STAGE_BYTES;
+          uint8_t* sb = sa + G_A_BYTES;
+          mbar_expect_tx(full + stage, tx);
+          if (a.a_mn) {
+            for (int i = 0; i < a_boxes; ++i) tma_load_2d(sa + i * 8192, &a.tma, full + stage, mt * G_BM + i * 64, kb * G_BK);
+          } else {
+            tma_load_2d(sa, &a.tma, full + stage, kb * G_BK, mt * G_BM);
+          }
+          if (a.b_mn) {
+            for (int i = 0; i < b_boxes; ++i) tma_load_2d(sb + i * 8192, &a.tmb, full + stage, nt * G_BN + i * 64, kb * G_BK);
+          } else {
+            tma_load_2d(sb, &a.tmb, full + stage, kb * G_BK, nt * G_BN);
+          }
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(G_BM, a.bn) | ((uint32_t)(a.a_mn ? 1 : 0) << 15) |
+                             ((uint32_t)(a.b_mn ? 1 : 0) << 16);
+      const uint64_t a_step = a.a_mn ? (uint64_t)(2048 >> 4) : 2ull;      // advance K by 16 elements
+      const uint64_t b_step = a.b_mn ? (uint64_t)(2048 >> 4) : 2ull;
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+        int mt, nt, kbA, kbB;
+        decode(item, mt, nt, kbA, kbB);
+        const int acc = it & 1;
+        mbar_wait(tempty + acc, (uint32_t)((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * G_BN);
+        for (int kb = kbA; kb < kbB; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * G_STAGE_BYTES);
+          const uint64_t adesc = a.a_mn ? umma_desc_mnmajor_sw128(sa) : umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = a.b_mn ? umma_desc_mnmajor_sw128(sa + G_A_BYTES) : umma_desc_kmajor_sw128(sa + G_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < G_BK / 16; ++k)
+            umma_bf16(tmem_d, adesc + a_step * (uint64_t)k, bdesc + b_step * (uint64_t)k, idesc, (kb > kbA || k > 0) ? 1u : 0u);
+          umma_commit(empty + stage);
+          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull + acc);
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps, two per TMEM lane quarter (column halves) =====================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;                                   // accumulator row
+    const int et = (int)threadIdx.x - 64;
+    const int hc = ((a.bn / 2) + 15) / 16 * 16;                    // columns per half (multiple of 16)
+    int it = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
+      int mt, nt, kbA, kbB;
+      decode(item, mt, nt, kbA, kbB);
+      const int acc = it & 1;
+      const int n0 = nt * G_BN;
+      const int m = mt * G_BM + r;
+      const bool row_ok = m < a.M;
+      float* sb_ = sbias + acc * G_BN;
+      float* sw_ = sw2 + acc * G_BN;
+      if (a.epi == G_EPI_RELU_BF16) {
+        // stage this tile's bias / second-layer weights while its MMAs are still running.  Buffer `acc` was last
+        // read two items ago; the barrier at the end of the previous item orders those reads before these writes.
+        for (int c = et; c < a.bn; c += G_EPI) {
+          const bool ok = n0 + c < a.N;
+          sb_[c] = ok ? a.bias[n0 + c] : 0.f;
+          sw_[c] = ok ? a.w2[n0 + c] : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      mbar_wait(tfull + acc, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G_BN);
+      const int c_lo = half * hc, c_hi = min(a.bn, c_lo + hc);
+      float dot = 0.f;
+      for (int c = c_lo; c < c_hi; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        reg_fence<16>(v);
+        const int n = n0 + c;
+        if (a.epi == G_EPI_RELU_BF16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float h0 = fmaxf(__uint_as_float(v[e]) + sb_[c + e], 0.f);
+            const float h1 = fmaxf(__uint_as_float(v[e + 1]) + sb_[c + e + 1], 0.f);
+            dot = fmaf(h0, sw_[c + e], dot);
+            dot = fmaf(h1, sw_[c + e + 1], dot);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(h0, h1);
+            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&p2);
+          }
+          if (a.h_bf16 && row_ok) {
+            __nv_bfloat16* dst = a.h_bf16 + (int64_t)m * a.ldc + n;
+            if (n + 16 <= a.N) {
+              *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+              for (int e = 0; e < 16 && n + e < a.N; ++e)
+                dst[e] = reinterpret_cast<__nv_bfloat16*>(pk)[e];
+            }
+          }
+        } else if (row_ok) {
+          float* dst = a.c_f32 + (int64_t)m * a.ldc + n;
+          if (a.epi == G_EPI_STORE_F32) {
+            if (n + 16 <= a.N) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 4)
+                *reinterpret_cast<float4*>(dst + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                  __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            } else {
+              for (int e = 0; e < 16 && n + e < a.N; ++e) dst[e] = __uint_as_float(v[e]);
+            }
+          } else {
+            for (int e = 0; e < 16 && n + e < a.N; ++e) red_add_f32(dst + e, __uint_as_float(v[e]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty + acc);
+      if (a.epi == G_EPI_RELU_BF16) {
+        if (row_ok) atomicAdd(a.logits + m, dot);
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // sbias / sw2 of this item fully read
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// bf16 2-D tensor map over a row-major [rows, cols] array with leading dimension ld: boxes {64 columns, box_rows},
+// 128B swizzle.  K-major operand: cols = K; MN-major operand: cols = M or N, rows = K.
+static int gemm_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFnG enc = gemm_get_encode();
+  NR_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NR_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(gemm) failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", (int)r,
+               (long long)rows, (long long)cols, (long long)ld, box_rows);
+  return 0;
+}
+
+static int gemm_launch(GemmArgs& a, const void* A, int64_t lda, const void* B, int64_t ldb, int want_split,
+                       cudaStream_t stream) {
+  NR_CHECK_ARG(A && B && a.M > 0 && a.N > 0 && a.K > 0, "nr_gemm: bad arguments");
+  NR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && lda % 8 == 0 && ldb % 8 == 0,
+               "nr_gemm: operands must be 16-byte aligned with leading dimensions that are multiples of 8");
+  NR_CHECK_ARG(a.N % 16 == 0, "nr_gemm: N=%d must be a multiple of 16", a.N);
+  a.bn = a.N < G_BN ? a.N : G_BN;
+  a.n_mt = (a.M + G_BM - 1) / G_BM;
+  a.n_nt = (a.N + G_BN - 1) / G_BN;
+  a.num_kb = (a.K + G_BK - 1) / G_BK;
+  int dev = 0, sms = 0;
+  NR_CUDA(cudaGetDevice(&dev));
+  NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int tiles = a.n_mt * a.n_nt;
+  int ks = 1;
+  if (want_split && tiles < sms) {
+    ks = sms / tiles;
+    if (ks > a.num_kb) ks = a.num_kb;
+    if (ks < 1) ks = 1;
+  }
+  a.kb_per_split = (a.num_kb + ks - 1) / ks;
+  a.ksplit = (a.num_kb + a.kb_per_split - 1) / a.kb_per_split;
+  a.n_items = tiles * a.ksplit;
+  if (a.a_mn) { if (int e = gemm_tmap(&a.tma, A, a.K, a.M, lda, 64)) return e; }
+  else { if (int e = gemm_tmap(&a.tma, A, a.M, a.K, lda, G_BM)) return e; }
+  if (a.b_mn) { if (int e = gemm_tmap(&a.tmb, B, a.K, a.N, ldb, 64)) return e; }
+  else { if (int e = gemm_tmap(&a.tmb, B, a.N, a.K, ldb, a.bn)) return e; }
+  const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 4 * G_BN * sizeof(float) + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NR_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int grid = a.n_items < sms ? a.n_items : sms;
+  gemm_bf16_tc_kernel<<<grid, G_THREADS, smem, stream>>>(a);
+  NR_CHECK_LAUNCH("nr_gemm");
+  return 0;
+}
+
+// fp32 -> bf16 copy (operand copies of the MLP inputs / W1); 8 elements per thread
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(x + i), b = *reinterpret_cast<const float4*>(x + i + 4);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    *reinterpret_cast<uint4*>(y + i) = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                                  *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+  } else {
+    for (int64_t j = i; j < n; ++j) y[j] = __float2bfloat16_rn(x[j]);
+  }
+}
+
+// masked softmax over the tokens of each sample from the second-layer logits (reference modeling.py:486-487,
+// 491-492): one warp per sample, N <= 128 tokens
+__global__ void __launch_bounds__(256) token_softmax_kernel(const float* __restrict__ logits, const float* __restrict__ b2,
+                                                            const int64_t* __restrict__ mask_a, const int64_t* __restrict__ mask_b,
+                                                            int Ra, int R, int N, float* __restrict__ w) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const int64_t* mk = row < Ra ? (mask_a ? mask_a + (int64_t)row * N : nullptr)
+                               : (mask_b ? mask_b + (int64_t)(row - Ra) * N : nullptr);
+  const float bias = b2[0];
+  float v[4];
+  float mx = NR_NEG_INF;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = lane + 32 * i;
+    v[i] = NR_NEG_INF;
+    if (t < N) {
+      v[i] = logits[(int64_t)row * N + t] + bias;
+      if (mk && mk[t] == 0) v[i] = -9e15f;                  // masked_fill_ value of the reference
+      mx = fmaxf(mx, v[i]);
+    }
+  }
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = lane + 32 * i;
+    v[i] = (t < N) ? expf(v[i] - mx) : 0.f;
+    s += v[i];
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = lane + 32 * i;
+    if (t < N) w[(int64_t)row * N + t] = v[i] / s;
+  }
+}
+
+}  // namespace nr
+
+using namespace nr;
+
+extern "C" int nr_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
+  NR_CHECK_ARG(x && y && n > 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "nr_cast_bf16: bad arguments");
+  const int64_t blocks = (n + 2047) / 2048;
+  cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, n);
+  NR_CHECK_LAUNCH("nr_cast_bf16");
+  return 0;
+}
+
+extern "C" int nr_mlp_fwd(const void* x_bf16, int64_t T, int64_t D, const void* w1_bf16, int64_t H, const float* b1,
+                          const float* w2, void* h_bf16, float* logits, void* stream) {
+  NR_CHECK_ARG(b1 && w2 && logits, "nr_mlp_fwd: bad arguments");
+  GemmArgs a{};
+  a.M = (int)T; a.N = (int)H; a.K = (int)D;
+  a.a_mn = 0; a.b_mn = 0;
+  a.epi = G_EPI_RELU_BF16;
+  a.h_bf16 = (__nv_bfloat16*)h_bf16; a.ldc = H;
+  a.bias = b1; a.w2 = w2; a.logits = logits;
+  return gemm_launch(a, x_bf16, D, w1_bf16, D, 0, (cudaStream_t)stream);
+}
+
+extern "C" int nr_mlp_bwd_dx(const void* dh_bf16, int64_t T, int64_t H, const void* w1_bf16, int64_t D, float* dx,
+                             int accumulate, void* stream) {
+  NR_CHECK_ARG(dx, "nr_mlp_bwd_dx: bad arguments");
+  GemmArgs a{};
+  a.M = (int)T; a.N = (int)D; a.K = (int)H;
+  a.a_mn = 0; a.b_mn = 1;                  // B[n=d][k=h] = W1[h][d]: stored with n contiguous
+  a.epi = accumulate ? G_EPI_RED_F32 : G_EPI_STORE_F32;
+  a.c_f32 = dx; a.ldc = D;
+  return gemm_launch(a, dh_bf16, H, w1_bf16, D, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int nr_mlp_bwd_dw1(const void* dh_bf16, int64_t T, int64_t H, const void* x_bf16, int64_t D, float* dw1,
+                              void* stream) {
+  NR_CHECK_ARG(dw1, "nr_mlp_bwd_dw1: bad arguments");
+  GemmArgs a{};
+  a.M = (int)H; a.N = (int)D; a.K = (int)T;
+  a.a_mn = 1; a.b_mn = 1;                  // A[m=h][k=t] = dh[t][h], B[n=d][k=t] = x[t][d]: both as stored
+  a.epi = G_EPI_RED_F32;                   // split-K over the tokens: dw1 must be zero- or partially filled
+  a.c_f32 = dw1; a.ldc = D;
+  return gemm_launch(a, dh_bf16, H, x_bf16, D, 1, (cudaStream_t)stream);
+}
+
+extern "C" int nr_token_softmax(const float* logits, const float* b2, const int64_t* mask_a, const int64_t* mask_b,
+                                int64_t Ra, int64_t R, int64_t N, float* w, void* stream) {
+  NR_CHECK_ARG(logits && b2 && w && R > 0 && N > 0 && N <= 128 && Ra >= 0 && Ra <= R, "nr_token_softmax: bad arguments");
+  token_softmax_kernel<<<(unsigned)((R + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, b2, mask_a, mask_b, (int)Ra, (int)R,
+                                                                                 (int)N, w);
+  NR_CHECK_LAUNCH("nr_token_softmax");
+  return 0;
+}

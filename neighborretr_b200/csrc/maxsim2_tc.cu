@@ -11,7 +11,8 @@
 // fp32 accumulator is read from TMEM once and reduced in BOTH directions:
 //   row direction    (max over the Ny columns of a Y sample): one accumulator row per thread, in registers;
 //   column direction (max over the Nx rows of an X sample):  rows live in different lanes -> (value, row) keys
-//                    (fp32 bits of v+2 with the low log2(GL) bits replaced by the row index) are reduced by a
+//                    (order-preserving integer image of the fp32 value with its log2(GL) lowest mantissa bits
+//                    replaced by the row index: 2^-20 RELATIVE resolution at every magnitude) are reduced by a
 //                    halving butterfly over aligned groups of GL lanes (GL columns in, one column per lane out),
 //                    the 128/GL group partials go to shared memory and are combined per X sample afterwards.
 // Up to 4 independent (X, Y) problems with the same token counts share a launch (the batch pair and the two bank
@@ -56,7 +57,15 @@ struct alignas(64) Tc2Args {
   int nprob, n_tiles;
   int Nx, SX, MU, SY, UN, num_kb, stages, b_bytes, hp_ld, kg_ld;
   unsigned int* tile_counter;              // zeroed per launch: dynamic tile scheduler
+  unsigned long long* trace;               // debug (NR_TC2_TRACE=1): 16 globaltimer stamps per CTA, else nullptr
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define T2_TRACE(slot) do { if (a.trace) a.trace[(size_t)blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 
 __host__ __device__ constexpr int t2_gcd(int a, int b) { return b == 0 ? a : t2_gcd(b, a % b); }
 __host__ __device__ constexpr int t2_lcm(int a, int b) { return a / t2_gcd(a, b) * b; }
@@ -138,6 +147,7 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
   if (CL2) cluster_sync_all();                            // the peer's barriers are initialised before any remote use
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) T2_TRACE(0);                      // set-up done
   // consumers of a ring slot: read the tile, release the slot on the LEADER's barrier
   auto ring_take = [&](int it) {
     const int slot = it & (T2_RING - 1);
@@ -174,6 +184,8 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
           else mbar_wait(rempty + slot, ((uint32_t)(n / T2_RING) & 1u) ^ 1u);
           tile = (int)atomicAdd(a.tile_counter, 1u);
           if (tile >= a.n_tiles) tile = -1;
+          if (n == 0) T2_TRACE(1);                        // first claim
+          if (tile < 0) { T2_TRACE(2); if (a.trace) a.trace[(size_t)blockIdx.x * 16 + 3] = (unsigned long long)n; }
           ring[slot] = tile;
           if (CL2) {
             st_remote_u32(ring + slot, 1, (uint32_t)tile);
@@ -243,6 +255,7 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
         for (int kb = 0; kb < a.num_kb; ++kb) {
           mbar_wait(full + stage, phase);
           tc_fence_after();
+          if (it == 0 && kb == 0) T2_TRACE(4);             // first operands landed
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = umma_desc_kmajor_sw128(sa + T2_A_BYTES);
@@ -254,6 +267,8 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull + acc);                        // accumulator ready for the epilogue
+        if (it == 0) T2_TRACE(5);                          // first tile issued
+        T2_TRACE(6);                                       // last tile issued (overwritten per tile)
       }
     }
   } else {
@@ -297,6 +312,7 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
       for (int c = et; c < ncols; c += T2_SET) wys[c] = P.wy[(int64_t)ry0 * NY + c];
       mbar_wait(tfull + set, acc_phase);
       tc_fence_after();
+      if (et == 0 && it == set) T2_TRACE(8 + 2 * set);     // first accumulator of this set ready
       auto process = [&](const uint32_t* v, int ch) {
         // row direction: max / arg-max over the NY columns of each Y sample of the chunk
 #pragma unroll
@@ -319,7 +335,12 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
         for (int g = 0; g < CH / GL; ++g) {
           uint32_t k[GL];
 #pragma unroll
-          for (int j = 0; j < GL; ++j) k[j] = (__float_as_uint(__uint_as_float(v[g * GL + j]) + 2.0f) & ~LOWM) | low;
+          for (int j = 0; j < GL; ++j) {
+            // order-preserving integer image of the fp32 value (all exponents keep their full relative precision:
+            // only the log2(GL) lowest mantissa bits give way to the row index), ties -> lower row
+            const uint32_t u = v[g * GL + j];
+            k[j] = ((u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u)) & ~LOWM) | low;
+          }
           kg_row[ch * CH + g * GL] = group_colmax<GL>(k, lane);
         }
       };
@@ -366,7 +387,8 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
             const uint32_t kk = kp[gi * a.kg_ld];
             if ((kk & ~LOWM) > (best & ~LOWM)) { best = kk; bg = gi; }   // equal values: the lower group stays
           }
-          const float val = __uint_as_float(best & ~LOWM) - 2.0f;
+          const uint32_t tb = best & ~LOWM;
+          const float val = __uint_as_float((tb & 0x80000000u) ? (tb ^ 0x80000000u) : ~tb);
           const int xs = bg * GL + (int)(LOWM - (best & LOWM));
           const int64_t o = ((int64_t)(mt * a.SX + s) * P.Ry + ry0) * NY + c;
           if (P.pmax_y) P.pmax_y[o] = val;
@@ -395,10 +417,12 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
         if (P.out2) P.out2[(int64_t)rxx * P.out2_sr + (int64_t)ry * P.out2_sc] = h;
       }
       set_barrier<T2_SET>(set);       // the set's staging buffers (hp, keyG, colw, wys) are free for its next tile
+      if (et == 0) T2_TRACE(9 + 2 * set);                  // end of this set's latest tile (overwritten per tile)
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) T2_TRACE(12);                      // CTA done
   if (CL2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == 1) {
     __syncwarp();
@@ -530,6 +554,10 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
   }
   a.n_tiles = tiles;
   a.tile_counter = (unsigned int*)workspace;        // {next tile, finished claimers}: zero on entry, zero again on exit
+  // debug timeline: the caller provides >= 16 + 8 * 16 * gridDim bytes of workspace when it sets NR_TC2_TRACE
+  a.trace = nullptr;
+  if (const char* tv = getenv("NR_TC2_TRACE"))
+    if (atoi(tv) != 0) a.trace = (unsigned long long*)((uint8_t*)workspace + 16);
   const size_t tail = (size_t)2 * T2_BM * a.hp_ld * 4 + (size_t)2 * (T2_BM / GL) * a.kg_ld * 4 +
                       (size_t)2 * a.SX * a.UN * 4 + (size_t)2 * a.UN * 4 + 512;
   const size_t budget = 227 * 1024 - 1024;   // alignment slack

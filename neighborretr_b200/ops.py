@@ -289,7 +289,7 @@ def _tile_workspace(dev):
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _TILE_WS.get(key)
     if ws is None:
-        ws = _TILE_WS[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+        ws = _TILE_WS[key] = torch.zeros(4 + 2 * 16 * 256, dtype=torch.int32, device=dev)   # counters + debug timeline
     return ws
 
 
@@ -526,6 +526,9 @@ class _tf32:
 
 
 MLP_FP32, MLP_TF32, MLP_BF16 = 0, 1, 2
+# bf16 mode: the MLP GEMMs run on this repo's tcgen05 kernel (csrc/gemm_tc.cu); tests flip this to compare against the
+# library GEMMs
+USE_OWN_GEMM = True
 
 
 def mlp_mode(v):
@@ -556,6 +559,30 @@ class TokenWeightsFunction(torch.autograd.Function):
         H = w1.shape[0]
         Ta, Tb = Ra * N, Rb * N
         lp = mode == MLP_BF16
+        own = lp and USE_OWN_GEMM and D % 8 == 0 and H % 16 == 0 and N <= 128
+        ma, mb = _mask(ma), (_mask(mb) if Rb else None)
+        w = torch.empty(Ra + Rb, N, dtype=torch.float32, device=xa.device)
+        w2c, b2c = _f32c(w2).reshape(-1), _f32c(b2).reshape(-1)
+        ctx.mode, ctx.dims, ctx.own = mode, (Ra, Rb, N, D, H), own
+        ctx.xshape = xa.shape
+        if own:
+            # libnrhead.so end to end: bf16 operand copies, ONE tcgen05 GEMM over batch + bank tokens with bias, ReLU
+            # and the second layer's dot product in its epilogue, then the masked softmax over tokens
+            st = _stream()
+            dev = xa.device
+            xbf = torch.empty(Ta + Tb, D, dtype=torch.bfloat16, device=dev)
+            w1bf = torch.empty(H, D, dtype=torch.bfloat16, device=dev)
+            _call("nr_cast_bf16", _p(_f32c(xa)), _p(xbf), Ta * D, st)
+            if Rb:
+                _call("nr_cast_bf16", _p(_f32c(xb)), _p(xbf[Ta:]), Tb * D, st)
+            _call("nr_cast_bf16", _p(_f32c(w1)), _p(w1bf), H * D, st)
+            keep = any(ctx.needs_input_grad)
+            h = torch.empty(Ta + Tb, H, dtype=torch.bfloat16, device=dev) if keep else None
+            logits = torch.zeros(Ra + Rb, N, dtype=torch.float32, device=dev)
+            _call("nr_mlp_fwd", _p(xbf), Ta + Tb, D, _p(w1bf), H, _p(_f32c(b1)), _p(w2c), _p(h), _p(logits), st)
+            _call("nr_token_softmax", _p(logits), _p(b2c), _p(ma), _p(mb), Ra, Ra + Rb, N, _p(w), st)
+            ctx.save_for_backward(xbf, None, h, w, w1bf, w2c)
+            return (w[:Ra], w[Ra:]) if Rb else (w[:Ra], None)
         cdt = torch.bfloat16 if lp else torch.float32
         xa2 = _f32c(xa).reshape(Ta, D)
         xb2 = _f32c(xb).reshape(Tb, D) if Rb else None
@@ -564,19 +591,14 @@ class TokenWeightsFunction(torch.autograd.Function):
             xa2 = xa2.to(cdt)
             xb2 = xb2.to(cdt) if Rb else None
             w1c, b1c = w1.to(cdt), b1.to(cdt)
-        ma, mb = _mask(ma), (_mask(mb) if Rb else None)
         h = torch.empty(Ta + Tb, H, dtype=cdt, device=xa.device)
-        w = torch.empty(Ra + Rb, N, dtype=torch.float32, device=xa.device)
-        w2c, b2c = _f32c(w2).reshape(-1), _f32c(b2).reshape(-1)
         with _tf32(mode == MLP_TF32):
             torch._addmm_activation(b1c, xa2, w1c.t(), use_gelu=False, out=h[:Ta])     # bias + ReLU in the epilogue
             if Rb:
                 torch._addmm_activation(b1c, xb2, w1c.t(), use_gelu=False, out=h[Ta:])
         _call("nr_token_weights_fwd", _p(h), int(lp), _p(w2c), _p(b2c), _p(ma), _p(mb), Ra, Ra + Rb, N, H, _p(w),
               _stream())
-        ctx.mode, ctx.dims = mode, (Ra, Rb, N, D, H)
         ctx.save_for_backward(xa2, xb2, h, w, w1c, w2c)
-        ctx.xshape = xa.shape
         wa = w[:Ra]
         if Rb:
             return wa, w[Ra:]
@@ -595,20 +617,33 @@ class TokenWeightsFunction(torch.autograd.Function):
         nch = _lib.load().nr_mlp_chunks(Ta + Tb)
         partials = torch.empty(2 * H + 1, nch, dtype=torch.float32, device=h.device)
         sums = torch.empty(2 * H + 1, dtype=torch.float32, device=h.device)
+        dw1 = dx = None
+        if ctx.own:
+            if need[4]:
+                dw1 = torch.zeros(H, D, dtype=torch.float32, device=h.device)
+            if need[0]:
+                dx = torch.zeros(Ta, D, dtype=torch.float32, device=h.device)
         st = _stream()
         _call("nr_token_weights_bwd", _p(h), int(lp), _p(w), _p(dwa), _p(dwb), Ra, Ra + Rb, N, _p(w2c), H, _p(dh),
               _p(partials), st)
-        dw1 = dx = None
         with ForkJoin(1) as fj:
             with fj.on(0):                        # bias / second-layer gradients next to the GEMMs
                 _call("nr_vec_sums", _p(partials), 2 * H + 1, nch, None, _p(sums), _stream())
-            with _tf32(ctx.mode == MLP_TF32):
+            if ctx.own:
+                # dW1 = dh^T x over batch + bank tokens (operands as stored, split-K), dx = dh W1 for the batch tokens
                 if need[4]:
-                    dw1 = _dw1_splitk(dh[:Ta], xa2)
-                    if Rb:
-                        dw1 += _dw1_splitk(dh[Ta:], xb2)
+                    _call("nr_mlp_bwd_dw1", _p(dh), Ta + Tb, H, _p(xa2), D, _p(dw1), _stream())
                 if need[0]:
-                    dx = (torch.mm(dh[:Ta], w1c, out_dtype=torch.float32) if lp else dh[:Ta] @ w1c).reshape(ctx.xshape)
+                    _call("nr_mlp_bwd_dx", _p(dh), Ta, H, _p(w1c), D, _p(dx), 1, _stream())
+                    dx = dx.reshape(ctx.xshape)
+            else:
+                with _tf32(ctx.mode == MLP_TF32):
+                    if need[4]:
+                        dw1 = _dw1_splitk(dh[:Ta], xa2)
+                        if Rb:
+                            dw1 += _dw1_splitk(dh[Ta:], xb2)
+                    if need[0]:
+                        dx = (torch.mm(dh[:Ta], w1c, out_dtype=torch.float32) if lp else dh[:Ta] @ w1c).reshape(ctx.xshape)
         db1 = sums[:H] if need[5] else None
         dw2 = sums[H:2 * H].reshape(1, H) if need[6] else None
         db2 = sums[2 * H:] if need[7] else None

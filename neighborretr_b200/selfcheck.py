@@ -81,7 +81,13 @@ def compare_step(ref, rank, b, losses, grads, model):
          "logit_scale": _rel_l2(model.clip.logit_scale.grad, ref["logit_scale"])}
     for n in PARAM_NAMES:
         for pn, p in getattr(model, n).named_parameters():
-            g[f"{n}.{pn}"] = _rel_l2(p.grad, ref[f"{n}.{pn}"])
+            if pn == "2.bias":
+                # the softmax over tokens is invariant to the second layer's bias: its gradient is 0 up to rounding,
+                # so it is compared on the scale of the second layer's weight gradient instead of relatively
+                scale = ref[f"{n}.2.weight"].double().norm().clamp_min(1e-30)
+                g[f"{n}.{pn}"] = float((p.grad.double() - ref[f"{n}.{pn}"].double()).norm() / scale)
+            else:
+                g[f"{n}.{pn}"] = _rel_l2(p.grad, ref[f"{n}.{pn}"])
     e["grads"] = g
     e["grad_rel_l2"] = max(g.values())
     e["bank_equal"] = all(bool(torch.equal(getattr(model, n), ref[n]))

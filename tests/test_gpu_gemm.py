@@ -1,0 +1,80 @@
+"""The tcgen05 GEMM of the token-weight MLPs (csrc/gemm_tc.cu) against float64 products of the SAME bf16 operands:
+forward (K-major x K-major, bias + ReLU + second-layer dot in the epilogue), dx (K-major x MN-major),
+dW1 (MN-major x MN-major, split-K over the tokens).  Operands are consumed as stored — no transposed copies — so these
+tests pin the MN-major shared-memory descriptors.  Tolerance: fp32 accumulation of bf16 products, 2e-5 relative to the
+largest entry (h is stored as bf16: 2^-9 relative)."""
+import ctypes
+
+import pytest
+import torch
+
+from neighborretr_b200 import ops
+from neighborretr_b200.ops import _call, _p, _stream
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).contiguous()
+
+
+@pytest.mark.parametrize("T,D,H", [(300, 512, 1024), (15360, 512, 1024), (128, 256, 512), (1000, 64, 256)])
+def test_mlp_forward_gemm(T, D, H):
+    g = torch.Generator().manual_seed(T)
+    x = _bf(torch.randn(T, D, generator=g).cuda()); w1 = _bf((0.05 * torch.randn(H, D, generator=g)).cuda())
+    b1 = (0.1 * torch.randn(H, generator=g)).cuda(); w2 = (0.05 * torch.randn(H, generator=g)).cuda()
+    h = torch.empty(T, H, dtype=torch.bfloat16, device="cuda")
+    logits = torch.zeros(T, device="cuda")
+    _call("nr_mlp_fwd", _p(x), T, D, _p(w1), H, _p(b1), _p(w2), _p(h), _p(logits), _stream())
+    want = torch.relu(x.double() @ w1.double().t() + b1.double())
+    herr = (h.double() - want).abs().max().item() / want.abs().max().item()
+    lwant = want @ w2.double()
+    lerr = (logits.double() - lwant).abs().max().item() / lwant.abs().max().item()
+    print(f"mlp_fwd T={T} D={D} H={H}: h rel err {herr:.2e}, logits rel err {lerr:.2e}")
+    assert herr < 5e-3 and lerr < 2e-5
+    # evaluation form: no hidden activations kept
+    logits2 = torch.zeros(T, device="cuda")
+    _call("nr_mlp_fwd", _p(x), T, D, _p(w1), H, _p(b1), _p(w2), None, _p(logits2), _stream())
+    assert (logits2.double() - lwant).abs().max().item() / lwant.abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("T,D,H", [(300, 512, 1024), (3072, 512, 1024), (64, 256, 512)])
+@pytest.mark.parametrize("acc", [0, 1])
+def test_mlp_backward_dx_gemm(T, D, H, acc):
+    g = torch.Generator().manual_seed(T + acc)
+    dh = _bf(torch.randn(T, H, generator=g).cuda()); w1 = _bf((0.05 * torch.randn(H, D, generator=g)).cuda())
+    dx = torch.zeros(T, D, device="cuda") if acc else torch.full((T, D), float("nan"), device="cuda")
+    _call("nr_mlp_bwd_dx", _p(dh), T, H, _p(w1), D, _p(dx), acc, _stream())
+    want = dh.double() @ w1.double()
+    err = (dx.double() - want).abs().max().item() / want.abs().max().item()
+    print(f"mlp_bwd_dx T={T} acc={acc}: rel err {err:.2e}")
+    assert err < 2e-5
+
+
+@pytest.mark.parametrize("T,D,H", [(300, 512, 1024), (15360, 512, 1024), (7680, 512, 1024), (200, 256, 512)])
+def test_mlp_backward_dw1_gemm(T, D, H):
+    g = torch.Generator().manual_seed(T)
+    dh = _bf(torch.randn(T, H, generator=g).cuda()); x = _bf(torch.randn(T, D, generator=g).cuda())
+    dw1 = torch.zeros(H, D, device="cuda")
+    _call("nr_mlp_bwd_dw1", _p(dh), T, H, _p(x), D, _p(dw1), _stream())
+    want = dh.double().t() @ x.double()
+    err = (dw1.double() - want).abs().max().item() / want.abs().max().item()
+    print(f"mlp_bwd_dw1 T={T}: rel err {err:.2e}")
+    assert err < 2e-5
+
+
+def test_token_softmax_and_cast():
+    g = torch.Generator().manual_seed(1)
+    ra, rb, n = 7, 5, 24
+    logits = torch.randn(ra + rb, n, generator=g).cuda(); b2 = torch.tensor([0.3]).cuda()
+    ma = (torch.rand(ra, n, generator=g) > 0.4).long().cuda(); mb = (torch.rand(rb, n, generator=g) > 0.4).long().cuda()
+    ma[:, 0] = 1; mb[:, 0] = 1
+    w = torch.empty(ra + rb, n, device="cuda")
+    _call("nr_token_softmax", _p(logits), _p(b2), _p(ma), _p(mb), ra, ra + rb, n, _p(w), _stream())
+    m = torch.cat([ma, mb])
+    want = torch.softmax((logits.double() + 0.3).masked_fill(m == 0, -9e15), -1)
+    assert (w.double() - want).abs().max().item() < 1e-6 and w[m == 0].abs().max().item() == 0.0
+    x = torch.randn(1000 * 512 + 3, generator=g).cuda()[: 1000 * 512]
+    y = torch.empty(x.numel(), dtype=torch.bfloat16, device="cuda")
+    _call("nr_cast_bf16", _p(x.contiguous()), _p(y), x.numel(), _stream())
+    assert torch.equal(y, x.to(torch.bfloat16))

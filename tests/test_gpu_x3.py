@@ -52,10 +52,13 @@ def test_maxsim_x3_forward_and_backward_vs_float64(shape):
     assert max(gerr[:2]) < 2e-3 and max(gerr[2:]) < 1e-4
 
 
-@pytest.mark.parametrize("name", ["small", "cfg1"])
+X3_CASES = {"cfg1": CASES["cfg1"], "tiny": dict(b=40, nt=8, nv=4, d=64, m=56, k=20)}
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1"])
 def test_head_x3_vs_reference_golden_and_oracle(name):
-    c = CASES[name]
-    gold = load_golden(name)
+    c = X3_CASES[name]
+    gold = load_golden(name) if name in CASES else None
     h, bank, params, cfg = make_case(c)
     ref, rgrads = oracle_losses(h, bank, params, cfg)
     m = make_head(c["d"], cfg, params, "bf16x3")
@@ -64,7 +67,8 @@ def test_head_x3_vs_reference_golden_and_oracle(name):
     lerr = float((losses / ref - 1).abs().max())
     gerr = {k: rel_l2(grads[k], rgrads[k]) for k in rgrads}
     print(f"head x3 [{name}]: loss rel err {lerr:.2e}; grad rel-L2 {gerr}")
-    np.testing.assert_allclose(losses.numpy(), gold["losses"], rtol=1e-4)      # the reference's own values
+    if gold is not None:
+        np.testing.assert_allclose(losses.numpy(), gold["losses"], rtol=1e-4)      # the reference's own values
     np.testing.assert_allclose(losses.numpy(), ref.numpy(), rtol=1e-4)
     for k in ("text", "video", "gt", "gv"):
         assert gerr[k] < 5e-3, (k, gerr[k])
