@@ -103,10 +103,10 @@ class GraphedHeadStep:
                                        global_feats=(s["global_text"], s["global_video"]))
             new_rows = (s["idx"], s["text_feat"], s["video_feat"], s["text_mask"], s["video_mask"])
         else:       # row-block sharded head; the NCCL collectives are captured in the graph
-            from .until_module import _gather_contiguous
-            losses, (ta, va, tma, vma) = m._sharded_losses(s["text_feat"], s["video_feat"], s["text_mask"],
-                                                           s["video_mask"], (s["global_text"], s["global_video"]))
-            new_rows = (_gather_contiguous(s["idx"], self.world), ta, va, tma, vma)
+            losses, (ta, va, tma, vma, ia) = m._sharded_losses(s["text_feat"], s["video_feat"], s["text_mask"],
+                                                               s["video_mask"], (s["global_text"], s["global_video"]),
+                                                               idx=s["idx"])
+            new_rows = (ia, ta, va, tma, vma)
         # With bf16 weight-MLP GEMMs the backward reads bf16 copies, never the bank itself: the FIFO update can then
         # leave the critical path and run on its own branch next to the backward.
         early_fifo = self.world == 1 and m._mlp_precision() == "bf16"

@@ -237,9 +237,10 @@ class HeadMixin:
         self.mb_mask_v = ops.fifo_update(video_mask.to(self.mb_mask_v.dtype), self.mb_mask_v, cap)
 
     # --- everything of reference forward() below the encoders (:269-312) -----------------------------
-    def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats):
+    def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats, idx=None):
         """W > 1: row-block sharded head (sharded.py) on the LOCAL batch; gathers happen inside.
-        Returns (5 losses, gathered (text, video, text_mask, video_mask))."""
+        Returns (5 losses, gathered (text, video, text_mask, video_mask[, idx])); idx (the dataset indices the bank
+        FIFO stores) rides on the packed small gather when given."""
         from .fused import head_hparams
         from .sharded import ShardedHeadFunction, ShardedPrologue, SumGradsAcrossRanks
         cfg = self.config
@@ -253,11 +254,11 @@ class HeadMixin:
                           cfg.neighbor_weight, cfg.kl_weight, self._head_precision(), self._head_bwd_precision())
         # gathers, token preparation, centrality weights, global similarity + Sinkhorn: forked next to the MLPs
         pro = ShardedPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, self.mb_feat_t, self.mb_feat_v,
-                              self.mb_mask_t, self.mb_mask_v, hp)
+                              self.mb_mask_t, self.mb_mask_v, hp, idx_l=idx)
         with ops.ForkJoin(4) as fj:
             main = fj.main
             with fj.on(3):
-                pro.run_global()             # first: its small gather must not queue behind the feature gathers
+                pro.run_global()             # first: Sinkhorn is the longest chain of the forward
             pro.global_done = fj.detach(3)
             with fj.on(2):
                 pro.run_video_side()
@@ -272,14 +273,16 @@ class HeadMixin:
             self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v, hp, pro)
         self.last_neighbors = (nbr[0], nbr[1])
         self._text_ready = pro.text_ready          # event of the deferred text gather (None: already joined)
+        if idx is not None:
+            return tuple(out5.unbind(0)), (text_all, video_all, tm_all, vm_all, pro.idx_all)
         return tuple(out5.unbind(0)), (text_all, video_all, tm_all, vm_all)
 
     def _head_forward_sharded(self, text_feat, video_feat, text_mask, video_mask, idx, global_feats):
-        losses, (text_all, video_all, tm_all, vm_all) = self._sharded_losses(text_feat, video_feat, text_mask,
-                                                                             video_mask, global_feats)
+        losses, (text_all, video_all, tm_all, vm_all, idx_all) = self._sharded_losses(
+            text_feat, video_feat, text_mask, video_mask, global_feats, idx=idx)
         with torch.no_grad():
             self.wait_gathered_text()
-            self.update_memory_bank(allgather(idx, self.config), text_all, video_all, tm_all, vm_all)
+            self.update_memory_bank(idx_all.to(idx.dtype), text_all, video_all, tm_all, vm_all)
         return losses
 
     def wait_gathered_text(self):

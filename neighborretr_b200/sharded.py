@@ -104,7 +104,8 @@ class ShardedPrologue:
     the preparation needs); the three run_* groups are independent and are enqueued on forked streams next to the
     MLP evaluations (modeling._sharded_losses) — the NCCL collectives overlap them."""
 
-    def __init__(self, text_l, video_l, gt_l, gv_l, tm_l, vm_l, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp):
+    def __init__(self, text_l, video_l, gt_l, gv_l, tm_l, vm_l, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp,
+                 idx_l=None):
         cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
         _req_cuda(text_l, video_l, gt_l, gv_l, mb_feat_t, mb_feat_v)
         self.hp = hp
@@ -118,8 +119,6 @@ class ShardedPrologue:
         self.text = torch.empty(B, nt, d, **f32)
         self.video = torch.empty(B, nv, d, **f32)
         self.g_l = (_f32c(gt_l.detach()).reshape(b, d).contiguous(), _f32c(gv_l.detach()).reshape(b, d).contiguous())
-        self.gl = torch.stack(self.g_l, 1)                                                    # [b,2,d]
-        self.gall = torch.empty(B, 2, d, **f32)
         self.g2, self.v2 = torch.empty(B, d, **f32), torch.empty(B, d, **f32)
         x3 = prec == NR_PREC_BF16X3
         bf_ = prec in ops.TC_PRECISIONS or bprec in ops.TC_PRECISIONS
@@ -133,9 +132,20 @@ class ShardedPrologue:
             # aligned column offsets; decided from (b, Nt, Nv) alone so that EVERY rank raises before any collective
             raise RuntimeError(f"sharded head, bf16 one-direction kernels: per-rank batch x tokens must be a multiple "
                                f"of 8 (b={b}, Nt={nt}, Nv={nv}); use head_bwd_precision='fp32' or an even batch")
-        # ---- exchange 0: masks (the operand preparation needs them)
-        masks = _gather(torch.cat([_mask(tm_l), _mask(vm_l)], dim=1))                       # [B, Nt+Nv] int64
+        # ---- exchange 0: ONE packed gather of everything small that exists before any kernel has run — the masks (the
+        # operand preparation needs them), the global features (Sinkhorn starts from them) and the dataset indices of
+        # the bank FIFO: [masks int64 b x (Nt+Nv) | globals f32 b x 2 x d | idx int64 b] as bytes
+        idx_l = (idx_l if idx_l is not None else torch.zeros(b, dtype=torch.int64, device=dev)).reshape(b).to(torch.int64)
+        pieces = [torch.cat([_mask(tm_l), _mask(vm_l)], dim=1).reshape(-1).view(torch.uint8),
+                  torch.stack(self.g_l, 1).reshape(-1).view(torch.uint8), idx_l.contiguous().view(torch.uint8)]
+        o1 = pieces[0].numel()
+        o2 = o1 + pieces[1].numel()
+        packed = _gather(torch.cat(pieces).unsqueeze(0))                                     # [W, bytes]
+        masks = packed[:, :o1].view(torch.int64).reshape(B, nt + nv)
         self.tm, self.vm = masks[:, :nt].contiguous(), masks[:, nt:].contiguous()
+        gall = packed[:, o1:o2].view(torch.float32).reshape(B, 2, d)
+        self.g2.copy_(gall[:, 0]); self.v2.copy_(gall[:, 1])
+        self.idx_all = packed[:, o2:].view(torch.int64).reshape(B)
         self.mtm, self.mvm = _mask(mb_mask_t), _mask(mb_mask_v)
         self.bf, self.fusedk = bf, fk = bf_, fk_
         # Fused (bf16) path = "exchange" design: a rank contracts only ITS text rows against all videos (P = S[rows_r,
@@ -177,10 +187,9 @@ class ShardedPrologue:
             self.MT.run()
             self.Tl.run()
             self.MT.bwd_source(bprec); self.Tl.bwd_source(bprec)
-            # column mean over ALL text tokens (modeling.py:419-424) from per-rank column sums
+            # column mean over ALL text tokens (modeling.py:419-424) from per-rank column sums: the [W, D] exchange
+            # rides with the gather of the video token weights in the head forward (finish_text_centrality)
             torch.sum(self.Tl.partials, dim=0, keepdim=True, out=self.tsum_l)
-            dist.all_gather_into_tensor(self.tsum, self.tsum_l)      # exchange 1a' ([W, D])
-            self._centrality(self.tsum, self.t_rows, 0)
             return                                                   # the text gather is deferred: gather_text_async()
         dist.all_gather_into_tensor(self.text, self.text_l)          # exchange 1a
         self.MT.run()
@@ -188,6 +197,9 @@ class ShardedPrologue:
         if self.bf:
             self.MT.bwd_source(bprec); self.T.bwd_source(bprec)
         self._centrality(self.T.partials, self.T.rows, 0)
+
+    def finish_text_centrality(self):
+        self._centrality(self.tsum, self.t_rows, 0)
 
     def gather_text_async(self):
         """Exchange design only: other ranks' text tokens feed nothing but the memory-bank FIFO, so their gather is
@@ -211,8 +223,6 @@ class ShardedPrologue:
 
     def run_global(self):
         B, iters = self.B, int(self.hp[4])
-        dist.all_gather_into_tensor(self.gall, self.gl)              # exchange 1c
-        self.g2.copy_(self.gall[:, 0]); self.v2.copy_(self.gall[:, 1])
         _call("nr_gram_f32", _p(self.g2), _p(self.v2), B, B, self.V.d, _p(self.GG[0]), _p(self.GG[1]), _stream())
         d_ = self.duals
         _call("nr_sinkhorn", _p(self.GG[0]), _p(self.GG[1]), B, iters, _p(d_[0]), _p(d_[1]), _p(d_[2]), _p(d_[3]),
@@ -248,7 +258,11 @@ class ShardedHeadFunction(torch.autograd.Function):
         # ---- exchange 2: token weights of the local rows (the only gather that needs the MLPs)
         a2a = pro.a2a
         if a2a:                                   # other ranks never touch this rank's text weights
-            vw = _gather(_f32c(vw_l))                                                        # [B, Nv]
+            # [video token weights b x Nv | text column sums d] per rank in one gather
+            pk = _gather(torch.cat([_f32c(vw_l).reshape(-1), pro.tsum_l.reshape(-1)]).unsqueeze(0))   # [W, b*Nv + d]
+            vw = pk[:, :b * nv_].reshape(B, nv_)                                             # [B, Nv]
+            pro.tsum.copy_(pk[:, b * nv_:])
+            pro.finish_text_centrality()
             tw = _f32c(tw_l)                                                                 # [b, Nt]
             tw_lc = tw
         else:
@@ -266,18 +280,25 @@ class ShardedHeadFunction(torch.autograd.Function):
         if fusedk:
             # ONE launch, 3 problems, every token pair multiplied once: S_row = S(text_l, video) [b,B] (and its
             # transpose [B,b], whose [b,b] row chunks are what the other ranks need) and the two bank blocks
-            PT = torch.empty(B, b, **f32)
+            # the transposed block is written with a leading dimension of b + 2: chunk q (rows q*b..) is then the
+            # [b, b+2] payload for rank q, whose two spare columns carry this rank's bank centralities (exchange 3)
+            PT = torch.empty(B, b + 2, **f32)
             sv1, svA, svC = ops.maxsim2_fwd([
-                dict(X=Tl, Y=V, wx=tw_lc, wy=vw, alpha=0.5, out=S_row, strides=(B, 1), out2=PT, strides2=(1, b)),
+                dict(X=Tl, Y=V, wx=tw_lc, wy=vw, alpha=0.5, out=S_row, strides=(B, 1), out2=PT, strides2=(1, b + 2)),
                 dict(X=Tl, Y=MV, wx=tw_lc, wy=vw_mb, alpha=0.5, out=mb_t2v, strides=(M, 1)),
                 dict(X=MT, Y=Vl, wx=tw_mb, wy=vw_lc, alpha=0.5, out=mb_v2t, strides=(1, M))])
             p1, y1, p2, y2 = sv1          # (pmax_x, ystar, pmax_y, xstar) of each pair
             p3 = y3 = p4 = y4 = None
             pA, yA, pB, yB = svA
             pC, yC, pD, yD = svC
-            # ---- exchange 2b: S_col[v_l, (q, a)] = S[(q, a), lo + v_l] = chunk r of rank q's transposed block
-            recv = _all_to_all_blocks(PT.view(W, b, b))                                      # [q, v_l, a]
-            S_col.view(b, W, b).copy_(recv.permute(1, 0, 2))
+            c_l = torch.empty(2, b, **f32)
+            _call("nr_row_mean", _p(mbb), M, 2 * b, M, _p(c_l), st)
+            PT.view(W, b, b + 2)[:, :, b:] = c_l.t()
+            # ---- exchange 2b + 3: S_col[v_l, (q, a)] = S[(q, a), lo + v_l] = chunk r of rank q's transposed block;
+            #      the bank centrality of every sample (indexed by COLUMN in the neighbour loss) in the spare columns
+            recv = _all_to_all_blocks(PT.view(W, b, b + 2))                                  # [q, v_l, a | c_q]
+            S_col.view(b, W, b).copy_(recv[:, :, :b].permute(1, 0, 2))
+            cb = recv[:, :, b:].permute(2, 0, 1).reshape(2, B).contiguous()                  # [c_t2v ; c_v2t]
         else:
             p1, y1 = _fwd_dir(prec, Tl, V, tw_lc, tm_lc, vm, S_row, B, 1, None, 0, 0, 0)      # H(text_l, video)
             p2, y2 = _fwd_dir(prec, V, Tl, vw, vm, tm_lc, S_row, 1, B, None, 0, 0, 1)         # H(video, text_l)^T
@@ -288,10 +309,11 @@ class ShardedHeadFunction(torch.autograd.Function):
             pD, yD = _fwd_dir(prec, Vl, MT, vw_lc, vm_lc, mtm, mb_v2t, M, 1, None, 0, 0, 0)
             pC, yC = _fwd_dir(prec, MT, Vl, tw_mb, mtm, vm_lc, mb_v2t, 1, M, None, 0, 0, 1)
         ctx.fusedk = fusedk
-        c_l = torch.empty(2, b, **f32)
-        _call("nr_row_mean", _p(mbb), M, 2 * b, M, _p(c_l), st)
-        # ---- exchange 3: bank centrality of every sample (indexed by COLUMN in the neighbour loss)
-        cb = _gather(c_l.unsqueeze(0)).permute(1, 0, 2).reshape(2, B).contiguous()       # [c_t2v ; c_v2t]
+        if not fusedk:
+            c_l = torch.empty(2, b, **f32)
+            _call("nr_row_mean", _p(mbb), M, 2 * b, M, _p(c_l), st)
+            # ---- exchange 3: bank centrality of every sample (indexed by COLUMN in the neighbour loss)
+            cb = _gather(c_l.unsqueeze(0)).permute(1, 0, 2).reshape(2, B).contiguous()       # [c_t2v ; c_v2t]
         if pro.global_done is not None:                  # G, G^T and the Sinkhorn duals from the detached branch
             torch.cuda.current_stream().wait_event(pro.global_done)
             pro.global_done = None
@@ -451,13 +473,21 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
           0, _p(dmean_t), st, launches=2)
     _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), b, d, cs, V.rows, _p(dgl[1]),
           0, _p(dmean_v), st, launches=2)
-    # ---- exchange 4: dc, d logit_scale, d mean_text (every rank's centrality weights read the global text mean)
-    dist.all_reduce(z[:d + 2 * B + 1], op=dist.ReduceOp.SUM)
-    dc_l = dc[:, lo:lo + b].contiguous()                           # this rank's samples
-    # ---- exchange 4b: dS_col entries belong to the text rows of other ranks: inverse all-to-all, then
-    #      dP[a, (r, v)] = dS_row[a, (r, v)] + recv[r, v, a]
-    recv = _all_to_all_blocks(dS_col.view(b, W, b).permute(1, 0, 2))                         # [r, v, a]
-    dP = dS_row.view(b, W, b) + recv.permute(2, 0, 1)
+    # ---- exchange 4 (ONE all-to-all): to rank q go the dS_col block whose text rows q owns, this rank's share of
+    #      dc for q's samples, and this rank's d mean_text / d logit_scale (every rank's centrality weights read the
+    #      global text mean); the receiver sums the tails over ranks:  dP[a, (r, v)] = dS_row[a, (r, v)] + recv[r, v, a]
+    bb = b * b
+    send = torch.empty(W, bb + 2 * b + d + 1, **f32)
+    send[:, :bb].view(W, b, b).copy_(dS_col.view(b, W, b).permute(1, 0, 2))
+    send[:, bb:bb + 2 * b].view(W, 2, b).copy_(dc.view(2, W, b).permute(1, 0, 2))
+    send[:, bb + 2 * b:bb + 2 * b + d] = dmean_t
+    send[:, bb + 2 * b + d:] = z[d + 2 * B:d + 2 * B + 1]
+    recv = _all_to_all_blocks(send)                                                          # [r, (v, a) | tails]
+    tail = recv[:, bb:].sum(0)
+    dc_l = tail[:2 * b].view(2, b).contiguous()                    # this rank's samples, summed over ranks
+    dmean_t.copy_(tail[2 * b:2 * b + d])
+    z[d + 2 * B:d + 2 * B + 1].copy_(tail[2 * b + d:])             # d logit_scale (returned by the caller)
+    dP = dS_row.view(b, W, b) + recv[:, :bb].view(W, b, b).permute(2, 0, 1)
     dP = dP.view(b, B)
     # global similarity: dG has a row block (direction 1) and a column block (direction 2) on this rank; its two
     # library GEMMs run on their own branch next to the contraction (buffers allocated here, before the fork)
