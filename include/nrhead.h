@@ -70,6 +70,17 @@ int nr_prep_tokens_split(const float* x, int64_t rows, int64_t d, float* xn_f32,
 int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* dxn, const float* add_vec,
                        const int64_t* mask, int64_t rows, int64_t d, float* dx, int accumulate, void* stream);
 
+/* ---- small exact-fp32 products (CUDA cores) --------------------------------------------------------------------
+ * nr_matmul_f32: out[M,N] (+)= op(A)[M,K] X[K,N]; transA != 0: A is stored [K, M].  The global-feature gradients
+ *   dgT = dG gV, dgV = dG^T gT (autograd of modeling.py:516-539 with one global token per sample).
+ * nr_matvec_small: out = A (x + x2) (trans == 0, A [rows, cols]) or A^T (x + x2); x2 nullable; rows, cols <= 32.
+ *   The 5 x 4 combination of the raw row sums into [total, centrality, uniform, neighbor, kl] (modeling.py:353-358)
+ *   and its backward. */
+int nr_matmul_f32(const float* A, int64_t lda, int transA, const float* X, int64_t ldx, int64_t M, int64_t K, int64_t N,
+                  float* out, int64_t ldo, int accumulate, void* stream);
+int nr_matvec_small(const float* A, int64_t rows, int64_t cols, int trans, const float* x, const float* x2, float* out,
+                    void* stream);
+
 /* ---- tcgen05 GEMMs of the token-weight MLPs (reference modeling.py:137-153, used :485-492) -------------------------
  * Linear(D -> H) + ReLU + Linear(H -> 1) per token, then masked softmax over the tokens of a sample.  bf16
  * operands, fp32 accumulation; operands are consumed AS STORED (K-major or MN-major TMA tiles), no transposes.

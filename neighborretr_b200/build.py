@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnrhead.so")
 SOURCES = ["api.cu", "prep.cu", "rowloss.cu", "sinkhorn.cu", "eval.cu", "multisent.cu", "maxsim_simt.cu", "maxsim_tc.cu",
-           "maxsim2_tc.cu", "maxsim2_bwd_tc.cu", "maxsim_api.cu", "gemm_tc.cu"]
+           "maxsim2_tc.cu", "maxsim2_bwd_tc.cu", "maxsim_api.cu", "gemm_tc.cu", "linalg.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

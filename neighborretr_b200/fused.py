@@ -195,7 +195,8 @@ class HeadFunction(torch.autograd.Function):
                       0, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[1]), _p(nbr[1]), _p(saved[1]), _stream())
         _call("nr_vec_sums", _p(row_out), 8, B, None, _p(sums), st)
         # [total, centrality, uniform, neighbor, kl] = M54 @ (sums_dir1 + sums_dir2);  sums order: c, n, kl, u
-        out5 = m54 @ (sums[:4] + sums[4:])
+        out5 = torch.empty(5, **f32)
+        _call("nr_matvec_small", _p(m54), 5, 4, 0, _p(sums), _p(sums[4:]), _p(out5), st)
         ctx.hp = hp
         ctx.objs = (T, V, MT, MV)
         # the masks are only read by the one-direction backward kernels (the fused path folded them into the operand
@@ -220,7 +221,8 @@ class HeadFunction(torch.autograd.Function):
         nt, nv = T.n, V.n
         f32 = dict(dtype=torch.float32, device=dev)
         # ---- every buffer of the backward, allocated on the main stream before any fork
-        gscale = m54.t() @ _f32c(g5)                                  # upstream multipliers of the raw row terms
+        gscale = torch.empty(4, **f32)                                # upstream multipliers of the raw row terms
+        _call("nr_matvec_small", _p(m54), 5, 4, 1, _p(_f32c(g5)), None, _p(gscale), _stream())
         # one zero-fill: [dtn | dvn | dc_t2v | dc_v2t | dw_t | dw_v | dtw | dvw | dtw_mb | dvw_mb | dls]
         # (the token gradients first: their red.global.add.v4 needs 16-byte alignment)
         nw = tw.numel() + vw.numel() + tw_mb.numel() + vw_mb.numel()
@@ -266,13 +268,13 @@ class HeadFunction(torch.autograd.Function):
                     ev = torch.cuda.Event()
                     ev.record()
                     if need[2]:
-                        torch.mm(dG, v2, out=dgt)
+                        _call("nr_matmul_f32", _p(dG), B, 0, _p(v2), d, B, B, d, _p(dgt), d, 0, _stream())
                     _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs,
                           T.rows, _p(dgt), 1, _p(dmean[0]), _stream())
                     return ev
                 torch.cuda.current_stream().wait_event(ev_dG)
                 if need[3]:
-                    torch.mm(dG.t(), g2, out=dgv)
+                    _call("nr_matmul_f32", _p(dG), B, 1, _p(g2), d, B, B, d, _p(dgv), d, 0, _stream())
                 _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows,
                       _p(dgv), 1, _p(dmean[1]), _stream())
                 return None

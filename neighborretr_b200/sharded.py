@@ -336,7 +336,8 @@ class ShardedHeadFunction(torch.autograd.Function):
         # ---- exchange 4: loss partial sums
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         m54 = _combine_matrix(B, wu, wn, wkl, dev)
-        out5 = m54 @ (sums[:4] + sums[4:])
+        out5 = torch.empty(5, **f32)
+        _call("nr_matvec_small", _p(m54), 5, 4, 0, _p(sums), _p(sums[4:]), _p(out5), st)
         if a2a:
             pro.gather_text_async()
         ctx.hp, ctx.dims = hp, (W, r, b, B, lo, M, d, nt, nv)
@@ -359,7 +360,8 @@ class ShardedHeadFunction(torch.autograd.Function):
         dev = S_row.device
         st = _stream()
         f32 = dict(dtype=torch.float32, device=dev)
-        gscale = m54.t() @ _f32c(g5)
+        gscale = torch.empty(4, **f32)
+        _call("nr_matvec_small", _p(m54), 5, 4, 1, _p(_f32c(g5)), None, _p(gscale), st)
         # [dmean_text | dc_t2v | dc_v2t | dls | dw_t | dw_v]  (dmean first: it is read with 16-byte loads)
         z = torch.zeros(d + 2 * B + 1 + 2 * b, **f32)
         dcs, dls, dw = z[d:d + 2 * B + 1], z[d + 2 * B:d + 2 * B + 1], z[d + 2 * B + 1:].view(2, b)
@@ -497,8 +499,8 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
     def global_path():
         dG[lo:lo + b] += dG1
         dG[:, lo:lo + b] += dG2.t()
-        torch.mm(dG, v2, out=dg_all)                               # partial over ranks
-        torch.mm(dG.t(), g2, out=dv_all)
+        _call("nr_matmul_f32", _p(dG), B, 0, _p(v2), d, B, B, d, _p(dg_all), d, 0, _stream())     # partial over ranks
+        _call("nr_matmul_f32", _p(dG), B, 1, _p(g2), d, B, B, d, _p(dv_all), d, 0, _stream())
         dg_all[lo:lo + b] += dgl[0]
         dv_all[lo:lo + b] += dgl[1]
     # ---- token-pair products: text rows complete locally, video rows partial over ranks

@@ -78,3 +78,25 @@ def test_token_softmax_and_cast():
     y = torch.empty(x.numel(), dtype=torch.bfloat16, device="cuda")
     _call("nr_cast_bf16", _p(x.contiguous()), _p(y), x.numel(), _stream())
     assert torch.equal(y, x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,K,N,trans", [(128, 128, 512, 0), (128, 128, 512, 1), (40, 40, 64, 1), (1024, 1024, 512, 0),
+                                         (70, 33, 20, 0), (33, 70, 20, 1)])
+def test_small_fp32_matmul(M, K, N, trans):
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.randn((K, M) if trans else (M, K), generator=g).cuda(); X = torch.randn(K, N, generator=g).cuda()
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _call("nr_matmul_f32", _p(A), A.shape[1], trans, _p(X), N, M, K, N, _p(out), N, 0, _stream())
+    want = (A.double().t() if trans else A.double()) @ X.double()
+    assert (out.double() - want).abs().max().item() < 1e-5 * want.abs().max().item()
+    _call("nr_matmul_f32", _p(A), A.shape[1], trans, _p(X), N, M, K, N, _p(out), N, 1, _stream())
+    assert (out.double() - 2 * want).abs().max().item() < 2e-5 * want.abs().max().item()
+
+
+def test_small_matvec():
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(5, 4, generator=g).cuda(); x = torch.randn(8, generator=g).cuda(); y = torch.randn(5, generator=g).cuda()
+    o = torch.empty(5, device="cuda"); ot = torch.empty(4, device="cuda")
+    _call("nr_matvec_small", _p(A), 5, 4, 0, _p(x), _p(x[4:]), _p(o), _stream())
+    _call("nr_matvec_small", _p(A), 5, 4, 1, _p(y), None, _p(ot), _stream())
+    assert torch.allclose(o, A @ (x[:4] + x[4:]), atol=1e-6) and torch.allclose(ot, A.t() @ y, atol=1e-6)
