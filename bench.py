@@ -95,7 +95,8 @@ def flops_maxsim(rx, ry, nt, nv, d=D):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(shape, steps, warmup, b=B_PER_GPU):
+def cpu_reference_steps(shape, steps, warmup, b=None):
+    b = b or B_PER_GPU
     from oracle import head as O
     nt, nv, mrows = synth.SHAPES[shape]
     threads = os.cpu_count() or 1
@@ -377,6 +378,37 @@ def run_ours(args):
     timed(lambda: step(resident, False), ksteps)
     kt = ops.KERNEL_TIMER.collect()
     ops.KERNEL_TIMER.disable()
+    # ---- the module API a trainer uses (model.head_forward(...) -> loss.backward()) with head_graph on: one graph
+    #      replay per step behind autograd (graph.GraphedHead), host buffers in, losses read back
+    extra = {}
+    if not args.no_extra:
+        reset_bank()
+        model.head_graph = True
+        for _ in range(3):
+            step(pinned, True)
+        ms_api = timed(lambda: step(pinned, True), args.steps)
+        model.head_graph = False
+        extra["module_api_graph_steps_per_s"] = args.steps / (ms_api * 1e-3)
+        # ---- the other arithmetic modes of the same step (graph replay, inputs resident)
+        from neighborretr_b200 import selfcheck
+        from neighborretr_b200.graph import FIELDS as _F, GraphedHeadStep as _G
+        for mode in ("bf16x3", "fp32"):
+            if mode == args.precision or (mode == "fp32" and (world > 1 or args.shape != "msrvtt" or B_PER_GPU > 256)):
+                continue
+            m2 = selfcheck.make_model(cfg, dev, mode)
+            selfcheck.set_bank(m2, bank, dev)
+            g2 = _G(m2, [resident[f] for f in _F], warmup=3)
+            rl = [resident[f] for f in _F]
+            for _ in range(2):
+                g2(*rl)
+            nst = max(3, args.steps // 2)
+            ms2 = timed(lambda: g2(*rl), nst)
+            extra[mode] = {"steps_per_s": nst / (ms2 * 1e-3), "ms_per_step": ms2 / nst,
+                           "losses": [float(x) for x in g2.losses.tolist()]}
+            if world > 1:
+                g2.graph.reset()
+            del g2, m2
+
     def finish():
         """Multi-rank exit: captured NCCL work keeps the communicator busy, and destroy_process_group() then
         blocks; release the graph, synchronise, and leave without tearing NCCL down."""
@@ -438,6 +470,14 @@ def run_ours(args):
     }
     if world == 1:
         line["eval"] = run_eval_bench(model, dev, 10)
+        ev = line["eval"]
+        ach = ev["flops"] / (ev["resident_ms"] * 1e-3) / 1e12
+        ev["roofline"] = {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                          "frac": ach / pk["bf16_burst"],
+                          "note": "2*Q*N*Nt*Nv*D flops of the similarity matrix / the whole resident eval call (token-weight "
+                                  "MLPs, preparation, max-sim, two rank-count passes, D2H of the counts); peak = burst "
+                                  "bf16 (a ~1 ms call)"}
+    line["modes"] = extra
     if world == 1 and not args.no_cpu_baseline:
         ems, er1, er2 = eval_cpu_baseline()
         line["eval"]["cpu_baseline_ms"] = ems
@@ -451,6 +491,7 @@ def run_ours(args):
 
 
 def main():
+    global B_PER_GPU
     if os.environ.get("NR_DEBUG_HANG"):
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["NR_DEBUG_HANG"]), exit=True)
@@ -468,8 +509,18 @@ def main():
                     help="before timing, compare the (graph-captured) step with the single-process full-batch head "
                          "(default: on when N > 1)")
     ap.add_argument("--no-check", dest="check", action="store_const", const=0)
+    ap.add_argument("--per-gpu-batch", type=int, default=128,
+                    help="samples per GPU (BASELINE configs[4]: 1024 per GPU on 8 GPUs = global batch 8192)")
+    ap.add_argument("--workload", default="head", choices=["head", "eval"],
+                    help="head: fwd+bwd steps/s (the metric BASELINE.json quotes); eval: column-sharded similarity + "
+                         "R@K latency on an --eval-size x --eval-size test set (configs[4]: 100000)")
+    ap.add_argument("--eval-size", type=int, default=100000)
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra precision-mode / module-API measurements")
     args = ap.parse_args()
-    if args.impl == "reference":
+    B_PER_GPU = args.per_gpu_batch
+    if args.workload == "eval":
+        run_eval_workload(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         if not torch.cuda.is_available():
