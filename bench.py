@@ -206,6 +206,105 @@ def run_eval_bench(model, dev, steps, nq=1000):
     return out
 
 
+def run_eval_workload(args):
+    """BASELINE.json configs[4], evaluation half: N x N test set (default 100 000) with the video gallery sharded by
+    column over the ranks (evaluator.sharded_retrieval): per-rank similarity block S[:, cols_r] on the tensor cores,
+    per-shard rank counts all-reduced, per-shard top-10 merged.  One "step" = one full evaluation (t2v and v2t
+    metrics + merged top-10), features resident in HBM; `e2e` repeats it with the features copied from pinned host
+    memory inside the timed region.  --impl reference: the oracle's tiled evaluation on the host cores over a bounded
+    sample, scaled by the number of query x gallery pairs."""
+    import torch.distributed as dist
+    n = args.eval_size
+    nt, nv, _ = synth.SHAPES[args.shape]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    cfg_line = {"workload": f"{args.shape}_eval_{n}x{n}_column_sharded", "queries": n, "gallery": n, "words": nt,
+                "frames": nv, "dim": D, "topk": 10, "parallelism": f"column shards x{world}",
+                "l2": "inputs (GBs of features) larger than L2"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import head as O
+        from oracle import metrics as OM
+        ns = 1000
+        torch.set_num_threads(os.cpu_count() or 1)
+        h = synth.make_batch(ns, nt, nv, d=D, seed=77)
+        params = synth.make_mlp_params(d=D)
+        t0 = time.perf_counter()
+        sim, sim_t = O.eval_similarity(h.text_feat, h.video_feat, h.text_mask, h.video_mask, params)
+        OM.compute_metrics(sim); OM.compute_metrics(sim_t)
+        ms = (time.perf_counter() - t0) * 1e3 * (n / ns) ** 2
+        print(json.dumps({"impl": "reference", "metric": "eval_sim_rank_latency_ms", "value": ms, "unit": "ms",
+                          "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": ms, "higher_is_better": False,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_line,
+                          "cpu_baseline": {"value": ms, "unit": "ms", "cores": os.cpu_count(), "kind": "port",
+                                           "sample": f"{ns} x {ns} tiled evaluation + both metric passes, scaled by "
+                                                     f"({n}/{ns})^2 pairs"},
+                          "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from neighborretr_b200 import ops, selfcheck
+    from neighborretr_b200.evaluator import sharded_retrieval
+    model = selfcheck.make_model(synth.default_config(world_size=world, local_rank=local, rank=rank), dev, args.precision).eval()
+    # every rank holds all features, as after the reference's eval gather (training/evaluator.py:173-189)
+    g = torch.Generator().manual_seed(77)
+    chunk = 10000
+    tf = torch.empty(n, nt, D, device=dev); vf = torch.empty(n, nv, D, device=dev)
+    tm = torch.empty(n, nt, dtype=torch.int64, device=dev); vm = torch.empty(n, nv, dtype=torch.int64, device=dev)
+    for c0 in range(0, n, chunk):
+        hb = synth.make_batch(min(chunk, n - c0), nt, nv, d=D, seed=77 + c0)
+        tf[c0:c0 + chunk] = hb.text_feat.to(dev); vf[c0:c0 + chunk] = hb.video_feat.to(dev)
+        tm[c0:c0 + chunk] = hb.text_mask.to(dev); vm[c0:c0 + chunk] = hb.video_mask.to(dev)
+
+    def once():
+        return sharded_retrieval(model, tm, vm, tf, vf, topk=10)
+
+    def sync_all():
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        r = once()
+    steps = max(1, min(args.steps, 5))
+    ops.LAUNCHES["count"] = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    evs = []
+    for _ in range(steps):
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record(); r = once(); e_.record()
+        evs.append((s_, e_))
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.LAUNCHES["count"]
+    t = torch.tensor([sum(a.elapsed_time(b_) for a, b_ in evs)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    if rank == 0:
+        pk = peaks()
+        fl = flops_maxsim(n, n, nt, nv) / world                      # per rank: its column shard
+        ach = fl / (ms * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "eval_sim_rank_latency_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else args.precision, "data": "synthetic",
+            "config": cfg_line, "t2v_R1": r[0]["R1"], "v2t_R1": r[1]["R1"], "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"kernel": "nr_maxsim2_fwd", "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
+                         "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                         "note": "per-rank similarity flops 2*Q*(N/W)*Nt*Nv*D / the WHOLE evaluation call (MLPs, "
+                                 "preparation, contraction, rank counts, top-k, collectives)"}}), flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
 def workload_config(shape, world):
     """The workload both arms run (the arithmetic type of an arm is its `dtype`, not part of the workload)."""
     nt, nv, mrows = synth.SHAPES[shape]
@@ -375,7 +474,14 @@ def run_ours(args):
     kname = "nr_maxsim2_fwd" if (args.precision == "bf16" and (args.bwd_precision or "bf16") == "bf16") else "nr_maxsim_fwd"
     ops.KERNEL_TIMER.enable(kname)
     ksteps = min(args.steps, 10)
-    timed(lambda: step(resident, False), ksteps)
+
+    def held_step():
+        # park the stream on a spin kernel so that the host is ahead of the device when the timed launch is enqueued:
+        # the event pair then brackets GPU time only (see ops._KernelTimer)
+        ops.KERNEL_TIMER.hold(4.0)
+        step(resident, False)
+
+    timed(held_step, ksteps)
     kt = ops.KERNEL_TIMER.collect()
     ops.KERNEL_TIMER.disable()
     # ---- the module API a trainer uses (model.head_forward(...) -> loss.backward()) with head_graph on: one graph
@@ -465,7 +571,8 @@ def run_ours(args):
                                      "HBM once, the 27e6 B of saved max/arg-max and similarities stay in L2",
                      "launches_timed": n_l, "avg_launch_ms": kt["ms"] / n_l,
                      "share_of_step": (kt["ms"] / ksteps) / (ms_total / args.steps) if ms_total else None,
-                     "timed_in": "eager steps on the launching stream (events cannot be read inside a graph replay)",
+                     "timed_in": "eager steps on the launching stream (events cannot be read inside a graph replay), the "
+                                 "stream parked on a spin kernel first so that the event pair brackets device time only",
                      "peak_source": pk["source"] + " bf16_tflops_sustained (kernel timed inside the step)"},
     }
     if world == 1:

@@ -74,6 +74,11 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_tc_kernel(const __grid_constant__ GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t g_smem_raw[];
   // keep the shared-space provenance of the pointer (offset add, no integer round trip): STS/LDS, not generic ST/LD
@@ -243,6 +248,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_bf16_tc_kernel(const __grid
             } else {
               for (int e = 0; e < 16 && n + e < a.N; ++e) dst[e] = __uint_as_float(v[e]);
             }
+          } else if (n + 16 <= a.N) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              red_add_v4_f32(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                             __uint_as_float(v[e + 3]));
           } else {
             for (int e = 0; e < 16 && n + e < a.N; ++e) red_add_f32(dst + e, __uint_as_float(v[e]));
           }
@@ -287,6 +297,8 @@ static int gemm_launch(GemmArgs& a, const void* A, int64_t lda, const void* B, i
   NR_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && lda % 8 == 0 && ldb % 8 == 0,
                "nr_gemm: operands must be 16-byte aligned with leading dimensions that are multiples of 8");
   NR_CHECK_ARG(a.N % 16 == 0, "nr_gemm: N=%d must be a multiple of 16", a.N);
+  NR_CHECK_ARG(a.epi == G_EPI_RELU_BF16 || (((uintptr_t)a.c_f32 & 15) == 0 && a.ldc % 4 == 0),
+               "nr_gemm: fp32 output must be 16-byte aligned with ldc %% 4 == 0");
   a.bn = a.N < G_BN ? a.N : G_BN;
   a.n_mt = (a.M + G_BM - 1) / G_BM;
   a.n_nt = (a.N + G_BN - 1) / G_BN;

@@ -100,10 +100,19 @@ class ForkJoin:
 
 
 class _KernelTimer:
-    """CUDA-event timing of one C-ABI entry point on the launching stream (bench.py roofline)."""
+    """CUDA-event timing of one C-ABI entry point on the launching stream (bench.py roofline).
+
+    An event pair around a launch measures the kernel only if the GPU is still busy when the first event is
+    enqueued; otherwise the host time between the two record() calls (building the argument block, encoding tensor
+    maps, the launch itself: 10-20 us through ctypes) is counted as kernel time.  `hold(stream)` therefore parks the
+    stream on a spin kernel first, so that the host runs ahead of the device through the whole timed step."""
 
     def __init__(self):
         self.name, self.events = None, []
+
+    @staticmethod
+    def hold(ms=3.0):
+        torch.cuda._sleep(int(ms * 1.9e6))          # cycles at ~1.9 GHz
 
     def enable(self, name):
         self.name, self.events = name, []

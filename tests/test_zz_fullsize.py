@@ -32,6 +32,28 @@ def _params_cuda(params):
     return {k: {n: v.cuda() for n, v in sd.items()} for k, sd in params.items()}
 
 
+_FLOOR = {}
+
+
+def _fp32_vs_fp64_floor(b, shape):
+    """Feature-gradient rel-L2 between the oracle in fp32 and in float64 on the same inputs: how far two correct
+    implementations with different rounding are apart (the gradient of a max goes to ONE token; a pair of candidates
+    closer than the arithmetic's noise flips it).  Cached per case."""
+    key = (b, shape)
+    if key not in _FLOOR:
+        nt, nv, mrows = synth.SHAPES[shape]
+        h = synth.make_batch(b, nt, nv, d=512, seed=1234).to("cuda")
+        bank = _bank_cuda(synth.make_bank(mrows, nt, nv, d=512))
+        params = _params_cuda(synth.make_mlp_params(d=512))
+        cfg = synth.default_config()
+        _, g32 = oracle_losses(h, bank, params, cfg)
+        _, g64 = oracle_losses(h, bank, params, cfg, dtype=torch.float64)
+        _FLOOR[key] = max(rel_l2(g32[k], g64[k]) for k in ("text", "video"))
+        del g32, g64
+        torch.cuda.empty_cache()
+    return _FLOOR[key]
+
+
 def _head_case(b, shape, precision):
     nt, nv, mrows = synth.SHAPES[shape]
     h = synth.make_batch(b, nt, nv, d=512, seed=1234)
@@ -55,6 +77,12 @@ def _check_head(losses, grads, ref, rgrads, precision, tag):
     gerr = {k: rel_l2(grads[k], rgrads[k]) for k in ("text", "video", "gt", "gv")}
     print(f"{tag}[{precision}] losses {losses.tolist()} max rel err {lerr:.2e}; grad rel-L2 {gerr}")
     np.testing.assert_allclose(losses.numpy(), ref.numpy(), rtol=ltol)
+    if precision == "bf16x3":
+        # against an fp32 reference the bar cannot be below what separates two correct fp32-class implementations
+        b_, shape_ = tag
+        floor = _fp32_vs_fp64_floor(b_, shape_)
+        print(f"   fp32-oracle vs float64-oracle feature-gradient rel-L2 (noise floor): {floor:.2e}")
+        gtol = max(gtol, 2.5 * floor + 1e-3)
     for k, e in gerr.items():
         assert e < gtol, (k, e)
     ls_err = abs(grads["logit_scale"].item() / rgrads["logit_scale"].item() - 1)
@@ -63,12 +91,12 @@ def _check_head(losses, grads, ref, rgrads, precision, tag):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_cfg2_msrvtt_head_global_batch_1024(precision):
-    _check_head(*_head_case(1024, "msrvtt", precision), precision, "cfg2 B=1024")
+    _check_head(*_head_case(1024, "msrvtt", precision), precision, (1024, "msrvtt"))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "bf16x3"])
 def test_cfg3_activitynet_head_b128(precision):
-    _check_head(*_head_case(128, "activitynet", precision), precision, "cfg3 ACT b=128")
+    _check_head(*_head_case(128, "activitynet", precision), precision, (128, "activitynet"))
 
 
 def test_cfg4_eval_1000x1000_similarity_and_ranks():
