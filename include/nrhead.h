@@ -92,6 +92,8 @@ int nr_matvec_small(const float* A, int64_t rows, int64_t cols, int trans, const
  * nr_mlp_bwd_dx : dx [T, D] (+)= dh [T, H] W1 [H, D]       (accumulate != 0: split-K with red.add into dx)
  * nr_mlp_bwd_dw1: dw1 [H, D] += dh^T [H, T] x [T, D]       (split-K over the tokens, red.add: zero dw1 first) */
 int nr_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* up to 8 such copies in one launch (src[i] -> dst[i], n[i] elements; host arrays of pointers / sizes) */
+int nr_cast_bf16_multi(const float* const* src, void* const* dst, const int64_t* n, int n_segments, void* stream);
 int nr_mlp_fwd(const void* x_bf16, int64_t T, int64_t D, const void* w1_bf16, int64_t H, const float* b1,
                const float* w2, void* h_bf16, float* logits, void* stream);
 int nr_token_softmax(const float* logits, const float* b2, const int64_t* mask_a, const int64_t* mask_b, int64_t Ra,
@@ -99,6 +101,16 @@ int nr_token_softmax(const float* logits, const float* b2, const int64_t* mask_a
 int nr_mlp_bwd_dx(const void* dh_bf16, int64_t T, int64_t H, const void* w1_bf16, int64_t D, float* dx, int accumulate,
                   void* stream);
 int nr_mlp_bwd_dw1(const void* dh_bf16, int64_t T, int64_t H, const void* x_bf16, int64_t D, float* dw1, void* stream);
+/* The text and the video MLP in ONE launch each way (a persistent grid per modality would serialise on shared memory):
+ * nr_mlp_fwd_pair = nr_mlp_fwd of every side; nr_mlp_bwd_pair = nr_mlp_bwd_dw1 over T tokens (dw1 nullable) and
+ * nr_mlp_bwd_dx (accumulating; dx nullable, zero on entry) over the first T_dx tokens of every side. */
+typedef struct {
+  const void* x_bf16; const void* w1_bf16; int64_t T;
+  const float* b1; const float* w2; void* h_bf16; float* logits;       /* forward */
+  const void* dh_bf16; float* dw1; float* dx; int64_t T_dx;            /* backward */
+} nr_mlp_side;
+int nr_mlp_fwd_pair(const nr_mlp_side* sides, int n_sides, int64_t D, int64_t H, void* stream);
+int nr_mlp_bwd_pair(const nr_mlp_side* sides, int n_sides, int64_t D, int64_t H, void* stream);
 
 /* chunks of 32 token rows: column count of the partial-sum buffer of nr_token_weights_bwd */
 int64_t nr_mlp_chunks(int64_t T);

@@ -29,10 +29,13 @@ SIGNATURES = {
     "nr_matmul_f32": (_I, [_P, _I64, _I, _P, _I64, _I64, _I64, _I64, _P, _I64, _I, _P]),
     "nr_matvec_small": (_I, [_P, _I64, _I64, _I, _P, _P, _P, _P]),
     "nr_cast_bf16": (_I, [_P, _P, _I64, _P]),
+    "nr_cast_bf16_multi": (_I, [_P, _P, _P, _I, _P]),
     "nr_mlp_fwd": (_I, [_P, _I64, _I64, _P, _I64, _P, _P, _P, _P, _P]),
     "nr_token_softmax": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "nr_mlp_bwd_dx": (_I, [_P, _I64, _I64, _P, _I64, _P, _I, _P]),
     "nr_mlp_bwd_dw1": (_I, [_P, _I64, _I64, _P, _I64, _P, _P]),
+    "nr_mlp_fwd_pair": (_I, [_P, _I, _I64, _I64, _P]),
+    "nr_mlp_bwd_pair": (_I, [_P, _I, _I64, _I64, _P]),
     "nr_mlp_chunks": (_I64, [_I64]),
     "nr_token_weights_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
     "nr_token_weights_bwd": (_I, [_P, _I, _P, _P, _P, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
@@ -73,6 +76,12 @@ class MaxSim2Problem(ctypes.Structure):
     _fields_ = [("x_bf16", _P), ("y_bf16", _P), ("wx", _P), ("wy", _P), ("Rx", _I64), ("Ry", _I64), ("alpha", _F),
                 ("out", _P), ("out_sr", _I64), ("out_sc", _I64), ("out2", _P), ("out2_sr", _I64), ("out2_sc", _I64),
                 ("pmax_x", _P), ("ystar", _P), ("pmax_y", _P), ("xstar", _P)]
+
+
+class MlpSide(ctypes.Structure):
+    """nr_mlp_side of include/nrhead.h (field order and types must match)."""
+    _fields_ = [("x_bf16", _P), ("w1_bf16", _P), ("T", _I64), ("b1", _P), ("w2", _P), ("h_bf16", _P), ("logits", _P),
+                ("dh_bf16", _P), ("dw1", _P), ("dx", _P), ("T_dx", _I64)]
 
 
 class MaxSim2BwdJob(ctypes.Structure):

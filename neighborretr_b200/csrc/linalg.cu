@@ -10,60 +10,72 @@
 
 namespace nr {
 
-// 64x64 output tile per CTA, 4x4 outputs per thread, k-chunks of 16 through shared memory
+// 32x64 output tile per CTA (256 threads, 2x4 outputs each), k-chunks of 32 staged in shared memory with the next
+// chunk's global loads in flight during the FMAs (one barrier per chunk).  These products are tiny (B = 128: 17
+// MFLOP) and sit on the backward's critical path, so the kernel is sized for latency: many small CTAs.
 __global__ void __launch_bounds__(256)
 matmul_f32_kernel(const float* __restrict__ A, int64_t lda, int transA, const float* __restrict__ X, int64_t ldx, int M,
                   int K, int N, float* __restrict__ out, int64_t ldo, int accumulate) {
-  __shared__ float As[16][68], Xs[16][68];
-  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64, tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
+  __shared__ float As[2][32][33];      // [k][m]
+  __shared__ float Xs[2][32][68];      // [k][n]
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 64, tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;               // outputs: rows ty*2..+1, columns tx*4..+3
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float ra[4], rx[8];
+  auto gload = [&](int k0) {
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[p][q] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    if (transA) {             // A stored [K, M]
-      const int kk = tid >> 4, m4 = (tid & 15) * 4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int m = i0 + m4 + q, k = k0 + kk;
-        As[kk][m4 + q] = (m < M && k < K) ? A[(int64_t)k * lda + m] : 0.f;
-      }
-    } else {                  // A stored [M, K]
-      const int r = tid >> 2, c4 = (tid & 3) * 4;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int m = i0 + r, k = k0 + c4 + q;
-        As[c4 + q][r] = (m < M && k < K) ? A[(int64_t)m * lda + k] : 0.f;
-      }
+    for (int it = 0; it < 4; ++it) {                    // A chunk: 32 (m) x 32 (k)
+      const int e = it * 256 + tid;
+      int m, k;
+      if (transA) { k = e >> 5; m = e & 31; } else { m = e >> 5; k = e & 31; }
+      const bool ok = (i0 + m < M) && (k0 + k < K);
+      ra[it] = ok ? (transA ? A[(int64_t)(k0 + k) * lda + i0 + m] : A[(int64_t)(i0 + m) * lda + k0 + k]) : 0.f;
     }
-    {
-      const int kk = tid >> 4, n4 = (tid & 15) * 4;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int n = j0 + n4 + q, k = k0 + kk;
-        Xs[kk][n4 + q] = (n < N && k < K) ? X[(int64_t)k * ldx + n] : 0.f;
-      }
+    for (int it = 0; it < 8; ++it) {                    // X chunk: 32 (k) x 64 (n)
+      const int e = it * 256 + tid, k = e >> 6, n = e & 63;
+      rx[it] = (k0 + k < K && j0 + n < N) ? X[(int64_t)(k0 + k) * ldx + j0 + n] : 0.f;
     }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int e = it * 256 + tid;
+      int m, k;
+      if (transA) { k = e >> 5; m = e & 31; } else { m = e >> 5; k = e & 31; }
+      As[buf][k][m] = ra[it];
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int e = it * 256 + tid;
+      Xs[buf][e >> 6][e & 63] = rx[it];
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const bool more = k0 + 32 < K;
+    if (more) gload(k0 + 32);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[buf][k][ty * 2], a1 = As[buf][k][ty * 2 + 1];
+      const float4 b = *reinterpret_cast<const float4*>(&Xs[buf][k][tx * 4]);
+      acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+    }
+    if (more) sstore(buf ^ 1);
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Xs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
-    }
-    __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
+  for (int p = 0; p < 2; ++p)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int m = i0 + ty * 4 + p, n = j0 + tx * 4 + q;
+      const int m = i0 + ty * 2 + p, n = j0 + tx * 4 + q;
       if (m < M && n < N) {
         float* o = out + (int64_t)m * ldo + n;
         *o = accumulate ? *o + acc[p][q] : acc[p][q];
@@ -89,7 +101,7 @@ __global__ void matvec_small_kernel(const float* __restrict__ A, int rows, int c
 extern "C" int nr_matmul_f32(const float* A, int64_t lda, int transA, const float* X, int64_t ldx, int64_t M, int64_t K,
                              int64_t N, float* out, int64_t ldo, int accumulate, void* stream) {
   NR_CHECK_ARG(A && X && out && M > 0 && K > 0 && N > 0, "nr_matmul_f32: bad arguments");
-  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 31) / 32));
   nr::matmul_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, transA, X, ldx, (int)M, (int)K, (int)N, out, ldo,
                                                               accumulate);
   NR_CHECK_LAUNCH("nr_matmul_f32");

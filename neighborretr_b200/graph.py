@@ -18,6 +18,8 @@ selfcheck.py (bench.py --check, tests/dist_graph_check.py).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -109,7 +111,7 @@ class GraphedHeadStep:
             new_rows = (ia, ta, va, tma, vma)
         # With bf16 weight-MLP GEMMs the backward reads bf16 copies, never the bank itself: the FIFO update can then
         # leave the critical path and run on its own branch next to the backward.
-        early_fifo = self.world == 1 and m._mlp_precision() == "bf16"
+        early_fifo = self.world == 1 and m._mlp_precision() == "bf16" and os.environ.get("NR_EARLY_FIFO", "1") != "0"
         if early_fifo:
             main = torch.cuda.current_stream()
             self._fifo_stream.wait_stream(main)

@@ -178,23 +178,20 @@ class HeadMixin:
             # its forward stream, so the backward GEMMs overlap as well.
             pro = HeadPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, mb_feat_t, mb_feat_v,
                                mb_mask_t, mb_mask_v, hp, text_feat.requires_grad, video_feat.requires_grad)
-            with ops.ForkJoin(4) as fj:
-                main = fj.main
-                # one node per modality: batch tokens and bank tokens share the hidden buffer and the kernels
-                tw, tw_mb = ops.token_weights(self.text_weight_fc, text_feat, text_mask, lowp, mb_feat_t, mb_mask_t)
+            with ops.ForkJoin(3) as fj:
                 with fj.on(0):
-                    vw, vw_mb = ops.token_weights(self.video_weight_fc, video_feat, video_mask, lowp, mb_feat_v,
-                                                  mb_mask_v)
-                    vw.record_stream(main)
-                with fj.on(1):
                     pro.run_text_side()
-                with fj.on(2):
+                with fj.on(1):
                     pro.run_video_side()
-                with fj.on(3):
+                with fj.on(2):
                     pro.run_global()
+                # both modalities' weight MLPs (batch tokens and bank tokens share the hidden buffers and the kernels)
+                tw, tw_mb, vw, vw_mb = ops.token_weights_pair(self.text_weight_fc, self.video_weight_fc, text_feat,
+                                                              text_mask, video_feat, video_mask, lowp, mb_feat_t,
+                                                              mb_mask_t, mb_feat_v, mb_mask_v)
                 # the Sinkhorn duals are first needed by the row losses, after the token-pair contraction: the
                 # head node waits on this event there instead of joining the branch here
-                pro.global_done = fj.detach(3)
+                pro.global_done = fj.detach(2)
             out5, nbr = HeadFunction.apply(text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, ls, text_mask,
                                            video_mask, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp, pro)
             self.last_neighbors = (nbr[0], nbr[1])
@@ -255,19 +252,16 @@ class HeadMixin:
         # gathers, token preparation, centrality weights, global similarity + Sinkhorn: forked next to the MLPs
         pro = ShardedPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, self.mb_feat_t, self.mb_feat_v,
                               self.mb_mask_t, self.mb_mask_v, hp, idx_l=idx)
-        with ops.ForkJoin(4) as fj:
-            main = fj.main
-            with fj.on(3):
-                pro.run_global()             # first: Sinkhorn is the longest chain of the forward
-            pro.global_done = fj.detach(3)
+        with ops.ForkJoin(3) as fj:
             with fj.on(2):
-                pro.run_video_side()
+                pro.run_global()             # first: Sinkhorn is the longest chain of the forward
+            pro.global_done = fj.detach(2)
             with fj.on(1):
-                pro.run_text_side()
-            tw, tw_mb = ops.token_weights(tmlp, text_feat, text_mask, lowp, self.mb_feat_t, self.mb_mask_t)
+                pro.run_video_side()
             with fj.on(0):
-                vw, vw_mb = ops.token_weights(vmlp, video_feat, video_mask, lowp, self.mb_feat_v, self.mb_mask_v)
-                vw.record_stream(main)
+                pro.run_text_side()
+            tw, tw_mb, vw, vw_mb = ops.token_weights_pair(tmlp, vmlp, text_feat, text_mask, video_feat, video_mask, lowp,
+                                                          self.mb_feat_t, self.mb_mask_t, self.mb_feat_v, self.mb_mask_v)
         out5, nbr, text_all, video_all, tm_all, vm_all = ShardedHeadFunction.apply(
             text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, self.clip.logit_scale.exp(), text_mask, video_mask,
             self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v, hp, pro)

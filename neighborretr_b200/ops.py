@@ -6,6 +6,7 @@ of the path runs in libnrhead.so kernels.  Every op refuses CPU tensors — ther
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -65,16 +66,16 @@ class ForkJoin:
     Under CUDA-graph capture the side streams become parallel branches of the graph.  Callers allocate every buffer
     a branch touches BEFORE the fork, on the main stream (the caching allocator tracks one stream per block)."""
 
-    def __init__(self, n):
+    def __init__(self, n, offset=0):
+        """offset: use side streams [offset, offset + n) — a fork nested inside another fork's main section must not
+        reuse the outer fork's streams."""
         self.main = torch.cuda.current_stream()
-        key = (self.main.device.index, n)
         lst = _SIDE_STREAMS.get(self.main.device.index, [])
-        while len(lst) < n:
+        while len(lst) < offset + n:
             lst.append(torch.cuda.Stream(device=self.main.device))
         _SIDE_STREAMS[self.main.device.index] = lst
-        self.side = lst[:n]
+        self.side = lst[offset:offset + n]
         self.detached = set()
-        del key
 
     def __enter__(self):
         for s in self.side:
@@ -537,7 +538,7 @@ class _tf32:
 MLP_FP32, MLP_TF32, MLP_BF16 = 0, 1, 2
 # bf16 mode: the MLP GEMMs run on this repo's tcgen05 kernel (csrc/gemm_tc.cu); tests flip this to compare against the
 # library GEMMs
-USE_OWN_GEMM = True
+USE_OWN_GEMM = os.environ.get("NR_OWN_GEMM", "1") != "0"
 
 
 def mlp_mode(v):
@@ -657,6 +658,136 @@ class TokenWeightsFunction(torch.autograd.Function):
         dw2 = sums[H:2 * H].reshape(1, H) if need[6] else None
         db2 = sums[2 * H:] if need[7] else None
         return dx, None, None, None, dw1, db1, dw2, db2, None
+
+
+def _cast_multi(pairs):
+    """[(fp32 source, bf16 destination view)] -> one nr_cast_bf16_multi launch."""
+    n = len(pairs)
+    srcs = (ctypes.c_void_p * n)(*[p_[0].data_ptr() for p_ in pairs])
+    dsts = (ctypes.c_void_p * n)(*[p_[1].data_ptr() for p_ in pairs])
+    sizes = (ctypes.c_int64 * n)(*[p_[0].numel() for p_ in pairs])
+    _call("nr_cast_bf16_multi", ctypes.cast(srcs, ctypes.c_void_p), ctypes.cast(dsts, ctypes.c_void_p),
+          ctypes.cast(sizes, ctypes.c_void_p), n, _stream())
+
+
+class TokenWeightsPairFunction(torch.autograd.Function):
+    """The text AND the video token-weight MLP of a head step (batch + bank tokens each) as ONE autograd node on the
+    tcgen05 GEMM (bf16 mode): one operand-copy launch, one forward GEMM launch over both modalities, two softmax
+    launches; backward: the hidden-layer pass per modality, then ONE GEMM launch for dW1 and dx of both.  A persistent
+    GEMM grid per modality would serialise on shared memory and pay its ramp-up four times per step."""
+
+    @staticmethod
+    def forward(ctx, xt, mt, xtb, mtb, xv, mv, xvb, mvb, w1t, b1t, w2t, b2t, w1v, b1v, w2v, b2v):
+        _req_cuda(xt, xtb, xv, xvb, w1t, w1v)
+        dev = xt.device
+        D, H = xt.shape[2], w1t.shape[0]
+        sides, casts = [], []
+        for (xa, ma, xb, mb, w1, b1, w2, b2) in ((xt, mt, xtb, mtb, w1t, b1t, w2t, b2t), (xv, mv, xvb, mvb, w1v, b1v, w2v, b2v)):
+            Ra, N = xa.shape[0], xa.shape[1]
+            Rb = xb.shape[0] if xb is not None else 0
+            if Rb and tuple(xb.shape[1:]) != (N, D):
+                raise RuntimeError("token_weights: batch and bank tokens differ in shape")
+            Ta, Tb = Ra * N, Rb * N
+            xbf = torch.empty(Ta + Tb, D, dtype=torch.bfloat16, device=dev)
+            w1bf = torch.empty(H, D, dtype=torch.bfloat16, device=dev)
+            casts += [(_f32c(xa), xbf), (_f32c(w1), w1bf)]
+            if Rb:
+                casts.append((_f32c(xb), xbf[Ta:]))
+            sides.append(dict(Ra=Ra, Rb=Rb, N=N, Ta=Ta, Tb=Tb, xbf=xbf, w1bf=w1bf, ma=_mask(ma), mb=_mask(mb) if Rb else None,
+                              b1=_f32c(b1), w2=_f32c(w2).reshape(-1), b2=_f32c(b2).reshape(-1), xshape=xa.shape))
+        _cast_multi(casts)
+        keep = any(ctx.needs_input_grad)
+        arr = (_lib.MlpSide * 2)()
+        for i, sd in enumerate(sides):
+            sd["h"] = torch.empty(sd["Ta"] + sd["Tb"], H, dtype=torch.bfloat16, device=dev) if keep else None
+            sd["logits"] = torch.zeros(sd["Ra"] + sd["Rb"], sd["N"], dtype=torch.float32, device=dev)
+            sd["w"] = torch.empty(sd["Ra"] + sd["Rb"], sd["N"], dtype=torch.float32, device=dev)
+            a = arr[i]
+            a.x_bf16, a.w1_bf16, a.T = sd["xbf"].data_ptr(), sd["w1bf"].data_ptr(), sd["Ta"] + sd["Tb"]
+            a.b1, a.w2, a.logits = sd["b1"].data_ptr(), sd["w2"].data_ptr(), sd["logits"].data_ptr()
+            a.h_bf16 = sd["h"].data_ptr() if keep else None
+        st = _stream()
+        _call("nr_mlp_fwd_pair", ctypes.cast(arr, ctypes.c_void_p), 2, D, H, st)
+        for sd in sides:
+            _call("nr_token_softmax", _p(sd["logits"]), _p(sd["b2"]), _p(sd["ma"]), _p(sd["mb"]), sd["Ra"], sd["Ra"] + sd["Rb"],
+                  sd["N"], _p(sd["w"]), st)
+        ctx.dims = [(sd["Ra"], sd["Rb"], sd["N"], sd["xshape"]) for sd in sides] + [(D, H)]
+        saved = []
+        for sd in sides:
+            saved += [sd["xbf"], sd["h"], sd["w"], sd["w1bf"], sd["w2"]]
+        ctx.save_for_backward(*saved)
+        out = []
+        for sd in sides:
+            out += [sd["w"][:sd["Ra"]], sd["w"][sd["Ra"]:] if sd["Rb"] else None]
+        return tuple(out)
+
+    @staticmethod
+    def backward(ctx, dwt, dwtb, dwv, dwvb):
+        sv = ctx.saved_tensors
+        D, H = ctx.dims[2]
+        need = ctx.needs_input_grad
+        dev = sv[0].device
+        f32 = dict(dtype=torch.float32, device=dev)
+        arr = (_lib.MlpSide * 2)()
+        res = []
+        keepalive = []
+        # every buffer before the fork
+        for i, (dwa, dwb, nx, nw1) in enumerate(((dwt, dwtb, need[0], need[8]), (dwv, dwvb, need[4], need[12]))):
+            xbf, h, w, w1bf, w2c = sv[5 * i:5 * i + 5]
+            Ra, Rb, N, xshape = ctx.dims[i]
+            Ta, T = Ra * N, (Ra + Rb) * N
+            nch = _lib.load().nr_mlp_chunks(T)
+            res.append(dict(xbf=xbf, h=h, w=w, w1bf=w1bf, w2c=w2c, Ra=Ra, Rb=Rb, N=N, Ta=Ta, T=T, xshape=xshape, nx=nx, nw1=nw1,
+                            dwa=_f32c(dwa) if dwa is not None else None, dwb=_f32c(dwb) if (dwb is not None and Rb) else None,
+                            dh=torch.empty_like(h), partials=torch.empty(2 * H + 1, nch, **f32), nch=nch,
+                            sums=torch.empty(2 * H + 1, **f32),
+                            dw1=torch.zeros(H, D, **f32) if nw1 else None, dx=torch.zeros(Ta, D, **f32) if nx else None))
+        def hidden_bwd(r):
+            _call("nr_token_weights_bwd", _p(r["h"]), 1, _p(r["w"]), _p(r["dwa"]), _p(r["dwb"]), r["Ra"], r["Ra"] + r["Rb"],
+                  r["N"], _p(r["w2c"]), H, _p(r["dh"]), _p(r["partials"]), _stream())
+
+        with ForkJoin(1, offset=4) as fj:
+            hidden_bwd(res[0])
+            with fj.on(0):
+                hidden_bwd(res[1])
+        for i, r in enumerate(res):
+            a = arr[i]
+            a.x_bf16, a.w1_bf16, a.T, a.T_dx = r["xbf"].data_ptr(), r["w1bf"].data_ptr(), r["T"], r["Ta"]
+            a.dh_bf16 = r["dh"].data_ptr()
+            a.dw1 = r["dw1"].data_ptr() if r["dw1"] is not None else None
+            a.dx = r["dx"].data_ptr() if r["dx"] is not None else None
+        with ForkJoin(1, offset=4) as fj:
+            with fj.on(0):                        # bias / second-layer gradients next to the GEMMs
+                for r in res:
+                    _call("nr_vec_sums", _p(r["partials"]), 2 * H + 1, r["nch"], None, _p(r["sums"]), _stream())
+            _call("nr_mlp_bwd_pair", ctypes.cast(arr, ctypes.c_void_p), 2, D, H, _stream())
+        out = []
+        for i, r in enumerate(res):
+            base = 8 + 4 * i
+            s_ = r["sums"]
+            out.append((r["dx"].reshape(r["xshape"]) if r["dx"] is not None else None,
+                        r["dw1"], s_[:H] if need[base + 1] else None, s_[H:2 * H].reshape(1, H) if need[base + 2] else None,
+                        s_[2 * H:] if need[base + 3] else None))
+        (dxt, dw1t, db1t, dw2t, db2t), (dxv, dw1v, db1v, dw2v, db2v) = out
+        return (dxt, None, None, None, dxv, None, None, None, dw1t, db1t, dw2t, db2t, dw1v, db1v, dw2v, db2v)
+
+
+def token_weights_pair(text_mlp, video_mlp, text, text_mask, video, video_mask, mode, bank_t=None, bank_mt=None,
+                       bank_v=None, bank_mv=None):
+    """(tw, tw_bank, vw, vw_bank): both token-weight MLPs of a step.  bf16 mode on the tcgen05 GEMM: one merged node
+    (TokenWeightsPairFunction); any other mode: the two per-modality nodes, the video one on a forked stream."""
+    pt = text_mlp if isinstance(text_mlp, (tuple, list)) else mlp_params(text_mlp)
+    pv = video_mlp if isinstance(video_mlp, (tuple, list)) else mlp_params(video_mlp)
+    D, H = text.shape[2], pt[0].shape[0]
+    if (mlp_mode(mode) == MLP_BF16 and USE_OWN_GEMM and D % 8 == 0 and H % 16 == 0 and text.shape[1] <= 128
+            and video.shape[1] <= 128 and video.shape[2] == D and pv[0].shape[0] == H):
+        return TokenWeightsPairFunction.apply(text, text_mask, bank_t, bank_mt, video, video_mask, bank_v, bank_mv, *pt, *pv)
+    with ForkJoin(1, offset=5) as fj:
+        tw, tw_mb = token_weights(pt, text, text_mask, mode, bank_t, bank_mt)
+        with fj.on(0):
+            vw, vw_mb = token_weights(pv, video, video_mask, mode, bank_v, bank_mv)
+            vw.record_stream(fj.main)
+    return tw, tw_mb, vw, vw_mb
 
 
 def _dw1_splitk(dh, x):

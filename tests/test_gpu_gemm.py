@@ -100,3 +100,49 @@ def test_small_matvec():
     _call("nr_matvec_small", _p(A), 5, 4, 0, _p(x), _p(x[4:]), _p(o), _stream())
     _call("nr_matvec_small", _p(A), 5, 4, 1, _p(y), None, _p(ot), _stream())
     assert torch.allclose(o, A @ (x[:4] + x[4:]), atol=1e-6) and torch.allclose(ot, A.t() @ y, atol=1e-6)
+
+
+def test_token_weights_pair_matches_the_two_single_nodes():
+    """Both modalities in one node (one cast launch, one grouped forward GEMM, one grouped backward GEMM) against the
+    per-modality nodes on the library GEMMs, forward and every gradient (same bf16 arithmetic: 2e-2 on the gradients
+    that sum thousands of cancelling terms, 1e-3 elsewhere)."""
+    d, nt, nv, ra, rb = 256, 24, 12, 11, 17
+    g = torch.Generator().manual_seed(8)
+    mk = lambda *sh: torch.randn(*sh, generator=g).cuda()
+    xt, xtb, xv, xvb = mk(ra, nt, d), mk(rb, nt, d), mk(ra, nv, d), mk(rb, nv, d)
+    masks = [(torch.rand(r, n, generator=g) > 0.3).long().cuda() for r, n in ((ra, nt), (rb, nt), (ra, nv), (rb, nv))]
+    for m in masks:
+        m[:, 0] = 1
+    ps = [[(0.05 * torch.randn(2 * d, d, generator=g)).cuda(), (0.05 * torch.randn(2 * d, generator=g)).cuda(),
+           (0.05 * torch.randn(1, 2 * d, generator=g)).cuda(), (0.05 * torch.randn(1, generator=g)).cuda()] for _ in range(2)]
+    ups = [torch.randn(r, n, generator=g).cuda() for r, n in ((ra, nt), (rb, nt), (ra, nv), (rb, nv))]
+
+    def run(pair):
+        leaves = [xt.clone().requires_grad_(True), xv.clone().requires_grad_(True)] + \
+                 [t.clone().requires_grad_(True) for p_ in ps for t in p_]
+        pt, pv = tuple(leaves[2:6]), tuple(leaves[6:10])
+        if pair:
+            outs = ops.token_weights_pair(pt, pv, leaves[0], masks[0], leaves[1], masks[2], "bf16", xtb, masks[1], xvb, masks[3])
+        else:
+            ops.USE_OWN_GEMM = False
+            try:
+                outs = (*ops.token_weights(pt, leaves[0], masks[0], "bf16", xtb, masks[1]),
+                        *ops.token_weights(pv, leaves[1], masks[2], "bf16", xvb, masks[3]))
+            finally:
+                ops.USE_OWN_GEMM = True
+        sum((o * u).sum() for o, u in zip(outs, ups)).backward()
+        return [o.detach() for o in outs], [l.grad for l in leaves]
+
+    o1, g1 = run(True)
+    o2, g2 = run(False)
+    for a, b in zip(o1, o2):
+        assert (a - b).abs().max().item() < 2e-3
+    names = ["dxt", "dxv", "w1t", "b1t", "w2t", "b2t", "w1v", "b1v", "w2v", "b2v"]
+    errs = {}
+    for n, a, b in zip(names, g1, g2):
+        if n.startswith("b2"):
+            assert a.abs().max().item() < 1e-4
+            continue
+        errs[n] = ((a.double() - b.double()).norm() / b.double().norm()).item()
+    print("token_weights_pair vs single nodes:", errs)
+    assert all(v < 3e-2 for v in errs.values()), errs

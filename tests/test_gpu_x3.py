@@ -22,8 +22,33 @@ def _emulate(text, video, tw, vw, tm, vm):
     return (t2v + v2t) / 2
 
 
-@pytest.mark.parametrize("shape", [(40, 24, 12), (33, 12, 24), (17, 64, 64), (25, 8, 4)])
+def _emulate_routed(text, video, tw, vw, tm, vm, fn):
+    """float64 value of S with the KERNEL's arg-maxima (saved by the autograd node): differentiating it gives exactly
+    the gradients the kernel's backward must produce for its own routing, whatever near-ties it resolved."""
+    _tw, _vw, _tm, _vm, _px, ystar, _py, xstar = fn.saved_tensors
+    t = torch.nn.functional.normalize(text.double(), dim=-1) * tm.double()[..., None]
+    v = torch.nn.functional.normalize(video.double(), dim=-1) * vm.double()[..., None]
+    if fn.swap:                                    # X = video, Y = text
+        r = torch.einsum("bvd,atd->bavt", v, t)    # [Rx, Ry, Nx, Ny]
+        wx, wy = vw.double(), tw.double()
+    else:
+        r = torch.einsum("atd,bvd->abtv", t, v)
+        wx, wy = tw.double(), vw.double()
+    rowpart = (torch.gather(r, 3, ystar.long().unsqueeze(3)).squeeze(3) * wx[:, None, :]).sum(2)
+    colpart = (torch.gather(r, 2, xstar.long().unsqueeze(2)).squeeze(2) * wy[None, :, :]).sum(2)
+    s = (rowpart + colpart) / 2
+    # how far the kernel's arg-maxima are from the true ones, in similarity units
+    gap = max(float((r.max(dim=3)[0] - torch.gather(r, 3, ystar.long().unsqueeze(3)).squeeze(3)).max()),
+              float((r.max(dim=2)[0] - torch.gather(r, 2, xstar.long().unsqueeze(2)).squeeze(2)).max()))
+    return (s.t() if fn.swap else s), gap
+
+
+@pytest.mark.parametrize("shape", [(40, 24, 12), (33, 12, 24), (17, 64, 64), (25, 8, 4), (21, 12, 8)])
 def test_maxsim_x3_forward_and_backward_vs_float64(shape):
+    """Forward against the exact float64 similarity (abs 1e-5); arg-maxima within 1e-6 of the true maxima (bf16: 1e-3);
+    every gradient against float64 autograd THROUGH THE KERNEL'S OWN ROUTING (rel-L2 1e-4: split coefficients and
+    split source tokens).  (The gradient of a max goes to one token, so a single near-tie resolved differently moves
+    the plain rel-L2 against float64 by ~1e-2 at these sizes — measured — without being an error.)"""
     b, nt, nv = shape
     d = 512
     h = synth.make_batch(b, nt, nv, d=d, seed=91).to("cuda")
@@ -31,25 +56,25 @@ def test_maxsim_x3_forward_and_backward_vs_float64(shape):
     tw = torch.softmax(torch.randn(b, nt, generator=g), -1).cuda() * h.text_mask
     vw = torch.softmax(torch.randn(b, nv, generator=g), -1).cuda() * h.video_mask
     up = torch.randn(b, b, generator=g).cuda()
-    res = {}
-    for prec in ("bf16x3", "bf16"):
+    for prec, gap_tol, gtol in (("bf16x3", 1e-6, 1e-4), ("bf16", 2e-3, 1e-2)):
         text = h.text_feat.clone().requires_grad_(True); video = h.video_feat.clone().requires_grad_(True)
         twp = tw.clone().requires_grad_(True); vwp = vw.clone().requires_grad_(True)
         s, st = ops.maxsim(text, video, twp, vwp, h.text_mask, h.video_mask, prec)
         assert torch.equal(st, s.t())
+        fn = s.grad_fn
         (s * up).sum().backward()
-        res[prec] = (s.detach(), text.grad, video.grad, twp.grad, vwp.grad)
-    text = h.text_feat.clone().requires_grad_(True); video = h.video_feat.clone().requires_grad_(True)
-    twp = tw.clone().requires_grad_(True); vwp = vw.clone().requires_grad_(True)
-    want = _emulate(text, video, twp, vwp, h.text_mask, h.video_mask)
-    (want * up.double()).sum().backward()
-    s3 = res["bf16x3"]
-    serr = float((s3[0].double() - want).abs().max())
-    gerr = [rel_l2(a, b_) for a, b_ in zip(s3[1:], (text.grad, video.grad, twp.grad, vwp.grad))]
-    gerr_b = [rel_l2(a, b_) for a, b_ in zip(res["bf16"][1:], (text.grad, video.grad, twp.grad, vwp.grad))]
-    print(f"x3 {shape}: S abs err {serr:.2e}; grad rel-L2 x3 {gerr} (bf16 {gerr_b})")
-    assert serr < 1e-5
-    assert max(gerr[:2]) < 2e-3 and max(gerr[2:]) < 1e-4
+        t64 = h.text_feat.clone().requires_grad_(True); v64 = h.video_feat.clone().requires_grad_(True)
+        tw64 = tw.clone().requires_grad_(True); vw64 = vw.clone().requires_grad_(True)
+        routed, gap = _emulate_routed(t64, v64, tw64, vw64, h.text_mask, h.video_mask, fn)
+        (routed * up.double()).sum().backward()
+        exact = _emulate(h.text_feat, h.video_feat, tw, vw, h.text_mask, h.video_mask)
+        serr = float((s.detach().double() - exact).abs().max())
+        gerr = [rel_l2(a, b_) for a, b_ in zip((text.grad, video.grad, twp.grad, vwp.grad), (t64.grad, v64.grad, tw64.grad, vw64.grad))]
+        print(f"{prec} {shape}: S abs err {serr:.2e}; arg-max gap {gap:.1e}; grad rel-L2 vs routed float64 {gerr}")
+        assert gap < gap_tol
+        assert max(gerr) < gtol
+        if prec == "bf16x3":
+            assert serr < 1e-5
 
 
 X3_CASES = {"cfg1": CASES["cfg1"], "tiny": dict(b=40, nt=8, nv=4, d=64, m=56, k=20)}
@@ -65,13 +90,18 @@ def test_head_x3_vs_reference_golden_and_oracle(name):
     set_bank(m, bank)
     losses, grads = cuda_losses(m, h, cfg)
     lerr = float((losses / ref - 1).abs().max())
-    gerr = {k: rel_l2(grads[k], rgrads[k]) for k in rgrads}
-    print(f"head x3 [{name}]: loss rel err {lerr:.2e}; grad rel-L2 {gerr}")
+    gerr = {k: rel_l2(grads[k], rgrads[k]) for k in rgrads if not k.endswith("2.bias")}    # d/d b2 is identically 0
+    # what separates two correct fp32-class implementations on these inputs (arg-max near-ties): the oracle in fp32
+    # against the oracle in float64
+    _, g64 = oracle_losses(h, bank, params, cfg, dtype=torch.float64)
+    floor = max(rel_l2(rgrads[k], g64[k]) for k in ("text", "video"))
+    ftol = max(5e-3, 2.5 * floor + 1e-3)
+    print(f"head x3 [{name}]: loss rel err {lerr:.2e}; fp32-vs-fp64 oracle floor {floor:.2e}; grad rel-L2 {gerr}")
     if gold is not None:
         np.testing.assert_allclose(losses.numpy(), gold["losses"], rtol=1e-4)      # the reference's own values
     np.testing.assert_allclose(losses.numpy(), ref.numpy(), rtol=1e-4)
     for k in ("text", "video", "gt", "gv"):
-        assert gerr[k] < 5e-3, (k, gerr[k])
+        assert gerr[k] < ftol, (k, gerr[k], ftol)
     assert gerr["logit_scale"] < 1e-3
     # token-weight MLP parameters: TF32 library GEMMs in this mode
     for k, e in gerr.items():
