@@ -261,28 +261,39 @@ class HeadFunction(torch.autograd.Function):
             ev_dS.record()
 
             def global_path(ev_dG=None):
-                # dgT = dG gV, dgV = dG^T gT (library GEMMs, fp32), each followed by its centrality backward; the video
-                # half runs on its own branch once dG exists
+                # centrality backward FIRST (it only needs dw from the row losses and writes d mean, which the token
+                # normalisation backward at the end of the critical path is waiting for); then dgT += dG gV and
+                # dgV += dG^T gT accumulate on top of it, off the critical path.  The video half runs on its own branch.
                 if ev_dG is None:
+                    if need[2]:
+                        _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs,
+                              T.rows, _p(dgt), 0, _p(dmean[0]), _stream())
+                    else:
+                        _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs,
+                              T.rows, None, 0, _p(dmean[0]), _stream())
+                    ev_dm.append(torch.cuda.Event()); ev_dm[-1].record()
                     _call("nr_transpose_add", _p(dG1), B, _p(dG2), B, _p(dG), B, B, B, 1.0, 1.0, _stream())
                     ev = torch.cuda.Event()
                     ev.record()
                     if need[2]:
-                        _call("nr_matmul_f32", _p(dG), B, 0, _p(v2), d, B, B, d, _p(dgt), d, 0, _stream())
-                    _call("nr_centrality_bwd", _p(mean[0]), _p(gn[0]), _p(ginv[0]), _p(w[0]), _p(dw[0]), B, d, cs,
-                          T.rows, _p(dgt), 1, _p(dmean[0]), _stream())
+                        _call("nr_matmul_f32", _p(dG), B, 0, _p(v2), d, B, B, d, _p(dgt), d, 1, _stream())
                     return ev
+                _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows,
+                      _p(dgv) if need[3] else None, 0, _p(dmean[1]), _stream())
+                ev_dm.append(torch.cuda.Event()); ev_dm[-1].record()
                 torch.cuda.current_stream().wait_event(ev_dG)
                 if need[3]:
-                    _call("nr_matmul_f32", _p(dG), B, 1, _p(g2), d, B, B, d, _p(dgv), d, 0, _stream())
-                _call("nr_centrality_bwd", _p(mean[1]), _p(gn[1]), _p(ginv[1]), _p(w[1]), _p(dw[1]), B, d, cs, V.rows,
-                      _p(dgv), 1, _p(dmean[1]), _stream())
+                    _call("nr_matmul_f32", _p(dG), B, 1, _p(g2), d, B, B, d, _p(dgv), d, 1, _stream())
                 return None
 
+            ev_dm = []
             with fj.on(1):
                 ev_dG = global_path()
             with fj.on(3):
                 global_path(ev_dG)
+            # the two branches stay open past this fork: the normalisation backward only waits for their d mean
+            # events, the dG products are joined right before the gradients are handed back
+            ev_global_end = (fj.detach(1), fj.detach(3))
             if ctx.fusedk:
                 # one routing matrix per pair, applied from either side; ALL contractions in one launch (the text
                 # gradient accumulates over [video ; bank-video] sources, the video gradient over [text ; bank-text])
@@ -342,12 +353,16 @@ class HeadFunction(torch.autograd.Function):
                 if need[7]:
                     _call("nr_maxsim_bwd_w", _p(pB), _p(dc[0]), 0, 1, 0.5 / M, M, nv, B, _p(dvw_mb), st)
         # ---- fork 3: normalisation backward of the two modalities
+        for ev in ev_dm:
+            torch.cuda.current_stream().wait_event(ev)
         with ops.ForkJoin(1) as fj:
             if need[0]:
                 T.backward(dtn, add_vec=dmean[0], out=dtext)
             with fj.on(0):
                 if need[1]:
                     V.backward(dvn, add_vec=dmean[1], out=dvideo)
+        for ev in ev_global_end:
+            torch.cuda.current_stream().wait_event(ev)
         ctx.objs = None
         gs_t, gs_v = ctx.gshape
         return (dtext, dvideo, dgt.reshape(gs_t) if need[2] else None, dgv.reshape(gs_v) if need[3] else None,
