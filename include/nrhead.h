@@ -70,6 +70,19 @@ int nr_prep_tokens_split(const float* x, int64_t rows, int64_t d, float* xn_f32,
 int nr_prep_tokens_bwd(const float* xn_f32, const float* inv_norm, const float* dxn, const float* add_vec,
                        const int64_t* mask, int64_t rows, int64_t d, float* dx, int accumulate, void* stream);
 
+/* ---- persistent prepared memory bank: ring insert (reference modeling.py:222-249) ------------------
+ * The bank lives in place as a ring of M sample slots; reference row i (newest first) = slot (head + i) mod M with
+ * `head` an int32 in DEVICE memory (the launches replay inside a CUDA graph).  A step first moves the head back by
+ * its n_new <= M samples (nr_bank_advance, which also stores their dataset indices), then writes the samples of one
+ * modality at slots (head + j) mod M into every buffer given (all nullable): raw fp32 rows [M,N,d], int64 masks
+ * [M,N], raw bf16 rows (the weight MLP's operand), the L2-normalised bf16 operand copy [M*N, d] (split_role 0) or
+ * its split form [M*N, 3d] (split_role 1 / 2, see nr_prep_tokens_split) with masked tokens zeroed, and its transposed
+ * copy [d or 3d, ld]. */
+int nr_bank_advance(int* head, int64_t n_new, int64_t M, const int64_t* new_ind, int64_t* ring_ind, void* stream);
+int nr_bank_insert(const float* new_feat, const int64_t* new_mask, int64_t n_new, int64_t N, int64_t d, int64_t M,
+                   const int* head, float* ring_feat, int64_t* ring_mask, void* ring_raw_bf16, void* ring_xn_bf16,
+                   int split_role, void* ring_xnT_bf16, int64_t ld, void* stream);
+
 /* ---- small exact-fp32 products (CUDA cores) --------------------------------------------------------------------
  * nr_matmul_f32: out[M,N] (+)= op(A)[M,K] X[K,N]; transA != 0: A is stored [K, M].  The global-feature gradients
  *   dgT = dG gV, dgV = dG^T gT (autograd of modeling.py:516-539 with one global token per sample).

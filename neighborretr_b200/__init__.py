@@ -21,8 +21,8 @@ def bind_head(cls, graph=True, precision=None):
     from . import modeling as md
     names = []
     for name, fn in vars(md.HeadMixin).items():
-        if callable(fn) and not name.startswith("__"):
-            setattr(cls, name, fn)
+        if (callable(fn) or isinstance(fn, property)) and not name.startswith("__"):
+            setattr(cls, name, fn)              # methods, and the five mb_* bank properties
             names.append(name)
     cls.forward = md.installed_forward
     cls.head_graph = bool(graph)

@@ -26,6 +26,8 @@ SIGNATURES = {
     "nr_prep_tokens": (_I, [_P, _I64, _I64, _P, _P, _P, _P, _P, _P]),
     "nr_prep_tokens_split": (_I, [_P, _I64, _I64, _P, _P, _I, _P, _P, _P, _P]),
     "nr_prep_tokens_bwd": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I, _P]),
+    "nr_bank_advance": (_I, [_P, _I64, _I64, _P, _P, _P]),
+    "nr_bank_insert": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _I64, _P]),
     "nr_matmul_f32": (_I, [_P, _I64, _I, _P, _I64, _I64, _I64, _I64, _P, _I64, _I, _P]),
     "nr_matvec_small": (_I, [_P, _I64, _I64, _I, _P, _P, _P, _P]),
     "nr_cast_bf16": (_I, [_P, _P, _I64, _P]),

@@ -570,3 +570,124 @@ extern "C" int nr_token_weights_bwd(const void* h, int h_bf16, const float* w, c
   NR_CHECK_LAUNCH("nr_token_weights_bwd");
   return 0;
 }
+
+// ---- persistent prepared memory bank (reference NeighborRetr/models/modeling.py:222-249) ----------
+// The reference rebuilds the bank every step with five torch.cat calls; a head that re-prepares it would also
+// re-normalise, re-cast and re-transpose all M rows although only the newest B changed.  Here the bank is a RING:
+// raw fp32 rows, masks, the normalised bf16 operand copy (plain or split), its transposed copy and the raw bf16 copy
+// the weight MLP multiplies all live in place, and a step writes only its B new samples at slots (head + j) mod M.
+// `head` lives in device memory, so the same launch replays inside a CUDA graph.  Reference order is recovered as
+// row i = slot (head + i) mod M (newest first).  HBM-bound: B*N*D*(4 read + 4 + 2 + 2 + 2 written) bytes.
+namespace nr {
+
+__global__ void bank_advance_kernel(int* __restrict__ head, int n_new, int M, const int64_t* __restrict__ new_ind,
+                                    int64_t* __restrict__ ring_ind) {
+  __shared__ int h;
+  if (threadIdx.x == 0) {
+    int v = *head - n_new;
+    v %= M;
+    if (v < 0) v += M;
+    h = v;
+  }
+  __syncthreads();
+  if (ring_ind)
+    for (int j = threadIdx.x; j < n_new; j += blockDim.x) ring_ind[(h + j) % M] = new_ind[j];
+  __syncthreads();
+  if (threadIdx.x == 0) *head = h;
+}
+
+__global__ void __launch_bounds__(PREP_WARPS * 32)
+bank_insert_kernel(const float* __restrict__ x, const int64_t* __restrict__ mask, int rows, int N, int d, int M,
+                   const int* __restrict__ head, float* __restrict__ ring_feat, int64_t* __restrict__ ring_mask,
+                   __nv_bfloat16* __restrict__ ring_raw, __nv_bfloat16* __restrict__ ring_xn, int split,
+                   __nv_bfloat16* __restrict__ ring_xnT, int64_t ld) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * PREP_WARPS + warp;
+  if (row >= rows) return;
+  const int j = row / N, n = row - j * N;
+  const int slot = (*head + j) % M;
+  const int64_t drow = (int64_t)slot * N + n;
+  const float* xr = x + (int64_t)row * d;
+  float4 v[PREP_MAXQ];
+  float ss = 0.f;
+#pragma unroll
+  for (int q = 0; q < PREP_MAXQ; ++q) {
+    const int c = q * 128 + lane * 4;
+    if (c < d) {
+      v[q] = *reinterpret_cast<const float4*>(xr + c);
+      ss += v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w;
+    }
+  }
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  const bool live = mask ? (mask[row] != 0) : true;
+  if (ring_mask && lane == 0) ring_mask[drow] = mask ? mask[row] : 1;
+  const int kd = split ? 3 * d : d;
+#pragma unroll
+  for (int q = 0; q < PREP_MAXQ; ++q) {
+    const int c = q * 128 + lane * 4;
+    if (c >= d) continue;
+    if (ring_feat) *reinterpret_cast<float4*>(ring_feat + drow * d + c) = v[q];
+    const float f[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+    if (ring_raw) {
+      __nv_bfloat16 r4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) r4[e] = __float2bfloat16_rn(f[e]);
+      *reinterpret_cast<uint2*>(ring_raw + drow * d + c) = *reinterpret_cast<uint2*>(r4);
+    }
+    if (ring_xn || ring_xnT) {
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float nv = live ? f[e] / denom : 0.f;
+        h[e] = __float2bfloat16_rn(nv);
+        l[e] = __float2bfloat16_rn(live ? nv - __bfloat162float(h[e]) : 0.f);
+      }
+      const uint2 ph = *reinterpret_cast<uint2*>(h), pl = *reinterpret_cast<uint2*>(l);
+      if (ring_xn) {
+        __nv_bfloat16* o = ring_xn + drow * kd + c;
+        *reinterpret_cast<uint2*>(o) = ph;
+        if (split) {
+          *reinterpret_cast<uint2*>(o + d) = (split == 1) ? pl : ph;
+          *reinterpret_cast<uint2*>(o + 2 * d) = (split == 1) ? ph : pl;
+        }
+      }
+      if (ring_xnT) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ring_xnT[(int64_t)(c + e) * ld + drow] = h[e];
+          if (split) {
+            ring_xnT[(int64_t)(d + c + e) * ld + drow] = (split == 1) ? l[e] : h[e];
+            ring_xnT[(int64_t)(2 * d + c + e) * ld + drow] = (split == 1) ? h[e] : l[e];
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace nr
+
+extern "C" int nr_bank_advance(int* head, int64_t n_new, int64_t M, const int64_t* new_ind, int64_t* ring_ind,
+                               void* stream) {
+  NR_CHECK_ARG(head && n_new > 0 && M > 0 && n_new <= M && (!ring_ind || new_ind), "nr_bank_advance: bad arguments");
+  nr::bank_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(head, (int)n_new, (int)M, new_ind, ring_ind);
+  NR_CHECK_LAUNCH("nr_bank_advance");
+  return 0;
+}
+
+extern "C" int nr_bank_insert(const float* new_feat, const int64_t* new_mask, int64_t n_new, int64_t N, int64_t d,
+                              int64_t M, const int* head, float* ring_feat, int64_t* ring_mask, void* ring_raw_bf16,
+                              void* ring_xn_bf16, int split_role, void* ring_xnT_bf16, int64_t ld, void* stream) {
+  NR_CHECK_ARG(new_feat && head && n_new > 0 && n_new <= M && N > 0, "nr_bank_insert: bad arguments");
+  NR_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 128 * nr::PREP_MAXQ, "nr_bank_insert: d=%lld must be a multiple of 4, <= %d",
+               (long long)d, 128 * nr::PREP_MAXQ);
+  NR_CHECK_ARG(split_role >= 0 && split_role <= 2 && (!ring_xnT_bf16 || ld >= M * N), "nr_bank_insert: bad split role or ld");
+  const int64_t rows = n_new * N;
+  const int grid = (int)((rows + nr::PREP_WARPS - 1) / nr::PREP_WARPS);
+  nr::bank_insert_kernel<<<grid, nr::PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      new_feat, new_mask, (int)rows, (int)N, (int)d, (int)M, head, ring_feat, ring_mask, (__nv_bfloat16*)ring_raw_bf16,
+      (__nv_bfloat16*)ring_xn_bf16, split_role, (__nv_bfloat16*)ring_xnT_bf16, ld);
+  NR_CHECK_LAUNCH("nr_bank_insert");
+  return 0;
+}

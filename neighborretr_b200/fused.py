@@ -55,13 +55,16 @@ class HeadPrologue:
     be enqueued on forked streams next to the MLP evaluations (modeling._compute_losses)."""
 
     def __init__(self, text, video, gt, gv, text_mask, video_mask, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp,
-                 need_text_grad=True, need_video_grad=True):
+                 need_text_grad=True, need_video_grad=True, bank_ring=None):
+        """bank_ring (bank.BankRing): the bank's prepared operands already exist and persist across steps; nothing of
+        the bank is prepared here (mb_* are then only read for their shapes)."""
         cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
         _req_cuda(text, video, gt, gv, mb_feat_t, mb_feat_v)
         dev = text.device
         self.hp = hp
         self.tm, self.vm = _mask(text_mask), _mask(video_mask)
-        self.mtm, self.mvm = _mask(mb_mask_t), _mask(mb_mask_v)
+        self.bank_static = bank_ring is not None
+        self.mtm, self.mvm = (bank_ring.mask_t, bank_ring.mask_v) if self.bank_static else (_mask(mb_mask_t), _mask(mb_mask_v))
         self.bf = bf = prec in ops.TC_PRECISIONS or bprec in ops.TC_PRECISIONS
         x3 = prec == NR_PREC_BF16X3
         # bf16: masks are folded into the operand copies (masked tokens = zero rows) for the two-direction kernel
@@ -72,8 +75,13 @@ class HeadPrologue:
         rx, ry = (ops.ROLE_X, ops.ROLE_Y) if x3 else (0, 0)      # the text side is X, the video side Y (HeadFunction)
         self.T = Prepared(text.detach(), bf16=bf, colsum=True, mask=self.tm if fk else None, defer=True, split=rx)
         self.V = Prepared(video.detach(), bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True, split=ry)
-        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk, split=rx)
-        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk, split=ry)
+        if self.bank_static:
+            if not fk or bank_ring.x3 != x3:
+                raise RuntimeError("bank ring: needs the fused tensor-core path in the precision it was built for")
+            self.MT, self.MV = bank_ring.MT, bank_ring.MV
+        else:
+            self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk, split=rx)
+            self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk, split=ry)
         B, M, d = self.T.r, self.MT.r, self.T.d
         if self.V.r != B or self.MV.r != M:
             raise RuntimeError("text/video batch sizes (or bank sizes) differ")
@@ -97,19 +105,25 @@ class HeadPrologue:
 
     def run_text_side(self):
         bprec = self.hp[9]
-        self.MT.run()
+        if not self.bank_static:
+            self.MT.run()
         self.T.run()
-        if self.bf and self.need_v:        # sources of the video-side backward contraction, off its critical path
-            self.MT.bwd_source(bprec); self.T.bwd_source(bprec)
         self._centrality(self.T, self.g2, 0)
+        if self.bf and self.need_v:        # sources of the video-side backward contraction, off its critical path
+            self.T.bwd_source(bprec)
+            if not self.bank_static:
+                self.MT.bwd_source(bprec)
 
     def run_video_side(self):
         bprec = self.hp[9]
-        self.MV.run()
+        if not self.bank_static:
+            self.MV.run()
         self.V.run()
-        if self.bf and self.need_t:
-            self.MV.bwd_source(bprec); self.V.bwd_source(bprec)
         self._centrality(self.V, self.v2, 1)
+        if self.bf and self.need_t:
+            self.V.bwd_source(bprec)
+            if not self.bank_static:
+                self.MV.bwd_source(bprec)
 
     def run_global(self):
         # global similarity: one token per sample -> plain dot products (library GEMM, fp32), then the Sinkhorn duals

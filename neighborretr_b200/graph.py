@@ -51,9 +51,11 @@ class GraphedHeadStep:
                 s.requires_grad_(True)
             self.static[f] = s
         self.bank_names = ("mb_ind", "mb_feat_t", "mb_feat_v", "mb_mask_t", "mb_mask_v")
-        for n in self.bank_names:                       # own the bank storage
-            setattr(model, n, getattr(model, n).detach().to(dev).clone())
-        bank0 = {n: getattr(model, n).clone() for n in self.bank_names}
+        bank0 = {n: getattr(model, n).detach().to(dev).clone() for n in self.bank_names}     # reference order
+        self.ring = self._make_ring(model, bank0, self.static["text_feat"].shape[0])
+        if self.ring is None:
+            for n in self.bank_names:                   # own the bank storage
+                setattr(model, n, bank0[n].clone())
         self.params = head_params(model) if self.explicit else [p for p in model.parameters() if p.requires_grad]
         self.grad_list = None
         self._e0 = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.0], device=dev)
@@ -74,16 +76,49 @@ class GraphedHeadStep:
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.losses = self._body()
         self.launches_per_replay = ops.LAUNCHES["count"] - n0
-        for n in self.bank_names:                       # warm-up steps advanced the bank: restore it in place
-            getattr(model, n).copy_(bank0[n])
+        if self.ring is not None:                       # warm-up steps advanced the bank: restore it in place
+            self.ring.load(*[bank0[n] for n in self.bank_names])
+        else:
+            for n in self.bank_names:
+                getattr(model, n).copy_(bank0[n])
         if self.explicit:
             self.grads = dict(zip(GRAD_FIELDS, self.grad_list[:len(GRAD_FIELDS)]))
         else:
             self.grads = {f: self.static[f].grad for f in GRAD_FIELDS}
 
+    def _make_ring(self, model, bank0, b):
+        """The persistent prepared bank (bank.BankRing) when the step runs the fused tensor-core kernels; None
+        otherwise (fp32 mode, unsupported token counts, or NR_BANK_RING=0): the bank then stays five tensors that
+        the captured FIFO kernels rewrite."""
+        if os.environ.get("NR_BANK_RING", "1") == "0" or bank0["mb_feat_v"].dim() != 3 or bank0["mb_feat_v"].shape[0] == 0:
+            return None
+        prec, bprec = model._head_precision(), model._head_bwd_precision()
+        nt, nv, d = bank0["mb_feat_t"].shape[1], bank0["mb_feat_v"].shape[1], bank0["mb_feat_t"].shape[2]
+        x3 = prec == "bf16x3"
+        if prec not in ("bf16", "bf16x3") or bprec != prec or not ops.USE_FUSED_MAXSIM \
+                or not ops.maxsim2_supported(nt, nv, d * (3 if x3 else 1)):
+            return None
+        from .bank import BankRing
+        mlp_bf16 = model._mlp_precision() == "bf16" and ops.USE_OWN_GEMM
+        rows = b * self.world                      # the FIFO stores the gathered batch; the MLP sees the local one
+        ring = model.__dict__.get("_nr_ring")
+        if ring is None or not ring.matches(bank0["mb_feat_t"], bank0["mb_feat_v"], x3, mlp_bf16, b):
+            ring = BankRing(*[bank0[n] for n in self.bank_names], x3=x3, mlp_bf16=mlp_bf16, batch_rows=b)
+            model.__dict__["_nr_ring"] = ring
+        else:
+            ring.load(*[bank0[n] for n in self.bank_names])
+        model.__dict__["_nr_ring_live"] = True
+        self._fifo_rows = rows
+        return ring
+
     def set_bank(self, bank):
         """Overwrite the memory bank IN PLACE (the captured graph holds the storage): `bank` has mb_ind, mb_feat_t,
         mb_feat_v, mb_mask_t, mb_mask_v (any device)."""
+        if self.ring is not None:
+            dev = self.ring.device
+            self.ring.load(*[getattr(bank, n).to(dev) for n in self.bank_names])
+            self.model.__dict__["_nr_ring_live"] = True
+            return
         with torch.no_grad():
             for n in self.bank_names:
                 getattr(self.model, n).copy_(getattr(bank, n))
@@ -97,21 +132,25 @@ class GraphedHeadStep:
     def _body(self):
         m, s = self.model, self.static
         cfg = m.config
+        ring = self.ring
         if self.world == 1:
             logit_scale = m.clip.logit_scale.exp()
-            losses = m._compute_losses(s["text_feat"], s["video_feat"], s["text_mask"], s["video_mask"], m.mb_feat_t,
-                                       m.mb_feat_v, m.mb_mask_t, m.mb_mask_v, cfg.centrality_scale, cfg.beta,
-                                       cfg.num_neighbors, cfg.temperature, logit_scale,
-                                       global_feats=(s["global_text"], s["global_video"]))
+            # with a ring the mb_* arguments only carry shapes (ring order); the prepared operands come from the ring
+            bank = (ring.feat_t, ring.feat_v, ring.mask_t, ring.mask_v) if ring is not None else \
+                (m.mb_feat_t, m.mb_feat_v, m.mb_mask_t, m.mb_mask_v)
+            losses = m._compute_losses(s["text_feat"], s["video_feat"], s["text_mask"], s["video_mask"], *bank,
+                                       cfg.centrality_scale, cfg.beta, cfg.num_neighbors, cfg.temperature, logit_scale,
+                                       global_feats=(s["global_text"], s["global_video"]), bank_ring=ring)
             new_rows = (s["idx"], s["text_feat"], s["video_feat"], s["text_mask"], s["video_mask"])
         else:       # row-block sharded head; the NCCL collectives are captured in the graph
             losses, (ta, va, tma, vma, ia) = m._sharded_losses(s["text_feat"], s["video_feat"], s["text_mask"],
                                                                s["video_mask"], (s["global_text"], s["global_video"]),
-                                                               idx=s["idx"])
+                                                               idx=s["idx"], bank_ring=ring)
             new_rows = (ia, ta, va, tma, vma)
         # With bf16 weight-MLP GEMMs the backward reads bf16 copies, never the bank itself: the FIFO update can then
         # leave the critical path and run on its own branch next to the backward.
-        early_fifo = self.world == 1 and m._mlp_precision() == "bf16" and os.environ.get("NR_EARLY_FIFO", "1") != "0"
+        early_fifo = (ring is None and self.world == 1 and m._mlp_precision() == "bf16"
+                      and os.environ.get("NR_EARLY_FIFO", "1") != "0")
         if early_fifo:
             main = torch.cuda.current_stream()
             self._fifo_stream.wait_stream(main)
@@ -138,7 +177,12 @@ class GraphedHeadStep:
         else:
             if self.world > 1:
                 m.wait_gathered_text()
-            self._fifo(new_rows)
+            if ring is not None:
+                # after every reader of the step (both contractions, the MLP GEMMs): only the new rows are written
+                with torch.no_grad():
+                    ring.insert(*new_rows)
+            else:
+                self._fifo(new_rows)
         return out5.detach() if out5 is not None else torch.stack([x.detach() for x in losses])
 
     def _fifo(self, new_rows):
@@ -187,6 +231,8 @@ class GraphedHeadStep:
                 self.static[f].data.copy_(t, non_blocking=True)
         self.graph.replay()
         ops.LAUNCHES["count"] += self.launches_per_replay
+        if self.ring is not None:
+            self.ring.note_replay(self._fifo_rows)
         if sync_losses_to is not None:
             sync_losses_to.copy_(self.losses, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -208,6 +254,8 @@ class _ReplayFunction(torch.autograd.Function):
                 step.static[f].data.copy_(t.reshape(step.static[f].shape), non_blocking=True)
         step.graph.replay()
         ops.LAUNCHES["count"] += step.launches_per_replay
+        if step.ring is not None:
+            step.ring.note_replay(step._fifo_rows)
         ctx.runner = runner
         ctx.token = runner.replays = runner.replays + 1
         ctx.meta = [(t.dtype, t.shape) for t in (text, video, gt, gv)]
@@ -250,6 +298,8 @@ class GraphedHead:
         m = self.model
         key = self._key(text, video, gt, gv, tm, vm)
         r = self.runners.get(key)
+        if r is not None and r.step.ring is not None and m.__dict__.get("_nr_ring") is not r.step.ring:
+            r = None                                          # another capture replaced the model's bank ring
         if r is None:
             if len(self.runners) >= self.MAX_SHAPES:
                 return None                                   # too many distinct shapes: the caller runs eagerly
@@ -272,7 +322,16 @@ class _Runner:
         del bank_in
 
     def sync_bank(self, model):
-        """Static bank storage <- whatever was assigned to model.mb_* since the last step (identity check)."""
+        """Static bank storage <- whatever was assigned to model.mb_* since the last step (identity check; with a
+        ring: the `_nr_ring_live` flag the attribute setters clear)."""
+        ring = self.step.ring
+        if ring is not None:
+            if model.__dict__.get("_nr_ring") is not ring:
+                raise RuntimeError("GraphedHead: the model's bank ring was replaced; re-capture the step")
+            if not model.__dict__.get("_nr_ring_live"):
+                ring.load(*[getattr(model, n) for n in self.step.bank_names])
+                model.__dict__["_nr_ring_live"] = True
+            return
         for n, st in self.bank.items():
             cur = getattr(model, n)
             if cur is not st:

@@ -40,8 +40,41 @@ def _token_weights(mlp, feat, mask, lowp=False):
     return ops.token_weights(mlp, feat, mask, lowp)[0]
 
 
+def _bank_property(name):
+    """The five public bank attributes stay plain assignable tensors for their users (the reference's forward,
+    MemoryBankManager — reference utils/memory_bank.py:206-211, 255-260), but while a captured step owns the bank as
+    a ring (bank.BankRing) reading one of them materialises the reference's row order from the ring, and assigning one
+    hands the bank back to the attributes (the next captured step reloads its ring from them)."""
+    key = "_" + name
+
+    def get(self):
+        d = self.__dict__
+        ring = d.get("_nr_ring")
+        if ring is not None and d.get("_nr_ring_live"):
+            return ring.export()[name]
+        if key in d:
+            return d[key]
+        raise AttributeError(name)
+
+    def set_(self, value):
+        d = self.__dict__
+        ring = d.get("_nr_ring")
+        if ring is not None and d.get("_nr_ring_live"):
+            for n, t in ring.export().items():          # the other four attributes keep showing the ring's rows
+                d["_" + n] = t
+            d["_nr_ring_live"] = False
+        d[key] = value
+
+    return property(get, set_)
+
+
 class HeadMixin:
     """Head methods; ``self`` provides the weight MLPs, ``config``, ``clip.logit_scale`` and mb_* state."""
+    mb_ind = _bank_property("mb_ind")
+    mb_feat_t = _bank_property("mb_feat_t")
+    mb_feat_v = _bank_property("mb_feat_v")
+    mb_mask_t = _bank_property("mb_mask_t")
+    mb_mask_v = _bank_property("mb_mask_v")
 
     # --- precision of the token-pair contraction: "bf16" (tcgen05) or "fp32" (CUDA cores) -----------
     def _head_precision(self):
@@ -150,7 +183,7 @@ class HeadMixin:
     # --- a14: _compute_losses (reference :314-360) ----------------------------------------------------
     def _compute_losses(self, text_feat, video_feat, text_mask, video_mask, mb_feat_t, mb_feat_v, mb_mask_t,
                         mb_mask_v, centrality_scale, beta, num_neighbors, temperature, logit_scale,
-                        global_feats=None):
+                        global_feats=None, bank_ring=None):
         cfg = self.config
         fused_ok = getattr(self, "head_fused", getattr(cfg, "head_fused", True))
         if fused_ok:
@@ -177,7 +210,8 @@ class HeadMixin:
             # weight-MLP evaluations: parallel branches of the step's CUDA graph.  Autograd runs each MLP backward on
             # its forward stream, so the backward GEMMs overlap as well.
             pro = HeadPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, mb_feat_t, mb_feat_v,
-                               mb_mask_t, mb_mask_v, hp, text_feat.requires_grad, video_feat.requires_grad)
+                               mb_mask_t, mb_mask_v, hp, text_feat.requires_grad, video_feat.requires_grad,
+                               bank_ring=bank_ring)
             with ops.ForkJoin(3) as fj:
                 with fj.on(0):
                     pro.run_text_side()
@@ -186,9 +220,10 @@ class HeadMixin:
                 with fj.on(2):
                     pro.run_global()
                 # both modalities' weight MLPs (batch tokens and bank tokens share the hidden buffers and the kernels)
-                tw, tw_mb, vw, vw_mb = ops.token_weights_pair(self.text_weight_fc, self.video_weight_fc, text_feat,
-                                                              text_mask, video_feat, video_mask, lowp, mb_feat_t,
-                                                              mb_mask_t, mb_feat_v, mb_mask_v)
+                tw, tw_mb, vw, vw_mb = ops.token_weights_pair(
+                    self.text_weight_fc, self.video_weight_fc, text_feat, text_mask, video_feat, video_mask, lowp,
+                    mb_feat_t, mb_mask_t, mb_feat_v, mb_mask_v,
+                    bank_bf16=bank_ring.mlp_operands(text_feat.shape[0]) if bank_ring is not None else None)
                 # the Sinkhorn duals are first needed by the row losses, after the token-pair contraction: the
                 # head node waits on this event there instead of joining the branch here
                 pro.global_done = fj.detach(2)
@@ -234,7 +269,7 @@ class HeadMixin:
         self.mb_mask_v = ops.fifo_update(video_mask.to(self.mb_mask_v.dtype), self.mb_mask_v, cap)
 
     # --- everything of reference forward() below the encoders (:269-312) -----------------------------
-    def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats, idx=None):
+    def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats, idx=None, bank_ring=None):
         """W > 1: row-block sharded head (sharded.py) on the LOCAL batch; gathers happen inside.
         Returns (5 losses, gathered (text, video, text_mask, video_mask[, idx])); idx (the dataset indices the bank
         FIFO stores) rides on the packed small gather when given."""
@@ -250,8 +285,12 @@ class HeadMixin:
         hp = head_hparams(cfg.centrality_scale, cfg.beta, cfg.num_neighbors, cfg.temperature, cfg.uniform_weight,
                           cfg.neighbor_weight, cfg.kl_weight, self._head_precision(), self._head_bwd_precision())
         # gathers, token preparation, centrality weights, global similarity + Sinkhorn: forked next to the MLPs
-        pro = ShardedPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, self.mb_feat_t, self.mb_feat_v,
-                              self.mb_mask_t, self.mb_mask_v, hp, idx_l=idx)
+        if bank_ring is not None:      # ring order; only the shapes and the prepared views are used
+            bank = (bank_ring.feat_t, bank_ring.feat_v, bank_ring.mask_t, bank_ring.mask_v)
+        else:
+            bank = (self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v)
+        pro = ShardedPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, *bank, hp, idx_l=idx,
+                              bank_ring=bank_ring)
         with ops.ForkJoin(3) as fj:
             with fj.on(2):
                 pro.run_global()             # first: Sinkhorn is the longest chain of the forward
@@ -260,11 +299,12 @@ class HeadMixin:
                 pro.run_video_side()
             with fj.on(0):
                 pro.run_text_side()
-            tw, tw_mb, vw, vw_mb = ops.token_weights_pair(tmlp, vmlp, text_feat, text_mask, video_feat, video_mask, lowp,
-                                                          self.mb_feat_t, self.mb_mask_t, self.mb_feat_v, self.mb_mask_v)
+            tw, tw_mb, vw, vw_mb = ops.token_weights_pair(
+                tmlp, vmlp, text_feat, text_mask, video_feat, video_mask, lowp, bank[0], bank[2], bank[1], bank[3],
+                bank_bf16=bank_ring.mlp_operands(text_feat.shape[0]) if bank_ring is not None else None)
         out5, nbr, text_all, video_all, tm_all, vm_all = ShardedHeadFunction.apply(
             text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, self.clip.logit_scale.exp(), text_mask, video_mask,
-            self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v, hp, pro)
+            *bank, hp, pro)
         self.last_neighbors = (nbr[0], nbr[1])
         self._text_ready = pro.text_ready          # event of the deferred text gather (None: already joined)
         if idx is not None:

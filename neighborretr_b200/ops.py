@@ -677,22 +677,31 @@ class TokenWeightsPairFunction(torch.autograd.Function):
     GEMM grid per modality would serialise on shared memory and pay its ramp-up four times per step."""
 
     @staticmethod
-    def forward(ctx, xt, mt, xtb, mtb, xv, mv, xvb, mvb, w1t, b1t, w2t, b2t, w1v, b1v, w2v, b2v):
+    def forward(ctx, xt, mt, xtb, mtb, xv, mv, xvb, mvb, w1t, b1t, w2t, b2t, w1v, b1v, w2v, b2v, bank_bf16=None):
+        """bank_bf16 = (text buffer, video buffer) from bank.BankRing.mlp_operands(): [Ta + Tb, D] bf16 whose tail
+        already holds the bank rows (persistent across steps); only the batch tokens are cast, into its head."""
         _req_cuda(xt, xtb, xv, xvb, w1t, w1v)
         dev = xt.device
         D, H = xt.shape[2], w1t.shape[0]
         sides, casts = [], []
-        for (xa, ma, xb, mb, w1, b1, w2, b2) in ((xt, mt, xtb, mtb, w1t, b1t, w2t, b2t), (xv, mv, xvb, mvb, w1v, b1v, w2v, b2v)):
+        for i, (xa, ma, xb, mb, w1, b1, w2, b2) in enumerate(((xt, mt, xtb, mtb, w1t, b1t, w2t, b2t),
+                                                              (xv, mv, xvb, mvb, w1v, b1v, w2v, b2v))):
             Ra, N = xa.shape[0], xa.shape[1]
             Rb = xb.shape[0] if xb is not None else 0
             if Rb and tuple(xb.shape[1:]) != (N, D):
                 raise RuntimeError("token_weights: batch and bank tokens differ in shape")
             Ta, Tb = Ra * N, Rb * N
-            xbf = torch.empty(Ta + Tb, D, dtype=torch.bfloat16, device=dev)
             w1bf = torch.empty(H, D, dtype=torch.bfloat16, device=dev)
-            casts += [(_f32c(xa), xbf), (_f32c(w1), w1bf)]
-            if Rb:
-                casts.append((_f32c(xb), xbf[Ta:]))
+            if bank_bf16 is not None:
+                xbf = bank_bf16[i]
+                if tuple(xbf.shape) != (Ta + Tb, D) or xbf.dtype != torch.bfloat16:
+                    raise RuntimeError("token_weights: persistent bank operand does not match batch + bank tokens")
+                casts += [(_f32c(xa), xbf), (_f32c(w1), w1bf)]
+            else:
+                xbf = torch.empty(Ta + Tb, D, dtype=torch.bfloat16, device=dev)
+                casts += [(_f32c(xa), xbf), (_f32c(w1), w1bf)]
+                if Rb:
+                    casts.append((_f32c(xb), xbf[Ta:]))
             sides.append(dict(Ra=Ra, Rb=Rb, N=N, Ta=Ta, Tb=Tb, xbf=xbf, w1bf=w1bf, ma=_mask(ma), mb=_mask(mb) if Rb else None,
                               b1=_f32c(b1), w2=_f32c(w2).reshape(-1), b2=_f32c(b2).reshape(-1), xshape=xa.shape))
         _cast_multi(casts)
@@ -769,11 +778,11 @@ class TokenWeightsPairFunction(torch.autograd.Function):
                         r["dw1"], s_[:H] if need[base + 1] else None, s_[H:2 * H].reshape(1, H) if need[base + 2] else None,
                         s_[2 * H:] if need[base + 3] else None))
         (dxt, dw1t, db1t, dw2t, db2t), (dxv, dw1v, db1v, dw2v, db2v) = out
-        return (dxt, None, None, None, dxv, None, None, None, dw1t, db1t, dw2t, db2t, dw1v, db1v, dw2v, db2v)
+        return (dxt, None, None, None, dxv, None, None, None, dw1t, db1t, dw2t, db2t, dw1v, db1v, dw2v, db2v, None)
 
 
 def token_weights_pair(text_mlp, video_mlp, text, text_mask, video, video_mask, mode, bank_t=None, bank_mt=None,
-                       bank_v=None, bank_mv=None):
+                       bank_v=None, bank_mv=None, bank_bf16=None):
     """(tw, tw_bank, vw, vw_bank): both token-weight MLPs of a step.  bf16 mode on the tcgen05 GEMM: one merged node
     (TokenWeightsPairFunction); any other mode: the two per-modality nodes, the video one on a forked stream."""
     pt = text_mlp if isinstance(text_mlp, (tuple, list)) else mlp_params(text_mlp)
@@ -781,7 +790,8 @@ def token_weights_pair(text_mlp, video_mlp, text, text_mask, video, video_mask, 
     D, H = text.shape[2], pt[0].shape[0]
     if (mlp_mode(mode) == MLP_BF16 and USE_OWN_GEMM and D % 8 == 0 and H % 16 == 0 and text.shape[1] <= 128
             and video.shape[1] <= 128 and video.shape[2] == D and pv[0].shape[0] == H):
-        return TokenWeightsPairFunction.apply(text, text_mask, bank_t, bank_mt, video, video_mask, bank_v, bank_mv, *pt, *pv)
+        return TokenWeightsPairFunction.apply(text, text_mask, bank_t, bank_mt, video, video_mask, bank_v, bank_mv, *pt, *pv,
+                                              bank_bf16)
     with ForkJoin(1, offset=5) as fj:
         tw, tw_mb = token_weights(pt, text, text_mask, mode, bank_t, bank_mt)
         with fj.on(0):

@@ -105,7 +105,7 @@ class ShardedPrologue:
     MLP evaluations (modeling._sharded_losses) — the NCCL collectives overlap them."""
 
     def __init__(self, text_l, video_l, gt_l, gv_l, tm_l, vm_l, mb_feat_t, mb_feat_v, mb_mask_t, mb_mask_v, hp,
-                 idx_l=None):
+                 idx_l=None, bank_ring=None):
         cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
         _req_cuda(text_l, video_l, gt_l, gv_l, mb_feat_t, mb_feat_v)
         self.hp = hp
@@ -146,7 +146,10 @@ class ShardedPrologue:
         gall = packed[:, o1:o2].view(torch.float32).reshape(B, 2, d)
         self.g2.copy_(gall[:, 0]); self.v2.copy_(gall[:, 1])
         self.idx_all = packed[:, o2:].view(torch.int64).reshape(B)
-        self.mtm, self.mvm = _mask(mb_mask_t), _mask(mb_mask_v)
+        self.bank_static = bank_ring is not None
+        if self.bank_static and (not fk_ or bank_ring.x3 != x3):
+            raise RuntimeError("bank ring: needs the fused tensor-core path in the precision it was built for")
+        self.mtm, self.mvm = (bank_ring.mask_t, bank_ring.mask_v) if self.bank_static else (_mask(mb_mask_t), _mask(mb_mask_v))
         self.bf, self.fusedk = bf, fk = bf_, fk_
         # Fused (bf16) path = "exchange" design: a rank contracts only ITS text rows against all videos (P = S[rows_r,
         # :]); the column block the video->text direction needs is assembled from the other ranks' P by an
@@ -161,8 +164,11 @@ class ShardedPrologue:
             self.T = Prepared(self.text, bf16=bf, colsum=True, mask=None, defer=True)
             self.Tl = self.T.block(lo, b)
         self.V = Prepared(self.video, bf16=bf, colsum=True, mask=self.vm if fk else None, defer=True, split=ry)
-        self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk, split=rx)
-        self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk, split=ry)
+        if self.bank_static:
+            self.MT, self.MV = bank_ring.MT, bank_ring.MV
+        else:
+            self.MT = Prepared(mb_feat_t, bf16=bf, mask=self.mtm if fk else None, defer=True, f32=not fk, split=rx)
+            self.MV = Prepared(mb_feat_v, bf16=bf, mask=self.mvm if fk else None, defer=True, f32=not fk, split=ry)
         self.Vl = self.V.block(lo, b)
         self.t_rows = B * nt
         self.GG = torch.empty(2, B, B, **f32)              # [G ; G^T], replicated
@@ -184,9 +190,12 @@ class ShardedPrologue:
     def run_text_side(self):
         bprec = self.hp[9]
         if self.a2a:
-            self.MT.run()
+            if not self.bank_static:
+                self.MT.run()
             self.Tl.run()
-            self.MT.bwd_source(bprec); self.Tl.bwd_source(bprec)
+            self.Tl.bwd_source(bprec)
+            if not self.bank_static:
+                self.MT.bwd_source(bprec)
             # column mean over ALL text tokens (modeling.py:419-424) from per-rank column sums: the [W, D] exchange
             # rides with the gather of the video token weights in the head forward (finish_text_centrality)
             torch.sum(self.Tl.partials, dim=0, keepdim=True, out=self.tsum_l)
@@ -215,10 +224,13 @@ class ShardedPrologue:
     def run_video_side(self):
         bprec = self.hp[9]
         dist.all_gather_into_tensor(self.video, self.video_l)        # exchange 1b
-        self.MV.run()
+        if not self.bank_static:
+            self.MV.run()
         self.V.run()
         if self.bf:
-            self.MV.bwd_source(bprec); self.V.bwd_source(bprec)
+            self.V.bwd_source(bprec)
+            if not self.bank_static:
+                self.MV.bwd_source(bprec)
         self._centrality(self.V.partials, self.V.rows, 1)
 
     def run_global(self):
