@@ -82,6 +82,14 @@ int nr_bank_advance(int* head, int64_t n_new, int64_t M, const int64_t* new_ind,
 int nr_bank_insert(const float* new_feat, const int64_t* new_mask, int64_t n_new, int64_t N, int64_t d, int64_t M,
                    const int* head, float* ring_feat, int64_t* ring_mask, void* ring_raw_bf16, void* ring_xn_bf16,
                    int split_role, void* ring_xnT_bf16, int64_t ld, void* stream);
+/* the text and the video rows of a step in one launch */
+typedef struct {
+  const float* new_feat; const int64_t* new_mask; int64_t N;
+  float* ring_feat; int64_t* ring_mask; void* ring_raw_bf16; void* ring_xn_bf16; int split_role; void* ring_xnT_bf16;
+  int64_t ld;
+} nr_bank_side;
+int nr_bank_insert_pair(const nr_bank_side* sides, int n_sides, int64_t n_new, int64_t d, int64_t M, const int* head,
+                        void* stream);
 
 /* ---- small exact-fp32 products (CUDA cores) --------------------------------------------------------------------
  * nr_matmul_f32: out[M,N] (+)= op(A)[M,K] X[K,N]; transA != 0: A is stored [K, M].  The global-feature gradients
@@ -122,7 +130,9 @@ typedef struct {
   const float* b1; const float* w2; void* h_bf16; float* logits;       /* forward */
   const void* dh_bf16; float* dw1; float* dx; int64_t T_dx;            /* backward */
 } nr_mlp_side;
-int nr_mlp_fwd_pair(const nr_mlp_side* sides, int n_sides, int64_t D, int64_t H, void* stream);
+/* reserve_sms: CTAs the persistent grid leaves free (the forward runs next to the single-CTA Sinkhorn kernel, which
+ * needs a whole SM's registers and would otherwise wait for the first GEMM CTA to retire) */
+int nr_mlp_fwd_pair(const nr_mlp_side* sides, int n_sides, int64_t D, int64_t H, int reserve_sms, void* stream);
 int nr_mlp_bwd_pair(const nr_mlp_side* sides, int n_sides, int64_t D, int64_t H, void* stream);
 
 /* chunks of 32 token rows: column count of the partial-sum buffer of nr_token_weights_bwd */
@@ -207,6 +217,13 @@ int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int n_jobs, int64_t Nx, int64
 int nr_maxsim2_bwd_w(const float* pmax_x, const float* pmax_y, const float* dH, int64_t dh_sr, int64_t dh_sc,
                      float dh_scale, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, float* dwx, float* dwy,
                      void* stream);
+/* the same for up to 3 pairs in ONE launch (the batch pair and the two bank pairs of a step); gradients that
+ * several pairs share (the text weights of the batch pair and of the text-vs-bank pair, ...) accumulate atomically */
+typedef struct {
+  const float* pmax_x; const float* pmax_y; const float* dH; int64_t dh_sr, dh_sc; float dh_scale;
+  int64_t Rx, Ry; float* dwx; float* dwy;
+} nr_maxsim2_bwd_w_job;
+int nr_maxsim2_bwd_w_multi(const nr_maxsim2_bwd_w_job* jobs, int n_jobs, int64_t Nx, int64_t Ny, void* stream);
 /* bf16 operand copy [rows, d] -> transposed [d, ld] (ld >= rows, multiple of 8): the K-major source
  * operand of the tensor-core backward contractions. */
 int nr_transpose_tokens_bf16(const void* xn_bf16, int64_t rows, int64_t d, void* out, int64_t ld, void* stream);

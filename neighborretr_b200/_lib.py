@@ -28,6 +28,7 @@ SIGNATURES = {
     "nr_prep_tokens_bwd": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P, _I, _P]),
     "nr_bank_advance": (_I, [_P, _I64, _I64, _P, _P, _P]),
     "nr_bank_insert": (_I, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, _P, _P, _P, _I, _P, _I64, _P]),
+    "nr_bank_insert_pair": (_I, [_P, _I, _I64, _I64, _I64, _P, _P]),
     "nr_matmul_f32": (_I, [_P, _I64, _I, _P, _I64, _I64, _I64, _I64, _P, _I64, _I, _P]),
     "nr_matvec_small": (_I, [_P, _I64, _I64, _I, _P, _P, _P, _P]),
     "nr_cast_bf16": (_I, [_P, _P, _I64, _P]),
@@ -36,7 +37,7 @@ SIGNATURES = {
     "nr_token_softmax": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "nr_mlp_bwd_dx": (_I, [_P, _I64, _I64, _P, _I64, _P, _I, _P]),
     "nr_mlp_bwd_dw1": (_I, [_P, _I64, _I64, _P, _I64, _P, _P]),
-    "nr_mlp_fwd_pair": (_I, [_P, _I, _I64, _I64, _P]),
+    "nr_mlp_fwd_pair": (_I, [_P, _I, _I64, _I64, _I, _P]),
     "nr_mlp_bwd_pair": (_I, [_P, _I, _I64, _I64, _P]),
     "nr_mlp_chunks": (_I64, [_I64]),
     "nr_token_weights_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _P, _P]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "nr_maxsim2_fwd": (_I, [_P, _I, _I64, _I64, _I64, _P, _P]),
     "nr_maxsim2_bwd": (_I, [_P, _I, _I64, _I64, _I64, _P]),
     "nr_maxsim2_bwd_w": (_I, [_P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _P, _P, _P]),
+    "nr_maxsim2_bwd_w_multi": (_I, [_P, _I, _I64, _I64, _P]),
     "nr_transpose_tokens_bf16": (_I, [_P, _I64, _I64, _P, _I64, _P]),
     "nr_maxsim_bwd_x": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
     "nr_maxsim_bwd_y": (_I, [_I, _P, _I64, _P, _P, _P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _I64, _P, _P]),
@@ -78,6 +80,18 @@ class MaxSim2Problem(ctypes.Structure):
     _fields_ = [("x_bf16", _P), ("y_bf16", _P), ("wx", _P), ("wy", _P), ("Rx", _I64), ("Ry", _I64), ("alpha", _F),
                 ("out", _P), ("out_sr", _I64), ("out_sc", _I64), ("out2", _P), ("out2_sr", _I64), ("out2_sc", _I64),
                 ("pmax_x", _P), ("ystar", _P), ("pmax_y", _P), ("xstar", _P)]
+
+
+class MaxSim2BwdWJob(ctypes.Structure):
+    """nr_maxsim2_bwd_w_job of include/nrhead.h (field order and types must match)."""
+    _fields_ = [("pmax_x", _P), ("pmax_y", _P), ("dH", _P), ("dh_sr", _I64), ("dh_sc", _I64), ("dh_scale", _F),
+                ("Rx", _I64), ("Ry", _I64), ("dwx", _P), ("dwy", _P)]
+
+
+class BankSide(ctypes.Structure):
+    """nr_bank_side of include/nrhead.h (field order and types must match)."""
+    _fields_ = [("new_feat", _P), ("new_mask", _P), ("N", _I64), ("ring_feat", _P), ("ring_mask", _P), ("ring_raw_bf16", _P),
+                ("ring_xn_bf16", _P), ("split_role", _I), ("ring_xnT_bf16", _P), ("ld", _I64)]
 
 
 class MlpSide(ctypes.Structure):

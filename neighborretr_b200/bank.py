@@ -18,9 +18,11 @@ the bank are only ever averaged over the bank (until_module.py:181), so their or
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
-from . import ops
+from . import _lib, ops
 from .ops import Prepared, _call, _f32c, _mask, _p, _stream
 
 NAMES = ("mb_ind", "mb_feat_t", "mb_feat_v", "mb_mask_t", "mb_mask_v")
@@ -108,12 +110,20 @@ class BankRing:
         st = _stream()
         ind = ind.reshape(-1).to(torch.int64).contiguous()
         _call("nr_bank_advance", _p(self.head_dev), n_new, self.M, _p(ind), _p(self.ind), st)
-        for new, mask, feat, rmask, xn, xnT, ld, n, role, mlp in (
+        arr = (_lib.BankSide * 2)()
+        keep = []
+        for i, (new, mask, feat, rmask, xn, xnT, ld, n, role, mlp) in enumerate((
                 (feat_t, mask_t, self.feat_t, self.mask_t, self.xn_t, self.xnT_t, self.ld_t, self.nt, self.roles[0], self.mlp_t),
-                (feat_v, mask_v, self.feat_v, self.mask_v, self.xn_v, self.xnT_v, self.ld_v, self.nv, self.roles[1], self.mlp_v)):
+                (feat_v, mask_v, self.feat_v, self.mask_v, self.xn_v, self.xnT_v, self.ld_v, self.nv, self.roles[1], self.mlp_v))):
             raw = mlp[self.batch_rows * n:] if mlp is not None else None
-            _call("nr_bank_insert", _p(_f32c(new.detach())), _p(_mask(mask)), n_new, n, self.d, self.M, _p(self.head_dev),
-                  _p(feat), _p(rmask), _p(raw), _p(xn), role, _p(xnT), ld, st)
+            newc, maskc = _f32c(new.detach()), _mask(mask)
+            keep += [newc, maskc]
+            a = arr[i]
+            a.new_feat, a.new_mask, a.N = newc.data_ptr(), maskc.data_ptr(), n
+            a.ring_feat, a.ring_mask = feat.data_ptr(), rmask.data_ptr()
+            a.ring_raw_bf16 = raw.data_ptr() if raw is not None else None
+            a.ring_xn_bf16, a.split_role, a.ring_xnT_bf16, a.ld = xn.data_ptr(), role, xnT.data_ptr(), ld
+        _call("nr_bank_insert_pair", ctypes.cast(arr, ctypes.c_void_p), 2, n_new, self.d, self.M, _p(self.head_dev), st)
         self.head = (self.head - n_new) % self.M
         self.version += 1
         self._export = None

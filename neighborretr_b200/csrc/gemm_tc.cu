@@ -315,7 +315,7 @@ struct GemmJob {
   const float* bias; const float* w2; float* logits;
 };
 
-static int gemm_launch(const GemmJob* jobs, int njobs, cudaStream_t stream) {
+static int gemm_launch(const GemmJob* jobs, int njobs, cudaStream_t stream, int reserve_sms = 0) {
   NR_CHECK_ARG(jobs && njobs >= 1 && njobs <= G_MAX_PROB, "nr_gemm: 1..%d problems per launch (got %d)", G_MAX_PROB, njobs);
   int dev = 0, sms = 0;
   NR_CUDA(cudaGetDevice(&dev));
@@ -367,7 +367,9 @@ static int gemm_launch(const GemmJob* jobs, int njobs, cudaStream_t stream) {
     NR_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int grid = a.n_items < sms ? a.n_items : sms;
+  int cap = sms - reserve_sms;
+  if (cap < 1) cap = 1;
+  const int grid = a.n_items < cap ? a.n_items : cap;
   gemm_bf16_tc_kernel<<<grid, G_THREADS, smem, stream>>>(a);
   NR_CHECK_LAUNCH("nr_gemm");
   return 0;
@@ -520,14 +522,14 @@ extern "C" int nr_mlp_bwd_dw1(const void* dh_bf16, int64_t T, int64_t H, const v
 }
 
 /* Both modalities in ONE launch each way (nr_mlp_pair of include/nrhead.h). */
-extern "C" int nr_mlp_fwd_pair(const nr_mlp_side* s, int n, int64_t D, int64_t H, void* stream) {
+extern "C" int nr_mlp_fwd_pair(const nr_mlp_side* s, int n, int64_t D, int64_t H, int reserve_sms, void* stream) {
   NR_CHECK_ARG(s && n >= 1 && n <= 2, "nr_mlp_fwd_pair: 1 or 2 sides");
   GemmJob j[2];
   for (int i = 0; i < n; ++i) {
     NR_CHECK_ARG(s[i].b1 && s[i].w2 && s[i].logits, "nr_mlp_fwd_pair: side %d has a null pointer", i);
     j[i] = job_fwd(s[i].x_bf16, s[i].T, D, s[i].w1_bf16, H, s[i].b1, s[i].w2, s[i].h_bf16, s[i].logits);
   }
-  return gemm_launch(j, n, (cudaStream_t)stream);
+  return gemm_launch(j, n, (cudaStream_t)stream, reserve_sms < 0 ? 0 : reserve_sms);
 }
 
 extern "C" int nr_mlp_bwd_pair(const nr_mlp_side* s, int n, int64_t D, int64_t H, void* stream) {

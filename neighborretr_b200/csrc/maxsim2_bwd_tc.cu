@@ -342,44 +342,56 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
 }
 
 // dwx[rx,x] += scale * sum_ry g[rx,ry] pmax_x[rx,ry,x]   (blocks [0,Rx): one X sample each)
-// dwy[ry,y] += scale * sum_rx g[rx,ry] pmax_y[rx,ry,y]   (remaining blocks: 256 columns x a slice of rx, atomics)
-__global__ void __launch_bounds__(256)
-maxsim2_bwd_w_kernel(const float* __restrict__ pmax_x, const float* __restrict__ pmax_y, const float* __restrict__ dH,
-                     int64_t dh_sr, int64_t dh_sc, float scale, int Rx, int Nx, int Ry, int Ny, int nbx, int ncb,
-                     int rsplit, float* __restrict__ dwx, float* __restrict__ dwy) {
+// dwy[ry,y] += scale * sum_rx g[rx,ry] pmax_y[rx,ry,y]   (remaining blocks: 256 columns x a slice of rx)
+// Up to 3 pairs (the batch pair and the two bank pairs of a step) share ONE launch; outputs shared between pairs
+// (e.g. the text weights of the batch pair and of the text-vs-bank pair) are accumulated with atomics.
+struct BwdWJob {
+  const float* pmax_x; const float* pmax_y; const float* dH;
+  int64_t dh_sr, dh_sc; float scale;
+  int Rx, Nx, Ry, Ny, nbx, ncb, rsplit, blk0;
+  float* dwx; float* dwy;
+};
+struct BwdWArgs { BwdWJob j[3]; int njobs; };
+
+__global__ void __launch_bounds__(256) maxsim2_bwd_w_kernel(const BwdWArgs a) {
   __shared__ float part[256];
+  int ji = 0;
+  while (ji + 1 < a.njobs && (int)blockIdx.x >= a.j[ji + 1].blk0) ++ji;
+  const BwdWJob& J = a.j[ji];
+  const int blk = (int)blockIdx.x - J.blk0;
   const int tid = threadIdx.x;
-  if ((int)blockIdx.x < nbx) {
-    const int rx = blockIdx.x;
+  const int Nx = J.Nx, Ny = J.Ny, Rx = J.Rx, Ry = J.Ry;
+  if (blk < J.nbx) {
+    const int rx = blk;
     const int lanes = 256 / Nx;            // ry-lanes per x (Nx <= 128)
     const int x = tid % Nx, l = tid / Nx;
     float s = 0.f;
     if (l < lanes) {
 #pragma unroll 8
       for (int ry = l; ry < Ry; ry += lanes)
-        s += dH[(int64_t)rx * dh_sr + (int64_t)ry * dh_sc] * pmax_x[((int64_t)rx * Ry + ry) * Nx + x];
+        s += J.dH[(int64_t)rx * J.dh_sr + (int64_t)ry * J.dh_sc] * J.pmax_x[((int64_t)rx * Ry + ry) * Nx + x];
     }
     part[tid] = s;
     __syncthreads();
     if (tid < Nx) {
       float t = 0.f;
       for (int qq = 0; qq < lanes; ++qq) t += part[qq * Nx + tid];
-      dwx[(int64_t)rx * Nx + tid] += t * scale;
+      atomicAdd(J.dwx + (int64_t)rx * Nx + tid, t * J.scale);
     }
   } else {
-    const int bb = blockIdx.x - nbx;
-    const int cb = bb % ncb, sl = bb / ncb;
+    const int bb = blk - J.nbx;
+    const int cb = bb % J.ncb, sl = bb / J.ncb;
     const int c = cb * 256 + tid;
     const int cols = Ry * Ny;
     if (c >= cols) return;
     const int ry = c / Ny;
-    const int per = (Rx + rsplit - 1) / rsplit;
+    const int per = (Rx + J.rsplit - 1) / J.rsplit;
     const int r0 = sl * per, r1 = min(Rx, r0 + per);
     float s = 0.f;
 #pragma unroll 4
     for (int rx = r0; rx < r1; ++rx)
-      s += dH[(int64_t)rx * dh_sr + (int64_t)ry * dh_sc] * pmax_y[(int64_t)rx * cols + c];
-    atomicAdd(dwy + c, s * scale);
+      s += J.dH[(int64_t)rx * J.dh_sr + (int64_t)ry * J.dh_sc] * J.pmax_y[(int64_t)rx * cols + c];
+    atomicAdd(J.dwy + c, s * J.scale);
   }
 }
 
@@ -483,23 +495,49 @@ extern "C" int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int njobs, int64_t
   return 0;
 }
 
-extern "C" int nr_maxsim2_bwd_w(const float* pmax_x, const float* pmax_y, const float* dH, int64_t dh_sr, int64_t dh_sc,
-                                float dh_scale, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, float* dwx, float* dwy,
-                                void* stream) {
+static int bwd_w_fill(BwdWJob& J, const float* pmax_x, const float* pmax_y, const float* dH, int64_t dh_sr, int64_t dh_sc,
+                      float dh_scale, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, float* dwx, float* dwy, int& blocks) {
   NR_CHECK_ARG(dH && Rx > 0 && Ry > 0 && Nx > 0 && Nx <= NR_MAX_TOKENS && Ny > 0 && Ny <= NR_MAX_TOKENS,
                "nr_maxsim2_bwd_w: bad arguments");
   NR_CHECK_ARG((!dwx || pmax_x) && (!dwy || pmax_y) && (dwx || dwy), "nr_maxsim2_bwd_w: missing pmax for a requested gradient");
-  const int nbx = dwx ? (int)Rx : 0;
-  const int ncb = dwy ? (int)((Ry * Ny + 255) / 256) : 0;
-  int rsplit = 1;
+  J.pmax_x = pmax_x; J.pmax_y = pmax_y; J.dH = dH; J.dh_sr = dh_sr; J.dh_sc = dh_sc; J.scale = dh_scale;
+  J.Rx = (int)Rx; J.Nx = (int)Nx; J.Ry = (int)Ry; J.Ny = (int)Ny; J.dwx = dwx; J.dwy = dwy;
+  J.nbx = dwx ? (int)Rx : 0;
+  J.ncb = dwy ? (int)((Ry * Ny + 255) / 256) : 1;
+  J.rsplit = 1;
   if (dwy) {
-    rsplit = (296 + ncb - 1) / ncb;               // ~2 CTAs per SM in total
-    if (rsplit > Rx) rsplit = (int)Rx;
-    if (rsplit < 1) rsplit = 1;
+    J.rsplit = (296 + J.ncb - 1) / J.ncb;               // ~2 CTAs per SM in total
+    if (J.rsplit > Rx) J.rsplit = (int)Rx;
+    if (J.rsplit < 1) J.rsplit = 1;
   }
-  const int grid = nbx + ncb * rsplit;
-  maxsim2_bwd_w_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pmax_x, pmax_y, dH, dh_sr, dh_sc, dh_scale, (int)Rx,
-                                                               (int)Nx, (int)Ry, (int)Ny, nbx, ncb, rsplit, dwx, dwy);
+  J.blk0 = blocks;
+  blocks += J.nbx + (dwy ? J.ncb * J.rsplit : 0);
+  return 0;
+}
+
+extern "C" int nr_maxsim2_bwd_w(const float* pmax_x, const float* pmax_y, const float* dH, int64_t dh_sr, int64_t dh_sc,
+                                float dh_scale, int64_t Rx, int64_t Nx, int64_t Ry, int64_t Ny, float* dwx, float* dwy,
+                                void* stream) {
+  BwdWArgs a{};
+  int blocks = 0;
+  if (int e = bwd_w_fill(a.j[0], pmax_x, pmax_y, dH, dh_sr, dh_sc, dh_scale, Rx, Nx, Ry, Ny, dwx, dwy, blocks)) return e;
+  a.njobs = 1;
+  maxsim2_bwd_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
   NR_CHECK_LAUNCH("nr_maxsim2_bwd_w");
+  return 0;
+}
+
+/* up to 3 pairs in one launch (see nr_maxsim2_bwd_w_job in include/nrhead.h) */
+extern "C" int nr_maxsim2_bwd_w_multi(const nr_maxsim2_bwd_w_job* jobs, int njobs, int64_t Nx, int64_t Ny, void* stream) {
+  NR_CHECK_ARG(jobs && njobs >= 1 && njobs <= 3, "nr_maxsim2_bwd_w_multi: 1..3 jobs");
+  BwdWArgs a{};
+  int blocks = 0;
+  for (int i = 0; i < njobs; ++i)
+    if (int e = bwd_w_fill(a.j[i], jobs[i].pmax_x, jobs[i].pmax_y, jobs[i].dH, jobs[i].dh_sr, jobs[i].dh_sc, jobs[i].dh_scale,
+                           jobs[i].Rx, Nx, jobs[i].Ry, Ny, jobs[i].dwx, jobs[i].dwy, blocks))
+      return e;
+  a.njobs = njobs;
+  maxsim2_bwd_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  NR_CHECK_LAUNCH("nr_maxsim2_bwd_w_multi");
   return 0;
 }

@@ -346,46 +346,62 @@ namespace nr {
 __global__ void __launch_bounds__(256)
 gram_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, int Ra, int Rb, int d,
                 float* __restrict__ out, float* __restrict__ outT) {
-  __shared__ float As[2][32][33], Bs[2][32][33];
+  // k-chunks of 128 (float4 loads, the next chunk's loads in flight during the FMAs): 4 dependent global round trips
+  // for d = 512 instead of 16 — this kernel heads the longest chain of the forward (G -> Sinkhorn)
+  constexpr int KC = 128;
+  __shared__ __align__(16) float As[32][KC + 4], Bs[32][KC + 4];
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  // global -> registers one k-chunk ahead, registers -> the other smem buffer: one barrier per chunk and the
-  // global-load latency overlaps the FMAs of the previous chunk
-  float ra[4], rb[4];
+  float4 ra[4], rb[4];
+  const bool vec = (d % 4 == 0);
   auto gload = [&](int k0) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int e = it * 256 + threadIdx.x, r = e >> 5, c = e & 31;
-      ra[it] = (i0 + r < Ra && k0 + c < d) ? a[(int64_t)(i0 + r) * d + k0 + c] : 0.f;
-      rb[it] = (j0 + r < Rb && k0 + c < d) ? b[(int64_t)(j0 + r) * d + k0 + c] : 0.f;
+      const int e = it * 256 + threadIdx.x, r = e >> 5, c = (e & 31) * 4;
+      const int k = k0 + c;
+      if (vec && k + 3 < d) {
+        ra[it] = (i0 + r < Ra) ? *reinterpret_cast<const float4*>(a + (int64_t)(i0 + r) * d + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        rb[it] = (j0 + r < Rb) ? *reinterpret_cast<const float4*>(b + (int64_t)(j0 + r) * d + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        float t[4], u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          t[q] = (i0 + r < Ra && k + q < d) ? a[(int64_t)(i0 + r) * d + k + q] : 0.f;
+          u[q] = (j0 + r < Rb && k + q < d) ? b[(int64_t)(j0 + r) * d + k + q] : 0.f;
+        }
+        ra[it] = make_float4(t[0], t[1], t[2], t[3]);
+        rb[it] = make_float4(u[0], u[1], u[2], u[3]);
+      }
     }
   };
-  auto sstore = [&](int buf) {
+  auto sstore = [&]() {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int e = it * 256 + threadIdx.x, r = e >> 5, c = e & 31;
-      As[buf][r][c] = ra[it];
-      Bs[buf][r][c] = rb[it];
+      const int e = it * 256 + threadIdx.x, r = e >> 5, c = (e & 31) * 4;
+      *reinterpret_cast<float4*>(&As[r][c]) = ra[it];
+      *reinterpret_cast<float4*>(&Bs[r][c]) = rb[it];
     }
   };
   gload(0);
-  sstore(0);
-  __syncthreads();
-  int buf = 0;
-  for (int k0 = 0; k0 < d; k0 += 32) {
-    const bool more = k0 + 32 < d;
-    if (more) gload(k0 + 32);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float a0 = As[buf][ty * 2][k], a1 = As[buf][ty * 2 + 1][k];
-      const float b0 = Bs[buf][tx * 2][k], b1 = Bs[buf][tx * 2 + 1][k];
-      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
-      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
-    }
-    if (more) sstore(buf ^ 1);
+  for (int k0 = 0; k0 < d; k0 += KC) {
+    sstore();
     __syncthreads();
-    buf ^= 1;
+    if (k0 + KC < d) gload(k0 + KC);
+#pragma unroll 8
+    for (int k = 0; k < KC; k += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[ty * 2][k]), a1 = *reinterpret_cast<const float4*>(&As[ty * 2 + 1][k]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[tx * 2][k]), b1 = *reinterpret_cast<const float4*>(&Bs[tx * 2 + 1][k]);
+      acc[0][0] = fmaf(a0.x, b0.x, acc[0][0]); acc[0][0] = fmaf(a0.y, b0.y, acc[0][0]);
+      acc[0][0] = fmaf(a0.z, b0.z, acc[0][0]); acc[0][0] = fmaf(a0.w, b0.w, acc[0][0]);
+      acc[0][1] = fmaf(a0.x, b1.x, acc[0][1]); acc[0][1] = fmaf(a0.y, b1.y, acc[0][1]);
+      acc[0][1] = fmaf(a0.z, b1.z, acc[0][1]); acc[0][1] = fmaf(a0.w, b1.w, acc[0][1]);
+      acc[1][0] = fmaf(a1.x, b0.x, acc[1][0]); acc[1][0] = fmaf(a1.y, b0.y, acc[1][0]);
+      acc[1][0] = fmaf(a1.z, b0.z, acc[1][0]); acc[1][0] = fmaf(a1.w, b0.w, acc[1][0]);
+      acc[1][1] = fmaf(a1.x, b1.x, acc[1][1]); acc[1][1] = fmaf(a1.y, b1.y, acc[1][1]);
+      acc[1][1] = fmaf(a1.z, b1.z, acc[1][1]); acc[1][1] = fmaf(a1.w, b1.w, acc[1][1]);
+    }
+    __syncthreads();
   }
 #pragma unroll
   for (int p = 0; p < 2; ++p)
@@ -596,72 +612,98 @@ __global__ void bank_advance_kernel(int* __restrict__ head, int n_new, int M, co
   if (threadIdx.x == 0) *head = h;
 }
 
-__global__ void __launch_bounds__(PREP_WARPS * 32)
-bank_insert_kernel(const float* __restrict__ x, const int64_t* __restrict__ mask, int rows, int N, int d, int M,
-                   const int* __restrict__ head, float* __restrict__ ring_feat, int64_t* __restrict__ ring_mask,
-                   __nv_bfloat16* __restrict__ ring_raw, __nv_bfloat16* __restrict__ ring_xn, int split,
-                   __nv_bfloat16* __restrict__ ring_xnT, int64_t ld) {
+constexpr int BI_ROWS = 32;           // new token rows per CTA (= lanes of the transposed write)
+
+struct BankSide {
+  const float* x; const int64_t* mask; int rows, N;
+  float* ring_feat; int64_t* ring_mask; __nv_bfloat16* ring_raw; __nv_bfloat16* ring_xn; __nv_bfloat16* ring_xnT;
+  int64_t ld; int split, blk0;
+};
+struct BankInsertArgs { BankSide s[2]; int nsides, d, M; const int* head; };
+
+// One CTA = 32 consecutive new token rows of one modality: each warp normalises 4 rows (float4 loads, warp-shuffle
+// norm) and stores the row-major outputs directly; the bf16 hi (and lo) values are also staged in shared memory so
+// that the transposed copy is written with lane = token: 32 consecutive 2-byte elements per dim instead of one
+// 2-byte store per (token, dim) scattered over `ld`-strided rows.
+__global__ void __launch_bounds__(256) bank_insert_kernel(const BankInsertArgs a) {
+  extern __shared__ __align__(16) uint8_t bi_smem[];
+  int si = 0;
+  while (si + 1 < a.nsides && (int)blockIdx.x >= a.s[si + 1].blk0) ++si;
+  const BankSide& S = a.s[si];
+  const int d = a.d, M = a.M, N = S.N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * PREP_WARPS + warp;
-  if (row >= rows) return;
-  const int j = row / N, n = row - j * N;
-  const int slot = (*head + j) % M;
-  const int64_t drow = (int64_t)slot * N + n;
-  const float* xr = x + (int64_t)row * d;
-  float4 v[PREP_MAXQ];
-  float ss = 0.f;
+  const int row0 = ((int)blockIdx.x - S.blk0) * BI_ROWS;
+  const int sld = d + 2;                                          // padded row stride (elements): conflict-free columns
+  __nv_bfloat16* hi_s = reinterpret_cast<__nv_bfloat16*>(bi_smem);
+  __nv_bfloat16* lo_s = hi_s + BI_ROWS * sld;
+  __shared__ int64_t drow_s[BI_ROWS];
+  const int head = *a.head;
+  for (int rr = warp; rr < BI_ROWS; rr += 8) {
+    const int row = row0 + rr;
+    if (row >= S.rows) { if (lane == 0) drow_s[rr] = -1; continue; }
+    const int j = row / N, n = row - j * N;
+    const int64_t drow = (int64_t)((head + j) % M) * N + n;
+    if (lane == 0) drow_s[rr] = drow;
+    const float* xr = S.x + (int64_t)row * d;
+    float4 v[PREP_MAXQ];
+    float ss = 0.f;
 #pragma unroll
-  for (int q = 0; q < PREP_MAXQ; ++q) {
-    const int c = q * 128 + lane * 4;
-    if (c < d) {
-      v[q] = *reinterpret_cast<const float4*>(xr + c);
-      ss += v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w;
+    for (int q = 0; q < PREP_MAXQ; ++q) {
+      const int c = q * 128 + lane * 4;
+      if (c < d) {
+        v[q] = *reinterpret_cast<const float4*>(xr + c);
+        ss += v[q].x * v[q].x + v[q].y * v[q].y + v[q].z * v[q].z + v[q].w * v[q].w;
+      }
     }
-  }
-  ss = warp_sum(ss);
-  const float denom = fmaxf(sqrtf(ss), 1e-12f);
-  const bool live = mask ? (mask[row] != 0) : true;
-  if (ring_mask && lane == 0) ring_mask[drow] = mask ? mask[row] : 1;
-  const int kd = split ? 3 * d : d;
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    const bool live = S.mask ? (S.mask[row] != 0) : true;
+    if (S.ring_mask && lane == 0) S.ring_mask[drow] = S.mask ? S.mask[row] : 1;
+    const int kd = S.split ? 3 * d : d;
 #pragma unroll
-  for (int q = 0; q < PREP_MAXQ; ++q) {
-    const int c = q * 128 + lane * 4;
-    if (c >= d) continue;
-    if (ring_feat) *reinterpret_cast<float4*>(ring_feat + drow * d + c) = v[q];
-    const float f[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
-    if (ring_raw) {
-      __nv_bfloat16 r4[4];
+    for (int q = 0; q < PREP_MAXQ; ++q) {
+      const int c = q * 128 + lane * 4;
+      if (c >= d) continue;
+      if (S.ring_feat) *reinterpret_cast<float4*>(S.ring_feat + drow * d + c) = v[q];
+      const float f[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+      if (S.ring_raw) {
+        __nv_bfloat16 r4[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) r4[e] = __float2bfloat16_rn(f[e]);
-      *reinterpret_cast<uint2*>(ring_raw + drow * d + c) = *reinterpret_cast<uint2*>(r4);
-    }
-    if (ring_xn || ring_xnT) {
+        for (int e = 0; e < 4; ++e) r4[e] = __float2bfloat16_rn(f[e]);
+        *reinterpret_cast<uint2*>(S.ring_raw + drow * d + c) = *reinterpret_cast<uint2*>(r4);
+      }
       __nv_bfloat16 h[4], l[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float nv = live ? f[e] / denom : 0.f;
         h[e] = __float2bfloat16_rn(nv);
         l[e] = __float2bfloat16_rn(live ? nv - __bfloat162float(h[e]) : 0.f);
+        hi_s[rr * sld + c + e] = h[e];
+        if (S.split) lo_s[rr * sld + c + e] = l[e];
       }
-      const uint2 ph = *reinterpret_cast<uint2*>(h), pl = *reinterpret_cast<uint2*>(l);
-      if (ring_xn) {
-        __nv_bfloat16* o = ring_xn + drow * kd + c;
+      if (S.ring_xn) {
+        const uint2 ph = *reinterpret_cast<uint2*>(h), pl = *reinterpret_cast<uint2*>(l);
+        __nv_bfloat16* o = S.ring_xn + drow * kd + c;
         *reinterpret_cast<uint2*>(o) = ph;
-        if (split) {
-          *reinterpret_cast<uint2*>(o + d) = (split == 1) ? pl : ph;
-          *reinterpret_cast<uint2*>(o + 2 * d) = (split == 1) ? ph : pl;
+        if (S.split) {
+          *reinterpret_cast<uint2*>(o + d) = (S.split == 1) ? pl : ph;
+          *reinterpret_cast<uint2*>(o + 2 * d) = (S.split == 1) ? ph : pl;
         }
       }
-      if (ring_xnT) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ring_xnT[(int64_t)(c + e) * ld + drow] = h[e];
-          if (split) {
-            ring_xnT[(int64_t)(d + c + e) * ld + drow] = (split == 1) ? l[e] : h[e];
-            ring_xnT[(int64_t)(2 * d + c + e) * ld + drow] = (split == 1) ? h[e] : l[e];
-          }
-        }
-      }
+    }
+  }
+  if (!S.ring_xnT) return;
+  __syncthreads();
+  // transposed copy: lane = token (consecutive ring rows except across a sample that wraps), warps stride over dims
+  const int64_t drow = drow_s[lane];
+  if (drow < 0) return;
+  for (int c = warp; c < d; c += 8) {
+    const __nv_bfloat16 h = hi_s[lane * sld + c];
+    S.ring_xnT[(int64_t)c * S.ld + drow] = h;
+    if (S.split) {
+      const __nv_bfloat16 l = lo_s[lane * sld + c];
+      S.ring_xnT[(int64_t)(d + c) * S.ld + drow] = (S.split == 1) ? l : h;
+      S.ring_xnT[(int64_t)(2 * d + c) * S.ld + drow] = (S.split == 1) ? h : l;
     }
   }
 }
@@ -676,18 +718,57 @@ extern "C" int nr_bank_advance(int* head, int64_t n_new, int64_t M, const int64_
   return 0;
 }
 
+static int bank_side_fill(nr::BankSide& S, const float* new_feat, const int64_t* new_mask, int64_t n_new, int64_t N,
+                          int64_t M, float* ring_feat, int64_t* ring_mask, void* ring_raw_bf16, void* ring_xn_bf16,
+                          int split_role, void* ring_xnT_bf16, int64_t ld, int& blocks) {
+  NR_CHECK_ARG(new_feat && n_new > 0 && n_new <= M && N > 0, "nr_bank_insert: bad arguments");
+  NR_CHECK_ARG(split_role >= 0 && split_role <= 2 && (!ring_xnT_bf16 || ld >= M * N), "nr_bank_insert: bad split role or ld");
+  S.x = new_feat; S.mask = new_mask; S.rows = (int)(n_new * N); S.N = (int)N;
+  S.ring_feat = ring_feat; S.ring_mask = ring_mask; S.ring_raw = (__nv_bfloat16*)ring_raw_bf16;
+  S.ring_xn = (__nv_bfloat16*)ring_xn_bf16; S.ring_xnT = (__nv_bfloat16*)ring_xnT_bf16; S.ld = ld; S.split = split_role;
+  S.blk0 = blocks;
+  blocks += (S.rows + nr::BI_ROWS - 1) / nr::BI_ROWS;
+  return 0;
+}
+
+static int bank_insert_launch(nr::BankInsertArgs& a, int blocks, cudaStream_t stream) {
+  NR_CHECK_ARG(a.d > 0 && a.d % 4 == 0 && a.d <= 128 * nr::PREP_MAXQ, "nr_bank_insert: d=%d must be a multiple of 4, <= %d", a.d,
+               128 * nr::PREP_MAXQ);
+  const size_t smem = (size_t)2 * nr::BI_ROWS * (a.d + 2) * sizeof(__nv_bfloat16);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NR_CUDA(cudaFuncSetAttribute(nr::bank_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  nr::bank_insert_kernel<<<blocks, 256, smem, stream>>>(a);
+  NR_CHECK_LAUNCH("nr_bank_insert");
+  return 0;
+}
+
 extern "C" int nr_bank_insert(const float* new_feat, const int64_t* new_mask, int64_t n_new, int64_t N, int64_t d,
                               int64_t M, const int* head, float* ring_feat, int64_t* ring_mask, void* ring_raw_bf16,
                               void* ring_xn_bf16, int split_role, void* ring_xnT_bf16, int64_t ld, void* stream) {
-  NR_CHECK_ARG(new_feat && head && n_new > 0 && n_new <= M && N > 0, "nr_bank_insert: bad arguments");
-  NR_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 128 * nr::PREP_MAXQ, "nr_bank_insert: d=%lld must be a multiple of 4, <= %d",
-               (long long)d, 128 * nr::PREP_MAXQ);
-  NR_CHECK_ARG(split_role >= 0 && split_role <= 2 && (!ring_xnT_bf16 || ld >= M * N), "nr_bank_insert: bad split role or ld");
-  const int64_t rows = n_new * N;
-  const int grid = (int)((rows + nr::PREP_WARPS - 1) / nr::PREP_WARPS);
-  nr::bank_insert_kernel<<<grid, nr::PREP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      new_feat, new_mask, (int)rows, (int)N, (int)d, (int)M, head, ring_feat, ring_mask, (__nv_bfloat16*)ring_raw_bf16,
-      (__nv_bfloat16*)ring_xn_bf16, split_role, (__nv_bfloat16*)ring_xnT_bf16, ld);
-  NR_CHECK_LAUNCH("nr_bank_insert");
-  return 0;
+  NR_CHECK_ARG(head, "nr_bank_insert: head is null");
+  nr::BankInsertArgs a{};
+  int blocks = 0;
+  if (int e = bank_side_fill(a.s[0], new_feat, new_mask, n_new, N, M, ring_feat, ring_mask, ring_raw_bf16, ring_xn_bf16,
+                             split_role, ring_xnT_bf16, ld, blocks))
+    return e;
+  a.nsides = 1; a.d = (int)d; a.M = (int)M; a.head = head;
+  return bank_insert_launch(a, blocks, (cudaStream_t)stream);
+}
+
+/* both modalities of a step in one launch */
+extern "C" int nr_bank_insert_pair(const nr_bank_side* sides, int n_sides, int64_t n_new, int64_t d, int64_t M,
+                                   const int* head, void* stream) {
+  NR_CHECK_ARG(sides && n_sides >= 1 && n_sides <= 2 && head, "nr_bank_insert_pair: 1 or 2 sides, head required");
+  nr::BankInsertArgs a{};
+  int blocks = 0;
+  for (int i = 0; i < n_sides; ++i)
+    if (int e = bank_side_fill(a.s[i], sides[i].new_feat, sides[i].new_mask, n_new, sides[i].N, M, sides[i].ring_feat,
+                               sides[i].ring_mask, sides[i].ring_raw_bf16, sides[i].ring_xn_bf16, sides[i].split_role,
+                               sides[i].ring_xnT_bf16, sides[i].ld, blocks))
+      return e;
+  a.nsides = n_sides; a.d = (int)d; a.M = (int)M; a.head = head;
+  return bank_insert_launch(a, blocks, (cudaStream_t)stream);
 }

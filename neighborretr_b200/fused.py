@@ -323,15 +323,10 @@ class HeadFunction(torch.autograd.Function):
                     ops.maxsim2_bwd_multi(jobs, nt, nv, d)
                 with fj.on(2):
                     torch.cuda.current_stream().wait_event(ev_dS)
-                    if need[4] or need[5]:
-                        ops.maxsim2_bwd_w(p1, p2, dS, B, 1, 0.5, B, nt, B, nv, dtw if need[4] else None,
-                                          dvw if need[5] else None)
-                    if need[4] or need[7]:
-                        ops.maxsim2_bwd_w(pA, pB, dc[0], 1, 0, sc, B, nt, M, nv, dtw if need[4] else None,
-                                          dvw_mb if need[7] else None)
-                    if need[6] or need[5]:
-                        ops.maxsim2_bwd_w(pC, pD, dc[1], 0, 1, sc, M, nt, B, nv, dtw_mb if need[6] else None,
-                                          dvw if need[5] else None)
+                    ops.maxsim2_bwd_w_multi([
+                        (p1, p2, dS, B, 1, 0.5, B, B, dtw if need[4] else None, dvw if need[5] else None),
+                        (pA, pB, dc[0], 1, 0, sc, B, M, dtw if need[4] else None, dvw_mb if need[7] else None),
+                        (pC, pD, dc[1], 0, 1, sc, M, B, dtw_mb if need[6] else None, dvw if need[5] else None)], nt, nv)
             else:
                 st = _stream()
                 vs, vld = V.bwd_source(bprec); ts, tld = T.bwd_source(bprec)

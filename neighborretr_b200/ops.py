@@ -376,6 +376,22 @@ def maxsim2_bwd_w(pmax_x, pmax_y, g, g_sr, g_sc, scale, rx, nx, ry, ny, dwx, dwy
           _stream())
 
 
+def maxsim2_bwd_w_multi(jobs, nx, ny):
+    """jobs: (pmax_x, pmax_y, g, g_sr, g_sc, scale, rx, ry, dwx, dwy) tuples (dwx / dwy nullable; jobs without any
+    requested gradient are dropped) -> ONE launch."""
+    jobs = [j for j in jobs if j[8] is not None or j[9] is not None]
+    if not jobs:
+        return
+    arr = (_lib.MaxSim2BwdWJob * len(jobs))()
+    for i, (px, py, g, g_sr, g_sc, scale, rx, ry, dwx, dwy) in enumerate(jobs):
+        a = arr[i]
+        a.pmax_x, a.pmax_y, a.dH = px.data_ptr(), py.data_ptr(), g.data_ptr()
+        a.dh_sr, a.dh_sc, a.dh_scale, a.Rx, a.Ry = g_sr, g_sc, float(scale), rx, ry
+        a.dwx = dwx.data_ptr() if dwx is not None else None
+        a.dwy = dwy.data_ptr() if dwy is not None else None
+    _call("nr_maxsim2_bwd_w_multi", ctypes.cast(arr, ctypes.c_void_p), len(jobs), nx, ny, _stream())
+
+
 # the fused two-direction kernels are the bf16 path; tests flip this to compare against the one-direction kernels
 USE_FUSED_MAXSIM = True
 
@@ -716,7 +732,8 @@ class TokenWeightsPairFunction(torch.autograd.Function):
             a.b1, a.w2, a.logits = sd["b1"].data_ptr(), sd["w2"].data_ptr(), sd["logits"].data_ptr()
             a.h_bf16 = sd["h"].data_ptr() if keep else None
         st = _stream()
-        _call("nr_mlp_fwd_pair", ctypes.cast(arr, ctypes.c_void_p), 2, D, H, st)
+        # one SM stays free for the single-CTA Sinkhorn kernel that runs next to this GEMM in the head's forward
+        _call("nr_mlp_fwd_pair", ctypes.cast(arr, ctypes.c_void_p), 2, D, H, 1, st)
         for sd in sides:
             _call("nr_token_softmax", _p(sd["logits"]), _p(sd["b2"]), _p(sd["ma"]), _p(sd["mb"]), sd["Ra"], sd["Ra"] + sd["Rb"],
                   sd["N"], _p(sd["w"]), st)

@@ -527,9 +527,9 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
         with fj.on(1):
             global_path()
         with fj.on(0):                           # weight gradients NEXT TO the contraction, not after it
-            ops.maxsim2_bwd_w(p1, p2, dP, B, 1, 0.5, b, nt, B, nv, dtw_l, dvw)
-            ops.maxsim2_bwd_w(pA, pB, dc_l[0], 1, 0, sc, b, nt, M, nv, dtw_l, dvw_mb)
-            ops.maxsim2_bwd_w(pC, pD, dc_l[1], 0, 1, sc, M, nt, b, nv, dtw_mb, dvw_l)
+            ops.maxsim2_bwd_w_multi([(p1, p2, dP, B, 1, 0.5, b, B, dtw_l, dvw),
+                                     (pA, pB, dc_l[0], 1, 0, sc, b, M, dtw_l, dvw_mb),
+                                     (pC, pD, dc_l[1], 0, 1, sc, M, b, dtw_mb, dvw_l)], nt, nv)
         ops.maxsim2_bwd_multi([
             (0, V, tw, vw, y1, y2, dP, B, 1, 0.5, b, B, dtn_l),
             (0, MV, tw, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
