@@ -145,7 +145,7 @@ class GraphedHeadStep:
         else:       # row-block sharded head; the NCCL collectives are captured in the graph
             losses, (ta, va, tma, vma, ia) = m._sharded_losses(s["text_feat"], s["video_feat"], s["text_mask"],
                                                                s["video_mask"], (s["global_text"], s["global_video"]),
-                                                               idx=s["idx"], bank_ring=ring)
+                                                               idx=s["idx"], bank_ring=ring, defer_text=True)
             new_rows = (ia, ta, va, tma, vma)
         # With bf16 weight-MLP GEMMs the backward reads bf16 copies, never the bank itself: the FIFO update can then
         # leave the critical path and run on its own branch next to the backward.

@@ -269,7 +269,8 @@ class HeadMixin:
         self.mb_mask_v = ops.fifo_update(video_mask.to(self.mb_mask_v.dtype), self.mb_mask_v, cap)
 
     # --- everything of reference forward() below the encoders (:269-312) -----------------------------
-    def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats, idx=None, bank_ring=None):
+    def _sharded_losses(self, text_feat, video_feat, text_mask, video_mask, global_feats, idx=None, bank_ring=None,
+                        defer_text=False):
         """W > 1: row-block sharded head (sharded.py) on the LOCAL batch; gathers happen inside.
         Returns (5 losses, gathered (text, video, text_mask, video_mask[, idx])); idx (the dataset indices the bank
         FIFO stores) rides on the packed small gather when given."""
@@ -291,6 +292,8 @@ class HeadMixin:
             bank = (self.mb_feat_t, self.mb_feat_v, self.mb_mask_t, self.mb_mask_v)
         pro = ShardedPrologue(text_feat, video_feat, gtf, gvf, text_mask, video_mask, *bank, hp, idx_l=idx,
                               bank_ring=bank_ring)
+        pro.defer_text_to_backward = bool(defer_text)
+        self._last_pro = pro
         with ops.ForkJoin(3) as fj:
             with fj.on(2):
                 pro.run_global()             # first: Sinkhorn is the longest chain of the forward
@@ -323,6 +326,11 @@ class HeadMixin:
         """The sharded head gathers the other ranks' text tokens asynchronously (only the bank FIFO reads them):
         make the current stream wait for that gather before touching the gathered text."""
         ev = getattr(self, "_text_ready", None)
+        pro = self.__dict__.pop("_last_pro", None)
+        if ev is None and pro is not None:              # gather issued later than the forward (deferred to the backward)
+            if pro.a2a and pro.text_ready is None:
+                pro.gather_text_async()                 # no backward ran: issue it now
+            ev = pro.text_ready
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
             self._text_ready = None

@@ -178,6 +178,8 @@ class ShardedPrologue:
         self.ginv = torch.empty(2, b, **f32); self.w = torch.empty(2, b, **f32)
         self.global_done = None
         self.text_ready = None
+        # set by callers that always run the backward (the captured step): the text gather then moves there
+        self.defer_text_to_backward = False
         if bf:
             for P in (self.T if self.T is not None else self.Tl, self.V, self.MT, self.MV):
                 P.alloc_transposed()
@@ -350,8 +352,9 @@ class ShardedHeadFunction(torch.autograd.Function):
         m54 = _combine_matrix(B, wu, wn, wkl, dev)
         out5 = torch.empty(5, **f32)
         _call("nr_matvec_small", _p(m54), 5, 4, 0, _p(sums), _p(sums[4:]), _p(out5), st)
-        if a2a:
+        if a2a and not pro.defer_text_to_backward:
             pro.gather_text_async()
+        ctx.pro = pro if (a2a and pro.defer_text_to_backward) else None
         ctx.hp, ctx.dims = hp, (W, r, b, B, lo, M, d, nt, nv)
         ctx.objs = (T, V, MT, MV, Tl, Vl)
         ctx.a2a = a2a
@@ -497,22 +500,31 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
     send[:, bb + 2 * b:bb + 2 * b + d] = dmean_t
     send[:, bb + 2 * b + d:] = z[d + 2 * B:d + 2 * B + 1]
     recv = _all_to_all_blocks(send)                                                          # [r, (v, a) | tails]
+    if ctx.pro is not None:
+        # other ranks' text tokens feed only the bank FIFO at the very end of the step: their gather is queued behind
+        # the exchange the backward waits for, and runs under the contraction
+        ctx.pro.gather_text_async()
+        ctx.pro = None
     tail = recv[:, bb:].sum(0)
     dc_l = tail[:2 * b].view(2, b).contiguous()                    # this rank's samples, summed over ranks
     dmean_t.copy_(tail[2 * b:2 * b + d])
     z[d + 2 * B:d + 2 * B + 1].copy_(tail[2 * b + d:])             # d logit_scale (returned by the caller)
     dP = dS_row.view(b, W, b) + recv[:, :bb].view(W, b, b).permute(2, 0, 1)
     dP = dP.view(b, B)
-    # global similarity: dG has a row block (direction 1) and a column block (direction 2) on this rank; its two
-    # library GEMMs run on their own branch next to the contraction (buffers allocated here, before the fork)
-    dG = torch.zeros(B, B, **f32)
+    # global similarity: dG has a row block (direction 1: dG1 [b,B] at rows lo..) and a column block (direction 2:
+    # dG2^T) on this rank, so  dgT = dG gV  and  dgV = dG^T gT  are four [b,B] x [B,d] / [B,b] x [b,d] products
+    # (4 b B d multiply-adds instead of 2 B^2 d on an assembled [B,B] matrix); partial over ranks.  They run on their
+    # own branch, which stays open until the reduce-scatter that needs them.
     dg_all = torch.empty(B, d, **f32); dv_all = torch.empty(B, d, **f32)
+    v2_l, g2_l = v2[lo:lo + b], g2[lo:lo + b]
 
     def global_path():
-        dG[lo:lo + b] += dG1
-        dG[:, lo:lo + b] += dG2.t()
-        _call("nr_matmul_f32", _p(dG), B, 0, _p(v2), d, B, B, d, _p(dg_all), d, 0, _stream())     # partial over ranks
-        _call("nr_matmul_f32", _p(dG), B, 1, _p(g2), d, B, B, d, _p(dv_all), d, 0, _stream())
+        mm = lambda A, tA, X, M_, K_, out, acc: _call("nr_matmul_f32", _p(A), B, tA, _p(X), d, M_, K_, d, _p(out), d, acc,
+                                                      _stream())
+        mm(dG2, 1, v2_l, B, b, dg_all, 0)                          # column block: dG[:, lo:lo+b] = dG2^T
+        mm(dG1, 0, v2, b, B, dg_all[lo:lo + b], 1)                 # row block
+        mm(dG1, 1, g2_l, B, b, dv_all, 0)
+        mm(dG2, 0, g2, b, B, dv_all[lo:lo + b], 1)
         dg_all[lo:lo + b] += dgl[0]
         dv_all[lo:lo + b] += dgl[1]
     # ---- token-pair products: text rows complete locally, video rows partial over ranks
@@ -526,6 +538,7 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
     with ops.ForkJoin(2) as fj:
         with fj.on(1):
             global_path()
+        ev_global = fj.detach(1)
         with fj.on(0):                           # weight gradients NEXT TO the contraction, not after it
             ops.maxsim2_bwd_w_multi([(p1, p2, dP, B, 1, 0.5, b, B, dtw_l, dvw),
                                      (pA, pB, dc_l[0], 1, 0, sc, b, M, dtw_l, dvw_mb),
@@ -539,9 +552,11 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
         Tl.backward(dtn_l, add_vec=dmean_t, out=dtext)
         with fj.on(0):
             V.backward(dvn, add_vec=dmean_v, out=dvideo_all)
-    # ---- exchange 5: sum the partial video-side gradients, keep this rank's rows
-    dvideo = _reduce_scatter(dvideo_all, b)
+    # ---- exchange 5: sum the partial video-side gradients, keep this rank's rows.  The small one first: the video
+    #      token-weight gradients in it gate the MLP backward, the feature gradients are only handed back
+    torch.cuda.current_stream().wait_event(ev_global)
     small = _reduce_scatter(torch.cat([dg_all, dv_all, dvw], dim=1), b)                      # one collective
+    dvideo = _reduce_scatter(dvideo_all, b)
     return dtext, dvideo, small[:, :d], small[:, d:2 * d], dtw_l, small[:, 2 * d:], dtw_mb, dvw_mb
 
 
