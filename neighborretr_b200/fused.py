@@ -154,6 +154,7 @@ class HeadFunction(torch.autograd.Function):
                 mb_feat_v, mb_mask_t, mb_mask_v, hp, pro=None):
         cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
         _req_cuda(text, video, gt, gv, tw, vw, tw_mb, vw_mb, logit_scale, mb_feat_t, mb_feat_v)
+        ctx.set_materialize_grads(False)         # no zero-filled gradient for the neighbour lists
         dev = text.device
         tw, vw, tw_mb, vw_mb = _f32c(tw), _f32c(vw), _f32c(tw_mb), _f32c(vw_mb)
         if pro is None:                 # stand-alone use: the prologue runs here (already-joined when passed in)

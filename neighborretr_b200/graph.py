@@ -156,7 +156,7 @@ class GraphedHeadStep:
             self._fifo_stream.wait_stream(main)
             with torch.cuda.stream(self._fifo_stream):
                 self._fifo(new_rows)
-        out5 = getattr(m, "last_out5", None) if self.world == 1 else None
+        out5 = getattr(m, "last_out5", None)
         if out5 is not None and not out5.requires_grad:
             out5 = None
         if self.explicit:
@@ -175,6 +175,17 @@ class GraphedHeadStep:
         if early_fifo:
             main.wait_stream(self._fifo_stream)
         else:
+            ev = ops.EVENTS.pop("mlp_backward_done", None) if self.world > 1 else None
+            if ring is not None and ev is not None:
+                # every reader of the ring is enqueued before this event (it precedes the all-reduce of the head
+                # parameters at the end of the backward): the insert runs under that all-reduce on its own stream
+                main = torch.cuda.current_stream()
+                self._fifo_stream.wait_event(ev)
+                with torch.cuda.stream(self._fifo_stream), torch.no_grad():
+                    m.wait_gathered_text()
+                    ring.insert(*new_rows)
+                main.wait_stream(self._fifo_stream)
+                return out5.detach() if out5 is not None else torch.stack([x.detach() for x in losses])
             if self.world > 1:
                 m.wait_gathered_text()
             if ring is not None:

@@ -309,6 +309,7 @@ class HeadMixin:
             text_feat, video_feat, gtf, gvf, tw, vw, tw_mb, vw_mb, self.clip.logit_scale.exp(), text_mask, video_mask,
             *bank, hp, pro)
         self.last_neighbors = (nbr[0], nbr[1])
+        self.last_out5 = out5                      # as one tensor: graph.py differentiates it with e0 directly
         self._text_ready = pro.text_ready          # event of the deferred text gather (None: already joined)
         if idx is not None:
             return tuple(out5.unbind(0)), (text_all, video_all, tm_all, vm_all, pro.idx_all)

@@ -22,6 +22,8 @@ TC_PRECISIONS = (NR_PREC_BF16, NR_PREC_BF16X3)
 ROLE_X, ROLE_Y = 1, 2
 # kernel launches issued through the C ABI since the last reset (bench.py reports it as gpu_launches)
 LAUNCHES = {"count": 0}
+# named CUDA events a later stage may wait on instead of the whole stream ("mlp_backward_done": sharded.py)
+EVENTS = {}
 
 
 def _p(t):

@@ -79,6 +79,9 @@ class SumGradsAcrossRanks(torch.autograd.Function):
             if g is not None:
                 flat[o:o + n].copy_(g.reshape(-1))
             o += n
+        ev = torch.cuda.Event()                 # everything that reads the step's operands is enqueued: the captured
+        ev.record()                             # step starts its bank insert here, under the all-reduce
+        ops.EVENTS["mlp_backward_done"] = ev
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         out, o = [], 0
         for shp, n in zip(ctx.shapes, sizes):
@@ -258,6 +261,7 @@ class ShardedHeadFunction(torch.autograd.Function):
                 mb_feat_v, mb_mask_t, mb_mask_v, hp, pro=None):
         cs, beta, k, tau, iters, wu, wn, wkl, prec, bprec = hp
         _req_cuda(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale)
+        ctx.set_materialize_grads(False)         # no zero-filled gradients for the gathered tensors / neighbour lists
         if pro is None:
             pro = ShardedPrologue(text_l, video_l, gt_l, gv_l, tm_l, vm_l, mb_feat_t, mb_feat_v, mb_mask_t,
                                   mb_mask_v, hp).run_forked()
@@ -527,18 +531,28 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
         mm(dG2, 0, g2, b, B, dv_all[lo:lo + b], 1)
         dg_all[lo:lo + b] += dgl[0]
         dv_all[lo:lo + b] += dgl[1]
-    # ---- token-pair products: text rows complete locally, video rows partial over ranks
-    dtn_l = torch.zeros(Tl.rows, d, **f32); dvn = torch.zeros(V.rows, d, **f32)
-    dtw_l = torch.zeros(b, nt, **f32); dvw = torch.zeros(B, nv, **f32)
-    dtw_mb = torch.zeros_like(tw_mb); dvw_mb = torch.zeros_like(vw_mb)
+    # ---- token-pair products: text rows complete locally, video rows partial over ranks.  One zero fill for every
+    #      accumulation target: [dtn_l | dvn | dtw_l | dvw | dtw_mb | dvw_mb]  (token gradients first: 16-byte aligned)
+    n_t, n_v = Tl.rows * d, V.rows * d
+    sizes = [n_t, n_v, b * nt, B * nv, tw_mb.numel(), vw_mb.numel()]
+    zz = torch.zeros(sum(sizes), **f32)
+    offs = [0]
+    for n_ in sizes:
+        offs.append(offs[-1] + n_)
+    dtn_l, dvn = zz[offs[0]:offs[1]].view(Tl.rows, d), zz[offs[1]:offs[2]].view(V.rows, d)
+    dtw_l, dvw = zz[offs[2]:offs[3]].view(b, nt), zz[offs[3]:offs[4]].view(B, nv)
+    dtw_mb, dvw_mb = zz[offs[4]:offs[5]].view_as(tw_mb), zz[offs[5]:offs[6]].view_as(vw_mb)
     dvn_l, dvw_l = dvn[lo * nv:(lo + b) * nv], dvw[lo:lo + b]
     vw_l = vw[lo:lo + b]
     dtext = torch.empty_like(Tl.xn); dvideo_all = torch.empty_like(V.xn)
     sc = 0.5 / M
     with ops.ForkJoin(2) as fj:
+        # the small dG products FIRST and finished before the contraction is launched: once its persistent CTAs and
+        # the weight-gradient kernel hold every SM, a later small kernel only runs after they retire (measured: 54 us
+        # on the critical path of the gradient reduce-scatter)
         with fj.on(1):
             global_path()
-        ev_global = fj.detach(1)
+        fj.main.wait_stream(fj.side[1])
         with fj.on(0):                           # weight gradients NEXT TO the contraction, not after it
             ops.maxsim2_bwd_w_multi([(p1, p2, dP, B, 1, 0.5, b, B, dtw_l, dvw),
                                      (pA, pB, dc_l[0], 1, 0, sc, b, M, dtw_l, dvw_mb),
@@ -548,14 +562,14 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
             (0, MV, tw, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
             (1, Tl, tw, vw, y1, y2, dP, B, 1, 0.5, b, B, dvn),
             (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
+    # the video token-weight gradients gate the MLP backward: reduce-scatter them (with the global-feature gradients)
+    # as soon as the weight-gradient kernel is done, before the normalisation backward
+    small = _reduce_scatter(torch.cat([dg_all, dv_all, dvw], dim=1), b)                      # one collective
     with ops.ForkJoin(1) as fj:
         Tl.backward(dtn_l, add_vec=dmean_t, out=dtext)
         with fj.on(0):
             V.backward(dvn, add_vec=dmean_v, out=dvideo_all)
-    # ---- exchange 5: sum the partial video-side gradients, keep this rank's rows.  The small one first: the video
-    #      token-weight gradients in it gate the MLP backward, the feature gradients are only handed back
-    torch.cuda.current_stream().wait_event(ev_global)
-    small = _reduce_scatter(torch.cat([dg_all, dv_all, dvw], dim=1), b)                      # one collective
+    # ---- exchange 5: sum the partial video-side feature gradients, keep this rank's rows
     dvideo = _reduce_scatter(dvideo_all, b)
     return dtext, dvideo, small[:, :d], small[:, d:2 * d], dtw_l, small[:, 2 * d:], dtw_mb, dvw_mb
 

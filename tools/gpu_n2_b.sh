@@ -1,0 +1,23 @@
+#!/usr/bin/env bash
+set -u
+out=gpurun_out; mkdir -p $out
+run2() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
+run2 29551 bench.py --gpus 2 --steps 10 --warmup 3 > $out/r2_bench_n2.json 2> $out/r2_bench_n2.err; echo "bench n2 rc=$?"
+run2 29552 bench.py --gpus 2 --workload eval --eval-size 8000 --steps 3 > $out/r2_eval8k_n2.json 2> $out/r2_eval8k_n2.err; echo "eval n2 rc=$?"
+run2 29553 bench.py --gpus 2 --per-gpu-batch 512 --steps 3 --no-extra > $out/r2_b512_n2.json 2> $out/r2_b512_n2.err; echo "b512 n2 rc=$?"
+python bench.py --workload eval --eval-size 8000 --steps 3 > $out/r2_eval8k_n1.json 2> $out/r2_eval8k_n1.err; echo "eval n1 rc=$?"
+python bench.py --shape activitynet --steps 5 --no-cpu-baseline > $out/r2_act_n1.json 2> $out/r2_act_n1.err; echo "act n1 rc=$?"
+run2 29554 tools/trace_step.py --out $out/r2_trace_n2.txt > /dev/null 2> $out/r2_trace_n2.err
+for f in r2_bench_n2 r2_eval8k_n2 r2_b512_n2 r2_eval8k_n1 r2_act_n1; do
+  echo "== $f"; grep -v "Warning\|warn\|run_backward\|^\*\*\*\|OMP_NUM" $out/$f.err | tail -5
+  python - "$out/$f.json" <<'PY'
+import json,sys
+d=None
+for l in open(sys.argv[1]):
+    if l.startswith('{'): d=json.loads(l)
+if d is None: print('no json'); sys.exit()
+print({k:d.get(k) for k in ('metric','value','ms_per_step','n_gpus','gpu_launches')})
+print('parity', d.get('parity_checked')); print('roofline', {k:d['roofline'].get(k) for k in ('achieved','frac','avg_launch_ms')} if d.get('roofline') else None)
+print('modes', d.get('modes')); print('cfg', d.get('config',{}).get('workload'))
+PY
+done
