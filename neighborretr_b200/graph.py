@@ -175,6 +175,9 @@ class GraphedHeadStep:
         if early_fifo:
             main.wait_stream(self._fifo_stream)
         else:
+            evv = ops.EVENTS.pop("video_grad_ready", None)
+            if evv is not None:                 # the video-gradient reduce-scatter ran from a side stream (sharded.py)
+                torch.cuda.current_stream().wait_event(evv)
             ev = ops.EVENTS.pop("mlp_backward_done", None) if self.world > 1 else None
             if ring is not None and ev is not None:
                 # every reader of the ring is enqueued before this event (it precedes the all-reduce of the head

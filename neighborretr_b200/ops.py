@@ -102,6 +102,20 @@ class ForkJoin:
         return False
 
 
+_HP_STREAMS = {}
+
+
+def hp_stream(device=None):
+    """One high-priority side stream per device for SMALL kernels that gate a later stage while a persistent kernel
+    holds every SM: pending CTAs of a higher-priority stream are placed first whenever an SM has room, instead of
+    queueing behind the thousands of CTAs of a concurrent low-urgency kernel."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    st = _HP_STREAMS.get(dev.index)
+    if st is None:
+        st = _HP_STREAMS[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+    return st
+
+
 class _KernelTimer:
     """CUDA-event timing of one C-ABI entry point on the launching stream (bench.py roofline).
 

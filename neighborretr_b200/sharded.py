@@ -359,6 +359,7 @@ class ShardedHeadFunction(torch.autograd.Function):
         if a2a and not pro.defer_text_to_backward:
             pro.gather_text_async()
         ctx.pro = pro if (a2a and pro.defer_text_to_backward) else None
+        ctx.defer_video_rs = bool(a2a and pro.defer_text_to_backward)
         ctx.hp, ctx.dims = hp, (W, r, b, B, lo, M, d, nt, nv)
         ctx.objs = (T, V, MT, MV, Tl, Vl)
         ctx.a2a = a2a
@@ -546,13 +547,15 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
     vw_l = vw[lo:lo + b]
     dtext = torch.empty_like(Tl.xn); dvideo_all = torch.empty_like(V.xn)
     sc = 0.5 / M
-    with ops.ForkJoin(2) as fj:
-        # the small dG products FIRST and finished before the contraction is launched: once its persistent CTAs and
-        # the weight-gradient kernel hold every SM, a later small kernel only runs after they retire (measured: 54 us
-        # on the critical path of the gradient reduce-scatter)
-        with fj.on(1):
-            global_path()
-        fj.main.wait_stream(fj.side[1])
+    # the small dG products on the high-priority stream: once the contraction's persistent CTAs and the ~1700 CTAs of
+    # the weight-gradient kernel are resident or queued, a normal-priority small kernel only runs after they retire
+    # (measured: 54 us on the critical path of the gradient reduce-scatter)
+    main = torch.cuda.current_stream()
+    hp = ops.hp_stream(dev)
+    hp.wait_stream(main)
+    with torch.cuda.stream(hp):
+        global_path()
+    with ops.ForkJoin(1) as fj:
         with fj.on(0):                           # weight gradients NEXT TO the contraction, not after it
             ops.maxsim2_bwd_w_multi([(p1, p2, dP, B, 1, 0.5, b, B, dtw_l, dvw),
                                      (pA, pB, dc_l[0], 1, 0, sc, b, M, dtw_l, dvw_mb),
@@ -562,6 +565,7 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
             (0, MV, tw, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
             (1, Tl, tw, vw, y1, y2, dP, B, 1, 0.5, b, B, dvn),
             (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
+    main.wait_stream(hp)
     # the video token-weight gradients gate the MLP backward: reduce-scatter them (with the global-feature gradients)
     # as soon as the weight-gradient kernel is done, before the normalisation backward
     small = _reduce_scatter(torch.cat([dg_all, dv_all, dvw], dim=1), b)                      # one collective
@@ -569,8 +573,20 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
         Tl.backward(dtn_l, add_vec=dmean_t, out=dtext)
         with fj.on(0):
             V.backward(dvn, add_vec=dmean_v, out=dvideo_all)
-    # ---- exchange 5: sum the partial video-side feature gradients, keep this rank's rows
-    dvideo = _reduce_scatter(dvideo_all, b)
+    # ---- exchange 5: sum the partial video-side feature gradients, keep this rank's rows.  Nothing of the step reads
+    #      them; in the captured step (which joins `video_grad_ready` at its end) the collective therefore runs from a
+    #      side stream, under the MLP backward, instead of holding the main stream
+    if ctx.defer_video_rs:
+        side = _text_stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            dvideo = _reduce_scatter(dvideo_all, b)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        dvideo_all.record_stream(side)
+        ops.EVENTS["video_grad_ready"] = ev
+    else:
+        dvideo = _reduce_scatter(dvideo_all, b)
     return dtext, dvideo, small[:, :d], small[:, d:2 * d], dtw_l, small[:, 2 * d:], dtw_mb, dvw_mb
 
 
