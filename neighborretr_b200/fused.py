@@ -302,17 +302,13 @@ class HeadFunction(torch.autograd.Function):
                 return None
 
             ev_dm = []
-            hp = ops.hp_stream(dev)              # small kernels next to the contraction: placed first (ops.hp_stream)
-            hp.wait_stream(fj.main)
-            with torch.cuda.stream(hp):
+            with fj.on(1):
                 ev_dG = global_path()
             with fj.on(3):
                 global_path(ev_dG)
             # the two branches stay open past this fork: the normalisation backward only waits for their d mean
             # events, the dG products are joined right before the gradients are handed back
-            ev_hp = torch.cuda.Event()
-            ev_hp.record(hp)
-            ev_global_end = (ev_hp, fj.detach(3))
+            ev_global_end = (fj.detach(1), fj.detach(3))
             if ctx.fusedk:
                 # one routing matrix per pair, applied from either side; ALL contractions in one launch (the text
                 # gradient accumulates over [video ; bank-video] sources, the video gradient over [text ; bank-text])

@@ -547,13 +547,14 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
     vw_l = vw[lo:lo + b]
     dtext = torch.empty_like(Tl.xn); dvideo_all = torch.empty_like(V.xn)
     sc = 0.5 / M
-    # the small dG products on the high-priority stream: once the contraction's persistent CTAs and the ~1700 CTAs of
-    # the weight-gradient kernel are resident or queued, a normal-priority small kernel only runs after they retire
-    # (measured: 54 us on the critical path of the gradient reduce-scatter)
+    # The small dG products run on their own branch and are only joined by the LAST collective of the backward (the
+    # global-feature gradients feed nothing inside the step): next to the contraction, whose persistent CTAs and the
+    # ~1700 CTAs of the weight-gradient kernel hold every SM, they may start late without delaying anything.  The video
+    # token-weight gradients, which gate the MLP backward, get their own small reduce-scatter right after the kernels.
     main = torch.cuda.current_stream()
-    hp = ops.hp_stream(dev)
-    hp.wait_stream(main)
-    with torch.cuda.stream(hp):
+    gstream = ops.ForkJoin(1, offset=6).side[0]
+    gstream.wait_stream(main)
+    with torch.cuda.stream(gstream):
         global_path()
     with ops.ForkJoin(1) as fj:
         with fj.on(0):                           # weight gradients NEXT TO the contraction, not after it
@@ -565,29 +566,31 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
             (0, MV, tw, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
             (1, Tl, tw, vw, y1, y2, dP, B, 1, 0.5, b, B, dvn),
             (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
-    main.wait_stream(hp)
-    # the video token-weight gradients gate the MLP backward: reduce-scatter them (with the global-feature gradients)
-    # as soon as the weight-gradient kernel is done, before the normalisation backward
-    small = _reduce_scatter(torch.cat([dg_all, dv_all, dvw], dim=1), b)                      # one collective
+    dvw_o = _reduce_scatter(dvw, b)                                                          # [b, Nv]
     with ops.ForkJoin(1) as fj:
         Tl.backward(dtn_l, add_vec=dmean_t, out=dtext)
         with fj.on(0):
             V.backward(dvn, add_vec=dmean_v, out=dvideo_all)
-    # ---- exchange 5: sum the partial video-side feature gradients, keep this rank's rows.  Nothing of the step reads
-    #      them; in the captured step (which joins `video_grad_ready` at its end) the collective therefore runs from a
-    #      side stream, under the MLP backward, instead of holding the main stream
+    # ---- exchange 5: sum the partial video-side feature gradients and the global-feature gradients, keep this rank's
+    #      rows.  Nothing of the step reads them; in the captured step (which joins `video_grad_ready` at its end) the
+    #      two collectives therefore run from a side stream, under the MLP backward, instead of holding the main stream
     if ctx.defer_video_rs:
         side = _text_stream(dev)
         side.wait_stream(torch.cuda.current_stream())
+        side.wait_stream(gstream)
         with torch.cuda.stream(side):
             dvideo = _reduce_scatter(dvideo_all, b)
+            small = _reduce_scatter(torch.cat([dg_all, dv_all], dim=1), b)
             ev = torch.cuda.Event()
             ev.record(side)
-        dvideo_all.record_stream(side)
+        for t_ in (dvideo_all, dg_all, dv_all):
+            t_.record_stream(side)
         ops.EVENTS["video_grad_ready"] = ev
     else:
+        main.wait_stream(gstream)
         dvideo = _reduce_scatter(dvideo_all, b)
-    return dtext, dvideo, small[:, :d], small[:, d:2 * d], dtw_l, small[:, 2 * d:], dtw_mb, dvw_mb
+        small = _reduce_scatter(torch.cat([dg_all, dv_all], dim=1), b)
+    return dtext, dvideo, small[:, :d], small[:, d:2 * d], dtw_l, dvw_o, dtw_mb, dvw_mb
 
 
 def sharded_head(text_l, video_l, gt_l, gv_l, tw_l, vw_l, tw_mb, vw_mb, logit_scale, tm_l, vm_l, mb_feat_t, mb_feat_v,
