@@ -56,7 +56,7 @@ class GraphedHeadStep:
         if self.ring is None:
             for n in self.bank_names:                   # own the bank storage
                 setattr(model, n, bank0[n].clone())
-        self.params = head_params(model) if self.explicit else [p for p in model.parameters() if p.requires_grad]
+        self.params = head_params(model)
         self.grad_list = None
         self._e0 = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.0], device=dev)
         self._fifo_stream = torch.cuda.Stream(device=dev)
@@ -81,10 +81,10 @@ class GraphedHeadStep:
         else:
             for n in self.bank_names:
                 getattr(model, n).copy_(bank0[n])
-        if self.explicit:
-            self.grads = dict(zip(GRAD_FIELDS, self.grad_list[:len(GRAD_FIELDS)]))
-        else:
-            self.grads = {f: self.static[f].grad for f in GRAD_FIELDS}
+        self.grads = dict(zip(GRAD_FIELDS, self.grad_list[:len(GRAD_FIELDS)]))
+        if not self.explicit:              # the documented surface: parameter .grad = the static gradient tensors
+            for p_, g_ in zip(self.params, self.grad_list[len(GRAD_FIELDS):]):
+                p_.grad = g_
 
     def _make_ring(self, model, bank0, b):
         """The persistent prepared bank (bank.BankRing) when the step runs the fused tensor-core kernels; None
@@ -124,10 +124,7 @@ class GraphedHeadStep:
                 getattr(self.model, n).copy_(getattr(bank, n))
 
     def _zero_grads(self):
-        if self.explicit:                 # torch.autograd.grad never touches a .grad attribute
-            return
-        for t in list(self.static.values()) + self.params:
-            t.grad = None
+        pass                              # torch.autograd.grad never touches a .grad attribute
 
     def _body(self):
         m, s = self.model, self.static
@@ -159,19 +156,15 @@ class GraphedHeadStep:
         out5 = getattr(m, "last_out5", None)
         if out5 is not None and not out5.requires_grad:
             out5 = None
-        if self.explicit:
-            leaves = [s[f] for f in GRAD_FIELDS] + self.params
-            if out5 is not None:
-                self.grad_list = torch.autograd.grad(out5, leaves, grad_outputs=self._e0, allow_unused=True)
-            else:
-                self.grad_list = torch.autograd.grad(losses[0], leaves, allow_unused=True)
-            m.last_out5 = None
-        elif out5 is not None:
-            # d total / d out5 = e0: skips the unbind/stack bookkeeping kernels of losses[0].backward()
-            out5.backward(gradient=self._e0)
-            m.last_out5 = None
+        # torch.autograd.grad hands back the tensors the backward nodes produced (no AccumulateGrad copy that could read
+        # a gradient whose collective still runs on a side stream); d total / d out5 = e0 skips the unbind/stack
+        # bookkeeping kernels of losses[0].backward()
+        leaves = [s[f] for f in GRAD_FIELDS] + self.params
+        if out5 is not None:
+            self.grad_list = torch.autograd.grad(out5, leaves, grad_outputs=self._e0, allow_unused=True)
         else:
-            losses[0].backward()
+            self.grad_list = torch.autograd.grad(losses[0], leaves, allow_unused=True)
+        m.last_out5 = None
         if early_fifo:
             main.wait_stream(self._fifo_stream)
         else:

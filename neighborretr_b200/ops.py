@@ -811,6 +811,12 @@ class TokenWeightsPairFunction(torch.autograd.Function):
                         r["dw1"], s_[:H] if need[base + 1] else None, s_[H:2 * H].reshape(1, H) if need[base + 2] else None,
                         s_[2 * H:] if need[base + 3] else None))
         (dxt, dw1t, db1t, dw2t, db2t), (dxv, dw1v, db1v, dw2v, db2v) = out
+        # The sharded captured step reduces the video-feature gradients of the head on a side stream (sharded.py);
+        # autograd adds dxv to them right after this node: order that addition behind the collective.  Enqueued AFTER
+        # this node's own launches, so it delays nothing of the MLP backward.
+        ev = EVENTS.get("video_grad_ready")
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
         return (dxt, None, None, None, dxv, None, None, None, dw1t, db1t, dw2t, db2t, dw1v, db1v, dw2v, db2v, None)
 
 
