@@ -554,8 +554,6 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
     main = torch.cuda.current_stream()
     gstream = ops.ForkJoin(1, offset=6).side[0]
     gstream.wait_stream(main)
-    with torch.cuda.stream(gstream):
-        global_path()
     with ops.ForkJoin(1) as fj:
         with fj.on(0):                           # weight gradients NEXT TO the contraction, not after it
             ops.maxsim2_bwd_w_multi([(p1, p2, dP, B, 1, 0.5, b, B, dtw_l, dvw),
@@ -566,6 +564,8 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
             (0, MV, tw, vw_mb, yA, yB, dc_l[0], 1, 0, sc, b, M, dtn_l),
             (1, Tl, tw, vw, y1, y2, dP, B, 1, 0.5, b, B, dvn),
             (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
+        with torch.cuda.stream(gstream):         # enqueued after the contraction: a small kernel that grabs an SM
+            global_path()                        # first would delay one of its statically scheduled CTAs
     dvw_o = _reduce_scatter(dvw, b)                                                          # [b, Nv]
     with ops.ForkJoin(1) as fj:
         Tl.backward(dtn_l, add_vec=dmean_t, out=dtext)
