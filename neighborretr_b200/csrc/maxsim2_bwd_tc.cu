@@ -463,12 +463,20 @@ extern "C" int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int njobs, int64_t
   int dev = 0, sms = 0;
   NR_CUDA(cudaGetDevice(&dev));
   NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  // split-K per side so that all items have about the same number of k-blocks and fit one wave
+  // split-K per side so that all items have about the same number of k-blocks.  Small launches (a step at b = 128 on
+  // one GPU) fit ONE wave: per = work / SMs k-blocks per item.  Larger ones run several waves of items of <= ~40
+  // k-blocks through the persistent grid instead of one wave of very long items whose longest (an unsplit side)
+  // sets the kernel time (measured at 8 ranks: 463 us with one wave of up to 288 k-blocks per item).
   int64_t work = 0;
   int min_items = 0;
   for (int s = 0; s < a.nsides; ++s) { work += (int64_t)a.sides[s].n_mt * a.sides[s].kb_total; min_items += a.sides[s].n_mt; }
   int per = (int)((work + sms - 1) / sms);
   if (per < 1) per = 1;
+  int waves = 1;
+  if (per > 48) {
+    waves = (per + 39) / 40;
+    per = (int)((work + (int64_t)sms * waves - 1) / ((int64_t)sms * waves));
+  }
   if (const char* pv = getenv("NR_B2_PER")) { int p2 = atoi(pv); if (p2 >= 1) per = p2; }
   for (;;) {
     int items = 0;
@@ -483,7 +491,7 @@ extern "C" int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int njobs, int64_t
       items += S.n_mt * S.KS;
     }
     a.n_items = items;
-    if (items <= sms || min_items > sms || getenv("NR_B2_PER")) break;
+    if (items <= sms * waves || min_items > sms * waves || waves > 1 || getenv("NR_B2_PER")) break;
     ++per;
   }
   const size_t stage_bytes = (size_t)B2_A_BYTES + (size_t)a.n_half * B2_B_HALF_BYTES;

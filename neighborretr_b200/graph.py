@@ -168,6 +168,9 @@ class GraphedHeadStep:
         if early_fifo:
             main.wait_stream(self._fifo_stream)
         else:
+            part = ops.EVENTS.pop("loss_out5_partial", None)
+            if part is not None:                # no head parameter took a gradient: reduce the partial losses here
+                torch.distributed.all_reduce(part.detach(), op=torch.distributed.ReduceOp.SUM)
             evv = ops.EVENTS.pop("video_grad_ready", None)
             if evv is not None:                 # the video-gradient reduce-scatter ran from a side stream (sharded.py)
                 torch.cuda.current_stream().wait_event(evv)

@@ -73,7 +73,11 @@ class SumGradsAcrossRanks(torch.autograd.Function):
     def backward(ctx, *gs):
         sizes = [int(torch.Size(s).numel()) for s in ctx.shapes]
         ref = next(g for g in gs if g is not None)
-        flat = torch.zeros(sum(sizes), dtype=ref.dtype, device=ref.device)
+        extra = ops.EVENTS.pop("loss_out5_partial", None)          # partial losses of the captured step (see forward)
+        n_extra = extra.numel() if extra is not None else 0
+        flat = torch.zeros(sum(sizes) + n_extra, dtype=ref.dtype, device=ref.device)
+        if extra is not None:
+            flat[sum(sizes):].copy_(extra.detach().reshape(-1))
         o = 0
         for g, n in zip(gs, sizes):
             if g is not None:
@@ -83,6 +87,9 @@ class SumGradsAcrossRanks(torch.autograd.Function):
         ev.record()                             # step starts its bank insert here, under the all-reduce
         ops.EVENTS["mlp_backward_done"] = ev
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if extra is not None:
+            with torch.no_grad():
+                extra.detach().copy_(flat[sum(sizes):].reshape(extra.shape))      # the losses every rank reports
         out, o = [], 0
         for shp, n in zip(ctx.shapes, sizes):
             out.append(flat[o:o + n].view(shp))
@@ -351,11 +358,18 @@ class ShardedHeadFunction(torch.autograd.Function):
                       _p(duals[2][lo:lo + b]), _p(duals[3]), b, B, lo, _p(ls), k, tau, tau, beta, ALL_LOSSES,
                       _p(row_out[1]), _p(nbr[1]), _p(saved[1]), _stream())
         _call("nr_vec_sums", _p(row_out), 8, b, None, _p(sums), st)
-        # ---- exchange 4: loss partial sums
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        # ---- exchange 4: loss partial sums.  The backward never reads the reduced values (its upstream multipliers are
+        #      constants), so the captured step does not put this collective between the forward and the backward
+        #      exchange (measured at 8 ranks: 155 us of rank skew absorbed right there): the five partial losses ride
+        #      on the all-reduce of the head-parameter gradients at the end of the backward (SumGradsAcrossRanks).
+        piggy = bool(a2a and pro.defer_text_to_backward)
+        if not piggy:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         m54 = _combine_matrix(B, wu, wn, wkl, dev)
         out5 = torch.empty(5, **f32)
         _call("nr_matvec_small", _p(m54), 5, 4, 0, _p(sums), _p(sums[4:]), _p(out5), st)
+        if piggy:
+            ops.EVENTS["loss_out5_partial"] = out5
         if a2a and not pro.defer_text_to_backward:
             pro.gather_text_async()
         ctx.pro = pro if (a2a and pro.defer_text_to_backward) else None

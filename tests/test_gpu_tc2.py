@@ -213,7 +213,7 @@ def test_token_weights_node_vs_torch(mode, tol_w, tol_g):
     assert none is None and (w_only.double() - ra_).abs().max().item() < tol_w
 
 
-@pytest.mark.parametrize("ra,rb,d", [(128, 128, 512), (37, 70, 96), (256, 256, 512)])
+@pytest.mark.parametrize("ra,rb,d", [(128, 128, 512), (37, 70, 96), (256, 256, 512), (1000, 300, 512), (260, 257, 96)])
 def test_gram_f32_matches_float64(ra, rb, d):
     g = torch.Generator().manual_seed(1)
     a = torch.randn(ra, d, generator=g).cuda(); b = torch.randn(rb, d, generator=g).cuda()
