@@ -580,6 +580,10 @@ def _backward_exchange(ctx, tw, vw, tw_mb, vw_mb, G, GT, w, mean, gn, ginv, g2, 
             (1, MT, tw_mb, vw_l, yC, yD, dc_l[1], 0, 1, sc, M, b, dvn_l)], nt, nv, d)
         with torch.cuda.stream(gstream):         # enqueued after the contraction: a small kernel that grabs an SM
             global_path()                        # first would delay one of its statically scheduled CTAs
+        # this branch outlives the function in the captured step: everything it reads or writes must stay allocated
+        # until it has run (the caching allocator otherwise hands the blocks to the next main-stream allocation)
+        for t_ in (dG1, dG2, v2, g2, dgl, dg_all, dv_all):
+            t_.record_stream(gstream)
     dvw_o = _reduce_scatter(dvw, b)                                                          # [b, Nv]
     with ops.ForkJoin(1) as fj:
         Tl.backward(dtn_l, add_vec=dmean_t, out=dtext)

@@ -2,7 +2,7 @@
 set -u
 out=gpurun_out; mkdir -p $out
 run2() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $1 "${@:2}"; }
-timeout 900 python -m pytest tests/test_gpu_sharded.py tests/test_gpu_parity.py tests/test_gpu_bank_ring.py -q -p no:cacheprovider 2>&1 | tail -4
+timeout 900 python -m pytest tests/test_gpu_sharded.py tests/test_gpu_tc2.py tests/test_gpu_parity.py -q -p no:cacheprovider 2>&1 | tail -4
 run2 29551 bench.py --gpus 2 --steps 20 --warmup 3 > $out/r2_bench_n2.json 2> $out/r2_bench_n2.err; echo "bench n2 rc=$?"
 run2 29554 tools/trace_step.py --out $out/r2_trace_n2.txt > /dev/null 2> $out/r2_trace_n2.err
 python bench.py --steps 20 > $out/r2g_bench_n1.json 2> $out/r2g_bench_n1.err; echo "bench n1 rc=$?"
