@@ -189,6 +189,10 @@ typedef struct {
 int nr_maxsim2_supported(int64_t Nx, int64_t Ny, int64_t d);
 int nr_maxsim2_fwd(const nr_maxsim2_problem* problems, int n_problems, int64_t Nx, int64_t Ny, int64_t d,
                    void* workspace, void* stream);
+/* flags & 1: split-bf16 operands (NR_PREC_BF16X3, d = 3 x feature width): the column-direction arg-max compares
+ * exact-order keys (2^-20 relative resolution) instead of the fp32 bits of v + 2 (2e-6 absolute) */
+int nr_maxsim2_fwd_ex(const nr_maxsim2_problem* problems, int n_problems, int64_t Nx, int64_t Ny, int64_t d,
+                      void* workspace, int flags, void* stream);
 /* backward of nr_maxsim2_fwd w.r.t. the normalised tokens.  For one pair with g[rx,ry] = dH[rx*dh_sr + ry*dh_sc] *
  * dh_scale (dh_scale carries alpha) and the routing matrix
  *   C[(rx,x),(ry,y)] = g[rx,ry] * ( wx[rx,x] [y == ystar[rx,ry,x]] + wy[ry,y] [x == xstar[rx,ry,y]] ),

@@ -46,6 +46,7 @@ SIGNATURES = {
                            _I64, _I, _P, _P, _P]),
     "nr_maxsim2_supported": (_I, [_I64, _I64, _I64]),
     "nr_maxsim2_fwd": (_I, [_P, _I, _I64, _I64, _I64, _P, _P]),
+    "nr_maxsim2_fwd_ex": (_I, [_P, _I, _I64, _I64, _I64, _P, _I, _P]),
     "nr_maxsim2_bwd": (_I, [_P, _I, _I64, _I64, _I64, _P]),
     "nr_maxsim2_bwd_w": (_I, [_P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "nr_maxsim2_bwd_w_multi": (_I, [_P, _I, _I64, _I64, _P]),

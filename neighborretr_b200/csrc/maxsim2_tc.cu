@@ -101,7 +101,11 @@ __device__ __forceinline__ void set_barrier(int set) {      // named barrier 1 /
 // HS = 2: each epilogue set has 8 warps; the two warps that share a TMEM lane quarter split the accumulator
 // columns of the tile (chunks [0, n/2) and [n/2, n)), which doubles the warps available to hide the latency of the
 // shuffle / shared-memory / global-store chains of the reduction (ncu: 0.6 eligible warps per scheduler with HS = 1).
-template <int NY, int GL, bool CL2, int HS>
+// XK = true: exact-order column keys (order-preserving integer image of the fp32 value, 2^-20 RELATIVE resolution at
+// every magnitude) for the split-bf16 mode, whose products are good to ~3e-7; XK = false: keys are the fp32 bits of
+// v + 2 (one FADD + one LOP3 per element, 2e-6 absolute resolution — far below the 3e-4 noise of bf16 operands).  The
+// epilogue is issue-bound: the third instruction per element costs 8-10 % of the kernel (measured).
+template <int NY, int GL, bool CL2, int HS, bool XK>
 __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const __grid_constant__ Tc2Args a) {
   constexpr int T2_SET = 128 * HS;         // threads of one epilogue set
   constexpr int CH = t2_lcm(NY, GL);       // accumulator columns per epilogue chunk: whole samples, whole groups
@@ -339,7 +343,8 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
             // order-preserving integer image of the fp32 value (all exponents keep their full relative precision:
             // only the log2(GL) lowest mantissa bits give way to the row index), ties -> lower row
             const uint32_t u = v[g * GL + j];
-            k[j] = ((u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u)) & ~LOWM) | low;
+            if constexpr (XK) k[j] = ((u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u)) & ~LOWM) | low;
+            else k[j] = (__float_as_uint(__uint_as_float(u) + 2.0f) & ~LOWM) | low;
           }
           kg_row[ch * CH + g * GL] = group_colmax<GL>(k, lane);
         }
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
             if ((kk & ~LOWM) > (best & ~LOWM)) { best = kk; bg = gi; }   // equal values: the lower group stays
           }
           const uint32_t tb = best & ~LOWM;
-          const float val = __uint_as_float((tb & 0x80000000u) ? (tb ^ 0x80000000u) : ~tb);
+          const float val = XK ? __uint_as_float((tb & 0x80000000u) ? (tb ^ 0x80000000u) : ~tb) : __uint_as_float(tb) - 2.0f;
           const int xs = bg * GL + (int)(LOWM - (best & LOWM));
           const int64_t o = ((int64_t)(mt * a.SX + s) * P.Ry + ry0) * NY + c;
           if (P.pmax_y) P.pmax_y[o] = val;
@@ -431,17 +436,24 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
 }
 
 template <int NY, int GL>
-static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, int halves, cudaStream_t stream) {
-  if (halves == 2 && !pair) {
-    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, int halves, bool exact_keys, cudaStream_t stream) {
+  if (exact_keys) {            // split-bf16 operands: 16 epilogue warps, exact-order keys
+    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    maxsim2_fwd_tc_kernel<NY, GL, false, 2><<<grid, t2_threads(2), smem, stream>>>(a);
+    maxsim2_fwd_tc_kernel<NY, GL, false, 2, true><<<grid, t2_threads(2), smem, stream>>>(a);
+    NR_CHECK_LAUNCH("nr_maxsim2_fwd");
+    return 0;
+  }
+  if (halves == 2 && !pair) {
+    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    maxsim2_fwd_tc_kernel<NY, GL, false, 2, false><<<grid, t2_threads(2), smem, stream>>>(a);
     NR_CHECK_LAUNCH("nr_maxsim2_fwd");
     return 0;
   }
   if (pair) {
     // CTA pairs: thread-block clusters of 2 (same TPC), multicast of the shared Y box
-    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -453,27 +465,28 @@ static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, int halve
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NR_CUDA(cudaLaunchKernelEx(&cfg, maxsim2_fwd_tc_kernel<NY, GL, true, 1>, a));
+    NR_CUDA(cudaLaunchKernelEx(&cfg, maxsim2_fwd_tc_kernel<NY, GL, true, 1, false>, a));
     return 0;
   }
-  NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));
-  maxsim2_fwd_tc_kernel<NY, GL, false, 1><<<grid, t2_threads(1), smem, stream>>>(a);
+  maxsim2_fwd_tc_kernel<NY, GL, false, 1, false><<<grid, t2_threads(1), smem, stream>>>(a);
   NR_CHECK_LAUNCH("nr_maxsim2_fwd");
   return 0;
 }
 
 template <int GL>
-static int dispatch_ny(int Ny, const Tc2Args& a, size_t smem, int grid, bool pair, int halves, cudaStream_t stream) {
+static int dispatch_ny(int Ny, const Tc2Args& a, size_t smem, int grid, bool pair, int halves, bool exact_keys,
+                       cudaStream_t stream) {
   switch (Ny) {
-    case 4: return launch2<4, GL>(a, smem, grid, pair, halves, stream);
-    case 8: return launch2<8, GL>(a, smem, grid, pair, halves, stream);
-    case 12: return launch2<12, GL>(a, smem, grid, pair, halves, stream);
-    case 16: return launch2<16, GL>(a, smem, grid, pair, halves, stream);
-    case 24: return launch2<24, GL>(a, smem, grid, pair, halves, stream);
-    case 32: return launch2<32, GL>(a, smem, grid, pair, halves, stream);
-    case 48: return launch2<48, GL>(a, smem, grid, pair, halves, stream);
-    case 64: return launch2<64, GL>(a, smem, grid, pair, halves, stream);
+    case 4: return launch2<4, GL>(a, smem, grid, pair, halves, exact_keys, stream);
+    case 8: return launch2<8, GL>(a, smem, grid, pair, halves, exact_keys, stream);
+    case 12: return launch2<12, GL>(a, smem, grid, pair, halves, exact_keys, stream);
+    case 16: return launch2<16, GL>(a, smem, grid, pair, halves, exact_keys, stream);
+    case 24: return launch2<24, GL>(a, smem, grid, pair, halves, exact_keys, stream);
+    case 32: return launch2<32, GL>(a, smem, grid, pair, halves, exact_keys, stream);
+    case 48: return launch2<48, GL>(a, smem, grid, pair, halves, exact_keys, stream);
+    case 64: return launch2<64, GL>(a, smem, grid, pair, halves, exact_keys, stream);
     default:
       nr::set_error("nr_maxsim2_fwd: Ny=%d has no tensor-core instantiation (4,8,12,16,24,32,48,64)", Ny);
       return -3;
@@ -489,8 +502,22 @@ extern "C" int nr_maxsim2_supported(int64_t Nx, int64_t Ny, int64_t d) {
   return (ny_ok && Nx % 4 == 0 && Nx >= 4 && Nx <= 128 && d % T2_BK == 0 && d > 0) ? 1 : 0;
 }
 
+static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
+                           void* workspace, int flags, void* stream);
+
 extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
                               void* workspace, void* stream) {
+  return maxsim2_fwd_impl(probs, nprob, Nx, Ny, d, workspace, 0, stream);
+}
+
+/* flags & 1: the operands are split-bf16 (nr_prep_tokens_split): exact-order keys in the column direction */
+extern "C" int nr_maxsim2_fwd_ex(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
+                                 void* workspace, int flags, void* stream) {
+  return maxsim2_fwd_impl(probs, nprob, Nx, Ny, d, workspace, flags, stream);
+}
+
+static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
+                           void* workspace, int flags, void* stream) {
   NR_CHECK_ARG(workspace && ((uintptr_t)workspace & 3) == 0, "nr_maxsim2_fwd: workspace (>= 16 bytes, 4-byte aligned) required");
   NR_CHECK_ARG(probs && nprob >= 1 && nprob <= T2_MAX_PROB, "nr_maxsim2_fwd: 1..%d problems per launch (got %d)",
                T2_MAX_PROB, nprob);
@@ -571,6 +598,7 @@ extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_
   // epilogue warps per set: 8 (two column halves per TMEM lane quarter) unless NR_TC2_HALVES=1
   int halves = 2;
   if (const char* hv = getenv("NR_TC2_HALVES")) halves = atoi(hv) == 1 ? 1 : 2;
-  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, pair, halves, (cudaStream_t)stream);
-  return dispatch_ny<4>((int)Ny, a, smem, grid, pair, halves, (cudaStream_t)stream);
+  const bool exact_keys = (flags & 1) != 0;
+  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, pair && !exact_keys, halves, exact_keys, (cudaStream_t)stream);
+  return dispatch_ny<4>((int)Ny, a, smem, grid, pair && !exact_keys, halves, exact_keys, (cudaStream_t)stream);
 }

@@ -353,7 +353,10 @@ def maxsim2_fwd(problems, keep=True):
         a.out2_sr, a.out2_sc = q.get("strides2", (0, 0))
         a.pmax_x, a.ystar, a.pmax_y, a.xstar = [t.data_ptr() if t is not None else None for t in sv]
     ws = _tile_workspace(dev)                                   # counters of the dynamic tile scheduler
-    _call("nr_maxsim2_fwd", ctypes.cast(arr, ctypes.c_void_p), len(problems), nx, ny, d, _p(ws), _stream())
+    if problems[0]["X"].split:      # split-bf16 operands: exact-order column keys
+        _call("nr_maxsim2_fwd_ex", ctypes.cast(arr, ctypes.c_void_p), len(problems), nx, ny, d, _p(ws), 1, _stream())
+    else:
+        _call("nr_maxsim2_fwd", ctypes.cast(arr, ctypes.c_void_p), len(problems), nx, ny, d, _p(ws), _stream())
     return saved
 
 
