@@ -295,6 +295,10 @@ int nr_transpose_add(const float* a, int64_t lda, const float* b, int64_t ldb, f
 size_t nr_sinkhorn_workspace_bytes(int64_t B);
 int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
                 float* v2, void* workspace, size_t workspace_bytes, void* stream);
+/* as nr_sinkhorn with the rows per CTA of the multi-CTA variants chosen by the caller (0 = automatic): inside a head
+ * step fewer, larger CTAs leave SMs to the concurrent token-pair contraction */
+int nr_sinkhorn_ex(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2, float* v2,
+                   void* workspace, size_t workspace_bytes, int rows_per_cta, void* stream);
 
 /* ---- memory-bank FIFO (modeling.py:222-249): bank = cat(new, old)[:capacity] -----------------
  * out [cap, row_bytes] <- new [n_new, row_bytes] followed by old [n_old, row_bytes], truncated. */

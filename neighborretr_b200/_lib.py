@@ -66,6 +66,7 @@ SIGNATURES = {
     "nr_transpose_add": (_I, [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _F, _F, _P]),
     "nr_sinkhorn_workspace_bytes": (_SZ, [_I64]),
     "nr_sinkhorn": (_I, [_P, _P, _I64, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "nr_sinkhorn_ex": (_I, [_P, _P, _I64, _I, _P, _P, _P, _P, _P, _SZ, _I, _P]),
     "nr_fifo_update": (_I, [_P, _I64, _P, _I64, _P, _I64, _I64, _P]),
     "nr_rank_count": (_I, [_P, _I64, _I64, _I64, _P, _I64, _P, _P, _P]),
     "nr_topk_rows": (_I, [_P, _I64, _I64, _I64, _I, ctypes.c_int32, _P, _P, _P]),

@@ -522,8 +522,25 @@ extern "C" size_t nr_sinkhorn_workspace_bytes(int64_t B) {
   return 256 + 2 * 1024 * sizeof(float) + (size_t)4 * (size_t)B * 8;
 }
 
+static int sinkhorn_impl(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
+                         float* v2, void* workspace, size_t workspace_bytes, int rows_hint, void* stream);
+
 extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
                            float* v2, void* workspace, size_t workspace_bytes, void* stream) {
+  return sinkhorn_impl(G, GT, B, iters, u1, v1, u2, v2, workspace, workspace_bytes, 0, stream);
+}
+
+/* rows_per_cta > 0: matrix rows per CTA of the multi-CTA variants.  The chain is latency-bound (its CTAs mostly wait
+ * for each other), so inside a head step — where the token-pair contraction wants every SM the chain does not hold —
+ * fewer, larger CTAs make the STEP faster although the chain alone gets slower (measured at 2 ranks: B = 256 with 16
+ * rows per CTA 705 us per step vs 744 us with 4; B = 1024 with 16 rows 2.21 ms vs 2.40 ms with 8). */
+extern "C" int nr_sinkhorn_ex(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
+                              float* v2, void* workspace, size_t workspace_bytes, int rows_per_cta, void* stream) {
+  return sinkhorn_impl(G, GT, B, iters, u1, v1, u2, v2, workspace, workspace_bytes, rows_per_cta, stream);
+}
+
+static int sinkhorn_impl(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
+                         float* v2, void* workspace, size_t workspace_bytes, int rows_hint, void* stream) {
   NR_CHECK_ARG(G && GT && u1 && v1 && u2 && v2 && workspace && B > 0 && iters >= 0, "nr_sinkhorn: bad arguments");
   NR_CHECK_ARG(workspace_bytes >= nr_sinkhorn_workspace_bytes(B), "nr_sinkhorn: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
@@ -565,6 +582,7 @@ extern "C" int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters
   // B=512 335 / 185 / 217, B=1024 319 / 265 / 336 -> 4 rows up to B=383, 8 rows beyond (more if the grid would not
   // be co-resident, see below)
   int rows_per_cta = B < 384 ? 4 : 8;
+  if (rows_hint > 0) rows_per_cta = rows_hint;
   if (const char* rv = getenv("NR_SINKHORN_ROWS")) { int r2 = atoi(rv); if (r2 >= 1) rows_per_cta = r2; }   // tuning knob
   while (rows_per_cta > 4 && ((size_t)2 * rows_per_cta * B + (size_t)2 * B) * sizeof(float) > 200 * 1024 &&
          (B + rows_per_cta - 2) / (rows_per_cta - 1) <= sms)

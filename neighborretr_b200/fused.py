@@ -130,8 +130,9 @@ class HeadPrologue:
         B, iters = self.T.r, int(self.hp[4])
         _call("nr_gram_f32", _p(self.g2), _p(self.v2), B, B, self.T.d, _p(self.GG[0]), _p(self.GG[1]), _stream())
         d_ = self.duals
-        _call("nr_sinkhorn", _p(self.GG[0]), _p(self.GG[1]), B, iters, _p(d_[0]), _p(d_[1]), _p(d_[2]), _p(d_[3]),
-              _p(self.lib_ws), self.nws, _stream())
+        # in-step: 16 rows per CTA for the multi-CTA variants (the chain shares the GPU with the contraction)
+        _call("nr_sinkhorn_ex", _p(self.GG[0]), _p(self.GG[1]), B, iters, _p(d_[0]), _p(d_[1]), _p(d_[2]), _p(d_[3]),
+              _p(self.lib_ws), self.nws, 16 if B >= 256 else 0, _stream())
 
     def run_forked(self):
         with ops.ForkJoin(2) as fj:
