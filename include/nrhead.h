@@ -292,6 +292,8 @@ int nr_transpose_add(const float* a, int64_t lda, const float* b, int64_t ldb, f
  * G [B,B], GT [B,B] (= G^T, caller-provided).  Chain 1 runs on G, chain 2 on G^T; outputs the
  * duals u1,v1,u2,v2 [B].  workspace: nr_sinkhorn_workspace_bytes(B) bytes, zero-initialised by
  * the library on `stream`. */
+/* (for B > 1536 the workspace also holds exp(G - max G) and its transpose, 2 * B * B floats: the batch no longer
+ * fits shared memory and every half-iteration streams them from HBM) */
 size_t nr_sinkhorn_workspace_bytes(int64_t B);
 int nr_sinkhorn(const float* G, const float* GT, int64_t B, int iters, float* u1, float* v1, float* u2,
                 float* v2, void* workspace, size_t workspace_bytes, void* stream);
