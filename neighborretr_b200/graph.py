@@ -278,11 +278,19 @@ class _ReplayFunction(torch.autograd.Function):
             raise RuntimeError("GraphedHead: backward() of a step whose static gradients were overwritten by a later "
                                "forward; call loss.backward() before the next model(...) (or set head_graph=False)")
         s = g5[0]
+        gl = r.step.grad_list
+        live = [g for g in gl if g is not None]
+        scaled = iter(torch._foreach_mul(live, s))              # one multi-tensor launch for all 13 gradients
         out = []
-        for g, (dt, shp) in zip(r.step.grad_list[:4], ctx.meta):
-            out.append(None if g is None else (s * g).to(dt).reshape(shp))
-        for g in r.step.grad_list[4:]:
-            out.append(None if g is None else s * g)
+        for i, g in enumerate(gl):
+            if g is None:
+                out.append(None)
+                continue
+            t = next(scaled)
+            if i < 4:
+                dt, shp = ctx.meta[i]
+                t = t.to(dt).reshape(shp)
+            out.append(t)
         return (None, None, None, None, *out)
 
 
