@@ -35,7 +35,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t d, in
 __host__ __device__ constexpr int t2_threads(int hs) { return 64 + 2 * 128 * hs; }
 constexpr int T2_BM = 128;
 constexpr int T2_BK = 64;                  // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int T2_MAX_STAGES = 4;
+constexpr int T2_MAX_STAGES = 6;
 constexpr int T2_A_BYTES = T2_BM * 128;    // 16 KB
 constexpr int T2_ACC_COLS = 256;           // TMEM columns per accumulator stage
 constexpr int T2_MAX_PROB = 4;
@@ -88,16 +88,26 @@ __device__ __forceinline__ uint32_t group_colmax(uint32_t* k, int lane) {
   return k[0];
 }
 
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t m, uint32_t c) {    // (a & m) | c
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(m), "r"(c));
+  return d;
+}
+
 template <int N>
 __device__ __forceinline__ void set_barrier(int set) {      // named barrier 1 / 2: the N threads of one epilogue set
   if (set == 0) asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
   else asm volatile("bar.sync 2, %0;" ::"n"(N) : "memory");
 }
 
-// CL2 (opt-in, see nr_maxsim2_fwd): CTA pairs (clusters of 2).  The two CTAs of a pair work on the SAME Y box and
-// adjacent X boxes; each loads half of the Y box and multicasts it to both, which halves the L2 reads of the dominant
-// operand.  The leader CTA claims pair-tiles and publishes them into both rings; smem stages are released by both
-// MMA issuers.
+// CL2: CTA pairs (clusters of 2, the two SMs of a TPC) running tcgen05.mma.cta_group::2.  A pair works on two adjacent X
+// boxes against ONE Y box: each CTA loads its own X box and HALF of the Y box into its own shared memory, the leader's
+// MMA issuer multiplies M = 256 rows (128 per CTA, accumulators in each CTA's own TMEM) by the N columns whose halves
+// the two CTAs hold.  Per tile an SM ingests its X box + half a Y box instead of X + Y: the L2 -> SM operand stream
+// (ncu: 584 MB per MSR-VTT step launch with independent CTAs) drops by a third, and a stage is 31 KB instead of 46, so
+// the ring gets deeper.  The leader CTA claims pair-tiles and publishes them into both CTAs' rings; every operand
+// barrier that the MMA issuer waits on lives in the leader, the stage-free and accumulator-ready barriers are
+// signalled in both CTAs by a multicast commit.  Opt-in: see the measurement quoted in maxsim2_fwd_impl.
 // HS = 2: each epilogue set has 8 warps; the two warps that share a TMEM lane quarter split the accumulator
 // columns of the tile (chunks [0, n/2) and [n/2, n)), which doubles the warps available to hide the latency of the
 // shuffle / shared-memory / global-store chains of the reduction (ncu: 0.6 eligible warps per scheduler with HS = 1).
@@ -114,7 +124,9 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A | B)] then per epilogue set: [hp 128 x hp_ld f32] [keyG (128/GL) x kg_ld u32]
   // [colw SX x UN f32] [wy UN f32], then the barriers
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the extern array, not an integer round trip: the compiler keeps the shared address space and
+  // emits 32-bit LDS / STS instead of generic accesses with 64-bit address arithmetic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = T2_A_BYTES + a.b_bytes;
   float* hp = reinterpret_cast<float*>(smem + (size_t)a.stages * stage_bytes);
   uint32_t* keyG = reinterpret_cast<uint32_t*>(hp + 2 * T2_BM * a.hp_ld);
@@ -135,16 +147,17 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
 
   if (warp == 0 && lane == 0) {
     for (int p = 0; p < a.nprob; ++p) { tma_prefetch_desc(&a.tmx[p]); tma_prefetch_desc(&a.tmy[p]); }
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CL2 ? 2 : 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, T2_SET); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    // CL2: the leader's issuer overwrites the accumulator stage in BOTH CTAs: both epilogue sets release it there
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, CL2 ? 2 * T2_SET : T2_SET); }
     // ring: filled by the (leader's) scheduler; released by the MMA issuer and one epilogue set of every CTA of the
     // pair, plus the non-leader's TMA producer
     for (int s = 0; s < T2_RING; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, CL2 ? 2 * (1 + T2_SET) + 1 : 1 + T2_SET); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CL2) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -177,7 +190,9 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)(a.MU + a.SY * NY) * 128u;
+      // CL2: the leader's barrier collects the bytes of both CTAs (X box + half a Y box each)
+      const int hb = a.SY * NY / 2;
+      const uint32_t tx_bytes = CL2 ? 2u * (uint32_t)(a.MU + hb) * 128u : (uint32_t)(a.MU + a.SY * NY) * 128u;
       // Dynamic tile scheduler: tiles are claimed from a global counter, so a CTA whose SM was still busy with
       // another kernel of the step graph (the persistent grid is one CTA per SM) simply takes fewer tiles.
       for (int n = 0;; ++n) {
@@ -228,15 +243,15 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
         decode(tile, p, mt, nt);
         const int row_x = mt * a.MU, row_y = nt * a.SY * NY;
         for (int kb = 0; kb < a.num_kb; ++kb) {
-          mbar_wait(empty + stage, phase ^ 1);             // CL2: released by BOTH MMA issuers (count 2)
+          mbar_wait(empty + stage, phase ^ 1);             // CL2: the leader's commit frees the stage in both CTAs
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(full + stage, tx_bytes);
-          tma_load_2d(sa, &a.tmx[p], full + stage, kb * T2_BK, row_x);
-          if (CL2) {                                       // my half of the Y box, to both CTAs of the pair
-            const int hb = a.SY * NY / 2;
-            tma_load_2d_mc(sa + T2_A_BYTES + (size_t)cr * hb * 128, &a.tmy[p], full + stage, kb * T2_BK,
-                           row_y + (int)cr * hb, (uint16_t)3);
+          if (CL2) {                                       // my X box and my half of the Y box, into MY shared memory
+            if (cr == 0) mbar_expect_tx(full + stage, tx_bytes);
+            tma_load_2d_cg2(sa, &a.tmx[p], full + stage, kb * T2_BK, row_x);
+            tma_load_2d_cg2(sa + T2_A_BYTES, &a.tmy[p], full + stage, kb * T2_BK, row_y + (int)cr * hb);
           } else {
+            mbar_expect_tx(full + stage, tx_bytes);
+            tma_load_2d(sa, &a.tmx[p], full + stage, kb * T2_BK, row_x);
             tma_load_2d(sa + T2_A_BYTES, &a.tmy[p], full + stage, kb * T2_BK, row_y);
           }
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -246,14 +261,16 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(T2_BM, a.UN);
+      const uint32_t idesc = umma_idesc_bf16(CL2 ? 2 * T2_BM : T2_BM, a.UN);
       int stage = 0; uint32_t phase = 0;
       for (int it = 0;; ++it) {
         const int tile = ring_take(it);
         if (tile < 0) { if (CL2) ring_take(it + 1); break; }
+        if (CL2 && cr != 0) continue;                    // the leader issues for the pair; the peer only frees ring slots
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty + acc, acc_phase ^ 1);          // epilogue drained this accumulator
+        if (CL2) mbar_wait_cluster(tempty + acc, acc_phase ^ 1);   // both CTAs' epilogues drained this accumulator
+        else mbar_wait(tempty + acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * T2_ACC_COLS);
         for (int kb = 0; kb < a.num_kb; ++kb) {
@@ -264,13 +281,16 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = umma_desc_kmajor_sw128(sa + T2_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < T2_BK / 16; ++k)           // advance 32 B (16 bf16) inside the swizzle row
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-          if (CL2) umma_commit_mc(empty + stage, (uint16_t)3);   // the peer multicasts into this stage too
+          for (int k = 0; k < T2_BK / 16; ++k) {         // advance 32 B (16 bf16) inside the swizzle row
+            if (CL2) umma_bf16_cg2(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          if (CL2) umma_commit_cg2(empty + stage, (uint16_t)3);  // the stage is free in both CTAs
           else umma_commit(empty + stage);               // smem slot free when these MMAs retire
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull + acc);                        // accumulator ready for the epilogue
+        if (CL2) umma_commit_cg2(tfull + acc, (uint16_t)3);      // accumulator ready for the epilogues of both CTAs
+        else umma_commit(tfull + acc);                   // accumulator ready for the epilogue
         if (it == 0) T2_TRACE(5);                          // first tile issued
         T2_TRACE(6);                                       // last tile issued (overwritten per tile)
       }
@@ -287,6 +307,9 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
     const int Nx = a.Nx;
     const int sx = r / Nx, x = r - sx * Nx;
     const uint32_t low = LOWM - ((uint32_t)lane & LOWM);
+    const uint32_t himask = ~LOWM;
+    // and_or(): (u & himask) | low as ONE explicit LOP3 per accumulator element (left to the compiler it becomes an
+    // AND with the immediate plus a second LOP3 that recomputes `low` from the lane index)
     float* const hpb = hp + (size_t)set * T2_BM * a.hp_ld;
     uint32_t* const kgs = keyG + (size_t)set * (T2_BM / GL) * a.kg_ld;
     float* const cws = colw + (size_t)set * a.SX * a.UN;
@@ -308,9 +331,11 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
       const int rx = mt * a.SX + sx;
       const bool row_ok = (r < a.MU) && (rx < P.Rx);
       const float wxv = row_ok ? P.wx[(int64_t)rx * Nx + x] : 0.f;
+      // per-tile base pointers: inside the tile every offset is a small 32-bit product
       const int64_t obase = ((int64_t)rx * P.Ry + ry0) * Nx + x;
-      float* const pmx = row_ok ? P.pmax_x : nullptr;
-      uint8_t* const yst = row_ok ? P.ystar : nullptr;
+      float* const pmx = (row_ok && P.pmax_x) ? P.pmax_x + obase : nullptr;
+      uint8_t* const yst = (row_ok && P.ystar) ? P.ystar + obase : nullptr;
+      float* const hp_row = hpb + r * a.hp_ld;
       // the Y token weights of this tile, staged while the MMAs of the tile are still running (the set's previous
       // tile finished with a set barrier after its last read of wys)
       for (int c = et; c < ncols; c += T2_SET) wys[c] = P.wy[(int64_t)ry0 * NY + c];
@@ -328,8 +353,8 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
           const float best = TreeRed<NY>::fmax_(f);
           const int bi = TreeRed<NY>::first_eq(f, best, 0);
           if (sy < sy_n) {
-            hpb[r * a.hp_ld + sy] = wxv * best;
-            const int64_t o = obase + (int64_t)sy * Nx;
+            hp_row[sy] = wxv * best;
+            const int o = sy * Nx;
             if (pmx) pmx[o] = best;
             if (yst) yst[o] = (uint8_t)bi;
           }
@@ -343,8 +368,8 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
             // order-preserving integer image of the fp32 value (all exponents keep their full relative precision:
             // only the log2(GL) lowest mantissa bits give way to the row index), ties -> lower row
             const uint32_t u = v[g * GL + j];
-            if constexpr (XK) k[j] = ((u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u)) & ~LOWM) | low;
-            else k[j] = (__float_as_uint(__uint_as_float(u) + 2.0f) & ~LOWM) | low;
+            if constexpr (XK) k[j] = and_or(u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u), himask, low);
+            else k[j] = and_or(__float_as_uint(__uint_as_float(u) + 2.0f), himask, low);
           }
           kg_row[ch * CH + g * GL] = group_colmax<GL>(k, lane);
         }
@@ -379,13 +404,20 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty + set);                         // TMEM stage may be overwritten
+      if (CL2) mbar_arrive_remote(tempty + set, 0);      // TMEM stage may be overwritten (the leader issues for both)
+      else mbar_arrive(tempty + set);
       set_barrier<T2_SET>(set);
-      // F1: combine the Nx/GL group partials of each (X sample, column): value, arg-max row, weighted value
+      // F1: combine the Nx/GL group partials of each (X sample, column): value, arg-max row, weighted value.
+      // Element e = s * ncols + c, e = et, et + T2_SET, ...: (s, c) advance without a division.
       {
         const int ng = Nx / GL;
-        for (int e = et; e < sx_n * ncols; e += T2_SET) {
-          const int s = e / ncols, c = e - s * ncols;
+        const int64_t ybase = ((int64_t)(mt * a.SX) * P.Ry + ry0) * NY;
+        float* const pmy = P.pmax_y ? P.pmax_y + ybase : nullptr;
+        uint8_t* const xst = P.xstar ? P.xstar + ybase : nullptr;
+        const int srow = P.Ry * NY;                       // output stride between the X samples of the tile
+        int s = 0, c = et;
+        while (c >= ncols) { c -= ncols; ++s; }
+        for (; s < sx_n;) {
           const uint32_t* kp = kgs + (s * ng) * a.kg_ld + c;
           uint32_t best = kp[0]; int bg = 0;
           for (int gi = 1; gi < ng; ++gi) {
@@ -395,16 +427,18 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
           const uint32_t tb = best & ~LOWM;
           const float val = XK ? __uint_as_float((tb & 0x80000000u) ? (tb ^ 0x80000000u) : ~tb) : __uint_as_float(tb) - 2.0f;
           const int xs = bg * GL + (int)(LOWM - (best & LOWM));
-          const int64_t o = ((int64_t)(mt * a.SX + s) * P.Ry + ry0) * NY + c;
-          if (P.pmax_y) P.pmax_y[o] = val;
-          if (P.xstar) P.xstar[o] = (uint8_t)xs;
+          const int o = s * srow + c;
+          if (pmy) pmy[o] = val;
+          if (xst) xst[o] = (uint8_t)xs;
           cws[s * a.UN + c] = wys[c] * val;
+          c += T2_SET;
+          while (c >= ncols) { c -= ncols; ++s; }
         }
       }
       set_barrier<T2_SET>(set);
       // F2: S[rx, ry] = alpha * (sum over the Nx rows of hp + sum over the NY columns of colw)
-      for (int e = et; e < sx_n * sy_n; e += T2_SET) {
-        const int s = e / sy_n, sy = e - s * sy_n;
+      for (int e = et, s = 0, sy = et; e < sx_n * sy_n; e += T2_SET, sy += T2_SET) {
+        while (sy >= sy_n) { sy -= sy_n; ++s; }           // e = s * sy_n + sy without a division
         const float* hrow = hpb + (s * Nx) * a.hp_ld + sy;
         float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;     // independent chains: the loads pipeline
         int xx = 0;
@@ -431,33 +465,19 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
   if (CL2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or signal its barriers
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if (CL2) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int NY, int GL>
-static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, int halves, bool exact_keys, cudaStream_t stream) {
-  if (exact_keys) {            // split-bf16 operands: 16 epilogue warps, exact-order keys
-    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    maxsim2_fwd_tc_kernel<NY, GL, false, 2, true><<<grid, t2_threads(2), smem, stream>>>(a);
-    NR_CHECK_LAUNCH("nr_maxsim2_fwd");
-    return 0;
-  }
-  if (halves == 2 && !pair) {
-    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    maxsim2_fwd_tc_kernel<NY, GL, false, 2, false><<<grid, t2_threads(2), smem, stream>>>(a);
-    NR_CHECK_LAUNCH("nr_maxsim2_fwd");
-    return 0;
-  }
-  if (pair) {
-    // CTA pairs: thread-block clusters of 2 (same TPC), multicast of the shared Y box
-    NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
+template <int NY, int GL, bool CL2, int HS, bool XK>
+static int launch_variant(const Tc2Args& a, size_t smem, int grid, cudaStream_t stream) {
+  auto kern = maxsim2_fwd_tc_kernel<NY, GL, CL2, HS, XK>;
+  NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CL2) {                   // CTA pairs: thread-block clusters of 2 (the two SMs of a TPC)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(t2_threads(1));
+    cfg.blockDim = dim3(t2_threads(HS));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -465,14 +485,24 @@ static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, int halve
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    NR_CUDA(cudaLaunchKernelEx(&cfg, maxsim2_fwd_tc_kernel<NY, GL, true, 1, false>, a));
+    NR_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     return 0;
   }
-  NR_CUDA(cudaFuncSetAttribute(maxsim2_fwd_tc_kernel<NY, GL, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  maxsim2_fwd_tc_kernel<NY, GL, false, 1, false><<<grid, t2_threads(1), smem, stream>>>(a);
+  kern<<<grid, t2_threads(HS), smem, stream>>>(a);
   NR_CHECK_LAUNCH("nr_maxsim2_fwd");
   return 0;
+}
+
+// exact_keys: split-bf16 operands (exact-order column keys); pair: cta_group::2; halves == 1: 8 epilogue warps (debug)
+template <int NY, int GL>
+static int launch2(const Tc2Args& a, size_t smem, int grid, bool pair, int halves, bool exact_keys, cudaStream_t stream) {
+  if (pair) {
+    if (exact_keys) return launch_variant<NY, GL, true, 2, true>(a, smem, grid, stream);
+    return launch_variant<NY, GL, true, 2, false>(a, smem, grid, stream);
+  }
+  if (exact_keys) return launch_variant<NY, GL, false, 2, true>(a, smem, grid, stream);
+  if (halves == 2) return launch_variant<NY, GL, false, 2, false>(a, smem, grid, stream);
+  return launch_variant<NY, GL, false, 1, false>(a, smem, grid, stream);
 }
 
 template <int GL>
@@ -546,24 +576,29 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
   if (a.SY > max_ry) a.SY = (int)((max_ry + SPC - 1) / SPC * SPC);
   a.UN = (a.SY * (int)Ny + 15) / 16 * 16;
   a.num_kb = (int)(d / T2_BK);
-  a.b_bytes = (a.UN * 128 + 1023) / 1024 * 1024;
   a.hp_ld = a.SY | 1;
   a.kg_ld = a.UN;
   if (GL == 8) { while (a.kg_ld % 32 != 8 && a.kg_ld % 32 != 24) a.kg_ld += 8; }
   else { while (a.kg_ld % 8 != 4) a.kg_ld += 4; }
-  // CTA pairs when the Y box splits into two swizzle-aligned halves and there is more than a wave of work
   int dev = 0, sms = 0;
   NR_CUDA(cudaGetDevice(&dev));
   NR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int64_t est_tiles = 0;
   for (int i = 0; i < nprob; ++i)
     est_tiles += ((probs[i].Rx + a.SX - 1) / a.SX) * ((probs[i].Ry + a.SY - 1) / a.SY);
-  // Opt-in (NR_TC2_PAIR=1): measured SLOWER than independent CTAs on B200 (MSR-VTT step 80 vs 75 us, b=1024 812 vs 760 us,
-  // ActivityNet tiles 554 vs 486 us): the multicast halves the L2 slice reads but every SM still ingests the whole
-  // Y box, and the shared stage release couples the two CTAs' pipelines.  Kept for the cta_group::2 follow-up.
+  // CTA pairs (cta_group::2): possible when the Y box splits into two swizzle-aligned halves.  Opt-in — NR_TC2_PAIR=1:
+  // when there are more than two waves of tiles; =2: whenever the shape allows (tests/test_gpu_tc2.py runs the parity
+  // cases this way).  Measured on B200 (profiles/r2_pair_vs_single.txt): parity-exact, a third less L2 -> SM traffic,
+  // but 6-9 % SLOWER than independent CTAs (MSR-VTT step tiles 4.14 vs 3.72 us, b = 1024 593 vs 557 us, ActivityNet
+  // tiles 469 vs 430 us): with two 256-column accumulator stages per SM the leader's issuer waits for the epilogues of
+  // BOTH CTAs (two cluster-scope barrier hops per tile), and the epilogue, not the operand stream, paces this kernel.
+  const bool pair_ok = (a.SY * (int)Ny) % 16 == 0 && a.UN == a.SY * (int)Ny;
   bool pair = false;
-  if (const char* ev = getenv("NR_TC2_PAIR"))
-    pair = atoi(ev) != 0 && (a.SY * (int)Ny) % 16 == 0 && a.UN == a.SY * (int)Ny && est_tiles >= 2 * sms;
+  if (const char* ev = getenv("NR_TC2_PAIR")) {
+    const int v = atoi(ev);
+    pair = v >= 2 ? pair_ok : (v == 1 && pair_ok && est_tiles >= 2 * sms);
+  }
+  a.b_bytes = ((pair ? a.UN / 2 : a.UN) * 128 + 1023) / 1024 * 1024;
   int tiles = 0;
   for (int i = 0; i < nprob; ++i) {
     const nr_maxsim2_problem& q = probs[i];
@@ -577,7 +612,7 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
     P.tile0 = tiles;
     tiles += (pair ? (P.n_mt + 1) / 2 : P.n_mt) * P.n_nt;        // pair-tiles: two adjacent X boxes x one Y box
     if (int e = make_tmap_bf16(&a.tmx[i], q.x_bf16, q.Rx * Nx, d, a.MU)) return e;
-    if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny / (pair ? 2 : 1))) return e;
+    if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny / (pair ? 2 : 1))) return e;   // pair: half boxes
   }
   a.n_tiles = tiles;
   a.tile_counter = (unsigned int*)workspace;        // {next tile, finished claimers}: zero on entry, zero again on exit
@@ -599,6 +634,6 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
   int halves = 2;
   if (const char* hv = getenv("NR_TC2_HALVES")) halves = atoi(hv) == 1 ? 1 : 2;
   const bool exact_keys = (flags & 1) != 0;
-  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, pair && !exact_keys, halves, exact_keys, (cudaStream_t)stream);
-  return dispatch_ny<4>((int)Ny, a, smem, grid, pair && !exact_keys, halves, exact_keys, (cudaStream_t)stream);
+  if (GL == 8) return dispatch_ny<8>((int)Ny, a, smem, grid, pair, halves, exact_keys, (cudaStream_t)stream);
+  return dispatch_ny<4>((int)Ny, a, smem, grid, pair, halves, exact_keys, (cudaStream_t)stream);
 }
