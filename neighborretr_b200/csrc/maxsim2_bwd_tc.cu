@@ -44,10 +44,12 @@ struct B2Src {
   const float* dH; int64_t g_o, g_s; float scale;
   int Rs, Ns, src_tokens, num_kb, kb0;        // kb0: first k-block of this source in the side's concatenated K range
   int part;                                   // 0 plain bf16 tile; 2 / 3: hi / lo tile of the exact fp32 coefficient
+  uint32_t ns_magic;                          // ceil(2^32 / Ns): t / Ns == umulhi(t, ns_magic) for t < 2^25
 };
 struct B2Side {
   const float* wO; float* dst;
   int Ro, No, out_tokens, n_mt, nsrc, kb_total, KS, kb_per_split, item0;
+  uint32_t no_magic;                          // ceil(2^32 / No)
   int src[B2_MAX_SRC];                        // indices into srcs[] / tms[]
 };
 struct alignas(64) B2Args {
@@ -56,6 +58,10 @@ struct alignas(64) B2Args {
   B2Side sides[B2_MAX_SIDES];
   int nsides, n_items, D, n_half, half_cols, debug;
 };
+
+// t / n for 0 <= t < 2^25, 2 <= n <= 128 (exact up to n = 144), magic = ceil(2^32 / n) (0 stands for n = 1): one IMAD.HI instead of the
+// ~25-instruction division
+__device__ __forceinline__ int div_magic(int t, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)t, magic) : t; }
 
 // plain bf16 coefficient (part 0 / 2) or the remainder of its bf16 rounding (part 3)
 __device__ __forceinline__ __nv_bfloat16 coef_part(float c, int part) {
@@ -73,7 +79,8 @@ __device__ __forceinline__ void red_add_v4_(float* addr, float a, float b, float
 // one accumulator pass and ONE red.add epilogue serve every pair that feeds the same output rows.
 __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __grid_constant__ B2Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // offset arithmetic on the extern array (no integer round trip): the routing-tile stores stay STS with 32-bit addresses
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = B2_A_BYTES + a.n_half * B2_B_HALF_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)2 * stage_bytes);
   uint64_t* b_full = bars;            // [2] TMA -> MMA
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
     uint8_t* const sa = smem + (size_t)grp * stage_bytes;
     uint32_t c = 0;
     int it = 0;
-    struct Pre { int sv[8]; float gv[8]; int ov[8]; float hv[8]; float cw; };
+    struct Pre { int sv[8]; float gv[8]; int ov[8]; float hv[8]; float cw; int rs_lo, n_rs, rs_j, sidx_j; };
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++it) {
       int sd, mt, kbA, kbB;
       decode(item, sd, mt, kbA, kbB);
@@ -190,35 +197,52 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
       const int row0 = mt * B2_BM;
       const int g = row0 + m;                          // global output token
       const bool valid = g < S.out_tokens;
-      const int ro = valid ? g / No : 0, o = valid ? g - ro * No : 0;   // (sample, token) of the output row
+      const int ro = valid ? div_magic(g, S.no_magic) : 0, o = valid ? g - ro * No : 0;   // (sample, token) of the row
       const float wo = valid ? S.wO[g] : 0.f;
-      const int ro_lo = row0 / No, ro_hi = min(S.Ro - 1, (row0 + B2_BM - 1) / No);   // out samples touching this tile
+      const int ro_lo = div_magic(row0, S.no_magic);                   // out samples touching this tile
+      const int ro_hi = min(S.Ro - 1, div_magic(row0 + B2_BM - 1, S.no_magic));
       // Routing data (arg-max bytes, upstream gradients) of a k-block is loaded into registers while the group's
       // previous k-block is being built.  Slots cover 8 partner samples per row / 8 out samples per column thread;
       // longer ranges (tiny Ns / No) take the direct-load remainder loops below.
+      // (walking pointers and validity predicates instead of per-entry 64-bit index products and clamped indices)
       auto load_pre = [&](int kb, Pre& P) {
         const B2Src& J = a.srcs[S.src[which_src(S, kb)]];
         const int Ns = J.Ns;
         const int t0 = (kb - J.kb0) * B2_BK;
-        const int rs_lo = t0 / Ns, rs_hi = min(J.Rs - 1, (t0 + B2_BK - 1) / Ns);
-        const uint8_t* stO = J.starO + (int64_t)ro * J.aO_o + o;
-        const float* gpO = J.dH + (int64_t)ro * J.g_o;
+        const int rs_lo = div_magic(t0, J.ns_magic);
+        const int n_rs = min(J.Rs - 1, div_magic(t0 + B2_BK - 1, J.ns_magic)) - rs_lo + 1;
+        P.rs_lo = rs_lo; P.n_rs = n_rs;
+        {
+          const uint8_t* stO = J.starO + ((int64_t)ro * J.aO_o + (int64_t)rs_lo * J.aO_s + o);
+          const float* gpO = J.dH + ((int64_t)ro * J.g_o + (int64_t)rs_lo * J.g_s);
+          const int64_t so = J.aO_s, sg = J.g_s;
+          const bool on = wo != 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rs = min(rs_lo + i, rs_hi);
-          P.sv[i] = (wo != 0.f) ? (int)stO[(int64_t)rs * J.aO_s] : 0;
-          P.gv[i] = (wo != 0.f) ? gpO[(int64_t)rs * J.g_s] : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = on && i < n_rs;
+            P.sv[i] = ok ? (int)*stO : 0;
+            P.gv[i] = ok ? *gpO : 0.f;
+            stO += so; gpO += sg;
+          }
         }
-        const int tsrc = min(t0 + j, J.src_tokens - 1);
-        const int rs = tsrc / Ns, sidx = tsrc - rs * Ns;
-        P.cw = (t0 + j < J.src_tokens) ? J.wS[tsrc] * J.scale : 0.f;
-        const uint8_t* st = J.starS + (int64_t)rs * J.aS_s + sidx;
-        const float* gp = J.dH + (int64_t)rs * J.g_s;
+        const bool cok = t0 + j < J.src_tokens;
+        const int tsrc = cok ? t0 + j : J.src_tokens - 1;
+        const int rs = div_magic(tsrc, J.ns_magic), sidx = tsrc - rs * Ns;
+        P.rs_j = rs; P.sidx_j = sidx;
+        P.cw = cok ? J.wS[tsrc] * J.scale : 0.f;
+        {
+          const int r2_0 = ro_lo + jh;
+          const uint8_t* st = J.starS + ((int64_t)rs * J.aS_s + (int64_t)r2_0 * J.aS_o + sidx);
+          const float* gp = J.dH + ((int64_t)rs * J.g_s + (int64_t)r2_0 * J.g_o);
+          const int64_t so = 2 * J.aS_o, sg = 2 * J.g_o;
+          const bool on = P.cw != 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r2 = min(ro_lo + jh + 2 * i, ro_hi);
-          P.ov[i] = (P.cw != 0.f) ? (int)st[(int64_t)r2 * J.aS_o] : 0;
-          P.hv[i] = (P.cw != 0.f) ? gp[(int64_t)r2 * J.g_o] : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = on && r2_0 + 2 * i <= ro_hi;
+            P.ov[i] = ok ? (int)*st : 0;
+            P.hv[i] = ok ? *gp : 0.f;
+            st += so; gp += sg;
+          }
         }
       };
       // this group's k-blocks of the item: those whose CTA-wide counter has parity grp
@@ -246,12 +270,12 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
         // (1) out-token side: row m, one entry per source sample overlapping this k-block
         if (coefo != 0.f) {
           uint8_t* srow = sa + m * 128;
-          const int rs_lo = t0 / Ns, rs_hi = min(J.Rs - 1, (t0 + B2_BK - 1) / Ns);
+          const int rs_lo = cur.rs_lo, rs_hi = rs_lo + cur.n_rs - 1;
+          const int tb = rs_lo * Ns - t0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rs = rs_lo + i;
-            const int t = rs * Ns + cur.sv[i] - t0;
-            if (rs <= rs_hi && t >= 0 && t < B2_BK)
+            const int t = tb + i * Ns + cur.sv[i];
+            if (i < cur.n_rs && (unsigned)t < (unsigned)B2_BK)
               *reinterpret_cast<__nv_bfloat16*>(srow + (((t >> 3) ^ (m & 7)) << 4) + (t & 7) * 2) =
                   coef_part(cur.gv[i] * coefo, J.part);
           }
@@ -271,11 +295,10 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
         // (2) source-token side: column j, one entry per out sample of this tile; lands in row (ro, o*) and is
         //     ADDED to whatever side (1) put there (mutual arg-max pairs)
         if (cur.cw != 0.f) {
-          const int tsrc_j = t0 + j;                     // cur.cw != 0 implies tsrc_j < src_tokens
-          const int rs_j = tsrc_j / Ns, sidx_j = tsrc_j - rs_j * Ns;
+          const int rs_j = cur.rs_j, sidx_j = cur.sidx_j;   // cur.cw != 0 implies t0 + j < src_tokens
           auto put = [&](int r2, int ostar, float gval) {
             const int mm = r2 * No + ostar - row0;
-            if (mm >= 0 && mm < B2_BM) {
+            if ((unsigned)mm < (unsigned)B2_BM) {
               __nv_bfloat16* e =
                   reinterpret_cast<__nv_bfloat16*>(sa + mm * 128 + (((j >> 3) ^ (mm & 7)) << 4) + (j & 7) * 2);
               if (J.part == 0) {
@@ -296,10 +319,8 @@ __global__ void __launch_bounds__(B2_THREADS, 1) maxsim2_bwd_tc_kernel(const __g
             if (r2 <= ro_hi) put(r2, cur.ov[i], cur.hv[i]);
           }
           if (ro_lo + jh + 16 <= ro_hi) {                        // remainder (No < 10 only)
-            const int tsrc = t0 + j;
-            const int rs = tsrc / Ns, sidx = tsrc - rs * Ns;
-            const uint8_t* st = J.starS + (int64_t)rs * J.aS_s + sidx;
-            const float* gp = J.dH + (int64_t)rs * J.g_s;
+            const uint8_t* st = J.starS + (int64_t)rs_j * J.aS_s + sidx_j;
+            const float* gp = J.dH + (int64_t)rs_j * J.g_s;
             for (int r2 = ro_lo + jh + 16; r2 <= ro_hi; r2 += 2)
               put(r2, (int)st[(int64_t)r2 * J.aS_o], gp[(int64_t)r2 * J.g_o]);
           }
@@ -441,6 +462,9 @@ extern "C" int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int njobs, int64_t
     NR_CHECK_ARG(jb.part == 0 || jb.part == 2 || jb.part == 3, "nr_maxsim2_bwd: job %d: part must be 0, 2 or 3", i);
     J.part = jb.part;
     J.src_tokens = J.Rs * J.Ns;
+    J.ns_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)J.Ns - 1) / (uint64_t)J.Ns);
+    NR_CHECK_ARG((int64_t)J.Rs * J.Ns < ((int64_t)1 << 25) && (int64_t)Ro * No < ((int64_t)1 << 25),
+                 "nr_maxsim2_bwd: job %d: more than 2^25 tokens on one side", i);
     J.num_kb = (J.src_tokens + B2_BK - 1) / B2_BK;
     if (int e = make_tmap_srcT(&a.tms[i], jb.srcT, d, J.src_tokens, jb.src_ld, a.half_cols)) return e;
     // side = jobs with the same output rows
@@ -453,6 +477,7 @@ extern "C" int nr_maxsim2_bwd(const nr_maxsim2_bwd_job* jobs, int njobs, int64_t
       B2Side& S = a.sides[sd];
       S.wO = wO; S.dst = jb.dst; S.Ro = Ro; S.No = No; S.out_tokens = Ro * No;
       S.n_mt = (S.out_tokens + B2_BM - 1) / B2_BM;
+      S.no_magic = (uint32_t)((((uint64_t)1 << 32) + (uint64_t)No - 1) / (uint64_t)No);
     }
     B2Side& S = a.sides[sd];
     NR_CHECK_ARG(S.nsrc < B2_MAX_SRC, "nr_maxsim2_bwd: more than %d sources for one output", B2_MAX_SRC);
