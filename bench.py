@@ -169,7 +169,7 @@ def eval_cpu_baseline(nq=1000):
 def run_eval_bench(model, dev, steps, nq=1000):
     """Eval sim + R@K latency (BASELINE.json configs[3]): 1k x 1k MSR-VTT-shaped test set, t2v and v2t."""
     from neighborretr_b200 import ops
-    from neighborretr_b200.evaluator import _run_on_single_gpu, similarity_matrix
+    from neighborretr_b200.evaluator import _run_on_single_gpu, retrieval_metrics_fused, similarity_matrix
     from neighborretr_b200.metrics import RetrievalMetrics, metrics_from_counts
     nt, nv, _ = synth.SHAPES["msrvtt"]
     host = synth.make_batch(nq, nt, nv, d=D, seed=77)
@@ -189,8 +189,21 @@ def run_eval_bench(model, dev, steps, nq=1000):
         sim, sim_t = _run_on_single_gpu(model, d["text_mask"], d["video_mask"], d["text_feat"], d["video_feat"])
         return RetrievalMetrics.compute_metrics(sim), RetrievalMetrics.compute_metrics(sim_t)
 
-    out = {}
-    for name, fn in (("resident_ms", resident), ("e2e_ms", e2e)):
+    def fused():    # ranks straight from the contraction's epilogue: the similarity matrix is never written
+        return retrieval_metrics_fused(model, res["text_mask"], res["video_mask"], res["text_feat"], res["video_feat"])
+
+    # ranks of the fused path against ranks counted on the materialised matrix, same token weights (two evaluations of
+    # the weight MLPs differ in the last bit: float atomics in the second layer)
+    from neighborretr_b200.evaluator import _eval_operands
+    with torch.no_grad():
+        tm_, vm_, tw_, vw_, prec_ = _eval_operands(model, res["text_mask"], res["video_mask"], res["text_feat"],
+                                                   res["video_feat"], 64)
+        s_, _ = ops.maxsim(res["text_feat"], res["video_feat"], tw_, vw_, tm_, vm_, prec_)
+        fr = ops.FusedRanker(res["text_feat"], res["video_feat"], tw_, vw_, tm_, vm_, prec_)
+        cf = torch.stack(fr.counts(fr.diagonal(nq)))
+        cm = torch.stack([*ops.rank_counts(s_), *ops.rank_counts(s_.t().contiguous())])
+    out = {"fused_equals_materialised": bool(torch.equal(cf, cm))}       # every count of every query, both directions
+    for name, fn in (("fused_resident_ms", fused), ("resident_ms", resident), ("e2e_ms", e2e)):
         for _ in range(3):
             r = fn()
         torch.cuda.synchronize()
@@ -262,8 +275,12 @@ def run_eval_workload(args):
         tf[c0:c0 + chunk] = hb.text_feat.to(dev); vf[c0:c0 + chunk] = hb.video_feat.to(dev)
         tm[c0:c0 + chunk] = hb.text_mask.to(dev); vm[c0:c0 + chunk] = hb.video_mask.to(dev)
 
+    fused = args.eval_ranks == "fused"
+    cfg_line["ranks"] = ("counted in the contraction's epilogue, S never written (no top-k lists)" if fused else
+                         "per-rank block of S written, rank-count + top-10 kernels over it")
+
     def once():
-        return sharded_retrieval(model, tm, vm, tf, vf, topk=10)
+        return sharded_retrieval(model, tm, vm, tf, vf, topk=10, fused=fused)
 
     def sync_all():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -622,6 +639,9 @@ def main():
                     help="head: fwd+bwd steps/s (the metric BASELINE.json quotes); eval: column-sharded similarity + "
                          "R@K latency on an --eval-size x --eval-size test set (configs[4]: 100000)")
     ap.add_argument("--eval-size", type=int, default=100000)
+    ap.add_argument("--eval-ranks", default="fused", choices=["fused", "materialised"],
+                    help="--workload eval: rank counts from the contraction's epilogue (no similarity matrix), or the "
+                         "per-rank block of S + rank-count / top-k kernels")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra precision-mode / module-API measurements")
     args = ap.parse_args()
     B_PER_GPU = args.per_gpu_batch

@@ -193,6 +193,29 @@ int nr_maxsim2_fwd(const nr_maxsim2_problem* problems, int n_problems, int64_t N
  * exact-order keys (2^-20 relative resolution) instead of the fp32 bits of v + 2 (2e-6 absolute) */
 int nr_maxsim2_fwd_ex(const nr_maxsim2_problem* problems, int n_problems, int64_t Nx, int64_t Ny, int64_t d,
                       void* workspace, int flags, void* stream);
+/* ---- evaluation ranks straight from the accumulator: the similarity matrix is never written ----------------
+ * (reference: training/evaluator.py:21-63 builds the [Nq,Ng] matrix tile by tile on the host, utils/metrics.py:58-66
+ * sorts every row and locates the positive; at a 100k gallery that matrix is 37 GiB.)
+ * One block of nr_maxsim2_fwd's problem: X rows are the pairs gx0 .. gx0+Rx-1, Y rows the pairs gy0 .. gy0+Ry-1 of a
+ * square test set; the positive of a row is the row of the other side with the same pair id.  diag [>= max(gx0+Rx,
+ * gy0+Ry)] f32 holds the positives' scores by pair id.
+ *   mode 1: diag[g] = S[g-gx0, g-gy0] for every pair g inside both ranges; only the tiles that contain a positive
+ *           are contracted (with the tile geometry of mode 2: the values are the ones mode 2 recomputes).
+ *   mode 2: gt_x[rx] += #{ry : S[rx,ry] > diag[gx0+rx]},  eq_x[rx] += #{ry : S[rx,ry] == diag[gx0+rx]},
+ *           gt_y[ry] += #{rx : S[rx,ry] > diag[gy0+ry]},  eq_y[ry] += #{rx : S[rx,ry] == diag[gy0+ry]}
+ *           (int32, accumulate; the positive itself counts as equal) — the (g, e) pairs nr_rank_count produces.
+ * workspace / flags as nr_maxsim2_fwd_ex. */
+typedef struct {
+  const void* x_bf16; const void* y_bf16;
+  const float* wx; const float* wy;
+  int64_t Rx, Ry;
+  float alpha;
+  int64_t gx0, gy0;
+  float* diag;
+  int32_t* gt_x; int32_t* eq_x; int32_t* gt_y; int32_t* eq_y;
+} nr_maxsim2_rank_problem;
+int nr_maxsim2_rank(const nr_maxsim2_rank_problem* problem, int mode, int64_t Nx, int64_t Ny, int64_t d,
+                    void* workspace, int flags, void* stream);
 /* backward of nr_maxsim2_fwd w.r.t. the normalised tokens.  For one pair with g[rx,ry] = dH[rx*dh_sr + ry*dh_sc] *
  * dh_scale (dh_scale carries alpha) and the routing matrix
  *   C[(rx,x),(ry,y)] = g[rx,ry] * ( wx[rx,x] [y == ystar[rx,ry,x]] + wy[ry,y] [x == xstar[rx,ry,y]] ),

@@ -47,6 +47,7 @@ SIGNATURES = {
     "nr_maxsim2_supported": (_I, [_I64, _I64, _I64]),
     "nr_maxsim2_fwd": (_I, [_P, _I, _I64, _I64, _I64, _P, _P]),
     "nr_maxsim2_fwd_ex": (_I, [_P, _I, _I64, _I64, _I64, _P, _I, _P]),
+    "nr_maxsim2_rank": (_I, [_P, _I, _I64, _I64, _I64, _P, _I, _P]),
     "nr_maxsim2_bwd": (_I, [_P, _I, _I64, _I64, _I64, _P]),
     "nr_maxsim2_bwd_w": (_I, [_P, _P, _P, _I64, _I64, _F, _I64, _I64, _I64, _I64, _P, _P, _P]),
     "nr_maxsim2_bwd_w_multi": (_I, [_P, _I, _I64, _I64, _P]),
@@ -82,6 +83,12 @@ class MaxSim2Problem(ctypes.Structure):
     _fields_ = [("x_bf16", _P), ("y_bf16", _P), ("wx", _P), ("wy", _P), ("Rx", _I64), ("Ry", _I64), ("alpha", _F),
                 ("out", _P), ("out_sr", _I64), ("out_sc", _I64), ("out2", _P), ("out2_sr", _I64), ("out2_sc", _I64),
                 ("pmax_x", _P), ("ystar", _P), ("pmax_y", _P), ("xstar", _P)]
+
+
+class MaxSim2RankProblem(ctypes.Structure):
+    """nr_maxsim2_rank_problem of include/nrhead.h (field order and types must match)."""
+    _fields_ = [("x_bf16", _P), ("y_bf16", _P), ("wx", _P), ("wy", _P), ("Rx", _I64), ("Ry", _I64), ("alpha", _F),
+                ("gx0", _I64), ("gy0", _I64), ("diag", _P), ("gt_x", _P), ("eq_x", _P), ("gt_y", _P), ("eq_y", _P)]
 
 
 class MaxSim2BwdWJob(ctypes.Structure):

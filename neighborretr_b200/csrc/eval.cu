@@ -52,26 +52,37 @@ topk_rows_kernel(const float* __restrict__ S, int64_t lds, int N, int k, int32_t
   __shared__ unsigned long long red64[32];
   const int q = blockIdx.x, tid = threadIdx.x;
   const float* row = S + (int64_t)q * lds;
-  for (int j = tid; j < N; j += 256) rowsm[j] = row[j];
-  __syncthreads();
-  for (int r = 0; r < k; ++r) {
-    unsigned long long best = 0ull;
-    for (int j = tid; j < N; j += 256) {
-      float v = rowsm[j];
-      if (v != NR_NEG_INF) {
-        unsigned long long key = argmax_key(v, (uint32_t)j);
-        best = key > best ? key : best;
-      }
+  // every thread stages its columns (j = tid, tid + 256, ...) and keeps the best key among them in a register; a
+  // selection round is one block reduction of those keys, and only the owner of the winner rescans its columns
+  // (k full passes over the staged row made this kernel 0.10 of the HBM stream)
+  unsigned long long mine = 0ull;
+  for (int j = tid; j < N; j += 256) {
+    const float v = row[j];
+    rowsm[j] = v;
+    if (v != NR_NEG_INF) {
+      const unsigned long long key = argmax_key(v, (uint32_t)j);
+      mine = key > mine ? key : mine;
     }
-    best = block_max_u64(best, red64);
+  }
+  for (int r = 0; r < k; ++r) {
+    const unsigned long long best = block_max_u64(mine, red64);
     if (best == 0ull) {                 // fewer than k finite entries
       if (tid == 0) { vals[(int64_t)q * k + r] = NR_NEG_INF; idx[(int64_t)q * k + r] = -1; }
       continue;
     }
-    int j = (int)key_index(best);
+    const int j = (int)key_index(best);
     if (tid == 0) { vals[(int64_t)q * k + r] = argmax_key_value(best); idx[(int64_t)q * k + r] = j + col_offset; }
-    if ((j & 255) == tid) rowsm[j] = NR_NEG_INF;
-    __syncthreads();
+    if ((j & 255) == tid) {             // only the owner ever reads its columns again
+      rowsm[j] = NR_NEG_INF;
+      mine = 0ull;
+      for (int jj = tid; jj < N; jj += 256) {
+        const float v = rowsm[jj];
+        if (v != NR_NEG_INF) {
+          const unsigned long long key = argmax_key(v, (uint32_t)jj);
+          mine = key > mine ? key : mine;
+        }
+      }
+    }
   }
 }
 

@@ -48,7 +48,16 @@ struct Tc2Prob {
   float* out; int64_t out_sr, out_sc; float* out2; int64_t out2_sr, out2_sc;
   float* pmax_x; uint8_t* ystar; float* pmax_y; uint8_t* xstar;
   int n_mt, n_nt;
+  // evaluation modes (T2_MODE_DIAG / T2_MODE_COUNT): X row rx is pair gx0 + rx, Y row ry is pair gy0 + ry; the
+  // positive of a row is the row of the other side with the same pair id
+  float* diag;                             // [pairs]: DIAG writes S of the positives it covers, COUNT reads it
+  int* gt_x; int* eq_x; int* gt_y; int* eq_y;
+  int gx0, gy0, dj;                        // dj: Y tiles one X box can need for its positives (DIAG tile list)
 };
+
+constexpr int T2_MODE_SIM = 0;             // write S (and what backward needs)
+constexpr int T2_MODE_DIAG = 1;            // only the tiles that hold a positive pair: diag[pair] = S[positive]
+constexpr int T2_MODE_COUNT = 2;           // every tile: rank counts against diag straight from the accumulator
 
 struct alignas(64) Tc2Args {
   CUtensorMap tmx[T2_MAX_PROB];
@@ -56,6 +65,7 @@ struct alignas(64) Tc2Args {
   Tc2Prob p[T2_MAX_PROB];
   int nprob, n_tiles;
   int Nx, SX, MU, SY, UN, num_kb, stages, b_bytes, hp_ld, kg_ld;
+  int mode, cnt_w;                         // cnt_w: ints per count vector in shared memory (COUNT), else 0
   unsigned int* tile_counter;              // zeroed per launch: dynamic tile scheduler
   unsigned long long* trace;               // debug (NR_TC2_TRACE=1): 16 globaltimer stamps per CTA, else nullptr
 };
@@ -86,6 +96,19 @@ __device__ __forceinline__ uint32_t group_colmax(uint32_t* k, int lane) {
     }
   }
   return k[0];
+}
+
+// DIAG tile list: entry `local` of a problem = (X box mt, j-th Y tile that holds positives of that box).  Returns
+// false for entries with no such tile (the scheduler skips them).
+__device__ __forceinline__ bool diag_tile(const Tc2Prob& P, int SX, int SY, int local, int& mt, int& nt) {
+  mt = local / P.dj;
+  const int j = local - mt * P.dj;
+  const int off = P.gx0 - P.gy0;                         // positive of X row rx: Y row rx + off
+  const int x0 = mt * SX;
+  const int lo = max(x0 + off, 0);
+  const int hi = min(min(x0 + SX, P.Rx) - 1 + off, P.Ry - 1);
+  nt = lo / SY + j;
+  return hi >= lo && nt <= hi / SY;
 }
 
 __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t m, uint32_t c) {    // (a & m) | c
@@ -132,7 +155,8 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
   uint32_t* keyG = reinterpret_cast<uint32_t*>(hp + 2 * T2_BM * a.hp_ld);
   float* colw = reinterpret_cast<float*>(keyG + 2 * (T2_BM / GL) * a.kg_ld);
   float* wyst = colw + 2 * a.SX * a.UN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wyst + 2 * a.UN);
+  int* cnts = reinterpret_cast<int*>(wyst + 2 * a.UN);    // COUNT: per set {gt_x, eq_x, gt_y, eq_y} x cnt_w
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cnts + 2 * 4 * a.cnt_w);
   uint64_t* full = bars;                          // [stages]  TMA -> MMA
   uint64_t* empty = bars + T2_MAX_STAGES;         // [stages]  MMA -> TMA
   uint64_t* tfull = bars + 2 * T2_MAX_STAGES;     // [2]       MMA -> epilogue
@@ -177,13 +201,15 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
   };
 
   // tile index -> (problem, m-tile, n-tile); n fastest so that concurrently running CTAs share the X box in L2
-  auto decode = [&](int tile, int& p, int& mt, int& nt) {
+  auto decode = [&](int tile, int& p, int& mt, int& nt) -> bool {
     p = 0;
     while (p + 1 < a.nprob && tile >= a.p[p + 1].tile0) ++p;
     const int local = tile - a.p[p].tile0;
+    if (a.mode == T2_MODE_DIAG) return diag_tile(a.p[p], a.SX, a.SY, local, mt, nt);
     mt = local / a.p[p].n_nt;
     nt = local - mt * a.p[p].n_nt;
     if (CL2) mt = 2 * mt + (int)cr;                      // a pair-tile = two adjacent X boxes against one Y box
+    return true;
   };
 
   if (warp == 0) {
@@ -202,6 +228,10 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
           if (CL2) mbar_wait_cluster(rempty + slot, ((uint32_t)(n / T2_RING) & 1u) ^ 1u);
           else mbar_wait(rempty + slot, ((uint32_t)(n / T2_RING) & 1u) ^ 1u);
           tile = (int)atomicAdd(a.tile_counter, 1u);
+          if (a.mode == T2_MODE_DIAG) {                    // entries of the list without a positive are skipped HERE:
+            int p_, mt_, nt_;                              // the MMA issuer and the epilogues never see them
+            while (tile < a.n_tiles && !decode(tile, p_, mt_, nt_)) tile = (int)atomicAdd(a.tile_counter, 1u);
+          }
           if (tile >= a.n_tiles) tile = -1;
           if (n == 0) T2_TRACE(1);                        // first claim
           if (tile < 0) { T2_TRACE(2); if (a.trace) a.trace[(size_t)blockIdx.x * 16 + 3] = (unsigned long long)n; }
@@ -316,6 +346,9 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
     float* const wys = wyst + (size_t)set * a.UN;
     uint32_t* const kg_row = kgs + (r / GL) * a.kg_ld + (lane & (int)LOWM);
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * T2_ACC_COLS);
+    int* const cset = cnts + (size_t)set * 4 * a.cnt_w;
+    // COUNT: zeroed once; afterwards the thread that flushes an entry re-zeroes it (two set barriers before its next use)
+    for (int i = et; i < 4 * a.cnt_w; i += T2_SET) cset[i] = 0;
     for (int it = set;; it += 2) {
       const int tile = ring_take(it);
       if (tile < 0) break;
@@ -452,10 +485,37 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
         for (int y = 0; y < NY; y += 4) { h0 += cw[y]; h1 += cw[y + 1]; h2 += cw[y + 2]; h3 += cw[y + 3]; }
         const float h = ((h0 + h1) + (h2 + h3)) * P.alpha;
         const int rxx = mt * a.SX + s, ry = ry0 + sy;
-        P.out[(int64_t)rxx * P.out_sr + (int64_t)ry * P.out_sc] = h;
-        if (P.out2) P.out2[(int64_t)rxx * P.out2_sr + (int64_t)ry * P.out2_sc] = h;
+        if (a.mode == T2_MODE_SIM) {
+          P.out[(int64_t)rxx * P.out_sr + (int64_t)ry * P.out_sc] = h;
+          if (P.out2) P.out2[(int64_t)rxx * P.out2_sr + (int64_t)ry * P.out2_sc] = h;
+        } else {
+          // evaluation without S (reference utils/metrics.py:58-66 locates the positive in the sorted row: the same
+          // rank follows from #{> positive} and #{== positive})
+          const int gx = P.gx0 + rxx, gy = P.gy0 + ry;
+          if (a.mode == T2_MODE_DIAG) {
+            if (gx == gy) P.diag[gx] = h;
+          } else {
+            const float dx = P.diag[gx], dy = P.diag[gy];
+            const bool self = gx == gy;                     // the positive itself: equal by definition
+            if (self || h == dx) atomicAdd(cset + a.cnt_w + s, 1);
+            else if (h > dx) atomicAdd(cset + s, 1);
+            if (self || h == dy) atomicAdd(cset + 3 * a.cnt_w + sy, 1);
+            else if (h > dy) atomicAdd(cset + 2 * a.cnt_w + sy, 1);
+          }
+        }
       }
       set_barrier<T2_SET>(set);       // the set's staging buffers (hp, keyG, colw, wys) are free for its next tile
+      if (a.mode == T2_MODE_COUNT) {  // one global atomic per (row of the tile, non-zero count)
+        auto flush = [&](int* c, int* g) { const int v = *c; if (v) { atomicAdd(g, v); *c = 0; } };
+        if (et < sx_n) {
+          flush(cset + et, P.gt_x + mt * a.SX + et);
+          flush(cset + a.cnt_w + et, P.eq_x + mt * a.SX + et);
+        }
+        if (et < sy_n) {
+          flush(cset + 2 * a.cnt_w + et, P.gt_y + ry0 + et);
+          flush(cset + 3 * a.cnt_w + et, P.eq_y + ry0 + et);
+        }
+      }
       if (et == 0) T2_TRACE(9 + 2 * set);                  // end of this set's latest tile (overwritten per tile)
     }
   }
@@ -532,8 +592,12 @@ extern "C" int nr_maxsim2_supported(int64_t Nx, int64_t Ny, int64_t d) {
   return (ny_ok && Nx % 4 == 0 && Nx >= 4 && Nx <= 128 && d % T2_BK == 0 && d > 0) ? 1 : 0;
 }
 
+// evaluation modes: per-problem extension of nr_maxsim2_problem (nullptr = T2_MODE_SIM)
+struct RankExt { float* diag; int* gt_x; int* eq_x; int* gt_y; int* eq_y; int64_t gx0, gy0; };
+
 static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
-                           void* workspace, int flags, void* stream);
+                           void* workspace, int flags, void* stream, int mode = T2_MODE_SIM,
+                           const RankExt* ext = nullptr);
 
 extern "C" int nr_maxsim2_fwd(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
                               void* workspace, void* stream) {
@@ -546,8 +610,26 @@ extern "C" int nr_maxsim2_fwd_ex(const nr_maxsim2_problem* probs, int nprob, int
   return maxsim2_fwd_impl(probs, nprob, Nx, Ny, d, workspace, flags, stream);
 }
 
+/* Evaluation ranks without the similarity matrix (reference utils/metrics.py:38-79 on the matrix of
+ * training/evaluator.py:21-63).  mode 1: diag[pair] = S[positive pair] for the positives inside the block (only the
+ * tiles that hold one are computed); mode 2: the whole block is contracted and every S value is compared with the
+ * positives' scores in the epilogue — S is never written. */
+extern "C" int nr_maxsim2_rank(const nr_maxsim2_rank_problem* q, int mode, int64_t Nx, int64_t Ny, int64_t d,
+                               void* workspace, int flags, void* stream) {
+  NR_CHECK_ARG(q && (mode == T2_MODE_DIAG || mode == T2_MODE_COUNT), "nr_maxsim2_rank: mode 1 (diag) or 2 (count)");
+  NR_CHECK_ARG(q->diag && q->gx0 >= 0 && q->gy0 >= 0, "nr_maxsim2_rank: diag and non-negative pair offsets required");
+  NR_CHECK_ARG(mode == T2_MODE_DIAG || (q->gt_x && q->eq_x && q->gt_y && q->eq_y),
+               "nr_maxsim2_rank: count mode needs the four count vectors");
+  NR_CHECK_ARG(q->gx0 + q->Rx < (1ll << 31) && q->gy0 + q->Ry < (1ll << 31), "nr_maxsim2_rank: pair ids must fit int32");
+  nr_maxsim2_problem p{};
+  p.x_bf16 = q->x_bf16; p.y_bf16 = q->y_bf16; p.wx = q->wx; p.wy = q->wy;
+  p.Rx = q->Rx; p.Ry = q->Ry; p.alpha = q->alpha;
+  RankExt e{q->diag, q->gt_x, q->eq_x, q->gt_y, q->eq_y, q->gx0, q->gy0};
+  return maxsim2_fwd_impl(&p, 1, Nx, Ny, d, workspace, flags, stream, mode, &e);
+}
+
 static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t Nx, int64_t Ny, int64_t d,
-                           void* workspace, int flags, void* stream) {
+                           void* workspace, int flags, void* stream, int mode, const RankExt* ext) {
   NR_CHECK_ARG(workspace && ((uintptr_t)workspace & 3) == 0, "nr_maxsim2_fwd: workspace (>= 16 bytes, 4-byte aligned) required");
   NR_CHECK_ARG(probs && nprob >= 1 && nprob <= T2_MAX_PROB, "nr_maxsim2_fwd: 1..%d problems per launch (got %d)",
                T2_MAX_PROB, nprob);
@@ -559,7 +641,7 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
   int64_t max_rx = 0, max_ry = 0;
   for (int i = 0; i < nprob; ++i) {
     const nr_maxsim2_problem& q = probs[i];
-    NR_CHECK_ARG(q.x_bf16 && q.y_bf16 && q.wx && q.wy && q.out && q.Rx > 0 && q.Ry > 0,
+    NR_CHECK_ARG(q.x_bf16 && q.y_bf16 && q.wx && q.wy && (q.out || mode != T2_MODE_SIM) && q.Rx > 0 && q.Ry > 0,
                  "nr_maxsim2_fwd: problem %d has a null pointer or an empty side", i);
     NR_CHECK_ARG(((uintptr_t)q.x_bf16 & 15) == 0 && ((uintptr_t)q.y_bf16 & 15) == 0,
                  "nr_maxsim2_fwd: operands must be 16-byte aligned");
@@ -568,6 +650,7 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
   }
   Tc2Args a{};
   a.nprob = nprob;
+  a.mode = mode;
   a.Nx = (int)Nx;
   a.SX = T2_BM / (int)Nx;
   if (a.SX > max_rx) a.SX = (int)max_rx;
@@ -594,7 +677,9 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
   // BOTH CTAs (two cluster-scope barrier hops per tile), and the epilogue, not the operand stream, paces this kernel.
   const bool pair_ok = (a.SY * (int)Ny) % 16 == 0 && a.UN == a.SY * (int)Ny;
   bool pair = false;
-  if (const char* ev = getenv("NR_TC2_PAIR")) {
+  if (mode != T2_MODE_SIM) {
+    // the evaluation modes index tiles themselves (DIAG) and count per X box (COUNT): independent CTAs only
+  } else if (const char* ev = getenv("NR_TC2_PAIR")) {
     const int v = atoi(ev);
     pair = v >= 2 ? pair_ok : (v == 1 && pair_ok && est_tiles >= 2 * sms);
   }
@@ -610,6 +695,15 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
     P.n_mt = (int)((q.Rx + a.SX - 1) / a.SX);
     P.n_nt = (int)((q.Ry + a.SY - 1) / a.SY);
     P.tile0 = tiles;
+    P.dj = 1;
+    if (ext) {
+      const RankExt& e = ext[i];
+      P.diag = e.diag; P.gt_x = e.gt_x; P.eq_x = e.eq_x; P.gt_y = e.gt_y; P.eq_y = e.eq_y;
+      P.gx0 = (int)e.gx0; P.gy0 = (int)e.gy0;
+      P.dj = (a.SX + a.SY - 2) / a.SY + 1;                       // SX consecutive Y rows touch at most this many Y tiles
+    }
+    if (mode == T2_MODE_DIAG) tiles += P.n_mt * P.dj;            // (X box, j-th Y tile with positives); empty entries are skipped
+    else
     tiles += (pair ? (P.n_mt + 1) / 2 : P.n_mt) * P.n_nt;        // pair-tiles: two adjacent X boxes x one Y box
     if (int e = make_tmap_bf16(&a.tmx[i], q.x_bf16, q.Rx * Nx, d, a.MU)) return e;
     if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny / (pair ? 2 : 1))) return e;   // pair: half boxes
@@ -620,8 +714,9 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
   a.trace = nullptr;
   if (const char* tv = getenv("NR_TC2_TRACE"))
     if (atoi(tv) != 0) a.trace = (unsigned long long*)((uint8_t*)workspace + 16);
+  a.cnt_w = mode == T2_MODE_COUNT ? ((a.SX > a.SY ? a.SX : a.SY) + 1) / 2 * 2 : 0;
   const size_t tail = (size_t)2 * T2_BM * a.hp_ld * 4 + (size_t)2 * (T2_BM / GL) * a.kg_ld * 4 +
-                      (size_t)2 * a.SX * a.UN * 4 + (size_t)2 * a.UN * 4 + 512;
+                      (size_t)2 * a.SX * a.UN * 4 + (size_t)2 * a.UN * 4 + (size_t)2 * 4 * a.cnt_w * 4 + 512;
   const size_t budget = 227 * 1024 - 1024;   // alignment slack
   int stages = (int)((budget - tail) / (size_t)(T2_A_BYTES + a.b_bytes));
   if (stages > T2_MAX_STAGES) stages = T2_MAX_STAGES;

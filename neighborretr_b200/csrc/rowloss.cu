@@ -132,26 +132,36 @@ row_losses_fwd_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __restric
   // ---- neighbour-adjusting row (until_module.py:161-211)
   if (a.flags & NR_LOSS_NEIGHBOR) {
     const int k = a.k;
-    // top-k of the off-diagonal entries: k rounds of block arg-max, ties -> lower column
-    for (int r = 0; r < k; ++r) {
-      unsigned long long best = 0ull;
+    // top-k of the off-diagonal entries: k rounds of block arg-max, ties -> lower column.  Every thread keeps the
+    // best key of ITS columns in a register; a round is one block reduction of those, and only the thread that owned
+    // the winner rescans its B/256 columns (the whole row was rescanned by everybody every round before: 20 passes
+    // over the staged row made this kernel 0.05 of the HBM stream at B = 8192).
+    auto local_best = [&]() {
+      unsigned long long b = 0ull;
       for (int j = tid; j < B; j += ROW_THREADS) {
-        float v = xs[j];
+        const float v = xs[j];
         if (v != NR_NEG_INF) {
-          unsigned long long key = argmax_key(v, (uint32_t)j);
-          best = key > best ? key : best;
+          const unsigned long long key = argmax_key(v, (uint32_t)j);
+          b = key > b ? key : b;
         }
       }
-      best = block_max_u64(best, red64);
-      int jsel = (int)key_index(best);
+      return b;
+    };
+    unsigned long long mine = local_best();
+    for (int r = 0; r < k; ++r) {
+      const unsigned long long best = block_max_u64(mine, red64);
+      const int jsel = (int)key_index(best);
       if (tid == 0) {
         nb_j[r] = jsel;
         nb_x[r] = x[jsel];
         nbr_idx[(int64_t)i * k + r] = jsel;
       }
-      if ((jsel % ROW_THREADS) == tid) xs[jsel] = NR_NEG_INF;
-      __syncthreads();
+      if ((jsel % ROW_THREADS) == tid) {       // xs[jsel] is only ever re-read by its owner until the barrier below
+        xs[jsel] = NR_NEG_INF;
+        mine = local_best();
+      }
     }
+    __syncthreads();
     // min / max over the NON-extended entries of x and of the bank centrality c (until_module.py:77-85)
     unsigned long long klo = 0ull, khi = 0ull, clo = 0ull, chi = 0ull;
     for (int j = tid; j < B; j += ROW_THREADS) {

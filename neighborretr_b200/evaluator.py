@@ -15,20 +15,63 @@ from . import ops
 from .modeling import _token_weights
 
 
+def _eval_operands(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, mini_batch):
+    """(flattened masks, token weights of both modalities, head precision): the MLPs run once per modality."""
+    t_mask = t_mask_list.view(-1, t_mask_list.shape[-1])
+    v_mask = v_mask_list.view(-1, v_mask_list.shape[-1])
+    chunk = max(int(mini_batch), 1) * 64
+    prec = model._head_precision() if hasattr(model, "_head_precision") else "fp32"
+    lowp = model._mlp_precision() if hasattr(model, "_mlp_precision") else ("tf32" if prec == "bf16" else "fp32")
+    tw = torch.cat([_token_weights(model.text_weight_fc, f, m, lowp)
+                    for f, m in zip(torch.split(t_feat_list, chunk), torch.split(t_mask, chunk))])
+    vw = torch.cat([_token_weights(model.video_weight_fc, f, m, lowp)
+                    for f, m in zip(torch.split(v_feat_list, chunk), torch.split(v_mask, chunk))])
+    return t_mask, v_mask, tw, vw, prec
+
+
 def similarity_matrix(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, mini_batch=64):
     """CUDA tensor [Nq, Ng] of local_level similarities."""
     with torch.no_grad():
-        t_mask = t_mask_list.view(-1, t_mask_list.shape[-1])
-        v_mask = v_mask_list.view(-1, v_mask_list.shape[-1])
-        chunk = max(int(mini_batch), 1) * 64
-        prec = model._head_precision() if hasattr(model, "_head_precision") else "fp32"
-        lowp = model._mlp_precision() if hasattr(model, "_mlp_precision") else ("tf32" if prec == "bf16" else "fp32")
-        tw = torch.cat([_token_weights(model.text_weight_fc, f, m, lowp)
-                        for f, m in zip(torch.split(t_feat_list, chunk), torch.split(t_mask, chunk))])
-        vw = torch.cat([_token_weights(model.video_weight_fc, f, m, lowp)
-                        for f, m in zip(torch.split(v_feat_list, chunk), torch.split(v_mask, chunk))])
+        t_mask, v_mask, tw, vw, prec = _eval_operands(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list,
+                                                      mini_batch)
         s, _ = ops.maxsim(t_feat_list, v_feat_list, tw, vw, t_mask, v_mask, prec)
     return s
+
+
+def retrieval_counts_fused(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, mini_batch=64, video0=0,
+                           total=None, reduce_diag=None):
+    """Rank counts of both retrieval directions WITHOUT the similarity matrix (north_star: the B x B logits never
+    round-trip HBM; at a 100 000 gallery the fp32 matrix of reference training/evaluator.py:21-63 is 37 GiB): the
+    texts are all `total` queries, the videos the gallery shard starting at pair id `video0`.  Pass 1 contracts only
+    the tiles that hold a positive pair and writes its score; `reduce_diag` (sharded galleries: a SUM all-reduce)
+    completes that vector; pass 2 contracts the whole block and compares every accumulator value with the
+    positives' scores in the kernel epilogue.  Returns int32 CUDA vectors (gt_t, eq_t, gt_v, eq_v): per text over
+    this shard's videos, per video of the shard over all texts — the counts ops.rank_counts gives on the block and on
+    its transpose, from which metrics_from_counts reproduces compute_metrics (reference utils/metrics.py:38-79)."""
+    with torch.no_grad():
+        t_mask, v_mask, tw, vw, prec = _eval_operands(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list,
+                                                      mini_batch)
+        if prec == "fp32":
+            raise RuntimeError("retrieval_counts_fused: the fused ranks come from the tensor-core kernel; use "
+                               "head_precision 'bf16' or 'bf16x3' (or the materialised path for CUDA-core fp32)")
+        r = ops.FusedRanker(t_feat_list, v_feat_list, tw, vw, t_mask, v_mask, prec, text0=0, video0=video0)
+        n_pairs = int(total) if total is not None else max(t_feat_list.shape[0], video0 + v_feat_list.shape[0])
+        diag = r.diagonal(n_pairs)
+        if reduce_diag is not None:
+            reduce_diag(diag)
+        return r.counts(diag)
+
+
+def retrieval_metrics_fused(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, mini_batch=64):
+    """(text->video, video->text) metric dicts of a square test set on one GPU, no similarity matrix: what
+    compute_metrics(sim_matrix), compute_metrics(sim_matrix.T) return after _run_on_single_gpu (reference
+    training/evaluator.py:253-266)."""
+    from .metrics import metrics_from_counts
+    if t_feat_list.shape[0] != v_feat_list.shape[0]:
+        raise ValueError("retrieval_metrics_fused: compute_metrics needs a square query x gallery problem")
+    cnt = retrieval_counts_fused(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, mini_batch)
+    c = torch.stack(cnt).cpu().numpy()                  # one device->host copy
+    return metrics_from_counts(c[0], c[1]), metrics_from_counts(c[2], c[3])
 
 
 def _run_on_single_gpu(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, mini_batch=64):
@@ -37,12 +80,14 @@ def _run_on_single_gpu(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list
     return sim_matrix, sim_matrix.T
 
 
-def sharded_retrieval(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, topk=10):
+def sharded_retrieval(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list, topk=10, fused=False):
     """Column-sharded evaluation over the default process group: every rank has all features
     (as after the reference's gather, training/evaluator.py:173-189), computes only S[:, cols_r] for its shard of
     the video gallery and never materialises the full matrix.  Exact global ranks come from per-shard counts
     (all_reduce of int32 vectors) against the positive's score; top-k lists are merged across shards
-    (ties -> lower global index).  Returns (t2v metrics, v2t metrics, (topk values, topk video ids) [Q,k])."""
+    (ties -> lower global index).  Returns (t2v metrics, v2t metrics, (topk values, topk video ids) [Q,k]).
+    fused=True: the counts come straight from the contraction's epilogue (retrieval_counts_fused) — not even the
+    shard's [Q, N/W] block exists; the top-k lists are then not produced (third value None)."""
     import torch.distributed as dist
     from .metrics import metrics_from_counts
     W, r = dist.get_world_size(), dist.get_rank()
@@ -51,6 +96,22 @@ def sharded_retrieval(model, t_mask_list, v_mask_list, t_feat_list, v_feat_list,
         raise ValueError("sharded_retrieval: compute_metrics needs a square query x gallery problem")
     n = (N + W - 1) // W
     c0, c1 = min(r * n, N), min((r + 1) * n, N)
+    if fused:
+        dev = t_feat_list.device
+        cnt = torch.zeros(2, Q, dtype=torch.int32, device=dev)
+        cnt_v = torch.zeros(2, W * n, dtype=torch.int32, device=dev)
+        if c1 > c0:
+            gt_t, eq_t, gt_v, eq_v = retrieval_counts_fused(
+                model, t_mask_list, v_mask_list[c0:c1], t_feat_list, v_feat_list[c0:c1], video0=c0, total=Q,
+                reduce_diag=lambda d: dist.all_reduce(d, op=dist.ReduceOp.SUM))
+            cnt[0], cnt[1] = gt_t, eq_t
+            cnt_v[0, c0:c1], cnt_v[1, c0:c1] = gt_v, eq_v
+        else:                                   # an empty shard still takes part in the collectives
+            dist.all_reduce(torch.zeros(Q, dtype=torch.float32, device=dev), op=dist.ReduceOp.SUM)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(cnt_v, op=dist.ReduceOp.SUM)
+        c = cnt.cpu().numpy(); cv = cnt_v[:, :N].cpu().numpy()
+        return metrics_from_counts(c[0], c[1]), metrics_from_counts(cv[0], cv[1]), None
     s = similarity_matrix(model, t_mask_list, v_mask_list[c0:c1], t_feat_list, v_feat_list[c0:c1])   # [Q, c1-c0]
     dev = s.device
     # positives' scores: owned by the rank whose shard holds column q

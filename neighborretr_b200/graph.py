@@ -33,6 +33,20 @@ def head_params(model):
     return list(model.text_weight_fc.parameters()) + list(model.video_weight_fc.parameters()) + [model.clip.logit_scale]
 
 
+def _slab_like(tensors, dev):
+    """One uint8 device buffer holding a tensor of every given shape / dtype at 256-byte aligned offsets; returns
+    (slab, {field: view})."""
+    offs, total = [], 0
+    for t in tensors:
+        offs.append(total)
+        total += (t.numel() * t.element_size() + 255) // 256 * 256
+    slab = torch.empty(total, dtype=torch.uint8, device=dev)
+    views = {}
+    for f, t, o in zip(FIELDS, tensors, offs):
+        views[f] = slab[o:o + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+    return slab, views
+
+
 class GraphedHeadStep:
     def __init__(self, model, example, warmup=3, explicit_grads=False):
         """explicit_grads: capture torch.autograd.grad(...) instead of .backward(): the gradients of the four
@@ -44,12 +58,12 @@ class GraphedHeadStep:
         self.model = model
         self.explicit = bool(explicit_grads)
         dev = example[0].device if example[0].is_cuda else next(model.parameters()).device
-        self.static = {}
+        # the static inputs are views of ONE byte slab: a staged batch moves in with a single device-to-device copy
+        self._static_slab, self.static = _slab_like(example, dev)
         for f, t in zip(FIELDS, example):
-            s = t.detach().to(dev).clone()
+            self.static[f].copy_(t.detach())
             if f in GRAD_FIELDS:
-                s.requires_grad_(True)
-            self.static[f] = s
+                self.static[f].requires_grad_(True)
         self.bank_names = ("mb_ind", "mb_feat_t", "mb_feat_v", "mb_mask_t", "mb_mask_v")
         bank0 = {n: getattr(model, n).detach().to(dev).clone() for n in self.bank_names}     # reference order
         self.ring = self._make_ring(model, bank0, self.static["text_feat"].shape[0])
@@ -211,7 +225,7 @@ class GraphedHeadStep:
         the previous staging content has been consumed; use __call__(..., prefetch_next=batch) inside a loop."""
         dev = self.static[FIELDS[0]].device
         if self._stage is None:
-            self._stage = {f: torch.empty_like(self.static[f].data) for f in FIELDS}
+            self._stage_slab, self._stage = _slab_like([self.static[f] for f in FIELDS], dev)
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._staged = torch.cuda.Event()
             self._stage_free = torch.cuda.Event()
@@ -231,16 +245,15 @@ class GraphedHeadStep:
         if prefetched:
             cur = torch.cuda.current_stream()
             cur.wait_event(self._staged)
-            for f in FIELDS:
-                self.static[f].data.copy_(self._stage[f], non_blocking=True)
+            self._static_slab.copy_(self._stage_slab, non_blocking=True)      # all seven inputs: one copy
             self._stage_free.record(cur)
-            if prefetch_next is not None:
-                self.prefetch(*prefetch_next)
         else:
             for f, t in zip(FIELDS, batch):
                 self.static[f].data.copy_(t, non_blocking=True)
         self.graph.replay()
         ops.LAUNCHES["count"] += self.launches_per_replay
+        if prefetched and prefetch_next is not None:      # issued AFTER the replay: the host enqueues the next batch's
+            self.prefetch(*prefetch_next)                 # copies while the device already runs this step
         if self.ring is not None:
             self.ring.note_replay(self._fifo_rows)
         if sync_losses_to is not None:

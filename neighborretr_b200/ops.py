@@ -1042,6 +1042,62 @@ def rank_counts(S, diag=None, diag_col0=0, gt=None, eq=None):
     return gt, eq
 
 
+class FusedRanker:
+    """Evaluation ranks straight from the tensor-core accumulator (nr_maxsim2_rank): the [Q, N] similarity block is
+    never written.  Texts are the pairs text0 .. text0+Q-1, videos the pairs video0 .. video0+N-1 of a square test
+    set; `diagonal(total)` returns the positives' scores this block holds (zeros elsewhere: shards add theirs with
+    an all-reduce), `counts(diag)` the (#greater, #equal) vectors of both retrieval directions — what
+    rank_counts gives on the materialised block and on its transpose (reference utils/metrics.py:58-66)."""
+
+    def __init__(self, text_feat, video_feat, tw, vw, text_mask, video_mask, precision="bf16", text0=0, video0=0):
+        _req_cuda(text_feat, video_feat, tw, vw, text_mask, video_mask)
+        prec = PRECISIONS[precision]
+        if prec not in TC_PRECISIONS:
+            raise RuntimeError("FusedRanker: the ranks come from the tensor-core kernel (precision 'bf16' or 'bf16x3')")
+        x3 = prec == NR_PREC_BF16X3
+        swap = _fused_orientation(text_feat.shape[1], video_feat.shape[1], text_feat.shape[2] * (3 if x3 else 1))
+        if swap is None:
+            raise RuntimeError("FusedRanker: token counts without a fused tensor-core instantiation")
+        self.swap, self.flags = swap, 1 if x3 else 0
+        self.tw, self.vw = _f32c(tw), _f32c(vw)
+        T = Prepared(text_feat, bf16=True, f32=False, mask=_mask(text_mask),
+                     split=(ROLE_Y if swap else ROLE_X) if x3 else 0)
+        V = Prepared(video_feat, bf16=True, f32=False, mask=_mask(video_mask),
+                     split=(ROLE_X if swap else ROLE_Y) if x3 else 0)
+        self.T, self.V, self.text0, self.video0 = T, V, int(text0), int(video0)
+
+    def _launch(self, mode, diag, cnt):
+        T, V = self.T, self.V
+        q = _lib.MaxSim2RankProblem()
+        X, Y, wx, wy, gx0, gy0 = ((V, T, self.vw, self.tw, self.video0, self.text0) if self.swap else
+                                  (T, V, self.tw, self.vw, self.text0, self.video0))
+        if diag.dtype != torch.float32 or not diag.is_contiguous() or diag.numel() < max(gx0 + X.r, gy0 + Y.r):
+            raise RuntimeError("FusedRanker: diag must be a contiguous fp32 vector covering every pair id of the block")
+        q.x_bf16, q.y_bf16, q.wx, q.wy = X.xn_bf16.data_ptr(), Y.xn_bf16.data_ptr(), wx.data_ptr(), wy.data_ptr()
+        q.Rx, q.Ry, q.alpha, q.gx0, q.gy0, q.diag = X.r, Y.r, 0.5, gx0, gy0, diag.data_ptr()
+        if cnt is not None:
+            t, v = (cnt[0], cnt[1]), (cnt[2], cnt[3])
+            cx, cy = (v, t) if self.swap else (t, v)
+            q.gt_x, q.eq_x, q.gt_y, q.eq_y = cx[0].data_ptr(), cx[1].data_ptr(), cy[0].data_ptr(), cy[1].data_ptr()
+        ws = _tile_workspace(X.device)
+        _call("nr_maxsim2_rank", ctypes.byref(q), mode, X.n, Y.n, X.kd, _p(ws), self.flags, _stream())
+
+    def diagonal(self, total):
+        """fp32 [total]: S[positive] at the pair ids whose text AND video are in this block, 0 elsewhere."""
+        diag = torch.zeros(int(total), dtype=torch.float32, device=self.T.device)
+        self._launch(1, diag, None)
+        return diag
+
+    def counts(self, diag):
+        """int32 (gt_t [Q], eq_t [Q], gt_v [N], eq_v [N]): per text row over this block's videos, per video over this
+        block's texts."""
+        dev = self.T.device
+        cnt = (torch.zeros(self.T.r, dtype=torch.int32, device=dev), torch.zeros(self.T.r, dtype=torch.int32, device=dev),
+               torch.zeros(self.V.r, dtype=torch.int32, device=dev), torch.zeros(self.V.r, dtype=torch.int32, device=dev))
+        self._launch(2, diag, cnt)
+        return cnt
+
+
 def topk_rows(S, k, col_offset=0):
     _req_cuda(S)
     S = _f32c(S)

@@ -81,6 +81,9 @@ def main():
     s_t2v, s_v2t, (tv, ti) = sharded_retrieval(full, ev.text_mask, ev.video_mask, ev.text_feat, ev.video_feat, topk=10)
     ref_i = torch.sort(S, dim=1, descending=True, stable=True)[1][:, :10]
     ok_eval = s_t2v == m_t2v and s_v2t == m_v2t and torch.equal(ti.long(), ref_i)
+    if a.precision != "fp32":      # ranks from the contraction's epilogue: not even the shard's block of S exists
+        f_t2v, f_v2t, none = sharded_retrieval(full, ev.text_mask, ev.video_mask, ev.text_feat, ev.video_feat, fused=True)
+        ok_eval = ok_eval and f_t2v == m_t2v and f_v2t == m_v2t and none is None
     errs["eval"] = 0.0 if ok_eval else 1.0
     ok = ok and ok_eval
     print(f"rank {rank}/{world} {'OK' if ok else 'FAIL'} {errs}", flush=True)
