@@ -102,14 +102,22 @@ class BankRing:
         self._export = None
 
     # ---- one step: the newest rows replace the oldest ------------------------------------------------------------
-    def insert(self, ind, feat_t, feat_v, mask_t, mask_v):
+    def insert(self, ind, feat_t, feat_v, mask_t, mask_v, phase="all"):
         """cat(new, bank)[:M] of the reference (modeling.py:235-249), in place.  Must be enqueued after every reader of
-        the step (forward AND backward contractions, the MLP GEMMs)."""
+        the step (forward AND backward contractions, the MLP GEMMs).
+        phase: "all", or the two halves of a split insert — "early": ring position, indices, raw rows, masks and the
+        contraction operands (their last reader is the backward contraction); "late": the MLP GEMM's bf16 operand
+        (its last reader is the backward GEMM).  A split insert is "early" then "late", exactly once each."""
+        if phase not in ("all", "early", "late"):
+            raise ValueError(f"BankRing.insert: unknown phase {phase!r}")
         B = feat_t.shape[0]
         n_new = min(B, self.M)
         st = _stream()
-        ind = ind.reshape(-1).to(torch.int64).contiguous()
-        _call("nr_bank_advance", _p(self.head_dev), n_new, self.M, _p(ind), _p(self.ind), st)
+        if phase != "late":
+            ind = ind.reshape(-1).to(torch.int64).contiguous()
+            _call("nr_bank_advance", _p(self.head_dev), n_new, self.M, _p(ind), _p(self.ind), st)
+        elif self.mlp_t is None:
+            return
         arr = (_lib.BankSide * 2)()
         keep = []
         for i, (new, mask, feat, rmask, xn, xnT, ld, n, role, mlp) in enumerate((
@@ -120,10 +128,15 @@ class BankRing:
             keep += [newc, maskc]
             a = arr[i]
             a.new_feat, a.new_mask, a.N = newc.data_ptr(), maskc.data_ptr(), n
-            a.ring_feat, a.ring_mask = feat.data_ptr(), rmask.data_ptr()
-            a.ring_raw_bf16 = raw.data_ptr() if raw is not None else None
-            a.ring_xn_bf16, a.split_role, a.ring_xnT_bf16, a.ld = xn.data_ptr(), role, xnT.data_ptr(), ld
+            a.split_role, a.ld = role, ld
+            if phase != "late":
+                a.ring_feat, a.ring_mask = feat.data_ptr(), rmask.data_ptr()
+                a.ring_xn_bf16, a.ring_xnT_bf16 = xn.data_ptr(), xnT.data_ptr()
+            if phase != "early":
+                a.ring_raw_bf16 = raw.data_ptr() if raw is not None else None
         _call("nr_bank_insert_pair", ctypes.cast(arr, ctypes.c_void_p), 2, n_new, self.d, self.M, _p(self.head_dev), st)
+        if phase == "late":
+            return                                # the ring position moved with the early half
         self.head = (self.head - n_new) % self.M
         self.version += 1
         self._export = None

@@ -114,4 +114,48 @@ __device__ __forceinline__ float argmin_key_value(unsigned long long k) {
   return ord_float(~(uint32_t)(k >> 32));
 }
 
+// Arg-max over (ord, index) candidates — ord = float_ord(value), or ~float_ord(value) for an arg-min; (0, NR_NO_INDEX) =
+// no candidate.  Largest ord wins, ties towards the LOWEST index: the order of argmax_key / argmin_key, but a warp
+// reduces it with two redux.sync instructions instead of a 5-stage shuffle tree over 64-bit keys.
+constexpr uint32_t NR_NO_INDEX = 0xffffffffu;
+__device__ __forceinline__ void warp_argmax_ord(uint32_t& o, uint32_t& j) {
+  const uint32_t m = __reduce_max_sync(0xffffffffu, o);
+  j = __reduce_min_sync(0xffffffffu, o == m ? j : NR_NO_INDEX);
+  o = m;
+}
+// block-wide; every thread gets the result.  `scratch` holds >= 32 uint2; safe back-to-back (leading barrier).
+__device__ __forceinline__ void block_argmax_ord(uint32_t& o, uint32_t& j, uint2* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  warp_argmax_ord(o, j);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = make_uint2(o, j);
+  __syncthreads();
+  const uint2 e = lane < nw ? scratch[lane] : make_uint2(0u, NR_NO_INDEX);
+  o = e.x; j = e.y;
+  warp_argmax_ord(o, j);
+}
+
+// Stage one row of n floats from global into shared memory with T threads: 16-byte loads, four per thread in flight
+// before the first store (a scalar load-store loop keeps 2 x 128 B per warp in flight: with one or two CTAs per SM
+// that is ~0.3 TB/s over the whole chip, measured on the B = 8192 row-loss kernels).  Falls back to scalar accesses
+// when the source row or the destination is not 16-byte aligned.
+template <int T>
+__device__ __forceinline__ void stage_row(const float* __restrict__ src, float* dst, int n, int tid) {
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)__cvta_generic_to_shared(dst)) & 15) == 0;
+  int done = 0;
+  if (vec) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const int n4 = n >> 2;
+    int j = tid;
+    for (; j + 3 * T < n4; j += 4 * T) {
+      const float4 a = __ldg(s4 + j), b = __ldg(s4 + j + T), c = __ldg(s4 + j + 2 * T), d = __ldg(s4 + j + 3 * T);
+      d4[j] = a; d4[j + T] = b; d4[j + 2 * T] = c; d4[j + 3 * T] = d;
+    }
+    for (; j < n4; j += T) d4[j] = __ldg(s4 + j);
+    done = n4 << 2;
+  }
+  for (int j = done + tid; j < n; j += T) dst[j] = src[j];
+}
+
 }  // namespace nr

@@ -48,7 +48,7 @@ rank_count_kernel(const float* __restrict__ S, int64_t lds, int N, const float* 
 __global__ void __launch_bounds__(256)
 topk_rows_kernel(const float* __restrict__ S, int64_t lds, int N, int k, int32_t col_offset,
                  float* __restrict__ vals, int32_t* __restrict__ idx) {
-  extern __shared__ float rowsm[];
+  extern __shared__ __align__(16) float rowsm[];
   __shared__ unsigned long long red64[32];
   const int q = blockIdx.x, tid = threadIdx.x;
   const float* row = S + (int64_t)q * lds;
@@ -56,9 +56,10 @@ topk_rows_kernel(const float* __restrict__ S, int64_t lds, int N, int k, int32_t
   // selection round is one block reduction of those keys, and only the owner of the winner rescans its columns
   // (k full passes over the staged row made this kernel 0.10 of the HBM stream)
   unsigned long long mine = 0ull;
+  stage_row<256>(row, rowsm, N, tid);
+  __syncthreads();
   for (int j = tid; j < N; j += 256) {
-    const float v = row[j];
-    rowsm[j] = v;
+    const float v = rowsm[j];
     if (v != NR_NEG_INF) {
       const unsigned long long key = argmax_key(v, (uint32_t)j);
       mine = key > mine ? key : mine;

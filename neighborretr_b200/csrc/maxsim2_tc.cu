@@ -53,6 +53,7 @@ struct Tc2Prob {
   float* diag;                             // [pairs]: DIAG writes S of the positives it covers, COUNT reads it
   int* gt_x; int* eq_x; int* gt_y; int* eq_y;
   int gx0, gy0, dj;                        // dj: Y tiles one X box can need for its positives (DIAG tile list)
+  int wn, n_me;                            // tile order: bands of wn Y tiles, inside a band X boxes (n_me of them) outermost
 };
 
 constexpr int T2_MODE_SIM = 0;             // write S (and what backward needs)
@@ -206,8 +207,16 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
     while (p + 1 < a.nprob && tile >= a.p[p + 1].tile0) ++p;
     const int local = tile - a.p[p].tile0;
     if (a.mode == T2_MODE_DIAG) return diag_tile(a.p[p], a.SX, a.SY, local, mt, nt);
-    mt = local / a.p[p].n_nt;
-    nt = local - mt * a.p[p].n_nt;
+    // Bands of wn Y tiles; inside a band the Y tile runs fastest, so the CTAs of a wave share a few X boxes and the
+    // band's Y boxes stay in L2 while every X box passes by once.  (One band = the plain row-major order, which at
+    // 8192 x 8192 re-read the Y operand from HBM for every X box: ncu 125 GB of DRAM reads for 0.3 GB of operands.)
+    const Tc2Prob& Q = a.p[p];
+    const int band_tiles = Q.n_me * Q.wn;
+    const int bnd = local / band_tiles;
+    const int rem = local - bnd * band_tiles;
+    const int w = min(Q.wn, Q.n_nt - bnd * Q.wn);
+    mt = rem / w;
+    nt = bnd * Q.wn + rem - mt * w;
     if (CL2) mt = 2 * mt + (int)cr;                      // a pair-tile = two adjacent X boxes against one Y box
     return true;
   };
@@ -702,9 +711,15 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
       P.gx0 = (int)e.gx0; P.gy0 = (int)e.gy0;
       P.dj = (a.SX + a.SY - 2) / a.SY + 1;                       // SX consecutive Y rows touch at most this many Y tiles
     }
+    P.n_me = pair ? (P.n_mt + 1) / 2 : P.n_mt;                   // pair-tiles: two adjacent X boxes x one Y box
+    // Y tiles per band: the band's Y boxes (16 MB) must survive in L2 — which holds a line once per die — while the
+    // X operand streams past; problems with fewer Y tiles are a single band
+    const int64_t box_bytes = (int64_t)a.SY * Ny * d * 2;
+    int64_t wn = (16ll << 20) / (box_bytes > 0 ? box_bytes : 1);
+    if (const char* wv = getenv("NR_TC2_BAND")) { if (atoi(wv) > 0) wn = atoi(wv); }
+    P.wn = (int)(wn < 1 ? 1 : (wn > P.n_nt ? P.n_nt : wn));
     if (mode == T2_MODE_DIAG) tiles += P.n_mt * P.dj;            // (X box, j-th Y tile with positives); empty entries are skipped
-    else
-    tiles += (pair ? (P.n_mt + 1) / 2 : P.n_mt) * P.n_nt;        // pair-tiles: two adjacent X boxes x one Y box
+    else tiles += P.n_me * P.n_nt;
     if (int e = make_tmap_bf16(&a.tmx[i], q.x_bf16, q.Rx * Nx, d, a.MU)) return e;
     if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny / (pair ? 2 : 1))) return e;   // pair: half boxes
   }

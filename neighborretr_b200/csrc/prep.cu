@@ -782,6 +782,26 @@ __global__ void __launch_bounds__(256) bank_insert_kernel(const BankInsertArgs a
   }
 }
 
+// The late half of a split insert: raw fp32 rows -> bf16 at the ring slots (head + j) mod M.  One thread = four
+// consecutive elements; 12 bytes of traffic per element, nothing else.
+__global__ void __launch_bounds__(256) bank_insert_raw_kernel(const BankInsertArgs a) {
+  const int d4 = a.d >> 2, M = a.M;
+  const int head = *a.head;
+  for (int si = 0; si < a.nsides; ++si) {
+    const BankSide& S = a.s[si];
+    const int64_t units = (int64_t)S.rows * d4;
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (int64_t)gridDim.x * blockDim.x) {
+      const int row = (int)(u / d4), c = (int)(u - (int64_t)row * d4) * 4;
+      const int j = row / S.N, n = row - j * S.N;
+      const int64_t drow = (int64_t)((head + j) % M) * S.N + n;
+      const float4 v = *reinterpret_cast<const float4*>(S.x + (int64_t)row * a.d + c);
+      __nv_bfloat16 r4[4] = {__float2bfloat16_rn(v.x), __float2bfloat16_rn(v.y), __float2bfloat16_rn(v.z),
+                             __float2bfloat16_rn(v.w)};
+      *reinterpret_cast<uint2*>(S.ring_raw + drow * a.d + c) = *reinterpret_cast<uint2*>(r4);
+    }
+  }
+}
+
 }  // namespace nr
 
 extern "C" int nr_bank_advance(int* head, int64_t n_new, int64_t M, const int64_t* new_ind, int64_t* ring_ind,
@@ -805,9 +825,26 @@ static int bank_side_fill(nr::BankSide& S, const float* new_feat, const int64_t*
   return 0;
 }
 
+static int bank_insert_launch(nr::BankInsertArgs& a, int blocks, cudaStream_t stream);
+
+// only the raw bf16 rows (the weight-MLP operand) are requested: a plain cast into the ring slots, no normalisation
+static bool bank_raw_only(const nr::BankInsertArgs& a) {
+  for (int i = 0; i < a.nsides; ++i)
+    if (!a.s[i].ring_raw || a.s[i].ring_feat || a.s[i].ring_mask || a.s[i].ring_xn || a.s[i].ring_xnT) return false;
+  return true;
+}
+
 static int bank_insert_launch(nr::BankInsertArgs& a, int blocks, cudaStream_t stream) {
   NR_CHECK_ARG(a.d > 0 && a.d % 4 == 0 && a.d <= 128 * nr::PREP_MAXQ, "nr_bank_insert: d=%d must be a multiple of 4, <= %d", a.d,
                128 * nr::PREP_MAXQ);
+  if (bank_raw_only(a)) {
+    int64_t units = 0;
+    for (int i = 0; i < a.nsides; ++i) units += (int64_t)a.s[i].rows * (a.d / 4);
+    const int grid = (int)((units + 255) / 256 < 148 * 8 ? (units + 255) / 256 : 148 * 8);
+    nr::bank_insert_raw_kernel<<<grid, 256, 0, stream>>>(a);
+    NR_CHECK_LAUNCH("nr_bank_insert(raw)");
+    return 0;
+  }
   const size_t smem = (size_t)2 * nr::BI_ROWS * (a.d + 2) * sizeof(__nv_bfloat16);
   static bool attr_set = false;
   if (!attr_set) {

@@ -9,12 +9,20 @@
 //   UniformRegularizationLoss NeighborRetr/models/until_module.py:263-291 (CE part; Sinkhorn in sinkhorn.cu)
 //   KLDivergenceLoss          NeighborRetr/models/until_module.py:339-359
 // Roofline: HBM/L2-bound, 4*B bytes per row and matrix read once.
+#include <stdlib.h>
 #include "common.cuh"
 #include "nrhead_internal.h"
 
 namespace nr {
 
-constexpr int ROW_THREADS = 256;
+// threads of a CTA-per-row kernel.  NR_ROW_THREADS=1024 selects the 1024-thread instantiation for rows beyond 2048
+// columns (measured on B200 at B = 8192: 2052 vs 1637 us forward, 674 vs 595 us backward — slower, so 256 stays)
+constexpr int ROW_THREADS_SMALL = 256;
+constexpr int ROW_THREADS_BIG = 1024;
+static bool row_big(int64_t B) {
+  const char* e = getenv("NR_ROW_THREADS");
+  return B > 2048 && e && atoi(e) == 1024;
+}
 
 struct RowArgs {
   const float* X; int64_t ldx;     // [rows, B] local similarity rows
@@ -33,12 +41,13 @@ __device__ __forceinline__ float load_ls(const float* p) { return p ? __ldg(p) :
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+template <int ROW_THREADS>
 __global__ void __launch_bounds__(ROW_THREADS)
 row_losses_fwd_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __restrict__ nbr_idx,
                       float* __restrict__ saved) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   __shared__ float red[32];
-  __shared__ unsigned long long red64[32];
+  __shared__ uint2 redk[32];
   __shared__ float nb_x[NR_MAX_K], nb_a[NR_MAX_K];
   __shared__ int nb_j[NR_MAX_K];
   const int B = a.B, tid = threadIdx.x, i = blockIdx.x, gi = a.row0 + i;
@@ -48,13 +57,13 @@ row_losses_fwd_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __restric
   const bool need_g = (a.flags & (NR_LOSS_KL | NR_LOSS_UNIFORM)) != 0;
   const float* Xr = a.X + (int64_t)i * a.ldx;
   const float* Gr = need_g ? a.G + (int64_t)i * a.ldg : nullptr;
-  for (int j = tid; j < B; j += ROW_THREADS) {
-    float v = Xr[j];
-    x[j] = v;
-    xs[j] = (j == gi) ? NR_NEG_INF : v;
-    if (need_g) g[j] = Gr[j];
-  }
+  stage_row<ROW_THREADS>(Xr, x, B, tid);
+  if (need_g) stage_row<ROW_THREADS>(Gr, g, B, tid);
   __syncthreads();
+  if (a.flags & NR_LOSS_NEIGHBOR) {          // selection copy: the row without its diagonal
+    for (int j = tid; j < B; j += ROW_THREADS) xs[j] = (j == gi) ? NR_NEG_INF : x[j];
+    __syncthreads();
+  }
   float* sv = saved + (int64_t)i * NR_NSAVE;
   float* ro = row_out;
   const int rows = a.rows;
@@ -132,54 +141,62 @@ row_losses_fwd_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __restric
   // ---- neighbour-adjusting row (until_module.py:161-211)
   if (a.flags & NR_LOSS_NEIGHBOR) {
     const int k = a.k;
-    // top-k of the off-diagonal entries: k rounds of block arg-max, ties -> lower column.  Every thread keeps the
-    // best key of ITS columns in a register; a round is one block reduction of those, and only the thread that owned
-    // the winner rescans its B/256 columns (the whole row was rescanned by everybody every round before: 20 passes
-    // over the staged row made this kernel 0.05 of the HBM stream at B = 8192).
-    auto local_best = [&]() {
-      unsigned long long b = 0ull;
-      for (int j = tid; j < B; j += ROW_THREADS) {
+    // top-k of the off-diagonal entries: k rounds of block arg-max, ties -> lower column.  Every thread keeps the best
+    // (ord, column) of ITS columns in registers; a round is one block arg-max of those (redux.sync, two barriers),
+    // and only the warp of the thread that owned the winner rescans that thread's B/256 columns, one per lane.
+    // (Before: every thread rescanned the whole staged row with 64-bit keys in every round; ncu at B = 8192: 71 k
+    // instructions per row, 41 % of the stall samples at the barrier behind a single rescanning thread.)
+    const int lane = tid & 31, warp = tid >> 5;
+    auto scan_cols = [&](int j0, int step, uint32_t& bo, uint32_t& bj) {
+      bo = 0u; bj = NR_NO_INDEX;
+      for (int j = j0; j < B; j += step) {                  // ascending columns + strict compare: ties -> lower column
         const float v = xs[j];
         if (v != NR_NEG_INF) {
-          const unsigned long long key = argmax_key(v, (uint32_t)j);
-          b = key > b ? key : b;
+          const uint32_t o = float_ord(v);
+          if (o > bo) { bo = o; bj = (uint32_t)j; }
         }
       }
-      return b;
     };
-    unsigned long long mine = local_best();
+    uint32_t bo, bj;
+    scan_cols(tid, ROW_THREADS, bo, bj);
     for (int r = 0; r < k; ++r) {
-      const unsigned long long best = block_max_u64(mine, red64);
-      const int jsel = (int)key_index(best);
+      uint32_t mo = bo, mj = bj;
+      block_argmax_ord(mo, mj, redk);
+      const int jsel = (int)mj;
       if (tid == 0) {
         nb_j[r] = jsel;
         nb_x[r] = x[jsel];
         nbr_idx[(int64_t)i * k + r] = jsel;
       }
-      if ((jsel % ROW_THREADS) == tid) {       // xs[jsel] is only ever re-read by its owner until the barrier below
-        xs[jsel] = NR_NEG_INF;
-        mine = local_best();
+      const int t_own = jsel % ROW_THREADS;
+      if (warp == (t_own >> 5)) {                           // xs[jsel] is only re-read by this warp until the barrier below
+        if (tid == t_own) xs[jsel] = NR_NEG_INF;
+        __syncwarp();
+        uint32_t so, sj;
+        scan_cols(t_own + lane * ROW_THREADS, 32 * ROW_THREADS, so, sj);
+        warp_argmax_ord(so, sj);
+        if (tid == t_own) { bo = so; bj = sj; }
       }
     }
     __syncthreads();
     // min / max over the NON-extended entries of x and of the bank centrality c (until_module.py:77-85)
-    unsigned long long klo = 0ull, khi = 0ull, clo = 0ull, chi = 0ull;
+    uint32_t xlo_o = 0u, xlo_j = NR_NO_INDEX, xhi_o = 0u, xhi_j = NR_NO_INDEX;
+    uint32_t clo_o = 0u, clo_j = NR_NO_INDEX, chi_o = 0u, chi_j = NR_NO_INDEX;
     for (int j = tid; j < B; j += ROW_THREADS) {
       if (xs[j] != NR_NEG_INF) {
-        float v = x[j], c = a.cbank[j];
-        unsigned long long t;
-        t = argmin_key(v, j); klo = t > klo ? t : klo;
-        t = argmax_key(v, j); khi = t > khi ? t : khi;
-        t = argmin_key(c, j); clo = t > clo ? t : clo;
-        t = argmax_key(c, j); chi = t > chi ? t : chi;
+        const uint32_t ov = float_ord(x[j]), oc = float_ord(a.cbank[j]);
+        if (~ov > xlo_o) { xlo_o = ~ov; xlo_j = (uint32_t)j; }
+        if (ov > xhi_o) { xhi_o = ov; xhi_j = (uint32_t)j; }
+        if (~oc > clo_o) { clo_o = ~oc; clo_j = (uint32_t)j; }
+        if (oc > chi_o) { chi_o = oc; chi_j = (uint32_t)j; }
       }
     }
-    klo = block_max_u64(klo, red64);
-    khi = block_max_u64(khi, red64);
-    clo = block_max_u64(clo, red64);
-    chi = block_max_u64(chi, red64);
-    const float lo_x = argmin_key_value(klo), hi_x = argmax_key_value(khi);
-    const float lo_c = argmin_key_value(clo), hi_c = argmax_key_value(chi);
+    block_argmax_ord(xlo_o, xlo_j, redk);
+    block_argmax_ord(xhi_o, xhi_j, redk);
+    block_argmax_ord(clo_o, clo_j, redk);
+    block_argmax_ord(chi_o, chi_j, redk);
+    const float lo_x = ord_float(~xlo_o), hi_x = ord_float(xhi_o);
+    const float lo_c = ord_float(~clo_o), hi_c = ord_float(chi_o);
     if (tid < k) {
       int j = nb_j[tid];
       float nx = (nb_x[tid] - lo_x) / (hi_x - lo_x);
@@ -202,10 +219,10 @@ row_losses_fwd_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __restric
       }
       ro[1 * rows + i] = -num / den;
       sv[6] = lo_x; sv[7] = hi_x; sv[8] = lo_c; sv[9] = hi_c; sv[10] = lse_ext; sv[11] = den;
-      sv[12] = __int_as_float((int)key_index(klo));
-      sv[13] = __int_as_float((int)key_index(khi));
-      sv[14] = __int_as_float((int)key_index(clo));
-      sv[15] = __int_as_float((int)key_index(chi));
+      sv[12] = __int_as_float((int)xlo_j);
+      sv[13] = __int_as_float((int)xhi_j);
+      sv[14] = __int_as_float((int)clo_j);
+      sv[15] = __int_as_float((int)chi_j);
     }
   }
 }
@@ -318,42 +335,44 @@ row_losses_fwd_warp_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __re
       const int j = lane + 32 * q;
       if (j < B && j != gi) alive |= 1u << q;
     }
-    // top-k of the off-diagonal entries: k rounds of warp arg-max, ties -> lower column
+    // top-k of the off-diagonal entries: k rounds of warp arg-max (redux.sync on the order-preserving integer image
+    // of the value, then on the column among the lanes that hold the maximum), ties -> lower column
+    uint32_t xo[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) xo[q] = float_ord(x[q]);
     for (int r = 0; r < k; ++r) {
-      unsigned long long best = 0ull;
+      uint32_t bo = 0u, bj = NR_NO_INDEX;
 #pragma unroll
       for (int q = 0; q < VPL; ++q) {
-        if ((alive >> q) & 1u) {
-          const unsigned long long key = argmax_key(x[q], (uint32_t)(lane + 32 * q));
-          best = key > best ? key : best;
-        }
+        if (((alive >> q) & 1u) && xo[q] > bo) { bo = xo[q]; bj = (uint32_t)(lane + 32 * q); }
       }
-      best = warp_max_u64(best);
-      const int jsel = (int)key_index(best);
+      warp_argmax_ord(bo, bj);
+      const int jsel = (int)bj;
       if ((jsel & 31) == lane) alive &= ~(1u << (jsel >> 5));
       if (lane == 0) {
         nb_j[r] = jsel;
-        nb_x[r] = argmax_key_value(best);
+        nb_x[r] = ord_float(bo);
         nbr_idx[(int64_t)i * k + r] = jsel;
       }
     }
     // min / max over the NON-extended entries of x and of the bank centrality c (until_module.py:77-85)
-    unsigned long long klo = 0ull, khi = 0ull, clo = 0ull, chi = 0ull;
+    uint32_t xlo_o = 0u, xlo_j = NR_NO_INDEX, xhi_o = 0u, xhi_j = NR_NO_INDEX;
+    uint32_t clo_o = 0u, clo_j = NR_NO_INDEX, chi_o = 0u, chi_j = NR_NO_INDEX;
 #pragma unroll
     for (int q = 0; q < VPL; ++q) {
       if ((alive >> q) & 1u) {
-        const int j = lane + 32 * q;
-        const float v = x[q], c = a.cbank[j];
-        unsigned long long t;
-        t = argmin_key(v, j); klo = t > klo ? t : klo;
-        t = argmax_key(v, j); khi = t > khi ? t : khi;
-        t = argmin_key(c, j); clo = t > clo ? t : clo;
-        t = argmax_key(c, j); chi = t > chi ? t : chi;
+        const uint32_t j = (uint32_t)(lane + 32 * q);
+        const uint32_t ov = xo[q], oc = float_ord(a.cbank[j]);
+        if (~ov > xlo_o) { xlo_o = ~ov; xlo_j = j; }
+        if (ov > xhi_o) { xhi_o = ov; xhi_j = j; }
+        if (~oc > clo_o) { clo_o = ~oc; clo_j = j; }
+        if (oc > chi_o) { chi_o = oc; chi_j = j; }
       }
     }
-    klo = warp_max_u64(klo); khi = warp_max_u64(khi); clo = warp_max_u64(clo); chi = warp_max_u64(chi);
-    const float lo_x = argmin_key_value(klo), hi_x = argmax_key_value(khi);
-    const float lo_c = argmin_key_value(clo), hi_c = argmax_key_value(chi);
+    warp_argmax_ord(xlo_o, xlo_j); warp_argmax_ord(xhi_o, xhi_j);
+    warp_argmax_ord(clo_o, clo_j); warp_argmax_ord(chi_o, chi_j);
+    const float lo_x = ord_float(~xlo_o), hi_x = ord_float(xhi_o);
+    const float lo_c = ord_float(~clo_o), hi_c = ord_float(chi_o);
     __syncwarp();
     for (int r = lane; r < k; r += 32) {
       const int j = nb_j[r];
@@ -382,10 +401,10 @@ row_losses_fwd_warp_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __re
     if (lane == 0) {
       ro[1 * rows + i] = -num / den;
       sv[6] = lo_x; sv[7] = hi_x; sv[8] = lo_c; sv[9] = hi_c; sv[10] = lse_ext; sv[11] = den;
-      sv[12] = __int_as_float((int)key_index(klo));
-      sv[13] = __int_as_float((int)key_index(khi));
-      sv[14] = __int_as_float((int)key_index(clo));
-      sv[15] = __int_as_float((int)key_index(chi));
+      sv[12] = __int_as_float((int)xlo_j);
+      sv[13] = __int_as_float((int)xhi_j);
+      sv[14] = __int_as_float((int)clo_j);
+      sv[15] = __int_as_float((int)chi_j);
     }
   }
 }
@@ -394,12 +413,13 @@ row_losses_fwd_warp_kernel(RowArgs a, float* __restrict__ row_out, int32_t* __re
 // backward: dX (dense row), dG (dense row), dc (atomic over rows), dw, d logit_scale
 // gscale[4] = upstream multipliers of the per-row terms {centrality, neighbour, kl, uniform}
 // ------------------------------------------------------------------------------------------
+template <int ROW_THREADS>
 __global__ void __launch_bounds__(ROW_THREADS)
 row_losses_bwd_kernel(RowArgs a, const int32_t* __restrict__ nbr_idx, const float* __restrict__ saved,
                       const float* __restrict__ gscale, float* __restrict__ dX, int64_t lddx,
                       float* __restrict__ dG, int64_t lddg, float* __restrict__ dc,
                       float* __restrict__ dw, float* __restrict__ dls) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   __shared__ float red[32];
   const int B = a.B, tid = threadIdx.x, i = blockIdx.x, gi = a.row0 + i;
   float* x = sm;
@@ -414,10 +434,8 @@ row_losses_bwd_kernel(RowArgs a, const int32_t* __restrict__ nbr_idx, const floa
   const float gs_n = (a.flags & NR_LOSS_NEIGHBOR) ? gscale[1] : 0.f;
   const float gs_k = (a.flags & NR_LOSS_KL) ? gscale[2] : 0.f;
   const float gs_u = (a.flags & NR_LOSS_UNIFORM) ? gscale[3] : 0.f;
-  for (int j = tid; j < B; j += ROW_THREADS) {
-    x[j] = Xr[j];
-    if (need_g) g[j] = Gr[j];
-  }
+  stage_row<ROW_THREADS>(Xr, x, B, tid);
+  if (need_g) stage_row<ROW_THREADS>(Gr, g, B, tid);
   __syncthreads();
   const float lse_c = sv[0], lse_x = sv[1], lse_g = sv[2], klrow = sv[3], lse_tg = sv[4], sumT = sv[5];
   const float wv = (a.flags & NR_LOSS_CENTRALITY) ? (a.w ? a.w[i] : 1.f) : 0.f;
@@ -619,9 +637,19 @@ extern "C" int nr_row_losses_fwd(const float* X, int64_t ldx, const float* G, in
     return 0;
   }
   size_t smem = row_smem((int)B);
-  if (smem > 48 * 1024)
-    NR_CUDA(cudaFuncSetAttribute(row_losses_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  row_losses_fwd_kernel<<<(unsigned)rows, ROW_THREADS, smem, (cudaStream_t)stream>>>(a, row_out, nbr_idx, saved);
+  if (row_big(B)) {
+    auto kern = row_losses_fwd_kernel<ROW_THREADS_BIG>;
+    NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<(unsigned)rows, ROW_THREADS_BIG, smem, (cudaStream_t)stream>>>(a, row_out, nbr_idx, saved);
+  } else {
+    auto kern = row_losses_fwd_kernel<ROW_THREADS_SMALL>;
+    if (smem > 48 * 1024) {
+      NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    kern<<<(unsigned)rows, ROW_THREADS_SMALL, smem, (cudaStream_t)stream>>>(a, row_out, nbr_idx, saved);
+  }
   NR_CHECK_LAUNCH("nr_row_losses_fwd");
   return 0;
 }
@@ -638,10 +666,21 @@ extern "C" int nr_row_losses_bwd(const float* X, int64_t ldx, const float* G, in
   RowArgs a{X, ldx, G, ldg, cbank, w, sk_u, sk_v, (int)rows, (int)B, (int)row0, logit_scale, k, tau_nbr,
             tau_uni, beta, flags};
   size_t smem = row_smem((int)B);
-  if (smem > 48 * 1024)
-    NR_CUDA(cudaFuncSetAttribute(row_losses_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  row_losses_bwd_kernel<<<(unsigned)rows, ROW_THREADS, smem, (cudaStream_t)stream>>>(
-      a, nbr_idx, saved, gscale, dX, lddx, dG, lddg, dc, dw, dls);
+  if (row_big(B)) {
+    auto kern = row_losses_bwd_kernel<ROW_THREADS_BIG>;
+    NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<(unsigned)rows, ROW_THREADS_BIG, smem, (cudaStream_t)stream>>>(a, nbr_idx, saved, gscale, dX, lddx, dG, lddg, dc,
+                                                                          dw, dls);
+  } else {
+    auto kern = row_losses_bwd_kernel<ROW_THREADS_SMALL>;
+    if (smem > 48 * 1024) {
+      NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      NR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
+    kern<<<(unsigned)rows, ROW_THREADS_SMALL, smem, (cudaStream_t)stream>>>(a, nbr_idx, saved, gscale, dX, lddx, dG, lddg,
+                                                                            dc, dw, dls);
+  }
   NR_CHECK_LAUNCH("nr_row_losses_bwd");
   return 0;
 }

@@ -174,7 +174,7 @@ class HeadFunction(torch.autograd.Function):
         mb_t2v, mb_v2t = mb[0], mb[1]
         cb = torch.empty(2, B, **f32)                     # [c_t2v ; c_v2t]
         ls = _f32c(logit_scale).reshape(1)
-        row_out = torch.zeros(2, 4, B, **f32)
+        row_out = torch.empty(2, 4, B, **f32)             # ALL_LOSSES: every entry is written by the row kernels
         nbr = torch.empty(2, B, k, dtype=torch.int32, device=dev)
         saved = torch.empty(2, B, NR_NSAVE, **f32)
         sums = torch.empty(8, **f32)
@@ -221,6 +221,9 @@ class HeadFunction(torch.autograd.Function):
         ctx.save_for_backward(tw, vw, tw_mb, vw_mb, *sm, S, ST, G, GT, cb, duals, w, ls, nbr, saved, mean,
                               gn, ginv, g2, v2, m54, p1, y1, p2, y2, pA, yA, pB, yB, pC, yC, pD, yD)
         ctx.gshape = (gt.shape, gv.shape)
+        # the backward's accumulators (token gradients, dc, dw, weight gradients, dls), zeroed next to the forward
+        nw_ = tw.numel() + vw.numel() + tw_mb.numel() + vw_mb.numel()
+        ctx.prezero = ops.prezeroed((T.rows + V.rows) * d + 4 * B + nw_ + 1, dev, 8) if any(ctx.needs_input_grad) else None
         ctx.nbr = nbr
         ctx.mark_non_differentiable(nbr)
         return out5, nbr
@@ -243,7 +246,12 @@ class HeadFunction(torch.autograd.Function):
         # (the token gradients first: their red.global.add.v4 needs 16-byte alignment)
         nw = tw.numel() + vw.numel() + tw_mb.numel() + vw_mb.numel()
         ntok = (T.rows + V.rows) * d
-        z = torch.zeros(ntok + 4 * B + nw + 1, **f32)
+        if ctx.prezero is not None:
+            z, ev_z = ctx.prezero
+            torch.cuda.current_stream().wait_event(ev_z)
+            ctx.prezero = None
+        else:
+            z = torch.zeros(ntok + 4 * B + nw + 1, **f32)
         dtn, dvn = z[:T.rows * d], z[T.rows * d:ntok]
         dc, dw = z[ntok:ntok + 2 * B].view(2, B), z[ntok + 2 * B:ntok + 4 * B].view(2, B)
         o = ntok + 4 * B
@@ -271,7 +279,9 @@ class HeadFunction(torch.autograd.Function):
                       _p(dG2), B, _p(dc[0]), _p(dw[1]), _p(dls), _stream())
         # ---- fork 2: token-pair contractions (main: text side, side 0: video side), global path (side 1),
         #      token-weight gradients (side 2)
-        with ops.ForkJoin(4) as fj:
+        # (the global branches on high-priority streams: their small kernels are placed as soon as an SM has room
+        # instead of queueing behind the ~1700 pending CTAs of the weight-gradient reduction)
+        with ops.ForkJoin(4, high=(1, 3)) as fj:
             _call("nr_transpose_add", _p(dS1), B, _p(dS2), B, _p(dS), B, B, B, 1.0, 1.0, _stream())
             ev_dS = torch.cuda.Event()
             ev_dS.record()
@@ -323,6 +333,10 @@ class HeadFunction(torch.autograd.Function):
                              (1, MT, tw_mb, vw, yC, yD, dc[1], 0, 1, sc, M, B, dvn)]
                 if jobs:
                     ops.maxsim2_bwd_multi(jobs, nt, nv, d)
+                if ops.EVENTS.get("_want_bank_events"):    # last reader of the bank's contraction operands (graph.py)
+                    ev_c = torch.cuda.Event()
+                    ev_c.record()
+                    ops.EVENTS["contraction_bwd_done"] = ev_c
                 with fj.on(2):
                     torch.cuda.current_stream().wait_event(ev_dS)
                     ops.maxsim2_bwd_w_multi([
@@ -363,6 +377,8 @@ class HeadFunction(torch.autograd.Function):
                     _call("nr_maxsim_bwd_w", _p(pC), _p(dc[1]), 0, 1, 0.5 / M, M, nt, B, _p(dtw_mb), st)
                 if need[7]:
                     _call("nr_maxsim_bwd_w", _p(pB), _p(dc[0]), 0, 1, 0.5 / M, M, nv, B, _p(dvw_mb), st)
+            # the weight-gradient reduction outlasts the contraction: the normalisation backward does not wait for it
+            ev_global_end = ev_global_end + (fj.detach(2),)
         # ---- fork 3: normalisation backward of the two modalities
         for ev in ev_dm:
             torch.cuda.current_stream().wait_event(ev)

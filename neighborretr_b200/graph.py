@@ -174,11 +174,31 @@ class GraphedHeadStep:
         # a gradient whose collective still runs on a side stream); d total / d out5 = e0 skips the unbind/stack
         # bookkeeping kernels of losses[0].backward()
         leaves = [s[f] for f in GRAD_FIELDS] + self.params
+        # split bank insert (single GPU, bf16 weight MLPs on the ring's operand): the backward nodes leave events behind
+        # their last reads of the ring
+        split_insert = self.world == 1 and ring is not None and ring.mlp_t is not None \
+            and os.environ.get("NR_SPLIT_INSERT", "1") != "0"
+        if split_insert:
+            ops.EVENTS["_want_bank_events"] = True
         if out5 is not None:
             self.grad_list = torch.autograd.grad(out5, leaves, grad_outputs=self._e0, allow_unused=True)
         else:
             self.grad_list = torch.autograd.grad(losses[0], leaves, allow_unused=True)
         m.last_out5 = None
+        ops.EVENTS.pop("_want_bank_events", None)
+        ev_c, ev_m = ops.EVENTS.pop("contraction_bwd_done", None), ops.EVENTS.pop("mlp_gemm_bwd_done", None)
+        if split_insert and ev_c is not None and ev_m is not None:
+            # the contraction operands, raw rows, masks and indices of the new samples go in right behind the backward
+            # contraction, next to the weight-MLP backward; only the MLP operand waits for the backward GEMM, and that
+            # last piece runs next to autograd's final gradient sums instead of after them
+            main = torch.cuda.current_stream()
+            self._fifo_stream.wait_event(ev_c)
+            with torch.cuda.stream(self._fifo_stream), torch.no_grad():
+                ring.insert(*new_rows, phase="early")
+                self._fifo_stream.wait_event(ev_m)
+                ring.insert(*new_rows, phase="late")
+            main.wait_stream(self._fifo_stream)
+            return out5.detach() if out5 is not None else torch.stack([x.detach() for x in losses])
         if early_fifo:
             main.wait_stream(self._fifo_stream)
         else:

@@ -55,6 +55,7 @@ def _mask(t):
 
 
 _SIDE_STREAMS = {}
+_SIDE_STREAMS_HP = {}
 
 
 class ForkJoin:
@@ -68,15 +69,22 @@ class ForkJoin:
     Under CUDA-graph capture the side streams become parallel branches of the graph.  Callers allocate every buffer
     a branch touches BEFORE the fork, on the main stream (the caching allocator tracks one stream per block)."""
 
-    def __init__(self, n, offset=0):
+    def __init__(self, n, offset=0, high=()):
         """offset: use side streams [offset, offset + n) — a fork nested inside another fork's main section must not
-        reuse the outer fork's streams."""
+        reuse the outer fork's streams.  high: branch indices that run on HIGH-PRIORITY streams: small kernels that
+        would otherwise queue behind the pending CTAs of a persistent kernel launched before them."""
         self.main = torch.cuda.current_stream()
         lst = _SIDE_STREAMS.get(self.main.device.index, [])
         while len(lst) < offset + n:
             lst.append(torch.cuda.Stream(device=self.main.device))
         _SIDE_STREAMS[self.main.device.index] = lst
-        self.side = lst[offset:offset + n]
+        self.side = list(lst[offset:offset + n])
+        for i in high:
+            key = (self.main.device.index, offset + i)
+            st = _SIDE_STREAMS_HP.get(key)
+            if st is None:
+                st = _SIDE_STREAMS_HP[key] = torch.cuda.Stream(device=self.main.device, priority=-1)
+            self.side[i] = st
         self.detached = set()
 
     def __enter__(self):
@@ -114,6 +122,20 @@ def hp_stream(device=None):
     if st is None:
         st = _HP_STREAMS[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
     return st
+
+
+def prezeroed(numel, device, offset):
+    """fp32 zeros for accumulators of a LATER stage, filled on a side stream now: inside a captured step the fill is a
+    parallel branch instead of a node on the critical path right before its consumer.  Only while capturing (returns
+    None otherwise: the consumer then allocates its zeros itself).  Returns (flat tensor, event to wait on)."""
+    if not torch.cuda.is_current_stream_capturing():
+        return None
+    z = torch.empty(int(numel), dtype=torch.float32, device=device)        # allocated on the main stream
+    with ForkJoin(1, offset=offset) as fj:
+        with fj.on(0):
+            z.zero_()
+        ev = fj.detach(0)
+    return z, ev
 
 
 class _KernelTimer:
@@ -312,10 +334,16 @@ _TILE_WS = {}
 
 def _tile_workspace(dev):
     """Persistent, self-resetting scheduler counters: one zero-initialised 16-byte buffer per (device, stream)."""
-    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    cap = torch.cuda.is_current_stream_capturing()
+    new = lambda: torch.zeros(4 + 2 * 16 * 256, dtype=torch.int32, device=dev)        # counters + debug timeline
+    key = (dev.index, "capture" if cap else torch.cuda.current_stream(dev).cuda_stream)
     ws = _TILE_WS.get(key)
     if ws is None:
-        ws = _TILE_WS[key] = torch.zeros(4 + 2 * 16 * 256, dtype=torch.int32, device=dev)   # counters + debug timeline
+        ws = _TILE_WS[key] = new()
+    if not cap and (dev.index, "capture") not in _TILE_WS:
+        # captured steps (one launch per step, replays never overlap on a device) share a buffer created HERE, outside
+        # any capture: allocated while capturing, its zero fill would become a node in front of every replayed launch
+        _TILE_WS[(dev.index, "capture")] = new()
     return ws
 
 
@@ -757,6 +785,11 @@ class TokenWeightsPairFunction(torch.autograd.Function):
             _call("nr_token_softmax", _p(sd["logits"]), _p(sd["b2"]), _p(sd["ma"]), _p(sd["mb"]), sd["Ra"], sd["Ra"] + sd["Rb"],
                   sd["N"], _p(sd["w"]), st)
         ctx.dims = [(sd["Ra"], sd["Rb"], sd["N"], sd["xshape"]) for sd in sides] + [(D, H)]
+        # the split-K accumulators of the backward GEMM (dW1, dx of both modalities), zeroed next to the forward
+        need = ctx.needs_input_grad
+        ctx.zsizes = [H * D if need[8] else 0, sides[0]["Ta"] * D if need[0] else 0,
+                      H * D if need[12] else 0, sides[1]["Ta"] * D if need[4] else 0]
+        ctx.prezero = prezeroed(sum(ctx.zsizes), dev, 7) if keep else None
         saved = []
         for sd in sides:
             saved += [sd["xbf"], sd["h"], sd["w"], sd["w1bf"], sd["w2"]]
@@ -776,6 +809,18 @@ class TokenWeightsPairFunction(torch.autograd.Function):
         arr = (_lib.MlpSide * 2)()
         res = []
         keepalive = []
+        if ctx.prezero is not None:
+            z, ev_z = ctx.prezero
+            torch.cuda.current_stream().wait_event(ev_z)
+        else:
+            z = torch.zeros(sum(ctx.zsizes), **f32)             # ONE fill for the four accumulators
+        zo = [0]
+
+        def take(n, shape):
+            t = z[zo[0]:zo[0] + n].view(shape)
+            zo[0] += n
+            return t
+
         # every buffer before the fork
         for i, (dwa, dwb, nx, nw1) in enumerate(((dwt, dwtb, need[0], need[8]), (dwv, dwvb, need[4], need[12]))):
             xbf, h, w, w1bf, w2c = sv[5 * i:5 * i + 5]
@@ -786,7 +831,7 @@ class TokenWeightsPairFunction(torch.autograd.Function):
                             dwa=_f32c(dwa) if dwa is not None else None, dwb=_f32c(dwb) if (dwb is not None and Rb) else None,
                             dh=torch.empty_like(h), partials=torch.empty(2 * H + 1, nch, **f32), nch=nch,
                             sums=torch.empty(2 * H + 1, **f32),
-                            dw1=torch.zeros(H, D, **f32) if nw1 else None, dx=torch.zeros(Ta, D, **f32) if nx else None))
+                            dw1=take(H * D, (H, D)) if nw1 else None, dx=take(Ta * D, (Ta, D)) if nx else None))
         def hidden_bwd(r):
             _call("nr_token_weights_bwd", _p(r["h"]), 1, _p(r["w"]), _p(r["dwa"]), _p(r["dwb"]), r["Ra"], r["Ra"] + r["Rb"],
                   r["N"], _p(r["w2c"]), H, _p(r["dh"]), _p(r["partials"]), _stream())
@@ -806,6 +851,10 @@ class TokenWeightsPairFunction(torch.autograd.Function):
                 for r in res:
                     _call("nr_vec_sums", _p(r["partials"]), 2 * H + 1, r["nch"], None, _p(r["sums"]), _stream())
             _call("nr_mlp_bwd_pair", ctypes.cast(arr, ctypes.c_void_p), 2, D, H, _stream())
+            if EVENTS.get("_want_bank_events"):       # last reader of the bank's MLP operand (graph.py: late insert)
+                ev_b = torch.cuda.Event()
+                ev_b.record()
+                EVENTS["mlp_gemm_bwd_done"] = ev_b
         out = []
         for i, r in enumerate(res):
             base = 8 + 4 * i

@@ -22,6 +22,26 @@ def prep(r, nt, nv, seed):
     return T, V, tw, vw
 
 
+if len(sys.argv) >= 3 and sys.argv[1] == "rank":
+    # evaluation ranks straight from the accumulator (nr_maxsim2_rank, count pass): q x q MSR-VTT-shaped test set
+    q, nt, nv = int(sys.argv[2]), 24, 12
+    h = synth.make_batch(q, nt, nv, d=d, seed=7).to("cuda")
+    tw = torch.full((q, nt), 1.0 / nt, device="cuda"); vw = torch.full((q, nv), 1.0 / nv, device="cuda")
+    r = ops.FusedRanker(h.text_feat, h.video_feat, tw, vw, h.text_mask, h.video_mask, "bf16")
+    diag = r.diagonal(q)
+    evs = []
+    for i in range(n):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); r._launch(2, diag, r.counts(diag) if i == 0 else cnt); e.record()
+        cnt = tuple(torch.zeros_like(c) for c in r.counts(diag)) if i == 0 else cnt
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ts = [a.elapsed_time(b_) * 1e3 for a, b_ in evs]
+    avg = sum(ts[2:]) / len(ts[2:])
+    fl = 2.0 * q * nt * q * nv * d
+    print(f"nr_maxsim2_rank count pass {q} x {q}: {min(ts):.1f} us best, {avg:.1f} us avg -> {fl / avg / 1e6:.0f} TFLOP/s; "
+          f"S ({q * q * 4 / 1e6:.0f} MB) is never written")
+    sys.exit(0)
 if len(sys.argv) >= 5:
     rx, nx, ry, ny = [int(v) for v in sys.argv[1:5]]
     X, _, wx, _ = prep(rx, nx, ny, 7)
