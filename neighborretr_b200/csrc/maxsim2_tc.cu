@@ -67,6 +67,7 @@ struct alignas(64) Tc2Args {
   int nprob, n_tiles;
   int Nx, SX, MU, SY, UN, num_kb, stages, b_bytes, hp_ld, kg_ld;
   int mode, cnt_w;                         // cnt_w: ints per count vector in shared memory (COUNT), else 0
+  int l2_hints;                            // 1: Y boxes evict_last, X boxes evict_first (banded order on large problems)
   unsigned int* tile_counter;              // zeroed per launch: dynamic tile scheduler
   unsigned long long* trace;               // debug (NR_TC2_TRACE=1): 16 globaltimer stamps per CTA, else nullptr
 };
@@ -228,6 +229,8 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
       // CL2: the leader's barrier collects the bytes of both CTAs (X box + half a Y box each)
       const int hb = a.SY * NY / 2;
       const uint32_t tx_bytes = CL2 ? 2u * (uint32_t)(a.MU + hb) * 128u : (uint32_t)(a.MU + a.SY * NY) * 128u;
+      const uint64_t pol_x = a.l2_hints == 2 ? l2_policy_evict_last() : l2_policy_evict_first();
+      const uint64_t pol_y = a.l2_hints == 2 ? l2_policy_evict_first() : l2_policy_evict_last();
       // Dynamic tile scheduler: tiles are claimed from a global counter, so a CTA whose SM was still busy with
       // another kernel of the step graph (the persistent grid is one CTA per SM) simply takes fewer tiles.
       for (int n = 0;; ++n) {
@@ -288,6 +291,10 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
             if (cr == 0) mbar_expect_tx(full + stage, tx_bytes);
             tma_load_2d_cg2(sa, &a.tmx[p], full + stage, kb * T2_BK, row_x);
             tma_load_2d_cg2(sa + T2_A_BYTES, &a.tmy[p], full + stage, kb * T2_BK, row_y + (int)cr * hb);
+          } else if (a.l2_hints) {
+            mbar_expect_tx(full + stage, tx_bytes);
+            tma_load_2d_hint(sa, &a.tmx[p], full + stage, kb * T2_BK, row_x, pol_x);
+            tma_load_2d_hint(sa + T2_A_BYTES, &a.tmy[p], full + stage, kb * T2_BK, row_y, pol_y);
           } else {
             mbar_expect_tx(full + stage, tx_bytes);
             tma_load_2d(sa, &a.tmx[p], full + stage, kb * T2_BK, row_x);
@@ -724,6 +731,8 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
     if (int e = make_tmap_bf16(&a.tmy[i], q.y_bf16, q.Ry * Ny, d, a.SY * (int)Ny / (pair ? 2 : 1))) return e;   // pair: half boxes
   }
   a.n_tiles = tiles;
+  a.l2_hints = 0;
+  if (const char* hv = getenv("NR_TC2_L2HINT")) a.l2_hints = atoi(hv);
   a.tile_counter = (unsigned int*)workspace;        // {next tile, finished claimers}: zero on entry, zero again on exit
   // debug timeline: the caller provides >= 16 + 8 * 16 * gridDim bytes of workspace when it sets NR_TC2_TRACE
   a.trace = nullptr;

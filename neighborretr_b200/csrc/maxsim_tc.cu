@@ -16,6 +16,7 @@
 // A tile is SX whole X samples (SX*Nx <= 128 rows; rows up to 128 are don't-care) by SY whole Y samples
 // (SY*Ny <= 256 columns), so every max / sum segment is tile-local.
 // Roofline: tensor pipe.  Algorithmic flops per launch 2*Rx*Nx*Ry*Ny*D; executed: 128/(SX*Nx) more.
+#include <stdlib.h>
 #include "common.cuh"
 #include "nrhead_internal.h"
 #include "tc_common.cuh"
@@ -271,9 +272,14 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int64_t rows, int64_t d, in
   cuuint64_t gstr[1] = {(cuuint64_t)d * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (const char* pv = getenv("NR_TMA_PROMO")) {        // measurement knob: 0 none, 64, 128, 256
+    const int v = atoi(pv);
+    promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+          : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NR_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%lld d=%lld box_rows=%d", (int)r,
                (long long)rows, (long long)d, box_rows);
   return 0;
@@ -573,9 +579,14 @@ int make_tmap_srcT(CUtensorMap* m, const void* base, int64_t d, int64_t tokens, 
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (const char* pv = getenv("NR_TMA_PROMO")) {        // measurement knob: 0 none, 64, 128, 256
+    const int v = atoi(pv);
+    promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+          : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NR_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(srcT) failed (%d) d=%lld tokens=%lld ld=%lld", (int)r,
                (long long)d, (long long)tokens, (long long)ld);
   return 0;

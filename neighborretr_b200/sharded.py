@@ -75,14 +75,22 @@ class SumGradsAcrossRanks(torch.autograd.Function):
         ref = next(g for g in gs if g is not None)
         extra = ops.EVENTS.pop("loss_out5_partial", None)          # partial losses of the captured step (see forward)
         n_extra = extra.numel() if extra is not None else 0
-        flat = torch.zeros(sum(sizes) + n_extra, dtype=ref.dtype, device=ref.device)
-        if extra is not None:
-            flat[sum(sizes):].copy_(extra.detach().reshape(-1))
-        o = 0
-        for g, n in zip(gs, sizes):
-            if g is not None:
-                flat[o:o + n].copy_(g.reshape(-1))
-            o += n
+        if all(g is not None and g.dtype == ref.dtype for g in gs):
+            # ONE gather kernel instead of a fill and a copy node per parameter (ten ~1.7 us nodes in a row at the end
+            # of the captured step's critical path)
+            parts = [g.reshape(-1) for g in gs]
+            if extra is not None:
+                parts.append(extra.detach().reshape(-1).to(ref.dtype))
+            flat = torch.cat(parts)
+        else:
+            flat = torch.zeros(sum(sizes) + n_extra, dtype=ref.dtype, device=ref.device)
+            if extra is not None:
+                flat[sum(sizes):].copy_(extra.detach().reshape(-1))
+            o = 0
+            for g, n in zip(gs, sizes):
+                if g is not None:
+                    flat[o:o + n].copy_(g.reshape(-1))
+                o += n
         ev = torch.cuda.Event()                 # everything that reads the step's operands is enqueued: the captured
         ev.record()                             # step starts its bank insert here, under the all-reduce
         ops.EVENTS["mlp_backward_done"] = ev
