@@ -85,7 +85,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
-K1_TRAFFIC = {(1, "msrvtt", "nr_maxsim2_fwd"): 23.73e6 + 0.73e6}
+K1_TRAFFIC = {(1, "msrvtt", "nr_maxsim2_fwd"): 23.73e6 + 0.44e6}
 
 
 def flops_maxsim(rx, ry, nt, nv, d=D):
@@ -583,9 +583,10 @@ def run_ours(args):
         "roofline": {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": K1_TRAFFIC.get((world, args.shape, kname)),
-                     "traffic_note": "dram bytes read+written per launch, ncu --set full of tools/k2_only.py "
-                                     "(profiles/r1_k2_fwd_ncu_full.txt): the 23.6e6 B of bf16 operands are read from "
-                                     "HBM once, the 27e6 B of saved max/arg-max and similarities stay in L2",
+                     "traffic_note": "a constant, not measured by this run: dram bytes read+written per launch in the ncu "
+                                     "--set full capture of tools/k2_only.py (profiles/r2_k2_fwd_ncu_full.txt): the 23.6e6 B "
+                                     "of bf16 operands are read from HBM once, the 27e6 B of saved max/arg-max and "
+                                     "similarities stay in L2",
                      "launches_timed": n_l, "avg_launch_ms": kt["ms"] / n_l,
                      "share_of_step": (kt["ms"] / ksteps) / (ms_total / args.steps) if ms_total else None,
                      "timed_in": "eager steps on the launching stream (events cannot be read inside a graph replay), the "

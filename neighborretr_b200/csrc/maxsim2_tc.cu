@@ -68,6 +68,7 @@ struct alignas(64) Tc2Args {
   int Nx, SX, MU, SY, UN, num_kb, stages, b_bytes, hp_ld, kg_ld;
   int mode, cnt_w;                         // cnt_w: ints per count vector in shared memory (COUNT), else 0
   int l2_hints;                            // 1: Y boxes evict_last, X boxes evict_first (banded order on large problems)
+  int elect;                               // barrier releases by one elected thread per epilogue set
   unsigned int* tile_counter;              // zeroed per launch: dynamic tile scheduler
   unsigned long long* trace;               // debug (NR_TC2_TRACE=1): 16 globaltimer stamps per CTA, else nullptr
 };
@@ -175,10 +176,13 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
     for (int p = 0; p < a.nprob; ++p) { tma_prefetch_desc(&a.tmx[p]); tma_prefetch_desc(&a.tmy[p]); }
     for (int s = 0; s < a.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     // CL2: the leader's issuer overwrites the accumulator stage in BOTH CTAs: both epilogue sets release it there
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, CL2 ? 2 * T2_SET : T2_SET); }
+    // a.elect: ONE elected thread per epilogue set releases the accumulator stage and the ring slot (behind the set
+    // barrier) instead of every thread of the set
+    const int per_set = a.elect ? 1 : T2_SET;
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, CL2 ? 2 * per_set : per_set); }
     // ring: filled by the (leader's) scheduler; released by the MMA issuer and one epilogue set of every CTA of the
     // pair, plus the non-leader's TMA producer
-    for (int s = 0; s < T2_RING; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, CL2 ? 2 * (1 + T2_SET) + 1 : 1 + T2_SET); }
+    for (int s = 0; s < T2_RING; ++s) { mbar_init(rfull + s, 1); mbar_init(rempty + s, CL2 ? 2 * (1 + per_set) + 1 : 1 + per_set); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -192,13 +196,19 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) T2_TRACE(0);                      // set-up done
   // consumers of a ring slot: read the tile, release the slot on the LEADER's barrier
-  auto ring_take = [&](int it) {
+  auto ring_release = [&](int it) {
+    const int slot = it & (T2_RING - 1);
+    if (CL2) mbar_arrive_remote(rempty + slot, 0);
+    else mbar_arrive(rempty + slot);
+  };
+  // release = false: the caller releases the slot later through ONE elected thread (the epilogue sets: 256 arrivals
+  // per tile on one shared-memory word — cluster-scope ones for the peer of a pair — become one)
+  auto ring_take = [&](int it, bool release = true) {
     const int slot = it & (T2_RING - 1);
     if (CL2) mbar_wait_cluster(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
     else mbar_wait(rfull + slot, (uint32_t)(it / T2_RING) & 1u);
     const int tile = ring[slot];
-    if (CL2) mbar_arrive_remote(rempty + slot, 0);
-    else mbar_arrive(rempty + slot);
+    if (release) ring_release(it);
     return tile;
   };
 
@@ -366,8 +376,11 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
     // COUNT: zeroed once; afterwards the thread that flushes an entry re-zeroes it (two set barriers before its next use)
     for (int i = et; i < 4 * a.cnt_w; i += T2_SET) cset[i] = 0;
     for (int it = set;; it += 2) {
-      const int tile = ring_take(it);
-      if (tile < 0) break;
+      const int tile = ring_take(it, !a.elect);
+      if (tile < 0) {                                      // end marker: nothing overwrites the ring any more
+        if (a.elect && et == 0) ring_release(it);
+        break;
+      }
       int pi, mt, nt;
       decode(tile, pi, mt, nt);
       const Tc2Prob& P = a.p[pi];
@@ -453,9 +466,16 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
         }
       }
       tc_fence_before();
-      if (CL2) mbar_arrive_remote(tempty + set, 0);      // TMEM stage may be overwritten (the leader issues for both)
-      else mbar_arrive(tempty + set);
-      set_barrier<T2_SET>(set);
+      if (!a.elect) {
+        if (CL2) mbar_arrive_remote(tempty + set, 0);    // TMEM stage may be overwritten (the leader issues for both)
+        else mbar_arrive(tempty + set);
+      }
+      set_barrier<T2_SET>(set);                          // every thread of the set has drained its part of the stage
+      if (a.elect && et == 0) {
+        if (CL2) mbar_arrive_remote(tempty + set, 0);
+        else mbar_arrive(tempty + set);
+        ring_release(it);                                // and every thread of the set has read its ring entry
+      }
       // F1: combine the Nx/GL group partials of each (X sample, column): value, arg-max row, weighted value.
       // Element e = s * ncols + c, e = et, et + T2_SET, ...: (s, c) advance without a division.
       {
@@ -733,6 +753,11 @@ static int maxsim2_fwd_impl(const nr_maxsim2_problem* probs, int nprob, int64_t 
   a.n_tiles = tiles;
   a.l2_hints = 0;
   if (const char* hv = getenv("NR_TC2_L2HINT")) a.l2_hints = atoi(hv);
+  // measured A/B on one B200 (tools/gpu_r2u.sh): no difference for independent CTAs (b = 1024: 584 vs 584 us), SLOWER for
+  // CTA pairs (617 -> 643 us: the release then waits for the slowest thread of the set plus a barrier, and the pair's
+  // critical path is exactly accumulator release -> leader's next MMA) -> off; NR_TC2_ELECT=1 turns it on
+  a.elect = 0;
+  if (const char* ev2 = getenv("NR_TC2_ELECT")) a.elect = atoi(ev2) != 0;
   a.tile_counter = (unsigned int*)workspace;        // {next tile, finished claimers}: zero on entry, zero again on exit
   // debug timeline: the caller provides >= 16 + 8 * 16 * gridDim bytes of workspace when it sets NR_TC2_TRACE
   a.trace = nullptr;

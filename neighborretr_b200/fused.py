@@ -209,10 +209,22 @@ class HeadFunction(torch.autograd.Function):
             with fj.on(0):
                 _call("nr_row_losses_fwd", _p(ST), B, _p(GT), B, _p(cb[0]), _p(w[1]), _p(duals[2]), _p(duals[3]), B, B,
                       0, _p(ls), k, tau, tau, beta, ALL_LOSSES, _p(row_out[1]), _p(nbr[1]), _p(saved[1]), _stream())
-        _call("nr_vec_sums", _p(row_out), 8, B, None, _p(sums), st)
         # [total, centrality, uniform, neighbor, kl] = M54 @ (sums_dir1 + sums_dir2);  sums order: c, n, kl, u
         out5 = torch.empty(5, **f32)
-        _call("nr_matvec_small", _p(m54), 5, 4, 0, _p(sums), _p(sums[4:]), _p(out5), st)
+        ctx.ev_out5 = None
+        if torch.cuda.is_current_stream_capturing() and any(ctx.needs_input_grad):
+            # captured step: nothing of the backward reads the loss VALUES, so their two small reductions leave the
+            # critical path between the row losses and their backward (joined at the end of backward())
+            with ops.ForkJoin(1, offset=9) as fj:
+                with fj.on(0):
+                    _call("nr_vec_sums", _p(row_out), 8, B, None, _p(sums), _stream())
+                    _call("nr_matvec_small", _p(m54), 5, 4, 0, _p(sums), _p(sums[4:]), _p(out5), _stream())
+                ctx.ev_out5 = fj.detach(0)
+            # the branch reads these after forward() has returned: keep them out of the allocator until it is joined
+            ctx.keep_out5 = (row_out, sums)
+        else:
+            _call("nr_vec_sums", _p(row_out), 8, B, None, _p(sums), st)
+            _call("nr_matvec_small", _p(m54), 5, 4, 0, _p(sums), _p(sums[4:]), _p(out5), st)
         ctx.hp = hp
         ctx.objs = (T, V, MT, MV)
         # the masks are only read by the one-direction backward kernels (the fused path folded them into the operand
@@ -390,6 +402,9 @@ class HeadFunction(torch.autograd.Function):
                     V.backward(dvn, add_vec=dmean[1], out=dvideo)
         for ev in ev_global_end:
             torch.cuda.current_stream().wait_event(ev)
+        if ctx.ev_out5 is not None:
+            torch.cuda.current_stream().wait_event(ctx.ev_out5)
+            ctx.keep_out5 = None
         ctx.objs = None
         gs_t, gs_v = ctx.gshape
         return (dtext, dvideo, dgt.reshape(gs_t) if need[2] else None, dgv.reshape(gs_v) if need[3] else None,

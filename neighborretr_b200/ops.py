@@ -770,9 +770,12 @@ class TokenWeightsPairFunction(torch.autograd.Function):
         _cast_multi(casts)
         keep = any(ctx.needs_input_grad)
         arr = (_lib.MlpSide * 2)()
+        # the second-layer dot products accumulate atomically: ONE zero fill for both modalities' logits
+        nlog = [(sd["Ra"] + sd["Rb"]) * sd["N"] for sd in sides]
+        zlog = torch.zeros(sum(nlog), dtype=torch.float32, device=dev)
         for i, sd in enumerate(sides):
             sd["h"] = torch.empty(sd["Ta"] + sd["Tb"], H, dtype=torch.bfloat16, device=dev) if keep else None
-            sd["logits"] = torch.zeros(sd["Ra"] + sd["Rb"], sd["N"], dtype=torch.float32, device=dev)
+            sd["logits"] = zlog[sum(nlog[:i]):sum(nlog[:i + 1])].view(sd["Ra"] + sd["Rb"], sd["N"])
             sd["w"] = torch.empty(sd["Ra"] + sd["Rb"], sd["N"], dtype=torch.float32, device=dev)
             a = arr[i]
             a.x_bf16, a.w1_bf16, a.T = sd["xbf"].data_ptr(), sd["w1bf"].data_ptr(), sd["Ta"] + sd["Tb"]
