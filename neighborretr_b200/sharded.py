@@ -14,6 +14,8 @@ Sinkhorn and the global similarity G [B,B] are replicated (2*B^2*D flops, no exc
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -103,6 +105,15 @@ class SumGradsAcrossRanks(torch.autograd.Function):
             out.append(flat[o:o + n].view(shp))
             o += n
         return tuple(out)
+
+
+def sinkhorn_serial(B):
+    """Global batch from which the forward contraction is ordered BEHIND the Sinkhorn chain instead of next to it
+    (NR_SINKHORN_SERIAL = smallest such batch, 0 = never = default).  Measured on 8 B200 (global batch 1024,
+    profiles/r2_n8_sinkhorn_serial_ab.txt): 624 steps/s serialised against 773 side by side — sharing the GPU costs
+    both kernels less than the lost overlap."""
+    v = int(os.environ.get("NR_SINKHORN_SERIAL", "0") or 0)
+    return v > 0 and B >= v
 
 
 _TEXT_STREAMS = {}
@@ -257,9 +268,11 @@ class ShardedPrologue:
         B, iters = self.B, int(self.hp[4])
         _call("nr_gram_f32", _p(self.g2), _p(self.v2), B, B, self.V.d, _p(self.GG[0]), _p(self.GG[1]), _stream())
         d_ = self.duals
-        # in-step: 16 rows per CTA for the multi-CTA variants (the chain shares the GPU with the contraction)
+        # in-step: 16 rows per CTA for the multi-CTA variants (the chain shares the GPU with the contraction); when the
+        # contraction waits for the chain (sinkhorn_serial), the chain's own best setting
+        rows = 0 if B < 256 else (8 if sinkhorn_serial(B) else 16)
         _call("nr_sinkhorn_ex", _p(self.GG[0]), _p(self.GG[1]), B, iters, _p(d_[0]), _p(d_[1]), _p(d_[2]), _p(d_[3]),
-              _p(self.lib_ws), self.nws, 16 if B >= 256 else 0, _stream())
+              _p(self.lib_ws), self.nws, rows, _stream())
 
     def run_forked(self):
         with ops.ForkJoin(2) as fj:
@@ -317,6 +330,11 @@ class ShardedHeadFunction(torch.autograd.Function):
             # the transposed block is written with a leading dimension of b + 2: chunk q (rows q*b..) is then the
             # [b, b+2] payload for rank q, whose two spare columns carry this rank's bank centralities (exchange 3)
             PT = torch.empty(B, b + 2, **f32)
+            if sinkhorn_serial(B) and pro.global_done is not None:
+                # large global batches: the Sinkhorn chain and the contraction exclude each other on an SM and both
+                # crawl when they share the GPU; the chain starts ~0.1 ms earlier, so the contraction waits for it
+                torch.cuda.current_stream().wait_event(pro.global_done)
+                pro.global_done = None
             sv1, svA, svC = ops.maxsim2_fwd([
                 dict(X=Tl, Y=V, wx=tw_lc, wy=vw, alpha=0.5, out=S_row, strides=(B, 1), out2=PT, strides2=(1, b + 2)),
                 dict(X=Tl, Y=MV, wx=tw_lc, wy=vw_mb, alpha=0.5, out=mb_t2v, strides=(M, 1)),

@@ -132,3 +132,72 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert parts[0] == cname
         assert int(parts[1]) == ctypes.sizeof(cls), cname
         assert [int(v) for v in parts[2:]] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
+
+
+def test_static_input_slab_views():
+    """graph._slab_like: the seven step inputs as views of ONE byte slab (so that a staged batch moves in with a single
+    copy): shapes / dtypes preserved, 256-byte aligned, non-overlapping, writes through the views land in the slab."""
+    import torch
+    from neighborretr_b200.graph import FIELDS, _slab_like
+    h = synth.make_batch(5, 7, 3, d=16, seed=3)
+    ex = [getattr(h, f) for f in FIELDS]
+    slab, views = _slab_like(ex, torch.device("cpu"))
+    assert slab.dtype == torch.uint8 and slab.dim() == 1
+    spans = []
+    for f, t in zip(FIELDS, ex):
+        v = views[f]
+        assert v.shape == t.shape and v.dtype == t.dtype and v.is_contiguous()
+        off = v.data_ptr() - slab.data_ptr()
+        assert off % 256 == 0
+        spans.append((off, off + t.numel() * t.element_size()))
+        v.copy_(t)
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= slab.numel()
+    slab2, views2 = _slab_like(ex, torch.device("cpu"))
+    slab2.copy_(slab)                          # a second slab filled by ONE copy of the first reproduces every input
+    for f, t in zip(FIELDS, ex):
+        assert torch.equal(views2[f], t)
+
+
+def _band_decode(local, n_me, n_nt, wn):
+    """Python restatement of the tile order of csrc/maxsim2_tc.cu (decode lambda): bands of wn Y tiles, inside a band
+    the Y tile runs fastest."""
+    band_tiles = n_me * wn
+    bnd, rem = divmod(local, band_tiles)
+    w = min(wn, n_nt - bnd * wn)
+    mt = rem // w
+    return mt, bnd * wn + rem - mt * w
+
+
+def _diag_tile(local, SX, SY, Rx, Ry, gx0, gy0, dj):
+    """... of diag_tile(): entry `local` = (X box, j-th Y tile holding positives of that box), or None."""
+    mt, j = divmod(local, dj)
+    off = gx0 - gy0
+    x0 = mt * SX
+    lo = max(x0 + off, 0)
+    hi = min(min(x0 + SX, Rx) - 1 + off, Ry - 1)
+    nt = lo // SY + j
+    return (mt, nt) if hi >= lo and nt <= hi // SY else None
+
+
+@pytest.mark.parametrize("n_me,n_nt,wn", [(1, 1, 1), (26, 26, 68), (1639, 410, 65), (7, 10, 3), (5, 9, 9), (3, 17, 16)])
+def test_band_order_visits_every_tile_once(n_me, n_nt, wn):
+    wn = min(wn, n_nt)
+    seen = [_band_decode(t, n_me, n_nt, wn) for t in range(n_me * n_nt)]
+    assert len(set(seen)) == n_me * n_nt
+    assert all(0 <= mt < n_me and 0 <= nt < n_nt for mt, nt in seen)
+    if wn == n_nt:                                  # a single band is the plain row-major order
+        assert seen == [(t // n_nt, t % n_nt) for t in range(n_me * n_nt)]
+
+
+@pytest.mark.parametrize("SX,SY,Rx,Ry,gx0,gy0", [(5, 20, 101, 101, 0, 0), (5, 20, 101, 37, 0, 40), (5, 20, 101, 6, 0, 95),
+                                               (2, 4, 37, 37, 0, 0), (10, 10, 45, 45, 0, 0), (10, 10, 12, 45, 20, 0),
+                                               (32, 5, 70, 70, 0, 0)])
+def test_diag_tile_list_covers_every_positive_once(SX, SY, Rx, Ry, gx0, gy0):
+    """Pass 1 of nr_maxsim2_rank contracts only tiles that hold a positive pair (pair id gx0+rx == gy0+ry): the tile
+    list must contain every such tile exactly once and nothing else."""
+    dj = (SX + SY - 2) // SY + 1
+    n_mt = (Rx + SX - 1) // SX
+    tiles = [t for t in (_diag_tile(l, SX, SY, Rx, Ry, gx0, gy0, dj) for l in range(n_mt * dj)) if t is not None]
+    want = {(rx // SX, (rx + gx0 - gy0) // SY) for rx in range(Rx) if 0 <= rx + gx0 - gy0 < Ry}
+    assert len(tiles) == len(set(tiles)) and set(tiles) == want
