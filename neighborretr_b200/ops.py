@@ -67,7 +67,10 @@ class ForkJoin:
             with fj.on(1): ...
 
     Under CUDA-graph capture the side streams become parallel branches of the graph.  Callers allocate every buffer
-    a branch touches BEFORE the fork, on the main stream (the caching allocator tracks one stream per block)."""
+    a branch touches BEFORE the fork, on the main stream (the caching allocator tracks one stream per block), and — for
+    a DETACHED branch — keep a reference to every such buffer until the branch has been joined: a block freed when its
+    Python owner goes out of scope is handed to the next main-stream allocation, which the still-running branch then
+    races with (fused.HeadFunction keeps `row_out` / `sums` in ctx for exactly this reason)."""
 
     def __init__(self, n, offset=0, high=()):
         """offset: use side streams [offset, offset + n) — a fork nested inside another fork's main section must not

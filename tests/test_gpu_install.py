@@ -176,4 +176,7 @@ def test_assigning_a_new_bank_between_graph_steps_is_picked_up():
         loss.backward()
         out.append(float(loss))
         model.zero_grad()
-    assert out[0] == out[2] and abs(out[0] - out[1]) > 1e-6, out
+    # same bank -> same loss up to the step's float atomics (the weight MLP's second layer accumulates its dot products
+    # with red.add: two replays may differ in the last bits; seen once in ~10 full-suite runs), another bank -> another loss
+    same, other = abs(out[0] - out[2]), abs(out[0] - out[1])
+    assert same <= 4e-6 * abs(out[0]) and other > 100 * same + 1e-6, out
