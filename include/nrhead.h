@@ -119,6 +119,13 @@ int nr_mlp_fwd(const void* x_bf16, int64_t T, int64_t D, const void* w1_bf16, in
                const float* w2, void* h_bf16, float* logits, void* stream);
 int nr_token_softmax(const float* logits, const float* b2, const int64_t* mask_a, const int64_t* mask_b, int64_t Ra,
                      int64_t R, int64_t N, float* w, void* stream);
+/* the softmaxes of both modalities (different token counts) in one launch */
+typedef struct {
+  const float* logits; const float* b2; const int64_t* mask_a; const int64_t* mask_b;
+  int64_t Ra, R, N;
+  float* w;
+} nr_softmax_side;
+int nr_token_softmax_pair(const nr_softmax_side* sides, int n_sides, void* stream);
 int nr_mlp_bwd_dx(const void* dh_bf16, int64_t T, int64_t H, const void* w1_bf16, int64_t D, float* dx, int accumulate,
                   void* stream);
 int nr_mlp_bwd_dw1(const void* dh_bf16, int64_t T, int64_t H, const void* x_bf16, int64_t D, float* dw1, void* stream);

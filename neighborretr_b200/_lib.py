@@ -35,6 +35,7 @@ SIGNATURES = {
     "nr_cast_bf16_multi": (_I, [_P, _P, _P, _I, _P]),
     "nr_mlp_fwd": (_I, [_P, _I64, _I64, _P, _I64, _P, _P, _P, _P, _P]),
     "nr_token_softmax": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
+    "nr_token_softmax_pair": (_I, [_P, _I, _P]),
     "nr_mlp_bwd_dx": (_I, [_P, _I64, _I64, _P, _I64, _P, _I, _P]),
     "nr_mlp_bwd_dw1": (_I, [_P, _I64, _I64, _P, _I64, _P, _P]),
     "nr_mlp_fwd_pair": (_I, [_P, _I, _I64, _I64, _I, _P]),
@@ -89,6 +90,11 @@ class MaxSim2RankProblem(ctypes.Structure):
     """nr_maxsim2_rank_problem of include/nrhead.h (field order and types must match)."""
     _fields_ = [("x_bf16", _P), ("y_bf16", _P), ("wx", _P), ("wy", _P), ("Rx", _I64), ("Ry", _I64), ("alpha", _F),
                 ("gx0", _I64), ("gy0", _I64), ("diag", _P), ("gt_x", _P), ("eq_x", _P), ("gt_y", _P), ("eq_y", _P)]
+
+
+class SoftmaxSide(ctypes.Structure):
+    """nr_softmax_side of include/nrhead.h (field order and types must match)."""
+    _fields_ = [("logits", _P), ("b2", _P), ("mask_a", _P), ("mask_b", _P), ("Ra", _I64), ("R", _I64), ("N", _I64), ("w", _P)]
 
 
 class MaxSim2BwdWJob(ctypes.Structure):

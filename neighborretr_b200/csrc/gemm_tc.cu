@@ -411,10 +411,9 @@ __global__ void __launch_bounds__(256) cast_bf16_multi_kernel(const CastSegs c) 
 
 // masked softmax over the tokens of each sample from the second-layer logits (reference modeling.py:486-487,
 // 491-492): one warp per sample, N <= 128 tokens
-__global__ void __launch_bounds__(256) token_softmax_kernel(const float* __restrict__ logits, const float* __restrict__ b2,
-                                                            const int64_t* __restrict__ mask_a, const int64_t* __restrict__ mask_b,
-                                                            int Ra, int R, int N, float* __restrict__ w) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+__device__ __forceinline__ void token_softmax_row(const float* __restrict__ logits, const float* __restrict__ b2,
+                                                  const int64_t* __restrict__ mask_a, const int64_t* __restrict__ mask_b,
+                                                  int Ra, int R, int N, float* __restrict__ w, int row, int lane) {
   if (row >= R) return;
   const int64_t* mk = row < Ra ? (mask_a ? mask_a + (int64_t)row * N : nullptr)
                                : (mask_b ? mask_b + (int64_t)(row - Ra) * N : nullptr);
@@ -445,6 +444,22 @@ __global__ void __launch_bounds__(256) token_softmax_kernel(const float* __restr
     const int t = lane + 32 * i;
     if (t < N) w[(int64_t)row * N + t] = v[i] / s;
   }
+}
+
+__global__ void __launch_bounds__(256) token_softmax_kernel(const float* __restrict__ logits, const float* __restrict__ b2,
+                                                            const int64_t* __restrict__ mask_a, const int64_t* __restrict__ mask_b,
+                                                            int Ra, int R, int N, float* __restrict__ w) {
+  token_softmax_row(logits, b2, mask_a, mask_b, Ra, R, N, w, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
+// both modalities of a step in one launch (their token counts differ): blocks [0, blk1) serve side 0, the rest side 1
+struct SoftmaxSide { const float* logits; const float* b2; const int64_t* mask_a; const int64_t* mask_b; int Ra, R, N; float* w; };
+struct SoftmaxPairArgs { SoftmaxSide s[2]; int blk1; };
+__global__ void __launch_bounds__(256) token_softmax_pair_kernel(const SoftmaxPairArgs a) {
+  const int si = (int)blockIdx.x >= a.blk1 ? 1 : 0;
+  const SoftmaxSide& S = a.s[si];
+  const int blk = (int)blockIdx.x - (si ? a.blk1 : 0);
+  token_softmax_row(S.logits, S.b2, S.mask_a, S.mask_b, S.Ra, S.R, S.N, S.w, blk * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 }  // namespace nr
@@ -544,6 +559,24 @@ extern "C" int nr_mlp_bwd_pair(const nr_mlp_side* s, int n, int64_t D, int64_t H
     if (s[i].dx) j[nj++] = job_dx(s[i].dh_bf16, s[i].T_dx, H, s[i].w1_bf16, D, s[i].dx, 1);
   if (nj == 0) return 0;
   return gemm_launch(j, nj, (cudaStream_t)stream);
+}
+
+extern "C" int nr_token_softmax_pair(const nr_softmax_side* sides, int n_sides, void* stream) {
+  NR_CHECK_ARG(sides && (n_sides == 1 || n_sides == 2), "nr_token_softmax_pair: 1 or 2 sides");
+  SoftmaxPairArgs a{};
+  int blocks = 0;
+  for (int i = 0; i < n_sides; ++i) {
+    const nr_softmax_side& q = sides[i];
+    NR_CHECK_ARG(q.logits && q.b2 && q.w && q.R > 0 && q.N > 0 && q.N <= 128 && q.Ra >= 0 && q.Ra <= q.R,
+                 "nr_token_softmax_pair: side %d: bad arguments", i);
+    a.s[i] = SoftmaxSide{q.logits, q.b2, q.mask_a, q.mask_b, (int)q.Ra, (int)q.R, (int)q.N, q.w};
+    if (i == 1) a.blk1 = blocks;
+    blocks += (int)((q.R + 7) / 8);
+  }
+  if (n_sides == 1) a.blk1 = blocks;
+  token_softmax_pair_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  NR_CHECK_LAUNCH("nr_token_softmax_pair");
+  return 0;
 }
 
 extern "C" int nr_token_softmax(const float* logits, const float* b2, const int64_t* mask_a, const int64_t* mask_b,

@@ -413,12 +413,13 @@ __global__ void __launch_bounds__(t2_threads(HS), 1) maxsim2_fwd_tc_kernel(const
 #pragma unroll
           for (int y = 0; y < NY; ++y) f[y] = __uint_as_float(v[s2 * NY + y]);
           const float best = TreeRed<NY>::fmax_(f);
-          const int bi = TreeRed<NY>::first_eq(f, best, 0);
           if (sy < sy_n) {
             hp_row[sy] = wxv * best;
             const int o = sy * Nx;
             if (pmx) pmx[o] = best;
-            if (yst) yst[o] = (uint8_t)bi;
+            // the arg-max (a third of the row direction's instructions) only where backward will read it: evaluation
+            // and the rank passes save nothing
+            if (yst) yst[o] = (uint8_t)TreeRed<NY>::first_eq(f, best, 0);
           }
         }
         // column direction: group partial of (value, row) keys, one column per lane

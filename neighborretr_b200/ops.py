@@ -787,9 +787,14 @@ class TokenWeightsPairFunction(torch.autograd.Function):
         st = _stream()
         # one SM stays free for the single-CTA Sinkhorn kernel that runs next to this GEMM in the head's forward
         _call("nr_mlp_fwd_pair", ctypes.cast(arr, ctypes.c_void_p), 2, D, H, 1, st)
-        for sd in sides:
-            _call("nr_token_softmax", _p(sd["logits"]), _p(sd["b2"]), _p(sd["ma"]), _p(sd["mb"]), sd["Ra"], sd["Ra"] + sd["Rb"],
-                  sd["N"], _p(sd["w"]), st)
+        sm = (_lib.SoftmaxSide * 2)()
+        for i, sd in enumerate(sides):
+            q = sm[i]
+            q.logits, q.b2, q.w = sd["logits"].data_ptr(), sd["b2"].data_ptr(), sd["w"].data_ptr()
+            q.mask_a = sd["ma"].data_ptr() if sd["ma"] is not None else None
+            q.mask_b = sd["mb"].data_ptr() if sd["mb"] is not None else None
+            q.Ra, q.R, q.N = sd["Ra"], sd["Ra"] + sd["Rb"], sd["N"]
+        _call("nr_token_softmax_pair", ctypes.cast(sm, ctypes.c_void_p), 2, st)
         ctx.dims = [(sd["Ra"], sd["Rb"], sd["N"], sd["xshape"]) for sd in sides] + [(D, H)]
         # the split-K accumulators of the backward GEMM (dW1, dx of both modalities), zeroed next to the forward
         need = ctx.needs_input_grad

@@ -114,7 +114,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         pytest.skip("gcc not available")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     structs = {"nr_maxsim2_problem": _lib.MaxSim2Problem, "nr_maxsim2_bwd_job": _lib.MaxSim2BwdJob,
-               "nr_maxsim2_rank_problem": _lib.MaxSim2RankProblem, "nr_maxsim2_bwd_w_job": _lib.MaxSim2BwdWJob}
+               "nr_maxsim2_rank_problem": _lib.MaxSim2RankProblem, "nr_maxsim2_bwd_w_job": _lib.MaxSim2BwdWJob,
+               "nr_softmax_side": _lib.SoftmaxSide, "nr_bank_side": _lib.BankSide, "nr_mlp_side": _lib.MlpSide}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrhead.h"', 'int main(void) {']
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
