@@ -35,6 +35,19 @@ def ranks_by_counting(sim: np.ndarray):
     return (sim > d).sum(axis=1).astype(np.int64), (sim == d).sum(axis=1).astype(np.int64)
 
 
+def shard_counts(sim: np.ndarray, lo: int, hi: int):
+    """What one gallery shard contributes to the ranks of a square test set (the host logic of
+    neighborretr_b200.evaluator.sharded_retrieval and of the fused rank pass nr_maxsim2_rank): from the column block
+    sim[:, lo:hi] and the positives' scores d = diag(sim),
+      per text q   : (#{j in shard: S[q,j] > d[q]}, #{j in shard: S[q,j] == d[q]})   -> summed over shards = ranks_by_counting(sim)
+      per video v in the shard: (#{q: S[q,v] > d[v]}, #{q: S[q,v] == d[v]})           -> complete = ranks_by_counting(sim.T)[lo:hi]
+    Returns (gt_t, eq_t, gt_v, eq_v) int64 arrays."""
+    d = np.diag(sim)
+    blk = sim[:, lo:hi]
+    return ((blk > d[:, None]).sum(axis=1).astype(np.int64), (blk == d[:, None]).sum(axis=1).astype(np.int64),
+            (blk > d[None, lo:hi]).sum(axis=0).astype(np.int64), (blk == d[None, lo:hi]).sum(axis=0).astype(np.int64))
+
+
 # ---- multi-sentence test sets (several captions per video; MSVD) ---------------------------------------------
 
 def multi_sentence_reshape(sim: np.ndarray, cut_off_points) -> np.ndarray:

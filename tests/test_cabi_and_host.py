@@ -62,6 +62,27 @@ def test_metrics_from_counts_matches_sort_form():
             assert a[k] == b[k]
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_counts_add_up_to_the_reference_ranks(world):
+    """Column-sharded evaluation (evaluator.sharded_retrieval, fused or not): per-shard (greater, equal) counts against
+    the all-reduced diagonal, summed over shards for text->video and concatenated for video->text, give exactly the
+    `cols` of compute_metrics on the full matrix and on its transpose (reference utils/metrics.py:58-66)."""
+    from neighborretr_b200.metrics import metrics_from_counts
+    rng = np.random.RandomState(world)
+    for mat in (rng.randn(37, 37).astype(np.float32), rng.randint(0, 3, (29, 29)).astype(np.float32)):
+        n = mat.shape[0]
+        per = (n + world - 1) // world
+        gt_t = np.zeros(n, np.int64); eq_t = np.zeros(n, np.int64)
+        gt_v = np.zeros(n, np.int64); eq_v = np.zeros(n, np.int64)
+        for r in range(world):
+            lo, hi = min(r * per, n), min((r + 1) * per, n)
+            a, b, c, d = OM.shard_counts(mat, lo, hi)
+            gt_t += a; eq_t += b
+            gt_v[lo:hi], eq_v[lo:hi] = c, d
+        assert metrics_from_counts(gt_t, eq_t)["cols"] == OM.compute_metrics(mat)["cols"]
+        assert metrics_from_counts(gt_v, eq_v)["cols"] == OM.compute_metrics(mat.T)["cols"]
+
+
 def test_synthetic_inputs_are_deterministic_and_ragged():
     a = synth.make_batch(16, 24, 12, d=64, seed=5, rank=1)
     b = synth.make_batch(16, 24, 12, d=64, seed=5, rank=1)

@@ -88,6 +88,9 @@ def test_fused_counts_of_a_gallery_shard(lo, hi):
     want = _materialised_counts(S, lo, hi)
     for g, w, name in zip(got, want, ("gt_t", "eq_t", "gt_v", "eq_v")):
         assert torch.equal(g, w), (name, (g != w).sum().item())
+    # and the oracle's numpy statement of a shard's contribution (oracle/metrics.py: shard_counts) on the same matrix
+    for g, w, name in zip(got, OM.shard_counts(S.cpu().numpy(), lo, hi), ("gt_t", "eq_t", "gt_v", "eq_v")):
+        assert np.array_equal(g.cpu().numpy().astype(np.int64), w), name
 
 
 def test_model_level_fused_metrics():
