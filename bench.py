@@ -510,8 +510,17 @@ def run_ours(args):
         for _ in range(3):
             step(pinned, True)
         ms_api = timed(lambda: step(pinned, True), args.steps)
+        # ... and as the reference's trainer sees it: the features come out of the encoders ON the device, the losses
+        # stay device tensors until the trainer logs them (training/trainer.py:84-125) — the cost of the API itself
+        for _ in range(2):
+            step(resident, False)
+        ms_api_res = timed(lambda: step(resident, False), args.steps)
         model.head_graph = False
         extra["module_api_graph_steps_per_s"] = args.steps / (ms_api * 1e-3)
+        extra["module_api_graph_resident_steps_per_s"] = args.steps / (ms_api_res * 1e-3)
+        extra["module_api_note"] = ("model.head_forward(...) + loss.backward() with head_graph=True: from pinned host "
+                                    "buffers with the losses read back (serial H2D of 10 MB in every step), and with "
+                                    "device-resident features as the reference trainer has them")
         # ---- the other arithmetic modes of the same step (graph replay, inputs resident)
         from neighborretr_b200 import selfcheck
         from neighborretr_b200.graph import FIELDS as _F, GraphedHeadStep as _G
