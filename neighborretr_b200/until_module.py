@@ -73,6 +73,9 @@ class UniformRegularizationLoss(nn.Module):
         return beta * q + (1 - beta) * torch.eye(b, device=g.device)
 
     def forward(self, similarity_matrix, logit_scale, beta=0.3, num_iterations=50):
+        # logit_scale is the reference's `temperature` hyper-parameter (a Python float at every call site,
+        # modeling.py:440-442); a tensor is accepted but costs a device synchronisation here — the fused head
+        # (fused.HeadFunction) takes it from the config and never syncs
         b = _square(similarity_matrix, "UniformRegularizationLoss")
         g = similarity_matrix
         u, v, _, _ = ops.sinkhorn_duals(g, g.detach().t().contiguous(), num_iterations)
