@@ -276,8 +276,9 @@ def run_eval_workload(args):
         tm[c0:c0 + chunk] = hb.text_mask.to(dev); vm[c0:c0 + chunk] = hb.video_mask.to(dev)
 
     fused = args.eval_ranks == "fused"
-    cfg_line["ranks"] = ("counted in the contraction's epilogue, S never written (no top-k lists)" if fused else
-                         "per-rank block of S written, rank-count + top-10 kernels over it")
+    # how the ranks are produced is a property of OUR arm, not of the workload both arms share: own top-level key
+    ranks_how = ("counted in the contraction's epilogue, S never written (no top-k lists)" if fused else
+                 "per-rank block of S written, rank-count + top-10 kernels over it")
 
     def once():
         return sharded_retrieval(model, tm, vm, tf, vf, topk=10, fused=fused)
@@ -312,7 +313,8 @@ def run_eval_workload(args):
             "metric": "eval_sim_rank_latency_ms", "value": ms, "unit": "ms", "n_gpus": world, "steps": steps,
             "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else args.precision, "data": "synthetic",
-            "config": cfg_line, "t2v_R1": r[0]["R1"], "v2t_R1": r[1]["R1"], "gpu_launches": launches, "clocks": clocks,
+            "config": cfg_line, "eval_ranks": ranks_how, "t2v_R1": r[0]["R1"], "v2t_R1": r[1]["R1"],
+            "gpu_launches": launches, "clocks": clocks,
             "roofline": {"kernel": "nr_maxsim2_fwd", "bound": "tensor", "achieved": ach, "peak": pk["bf16_sustained"],
                          "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
                          "note": "per-rank similarity flops 2*Q*(N/W)*Nt*Nv*D / the WHOLE evaluation call (MLPs, "
